@@ -1,0 +1,231 @@
+/* b2seg — C ABI of the B200-native UNet-family hot path.
+ *
+ * This is the drop-in boundary for the forward/backward/Adam path that the reference executes inside
+ * TensorFlow when `Model.fit` / `Model.predict` run the graphs built by
+ *   TensorFlow/2DCNN/models/unet_variants.py:977-1115 (class unet_model_builder) and
+ *   TensorFlow/1DCNN/Models/unet_variants.py:222-319 (class UNet), 1DCNN/Models/BCDUNet.py:79-174.
+ * The reference has no FFI of its own (it is pure Python on tf.keras); every entry point below replaces the
+ * tf.keras layer call(s) named in its comment.  Plain pointers and sizes only: all `uint64_t` "ptr" fields are
+ * CUDA device addresses owned by the caller; no torch / TF types cross this boundary.
+ *
+ * Conventions: every function returns 0 on success or a negative error code; `b2seg_last_error()` returns a
+ * thread-local message.  All launches are asynchronous on the `stream` argument (a CUstream / cudaStream_t cast
+ * to void*).  There is no CPU fallback: every entry point fails with B2SEG_ERR_DEVICE on a non-sm_100 device.
+ *
+ * Tensors are channels-last (NHWC; 1D tensors are NHWC with H == 1), bf16 unless stated, addressed through
+ * `b2seg_view` (a strided window into a wider NHWC buffer — this is how channel concatenation
+ * (2DCNN/models/unet_variants.py:27-32 Concat_Block) is realised without a copy).
+ */
+#ifndef B2SEG_H_
+#define B2SEG_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2SEG_OK 0
+#define B2SEG_ERR_ARG -1
+#define B2SEG_ERR_DEVICE -2
+#define B2SEG_ERR_CUDA -3
+
+#define B2SEG_MAX_SRC 4
+#define B2SEG_MAX_TAPS 16
+#define B2SEG_MAX_GROUPS 4
+#define B2SEG_MAX_GRADSRC 6
+
+/* activation codes (Keras Activation strings: 2DCNN/models/unet_variants.py:7-24,67-82) */
+enum { B2SEG_ACT_NONE = 0, B2SEG_ACT_RELU = 1, B2SEG_ACT_LEAKY = 2 /* slope 0.3 */, B2SEG_ACT_SIGMOID = 3, B2SEG_ACT_SOFTMAX = 4 };
+
+typedef struct b2seg_view {
+  uint64_t ptr;          /* address of element (n=0,h=0,w=0,c=0); 16-byte aligned */
+  int32_t N, H, W, C;    /* logical extents; channel stride is 1 element */
+  int64_t sn, sh, sw;    /* element strides; multiples of 8 for bf16 views */
+} b2seg_view;
+
+typedef struct b2seg_tap {
+  int32_t src;           /* index into src[] (conv) / pair index (wgrad) */
+  int32_t dh, dw;        /* spatial offset added to the output-grid coordinate when reading src */
+  int32_t widx;          /* index on the tap axis of the weight tensor */
+} b2seg_tap;
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores.  Replaces tf.keras.layers.Conv2D / Conv1D
+ * (unet_variants.py:9 / 1DCNN unet_variants.py:55), Conv2DTranspose / Conv1DTranspose forward
+ * (:19 / :104; one group per output parity class) and, with b_mn_major = 1, their input-gradient
+ * (Conv2DBackpropInput) kernels.
+ *   out[g](n,h,w, :) = act( bias + sum_{t in group g} sum_c src[tap.src](n, h+dh, w+dw, c) * Wt )
+ * Weights are bf16 [w_cout][w_taps][w_cin] (cin fastest).  b_mn_major = 0: GEMM-N = w_cout, K = w_cin per tap.
+ * b_mn_major = 1: GEMM-N = w_cin, K = w_cout per tap (the same buffer read transposed).
+ * Reads outside a source view return 0 (SAME padding).  stats (optional): fp32
+ * [n_groups * m_tiles][2][out.C] per-tile column sums and sums of squares of the stored bf16 values —
+ * the batch statistics of BatchNormalization (unet_variants.py:11). */
+typedef struct b2seg_conv_desc {
+  int32_t n_src;
+  b2seg_view src[B2SEG_MAX_SRC];
+  uint64_t weights;
+  int32_t w_cout, w_taps, w_cin;
+  int32_t b_mn_major;
+  int32_t n_groups, taps_per_group;
+  b2seg_tap taps[B2SEG_MAX_TAPS];
+  b2seg_view out[B2SEG_MAX_GROUPS]; /* per group; (N,H,W) is the GEMM-M grid, C the GEMM-N extent */
+  uint64_t bias;                    /* fp32 [out.C] or 0 */
+  int32_t act;
+  uint64_t stats;                   /* fp32 or 0 */
+  uint64_t mul_src;                 /* optional bf16 view-compatible tensor: see mul_mode */
+  b2seg_view mul_view;              /* dgrad fusion: out *= act'(mul_view) with mul_mode = B2SEG_ACT_*; 0 = off */
+  int32_t mul_mode;
+  int32_t block_n;                  /* 0 = auto; else 64 / 128 / 256 */
+} b2seg_conv_desc;
+
+/* Weight gradient (Conv2DBackpropFilter) on tcgen05: dW[co][widx][ci] (+)= sum_{n,h,w} dy[tap.src](n,h+dyh,w+dyw,co) * x[tap.src](n,h+dh,w+dw,ci)
+ * fp32 output laid out like the weights. */
+typedef struct b2seg_wgrad_tap {
+  int32_t pair;          /* index into dy[]/x[] */
+  int32_t dyh, dyw;      /* offset applied to dy coordinates */
+  int32_t dh, dw;        /* offset applied to x coordinates */
+  int32_t widx;
+} b2seg_wgrad_tap;
+
+typedef struct b2seg_wgrad_desc {
+  int32_t n_pair;
+  b2seg_view dy[B2SEG_MAX_SRC]; /* C = w_cout */
+  b2seg_view x[B2SEG_MAX_SRC];  /* C = w_cin  */
+  int32_t gN, gH, gW;           /* pixel iteration grid (GEMM-K) */
+  int32_t n_taps;
+  b2seg_wgrad_tap taps[B2SEG_MAX_TAPS];
+  uint64_t dw;                  /* fp32 [w_cout][w_taps][w_cin] */
+  int32_t w_cout, w_taps, w_cin;
+  int32_t ksplit;               /* 0 = auto */
+  int32_t accumulate;           /* 1: add into dw (must be pre-zeroed when ksplit > 1) */
+} b2seg_wgrad_desc;
+
+/* BatchNormalization, training mode (unet_variants.py:11; eps 1e-3, momentum 0.99). */
+typedef struct b2seg_bn_finalize_desc {
+  uint64_t partials;  /* fp32 [n_partials][2][C] from conv stats */
+  int32_t n_partials, C;
+  double count;       /* N*H*W */
+  uint64_t gamma, beta;            /* fp32 [C] */
+  uint64_t moving_mean, moving_var;/* fp32 [C], updated in place if update_moving */
+  int32_t update_moving, bessel;   /* bessel = 1 for 4-D inputs (fused Keras path), 0 for 3-D (1D models) */
+  float eps, momentum;
+  uint64_t scale, shift, mean, rstd; /* fp32 [C] outputs: y = x*scale + shift */
+  int32_t inference;               /* 1: use moving stats, ignore partials */
+} b2seg_bn_finalize_desc;
+
+/* y = act(x*scale + shift) written to up to 2 destinations, optional fused MaxPooling (p x p, stride p). */
+typedef struct b2seg_bn_act_desc {
+  b2seg_view x;
+  uint64_t scale, shift;  /* fp32 [C] or 0 (identity) */
+  int32_t act;
+  int32_t n_out;
+  b2seg_view out[2];
+  int32_t pool_h, pool_w; /* 0/1 = none */
+  b2seg_view pooled;
+} b2seg_bn_act_desc;
+
+typedef struct b2seg_gradsrc {
+  b2seg_view g;       /* gradient tensor view */
+  int32_t kind;       /* 0 direct (same grid), 1 max-pool routed (g is on the pooled grid) */
+  int32_t pool_h, pool_w;
+} b2seg_gradsrc;
+
+/* Backward of act(BN(x)): pass 0 reduces sum(dy*m) and sum(dy*m*xhat) into partials, pass 1 writes
+ *   dx = scale * (dy*m - dbeta/count - xhat*dgamma/count). With scale == 0 (no BN) dx = dy*m. */
+typedef struct b2seg_bn_bwd_desc {
+  b2seg_view x;                   /* stored pre-BN conv output */
+  uint64_t scale, shift, mean, rstd; /* fp32 [C] (0 => no BN) */
+  int32_t act;
+  int32_t n_src;
+  b2seg_gradsrc src[B2SEG_MAX_GRADSRC];
+  double count;
+  uint64_t partials;              /* fp32 [n_blocks][2][C] scratch */
+  int32_t n_blocks;               /* pixel slabs used by pass 0 */
+  uint64_t dgamma, dbeta;         /* fp32 [C] outputs of the finalize step */
+  b2seg_view dx;                  /* bf16 output */
+} b2seg_bn_bwd_desc;
+
+/* Fused Adam (utils/tf_optimizers.py:11; Keras-2 update rule): flat fp32 master weights, fp32 grads,
+ * bf16 shadow copy written in the same pass.  grad_scale multiplies the gradient (1/world_size). */
+typedef struct b2seg_adam_desc {
+  uint64_t w, g, m, v, w_bf16;
+  int64_t n;
+  float lr, beta1, beta2, eps, grad_scale;
+  int64_t step; /* t >= 1 */
+} b2seg_adam_desc;
+
+/* Pointwise head: out = act(x . W + b), Cout <= 8 (the `out` / `level{k}` Conv 1x1 layers,
+ * unet_variants.py:1106,137). fp32 logits/probabilities; backward produces dx (bf16), dW, db. */
+typedef struct b2seg_head_desc {
+  b2seg_view x;          /* bf16 activations */
+  uint64_t w, b;         /* fp32 [Cin][Cout], [Cout] (Keras kernel layout for 1x1) */
+  int32_t cout, act, stride; /* stride 1 or 2 (UNet3+ DS heads) */
+  uint64_t y;            /* fp32 [N,H',W',cout] activated output */
+  uint64_t dlogits;      /* fp32 [N,H',W',cout] (backward input) */
+  b2seg_view dx;         /* bf16 (backward output) */
+  uint64_t dw, db;       /* fp32 outputs */
+  uint64_t logits;      /* optional fp32 [N,H',W',cout] pre-activation output of the forward */
+} b2seg_head_desc;
+
+/* Loss seed. kind: 0 = binary cross-entropy on sigmoid probs (Keras evaluates from logits: d = (p-y)/count),
+ * 1 = categorical CE on softmax (d = (p-y)/pixels), 2 = MSE, 3 = MAE. */
+typedef struct b2seg_loss_desc {
+  uint64_t y_pred;   /* fp32 activated outputs */
+  uint64_t y_true;   /* fp32 targets */
+  int64_t n_pix; int32_t cout; int32_t kind; int32_t act;
+  float weight;      /* loss_weights entry */
+  uint64_t dlogits;  /* fp32 out */
+  uint64_t loss;     /* fp32[1] accumulates weight*loss */
+} b2seg_loss_desc;
+
+typedef struct b2seg_eltwise_desc {
+  int32_t op;  /* 0: out = a + b ; 1: out = a (copy) ; 2: out = a * leaky'(y=b) ; 3: out = a + b + c */
+  b2seg_view a, b, c, out;
+} b2seg_eltwise_desc;
+
+typedef struct b2seg_cast_desc { /* fp32 NHWC input -> bf16 view (channel-padded) */
+  uint64_t src; int32_t N, H, W, C;
+  b2seg_view out;
+} b2seg_cast_desc;
+
+typedef struct b2seg_colsum_desc { /* bias gradient: db[c] = sum over pixels of g (bf16 view) */
+  b2seg_view g; uint64_t out; uint64_t scratch; int32_t n_blocks;
+} b2seg_colsum_desc;
+
+const char* b2seg_last_error(void);
+int b2seg_version(void);
+int b2seg_device_check(int device);
+
+int b2seg_conv(const b2seg_conv_desc* d, void* stream);
+int b2seg_conv_num_mtiles(const b2seg_conv_desc* d);  /* tiles per group: size stats as n_groups*this*2*C floats */
+int b2seg_wgrad(const b2seg_wgrad_desc* d, void* stream);
+int b2seg_bn_finalize(const b2seg_bn_finalize_desc* d, void* stream);
+int b2seg_bn_act(const b2seg_bn_act_desc* d, void* stream);
+int b2seg_bn_bwd(const b2seg_bn_bwd_desc* d, void* stream);
+int b2seg_adam(const b2seg_adam_desc* d, void* stream);
+int b2seg_head_fwd(const b2seg_head_desc* d, void* stream);
+int b2seg_head_bwd(const b2seg_head_desc* d, void* stream);
+int b2seg_loss(const b2seg_loss_desc* d, void* stream);
+int b2seg_eltwise(const b2seg_eltwise_desc* d, void* stream);
+int b2seg_cast_input(const b2seg_cast_desc* d, void* stream);
+int b2seg_colsum(const b2seg_colsum_desc* d, void* stream);
+
+/* ---- plan: a recorded sequence of the ops above, replayed per step (optionally as a CUDA graph) ---- */
+typedef struct b2seg_plan b2seg_plan;
+enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
+       B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,
+       B2SEG_OP_MEMSET };
+typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
+
+int b2seg_plan_create(b2seg_plan** out);
+/* phase: 0 forward, 1 backward, 2 optimizer. desc is copied. */
+int b2seg_plan_add(b2seg_plan* p, int phase, int op, const void* desc, size_t desc_bytes);
+int b2seg_plan_run(b2seg_plan* p, int phase, void* stream);
+int b2seg_plan_num_launches(const b2seg_plan* p, int phase);
+int b2seg_plan_set_adam(b2seg_plan* p, float lr, int64_t step, float grad_scale);
+void b2seg_plan_destroy(b2seg_plan* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SEG_H_ */

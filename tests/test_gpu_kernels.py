@@ -1,0 +1,333 @@
+"""GPU parity of each C-ABI kernel (include/b2seg.h) against a plain PyTorch fp32 evaluation of the same op.
+
+Tolerances: inputs are bf16-rounded before both paths, accumulation is fp32 on both, outputs are rounded to
+bf16 by the kernel => rel-L2 <= 4e-3 (one bf16 rounding, 2^-9 relative, plus accumulation-order noise);
+fp32 outputs (wgrad, statistics, Adam) <= 1e-4.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from b2seg import _lib as L  # noqa: E402
+from b2seg import lowering as lw  # noqa: E402
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def tv(t, c_off=0, Cn=None):
+    N, H, W, Ct = t.shape
+    esz = t.element_size()
+    return lw.TView(t.data_ptr() + c_off * esz, N, H, W, Ct - c_off if Cn is None else Cn, t.stride(0), t.stride(1), t.stride(2), esz)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dev():
+    L.check(L.load().b2seg_device_check(0), "device_check")
+    torch.manual_seed(0)
+    yield
+    torch.cuda.synchronize()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, kh, kw, act, stats
+    (2, 16, 16, 64, 64, 3, 3, L.ACT_NONE, False),
+    (2, 16, 16, 64, 128, 3, 3, L.ACT_RELU, True),
+    (4, 8, 8, 128, 256, 3, 3, L.ACT_NONE, True),
+    (2, 8, 8, 320, 512, 3, 3, L.ACT_LEAKY, False),
+    (1, 32, 32, 8, 64, 3, 3, L.ACT_NONE, True),      # Cin = 3 padded to 8 (K tail zero-filled by TMA)
+    (3, 12, 20, 24, 40, 3, 3, L.ACT_NONE, True),     # ragged: tiles overhang the image, odd channel counts
+    (2, 1, 256, 64, 64, 1, 3, L.ACT_NONE, True),     # 1D, kernel 3
+    (5, 1, 32, 64, 128, 1, 5, L.ACT_NONE, False),    # 1D, kernel 5, short rows span several samples
+    (2, 16, 16, 64, 64, 1, 1, L.ACT_SIGMOID, False),
+    (8, 4, 4, 256, 256, 3, 3, L.ACT_NONE, True),
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,kh,kw,act,stats", CONV_CASES)
+def test_conv_fprop(N, H, W, Cin, Cout, kh, kw, act, stats):
+    dev = "cuda"
+    x = bf(torch.randn(N, H, W, Cin, device=dev))
+    w = bf(torch.randn(Cout, kh * kw, Cin, device=dev) * (1.0 / (kh * kw * Cin) ** 0.5))
+    bias = torch.randn(Cout, device=dev)
+    out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
+    d = lw.conv_fprop(tv(x), w.data_ptr(), Cout, kh, kw, Cin, tv(out), bias=bias.data_ptr(), act=act)
+    mt = L.load().b2seg_conv_num_mtiles(C.byref(d))
+    st = torch.zeros(mt, 2, Cout, device=dev) if stats else None
+    if stats:
+        d.stats = st.data_ptr()
+    L.call("b2seg_conv", d, stream())
+    torch.cuda.synchronize()
+    wt = w.float().view(Cout, kh, kw, Cin).permute(0, 3, 1, 2)
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (pw, kw - 1 - pw, ph, kh - 1 - ph))
+    ref = F.conv2d(xp, wt, bias)
+    if act == L.ACT_RELU:
+        ref = F.relu(ref)
+    elif act == L.ACT_LEAKY:
+        ref = F.leaky_relu(ref, 0.3)
+    elif act == L.ACT_SIGMOID:
+        ref = torch.sigmoid(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), ref) < 4e-3
+    if stats:
+        s = st.sum(0)
+        o = out.float().view(-1, Cout)
+        assert torch.allclose(s[0], o.sum(0), rtol=1e-3, atol=1e-2)
+        assert torch.allclose(s[1], (o * o).sum(0), rtol=1e-3, atol=1e-2)
+
+
+def test_conv_concat_slot_and_offsets():
+    """input read from, and output written to, channel windows of wider buffers (concat without copies)"""
+    dev = "cuda"
+    N, H, W = 2, 16, 16
+    xbuf = bf(torch.randn(N, H, W, 192, device=dev))
+    obuf = torch.full((N, H, W, 256), 7.0, device=dev, dtype=torch.bfloat16)
+    w = bf(torch.randn(64, 9, 128, device=dev) * 0.03)
+    d = lw.conv_fprop(tv(xbuf, 64, 128), w.data_ptr(), 64, 3, 3, 128, tv(obuf, 128, 64))
+    L.call("b2seg_conv", d, stream())
+    torch.cuda.synchronize()
+    ref = F.conv2d(xbuf[..., 64:192].float().permute(0, 3, 1, 2), w.float().view(64, 3, 3, 128).permute(0, 3, 1, 2), padding=1)
+    assert rel_l2(obuf[..., 128:192].float(), ref.permute(0, 2, 3, 1)) < 4e-3
+    assert float((obuf[..., :128].float() - 7).abs().max()) == 0 and float((obuf[..., 192:].float() - 7).abs().max()) == 0
+
+
+DGRAD_CASES = [(2, 16, 16, 64, 64, 3, 3), (2, 8, 8, 256, 128, 3, 3), (4, 8, 8, 128, 320, 3, 3), (3, 12, 20, 24, 40, 3, 3),
+               (2, 1, 128, 64, 128, 1, 3), (2, 16, 16, 64, 64, 1, 1)]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,kh,kw", DGRAD_CASES)
+def test_conv_dgrad(N, H, W, Cin, Cout, kh, kw):
+    dev = "cuda"
+    dy = bf(torch.randn(N, H, W, Cout, device=dev))
+    w = bf(torch.randn(Cout, kh * kw, Cin, device=dev) * 0.05)
+    dx = torch.zeros(N, H, W, Cin, device=dev, dtype=torch.bfloat16)
+    L.call("b2seg_conv", lw.conv_dgrad(tv(dy), w.data_ptr(), Cout, kh, kw, Cin, tv(dx)), stream())
+    torch.cuda.synchronize()
+    x = torch.zeros(N, Cin, H, W, device=dev, requires_grad=True)
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    y = F.conv2d(F.pad(x, (pw, kw - 1 - pw, ph, kh - 1 - ph)), w.float().view(Cout, kh, kw, Cin).permute(0, 3, 1, 2))
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(dx.float(), x.grad.permute(0, 2, 3, 1)) < 4e-3
+
+
+def test_conv_dgrad_mask_fusion():
+    dev = "cuda"
+    N, H, W, Cin, Cout = 2, 16, 16, 128, 64
+    dy = bf(torch.randn(N, H, W, Cout, device=dev))
+    w = bf(torch.randn(Cout, 9, Cin, device=dev) * 0.05)
+    yfwd = bf(torch.randn(N, H, W, Cin, device=dev))
+    dx = torch.zeros(N, H, W, Cin, device=dev, dtype=torch.bfloat16)
+    d = lw.conv_dgrad(tv(dy), w.data_ptr(), Cout, 3, 3, Cin, tv(dx), mul_view=tv(yfwd, 0, 64), mul_mode=L.ACT_LEAKY)
+    L.call("b2seg_conv", d, stream())
+    torch.cuda.synchronize()
+    x = torch.zeros(N, Cin, H, W, device=dev, requires_grad=True)
+    F.conv2d(x, w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2), padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    ref = x.grad.permute(0, 2, 3, 1).clone()
+    ref[..., :64] *= torch.where(yfwd[..., :64].float() > 0, 1.0, 0.3)
+    assert rel_l2(dx.float(), ref) < 6e-3
+
+
+WGRAD_CASES = [(2, 16, 16, 64, 64, 3, 3, 0), (2, 16, 16, 64, 64, 3, 3, 1), (4, 8, 8, 128, 256, 3, 3, 0), (2, 8, 8, 320, 136, 3, 3, 0),
+               (3, 12, 20, 24, 40, 3, 3, 0), (2, 1, 256, 64, 64, 1, 3, 0), (1, 32, 32, 8, 64, 3, 3, 0), (2, 16, 16, 64, 64, 1, 1, 0)]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,kh,kw,ksplit", WGRAD_CASES)
+def test_conv_wgrad(N, H, W, Cin, Cout, kh, kw, ksplit):
+    dev = "cuda"
+    dy = bf(torch.randn(N, H, W, Cout, device=dev))
+    xin = bf(torch.randn(N, H, W, Cin, device=dev))
+    dw = torch.zeros(Cout, kh * kw, Cin, device=dev)
+    L.call("b2seg_wgrad", lw.conv_wgrad(tv(dy), tv(xin), dw.data_ptr(), Cout, kh, kw, Cin, ksplit=ksplit), stream())
+    torch.cuda.synchronize()
+    w = torch.zeros(Cout, Cin, kh, kw, device=dev, requires_grad=True)
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    y = F.conv2d(F.pad(xin.float().permute(0, 3, 1, 2), (pw, kw - 1 - pw, ph, kh - 1 - ph)), w)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(dw.view(Cout, kh, kw, Cin), w.grad.permute(0, 2, 3, 1)) < 1e-4
+
+
+TCONV_CASES = [(2, 8, 8, 128, 64, 4, 4), (2, 4, 4, 256, 128, 4, 4), (2, 1, 64, 128, 64, 1, 2), (1, 6, 10, 24, 16, 4, 4)]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,kh,kw", TCONV_CASES)
+def test_tconv_all(N, H, W, Cin, Cout, kh, kw):
+    dev = "cuda"
+    sh = 2 if kh > 1 else 1
+    pad = (1 if kh == 4 else 0, 1 if kw == 4 else 0)
+    x = bf(torch.randn(N, H, W, Cin, device=dev))
+    w = bf(torch.randn(Cout, kh * kw, Cin, device=dev) * 0.05)  # internal layout
+    bias = torch.randn(Cout, device=dev)
+    out = torch.zeros(N, H * sh, W * 2, Cout, device=dev, dtype=torch.bfloat16)
+    L.call("b2seg_conv", lw.tconv_fprop(tv(x), w.data_ptr(), Cout, kh, kw, Cin, tv(out), bias=bias.data_ptr(), act=L.ACT_LEAKY), stream())
+    torch.cuda.synchronize()
+    wt = w.float().view(Cout, kh, kw, Cin).permute(3, 0, 1, 2).contiguous().requires_grad_(True)  # torch (Cin,Cout,kh,kw)
+    xt = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    pre = F.conv_transpose2d(xt, wt, bias, stride=(sh, 2), padding=pad)
+    ref = F.leaky_relu(pre, 0.3)
+    assert rel_l2(out.float(), ref.permute(0, 2, 3, 1)) < 4e-3
+    dy = bf(torch.randn(N, H * sh, W * 2, Cout, device=dev))
+    pre.backward(dy.float().permute(0, 3, 1, 2))
+    dx = torch.zeros(N, H, W, Cin, device=dev, dtype=torch.bfloat16)
+    L.call("b2seg_conv", lw.tconv_dgrad(tv(dy), w.data_ptr(), Cout, kh, kw, Cin, tv(dx)), stream())
+    dw = torch.zeros(Cout, kh * kw, Cin, device=dev)
+    L.call("b2seg_wgrad", lw.tconv_wgrad(tv(dy), tv(x), dw.data_ptr(), Cout, kh, kw, Cin), stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dx.float(), xt.grad.permute(0, 2, 3, 1)) < 4e-3
+    assert rel_l2(dw.view(Cout, kh, kw, Cin), wt.grad.permute(1, 2, 3, 0)) < 1e-4
+
+
+def test_bn_finalize_act_pool_and_backward():
+    dev = "cuda"
+    N, H, W, Cc = 4, 16, 16, 64
+    z = bf(torch.randn(N, H, W, Cc, device=dev) * 2 + 0.5)
+    gamma = torch.rand(Cc, device=dev) + 0.5
+    beta = torch.randn(Cc, device=dev) * 0.1
+    zf = z.float().view(-1, Cc)
+    part = torch.stack([zf.sum(0), (zf * zf).sum(0)]).view(1, 2, Cc).contiguous()
+    mm, mv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    scale, shift, mean, rstd = (torch.zeros(Cc, device=dev) for _ in range(4))
+    fd = L.BnFinalizeDesc(part.data_ptr(), 1, Cc, float(N * H * W), gamma.data_ptr(), beta.data_ptr(), mm.data_ptr(), mv.data_ptr(),
+                          1, 1, 1e-3, 0.99, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), 0)
+    L.call("b2seg_bn_finalize", fd, stream())
+    a = torch.zeros_like(z)
+    cat = torch.zeros(N, H, W, 2 * Cc, device=dev, dtype=torch.bfloat16)
+    pooled = torch.zeros(N, H // 2, W // 2, Cc, device=dev, dtype=torch.bfloat16)
+    ad = L.BnActDesc()
+    ad.x, ad.scale, ad.shift, ad.act, ad.n_out = tv(z).to_c(), scale.data_ptr(), shift.data_ptr(), L.ACT_RELU, 2
+    ad.out[0], ad.out[1] = tv(a).to_c(), tv(cat, Cc, Cc).to_c()
+    ad.pool_h, ad.pool_w, ad.pooled = 2, 2, tv(pooled).to_c()
+    L.call("b2seg_bn_act", ad, stream())
+    torch.cuda.synchronize()
+    zt = z.float().requires_grad_(True)
+    mu, var = zt.view(-1, Cc).mean(0), zt.view(-1, Cc).var(0, unbiased=False)
+    y = F.relu((zt - mu) / torch.sqrt(var + 1e-3) * gamma + beta)
+    assert torch.allclose(mean, mu.detach(), atol=1e-4) and torch.allclose(mm, 0.01 * mu.detach(), atol=1e-5)
+    cnt = N * H * W
+    assert torch.allclose(mv, 0.99 + 0.01 * var.detach() * cnt / (cnt - 1), atol=1e-4)
+    assert rel_l2(a.float(), y.detach()) < 4e-3
+    assert torch.equal(a, cat[..., Cc:])
+    yp = F.max_pool2d(y.permute(0, 3, 1, 2), 2)
+    assert rel_l2(pooled.float(), yp.detach().permute(0, 2, 3, 1)) < 4e-3
+    # backward with a direct and a pool-routed gradient source
+    g1 = bf(torch.randn(N, H, W, Cc, device=dev))
+    g2 = bf(torch.randn(N, H // 2, W // 2, Cc, device=dev))
+    (y * g1.float()).sum().backward(retain_graph=True)
+    (yp * g2.float().permute(0, 3, 1, 2)).sum().backward()
+    nb = 32
+    partials = torch.zeros(nb, 2, Cc, device=dev)
+    dgamma, dbeta = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev)
+    dz = torch.zeros_like(z)
+    bd = L.BnBwdDesc()
+    bd.x, bd.scale, bd.shift, bd.mean, bd.rstd = tv(z).to_c(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    bd.act, bd.n_src = L.ACT_RELU, 2
+    bd.src[0] = L.GradSrc(tv(g1).to_c(), 0, 1, 1)
+    bd.src[1] = L.GradSrc(tv(g2).to_c(), 1, 2, 2)
+    bd.count, bd.partials, bd.n_blocks = float(cnt), partials.data_ptr(), nb
+    bd.dgamma, bd.dbeta, bd.dx = dgamma.data_ptr(), dbeta.data_ptr(), tv(dz).to_c()
+    L.call("b2seg_bn_bwd", bd, stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dz.float(), zt.grad) < 8e-3
+    # dgamma/dbeta against autograd through gamma/beta
+    g_ = gamma.clone().requires_grad_(True)
+    b_ = beta.clone().requires_grad_(True)
+    zz = z.float()
+    y2 = F.relu((zz - mu.detach()) / torch.sqrt(var.detach() + 1e-3) * g_ + b_)
+    ((y2 * g1.float()).sum() + (F.max_pool2d(y2.permute(0, 3, 1, 2), 2) * g2.float().permute(0, 3, 1, 2)).sum()).backward()
+    assert rel_l2(dgamma, g_.grad) < 2e-3 and rel_l2(dbeta, b_.grad) < 2e-3
+
+
+def test_adam_keras_rule():
+    dev = "cuda"
+    n = 4096 + 8
+    w = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev) * 1e-3
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    wb = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    w0 = w.clone()
+    lr, b1, b2, eps = 2e-4, 0.9, 0.999, 1e-7
+    mr, vr, wr = torch.zeros_like(w), torch.zeros_like(w), w0.clone().double()
+    for t in (1, 2, 3):
+        L.call("b2seg_adam", L.AdamDesc(w.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), wb.data_ptr(), n, lr, b1, b2, eps, 1.0, t), stream())
+        mr = b1 * mr + (1 - b1) * g
+        vr = b2 * vr + (1 - b2) * g * g
+        alpha = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        wr = wr - alpha * mr.double() / (vr.double().sqrt() + eps)
+    torch.cuda.synchronize()
+    assert torch.allclose(w.double(), wr, atol=1e-6)
+    assert torch.equal(wb, w.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("cout,act,kind,Cin", [(1, L.ACT_SIGMOID, 0, 64), (4, L.ACT_SOFTMAX, 1, 64), (1, L.ACT_NONE, 2, 128), (2, L.ACT_NONE, 3, 64)])
+def test_head_and_loss(cout, act, kind, Cin):
+    dev = "cuda"
+    N, H, W = 2, 16, 16
+    x = bf(torch.randn(N, H, W, Cin, device=dev))
+    w = torch.randn(Cin, cout, device=dev) * 0.1
+    b = torch.randn(cout, device=dev) * 0.1
+    y = torch.zeros(N, H, W, cout, device=dev)
+    if kind == 1:
+        tgt = F.one_hot(torch.randint(0, cout, (N, H, W), device=dev), cout).float()
+    elif kind == 0:
+        tgt = (torch.rand(N, H, W, cout, device=dev) > 0.7).float()
+    else:
+        tgt = torch.randn(N, H, W, cout, device=dev)
+    dl = torch.zeros_like(y)
+    loss = torch.zeros(1, device=dev)
+    dx = torch.zeros_like(x)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    hd = L.HeadDesc()
+    hd.x, hd.w, hd.b, hd.cout, hd.act, hd.stride = tv(x).to_c(), w.data_ptr(), b.data_ptr(), cout, act, 1
+    hd.y, hd.dlogits, hd.dx, hd.dw, hd.db = y.data_ptr(), dl.data_ptr(), tv(dx).to_c(), dw.data_ptr(), db.data_ptr()
+    L.call("b2seg_head_fwd", hd, stream())
+    L.call("b2seg_loss", L.LossDesc(y.data_ptr(), tgt.data_ptr(), N * H * W, cout, kind, act, 1.0, dl.data_ptr(), loss.data_ptr()), stream())
+    L.call("b2seg_head_bwd", hd, stream())
+    torch.cuda.synchronize()
+    xt = x.float().requires_grad_(True)
+    wt, bt = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = xt @ wt + bt
+    if kind == 0:
+        ref_y, ref_loss = torch.sigmoid(z), F.binary_cross_entropy_with_logits(z, tgt)
+    elif kind == 1:
+        ref_y, ref_loss = torch.softmax(z, -1), -(tgt * torch.log_softmax(z, -1)).sum(-1).mean()
+    elif kind == 2:
+        ref_y, ref_loss = z, ((z - tgt) ** 2).mean()
+    else:
+        ref_y, ref_loss = z, (z - tgt).abs().mean()
+    ref_loss.backward()
+    assert torch.allclose(y, ref_y.detach(), atol=2e-5, rtol=1e-4)
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss)))
+    assert rel_l2(dx.float(), xt.grad) < 4e-3
+    assert rel_l2(dw, wt.grad) < 1e-4 and rel_l2(db, bt.grad) < 1e-4
+
+
+def test_cast_eltwise_colsum():
+    dev = "cuda"
+    N, H, W = 2, 8, 8
+    src = torch.rand(N, H, W, 3, device=dev)
+    out = torch.full((N, H, W, 8), 5.0, device=dev, dtype=torch.bfloat16)
+    L.call("b2seg_cast_input", L.CastDesc(src.data_ptr(), N, H, W, 3, tv(out).to_c()), stream())
+    a, b = bf(torch.randn(N, H, W, 64, device=dev)), bf(torch.randn(N, H, W, 64, device=dev))
+    o = torch.zeros_like(a)
+    L.call("b2seg_eltwise", L.EltwiseDesc(0, tv(a).to_c(), tv(b).to_c(), lw.NULL_VIEW.to_c(), tv(o).to_c()), stream())
+    cs = torch.zeros(64, device=dev)
+    L.call("b2seg_colsum", L.ColsumDesc(tv(a).to_c(), cs.data_ptr(), 0, 0), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., :3], src.to(torch.bfloat16)) and float(out[..., 3:].float().abs().max()) == 0
+    assert torch.equal(o, (a.float() + b.float()).to(torch.bfloat16))
+    assert torch.allclose(cs, a.float().view(-1, 64).sum(0), atol=1e-3)

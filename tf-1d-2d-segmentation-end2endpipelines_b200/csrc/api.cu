@@ -1,0 +1,221 @@
+// C ABI (include/b2seg.h): error plumbing, tensor-map encoding, op-level entry points and the plan object.
+#include <stdarg.h>
+#include <string.h>
+
+#include <memory>
+#include <vector>
+
+#include "common.h"
+
+namespace b2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int require_sm100() {
+  static int checked = 0;  // 0 unknown, 1 ok, -1 bad
+  if (checked == 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      checked = -1;
+    } else {
+      checked = (major == 10) ? 1 : -1;
+    }
+  }
+  if (checked != 1) return fail(B2SEG_ERR_DEVICE, "b2seg requires an sm_100 (B200) CUDA device; there is no CPU fallback");
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_act_map(CUtensorMap* m, const b2seg_view& v, int box_c, int box_w, int box_h, int box_n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B2SEG_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  if ((v.ptr & 15) || (v.sw % 8) || (v.sh % 8) || (v.sn % 8) || v.C < 1)
+    return fail(B2SEG_ERR_ARG, "view not 16-byte aligned (ptr=%llx sw=%lld sh=%lld sn=%lld)", (unsigned long long)v.ptr, (long long)v.sw,
+                (long long)v.sh, (long long)v.sn);
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<void*>(v.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B2SEG_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d (dims %d,%d,%d,%d strides %lld,%lld,%lld box %d,%d,%d,%d)", (int)r,
+                v.C, v.W, v.H, v.N, (long long)v.sw, (long long)v.sh, (long long)v.sn, box_c, box_w, box_h, box_n);
+  return 0;
+}
+
+int encode_weight_map(CUtensorMap* m, uint64_t ptr, int cout, int taps, int cin, int box_cin, int box_cout) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(B2SEG_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  if ((ptr & 15) || (cin % 8)) return fail(B2SEG_ERR_ARG, "weights not 16-byte aligned / cin %% 8");
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
+  cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * taps * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cin, 1, (cuuint32_t)box_cout};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, reinterpret_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2SEG_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return 0;
+}
+
+static int run_once(PreparedOp* op, void* stream) {
+  if (!op) return g_err[0] ? B2SEG_ERR_ARG : fail(B2SEG_ERR_ARG, "prepare failed");
+  std::unique_ptr<PreparedOp> guard(op);
+  return op->launch(reinterpret_cast<cudaStream_t>(stream));
+}
+
+static PreparedOp* prepare_any(int op, const void* desc, size_t bytes) {
+#define B2_CASE(code, type, fn)                                                                      \
+  case code:                                                                                         \
+    if (bytes != sizeof(type)) { set_error("op %d: descriptor size %zu != %zu", op, bytes, sizeof(type)); return nullptr; } \
+    return fn(reinterpret_cast<const type*>(desc));
+  switch (op) {
+    B2_CASE(B2SEG_OP_CONV, b2seg_conv_desc, prepare_conv)
+    B2_CASE(B2SEG_OP_WGRAD, b2seg_wgrad_desc, prepare_wgrad)
+    B2_CASE(B2SEG_OP_BN_FINALIZE, b2seg_bn_finalize_desc, prepare_bn_finalize)
+    B2_CASE(B2SEG_OP_BN_ACT, b2seg_bn_act_desc, prepare_bn_act)
+    B2_CASE(B2SEG_OP_BN_BWD, b2seg_bn_bwd_desc, prepare_bn_bwd)
+    B2_CASE(B2SEG_OP_ADAM, b2seg_adam_desc, prepare_adam)
+    B2_CASE(B2SEG_OP_HEAD_FWD, b2seg_head_desc, prepare_head_fwd)
+    B2_CASE(B2SEG_OP_HEAD_BWD, b2seg_head_desc, prepare_head_bwd)
+    B2_CASE(B2SEG_OP_LOSS, b2seg_loss_desc, prepare_loss)
+    B2_CASE(B2SEG_OP_ELTWISE, b2seg_eltwise_desc, prepare_eltwise)
+    B2_CASE(B2SEG_OP_CAST, b2seg_cast_desc, prepare_cast)
+    B2_CASE(B2SEG_OP_COLSUM, b2seg_colsum_desc, prepare_colsum)
+    B2_CASE(B2SEG_OP_MEMSET, b2seg_memset_desc, prepare_memset)
+    default:
+      set_error("unknown op code %d", op);
+      return nullptr;
+  }
+#undef B2_CASE
+}
+
+}  // namespace b2
+
+struct b2seg_plan {
+  std::vector<std::unique_ptr<b2::PreparedOp>> phase[3];
+};
+
+extern "C" {
+
+const char* b2seg_last_error(void) { return b2::g_err; }
+int b2seg_version(void) { return 100; }
+
+int b2seg_device_check(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return b2::fail(B2SEG_ERR_DEVICE, "cudaSetDevice(%d) failed", device);
+  return b2::require_sm100();
+}
+
+#define B2_ENTRY(name, type, prep)                          \
+  int name(const type* d, void* stream) {                   \
+    b2::g_err[0] = 0;                                       \
+    if (!d) return b2::fail(B2SEG_ERR_ARG, #name ": null descriptor"); \
+    int rc = b2::require_sm100();                           \
+    if (rc) return rc;                                      \
+    return b2::run_once(prep(d), stream);                   \
+  }
+
+B2_ENTRY(b2seg_conv, b2seg_conv_desc, b2::prepare_conv)
+B2_ENTRY(b2seg_wgrad, b2seg_wgrad_desc, b2::prepare_wgrad)
+B2_ENTRY(b2seg_bn_finalize, b2seg_bn_finalize_desc, b2::prepare_bn_finalize)
+B2_ENTRY(b2seg_bn_act, b2seg_bn_act_desc, b2::prepare_bn_act)
+B2_ENTRY(b2seg_bn_bwd, b2seg_bn_bwd_desc, b2::prepare_bn_bwd)
+B2_ENTRY(b2seg_adam, b2seg_adam_desc, b2::prepare_adam)
+B2_ENTRY(b2seg_head_fwd, b2seg_head_desc, b2::prepare_head_fwd)
+B2_ENTRY(b2seg_head_bwd, b2seg_head_desc, b2::prepare_head_bwd)
+B2_ENTRY(b2seg_loss, b2seg_loss_desc, b2::prepare_loss)
+B2_ENTRY(b2seg_eltwise, b2seg_eltwise_desc, b2::prepare_eltwise)
+B2_ENTRY(b2seg_cast_input, b2seg_cast_desc, b2::prepare_cast)
+B2_ENTRY(b2seg_colsum, b2seg_colsum_desc, b2::prepare_colsum)
+
+int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
+  if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");
+  return b2::conv_num_mtiles(d);
+}
+
+int b2seg_plan_create(b2seg_plan** out) {
+  b2::g_err[0] = 0;
+  if (!out) return b2::fail(B2SEG_ERR_ARG, "null out");
+  int rc = b2::require_sm100();
+  if (rc) return rc;
+  *out = new b2seg_plan();
+  return 0;
+}
+
+int b2seg_plan_add(b2seg_plan* p, int phase, int op, const void* desc, size_t desc_bytes) {
+  b2::g_err[0] = 0;
+  if (!p || phase < 0 || phase > 2 || !desc) return b2::fail(B2SEG_ERR_ARG, "plan_add: bad arguments");
+  b2::PreparedOp* po = b2::prepare_any(op, desc, desc_bytes);
+  if (!po) return b2::g_err[0] ? B2SEG_ERR_ARG : b2::fail(B2SEG_ERR_ARG, "plan_add: prepare failed for op %d", op);
+  p->phase[phase].emplace_back(po);
+  return 0;
+}
+
+int b2seg_plan_run(b2seg_plan* p, int phase, void* stream) {
+  if (!p || phase < 0 || phase > 2) return b2::fail(B2SEG_ERR_ARG, "plan_run: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  for (auto& op : p->phase[phase]) {
+    int rc = op->launch(s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b2seg_plan_num_launches(const b2seg_plan* p, int phase) {
+  if (!p || phase < 0 || phase > 2) return -1;
+  int n = 0;
+  for (auto& op : p->phase[phase]) n += op->num_launches();
+  return n;
+}
+
+int b2seg_plan_set_adam(b2seg_plan* p, float lr, int64_t step, float grad_scale) {
+  if (!p) return b2::fail(B2SEG_ERR_ARG, "null plan");
+  for (int ph = 0; ph < 3; ++ph)
+    for (auto& op : p->phase[ph])
+      if (b2::is_adam(op.get())) b2::adam_update(op.get(), lr, step, grad_scale);
+  return 0;
+}
+
+void b2seg_plan_destroy(b2seg_plan* p) { delete p; }
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Host-side helpers shared by the b2seg translation units: error reporting, tensor-map encoding,
+// and the "prepared launch" objects a plan replays.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/b2seg.h"
+
+namespace b2 {
+
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define B2_CUDA_OK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) return b2::fail(B2SEG_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+int num_sms();
+int require_sm100();
+
+// 4-D activation map over a view: dims (C, W, H, N), bf16, SWIZZLE_128B, zero OOB fill.
+int encode_act_map(CUtensorMap* m, const b2seg_view& v, int box_c, int box_w, int box_h, int box_n);
+// 3-D weight map over bf16 [cout][taps][cin]: dims (cin, taps, cout).
+int encode_weight_map(CUtensorMap* m, uint64_t ptr, int cout, int taps, int cin, int box_cin, int box_cout);
+
+// pick (bw, bh, bn) with bw*bh*bn == pixels (a power of two) covering the (N,H,W) grid with little waste
+void pick_box(int N, int H, int W, int pixels, int* bw, int* bh, int* bn);
+
+struct PreparedOp {
+  virtual ~PreparedOp() {}
+  virtual int launch(cudaStream_t s) = 0;
+  virtual int num_launches() const { return 1; }
+};
+
+PreparedOp* prepare_conv(const b2seg_conv_desc* d);
+PreparedOp* prepare_wgrad(const b2seg_wgrad_desc* d);
+PreparedOp* prepare_bn_finalize(const b2seg_bn_finalize_desc* d);
+PreparedOp* prepare_bn_act(const b2seg_bn_act_desc* d);
+PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d);
+PreparedOp* prepare_adam(const b2seg_adam_desc* d);
+PreparedOp* prepare_head_fwd(const b2seg_head_desc* d);
+PreparedOp* prepare_head_bwd(const b2seg_head_desc* d);
+PreparedOp* prepare_loss(const b2seg_loss_desc* d);
+PreparedOp* prepare_eltwise(const b2seg_eltwise_desc* d);
+PreparedOp* prepare_cast(const b2seg_cast_desc* d);
+PreparedOp* prepare_colsum(const b2seg_colsum_desc* d);
+PreparedOp* prepare_memset(const b2seg_memset_desc* d);
+
+// adam launches expose their mutable hyper-parameters to the plan
+void adam_update(PreparedOp* op, float lr, int64_t step, float grad_scale);
+bool is_adam(PreparedOp* op);
+
+int conv_num_mtiles(const b2seg_conv_desc* d);
+
+}  // namespace b2

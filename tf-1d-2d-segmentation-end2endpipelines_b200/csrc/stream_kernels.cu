@@ -1,0 +1,821 @@
+// HBM-streaming kernels of the hot path: BatchNorm finalize / apply (+activation, +max-pool) / backward,
+// fused Adam, the small-Cout pointwise heads, the loss seed, element-wise glue and input cast.
+// All activation tensors are NHWC bf16 addressed through b2seg_view; every thread moves 16-byte vectors
+// (8 channels) so global accesses are coalesced along the channel axis.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b2 {
+
+struct DView {
+  unsigned long long ptr;
+  int N, H, W, C;
+  long long sn, sh, sw;
+};
+static DView dv(const b2seg_view& v) { return DView{v.ptr, v.N, v.H, v.W, v.C, v.sn, v.sh, v.sw}; }
+
+__device__ __forceinline__ const __nv_bfloat16* vaddr(const DView& v, int n, int h, int w, int c) {
+  return reinterpret_cast<const __nv_bfloat16*>(v.ptr) + n * v.sn + h * v.sh + w * v.sw + c;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(const __nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(p)) = u;
+}
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case B2SEG_ACT_RELU: return fmaxf(x, 0.f);
+    case B2SEG_ACT_LEAKY: return x > 0.f ? x : 0.3f * x;
+    case B2SEG_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    default: return x;
+  }
+}
+// derivative of the activation given its output y
+__device__ __forceinline__ float act_bwd_from_y(float y, int act) {
+  switch (act) {
+    case B2SEG_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case B2SEG_ACT_LEAKY: return y > 0.f ? 1.f : 0.3f;
+    case B2SEG_ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+
+static inline int grid_for(long long work, int block) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > 0x7fffffffll) g = 0x7fffffffll;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------ cast input
+__global__ void cast_input_kernel(const float* __restrict__ src, int N, int H, int W, int C, DView out) {
+  const int cv = out.C / 8;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long pix = i / cv;
+    const int w = (int)(pix % W); pix /= W;
+    const int h = (int)(pix % H);
+    const int n = (int)(pix / H);
+    const float* sp = src + (((long long)n * H + h) * W + w) * C;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (v * 8 + e < C) ? __ldg(sp + v * 8 + e) : 0.f;
+    store8(vaddr(out, n, h, w, v * 8), f);
+  }
+}
+struct CastLaunch : PreparedOp {
+  b2seg_cast_desc d;
+  int launch(cudaStream_t s) override {
+    const long long work = (long long)d.N * d.H * d.W * (d.out.C / 8);
+    cast_input_kernel<<<grid_for(work, 256), 256, 0, s>>>(reinterpret_cast<const float*>(d.src), d.N, d.H, d.W, d.C, dv(d.out));
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_cast(const b2seg_cast_desc* d) {
+  if (d->out.C % 8) { set_error("cast: out.C %% 8"); return nullptr; }
+  CastLaunch* L = new CastLaunch(); L->d = *d; return L;
+}
+
+// ------------------------------------------------------------------------------------------ BN finalize
+__global__ void bn_finalize_kernel(b2seg_bn_finalize_desc d) {
+  __shared__ double sh_s[32][33], sh_q[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const float* part = reinterpret_cast<const float*>(d.partials);
+  double s = 0.0, q = 0.0;
+  if (c < d.C && !d.inference) {
+    for (int pp = ty; pp < d.n_partials; pp += 32) {
+      s += (double)part[(size_t)pp * 2 * d.C + c];
+      q += (double)part[(size_t)pp * 2 * d.C + d.C + c];
+    }
+  }
+  sh_s[ty][tx] = s;
+  sh_q[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < d.C) {
+    float* mm = reinterpret_cast<float*>(d.moving_mean);
+    float* mv = reinterpret_cast<float*>(d.moving_var);
+    const float gamma = d.gamma ? reinterpret_cast<const float*>(d.gamma)[c] : 1.f;
+    const float beta = d.beta ? reinterpret_cast<const float*>(d.beta)[c] : 0.f;
+    double mean, var;
+    if (d.inference) {
+      mean = mm[c];
+      var = mv[c];
+    } else {
+      for (int i = 1; i < 32; ++i) { s += sh_s[i][tx]; q += sh_q[i][tx]; }
+      mean = s / d.count;
+      var = q / d.count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      if (d.update_moving) {
+        const double uv = (d.bessel && d.count > 1.0) ? var * d.count / (d.count - 1.0) : var;
+        mm[c] = (float)(mm[c] * (double)d.momentum + mean * (1.0 - (double)d.momentum));
+        mv[c] = (float)(mv[c] * (double)d.momentum + uv * (1.0 - (double)d.momentum));
+      }
+    }
+    const double rstd = 1.0 / sqrt(var + (double)d.eps);
+    reinterpret_cast<float*>(d.scale)[c] = (float)(gamma * rstd);
+    reinterpret_cast<float*>(d.shift)[c] = (float)(beta - mean * gamma * rstd);
+    if (d.mean) reinterpret_cast<float*>(d.mean)[c] = (float)mean;
+    if (d.rstd) reinterpret_cast<float*>(d.rstd)[c] = (float)rstd;
+  }
+}
+struct BnFinalizeLaunch : PreparedOp {
+  b2seg_bn_finalize_desc d;
+  int launch(cudaStream_t s) override {
+    bn_finalize_kernel<<<(d.C + 31) / 32, 1024, 0, s>>>(d);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_bn_finalize(const b2seg_bn_finalize_desc* d) { auto* L = new BnFinalizeLaunch(); L->d = *d; return L; }
+
+// ------------------------------------------------------------------------------------------ BN apply + act (+pool)
+struct BnActK {
+  DView x, out0, out1, pooled;
+  const float* scale; const float* shift;
+  int act, n_out, ph, pw;
+};
+__global__ void bn_act_kernel(BnActK k) {
+  const int cv = k.x.C / 8;
+  const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
+  const long long total = (long long)k.x.N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long pix = i / cv;
+    const int wo = (int)(pix % Wo); pix /= Wo;
+    const int ho = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    float sc[8], sf[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = k.scale ? __ldg(k.scale + v * 8 + e) : 1.f;
+      sf[e] = k.shift ? __ldg(k.shift + v * 8 + e) : 0.f;
+    }
+    float mx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mx[e] = -INFINITY;
+    for (int a = 0; a < k.ph; ++a)
+      for (int b = 0; b < k.pw; ++b) {
+        const int h = ho * k.ph + a, w = wo * k.pw + b;
+        float f[8];
+        load8(vaddr(k.x, n, h, w, v * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[e] = act_fwd(fmaf(f[e], sc[e], sf[e]), k.act);
+          mx[e] = fmaxf(mx[e], f[e]);
+        }
+        if (k.n_out > 0) store8(vaddr(k.out0, n, h, w, v * 8), f);
+        if (k.n_out > 1) store8(vaddr(k.out1, n, h, w, v * 8), f);
+      }
+    if (k.pooled.ptr) store8(vaddr(k.pooled, n, ho, wo, v * 8), mx);
+  }
+}
+struct BnActLaunch : PreparedOp {
+  BnActK k;
+  int launch(cudaStream_t s) override {
+    const long long work = (long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw) * (k.x.C / 8);
+    bn_act_kernel<<<grid_for(work, 256), 256, 0, s>>>(k);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_bn_act(const b2seg_bn_act_desc* d) {
+  if (d->x.C % 8) { set_error("bn_act: C %% 8"); return nullptr; }
+  auto* L = new BnActLaunch();
+  BnActK& k = L->k;
+  memset(&k, 0, sizeof(k));
+  k.x = dv(d->x);
+  k.scale = reinterpret_cast<const float*>(d->scale);
+  k.shift = reinterpret_cast<const float*>(d->shift);
+  k.act = d->act;
+  k.n_out = d->n_out;
+  if (d->n_out > 0) k.out0 = dv(d->out[0]);
+  if (d->n_out > 1) k.out1 = dv(d->out[1]);
+  k.ph = d->pool_h > 1 ? d->pool_h : 1;
+  k.pw = d->pool_w > 1 ? d->pool_w : 1;
+  if (k.ph > 1 || k.pw > 1) k.pooled = dv(d->pooled);
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------ BN backward
+struct GradSrcK { DView g; int kind; };
+struct BnBwdK {
+  DView x, dx;
+  const float* scale; const float* shift; const float* mean; const float* rstd;
+  int act, n_src;
+  GradSrcK src[B2SEG_MAX_GRADSRC];
+  int ph, pw;        // window processed per thread (pool window if a pooled source exists, else 1x1)
+  float inv_count;
+  float* partials;   // [n_blocks][2][C]
+  int n_blocks;
+  float* dgamma; float* dbeta;
+  int cvb, rp;       // channel vectors per block-row, pixel rows per block
+};
+
+// Computes, for one window, the masked incoming gradient dyv[a][b][8] (sum of sources, act' applied) and xhat.
+template <int PASS>
+__global__ void bn_bwd_kernel(BnBwdK k) {
+  extern __shared__ float red[];  // PASS 0: [rp][cvb*16]
+  const int cvec_total = k.x.C / 8;
+  const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
+  const int v = blockIdx.x * k.cvb + tcv;
+  const bool active = trow < k.rp && v < cvec_total;
+  const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
+  const long long n_win = (long long)k.x.N * Ho * Wo;
+  float sc[8], sf[8], mu[8], rs[8], cb[8], cg[8];
+  float acc_b[8], acc_g[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { acc_b[e] = 0.f; acc_g[e] = 0.f; }
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e;
+      sc[e] = k.scale ? __ldg(k.scale + c) : 1.f;
+      sf[e] = k.shift ? __ldg(k.shift + c) : 0.f;
+      mu[e] = k.mean ? __ldg(k.mean + c) : 0.f;
+      rs[e] = k.rstd ? __ldg(k.rstd + c) : 1.f;
+      if (PASS == 1 && k.scale) {
+        cb[e] = __ldg(k.dbeta + c) * k.inv_count;
+        cg[e] = __ldg(k.dgamma + c) * k.inv_count;
+      } else { cb[e] = 0.f; cg[e] = 0.f; }
+    }
+    for (long long win = (long long)blockIdx.y * k.rp + trow; win < n_win; win += (long long)gridDim.y * k.rp) {
+      long long t = win;
+      const int wo = (int)(t % Wo); t /= Wo;
+      const int ho = (int)(t % Ho);
+      const int n = (int)(t / Ho);
+      // forward recompute over the window: y and first-argmax per channel
+      float xh[4][8], yv[4][8];
+      int amax[8];
+      float ymax[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { amax[e] = 0; ymax[e] = -INFINITY; }
+      const int nwin = k.ph * k.pw;
+      for (int q = 0; q < nwin; ++q) {
+        const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
+        float f[8];
+        load8(vaddr(k.x, n, h, w, v * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float y = act_fwd(fmaf(f[e], sc[e], sf[e]), k.act);
+          yv[q][e] = y;
+          xh[q][e] = (f[e] - mu[e]) * rs[e];
+          if (y > ymax[e]) { ymax[e] = y; amax[e] = q; }
+        }
+      }
+      for (int q = 0; q < nwin; ++q) {
+        const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = 0.f;
+        for (int s = 0; s < k.n_src; ++s) {
+          float f[8];
+          if (k.src[s].kind == 0) {
+            load8(vaddr(k.src[s].g, n, h, w, v * 8), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] += f[e];
+          } else {
+            load8(vaddr(k.src[s].g, n, ho, wo, v * 8), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (amax[e] == q) g[e] += f[e];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] *= act_bwd_from_y(yv[q][e], k.act);
+        if (PASS == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { acc_b[e] += g[e]; acc_g[e] += g[e] * xh[q][e]; }
+        } else {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = k.scale ? sc[e] * (g[e] - cb[e] - xh[q][e] * cg[e]) : g[e];
+          store8(vaddr(k.dx, n, h, w, v * 8), o);
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    float* mine = red + (size_t)threadIdx.x * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mine[e] = active ? acc_b[e] : 0.f; mine[8 + e] = active ? acc_g[e] : 0.f; }
+    __syncthreads();
+    if (trow == 0 && v < cvec_total) {
+      float sb[8], sg[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sb[e] = 0.f; sg[e] = 0.f; }
+      for (int r = 0; r < k.rp; ++r) {
+        const float* o = red + (size_t)(r * k.cvb + tcv) * 16;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sb[e] += o[e]; sg[e] += o[8 + e]; }
+      }
+      float* pp = k.partials + (size_t)blockIdx.y * 2 * k.x.C;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { pp[v * 8 + e] = sb[e]; pp[k.x.C + v * 8 + e] = sg[e]; }
+    }
+  }
+}
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_blocks, int C, float* dgamma, float* dbeta,
+                                       const float* __restrict__ rstd_unused) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double b = 0.0, g = 0.0;
+  for (int i = 0; i < n_blocks; ++i) {
+    b += (double)partials[(size_t)i * 2 * C + c];
+    g += (double)partials[(size_t)i * 2 * C + C + c];
+  }
+  dbeta[c] = (float)b;
+  dgamma[c] = (float)g;
+}
+struct BnBwdLaunch : PreparedOp {
+  BnBwdK k;
+  bool has_bn;
+  dim3 grid0, grid1;
+  int smem0;
+  int launch(cudaStream_t s) override {
+    if (has_bn) {
+      bn_bwd_kernel<0><<<grid0, 256, smem0, s>>>(k);
+      B2_CUDA_OK(cudaGetLastError());
+      bn_bwd_finalize_kernel<<<(k.x.C + 127) / 128, 128, 0, s>>>(k.partials, k.n_blocks, k.x.C, k.dgamma, k.dbeta, nullptr);
+      B2_CUDA_OK(cudaGetLastError());
+    }
+    bn_bwd_kernel<1><<<grid1, 256, 0, s>>>(k);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int num_launches() const override { return has_bn ? 3 : 1; }
+};
+PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
+  if (d->x.C % 8 || d->n_src < 1 || d->n_src > B2SEG_MAX_GRADSRC) { set_error("bn_bwd: bad C or n_src"); return nullptr; }
+  auto* L = new BnBwdLaunch();
+  BnBwdK& k = L->k;
+  memset(&k, 0, sizeof(k));
+  k.x = dv(d->x); k.dx = dv(d->dx);
+  k.scale = reinterpret_cast<const float*>(d->scale);
+  k.shift = reinterpret_cast<const float*>(d->shift);
+  k.mean = reinterpret_cast<const float*>(d->mean);
+  k.rstd = reinterpret_cast<const float*>(d->rstd);
+  k.act = d->act;
+  k.n_src = d->n_src;
+  k.ph = 1; k.pw = 1;
+  for (int i = 0; i < d->n_src; ++i) {
+    k.src[i].g = dv(d->src[i].g);
+    k.src[i].kind = d->src[i].kind;
+    if (d->src[i].kind == 1) {
+      const int ph = d->src[i].pool_h > 1 ? d->src[i].pool_h : 1, pw = d->src[i].pool_w > 1 ? d->src[i].pool_w : 1;
+      if ((k.ph != 1 || k.pw != 1) && (k.ph != ph || k.pw != pw)) { set_error("bn_bwd: mixed pool windows"); delete L; return nullptr; }
+      k.ph = ph; k.pw = pw;
+    }
+  }
+  if (k.ph * k.pw > 4) { set_error("bn_bwd: pool window > 4 elements unsupported"); delete L; return nullptr; }
+  k.inv_count = (float)(1.0 / d->count);
+  k.partials = reinterpret_cast<float*>(d->partials);
+  k.n_blocks = d->n_blocks;
+  k.dgamma = reinterpret_cast<float*>(d->dgamma);
+  k.dbeta = reinterpret_cast<float*>(d->dbeta);
+  L->has_bn = d->scale != 0;
+  const int cvec = k.x.C / 8;
+  k.cvb = cvec < 256 ? cvec : 256;
+  k.rp = 256 / k.cvb;
+  const int gx = (cvec + k.cvb - 1) / k.cvb;
+  const long long n_win = (long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw);
+  L->grid0 = dim3(gx, d->n_blocks > 0 ? d->n_blocks : 1);
+  long long gy1 = (n_win + k.rp - 1) / k.rp;
+  if (gy1 > 65535) gy1 = 65535;
+  if (gy1 < 1) gy1 = 1;
+  L->grid1 = dim3(gx, (unsigned)gy1);
+  L->smem0 = 256 * 16 * 4;
+  if (L->has_bn && (d->n_blocks < 1 || d->n_blocks > 65535 || !d->partials || !d->dgamma || !d->dbeta)) {
+    set_error("bn_bwd: partials/dgamma/dbeta/n_blocks required with BN");
+    delete L;
+    return nullptr;
+  }
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------ Adam (Keras-2 rule)
+struct AdamK { float* w; const float* g; float* m; float* v; __nv_bfloat16* wb; long long n; float alpha, b1, b2, eps, gs; };
+__global__ void adam_kernel(AdamK k) {
+  const long long n4 = k.n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 w = reinterpret_cast<float4*>(k.w)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(k.g)[i];
+    float4 m = reinterpret_cast<float4*>(k.m)[i];
+    float4 v = reinterpret_cast<float4*>(k.v)[i];
+    float* wp = &w.x; const float* gp = &g4.x; float* mp = &m.x; float* vp = &v.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float g = gp[e] * k.gs;
+      mp[e] = k.b1 * mp[e] + (1.f - k.b1) * g;
+      vp[e] = k.b2 * vp[e] + (1.f - k.b2) * g * g;
+      wp[e] -= k.alpha * mp[e] / (sqrtf(vp[e]) + k.eps);
+    }
+    reinterpret_cast<float4*>(k.w)[i] = w;
+    reinterpret_cast<float4*>(k.m)[i] = m;
+    reinterpret_cast<float4*>(k.v)[i] = v;
+    uint2 o;
+    o.x = pack_bf16x2(w.x, w.y);
+    o.y = pack_bf16x2(w.z, w.w);
+    reinterpret_cast<uint2*>(k.wb)[i] = o;
+  }
+}
+struct AdamLaunch : PreparedOp {
+  b2seg_adam_desc d;
+  int launch(cudaStream_t s) override {
+    AdamK k;
+    k.w = reinterpret_cast<float*>(d.w); k.g = reinterpret_cast<const float*>(d.g);
+    k.m = reinterpret_cast<float*>(d.m); k.v = reinterpret_cast<float*>(d.v);
+    k.wb = reinterpret_cast<__nv_bfloat16*>(d.w_bf16); k.n = d.n;
+    const double t = (double)d.step;
+    k.alpha = (float)((double)d.lr * sqrt(1.0 - pow((double)d.beta2, t)) / (1.0 - pow((double)d.beta1, t)));
+    k.b1 = d.beta1; k.b2 = d.beta2; k.eps = d.eps; k.gs = d.grad_scale;
+    int grid = grid_for(d.n / 4, 256);
+    const int cap = num_sms() * 16;
+    if (grid > cap) grid = cap;
+    adam_kernel<<<grid, 256, 0, s>>>(k);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_adam(const b2seg_adam_desc* d) {
+  if (d->n % 4) { set_error("adam: n must be a multiple of 4 (pad the flat buffer)"); return nullptr; }
+  auto* L = new AdamLaunch(); L->d = *d; return L;
+}
+bool is_adam(PreparedOp* op) { return dynamic_cast<AdamLaunch*>(op) != nullptr; }
+void adam_update(PreparedOp* op, float lr, int64_t step, float grad_scale) {
+  if (auto* a = dynamic_cast<AdamLaunch*>(op)) { a->d.lr = lr; a->d.step = step; a->d.grad_scale = grad_scale; }
+}
+
+// ------------------------------------------------------------------------------------------ pointwise head
+// One group of G lanes (G = 8..32) per output pixel: each lane covers 8 channels per step.
+__global__ void head_fwd_kernel(DView x, const float* __restrict__ w, const float* __restrict__ b, int cout, int act, int stride,
+                                float* __restrict__ y, float* __restrict__ logits, int G) {
+  const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
+  const long long n_pix = (long long)x.N * Ho * Wo;
+  const int gl = threadIdx.x % G;
+  const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+  const long long gstride = (long long)gridDim.x * blockDim.x / G;
+  const int cvec = x.C / 8;
+  const long long n_iter = (n_pix + gstride - 1) / gstride;  // uniform trip count: the shuffles below need whole warps
+  for (long long it = 0; it < n_iter; ++it) {
+    const long long pix = gid + it * gstride;
+    const bool valid = pix < n_pix;
+    long long t = valid ? pix : 0;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int v = gl; v < cvec; v += G) {
+      float f[8];
+      load8(vaddr(x, n, ho * stride, wo * stride, v * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        for (int o = 0; o < cout; ++o) acc[o] = fmaf(f[e], __ldg(w + (size_t)(v * 8 + e) * cout + o), acc[o]);
+    }
+    for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off, 32);
+    if (gl == 0 && valid) {
+      float z[8];
+      float zmax = -INFINITY;
+      for (int o = 0; o < cout; ++o) { z[o] = acc[o] + b[o]; zmax = fmaxf(zmax, z[o]); }
+      if (logits) for (int o = 0; o < cout; ++o) logits[pix * cout + o] = z[o];
+      if (act == B2SEG_ACT_SOFTMAX) {
+        float den = 0.f;
+        for (int o = 0; o < cout; ++o) { z[o] = __expf(z[o] - zmax); den += z[o]; }
+        for (int o = 0; o < cout; ++o) y[pix * cout + o] = z[o] / den;
+      } else {
+        for (int o = 0; o < cout; ++o) y[pix * cout + o] = act_fwd(z[o], act);
+      }
+    }
+  }
+}
+static int head_group(int C) {
+  int g = 8;
+  while (g < 32 && g * 8 < C) g <<= 1;
+  return g;
+}
+struct HeadFwdLaunch : PreparedOp {
+  b2seg_head_desc d;
+  int launch(cudaStream_t s) override {
+    const int st = d.stride > 1 ? d.stride : 1;
+    const long long n_pix = (long long)d.x.N * ((d.x.H + st - 1) / st) * ((d.x.W + st - 1) / st);
+    const int G = head_group(d.x.C);
+    int grid = grid_for(n_pix * G, 256);
+    const int cap = num_sms() * 32;
+    if (grid > cap) grid = cap;
+    head_fwd_kernel<<<grid, 256, 0, s>>>(dv(d.x), reinterpret_cast<const float*>(d.w), reinterpret_cast<const float*>(d.b), d.cout, d.act, st,
+                                         reinterpret_cast<float*>(d.y), reinterpret_cast<float*>(d.logits), G);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_head_fwd(const b2seg_head_desc* d) {
+  if (d->cout < 1 || d->cout > 8 || d->x.C % 8) { set_error("head: cout in 1..8, C %% 8 == 0"); return nullptr; }
+  auto* L = new HeadFwdLaunch(); L->d = *d; return L;
+}
+
+// backward: dx = dl . W^T (bf16); dW[c][o] += sum_pix x[c]*dl[o]; db[o] += sum_pix dl[o]
+__global__ void head_bwd_dx_kernel(DView x, DView dx, const float* __restrict__ w, int cout, int stride, const float* __restrict__ dl) {
+  const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
+  const int cvec = x.C / 8;
+  const long long total = (long long)x.N * x.H * x.W * cvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long long t = i / cvec;
+    const int wq = (int)(t % x.W); t /= x.W;
+    const int h = (int)(t % x.H);
+    const int n = (int)(t / x.H);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    if (h % stride == 0 && wq % stride == 0) {
+      const long long pix = ((long long)n * Ho + h / stride) * Wo + wq / stride;
+      for (int q = 0; q < cout; ++q) {
+        const float d = __ldg(dl + pix * cout + q);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(d, __ldg(w + (size_t)(v * 8 + e) * cout + q), o[e]);
+      }
+    }
+    store8(vaddr(dx, n, h, wq, v * 8), o);
+  }
+}
+__global__ void head_bwd_dw_kernel(DView x, int cout, int stride, const float* __restrict__ dl, float* dw, float* db, int cvb, int rp) {
+  extern __shared__ float red[];  // [256][8] per output channel pass
+  const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
+  const long long n_pix = (long long)x.N * Ho * Wo;
+  const int cvec = x.C / 8;
+  const int tcv = threadIdx.x % cvb, trow = threadIdx.x / cvb;
+  const int v = blockIdx.x * cvb + tcv;
+  const bool active = trow < rp && v < cvec;
+  float acc[8][8];
+  float accb[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) { accb[o] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[o][e] = 0.f; }
+  if (active) {
+    for (long long pix = (long long)blockIdx.y * rp + trow; pix < n_pix; pix += (long long)gridDim.y * rp) {
+      long long t = pix;
+      const int wo = (int)(t % Wo); t /= Wo;
+      const int ho = (int)(t % Ho);
+      const int n = (int)(t / Ho);
+      float f[8];
+      load8(vaddr(x, n, ho * stride, wo * stride, v * 8), f);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        if (o < cout) {
+          const float d = __ldg(dl + pix * cout + o);
+          accb[o] += d;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(d, f[e], acc[o][e]);
+        }
+      }
+    }
+  }
+  for (int o = 0; o < cout; ++o) {
+    float* mine = red + (size_t)threadIdx.x * 9;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mine[e] = active ? acc[o][e] : 0.f;
+    mine[8] = active ? accb[o] : 0.f;
+    __syncthreads();
+    if (trow == 0 && v < cvec) {
+      float s[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) s[e] = 0.f;
+      for (int r = 0; r < rp; ++r) {
+        const float* q = red + (size_t)(r * cvb + tcv) * 9;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) s[e] += q[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(dw + (size_t)(v * 8 + e) * cout + o, s[e]);
+      if (v == 0) atomicAdd(db + o, s[8]);
+    }
+    __syncthreads();
+  }
+}
+struct HeadBwdLaunch : PreparedOp {
+  b2seg_head_desc d;
+  int launch(cudaStream_t s) override {
+    const int st = d.stride > 1 ? d.stride : 1;
+    if (d.dx.ptr) {
+      const long long work = (long long)d.x.N * d.x.H * d.x.W * (d.x.C / 8);
+      head_bwd_dx_kernel<<<grid_for(work, 256), 256, 0, s>>>(dv(d.x), dv(d.dx), reinterpret_cast<const float*>(d.w), d.cout, st,
+                                                              reinterpret_cast<const float*>(d.dlogits));
+      B2_CUDA_OK(cudaGetLastError());
+    }
+    const int cvec = d.x.C / 8;
+    const int cvb = cvec < 256 ? cvec : 256, rp = 256 / cvb;
+    const long long n_pix = (long long)d.x.N * ((d.x.H + st - 1) / st) * ((d.x.W + st - 1) / st);
+    long long gy = (n_pix + rp * 64 - 1) / (rp * 64);
+    if (gy > 1024) gy = 1024;
+    if (gy < 1) gy = 1;
+    dim3 grid((cvec + cvb - 1) / cvb, (unsigned)gy);
+    head_bwd_dw_kernel<<<grid, 256, 256 * 9 * 4, s>>>(dv(d.x), d.cout, st, reinterpret_cast<const float*>(d.dlogits),
+                                                       reinterpret_cast<float*>(d.dw), reinterpret_cast<float*>(d.db), cvb, rp);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int num_launches() const override { return d.dx.ptr ? 2 : 1; }
+};
+PreparedOp* prepare_head_bwd(const b2seg_head_desc* d) {
+  if (d->cout < 1 || d->cout > 8 || d->x.C % 8) { set_error("head: cout in 1..8, C %% 8 == 0"); return nullptr; }
+  auto* L = new HeadBwdLaunch(); L->d = *d; return L;
+}
+
+// ------------------------------------------------------------------------------------------ loss seed
+__global__ void loss_kernel(b2seg_loss_desc d) {
+  const float* yp = reinterpret_cast<const float*>(d.y_pred);
+  const float* yt = reinterpret_cast<const float*>(d.y_true);
+  float* dl = reinterpret_cast<float*>(d.dlogits);
+  const int co = d.cout;
+  const float inv_elems = 1.f / ((float)d.n_pix * (float)co);
+  const float inv_pix = 1.f / (float)d.n_pix;
+  float local = 0.f;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < d.n_pix; pix += (long long)gridDim.x * blockDim.x) {
+    if (d.kind == 1) {  // categorical CE on softmax probabilities
+      for (int o = 0; o < co; ++o) {
+        const float p = yp[pix * co + o], t = yt[pix * co + o];
+        local -= t * logf(fmaxf(p, 1e-7f)) * inv_pix;
+        if (dl) dl[pix * co + o] = d.weight * (p - t) * inv_pix;
+      }
+    } else {
+      for (int o = 0; o < co; ++o) {
+        const float p = yp[pix * co + o], t = yt[pix * co + o];
+        float dldz;
+        if (d.kind == 0) {  // binary CE, evaluated like Keras from the logits of the sigmoid head
+          const float pc = fminf(fmaxf(p, 1e-7f), 1.f - 1e-7f);
+          local -= (t * logf(pc) + (1.f - t) * logf(1.f - pc)) * inv_elems;
+          dldz = (p - t) * inv_elems;
+        } else {
+          const float diff = p - t;
+          float dldp;
+          if (d.kind == 2) { local += diff * diff * inv_elems; dldp = 2.f * diff * inv_elems; }
+          else { local += fabsf(diff) * inv_elems; dldp = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * inv_elems; }
+          dldz = dldp * (d.act == B2SEG_ACT_SIGMOID ? p * (1.f - p) : 1.f);
+        }
+        if (dl) dl[pix * co + o] = d.weight * dldz;
+      }
+    }
+  }
+  __shared__ float sh[32];
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (threadIdx.x == 0 && d.loss) atomicAdd(reinterpret_cast<float*>(d.loss), d.weight * t);
+  }
+}
+struct LossLaunch : PreparedOp {
+  b2seg_loss_desc d;
+  int launch(cudaStream_t s) override {
+    int grid = grid_for(d.n_pix, 256);
+    if (grid > 1024) grid = 1024;
+    loss_kernel<<<grid, 256, 0, s>>>(d);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_loss(const b2seg_loss_desc* d) {
+  if (d->kind < 0 || d->kind > 3) { set_error("loss: kind 0..3"); return nullptr; }
+  if (d->kind >= 2 && d->act == B2SEG_ACT_SOFTMAX) { set_error("loss: MSE/MAE through softmax unsupported"); return nullptr; }
+  auto* L = new LossLaunch(); L->d = *d; return L;
+}
+
+// ------------------------------------------------------------------------------------------ element-wise
+struct EltK { int op; DView a, b, c, out; };
+__global__ void eltwise_kernel(EltK k) {
+  const int cv = k.out.C / 8;
+  const long long total = (long long)k.out.N * k.out.H * k.out.W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long t = i / cv;
+    const int w = (int)(t % k.out.W); t /= k.out.W;
+    const int h = (int)(t % k.out.H);
+    const int n = (int)(t / k.out.H);
+    float a[8], b[8], o[8];
+    load8(vaddr(k.a, n, h, w, v * 8), a);
+    if (k.op == 0 || k.op == 3) {
+      load8(vaddr(k.b, n, h, w, v * 8), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = a[e] + b[e];
+      if (k.op == 3) {
+        load8(vaddr(k.c, n, h, w, v * 8), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] += b[e];
+      }
+    } else if (k.op == 2) {
+      load8(vaddr(k.b, n, h, w, v * 8), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = a[e] * (b[e] > 0.f ? 1.f : 0.3f);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = a[e];
+    }
+    store8(vaddr(k.out, n, h, w, v * 8), o);
+  }
+}
+struct EltLaunch : PreparedOp {
+  EltK k;
+  int launch(cudaStream_t s) override {
+    const long long work = (long long)k.out.N * k.out.H * k.out.W * (k.out.C / 8);
+    eltwise_kernel<<<grid_for(work, 256), 256, 0, s>>>(k);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_eltwise(const b2seg_eltwise_desc* d) {
+  if (d->out.C % 8) { set_error("eltwise: C %% 8"); return nullptr; }
+  auto* L = new EltLaunch();
+  L->k.op = d->op; L->k.a = dv(d->a); L->k.b = dv(d->b); L->k.c = dv(d->c); L->k.out = dv(d->out);
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------ column sum (bias grad)
+__global__ void colsum_kernel(DView g, float* out, int cvb, int rp) {
+  extern __shared__ float red[];
+  const int cvec = g.C / 8;
+  const int tcv = threadIdx.x % cvb, trow = threadIdx.x / cvb;
+  const int v = blockIdx.x * cvb + tcv;
+  const bool active = trow < rp && v < cvec;
+  const long long n_pix = (long long)g.N * g.H * g.W;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (active)
+    for (long long pix = (long long)blockIdx.y * rp + trow; pix < n_pix; pix += (long long)gridDim.y * rp) {
+      long long t = pix;
+      const int w = (int)(t % g.W); t /= g.W;
+      const int h = (int)(t % g.H);
+      const int n = (int)(t / g.H);
+      float f[8];
+      load8(vaddr(g, n, h, w, v * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  float* mine = red + (size_t)threadIdx.x * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) mine[e] = active ? acc[e] : 0.f;
+  __syncthreads();
+  if (trow == 0 && v < cvec) {
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    for (int r = 0; r < rp; ++r) {
+      const float* q = red + (size_t)(r * cvb + tcv) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += q[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(out + v * 8 + e, s[e]);
+  }
+}
+struct ColsumLaunch : PreparedOp {
+  b2seg_colsum_desc d;
+  int launch(cudaStream_t s) override {
+    const int cvec = d.g.C / 8;
+    const int cvb = cvec < 256 ? cvec : 256, rp = 256 / cvb;
+    const long long n_pix = (long long)d.g.N * d.g.H * d.g.W;
+    long long gy = (n_pix + rp * 32 - 1) / (rp * 32);
+    if (gy > 2048) gy = 2048;
+    if (gy < 1) gy = 1;
+    colsum_kernel<<<dim3((cvec + cvb - 1) / cvb, (unsigned)gy), 256, 256 * 8 * 4, s>>>(dv(d.g), reinterpret_cast<float*>(d.out), cvb, rp);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_colsum(const b2seg_colsum_desc* d) {
+  if (d->g.C % 8) { set_error("colsum: C %% 8"); return nullptr; }
+  auto* L = new ColsumLaunch(); L->d = *d; return L;
+}
+
+// ------------------------------------------------------------------------------------------ memset
+struct MemsetLaunch : PreparedOp {
+  b2seg_memset_desc d;
+  int launch(cudaStream_t s) override {
+    B2_CUDA_OK(cudaMemsetAsync(reinterpret_cast<void*>(d.ptr), 0, (size_t)d.bytes, s));
+    return 0;
+  }
+};
+PreparedOp* prepare_memset(const b2seg_memset_desc* d) { auto* L = new MemsetLaunch(); L->d = *d; return L; }
+
+}  // namespace b2
