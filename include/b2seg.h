@@ -222,6 +222,9 @@ int b2seg_plan_create(b2seg_plan** out);
 int b2seg_plan_add(b2seg_plan* p, int phase, int op, const void* desc, size_t desc_bytes);
 int b2seg_plan_run(b2seg_plan* p, int phase, void* stream);
 int b2seg_plan_num_launches(const b2seg_plan* p, int phase);
+int b2seg_plan_num_ops(const b2seg_plan* p, int phase);
+/* replay one phase with a CUDA event after every op; ms_per_op[i] = device time of op i (profiling aid for bench.py) */
+int b2seg_plan_run_timed(b2seg_plan* p, int phase, void* stream, float* ms_per_op, int n_ops);
 int b2seg_plan_set_adam(b2seg_plan* p, float lr, int64_t step, float grad_scale);
 void b2seg_plan_destroy(b2seg_plan* p);
 

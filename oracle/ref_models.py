@@ -1,0 +1,334 @@
+"""ORACLE — test infrastructure, NOT product code (see keras_ref.py).
+
+Eager restatement of the reference's graph builders on the KerasRef mini-API: the same layer calls in the same
+order as TensorFlow/2DCNN/models/unet_variants.py and TensorFlow/1DCNN/Models/{unet_variants,BCDUNet}.py, so
+Keras auto-names, weight shapes and the arithmetic can be compared with the product's graph IR layer by layer.
+Written independently of tf-1d-2d-segmentation-end2endpipelines_b200/b2seg/models{1d,2d}.py on purpose.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .keras_ref import KerasRef
+
+
+# =============================================================================================== 2D family
+class Ref2D:
+    """unet_model_builder(...).<Encoder>() with train_mode='from_scratch' (2DCNN/models/unet_variants.py:1045-1115)."""
+
+    def __init__(self, decoder_name, length, width, model_width, model_depth, num_channels=3, output_nums=1, ds=0, ae=0, ag=0, lstm=0,
+                 dense_loop=1, feature_number=1024, is_transconv=True, alpha=1.0, final_activation="sigmoid"):
+        self.dec, self.W, self.d = decoder_name, model_width, model_depth
+        self.out_n, self.ds, self.ae, self.ag, self.lstm = output_nums, ds, ae, ag, lstm
+        self.dense_loop, self.feat, self.tc, self.alpha, self.fa = dense_loop, feature_number, is_transconv, alpha, final_activation
+
+    # block library ------------------------------------------------------------------------------ :7-122
+    def CB(self, k, x, f, ks, bn=True, act="ReLU"):                      # Conv_Block :7-14
+        x = k.Conv(x, f, ks, padding="same", kernel_initializer="he_uniform")
+        if bn:
+            x = k.BatchNormalization(x)
+        return k.Activation(x, act) if act is not None else x
+
+    def TC(self, k, x, f):                                                # trans_conv2D :17-24 (bn never enabled)
+        return k.Activation(k.ConvTranspose(x, f, (4, 4), (2, 2), "same"), "LeakyReLU")
+
+    def AG(self, k, skip, gate, nf, mult):                                # Attention_Block :67-82
+        c1 = k.BatchNormalization(k.Conv(skip, nf * mult, (1, 1), strides=(2, 2)))
+        c2 = k.BatchNormalization(k.Conv(gate, nf * mult, (1, 1), strides=(1, 1)))
+        s = k.Activation(k.add([c1, c2]), "relu")
+        s = k.Activation(k.BatchNormalization(k.Conv(s, 1, (1, 1), strides=(1, 1))), "sigmoid")
+        r1 = k.UpSampling(s, (2, 2), "bilinear")
+        r2 = self.TC(k, s, 1)
+        return k.multiply(skip, k.add([r1, r2]))
+
+    def MRB(self, k, x, mw, ks):                                          # MultiResBlock :85-100
+        w = self.alpha * mw
+        sc = self.CB(k, x, int(w * 0.167) + int(w * 0.333) + int(w * 0.5), (1, 1))
+        c3 = self.CB(k, x, int(w * 0.167), ks)
+        c5 = self.CB(k, c3, int(w * 0.333), ks)
+        c7 = self.CB(k, c5, int(w * 0.5), ks)
+        o = k.BatchNormalization(k.concatenate([c3, c5, c7]))
+        return k.BatchNormalization(k.Activation(k.add([sc, o]), "relu"))
+
+    def RP(self, k, x, length, mw, ks):                                   # ResPath :103-122
+        def step(t):
+            sc = self.CB(k, t, mw, (1, 1))
+            o = self.CB(k, t, mw, ks)
+            return k.BatchNormalization(k.Activation(k.add([sc, o]), "relu"))
+        out = step(x)
+        for _ in range(1, length):
+            out = step(out)
+        return out
+
+    def up(self, k, x, f):
+        return self.TC(k, x, f) if self.tc else k.UpSampling(x, (2, 2), "bilinear")
+
+    def fuse(self, k, skip, up, tot, lstm_f):
+        if self.lstm == 1:                                               # :145-149 / :330-332 (order skip, up, tot)
+            return k.ConvLSTM([skip, up] + ([] if tot is None else [tot]), int(np.int32(lstm_f)), (3, 3))
+        cat = up                                                          # Concat_Block left fold :27-32
+        for t in ([] if tot is None else [tot]) + [skip]:
+            cat = k.concatenate([cat, t])
+        return cat
+
+    # decoders -------------------------------------------------------------------------------------------
+    def dec_unet(self, k, skips, multires=False):                         # UNet :125-154 / MultiResUNet :459-487
+        W, d = self.W, self.d
+        levels, deconv = [], skips[-1]
+        for j in range(d):
+            l = d - j - 1
+            skip = skips[l]
+            if self.ag == 1:
+                skip = self.AG(k, skips[l], deconv, W, 2 ** l)
+            if self.ds == 1:
+                levels.append(k.Conv(deconv, 1, (1, 1), name=f"level{d - j}"))
+            deconv = self.up(k, deconv, W * 2 ** l)
+            deconv = self.fuse(k, skip, deconv, None, W * (2.0 ** (l - 1)))
+            deconv = self.MRB(k, deconv, W * 2 ** l, (3, 3)) if multires else self.CB(k, deconv, W * 2 ** l, (3, 3))
+        return deconv, levels
+
+    def dec_nested(self, k, skips):                                       # UNetE :157 / UNetP :217 / UNetPP :277
+        W, d = self.W, self.d
+        levels = []
+        if self.ds == 1:
+            levels.append(k.Conv(skips[0], 1, (1, 1), name=f"level{d}"))
+        D = {}
+        for i in range(1, d + 1):
+            for j in range(0, d - i + 1):
+                low = skips[j + 1] if i == 1 else D[j + 1, i - 1]
+                att = (lambda t: self.AG(k, t, low, W, 2 ** j)) if self.ag == 1 else (lambda t: t)
+                tot = None
+                if i == 1 or self.dec == "UNetE":
+                    skip = att(skips[j])
+                elif self.dec == "UNetP":
+                    skip = att(D[j, i - 1])
+                else:
+                    tot = att(D[j, 1])
+                    for q in range(2, i):
+                        tot = k.concatenate([tot, att(D[j, q])])
+                    skip = att(skips[j])
+                up = self.up(k, low, W * 2 ** j)
+                D[j, i] = self.CB(k, self.fuse(k, skip, up, tot, W * (2.0 ** (j - 1))), W * 2 ** j, (3, 3))
+                if self.ds == 1 and j == 0 and i < d:
+                    levels.append(k.Conv(D[j, i], 1, (1, 1), name=f"level{d - i}"))
+        return D[0, d], levels
+
+    def dec_unet3p(self, k, skips):                                       # UNet3P :346-376
+        W, d = self.W, self.d
+        levels, deconv, D = [], skips[-1], {}
+        for j in range(d):
+            allc = self.CB(k, skips[d - j - 1], W, (3, 3))
+            for q in range(0, d - j - 1):
+                p = 2 ** ((d - j) - q - 1)
+                allc = k.concatenate([allc, self.CB(k, k.MaxPooling(skips[q], (p, p)), W, (3, 3))])
+            t = k.Activation(k.UpSampling(self.CB(k, deconv, W, (3, 3)), (2, 2), "bilinear"), "sigmoid")
+            tot = k.concatenate([allc, t])
+            for m in range(j):
+                f = 2 ** (j - m)
+                t = k.Activation(k.UpSampling(self.CB(k, D[m], W, (3, 3)), (f, f), "bilinear"), "sigmoid")
+                tot = k.concatenate([tot, t])
+            deconv = self.CB(k, tot, W * (d + 1), (3, 3))
+            D[j] = deconv
+            if self.ds == 1:
+                levels.append(k.Conv(deconv, 1, (1, 1), strides=(2, 2), name=f"level{d - j}"))
+        return deconv, levels
+
+    # whole model ------------------------------------------------------------------------------------------
+    def __call__(self, k: KerasRef, x):
+        W, d = self.W, self.d
+        pool = k.Input(x)
+        convs = []
+        mres = self.dec in ("MultiResUNet", "MultiResUNet3P")
+        for i in range(1, d + 2):                                         # encoder_block_scratch :750-792
+            if mres:
+                conv = self.MRB(k, pool, W * 2 ** (i - 1), (3, 3))
+                pool = k.MaxPooling(conv, (2, 2))
+                convs.append(self.RP(k, conv, d - i + 1, W * 2 ** (i - 1), (3, 3)))
+            else:
+                conv = self.CB(k, pool, W * 2 ** (i - 1), (3, 3))
+                pool = k.MaxPooling(conv, (2, 2))
+                convs.append(conv)
+        if mres:                                                          # latent_layer :966-974
+            conv = self.MRB(k, conv, W * 2 ** d, (3, 3))
+        else:                                                             # dense_block :51-56
+            conv = self.CB(k, conv, W * 2 ** d, (3, 3))
+            for _ in range(self.dense_loop):
+                conv = k.add([conv, self.CB(k, conv, W * 2 ** d, (3, 3))])
+        if self.ae == 1:                                                  # Feature_Extraction_Block :41-48
+            sh = conv.shape
+            z = k.Dense(k.Flatten(conv), self.feat, name="features")
+            z = k.Dense(z, W * 2 ** d * sh[1] * sh[2])
+            conv = k.Reshape(z, (sh[1], sh[2], W * 2 ** d))
+        skips = convs[:d] + [conv]
+        if self.dec == "UNet":
+            deconv, levels = self.dec_unet(k, skips)
+        elif self.dec in ("UNetE", "UNetP", "UNetPP"):
+            deconv, levels = self.dec_nested(k, skips)
+        elif self.dec in ("UNet3P", "UNet4PV2"):
+            deconv, levels = self.dec_unet3p(k, skips)
+        elif self.dec == "MultiResUNet":
+            deconv, levels = self.dec_unet(k, skips, multires=True)
+        else:
+            raise NotImplementedError(self.dec)
+        out = k.Conv(deconv, self.out_n, (1, 1), activation=self.fa, name="out")   # :1106
+        return list(reversed(levels + [out])) if self.ds == 1 else [out]
+
+
+# =============================================================================================== 1D family
+class Ref1D:
+    """UNet(...).<variant>() (1DCNN/Models/unet_variants.py:222-897) and BCDUNet(...).BCDUNet() (BCDUNet.py:79-174)."""
+
+    def __init__(self, variant, length, model_depth, num_channel, model_width, kernel_size, problem_type="Regression", output_nums=1,
+                 ds=1, ae=0, ag=0, lstm=0, alpha=1, feature_number=1024, is_transconv=True, dense_loop=1):
+        self.var, self.L, self.d, self.W, self.ks = variant, length, model_depth, model_width, kernel_size
+        self.pt, self.out_n, self.ds, self.ae, self.ag, self.lstm = problem_type, output_nums, ds, ae, ag, lstm
+        self.alpha, self.feat, self.tc, self.dense_loop = alpha, feature_number, is_transconv, dense_loop
+
+    def CB(self, k, x, mw, ks, mult):                                     # Conv_Block uv:53-60
+        return k.Activation(k.BatchNormalization(k.Conv(x, mw * mult, ks, padding="same")), "relu")
+
+    def TC(self, k, x, mw, mult):                                         # trans_conv1D uv:102-108
+        return k.Activation(k.BatchNormalization(k.ConvTranspose(x, mw * mult, 2, 2, "same")), "relu")
+
+    def up(self, k, x, mult):
+        return self.TC(k, x, self.W, mult) if self.tc else k.UpSampling(x, 2)
+
+    def FE(self, k, x):                                                   # Feature_Extraction_Block uv:127-135
+        Ln = x.shape[1]
+        z = k.Dense(k.Flatten(x), self.feat, name="features")
+        return k.Reshape(k.Dense(z, self.W * Ln), (Ln, self.W))
+
+    def AG(self, k, skip, gate, nf, mult):                                # Attention_Block uv:154-170
+        c1 = k.BatchNormalization(k.Conv(skip, nf * mult, 1, strides=2))
+        c2 = k.BatchNormalization(k.Conv(gate, nf * mult, 1, strides=1))
+        s = k.Activation(k.add([c1, c2]), "relu")
+        s = k.Activation(k.BatchNormalization(k.Conv(s, 1, 1, strides=1)), "sigmoid")
+        return k.multiply(skip, k.add([k.UpSampling(s, 2), self.TC(k, s, 1, 1)]))
+
+    def MRB(self, k, x, mult):                                            # MultiResBlock uv:173-193
+        w = self.alpha * self.W
+        sc = self.CB(k, x, int(w * 0.167) + int(w * 0.333) + int(w * 0.5), 1, mult)
+        c3 = self.CB(k, x, int(w * 0.167), self.ks, mult)
+        c5 = self.CB(k, c3, int(w * 0.333), self.ks, mult)
+        c7 = self.CB(k, c5, int(w * 0.5), self.ks, mult)
+        o = k.BatchNormalization(k.concatenate([c3, c5, c7]))
+        return k.BatchNormalization(k.Activation(k.add([sc, o]), "relu"))
+
+    def RP(self, k, x, length, mult):                                     # ResPath uv:196-219
+        def step(t):
+            sc = self.CB(k, t, self.W, 1, mult)
+            o = self.CB(k, t, self.W, self.ks, mult)
+            return k.BatchNormalization(k.Activation(k.add([sc, o]), "relu"))
+        out = step(x)
+        for _ in range(1, length):
+            out = step(out)
+        return out
+
+    def fuse(self, k, skip, up, tot, l):
+        if self.lstm == 1:
+            return k.ConvLSTM([skip, up] + ([] if tot is None else [tot]), int(np.int32(self.W * (2.0 ** (l - 1)))), 3)
+        cat = up
+        for t in ([] if tot is None else [tot]) + [skip]:
+            cat = k.concatenate([cat, t])
+        return cat
+
+    def two(self, k, x, mult):
+        return self.CB(k, self.CB(k, x, self.W, self.ks, mult), self.W, self.ks, mult)
+
+    def head(self, k, deconv, levels):
+        act = "softmax" if self.pt == "Classification" else "linear"
+        out = k.Conv(deconv, self.out_n, 1, activation=act, name="out")
+        return list(reversed(levels + [out])) if self.ds == 1 else [out]
+
+    def __call__(self, k: KerasRef, x):
+        W, d = self.W, self.d
+        pool = k.Input(x)
+        levels = []
+        if self.var == "MultiResUNet":                                    # uv:836-897
+            paths = []
+            for i in range(1, d + 1):
+                blk = self.MRB(k, pool, 2 ** (i - 1))
+                pool = k.MaxPooling(blk, 2)
+                paths.append(self.RP(k, blk, d - i + 1, 2 ** (i - 1)))
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            deconv = self.MRB(k, pool, 2 ** d)
+            for j in range(d):
+                l = d - j - 1
+                skip = self.AG(k, paths[l], deconv, W, 2 ** l) if self.ag == 1 else paths[l]
+                if self.ds == 1:
+                    levels.append(k.Conv(deconv, 1, 1, name=f"level{d - j}"))
+                deconv = self.MRB(k, self.fuse(k, skip, self.up(k, deconv, 2 ** l), None, l), 2 ** l)
+            return self.head(k, deconv, levels)
+
+        convs = []
+        for i in range(1, d + 1):                                         # encoder uv:267-271
+            conv = self.two(k, pool, 2 ** (i - 1))
+            pool = k.MaxPooling(conv, 2)
+            convs.append(conv)
+        if self.var == "BCDUNet":                                         # BCDUNet.py:129-134
+            conv = pool
+            for _ in range(self.dense_loop - 1):
+                conv = k.concatenate([conv, self.two(k, conv, 2 ** d)])
+            if self.ae == 1:
+                conv = self.FE(k, conv)
+            conv = self.two(k, conv, 2 ** d)
+        else:
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            conv = self.two(k, pool, 2 ** d)
+
+        if self.var in ("UNet", "BCDUNet"):                               # uv:281-304 / BCDUNet.py:140-160
+            deconv = conv
+            for j in range(d):
+                l = d - j - 1
+                skip = self.AG(k, convs[l], deconv, W, 2 ** l) if self.ag == 1 else convs[l]
+                if self.ds == 1:
+                    levels.append(k.Conv(deconv, 1, 1, name=f"level{d - j}"))
+                deconv = self.up(k, deconv, 2 ** l)
+                if self.var == "UNet" or self.lstm == 1:
+                    deconv = self.fuse(k, skip, deconv, None, l)
+                deconv = self.two(k, deconv, 2 ** l)
+            return self.head(k, deconv, levels)
+
+        if self.var in ("UNetE", "UNetP", "UNetPP"):                      # uv:321-645
+            skips = convs + [conv]
+            if self.ds == 1:
+                levels.append(k.Conv(convs[0], 1, 1, name=f"level{d}"))
+            D = {}
+            for i in range(1, d + 1):
+                for j in range(0, d - i + 1):
+                    low = skips[j + 1] if i == 1 else D[j + 1, i - 1]
+                    att = (lambda t: self.AG(k, t, low, W, 2 ** j)) if self.ag == 1 else (lambda t: t)
+                    tot = None
+                    if i == 1 or self.var == "UNetE":
+                        skip = att(skips[j])
+                    elif self.var == "UNetP":
+                        skip = att(D[j, i - 1])
+                    else:
+                        tot = att(D[j, 1])
+                        for q in range(2, i):
+                            tot = k.concatenate([tot, att(D[j, q])])
+                        skip = att(skips[j])
+                    D[j, i] = self.two(k, self.fuse(k, skip, self.up(k, low, 2 ** j), tot, j), 2 ** j)
+                    if self.ds == 1 and j == 0 and i < d:
+                        levels.append(k.Conv(D[j, i], 1, 1, name=f"level{d - i}"))
+            return self.head(k, D[0, d], levels)
+
+        if self.var == "UNet3P":                                          # uv:647-715
+            deconv, D = conv, {}
+            for j in range(d):
+                allc = self.CB(k, convs[d - j - 1], W, self.ks, 1)
+                for q in range(0, d - j - 1):
+                    allc = k.concatenate([allc, self.CB(k, k.MaxPooling(convs[q], 2 ** ((d - j) - q - 1)), W, self.ks, 1)])
+                t = k.Activation(k.UpSampling(self.CB(k, deconv, W, self.ks, 1), 2), "sigmoid")
+                tot = k.concatenate([allc, t])
+                for m in range(j):
+                    t = k.Activation(k.UpSampling(self.CB(k, D[m], W, self.ks, 1), 2 ** (j - m)), "sigmoid")
+                    tot = k.concatenate([tot, t])
+                deconv = self.CB(k, tot, W, self.ks, d + 1)
+                D[j] = deconv
+                if self.ds == 1:
+                    levels.append(k.Conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
+            return self.head(k, deconv, levels)
+        raise NotImplementedError(self.var)

@@ -83,3 +83,263 @@ def run_wgrad(mem: FakeMem, d):
         dy = mem.shifted(d.dy[tap.pair], tap.dyh, tap.dyw, d.gN, d.gH, d.gW)
         x = mem.shifted(d.x[tap.pair], tap.dh, tap.dw, d.gN, d.gH, d.gW)
         dW[:, tap.widx, :] += torch.einsum("nhwo,nhwi->oi", dy, x)
+
+
+# ============================================================================================================
+# Whole-plan emulation: every op of include/b2seg.h in float64 on FakeMem.  Used by the CPU tests to check the
+# planner (fusion, concat slots, gradient routing, weight layouts) against the oracle without a GPU.
+import math
+
+import numpy as np
+
+from b2seg import _lib as L
+
+_ESIZE = {"act": 2, "grad": 2, "param_wb": 2}
+
+
+class PlanMem(FakeMem):
+    def alloc_bytes(self, nbytes, tag="act"):
+        es = _ESIZE.get(tag, 4)
+        base, _ = self.alloc(nbytes // es, es)
+        return base
+
+    def f32(self, ptr, n):
+        t, off = self.resolve(ptr)
+        return t[off:off + n]
+
+
+def _act(x, code):
+    if code == L.ACT_RELU:
+        return torch.relu(x)
+    if code == L.ACT_LEAKY:
+        return torch.where(x > 0, x, 0.3 * x)
+    if code == L.ACT_SIGMOID:
+        return torch.sigmoid(x)
+    return x
+
+
+def _dact_from_y(y, code):
+    if code == L.ACT_RELU:
+        return (y > 0).double()
+    if code == L.ACT_LEAKY:
+        return torch.where(y > 0, 1.0, 0.3).double()
+    if code == L.ACT_SIGMOID:
+        return y * (1 - y)
+    return torch.ones_like(y)
+
+
+def emu_conv(mem, d):
+    wt, woff = mem.resolve(d.weights)
+    Wm = wt[woff:woff + d.w_cout * d.w_taps * d.w_cin].view(d.w_cout, d.w_taps, d.w_cin)
+    tot_s, tot_q = None, None
+    for g in range(d.n_groups):
+        o = d.out[g]
+        acc = torch.zeros(o.N, o.H, o.W, o.C, dtype=torch.float64)
+        for t in range(d.taps_per_group):
+            tap = d.taps[g * d.taps_per_group + t]
+            xs = mem.shifted(d.src[tap.src], tap.dh, tap.dw, o.N, o.H, o.W)
+            if d.b_mn_major == 0:
+                acc += xs[..., :d.w_cin] @ Wm[:o.C, tap.widx, :xs.shape[-1]].T
+            else:
+                acc += xs[..., :d.w_cout] @ Wm[:xs.shape[-1], tap.widx, :o.C]
+        if d.bias:
+            acc = acc + mem.f32(d.bias, o.C)
+        acc = _act(acc, d.act)
+        if d.mul_mode:
+            mv = d.mul_view
+            y = mem.gather_view(mv)
+            acc[..., :mv.C] = acc[..., :mv.C] * _dact_from_y(y, d.mul_mode)
+        mem.write_view(o, acc)
+        if d.stats:
+            s, q = acc.reshape(-1, o.C).sum(0), (acc.reshape(-1, o.C) ** 2).sum(0)
+            tot_s = s if tot_s is None else tot_s + s
+            tot_q = q if tot_q is None else tot_q + q
+    if d.stats:
+        C = d.out[0].C
+        st = mem.f32(d.stats, 2 * C)   # emulator writes totals into partial 0; the rest stay zero
+        st[:C], st[C:] = tot_s, tot_q
+
+
+def emu_bn_finalize(mem, d):
+    C = d.C
+    mm, mv = mem.f32(d.moving_mean, C), mem.f32(d.moving_var, C)
+    gamma, beta = mem.f32(d.gamma, C), mem.f32(d.beta, C)
+    if d.inference:
+        mean, var = mm.clone(), mv.clone()
+    else:
+        part = mem.f32(d.partials, d.n_partials * 2 * C).view(d.n_partials, 2, C)
+        s, q = part[:, 0].sum(0), part[:, 1].sum(0)
+        mean = s / d.count
+        var = (q / d.count - mean * mean).clamp_min(0)
+        if d.update_moving:
+            uv = var * d.count / (d.count - 1) if (d.bessel and d.count > 1) else var
+            mm[:] = mm * d.momentum + mean * (1 - d.momentum)
+            mv[:] = mv * d.momentum + uv * (1 - d.momentum)
+    rstd = 1.0 / torch.sqrt(var + d.eps)
+    mem.f32(d.scale, C)[:] = gamma * rstd
+    mem.f32(d.shift, C)[:] = beta - mean * gamma * rstd
+    if d.mean:
+        mem.f32(d.mean, C)[:] = mean
+    if d.rstd:
+        mem.f32(d.rstd, C)[:] = rstd
+
+
+def emu_bn_act(mem, d):
+    x = mem.gather_view(d.x)
+    C = d.x.C
+    sc = mem.f32(d.scale, C) if d.scale else torch.ones(C, dtype=torch.float64)
+    sf = mem.f32(d.shift, C) if d.shift else torch.zeros(C, dtype=torch.float64)
+    y = _act(x * sc + sf, d.act)
+    for i in range(d.n_out):
+        mem.write_view(d.out[i], y)
+    ph, pw = max(d.pool_h, 1), max(d.pool_w, 1)
+    if ph > 1 or pw > 1:
+        N, H, W, _ = y.shape
+        p = y.view(N, H // ph, ph, W // pw, pw, C).amax(dim=(2, 4))
+        mem.write_view(d.pooled, p)
+
+
+def emu_bn_bwd(mem, d):
+    x = mem.gather_view(d.x)
+    N, H, W, C = x.shape
+    has_bn = bool(d.scale)
+    sc = mem.f32(d.scale, C) if has_bn else torch.ones(C, dtype=torch.float64)
+    sf = mem.f32(d.shift, C) if d.shift else torch.zeros(C, dtype=torch.float64)
+    mu = mem.f32(d.mean, C) if d.mean else torch.zeros(C, dtype=torch.float64)
+    rs = mem.f32(d.rstd, C) if d.rstd else torch.ones(C, dtype=torch.float64)
+    y = _act(x * sc + sf, d.act)
+    g = torch.zeros_like(x)
+    for i in range(d.n_src):
+        s = d.src[i]
+        gv = mem.gather_view(s.g)
+        if s.kind == 0:
+            g += gv
+        else:
+            ph, pw = s.pool_h, s.pool_w
+            yw = y.view(N, H // ph, ph, W // pw, pw, C).permute(0, 1, 3, 5, 2, 4).reshape(N, H // ph, W // pw, C, ph * pw)
+            first = yw.argmax(dim=-1)  # torch returns the first maximal index
+            onehot = torch.nn.functional.one_hot(first, ph * pw).double() * gv.unsqueeze(-1)
+            g += onehot.view(N, H // ph, W // pw, C, ph, pw).permute(0, 1, 4, 2, 5, 3).reshape(N, H, W, C)
+    g = g * _dact_from_y(y, d.act)
+    if has_bn:
+        xh = (x - mu) * rs
+        dbeta = g.reshape(-1, C).sum(0)
+        dgamma = (g * xh).reshape(-1, C).sum(0)
+        mem.f32(d.dbeta, C)[:] = dbeta
+        mem.f32(d.dgamma, C)[:] = dgamma
+        dx = sc * (g - dbeta / d.count - xh * dgamma / d.count)
+    else:
+        dx = g
+    mem.write_view(d.dx, dx)
+
+
+def emu_wgrad(mem, d):
+    run_wgrad(mem, d)
+
+
+def emu_adam(mem, d):
+    n = d.n
+    w, g, m, v = mem.f32(d.w, n), mem.f32(d.g, n), mem.f32(d.m, n), mem.f32(d.v, n)
+    gg = g * d.grad_scale
+    m[:] = d.beta1 * m + (1 - d.beta1) * gg
+    v[:] = d.beta2 * v + (1 - d.beta2) * gg * gg
+    alpha = d.lr * math.sqrt(1 - d.beta2 ** d.step) / (1 - d.beta1 ** d.step)
+    w[:] = w - alpha * m / (v.sqrt() + d.eps)
+    wb, off = mem.resolve(d.w_bf16)
+    wb[off:off + n] = w
+
+
+def _head_geom(d):
+    st = max(d.stride, 1)
+    return st, (d.x.H + st - 1) // st, (d.x.W + st - 1) // st
+
+
+def emu_head_fwd(mem, d):
+    st, Ho, Wo = _head_geom(d)
+    x = mem.gather_view(d.x)[:, ::st, ::st]
+    w = mem.f32(d.w, d.x.C * d.cout).view(d.x.C, d.cout)
+    z = x @ w + mem.f32(d.b, d.cout)
+    n = z.numel()
+    if d.logits:
+        mem.f32(d.logits, n)[:] = z.reshape(-1)
+    y = torch.softmax(z, -1) if d.act == L.ACT_SOFTMAX else _act(z, d.act)
+    mem.f32(d.y, n)[:] = y.reshape(-1)
+
+
+def emu_head_bwd(mem, d):
+    st, Ho, Wo = _head_geom(d)
+    xfull = mem.gather_view(d.x)
+    x = xfull[:, ::st, ::st]
+    w = mem.f32(d.w, d.x.C * d.cout).view(d.x.C, d.cout)
+    dl = mem.f32(d.dlogits, x.shape[0] * Ho * Wo * d.cout).view(x.shape[0], Ho, Wo, d.cout)
+    if d.dx.ptr:
+        dx = torch.zeros_like(xfull)
+        dx[:, ::st, ::st] = dl @ w.T
+        mem.write_view(d.dx, dx)
+    mem.f32(d.dw, d.x.C * d.cout)[:] += torch.einsum("nhwc,nhwo->co", x, dl).reshape(-1)
+    mem.f32(d.db, d.cout)[:] += dl.reshape(-1, d.cout).sum(0)
+
+
+def emu_loss(mem, d):
+    n = d.n_pix * d.cout
+    p, t = mem.f32(d.y_pred, n).view(d.n_pix, d.cout), mem.f32(d.y_true, n).view(d.n_pix, d.cout)
+    if d.kind == 1:
+        loss = -(t * p.clamp_min(1e-7).log()).sum(-1).mean()
+        dl = (p - t) / d.n_pix
+    elif d.kind == 0:
+        pc = p.clamp(1e-7, 1 - 1e-7)
+        loss = -(t * pc.log() + (1 - t) * (1 - pc).log()).mean()
+        dl = (p - t) / n
+    else:
+        diff = p - t
+        if d.kind == 2:
+            loss, dp = (diff ** 2).mean(), 2 * diff / n
+        else:
+            loss, dp = diff.abs().mean(), torch.sign(diff) / n
+        dl = dp * (p * (1 - p) if d.act == L.ACT_SIGMOID else 1.0)
+    if d.dlogits:
+        mem.f32(d.dlogits, n)[:] = (d.weight * dl).reshape(-1)
+    if d.loss:
+        mem.f32(d.loss, 1)[:] += d.weight * loss
+
+
+def emu_eltwise(mem, d):
+    a = mem.gather_view(d.a)
+    if d.op == 0:
+        o = a + mem.gather_view(d.b)
+    elif d.op == 3:
+        o = a + mem.gather_view(d.b) + mem.gather_view(d.c)
+    elif d.op == 2:
+        o = a * torch.where(mem.gather_view(d.b) > 0, 1.0, 0.3)
+    else:
+        o = a
+    mem.write_view(d.out, o)
+
+
+def emu_cast(mem, d):
+    src = mem.f32(d.src, d.N * d.H * d.W * d.C).view(d.N, d.H, d.W, d.C)
+    o = torch.zeros(d.N, d.H, d.W, d.out.C, dtype=torch.float64)
+    o[..., :d.C] = src
+    mem.write_view(d.out, o)
+
+
+def emu_colsum(mem, d):
+    g = mem.gather_view(d.g)
+    mem.f32(d.out, d.g.C)[:] += g.reshape(-1, d.g.C).sum(0)
+
+
+def emu_memset(mem, d):
+    t, off = mem.resolve(d.ptr)
+    es = next(es for (b, nb, tt, es) in mem.bufs if tt is t)
+    t[off:off + d.bytes // es] = 0
+
+
+EMU = {L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_finalize, L.OP_BN_ACT: emu_bn_act,
+       L.OP_BN_BWD: emu_bn_bwd, L.OP_ADAM: emu_adam, L.OP_HEAD_FWD: emu_head_fwd, L.OP_HEAD_BWD: emu_head_bwd,
+       L.OP_LOSS: emu_loss, L.OP_ELTWISE: emu_eltwise, L.OP_CAST: emu_cast, L.OP_COLSUM: emu_colsum,
+       L.OP_MEMSET: emu_memset}
+
+
+def run_phase(mem, planner, phase):
+    for (op, desc, _note) in planner.ops[phase]:
+        EMU[op](mem, desc)

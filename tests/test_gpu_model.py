@@ -1,0 +1,180 @@
+"""End-to-end GPU parity: builder API -> planner -> C ABI -> B200 kernels, against the oracle (float64 CPU restatement of
+the reference graphs) on identical weights and inputs.
+
+Tolerances are BASELINE.json's: per-layer activations and gradients rel-L2 <= 1e-2 in bf16, masks agreeing on
+>= 99.9 % of pixels.  Gradients of conv biases that feed a BatchNormalization are analytically zero and are
+compared by absolute size.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from b2seg.models1d import UNet  # noqa: E402
+from b2seg.models2d import unet_model_builder  # noqa: E402
+from oracle.keras_ref import KerasRef, keras_adam_step, keras_loss  # noqa: E402
+from oracle.ref_models import Ref1D, Ref2D  # noqa: E402
+
+TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _oracle(ref, ndim, params, x, targets, losses, out_names, loss_weights=None):
+    tp = {k: torch.from_numpy(np.array(v)).double() for k, v in params.items()}
+    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=True)
+    outs = ref(k, torch.from_numpy(x).double())
+    total = 0
+    for i, (o, t) in enumerate(zip(outs, targets)):
+        total = total + (loss_weights[i] if loss_weights else 1.0) * keras_loss(losses[i], o, torch.from_numpy(t).double(), logits=k.logits.get(out_names[i]))
+    total.backward()
+    return k, tp, outs, float(total)
+
+
+def _compare(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=None, act_tol=TOL, grad_tol=TOL):
+    model.compile(loss=losses if len(losses) > 1 else losses[0], optimizer=__import__("b2seg.model", fromlist=["Adam"]).Adam(lr), loss_weights=loss_weights)
+    params = model.get_weight_dict()
+    # bf16-representable weights so both paths start from the same numbers
+    params = {k: torch.from_numpy(v).to(torch.bfloat16).float().numpy() if k.endswith("/kernel") else v for k, v in params.items()}
+    model.set_weight_dict(params)
+    N = x.shape[0]
+    loss = model.train_on_batch(x, targets if len(targets) > 1 else targets[0])
+    eng = model._engine(N, True)
+    torch.cuda.synchronize()
+    k, tp, outs, ref_loss = _oracle(ref, ndim, params, x, targets, losses, model.output_names, loss_weights)
+    assert abs(loss - ref_loss) < 2e-2 * max(1.0, abs(ref_loss)), (loss, ref_loss)
+    # outputs + masks
+    for o, want in zip(eng.outputs, outs):
+        got = o["y"].cpu()
+        want = want.detach()
+        if ndim == 1:
+            got = got[:, 0]
+        assert rel_l2(got, want) < act_tol, (o["name"], rel_l2(got, want))
+        if want.shape[-1] == 1:
+            agree = float(((got >= 0.5) == (want >= 0.5)).double().mean())
+        else:
+            agree = float((got.argmax(-1) == want.argmax(-1)).double().mean())
+        assert agree >= 0.999 or o["name"].startswith("level"), (o["name"], agree)
+    # per-layer activations
+    worst = 0.0
+    n_checked = 0
+    for name, (view, C, kind) in eng.planner.taps.items():
+        if name not in k.acts or kind in ("post", "concat"):
+            continue
+        got = eng.tap(name).cpu()
+        if ndim == 1:
+            got = got[:, 0]
+        e = rel_l2(got, k.acts[name].detach())
+        worst = max(worst, e)
+        assert e < act_tol, ("activation", name, e)
+        n_checked += 1
+    assert n_checked >= 5
+    # gradients of raw conv outputs
+    for name, (view, C) in eng.planner.grad_taps.items():
+        if name in k.acts and k.acts[name].grad is not None and eng.planner.taps.get(name, (0, 0, ""))[2] == "raw":
+            got = eng.tap(name, grad=True).cpu()
+            if ndim == 1:
+                got = got[:, 0]
+            e = rel_l2(got, k.acts[name].grad)
+            assert e < 2 * grad_tol, ("activation grad", name, e)
+    # parameter gradients
+    grads = eng.get_grads()
+    gmax = max(float(tp[kk].grad.abs().max()) for kk in grads if tp[kk].grad is not None)
+    for key, g in grads.items():
+        want = tp[key].grad
+        if want is None:
+            assert float(np.abs(g).max()) == 0, key
+            continue
+        if float(want.norm()) < 1e-6 * gmax * want.numel() ** 0.5:
+            assert float(np.abs(g).max()) < 1e-4 * gmax + 1e-7, ("tiny grad", key)
+            continue
+        e = rel_l2(g, want)
+        assert e < 2 * grad_tol, ("param grad", key, e)
+    return worst
+
+
+def test_unet2d_small_end_to_end():
+    torch.manual_seed(0)
+    kw = dict(num_channels=3, output_nums=1, dense_loop=1, is_transconv=True)
+    m = unet_model_builder("UNet", 32, 32, 16, 3, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(0)
+    x = rng.random((4, 32, 32, 3), dtype=np.float32)
+    y = (rng.random((4, 32, 32, 1)) > 0.6).astype(np.float32)
+    _compare(m, Ref2D("UNet", 32, 32, 16, 3, **kw), 2, x, [y], ["bce"])
+
+
+def test_unet2d_cfg2_shape_reduced_batch():
+    """BASELINE config 2 (depth 5, width 64, 3 channels, transposed-conv decoder) at 64x64, batch 2"""
+    kw = dict(num_channels=3, output_nums=1, dense_loop=1, is_transconv=True)
+    m = unet_model_builder("UNet", 64, 64, 64, 5, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(1)
+    x = rng.random((2, 64, 64, 3), dtype=np.float32)
+    y = (rng.random((2, 64, 64, 1)) > 0.7).astype(np.float32)
+    _compare(m, Ref2D("UNet", 64, 64, 64, 5, **kw), 2, x, [y], ["bce"])
+
+
+def test_unet1d_cfg1_shape():
+    """BASELINE config 1: 1D UNet depth 5 width 64, 1 channel, 1024 samples, classification head (2 classes)"""
+    m = UNet(1024, 5, 1, 64, 3, problem_type="Classification", output_nums=2, ds=0, is_transconv=True).UNet()
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, 1024, 1)).astype(np.float32)
+    lab = (x[..., 0] > 0).astype(np.int64)
+    y = np.eye(2, dtype=np.float32)[lab]
+    _compare(m, Ref1D("UNet", 1024, 5, 1, 64, 3, problem_type="Classification", output_nums=2, ds=0), 1, x, [y], ["cce"])
+
+
+def test_training_reduces_loss_and_matches_oracle_trajectory():
+    """three Adam steps: loss trajectory tracks the oracle's (Keras-2 Adam rule, BN moving statistics)"""
+    kw = dict(num_channels=1, output_nums=1, dense_loop=1, is_transconv=True)
+    m = unet_model_builder("UNet", 32, 32, 8, 2, train_mode="from_scratch", **kw).ResNet50()
+    from b2seg.model import Adam
+    m.compile(loss="binary_crossentropy", optimizer=Adam(1e-3))
+    rng = np.random.default_rng(3)
+    x = rng.random((4, 32, 32, 1), dtype=np.float32)
+    y = (x > 0.5).astype(np.float32)
+    params = m.get_weight_dict()
+    tp = {k: torch.from_numpy(v.copy()).double() for k, v in params.items()}
+    ref = Ref2D("UNet", 32, 32, 8, 2, **kw)
+    st = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in tp.items()}
+    got, want = [], []
+    for t in range(1, 4):
+        got.append(m.train_on_batch(x, y))
+        k = KerasRef(2, params=tp, dtype=torch.float64, training=True, strict=True)
+        out = ref(k, torch.from_numpy(x).double())[0]
+        loss = keras_loss("bce", out, torch.from_numpy(y).double(), logits=k.logits["out"])
+        loss.backward()
+        want.append(float(loss))
+        with torch.no_grad():
+            for key in k.trainable:
+                w = tp[key]
+                if w.grad is None:
+                    continue
+                keras_adam_step(w, w.grad, st[key][0], st[key][1], t, lr=1e-3)
+                w.grad = None
+            for key, v in k.new_moving.items():
+                tp[key] = v
+    assert all(abs(a - b) < 3e-2 * max(1.0, abs(b)) for a, b in zip(got, want)), (got, want)
+    assert got[-1] < got[0]
+    mv = m.get_weight_dict()
+    for key in tp:
+        if key.endswith("moving_mean") or key.endswith("moving_variance"):
+            assert rel_l2(mv[key], tp[key]) < 2e-2, key
+
+
+def test_predict_uses_moving_statistics():
+    kw = dict(num_channels=3, output_nums=1, dense_loop=1, is_transconv=True)
+    m = unet_model_builder("UNet", 32, 32, 8, 2, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(4)
+    x = rng.random((5, 32, 32, 3), dtype=np.float32)
+    params = m.get_weight_dict()
+    pred = m.predict(x, batch_size=2)
+    assert pred.shape == (5, 32, 32, 1)
+    tp = {k: torch.from_numpy(v.copy()).double() for k, v in params.items()}
+    k = KerasRef(2, params=tp, dtype=torch.float64, training=False, strict=True)
+    want = Ref2D("UNet", 32, 32, 8, 2, **kw)(k, torch.from_numpy(x).double())[0]
+    assert rel_l2(pred, want) < TOL
+    assert float(((pred >= 0.5) == (want.numpy() >= 0.5)).mean()) >= 0.999

@@ -119,7 +119,7 @@ OP_DESC = {OP_CONV: ConvDesc, OP_WGRAD: WgradDesc, OP_BN_FINALIZE: BnFinalizeDes
 EXPORTED = ["b2seg_last_error", "b2seg_version", "b2seg_device_check", "b2seg_conv", "b2seg_conv_num_mtiles",
             "b2seg_wgrad", "b2seg_bn_finalize", "b2seg_bn_act", "b2seg_bn_bwd", "b2seg_adam", "b2seg_head_fwd",
             "b2seg_head_bwd", "b2seg_loss", "b2seg_eltwise", "b2seg_cast_input", "b2seg_colsum", "b2seg_plan_create",
-            "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_num_launches", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
+            "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
 
 _lib = None
 
@@ -151,6 +151,8 @@ def load():
     lib.b2seg_plan_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.b2seg_plan_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.b2seg_plan_num_launches.argtypes = [C.c_void_p, C.c_int]
+    lib.b2seg_plan_num_ops.argtypes = [C.c_void_p, C.c_int]
+    lib.b2seg_plan_run_timed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int]
     lib.b2seg_plan_set_adam.argtypes = [C.c_void_p, C.c_float, C.c_int64, C.c_float]
     lib.b2seg_plan_destroy.argtypes = [C.c_void_p]
     lib.b2seg_plan_destroy.restype = None

@@ -1,0 +1,152 @@
+"""Device engine: binds a Planner program to B200 memory and replays it through the C ABI (libb2seg.so).
+
+PyTorch is used only for plumbing — device allocation, streams, pinned staging buffers and (multi-GPU)
+torch.distributed/NCCL; every kernel that touches activations, gradients or weights is ours.
+There is no CPU fallback: constructing an Engine without a CUDA sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .graph import Graph
+from .planner import Planner
+
+
+class Engine:
+    def __init__(self, graph: Graph, batch: int, training: bool = True, losses: Optional[List[str]] = None,
+                 loss_weights: Optional[List[float]] = None, adam: Optional[dict] = None, device: Optional[int] = None,
+                 share_params_from: Optional["Engine"] = None):
+        if not torch.cuda.is_available():
+            raise L.B2SegError("b2seg needs a CUDA sm_100 (B200) device: the hot path has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else device
+        self.lib = L.load()
+        L.check(self.lib.b2seg_device_check(self.device), "device_check")
+        self.graph, self.batch, self.training = graph, batch, training
+        self._bufs: Dict[int, torch.Tensor] = {}
+        self._tagged: Dict[str, torch.Tensor] = {}
+        self._shared = share_params_from
+        self.dev = torch.device("cuda", self.device)
+        self.planner = Planner(graph, batch, self._alloc, training=training, losses=losses, loss_weights=loss_weights, adam=adam).build()
+        p = self.planner
+        n = max(p.n_train, 64)
+        self.w = self._typed("param_w", torch.float32, n)
+        self.g = self._typed("param_g", torch.float32, n)
+        self.m = self._typed("param_m", torch.float32, n)
+        self.v = self._typed("param_v", torch.float32, n)
+        self.wb = self._typed("param_wb", torch.bfloat16, n)
+        self.moving = self._typed("moving", torch.float32, max(p.n_moving, 64))
+        self.loss_buf = self._typed("loss", torch.float32, 1)
+        H, W, Cin = graph.inputs[0].shape
+        self.input_shape = (batch, H, W, Cin)
+        self.x_dev = self._typed("input", torch.float32, batch * H * W * Cin).view(batch, H, W, Cin)
+        self.outputs = []
+        for o in sorted(p.outputs, key=lambda o: o["index"]):
+            numel = int(np.prod(o["shape"]))
+            y = self._bufs[o["ptr"]].view(torch.float32)[:numel].view(o["shape"])
+            t = self._bufs[o["target_ptr"]].view(torch.float32)[:numel].view(o["shape"]) if training else None
+            self.outputs.append(dict(name=o["name"], y=y, target=t, shape=o["shape"]))
+        self.plan = C.c_void_p()
+        L.check(self.lib.b2seg_plan_create(C.byref(self.plan)), "plan_create")
+        for phase in (0, 1, 2):
+            for (op, desc, note) in p.ops[phase]:
+                rc = self.lib.b2seg_plan_add(self.plan, phase, op, C.byref(desc), C.sizeof(desc))
+                L.check(rc, f"plan_add[{note}]")
+        self.launches = [self.lib.b2seg_plan_num_launches(self.plan, ph) for ph in (0, 1, 2)]
+        self.step = 0
+
+    # ---- memory ------------------------------------------------------------------------------------------
+    def _alloc(self, nbytes, tag):
+        if self._shared is not None and tag in ("param_w", "param_g", "param_m", "param_v", "param_wb", "moving"):
+            t = self._shared._tagged[tag]
+            assert t.numel() >= nbytes
+        else:
+            t = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+        self._bufs[t.data_ptr()] = t
+        if tag in ("param_w", "param_g", "param_m", "param_v", "param_wb", "moving", "loss", "input"):
+            self._tagged[tag] = t
+        return t.data_ptr()
+
+    def _typed(self, tag, dtype, numel):
+        return self._tagged[tag].view(dtype)[:numel]
+
+    def memory_bytes(self):
+        return sum(t.numel() for t in self._bufs.values())
+
+    # ---- weights -----------------------------------------------------------------------------------------
+    def set_weights(self, params: Dict[str, np.ndarray], strict=True):
+        p = self.planner
+        w_host = self.w.cpu().numpy()
+        mov_host = self.moving.cpu().numpy()
+        for e in p.params:
+            if e.key not in params:
+                if strict:
+                    raise KeyError(f"missing weight {e.key}")
+                continue
+            arr = np.asarray(params[e.key], np.float32)
+            if tuple(arr.shape) != tuple(e.keras_shape):
+                raise ValueError(f"weight {e.key}: shape {arr.shape} != {e.keras_shape}")
+            flat = p.to_internal(e.key, arr)
+            (w_host if e.trainable else mov_host)[e.offset:e.offset + e.size] = flat
+        self.w.copy_(torch.from_numpy(w_host))
+        self.moving.copy_(torch.from_numpy(mov_host))
+        self.wb.copy_(self.w.to(torch.bfloat16))
+
+    def get_weights(self) -> Dict[str, np.ndarray]:
+        p = self.planner
+        w_host, mov_host = self.w.cpu().numpy(), self.moving.cpu().numpy()
+        return {e.key: p.from_internal(e.key, (w_host if e.trainable else mov_host)[e.offset:e.offset + e.size]) for e in p.params}
+
+    def get_grads(self) -> Dict[str, np.ndarray]:
+        p = self.planner
+        g_host = self.g.cpu().numpy()
+        return {e.key: p.from_internal(e.key, g_host[e.offset:e.offset + e.size]) for e in p.params if e.trainable}
+
+    def reset_optimizer(self):
+        self.m.zero_()
+        self.v.zero_()
+        self.step = 0
+
+    # ---- execution ---------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def run(self, phase):
+        L.check(self.lib.b2seg_plan_run(self.plan, phase, C.c_void_p(self._stream())), f"plan_run[{phase}]")
+
+    def forward(self):
+        self.run(0)
+
+    def backward(self):
+        self.run(1)
+
+    def optimizer_step(self, lr: float, grad_scale: float = 1.0):
+        self.step += 1
+        L.check(self.lib.b2seg_plan_set_adam(self.plan, lr, self.step, grad_scale), "set_adam")
+        self.run(2)
+
+    def tap(self, name: str, grad=False) -> torch.Tensor:
+        """activation (or raw-conv-output gradient) of a layer as an fp32 NHWC tensor with logical channels"""
+        p = self.planner
+        view, Cn = (p.grad_taps[name] if grad else p.taps[name][:2])
+        base = None
+        for ptr, t in self._bufs.items():
+            if ptr <= view.ptr < ptr + t.numel():
+                base = t
+                break
+        off = (view.ptr - base.data_ptr()) // 2
+        flat = base.view(torch.bfloat16)
+        out = torch.as_strided(flat, (view.N, view.H, view.W, view.C), (view.sn, view.sh, view.sw, 1), off)
+        return out[..., :Cn].float()
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None) is not None and self.plan.value:
+                self.lib.b2seg_plan_destroy(self.plan)
+                self.plan = C.c_void_p()
+        except Exception:
+            pass

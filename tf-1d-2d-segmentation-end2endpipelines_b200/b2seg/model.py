@@ -1,0 +1,356 @@
+"""Keras-`Model`-shaped facade over the B200 engine: the object the builder classes return.
+
+Mirrors the subset of the tf.keras.Model protocol the reference's callers use:
+compile / fit / predict / train_on_batch / evaluate / load_weights / save_weights / get_weights / set_weights /
+summary / count_params / trainable_weights / non_trainable_weights  (2DCNN/Train.py:322-415, Test.py:114-164,
+1DCNN/1D_Segmentation.ipynb cells 35-41).  Inputs/outputs are NumPy float32 channels-last arrays; with deep
+supervision `predict` returns the list [out, level1, ..., level_d] like Keras.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .graph import Graph, init_params
+
+_LOSS_ALIASES = {
+    "binary_crossentropy": "bce", "bce": "bce", "binarycrossentropy": "bce",
+    "categorical_crossentropy": "cce", "cce": "cce", "categoricalcrossentropy": "cce",
+    "mean_squared_error": "mse", "mse": "mse", "meansquarederror": "mse",
+    "mean_absolute_error": "mae", "mae": "mae", "meanabsoluteerror": "mae",
+}
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(learning_rate, beta_1, beta_2, epsilon) (utils/tf_optimizers.py:11)."""
+
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, amsgrad=False, **kw):
+        if amsgrad:
+            raise NotImplementedError("amsgrad=True is outside the hot-path scope")
+        self.learning_rate = float(kw.get("lr", learning_rate))
+        self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
+
+
+class _WeightRef:
+    def __init__(self, name, shape):
+        self.name, self.shape = name, tuple(shape)
+
+    def get_shape(self):
+        return self.shape
+
+
+class History:
+    def __init__(self):
+        self.history: Dict[str, List[float]] = {}
+        self.epoch: List[int] = []
+
+
+def _loss_name(obj) -> str:
+    if isinstance(obj, str):
+        key = obj.lower().replace(" ", "")
+    else:
+        key = getattr(obj, "name", None) or type(obj).__name__
+        key = key.lower()
+    if key not in _LOSS_ALIASES:
+        raise NotImplementedError(f"loss '{obj}' is outside the hot-path scope (supported: bce, cce, mse, mae)")
+    return _LOSS_ALIASES[key]
+
+
+class Model:
+    def __init__(self, graph: Graph):
+        self.graph = graph
+        self.name = graph.name
+        self.output_names = [n.name for n in graph.outputs]
+        self._weights: Dict[str, np.ndarray] = init_params(graph)
+        self._engines: Dict[tuple, object] = {}
+        self._primary = None
+        self._losses: Optional[List[str]] = None
+        self._loss_weights: Optional[List[float]] = None
+        self.optimizer: Optional[Adam] = None
+        self.stop_training = False
+        self.world_size = 1
+        self._dist = None
+
+    # ---- introspection -----------------------------------------------------------------------------------
+    @property
+    def input_shape(self):
+        H, W, C = self.graph.inputs[0].shape
+        return (None, H, W, C) if self.graph.ndim == 2 else (None, W, C)
+
+    @property
+    def trainable_weights(self):
+        return [_WeightRef(f"{l}/{w}", s) for (l, w, s, _, t) in self.graph.param_specs() if t]
+
+    @property
+    def non_trainable_weights(self):
+        return [_WeightRef(f"{l}/{w}", s) for (l, w, s, _, t) in self.graph.param_specs() if not t]
+
+    def count_params(self):
+        return sum(self.graph.count_params())
+
+    def summary(self, print_fn=print):
+        print_fn(f'Model: "{self.name}"')
+        print_fn(f"{'Layer (type)':<40}{'Output Shape':<28}{'Param #':>12}")
+        per_layer: Dict[str, int] = {}
+        for (l, _, s, _, _) in self.graph.param_specs():
+            per_layer[l] = per_layer.get(l, 0) + int(np.prod(s))
+        for n in self.graph.nodes:
+            shp = (None,) + (n.shape if self.graph.ndim == 2 else n.shape[1:])
+            print_fn(f"{(n.name + ' (' + n.op + ')'):<40}{str(shp):<28}{per_layer.get(n.name, 0):>12}")
+        tr, nt = self.graph.count_params()
+        print_fn(f"Total params: {tr + nt}\nTrainable params: {tr}\nNon-trainable params: {nt}")
+
+    # ---- weights -----------------------------------------------------------------------------------------
+    def _sync_from_device(self):
+        if self._primary is not None:
+            self._weights = self._primary.get_weights()
+
+    def get_weight_dict(self) -> Dict[str, np.ndarray]:
+        self._sync_from_device()
+        return {k: v.copy() for k, v in self._weights.items()}
+
+    def set_weight_dict(self, params: Dict[str, np.ndarray]):
+        for k, v in params.items():
+            if k not in self._weights:
+                raise KeyError(f"unknown weight {k}")
+            if tuple(np.shape(v)) != self._weights[k].shape:
+                raise ValueError(f"weight {k}: shape {np.shape(v)} != {self._weights[k].shape}")
+            self._weights[k] = np.asarray(v, np.float32).copy()
+        if self._primary is not None:
+            self._primary.set_weights(self._weights)
+
+    def get_weights(self):
+        self._sync_from_device()
+        return [self._weights[f"{l}/{w}"].copy() for (l, w, _, _, _) in self.graph.param_specs()]
+
+    def set_weights(self, weights):
+        specs = self.graph.param_specs()
+        if len(weights) != len(specs):
+            raise ValueError(f"You called `set_weights(weights)` with a weight list of length {len(weights)}, but the model was expecting {len(specs)} weights.")
+        self.set_weight_dict({f"{l}/{w}": a for (l, w, _, _, _), a in zip(specs, weights)})
+
+    def save_weights(self, path):
+        self._sync_from_device()
+        np.savez(path if str(path).endswith(".npz") else str(path) + ".npz", **{k.replace("/", "::"): v for k, v in self._weights.items()})
+
+    def load_weights(self, path):
+        p = str(path)
+        if not os.path.exists(p) and os.path.exists(p + ".npz"):
+            p = p + ".npz"
+        if p.endswith(".h5") or p.endswith(".keras"):
+            raise NotImplementedError("Keras .h5/.keras weight files: SURVEY §8(f) rank 1 (next); use the .npz produced by save_weights")
+        with np.load(p) as z:
+            self.set_weight_dict({k.replace("::", "/"): z[k] for k in z.files})
+
+    # ---- compile -----------------------------------------------------------------------------------------
+    def compile(self, loss=None, optimizer=None, metrics=None, loss_weights=None, **kw):
+        names = self.output_names
+        if isinstance(loss, dict):
+            self._losses = [_loss_name(loss[n]) for n in names]
+        elif isinstance(loss, (list, tuple)):
+            self._losses = [_loss_name(l) for l in loss]
+        else:
+            self._losses = [_loss_name(loss)] * len(names)
+        if loss_weights is None:
+            self._loss_weights = [1.0] * len(names)
+        elif isinstance(loss_weights, dict):
+            self._loss_weights = [float(loss_weights.get(n, 1.0)) for n in names]
+        else:
+            self._loss_weights = [float(w) for w in loss_weights]
+        if optimizer is None or (isinstance(optimizer, str) and optimizer.lower() == "adam"):
+            optimizer = Adam()
+        if not isinstance(optimizer, Adam):
+            if hasattr(optimizer, "learning_rate") and type(optimizer).__name__ == "Adam":
+                optimizer = Adam(float(optimizer.learning_rate), getattr(optimizer, "beta_1", 0.9), getattr(optimizer, "beta_2", 0.999),
+                                 getattr(optimizer, "epsilon", 1e-7))
+            else:
+                raise NotImplementedError("only the Adam optimizer is inside the hot-path scope (utils/tf_optimizers.py:11)")
+        self.optimizer = optimizer
+        self.metrics = metrics or []
+        self._engines = {k: e for k, e in self._engines.items() if not k[1]}
+
+    # ---- engines -----------------------------------------------------------------------------------------
+    def _engine(self, batch: int, training: bool):
+        from .engine import Engine
+        key = (batch, training)
+        if key not in self._engines:
+            adam = None
+            if training:
+                if self._losses is None:
+                    raise RuntimeError("You must compile your model before training/testing. Use `model.compile(optimizer, loss)`.")
+                o = self.optimizer
+                adam = dict(lr=o.learning_rate, beta1=o.beta_1, beta2=o.beta_2, eps=o.epsilon)
+            eng = Engine(self.graph, batch, training=training, losses=self._losses, loss_weights=self._loss_weights, adam=adam,
+                         share_params_from=self._primary)
+            if self._primary is None:
+                self._primary = eng
+                eng.set_weights(self._weights)
+            self._engines[key] = eng
+        return self._engines[key]
+
+    def _to_nhwc(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        if self.graph.ndim == 1:
+            if a.ndim != 3:
+                raise ValueError(f"expected input of rank 3 (N, length, channels), got shape {a.shape}")
+            return a[:, None, :, :]
+        if a.ndim != 4:
+            raise ValueError(f"expected input of rank 4 (N, H, W, channels), got shape {a.shape}")
+        return a
+
+    def _targets(self, y) -> List[np.ndarray]:
+        if isinstance(y, dict):
+            ys = [y[n] for n in self.output_names]
+        elif isinstance(y, (list, tuple)):
+            ys = list(y)
+        else:
+            ys = [y]
+        if len(ys) != len(self.output_names):
+            raise ValueError(f"expected {len(self.output_names)} target arrays, got {len(ys)}")
+        return [self._to_nhwc(t) for t in ys]
+
+    # ---- data parallel (one process per GPU; torch.distributed/NCCL only moves the flat gradient arena) -----
+    def distribute(self, process_group=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dist = dist
+        self._pg = process_group
+        self.world_size = dist.get_world_size(process_group)
+        return self
+
+    def broadcast_weights(self, src=0):
+        eng = self._primary
+        if eng is None:
+            raise RuntimeError("build an engine first (train_on_batch / predict)")
+        for t in (eng.w, eng.moving, eng.m, eng.v):
+            self._dist.broadcast(t, src, group=self._pg)
+        eng.wb.copy_(eng.w.to(eng.wb.dtype))
+
+    # ---- train / predict ---------------------------------------------------------------------------------
+    def train_on_batch(self, x, y, return_loss=True):
+        import torch
+        xs = self._to_nhwc(x)
+        ys = self._targets(y)
+        eng = self._engine(xs.shape[0], True)
+        eng.x_dev.copy_(torch.from_numpy(xs), non_blocking=True)
+        for o, t in zip(eng.outputs, ys):
+            if tuple(t.shape) != tuple(o["shape"]):
+                raise ValueError(f"target for '{o['name']}' has shape {t.shape}, expected {o['shape']}")
+            o["target"].copy_(torch.from_numpy(t), non_blocking=True)
+        return self._step(eng, return_loss)
+
+    def _step(self, eng, return_loss=True):
+        eng.forward()
+        eng.backward()
+        scale = 1.0
+        if self.world_size > 1:
+            self._dist.all_reduce(eng.g, group=self._pg)
+            scale = 1.0 / self.world_size
+        eng.optimizer_step(self.optimizer.learning_rate, scale)
+        if return_loss:
+            return float(eng.loss_buf.item())
+        return None
+
+    def predict(self, x, batch_size=None, verbose=0, **kw):
+        import torch
+        xs = self._to_nhwc(x)
+        n = xs.shape[0]
+        bs = int(batch_size) if batch_size else min(n, 32)
+        bs = max(1, min(bs, n))
+        eng = self._engine(bs, False)
+        outs = [np.empty((n,) + tuple(o["shape"][1:]), np.float32) for o in eng.outputs]
+        for s in range(0, n, bs):
+            chunk = xs[s:s + bs]
+            m = chunk.shape[0]
+            if m < bs:
+                chunk = np.concatenate([chunk, np.zeros((bs - m,) + chunk.shape[1:], np.float32)], 0)
+            eng.x_dev.copy_(torch.from_numpy(chunk), non_blocking=True)
+            eng.forward()
+            for i, o in enumerate(eng.outputs):
+                outs[i][s:s + m] = o["y"][:m].cpu().numpy()
+        if self.graph.ndim == 1:
+            outs = [o[:, 0] for o in outs]
+        return outs if len(outs) > 1 else outs[0]
+
+    def evaluate(self, x, y, batch_size=32, verbose=0, **kw):
+        """mean of the compiled (weighted) loss over batches, computed on the host from predict()"""
+        ys = self._targets(y)
+        pred = self.predict(x, batch_size=batch_size)
+        pred = pred if isinstance(pred, list) else [pred]
+        total = 0.0
+        for p, t, kind, w in zip(pred, ys, self._losses, self._loss_weights):
+            t = t[:, 0] if self.graph.ndim == 1 else t
+            p = p.astype(np.float64)
+            if kind == "bce":
+                pc = np.clip(p, 1e-7, 1 - 1e-7)
+                l = -(t * np.log(pc) + (1 - t) * np.log(1 - pc)).mean()
+            elif kind == "cce":
+                l = -(t * np.log(np.clip(p, 1e-7, 1))).sum(-1).mean()
+            elif kind == "mse":
+                l = ((p - t) ** 2).mean()
+            else:
+                l = np.abs(p - t).mean()
+            total += w * float(l)
+        return total
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, callbacks=None, validation_data=None, shuffle=True,
+            initial_epoch=0, steps_per_epoch=None, **kw):
+        hist = History()
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin({})
+        sequence = x if (y is None and hasattr(x, "__getitem__") and hasattr(x, "__len__") and not isinstance(x, np.ndarray)) else None
+        if sequence is None:
+            xs = np.asarray(x, np.float32)
+            ys = self._targets(y)
+            bs = int(batch_size or 32)
+            n = xs.shape[0]
+        rng = np.random.default_rng(0)
+        self.stop_training = False
+        for ep in range(initial_epoch, epochs):
+            t0 = time.time()
+            losses = []
+            if sequence is not None:
+                for bi in range(len(sequence)):
+                    bx, by = sequence[bi][:2]
+                    losses.append(self.train_on_batch(bx, by))
+                if hasattr(sequence, "on_epoch_end"):
+                    sequence.on_epoch_end()
+            else:
+                order = rng.permutation(n) if shuffle else np.arange(n)
+                for s in range(0, n, bs):
+                    idx = order[s:s + bs]
+                    by = [t[idx][:, 0] if self.graph.ndim == 1 else t[idx] for t in ys]
+                    losses.append(self.train_on_batch(xs[idx], by if len(by) > 1 else by[0]))
+                    if steps_per_epoch and len(losses) >= steps_per_epoch:
+                        break
+            logs = {"loss": float(np.mean(losses))}
+            if validation_data is not None:
+                vx, vy = validation_data[:2]
+                logs["val_loss"] = self.evaluate(vx, vy, batch_size=batch_size or 32)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            hist.epoch.append(ep)
+            if verbose:
+                print(f"Epoch {ep + 1}/{epochs} - {time.time() - t0:.1f}s - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(ep, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            if hasattr(cb, "on_train_end"):
+                cb.on_train_end({})
+        self.history = hist
+        return hist
+
+    # ---- parity taps --------------------------------------------------------------------------------------
+    def layer_output(self, name, batch, training=True, grad=False):
+        return self._engine(batch, training).tap(name, grad=grad)

@@ -1,0 +1,294 @@
+"""1D builder API — drop-in for the reference's TensorFlow/1DCNN/Models/unet_variants.py:222-897 (class UNet:
+UNet, UNetE, UNetP, UNetPP, UNet3P, MultiResUNet) and TensorFlow/1DCNN/Models/BCDUNet.py:79-174 (class BCDUNet).
+
+Same constructor arguments and method names; the methods return a b2seg.model.Model.  1D tensors (L, C) are held
+as (H=1, W=L, C).  Differences from the 2D family that matter for parity: two Conv-BN-ReLU per level,
+Conv1DTranspose(k=2, s=2) + BN + ReLU, nearest up-sampling, glorot_uniform initialisers, `problem_type` head.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .graph import Graph
+
+
+def conv_block(g: Graph, x, model_width, kernel, multiplier, use_batchnorm=True):           # uv.py:53-60
+    x = g.conv(x, model_width * multiplier, kernel, padding="same")
+    if use_batchnorm:
+        x = g.bn(x)
+    return g.act(x, "relu")
+
+
+def trans_conv1d(g: Graph, x, model_width, multiplier):                                      # uv.py:102-108
+    return g.act(g.bn(g.tconv(x, model_width * multiplier, 2, 2, padding="same")), "relu")
+
+
+def up_conv_block(g: Graph, x, size=2):                                                      # uv.py:120-124
+    return g.up(x, size, interpolation="nearest")
+
+
+def feature_extraction_block(g: Graph, x, model_width, feature_number):                      # uv.py:127-135
+    _, Ln, _ = x.shape
+    z = g.dense(g.flatten(x), feature_number, name="features")
+    z = g.dense(z, model_width * Ln)
+    return g.reshape(z, 1, Ln, model_width)
+
+
+def attention_block(g: Graph, skip, gate, num_filters, multiplier):                          # uv.py:154-170
+    a = g.bn(g.conv(skip, num_filters * multiplier, 1, strides=2))
+    b = g.bn(g.conv(gate, num_filters * multiplier, 1, strides=1))
+    c = g.act(g.add([a, b]), "relu")
+    c = g.act(g.bn(g.conv(c, 1, 1, strides=1)), "sigmoid")
+    r1 = up_conv_block(g, c)
+    r2 = trans_conv1d(g, c, 1, 1)
+    return g.mul(skip, g.add([r1, r2]))
+
+
+def multires_block(g: Graph, x, model_width, kernel, multiplier, alpha):                     # uv.py:173-193
+    w = alpha * model_width
+    a, b, c = int(w * 0.167), int(w * 0.333), int(w * 0.5)
+    shortcut = conv_block(g, x, a + b + c, 1, multiplier)
+    c3 = conv_block(g, x, a, kernel, multiplier)
+    c5 = conv_block(g, c3, b, kernel, multiplier)
+    c7 = conv_block(g, c5, c, kernel, multiplier)
+    out = g.bn(g.concat([c3, c5, c7]))
+    return g.bn(g.act(g.add([shortcut, out]), "relu"))
+
+
+def res_path(g: Graph, x, length, model_width, kernel, multiplier):                          # uv.py:196-219
+    out = x
+    for _ in range(max(int(length), 1)):
+        shortcut = conv_block(g, out, model_width, 1, multiplier)
+        o = conv_block(g, out, model_width, kernel, multiplier)
+        out = g.bn(g.act(g.add([shortcut, o]), "relu"))
+    return out
+
+
+def _merge(g: Graph, skip, up, extra, lstm, lstm_filters, expect_c):
+    if lstm == 1:
+        if skip.C != expect_c or up.C != expect_c:
+            raise ValueError(f"total size of new array must be unchanged, input_shape = {[up.shape[1], up.C]}, output_shape = [1, {up.shape[1]}, {expect_c}]")
+        return g.convlstm([skip, up] + ([extra] if extra is not None else []), int(np.int32(lstm_filters)), 3)
+    return g.concat([up] + ([extra] if extra is not None else []) + [skip])
+
+
+class UNet:
+    """Reference signature: 1DCNN/Models/unet_variants.py:222-253 (note ds defaults to 1)."""
+
+    def __init__(self, length, model_depth, num_channel, model_width, kernel_size, problem_type="Regression", output_nums=1, ds=1,
+                 ae=0, ag=0, lstm=0, alpha=1, t=2, feature_number=1024, is_transconv=True, q=3):
+        self.length = length
+        self.model_depth = model_depth
+        self.num_channel = num_channel
+        self.model_width = model_width
+        self.kernel_size = kernel_size
+        self.problem_type = problem_type
+        self.output_nums = output_nums
+        self.D_S = ds
+        self.A_E = ae
+        self.A_G = ag
+        self.LSTM = lstm
+        self.alpha = alpha
+        self.feature_number = feature_number
+        self.is_transconv = is_transconv
+        self.t = t
+        self.q = q
+
+    # -- shared pieces ----------------------------------------------------------------------------------------
+    def _check(self):
+        if self.length == 0 or self.model_depth == 0 or self.model_width == 0 or self.num_channel == 0 or self.kernel_size == 0:
+            raise ValueError("Please Check the Values of the Input Parameters!")
+
+    def _encoder(self, g):
+        W, k, d = self.model_width, self.kernel_size, self.model_depth
+        x = g.input(1, self.length, self.num_channel)
+        pool, convs = x, []
+        for i in range(1, d + 1):
+            conv = conv_block(g, pool, W, k, 2 ** (i - 1))
+            conv = conv_block(g, conv, W, k, 2 ** (i - 1))
+            pool = g.pool(conv, 2)
+            convs.append(conv)
+        if self.A_E == 1:
+            pool = feature_extraction_block(g, pool, W, self.feature_number)
+        conv = conv_block(g, pool, W, k, 2 ** d)
+        conv = conv_block(g, conv, W, k, 2 ** d)
+        return convs, conv
+
+    def _up(self, g, x, mult):
+        return trans_conv1d(g, x, self.model_width, mult) if self.is_transconv else up_conv_block(g, x)
+
+    def _finish(self, g, deconv, levels):
+        if self.problem_type == "Classification":
+            out = g.conv(deconv, self.output_nums, 1, activation="softmax", name="out")
+        elif self.problem_type == "Regression":
+            out = g.conv(deconv, self.output_nums, 1, activation="linear", name="out")
+        else:
+            # the reference leaves `outputs = []` and tf.keras.Model rejects it
+            raise ValueError("Output tensors of a Functional model must be the output of a TensorFlow `Layer`")
+        outputs = list(reversed(levels + [out])) if self.D_S == 1 else [out]
+        from .model import Model
+        return Model(g.finalize(outputs, "model"))
+
+    # -- builders ---------------------------------------------------------------------------------------------
+    def UNet(self):                                                                           # uv.py:255-319
+        self._check()
+        W, k, d = self.model_width, self.kernel_size, self.model_depth
+        g = Graph(1)
+        convs, deconv = self._encoder(g)
+        levels = []
+        for j in range(d):
+            l = d - j - 1
+            skip = convs[l]
+            if self.A_G == 1:
+                skip = attention_block(g, convs[l], deconv, W, 2 ** l)
+            if self.D_S == 1:
+                levels.append(g.conv(deconv, 1, 1, name=f"level{d - j}"))
+            deconv = self._up(g, deconv, 2 ** l)
+            deconv = _merge(g, skip, deconv, None, self.LSTM, W * 2.0 ** (l - 1), W * 2 ** l)
+            deconv = conv_block(g, deconv, W, k, 2 ** l)
+            deconv = conv_block(g, deconv, W, k, 2 ** l)
+        return self._finish(g, deconv, levels)
+
+    def _nested(self, variant):                                                               # uv.py:321-645
+        self._check()
+        W, k, d = self.model_width, self.kernel_size, self.model_depth
+        g = Graph(1)
+        convs, bottom = self._encoder(g)
+        skips = convs + [bottom]
+        levels = []
+        if self.D_S == 1:
+            levels.append(g.conv(convs[0], 1, 1, name=f"level{d}"))
+        X = {}
+        for i in range(1, d + 1):
+            for j in range(0, d - i + 1):
+                below = skips[j + 1] if i == 1 else X[(j + 1, i - 1)]
+                gated = (lambda t: attention_block(g, t, below, W, 2 ** j)) if self.A_G == 1 else (lambda t: t)
+                extra = None
+                if i == 1 or variant == "UNetE":
+                    skip = gated(skips[j])
+                elif variant == "UNetP":
+                    skip = gated(X[(j, i - 1)])
+                else:
+                    parts = [gated(X[(j, q)]) for q in range(1, i)]
+                    extra = parts[0] if len(parts) == 1 else g.concat(parts)
+                    skip = gated(skips[j])
+                up = self._up(g, below, 2 ** j)
+                node = _merge(g, skip, up, extra, self.LSTM, W * 2.0 ** (j - 1), W * 2 ** j)
+                node = conv_block(g, node, W, k, 2 ** j)
+                node = conv_block(g, node, W, k, 2 ** j)
+                X[(j, i)] = node
+                if self.D_S == 1 and j == 0 and i < d:
+                    levels.append(g.conv(node, 1, 1, name=f"level{d - i}"))
+        return self._finish(g, X[(0, d)], levels)
+
+    def UNetE(self):
+        return self._nested("UNetE")
+
+    def UNetP(self):
+        return self._nested("UNetP")
+
+    def UNetPP(self):
+        return self._nested("UNetPP")
+
+    def UNet3P(self):                                                                         # uv.py:647-715
+        self._check()
+        W, k, d = self.model_width, self.kernel_size, self.model_depth
+        g = Graph(1)
+        convs, deconv = self._encoder(g)
+        levels, decs = [], {}
+        for j in range(d):
+            parts = [conv_block(g, convs[d - j - 1], W, k, 1)]
+            for q in range(0, d - j - 1):
+                parts.append(conv_block(g, g.pool(convs[q], 2 ** ((d - j) - q - 1)), W, k, 1))
+            parts.append(g.act(up_conv_block(g, conv_block(g, deconv, W, k, 1), 2), "sigmoid"))
+            for m in range(j):
+                parts.append(g.act(up_conv_block(g, conv_block(g, decs[m], W, k, 1), 2 ** (j - m)), "sigmoid"))
+            deconv = conv_block(g, g.concat(parts), W, k, d + 1)
+            decs[j] = deconv
+            if self.D_S == 1:
+                levels.append(g.conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
+        return self._finish(g, deconv, levels)
+
+    def MultiResUNet(self):                                                                   # uv.py:836-897
+        self._check()
+        W, k, d = self.model_width, self.kernel_size, self.model_depth
+        g = Graph(1)
+        x = g.input(1, self.length, self.num_channel)
+        pool, paths = x, []
+        for i in range(1, d + 1):
+            blk = multires_block(g, pool, W, k, 2 ** (i - 1), self.alpha)
+            pool = g.pool(blk, 2)
+            paths.append(res_path(g, blk, d - i + 1, W, k, 2 ** (i - 1)))
+        if self.A_E == 1:
+            pool = feature_extraction_block(g, pool, W, self.feature_number)
+        deconv = multires_block(g, pool, W, k, 2 ** d, self.alpha)
+        levels = []
+        for j in range(d):
+            l = d - j - 1
+            skip = paths[l]
+            if self.A_G == 1:
+                skip = attention_block(g, paths[l], deconv, W, 2 ** l)
+            if self.D_S == 1:
+                levels.append(g.conv(deconv, 1, 1, name=f"level{d - j}"))
+            deconv = self._up(g, deconv, 2 ** l)
+            deconv = _merge(g, skip, deconv, None, self.LSTM, W * 2.0 ** (l - 1), W * 2 ** l)
+            deconv = multires_block(g, deconv, W, k, 2 ** l, self.alpha)
+        return self._finish(g, deconv, levels)
+
+
+class BCDUNet:
+    """Reference signature: 1DCNN/Models/BCDUNet.py:79-109; builder :111-174."""
+
+    def __init__(self, length, model_depth, num_channel, model_width, kernel_size, problem_type="Regression", output_nums=1, ds=1,
+                 ae=0, ag=0, lstm=0, dense_loop=1, feature_number=1024, is_transconv=True):
+        self.length = length
+        self.model_depth = model_depth
+        self.num_channel = num_channel
+        self.model_width = model_width
+        self.kernel_size = kernel_size
+        self.problem_type = problem_type
+        self.output_nums = output_nums
+        self.D_S = ds
+        self.A_E = ae
+        self.A_G = ag
+        self.LSTM = lstm
+        self.dense_loop = dense_loop
+        self.feature_number = feature_number
+        self.is_transconv = is_transconv
+
+    def BCDUNet(self):
+        if self.length == 0 or self.model_depth == 0 or self.model_width == 0 or self.num_channel == 0 or self.kernel_size == 0:
+            raise ValueError("Please Check the Values of the Input Parameters!")
+        W, k, d = self.model_width, self.kernel_size, self.model_depth
+        g = Graph(1)
+        x = g.input(1, self.length, self.num_channel)
+        pool, convs = x, []
+        for i in range(1, d + 1):
+            conv = conv_block(g, pool, W, k, 2 ** (i - 1))
+            conv = conv_block(g, conv, W, k, 2 ** (i - 1))
+            pool = g.pool(conv, 2)
+            convs.append(conv)
+        conv = pool
+        for _ in range(self.dense_loop - 1):                       # bcd.py:70-76: concat-dense, two convs per loop
+            cb = conv_block(g, conv, W, k, 2 ** d)
+            cb = conv_block(g, cb, W, k, 2 ** d)
+            conv = g.concat([conv, cb])
+        if self.A_E == 1:
+            conv = feature_extraction_block(g, conv, W, self.feature_number)
+        conv = conv_block(g, conv, W, k, 2 ** d)
+        conv = conv_block(g, conv, W, k, 2 ** d)
+        deconv, levels = conv, []
+        for j in range(d):
+            l = d - j - 1
+            skip = convs[l]
+            if self.A_G == 1:
+                skip = attention_block(g, convs[l], deconv, W, 2 ** l)
+            if self.D_S == 1:
+                levels.append(g.conv(deconv, 1, 1, name=f"level{d - j}"))
+            deconv = trans_conv1d(g, deconv, W, 2 ** l) if self.is_transconv else up_conv_block(g, deconv)
+            if self.LSTM == 1:  # with lstm == 0 the reference silently drops the skip connection (bcd.py:152-158)
+                deconv = _merge(g, skip, deconv, None, 1, W * 2.0 ** (l - 1), W * 2 ** l)
+            deconv = conv_block(g, deconv, W, k, 2 ** l)
+            deconv = conv_block(g, deconv, W, k, 2 ** l)
+        helper = UNet(self.length, d, self.num_channel, W, k, self.problem_type, self.output_nums, self.D_S)
+        return helper._finish(g, deconv, levels)

@@ -1,0 +1,685 @@
+"""Planner: lowers a layer graph (b2seg.graph.Graph) to the flat list of C-ABI descriptors a b2seg plan replays.
+
+It plays the role TensorFlow's graph executor + autodiff play for the reference (Model.fit / Model.predict on the
+graphs of 2DCNN/models/unet_variants.py and 1DCNN/Models/unet_variants.py):
+
+* fuses Conv -> BatchNormalization -> Activation (-> MaxPooling) chains into
+  [tcgen05 conv + statistics] -> [finalize] -> [apply + act (+ pool)],
+* realises `concatenate` by handing producers channel windows of one NHWC buffer (no copy),
+* emits the backward pass (BN/activation backward with gradient-source summation and max-pool routing, dgrad,
+  wgrad, bias gradients, head + loss seed) in reverse order, and the fused Adam update,
+* lays all trainable weights out in one flat fp32 arena (+ bf16 shadow) in kernel-friendly layouts and records how
+  each maps back to the Keras layout for weight exchange by layer name.
+
+The planner only does address arithmetic through an `alloc(nbytes) -> int` callback, so the same plan can be bound to
+device memory (b2seg.engine) or to the CPU descriptor emulator used by the CPU tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from . import lowering as lw
+from .graph import Graph, Node
+from .lowering import TView
+
+
+def ceil8(c):
+    return (c + 7) // 8 * 8
+
+
+def pick_box(N, H, W, pixels):
+    """Mirror of b2::pick_box (csrc/conv_gemm.cu): (bw, bh, bn) with bw*bh*bn == pixels."""
+    def best(extent, cap):
+        d = 1
+        while d * 2 <= cap and extent % (d * 2) == 0:
+            d <<= 1
+        if d >= 8 or d == extent:
+            return d
+        p = 1
+        while p < extent and p < cap:
+            p <<= 1
+        return p
+    w = best(W, pixels)
+    h = best(H, pixels // w)
+    return w, h, pixels // (w * h)
+
+
+def conv_num_mtiles(N, H, W):
+    bw, bh, bn = pick_box(N, H, W, 128)
+    return -(-W // bw) * -(-H // bh) * -(-N // bn)
+
+
+# ----------------------------------------------------------------------------------------------------------
+@dataclass
+class ParamEntry:
+    key: str                 # "layer/weight" (Keras names)
+    keras_shape: Tuple[int, ...]
+    kind: str                # conv | tconv | vec | head | dense
+    offset: int              # element offset into the flat arenas (trainable) or the moving-stat arena
+    size: int                # padded element count
+    trainable: bool
+    meta: dict = field(default_factory=dict)
+
+
+@dataclass
+class Phys:
+    """Physical realisation of a logical tensor: a bf16 view + map from logical channels to physical channels."""
+    view: TView
+    C: int
+    segs: List[Tuple[int, int]]  # [(physical offset, count)] in logical channel order
+
+    @property
+    def Cp(self):
+        return self.view.C
+
+
+@dataclass
+class GSrc:
+    view: TView
+    kind: int = 0      # 0 direct, 1 pooled
+    pool: Tuple[int, int] = (1, 1)
+    premasked: bool = False
+
+
+class PlanError(NotImplementedError):
+    pass
+
+
+LOSS_KINDS = {"bce": 0, "binary_crossentropy": 0, "cce": 1, "categorical_crossentropy": 1, "mse": 2, "mean_squared_error": 2,
+              "mae": 3, "mean_absolute_error": 3}
+
+
+class Planner:
+    def __init__(self, graph: Graph, batch: int, alloc: Callable[[int], int], training: bool = True,
+                 losses: Optional[List[str]] = None, loss_weights: Optional[List[float]] = None, adam=None):
+        self.g = graph
+        self.N = batch
+        self.alloc_fn = alloc
+        self.training = training
+        self.ndim = graph.ndim
+        self.ops: Dict[int, List[Tuple[int, object, str]]] = {0: [], 1: [], 2: []}
+        self.cons = graph.consumers()
+        self.phys: Dict[int, Phys] = {}
+        self.gsrc: Dict[int, List[GSrc]] = {}
+        self.params: List[ParamEntry] = []
+        self.pindex: Dict[str, ParamEntry] = {}
+        self.n_train = 0
+        self.n_moving = 0
+        self.buffers: List[Tuple[str, int, int]] = []  # (tag, ptr, nbytes)
+        self.taps: Dict[str, Tuple[TView, int, str]] = {}   # layer name -> (view, logical C, 'act'|'raw')
+        self.grad_taps: Dict[str, Tuple[TView, int]] = {}
+        self.outputs: List[dict] = []
+        self.losses = losses
+        self.loss_weights = loss_weights
+        self.adam = adam or dict(lr=2e-4, beta1=0.9, beta2=0.999, eps=1e-7)
+        self.input_ptr = 0
+        self.loss_ptr = 0
+        self.units: List[dict] = []
+        self.act_bytes = 0
+        self.op_info: Dict[Tuple[int, int], dict] = {}
+        self._analyse()
+        self._layout_params()
+
+    # ---------------------------------------------------------------------------------------- memory helpers
+    def alloc(self, nbytes, tag="act"):
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        ptr = self.alloc_fn(nbytes, tag)
+        self.buffers.append((tag, ptr, nbytes))
+        if tag in ("act", "grad"):
+            self.act_bytes += nbytes
+        return ptr
+
+    def new_act(self, H, W, Cp, tag="act") -> TView:
+        return TView.dense(self.alloc(self.N * H * W * Cp * 2, tag), self.N, H, W, Cp)
+
+    def emit(self, phase, op, desc, note="", flops=0.0, bytes_=0.0):
+        """flops: algorithmic FLOPs (2*MAC on logical channels) of a tensor-core op; bytes_: algorithmic HBM bytes of a streaming op"""
+        self.op_info[(phase, len(self.ops[phase]))] = dict(flops=float(flops), bytes=float(bytes_), note=note, op=op)
+        self.ops[phase].append((op, desc, note))
+
+    def _conv_flops(self, n: Node) -> float:
+        kh, kw = n.attrs["kernel"]
+        cin, co = n.inputs[0].C, n.attrs["filters"]
+        if n.op == "tconv":
+            H, W, _ = n.inputs[0].shape
+        else:
+            H, W, _ = n.shape
+        return 2.0 * self.N * H * W * cin * co * kh * kw
+
+    # ---------------------------------------------------------------------------------------- graph analysis
+    def _sole(self, n: Node, op: str) -> Optional[Node]:
+        c = self.cons[id(n)]
+        if len(c) == 1 and c[0].op == op and n not in self.g.outputs:
+            return c[0]
+        return None
+
+    def _analyse(self):
+        g = self.g
+        absorbed = set()
+        self.flat_concat: Dict[int, List[Node]] = {}
+        self.absorbed_concat = set()
+        # flatten nested concatenations (Concat_Block is a left fold of concatenate layers)
+        for n in g.nodes:
+            if n.op == "concat":
+                parts = []
+                for i in n.inputs:
+                    if i.op == "concat" and len(self.cons[id(i)]) == 1 and i not in g.outputs:
+                        parts += self.flat_concat[id(i)]
+                        absorbed.add(id(i))
+                        self.absorbed_concat.add(id(i))
+                    else:
+                        parts.append(i)
+                self.flat_concat[id(n)] = parts
+        for n in g.nodes:
+            if id(n) in absorbed:
+                continue
+            if n.op == "input":
+                self.units.append(dict(kind="input", node=n, out=n))
+            elif n.op in ("conv", "tconv"):
+                a = n.attrs
+                is_head = (n.op == "conv" and a["kernel"] == (1, 1) and a["filters"] <= 8 and n in g.outputs)
+                if is_head:
+                    self.units.append(dict(kind="head", node=n, out=n))
+                    continue
+                if a.get("activation") not in (None, "linear"):
+                    raise PlanError(f"conv {n.name}: fused activation only supported on output heads")
+                u = dict(kind="conv", node=n, bn=None, act=None, pool=None)
+                last = n
+                b = self._sole(last, "bn")
+                if b is not None:
+                    u["bn"] = b
+                    absorbed.add(id(b))
+                    last = b
+                c = self._sole(last, "act")
+                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                    u["act"] = c
+                    absorbed.add(id(c))
+                    last = c
+                u["out"] = last
+                if u["bn"] is not None and last not in g.outputs:
+                    want = (2, 2) if self.ndim == 2 else (1, 2)
+                    for p in self.cons[id(last)]:
+                        if p.op == "pool" and p.attrs["size"] == want and last.shape[0] % want[0] == 0 and last.shape[1] % want[1] == 0:
+                            u["pool"] = p
+                            absorbed.add(id(p))
+                            break
+                self.units.append(u)
+            elif n.op == "concat":
+                self.units.append(dict(kind="concat", node=n, out=n, parts=self.flat_concat[id(n)]))
+            elif n.op == "add":
+                self.units.append(dict(kind="add", node=n, out=n))
+            else:
+                raise PlanError(f"layer type '{n.op}' ({n.name}) is not lowered yet")
+        self.unit_of_out = {id(u["out"]): u for u in self.units}
+        for u in self.units:
+            if u.get("pool") is not None:
+                self.unit_of_out[id(u["pool"])] = u
+
+    # ---------------------------------------------------------------------------------------- parameters
+    def _add_param(self, key, keras_shape, kind, size, trainable, **meta):
+        size_p = (size + 63) // 64 * 64
+        if trainable:
+            off = self.n_train
+            self.n_train += size_p
+        else:
+            off = self.n_moving
+            self.n_moving += size_p
+        e = ParamEntry(key, tuple(keras_shape), kind, off, size_p, trainable, meta)
+        self.params.append(e)
+        self.pindex[key] = e
+        return e
+
+    def _layout_params(self):
+        """Assign arena offsets in layer creation order.  Input-channel maps are resolved at emission time."""
+        specs = {}
+        for (layer, wname, shape, init, tr) in self.g.param_specs():
+            specs[(layer, wname)] = (shape, tr)
+        for n in self.g.nodes:
+            if n.op in ("conv", "tconv"):
+                kh, kw = n.attrs["kernel"]
+                cin_p = self._cin_phys(n.inputs[0])
+                co = n.attrs["filters"]
+                u = self.unit_of_out.get(id(n))
+                if u is not None and u["kind"] == "head":
+                    self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], "head", cin_p * co, True, cin_p=cin_p, cout=co)
+                    self._add_param(f"{n.name}/bias", (co,), "vec", co, True, C=co)
+                else:
+                    cop = ceil8(co)
+                    self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], n.op, cop * kh * kw * cin_p, True,
+                                    cout=co, cout_p=cop, taps=kh * kw, cin_p=cin_p, kh=kh, kw=kw)
+                    self._add_param(f"{n.name}/bias", (co,), "vec", cop, True, C=co)
+            elif n.op == "bn":
+                cp = ceil8(n.C)
+                self._add_param(f"{n.name}/gamma", (n.C,), "vec", cp, True, C=n.C, fill=1.0)
+                self._add_param(f"{n.name}/beta", (n.C,), "vec", cp, True, C=n.C)
+                self._add_param(f"{n.name}/moving_mean", (n.C,), "vec", cp, False, C=n.C)
+                self._add_param(f"{n.name}/moving_variance", (n.C,), "vec", cp, False, C=n.C, fill=1.0)
+
+    def _segs(self, t: Node) -> List[Tuple[int, int]]:
+        """logical->physical channel segments a tensor will have once materialised (pure function of the graph)."""
+        if t.op == "concat" and id(t) in self.flat_concat:
+            segs, off = [], 0
+            for p in self.flat_concat[id(t)]:
+                for (o, c) in self._segs(p):
+                    segs.append((off + o, c))
+                off += self._cphys(p)
+            return segs
+        return [(0, t.C)]
+
+    def _cphys(self, t: Node) -> int:
+        if t.op == "concat" and id(t) in self.flat_concat:
+            return sum(self._cphys(p) for p in self.flat_concat[id(t)])
+        return ceil8(t.C)
+
+    def _cin_phys(self, t: Node) -> int:
+        return self._cphys(t)
+
+    # ---------------------------------------------------------------------------------------- arenas
+    def bind_arenas(self):
+        n = max(self.n_train, 64)
+        self.w_ptr = self.alloc(n * 4, "param_w")
+        self.g_ptr = self.alloc(n * 4, "param_g")
+        self.m_ptr = self.alloc(n * 4, "param_m")
+        self.v_ptr = self.alloc(n * 4, "param_v")
+        self.wb_ptr = self.alloc(n * 2, "param_wb")
+        self.mov_ptr = self.alloc(max(self.n_moving, 64) * 4, "moving")
+
+    def pw(self, key):   # fp32 master address
+        return self.w_ptr + 4 * self.pindex[key].offset
+
+    def pg(self, key):
+        return self.g_ptr + 4 * self.pindex[key].offset
+
+    def pwb(self, key):  # bf16 shadow address
+        return self.wb_ptr + 2 * self.pindex[key].offset
+
+    def pmov(self, key):
+        return self.mov_ptr + 4 * self.pindex[key].offset
+
+    # ---------------------------------------------------------------------------------------- build
+    def build(self):
+        self.bind_arenas()
+        self.loss_ptr = self.alloc(256, "loss")
+        for u in self.units:
+            getattr(self, "_fwd_" + u["kind"])(u)
+        if self.training:
+            self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.g_ptr, max(self.n_train, 64) * 4), "zero grads")
+            self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.loss_ptr, 256), "zero loss")
+            for u in reversed(self.units):
+                getattr(self, "_bwd_" + u["kind"])(u)
+            a = self.adam
+            self.emit(2, L.OP_ADAM, L.AdamDesc(self.w_ptr, self.g_ptr, self.m_ptr, self.v_ptr, self.wb_ptr, max(self.n_train, 64),
+                                               a["lr"], a["beta1"], a["beta2"], a["eps"], 1.0, 1), "adam")
+        return self
+
+    # -- destinations: where a produced tensor must live ------------------------------------------------------
+    def _concat_root(self, c: Node) -> Node:
+        """outermost concat a (possibly nested, flattened) concat node belongs to"""
+        while id(c) in self.absorbed_concat:
+            c = self.cons[id(c)][0]
+        return c
+
+    def _concat_buffer(self, c: Node) -> TView:
+        if id(c) not in self.phys:
+            H, W, _ = c.shape
+            view = self.new_act(H, W, self._cphys(c))
+            self.phys[id(c)] = Phys(view, c.C, self._segs(c))
+        return self.phys[id(c)].view
+
+    def _dests(self, t: Node) -> List[TView]:
+        """views the producer of t should write: one slot per consuming concat, else one dense buffer"""
+        dests = []
+        for c in self.cons[id(t)]:
+            if c.op == "concat":
+                root = self._concat_root(c)
+                parts = self.flat_concat[id(root)]
+                buf = self._concat_buffer(root)
+                off = 0
+                for p in parts:
+                    if p is t:
+                        dests.append(buf.chan(off, ceil8(t.C)))
+                    off += self._cphys(p)
+        H, W, _ = t.shape
+        if not dests:
+            dests.append(self.new_act(H, W, ceil8(t.C)))
+        self.phys[id(t)] = Phys(dests[0], t.C, [(0, t.C)])
+        return dests
+
+    def _copy_extra(self, src: TView, extra: List[TView]):
+        for d in extra:
+            self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(1, src.to_c(), lw.NULL_VIEW.to_c(), lw.NULL_VIEW.to_c(), d.to_c()), "concat copy")
+
+    # -- forward emitters ------------------------------------------------------------------------------------
+    def _fwd_input(self, u):
+        n = u["node"]
+        H, W, C = n.shape
+        self.input_ptr = self.alloc(self.N * H * W * C * 4, "input")
+        dests = self._dests(n)
+        self.emit(0, L.OP_CAST, L.CastDesc(self.input_ptr, self.N, H, W, C, dests[0].to_c()), n.name)
+        self._copy_extra(dests[0], dests[1:])
+
+    def _act_code(self, node: Optional[Node]):
+        return L.ACT_NONE if node is None else L.ACT_CODES[node.attrs["fn"]]
+
+    def _fwd_conv(self, u):
+        n: Node = u["node"]
+        a = n.attrs
+        kh, kw = a["kernel"]
+        x = self.phys[id(n.inputs[0])]
+        pe = self.pindex[f"{n.name}/kernel"]
+        pe.meta["segs"] = list(x.segs)
+        assert pe.meta["cin_p"] == x.Cp, (n.name, pe.meta["cin_p"], x.Cp)
+        co, cop, cin_p = a["filters"], pe.meta["cout_p"], x.Cp
+        H, W, _ = n.shape
+        out_node = u["out"]
+        act = self._act_code(u["act"])
+        bias = self.pw(f"{n.name}/bias")
+        strided = n.op == "conv" and a["strides"] != (1, 1)
+        if strided and not (a["kernel"] == (1, 1) and a["padding"] == "valid"):
+            raise PlanError(f"{n.name}: only 1x1 'valid' strided convolutions are lowered")
+
+        def conv_desc(out_view, act_code, stats_ptr):
+            if n.op == "tconv":
+                return lw.tconv_fprop(x.view, self.pwb(pe.key), cop, kh, kw, cin_p, out_view, bias=bias, act=act_code, stats=stats_ptr)
+            xin = x.view.parity(0, 0, a["strides"][0], a["strides"][1]) if strided else x.view
+            if a["padding"] == "same" or (kh, kw) == (1, 1):
+                return lw.conv_fprop(xin, self.pwb(pe.key), cop, kh, kw, cin_p, out_view, bias=bias, act=act_code, stats=stats_ptr)
+            raise PlanError(f"{n.name}: padding '{a['padding']}' with kernel {a['kernel']} is not lowered")
+
+        if u["bn"] is None:
+            dests = self._dests(out_node)
+            self.emit(0, L.OP_CONV, conv_desc(dests[0], act, 0), n.name, flops=self._conv_flops(n))
+            self._copy_extra(dests[0], dests[1:])
+            u["y"] = dests[0]
+            self.taps[out_node.name] = (dests[0], co, "act")
+            if u["act"] is not None:
+                self.taps[n.name] = (dests[0], co, "post")  # pre-activation is not materialised
+            return
+        bn = u["bn"]
+        z = self.new_act(H, W, cop)
+        u["z"] = z
+        if n.op == "tconv":
+            gh, gw = n.inputs[0].shape[0], n.inputs[0].shape[1]
+            n_part = (len(lw._tconv_axis(kh, 2)) * len(lw._tconv_axis(kw, 2))) * conv_num_mtiles(self.N, gh, gw)
+        else:
+            n_part = conv_num_mtiles(self.N, H, W)
+        stats = self.alloc(n_part * 2 * cop * 4, "scratch") if self.training else 0
+        self.emit(0, L.OP_CONV, conv_desc(z, L.ACT_NONE, stats), n.name, flops=self._conv_flops(n))
+        vec = self.alloc(4 * cop * 4, "scratch")
+        u["scale"], u["shift"], u["mean"], u["rstd"] = vec, vec + cop * 4, vec + 2 * cop * 4, vec + 3 * cop * 4
+        count = float(self.N * H * W)
+        self.emit(0, L.OP_BN_FINALIZE, L.BnFinalizeDesc(
+            stats, n_part, cop, count, self.pw(f"{bn.name}/gamma"), self.pw(f"{bn.name}/beta"),
+            self.pmov(f"{bn.name}/moving_mean"), self.pmov(f"{bn.name}/moving_variance"),
+            1 if self.training else 0, 1 if self.ndim == 2 else 0, bn.attrs["eps"], bn.attrs["momentum"],
+            u["scale"], u["shift"], u["mean"], u["rstd"], 0 if self.training else 1), bn.name)
+        dests = self._dests(out_node)
+        d = L.BnActDesc()
+        d.x, d.scale, d.shift, d.act = z.to_c(), u["scale"], u["shift"], act
+        d.n_out = min(len(dests), 2)
+        for i in range(d.n_out):
+            d.out[i] = dests[i].to_c()
+        if u["pool"] is not None:
+            pn = u["pool"]
+            pd = self._dests(pn)
+            d.pool_h, d.pool_w = pn.attrs["size"]
+            d.pooled = pd[0].to_c()
+            self.taps[pn.name] = (pd[0], pn.C, "act")
+        self.emit(0, L.OP_BN_ACT, d, out_node.name)
+        self._copy_extra(dests[0], dests[2:])
+        if u["pool"] is not None:
+            self._copy_extra(pd[0], pd[1:])
+        u["y"] = dests[0]
+        self.taps[n.name] = (z, co, "raw")
+        self.taps[out_node.name] = (dests[0], co, "act")
+
+    def _fwd_concat(self, u):
+        n = u["node"]
+        self._concat_buffer(n)  # producers already wrote their slots
+        self.taps[n.name] = (self.phys[id(n)].view, n.C, "concat")
+
+    def _fwd_add(self, u):
+        n = u["node"]
+        if len(n.inputs) != 2:
+            raise PlanError("add with != 2 inputs")
+        a, b = self.phys[id(n.inputs[0])], self.phys[id(n.inputs[1])]
+        dests = self._dests(n)
+        self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(0, a.view.to_c(), b.view.to_c(), lw.NULL_VIEW.to_c(), dests[0].to_c()), n.name)
+        self._copy_extra(dests[0], dests[1:])
+        self.taps[n.name] = (dests[0], n.C, "act")
+
+    def _fwd_head(self, u):
+        n = u["node"]
+        a = n.attrs
+        x = self.phys[id(n.inputs[0])]
+        pe = self.pindex[f"{n.name}/kernel"]
+        pe.meta["segs"] = list(x.segs)
+        co = a["filters"]
+        st = a["strides"][1]
+        if a["strides"][0] not in (1, st):
+            raise PlanError("anisotropic head stride")
+        Ho, Wo, _ = n.shape
+        npix = self.N * Ho * Wo
+        y = self.alloc(npix * co * 4, "output")
+        dl = self.alloc(npix * co * 4, "grad") if self.training else 0
+        tgt = self.alloc(npix * co * 4, "target") if self.training else 0
+        act = L.ACT_CODES[a.get("activation")]
+        d = L.HeadDesc()
+        d.x, d.w, d.b, d.cout, d.act, d.stride = x.view.to_c(), self.pw(pe.key), self.pw(f"{n.name}/bias"), co, act, st
+        d.y, d.dlogits = y, dl
+        d.dw, d.db = self.pg(pe.key), self.pg(f"{n.name}/bias")
+        u["desc"] = d
+        self.emit(0, L.OP_HEAD_FWD, d, n.name)
+        idx = self.g.outputs.index(n)
+        self.outputs.append(dict(index=idx, name=n.name, ptr=y, shape=(self.N, Ho, Wo, co), target_ptr=tgt, act=act, dlogits=dl, npix=npix, cout=co))
+
+    # -- backward emitters -----------------------------------------------------------------------------------
+    def _add_gsrc(self, t: Node, s: GSrc):
+        self.gsrc.setdefault(id(t), []).append(s)
+
+    def _bwd_head(self, u):
+        n = u["node"]
+        o = next(o for o in self.outputs if o["name"] == n.name)
+        idx = o["index"]
+        kind = LOSS_KINDS[(self.losses[idx] if self.losses else "bce")]
+        wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
+        self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr),
+                  f"loss {n.name}")
+        d: L.HeadDesc = u["desc"]
+        x = self.phys[id(n.inputs[0])]
+        H, W, _ = n.inputs[0].shape
+        d2 = L.HeadDesc.from_buffer_copy(d)
+        if n.inputs[0].op != "input":
+            dx = self.new_act(H, W, x.Cp, "grad")
+            d2.dx = dx.to_c()
+            self._add_gsrc(n.inputs[0], GSrc(dx))
+        self.emit(1, L.OP_HEAD_BWD, d2, f"head bwd {n.name}")
+
+    def _bwd_input(self, u):
+        pass
+
+    def _bwd_add(self, u):
+        n = u["node"]
+        for s in self.gsrc.get(id(n), []):
+            for i in n.inputs:
+                self._add_gsrc(i, s)
+
+    def _bwd_concat(self, u):
+        n = u["node"]
+        srcs = self.gsrc.get(id(n), [])
+        off = 0
+        for p in u["parts"]:
+            cp = self._cphys(p)
+            for s in srcs:
+                if s.kind != 0:
+                    raise PlanError("pooled gradient of a concat")
+                self._add_gsrc(p, GSrc(s.view.chan(off, cp), 0, (1, 1), s.premasked and off == 0))
+            off += cp
+
+    def _reduce_sources(self, srcs: List[GSrc], shape_like: TView) -> List[GSrc]:
+        """bn_bwd takes at most MAX_GRADSRC sources: pre-sum surplus direct sources."""
+        while len(srcs) > L.MAX_GRADSRC:
+            direct = [s for s in srcs if s.kind == 0]
+            if len(direct) < 2:
+                raise PlanError("too many pooled gradient sources")
+            a, b = direct[0], direct[1]
+            tmp = TView.dense(self.alloc(shape_like.N * shape_like.H * shape_like.W * shape_like.C * 2, "grad"),
+                              shape_like.N, shape_like.H, shape_like.W, shape_like.C)
+            self.emit(1, L.OP_ELTWISE, L.EltwiseDesc(0, a.view.to_c(), b.view.to_c(), lw.NULL_VIEW.to_c(), tmp.to_c()), "grad pre-sum")
+            srcs = [s for s in srcs if s is not a and s is not b] + [GSrc(tmp)]
+        return srcs
+
+    def _bwd_conv(self, u):
+        n: Node = u["node"]
+        a = n.attrs
+        kh, kw = a["kernel"]
+        out_node = u["out"]
+        srcs = list(self.gsrc.get(id(out_node), []))
+        if u["pool"] is not None:
+            ph, pw_ = u["pool"].attrs["size"]
+            for s in self.gsrc.get(id(u["pool"]), []):
+                if s.kind != 0:
+                    raise PlanError("pool of pool")
+                srcs.append(GSrc(s.view, 1, (ph, pw_)))
+        if not srcs:
+            return  # dead branch (no gradient reaches it)
+        x = self.phys[id(n.inputs[0])]
+        pe = self.pindex[f"{n.name}/kernel"]
+        co, cop, cin_p = a["filters"], pe.meta["cout_p"], x.Cp
+        H, W, _ = n.shape
+        act = self._act_code(u["act"])
+        y: TView = u["y"]
+        ydense = TView.dense(0, self.N, H, W, cop)
+        srcs = self._reduce_sources(srcs, ydense)
+        # ---- dZ: gradient w.r.t. the raw convolution output
+        if u["bn"] is not None:
+            bn = u["bn"]
+            dz = self.new_act(H, W, cop, "grad")
+            d = L.BnBwdDesc()
+            d.x, d.scale, d.shift, d.mean, d.rstd = u["z"].to_c(), u["scale"], u["shift"], u["mean"], u["rstd"]
+            d.act, d.n_src = act, len(srcs)
+            for i, s in enumerate(srcs):
+                d.src[i] = L.GradSrc(s.view.to_c(), s.kind, s.pool[0], s.pool[1])
+            d.count = float(self.N * H * W)
+            nb = max(1, min(296, (self.N * H * W) // 64))
+            d.partials, d.n_blocks = self.alloc(nb * 2 * cop * 4, "scratch"), nb
+            d.dgamma, d.dbeta = self.pg(f"{bn.name}/gamma"), self.pg(f"{bn.name}/beta")
+            d.dx = dz.to_c()
+            self.emit(1, L.OP_BN_BWD, d, f"bn bwd {bn.name}")
+            has_bias_grad = False
+        else:
+            if len(srcs) == 1 and srcs[0].kind == 0 and (act == L.ACT_NONE or srcs[0].premasked):
+                dz = srcs[0].view
+            else:
+                dz = self.new_act(H, W, cop, "grad")
+                d = L.BnBwdDesc()
+                d.x, d.act, d.n_src = y.to_c(), act, len(srcs)
+                if act == L.ACT_SIGMOID:
+                    raise PlanError("sigmoid epilogue backward")
+                for i, s in enumerate(srcs):
+                    d.src[i] = L.GradSrc(s.view.to_c(), s.kind, s.pool[0], s.pool[1])
+                d.count = 1.0
+                d.dx = dz.to_c()
+                self.emit(1, L.OP_BN_BWD, d, f"act bwd {out_node.name}")
+            has_bias_grad = True
+        self.grad_taps[n.name] = (dz, co)
+        # ---- weight / bias gradients
+        strided = n.op == "conv" and a["strides"] != (1, 1)
+        xin = x.view.parity(0, 0, a["strides"][0], a["strides"][1]) if strided else x.view
+        if n.op == "tconv":
+            self.emit(1, L.OP_WGRAD, lw.tconv_wgrad(dz, x.view, self.pg(pe.key), cop, kh, kw, cin_p), f"wgrad {n.name}", flops=self._conv_flops(n))
+        else:
+            self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, xin, self.pg(pe.key), cop, kh, kw, cin_p), f"wgrad {n.name}", flops=self._conv_flops(n))
+        if has_bias_grad:
+            self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")
+        # ---- input gradient
+        src_node = n.inputs[0]
+        if src_node.op == "input":
+            return
+        if strided:
+            raise PlanError("dgrad of strided conv not lowered yet")
+        Hi, Wi, _ = src_node.shape
+        dx = self.new_act(Hi, Wi, cin_p, "grad")
+        mul_view, mul_mode, premasked = None, 0, False
+        if src_node.op == "concat" and n.op == "conv":
+            first = u_first = self.flat_concat[id(src_node)][0]
+            pu = self.unit_of_out.get(id(first))
+            if (pu is not None and pu["kind"] == "conv" and pu["bn"] is None and pu["act"] is not None and pu["out"] is first
+                    and len(self.cons[id(first)]) == 1 and len(self.cons[id(src_node)]) == 1
+                    and self._act_code(pu["act"]) in (L.ACT_RELU, L.ACT_LEAKY)):
+                mul_view, mul_mode, premasked = x.view.chan(0, ceil8(first.C)), self._act_code(pu["act"]), True
+        if n.op == "tconv":
+            self.emit(1, L.OP_CONV, lw.tconv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx), f"dgrad {n.name}", flops=self._conv_flops(n))
+        else:
+            self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx, mul_view, mul_mode), f"dgrad {n.name}", flops=self._conv_flops(n))
+        self._add_gsrc(src_node, GSrc(dx, 0, (1, 1), premasked))
+
+    # ---------------------------------------------------------------------------------------- weights <-> Keras
+    def to_internal(self, key: str, arr: np.ndarray) -> np.ndarray:
+        """Keras-layout array -> flat internal layout (padded, kernel-friendly)."""
+        e = self.pindex[key]
+        m = e.meta
+        out = np.zeros(e.size, np.float32)
+        arr = np.asarray(arr, np.float32)
+        if e.kind == "vec":
+            out[:m["C"]] = arr
+            if m.get("fill") is not None:
+                out[m["C"]:ceil8(m["C"])] = m["fill"]
+        elif e.kind in ("conv", "tconv"):
+            k = arr if arr.ndim == 4 else arr[None]            # (kh,kw,Cin,Cout) | tconv (kh,kw,Cout,Cin)
+            if e.kind == "conv":
+                k = np.transpose(k, (3, 0, 1, 2))               # -> (Cout,kh,kw,Cin)
+            else:
+                k = np.transpose(k, (2, 0, 1, 3))               # -> (Cout,kh,kw,Cin)
+            w = np.zeros((m["cout_p"], m["taps"], m["cin_p"]), np.float32)
+            src = 0
+            for (po, c) in m["segs"]:
+                w[:m["cout"], :, po:po + c] = k[:, :, :, src:src + c].reshape(m["cout"], m["taps"], c)
+                src += c
+            out[:w.size] = w.reshape(-1)
+        elif e.kind == "head":
+            k = arr.reshape(-1, m["cout"])                      # (1,1,Cin,Cout) -> (Cin,Cout)
+            w = np.zeros((m["cin_p"], m["cout"]), np.float32)
+            src = 0
+            for (po, c) in m["segs"]:
+                w[po:po + c] = k[src:src + c]
+                src += c
+            out[:w.size] = w.reshape(-1)
+        else:
+            raise PlanError(e.kind)
+        return out
+
+    def from_internal(self, key: str, flat: np.ndarray) -> np.ndarray:
+        e = self.pindex[key]
+        m = e.meta
+        flat = np.asarray(flat, np.float32)
+        if e.kind == "vec":
+            return flat[:m["C"]].copy().reshape(e.keras_shape)
+        if e.kind in ("conv", "tconv"):
+            w = flat[:m["cout_p"] * m["taps"] * m["cin_p"]].reshape(m["cout_p"], m["taps"], m["cin_p"])
+            cin = sum(c for _, c in m["segs"])
+            k = np.zeros((m["cout"], m["taps"], cin), np.float32)
+            src = 0
+            for (po, c) in m["segs"]:
+                k[:, :, src:src + c] = w[:m["cout"], :, po:po + c]
+                src += c
+            k = k.reshape(m["cout"], m["kh"], m["kw"], cin)
+            k = np.transpose(k, (1, 2, 3, 0)) if e.kind == "conv" else np.transpose(k, (1, 2, 0, 3))
+            return k.reshape(e.keras_shape)
+        if e.kind == "head":
+            w = flat[:m["cin_p"] * m["cout"]].reshape(m["cin_p"], m["cout"])
+            cin = sum(c for _, c in m["segs"])
+            k = np.zeros((cin, m["cout"]), np.float32)
+            src = 0
+            for (po, c) in m["segs"]:
+                k[src:src + c] = w[po:po + c]
+                src += c
+            return k.reshape(e.keras_shape)
+        raise PlanError(e.kind)
+
+    def num_launch_ops(self, phase):
+        return len(self.ops[phase])

@@ -201,6 +201,30 @@ int b2seg_plan_run(b2seg_plan* p, int phase, void* stream) {
   return 0;
 }
 
+int b2seg_plan_run_timed(b2seg_plan* p, int phase, void* stream, float* ms_per_op, int n_ops) {
+  if (!p || phase < 0 || phase > 2 || !ms_per_op) return b2::fail(B2SEG_ERR_ARG, "plan_run_timed: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int n = (int)p->phase[phase].size();
+  if (n_ops < n) return b2::fail(B2SEG_ERR_ARG, "plan_run_timed: need room for %d ops", n);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) B2_CUDA_OK(cudaEventCreate(&e));
+  B2_CUDA_OK(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n; ++i) {
+    int rc = p->phase[phase][i]->launch(s);
+    if (rc) return rc;
+    B2_CUDA_OK(cudaEventRecord(ev[i + 1], s));
+  }
+  B2_CUDA_OK(cudaEventSynchronize(ev[n]));
+  for (int i = 0; i < n; ++i) B2_CUDA_OK(cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+int b2seg_plan_num_ops(const b2seg_plan* p, int phase) {
+  if (!p || phase < 0 || phase > 2) return -1;
+  return (int)p->phase[phase].size();
+}
+
 int b2seg_plan_num_launches(const b2seg_plan* p, int phase) {
   if (!p || phase < 0 || phase > 2) return -1;
   int n = 0;
