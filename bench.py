@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops-json", default="", help="dump per-op device times (profiling aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2seg" else args.warmup
     if args.impl == "reference":
@@ -239,7 +240,8 @@ def main():
     if rank == 0:
         peak_tf, peak_gbs, peak_src = measured_peaks()
         agg = {}
-        for phase in (0, 1):
+        op_rows = []
+        for phase in (0, 1, 2):
             n_ops = eng.lib.b2seg_plan_num_ops(eng.plan, phase)
             buf = (C.c_float * n_ops)()
             reps = 3
@@ -251,8 +253,14 @@ def main():
             for i in range(n_ops):
                 info = eng.planner.op_info[(phase, i)]
                 fam = {L.OP_CONV: "conv_gemm_kernel", L.OP_WGRAD: "wgrad_kernel"}.get(info["op"], "streaming")
+                op_rows.append({"phase": phase, "i": i, "op": info["op"], "note": info["note"], "ms": float(acc[i]),
+                                "tflops": info["flops"] / (acc[i] / 1e3) / 1e12 if info["flops"] and acc[i] > 0 else None})
                 a = agg.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0))
                 a["ms"] += float(acc[i]); a["flops"] += info["flops"]; a["launches"] += 1
+        if args.ops_json:
+            os.makedirs(os.path.dirname(os.path.abspath(args.ops_json)), exist_ok=True)
+            with open(args.ops_json, "w") as f:
+                json.dump(op_rows, f, indent=0)
         step_ms_ops = sum(a["ms"] for a in agg.values())
         dom = max(("conv_gemm_kernel", "wgrad_kernel"), key=lambda k: agg.get(k, {"ms": 0})["ms"])
         a = agg[dom]

