@@ -197,7 +197,10 @@ int b2seg_version(void);
 int b2seg_device_check(int device);
 
 int b2seg_conv(const b2seg_conv_desc* d, void* stream);
-int b2seg_conv_num_mtiles(const b2seg_conv_desc* d);  /* tiles per group: size stats as n_groups*this*2*C floats */
+int b2seg_conv_num_mtiles(const b2seg_conv_desc* d);  /* M tiles per group */
+/* rows of [2][C] floats the kernel writes into `stats` (one per CTA when a CTA always covers the same output columns,
+ * else one per (group, M tile)); pass it to b2seg_bn_finalize as n_partials */
+int b2seg_conv_num_stat_rows(const b2seg_conv_desc* d);
 int b2seg_wgrad(const b2seg_wgrad_desc* d, void* stream);
 int b2seg_bn_finalize(const b2seg_bn_finalize_desc* d, void* stream);
 int b2seg_bn_act(const b2seg_bn_act_desc* d, void* stream);

@@ -66,7 +66,9 @@ def test_conv_fprop(N, H, W, Cin, Cout, kh, kw, act, stats):
     bias = torch.randn(Cout, device=dev)
     out = torch.zeros(N, H, W, Cout, device=dev, dtype=torch.bfloat16)
     d = lw.conv_fprop(tv(x), w.data_ptr(), Cout, kh, kw, Cin, tv(out), bias=bias.data_ptr(), act=act)
-    mt = L.load().b2seg_conv_num_mtiles(C.byref(d))
+    mt = L.load().b2seg_conv_num_stat_rows(C.byref(d))
+    from b2seg.planner import conv_stat_rows
+    assert mt == conv_stat_rows(d, torch.cuda.get_device_properties(0).multi_processor_count)
     st = torch.zeros(mt, 2, Cout, device=dev) if stats else None
     if stats:
         d.stats = st.data_ptr()

@@ -31,7 +31,8 @@ class Engine:
         self._tagged: Dict[str, torch.Tensor] = {}
         self._shared = share_params_from
         self.dev = torch.device("cuda", self.device)
-        self.planner = Planner(graph, batch, self._alloc, training=training, losses=losses, loss_weights=loss_weights, adam=adam).build()
+        self.planner = Planner(graph, batch, self._alloc, training=training, losses=losses, loss_weights=loss_weights, adam=adam,
+                               stat_rows_fn=lambda d: self.lib.b2seg_conv_num_stat_rows(C.byref(d))).build()
         p = self.planner
         n = max(p.n_train, 64)
         self.w = self._typed("param_w", torch.float32, n)

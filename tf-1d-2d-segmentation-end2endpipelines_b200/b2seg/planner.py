@@ -53,6 +53,16 @@ def conv_num_mtiles(N, H, W):
     return -(-W // bw) * -(-H // bh) * -(-N // bn)
 
 
+def conv_stat_rows(desc, num_sms=148):
+    """Mirror of b2::conv_num_stat_rows (csrc/conv_gemm.cu) for a given SM count."""
+    o = desc.out[0]
+    m_tiles = conv_num_mtiles(o.N, o.H, o.W)
+    bn = desc.block_n or (64 if o.C <= 64 else (128 if o.C <= 128 else 256))
+    n_tiles = -(-o.C // bn)
+    total = desc.n_groups * m_tiles * n_tiles
+    return min(total, num_sms) if n_tiles == 1 else desc.n_groups * m_tiles
+
+
 # ----------------------------------------------------------------------------------------------------------
 @dataclass
 class ParamEntry:
@@ -95,7 +105,9 @@ LOSS_KINDS = {"bce": 0, "binary_crossentropy": 0, "cce": 1, "categorical_crossen
 
 class Planner:
     def __init__(self, graph: Graph, batch: int, alloc: Callable[[int], int], training: bool = True,
-                 losses: Optional[List[str]] = None, loss_weights: Optional[List[float]] = None, adam=None):
+                 losses: Optional[List[str]] = None, loss_weights: Optional[List[float]] = None, adam=None,
+                 stat_rows_fn: Optional[Callable] = None):
+        self.stat_rows_fn = stat_rows_fn or conv_stat_rows
         self.g = graph
         self.N = batch
         self.alloc_fn = alloc
@@ -402,13 +414,11 @@ class Planner:
         bn = u["bn"]
         z = self.new_act(H, W, cop)
         u["z"] = z
-        if n.op == "tconv":
-            gh, gw = n.inputs[0].shape[0], n.inputs[0].shape[1]
-            n_part = (len(lw._tconv_axis(kh, 2)) * len(lw._tconv_axis(kw, 2))) * conv_num_mtiles(self.N, gh, gw)
-        else:
-            n_part = conv_num_mtiles(self.N, H, W)
+        cd = conv_desc(z, L.ACT_NONE, 0)
+        n_part = int(self.stat_rows_fn(cd))
         stats = self.alloc(n_part * 2 * cop * 4, "scratch") if self.training else 0
-        self.emit(0, L.OP_CONV, conv_desc(z, L.ACT_NONE, stats), n.name, flops=self._conv_flops(n))
+        cd.stats = stats
+        self.emit(0, L.OP_CONV, cd, n.name, flops=self._conv_flops(n))
         vec = self.alloc(4 * cop * 4, "scratch")
         u["scale"], u["shift"], u["mean"], u["rstd"] = vec, vec + cop * 4, vec + 2 * cop * 4, vec + 3 * cop * 4
         count = float(self.N * H * W)
@@ -565,7 +575,7 @@ class Planner:
             for i, s in enumerate(srcs):
                 d.src[i] = L.GradSrc(s.view.to_c(), s.kind, s.pool[0], s.pool[1])
             d.count = float(self.N * H * W)
-            nb = max(1, min(296, (self.N * H * W) // 64))
+            nb = max(1, min(1184, (self.N * H * W) // 64))
             d.partials, d.n_blocks = self.alloc(nb * 2 * cop * 4, "scratch"), nb
             d.dgamma, d.dbeta = self.pg(f"{bn.name}/gamma"), self.pg(f"{bn.name}/beta")
             d.dx = dz.to_c()

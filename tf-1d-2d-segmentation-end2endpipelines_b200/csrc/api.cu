@@ -173,6 +173,11 @@ int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
   return b2::conv_num_mtiles(d);
 }
 
+int b2seg_conv_num_stat_rows(const b2seg_conv_desc* d) {
+  if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");
+  return b2::conv_num_stat_rows(d);
+}
+
 int b2seg_plan_create(b2seg_plan** out) {
   b2::g_err[0] = 0;
   if (!out) return b2::fail(B2SEG_ERR_ARG, "null out");

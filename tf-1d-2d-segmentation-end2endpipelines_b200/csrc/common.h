@@ -56,5 +56,6 @@ void adam_update(PreparedOp* op, float lr, int64_t step, float grad_scale);
 bool is_adam(PreparedOp* op);
 
 int conv_num_mtiles(const b2seg_conv_desc* d);
+int conv_num_stat_rows(const b2seg_conv_desc* d);
 
 }  // namespace b2

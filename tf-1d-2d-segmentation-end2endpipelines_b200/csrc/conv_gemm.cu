@@ -35,6 +35,8 @@ struct alignas(64) ConvKParams {
   unsigned long long mul_ptr;
   long long mul_sn, mul_sh, mul_sw;
   int mul_mode, mul_c;
+  int lbw, lbwh;       // log2(bw), log2(bw*bh): tile rows -> pixel coordinates by shifts
+  int stats_per_cta;   // 1: one statistics row per CTA (n_tiles == 1), else one per (group, m_tile)
 };
 
 template <int BLOCK_N>
@@ -165,7 +167,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int et = threadIdx.x - 64;           // 0..127
     const int row = (warp & 3) * 32 + lane;    // TMEM lane == tile row owned by this thread
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const int bwh = p.bw * p.bh;
+    const int bwm = p.bw - 1, bhm = p.bh - 1;
+    constexpr int kChunks = BLOCK_N / 64;
+    float cta_s[kChunks], cta_q[kChunks];      // per-CTA BN statistics (threads et < 64)
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) { cta_s[c] = 0.f; cta_q[c] = 0.f; }
+    const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row of the store pass
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -175,14 +182,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int w0 = (m_tile % p.tiles_w) * p.bw;
       const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
       const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.bn;
-      const bool my_valid = (n0 + row / bwh) < p.gN && (h0 + (row / p.bw) % p.bh) < p.gH && (w0 + row % p.bw) < p.gW;
+      const bool my_valid = (n0 + (row >> p.lbwh)) < p.gN && (h0 + ((row >> p.lbw) & bhm)) < p.gH && (w0 + (row & bwm)) < p.gW;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      constexpr int kChunks = BLOCK_N / 64;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int col0 = n_tile * BLOCK_N + c * 64;
+        const int cc_st = col0 + vq * 8;
+        // dgrad fusion: fetch the forward activations whose sign masks this chunk early, so the loads overlap the TMEM read
+        uint4 yv[8];
+        if (p.mul_mode != 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 16 * i;
+            const int pn = n0 + (r >> p.lbwh), ph = h0 + ((r >> p.lbw) & bhm), pw = w0 + (r & bwm);
+            yv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 -> derivative 1
+            if (pn < p.gN && ph < p.gH && pw < p.gW && cc_st < p.mul_c)
+              yv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mul_ptr) + pn * p.mul_sn + ph * p.mul_sh + pw * p.mul_sw + cc_st));
+          }
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
@@ -215,34 +234,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
         named_bar_sync(1, 128);
         // ---- coalesced store of the 128 x 64 chunk (+ optional derivative-mask multiply)
-#pragma unroll 2
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int idx = et + i * 128;
-          const int r = idx >> 3, vq = idx & 7;
-          const int pn = n0 + r / bwh, ph = h0 + (r / p.bw) % p.bh, pw = w0 + r % p.bw;
-          const int cc = col0 + vq * 8;
-          if (pn < p.gN && ph < p.gH && pw < p.gW && cc < p.n_extent) {
+          const int r = r0 + 16 * i;
+          const int pn = n0 + (r >> p.lbwh), ph = h0 + ((r >> p.lbw) & bhm), pw = w0 + (r & bwm);
+          if (pn < p.gN && ph < p.gH && pw < p.gW && cc_st < p.n_extent) {
             uint4 val = *reinterpret_cast<const uint4*>(staging + r * kStgPitch + vq * 16);
-            if (p.mul_mode != 0 && cc < p.mul_c) {
-              const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(p.mul_ptr) + pn * p.mul_sn + ph * p.mul_sh + pw * p.mul_sw + cc;
-              const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yp));
-              const __nv_bfloat16* ye = reinterpret_cast<const __nv_bfloat16*>(&yv);
+            if (p.mul_mode != 0) {
+              const __nv_bfloat16* ye = reinterpret_cast<const __nv_bfloat16*>(&yv[i]);
               __nv_bfloat16* ve = reinterpret_cast<__nv_bfloat16*>(&val);
               const float neg = p.mul_mode == B2SEG_ACT_LEAKY ? 0.3f : 0.f;
 #pragma unroll
               for (int e = 0; e < 8; ++e)
                 if (!(__bfloat162float(ye[e]) > 0.f)) ve[e] = __float2bfloat16(__bfloat162float(ve[e]) * neg);
             }
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out_ptr[g]) + pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + cc;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out_ptr[g]) + pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + cc_st;
             *reinterpret_cast<uint4*>(op) = val;
           }
         }
-        // ---- BatchNorm statistics of the stored values: per-tile column sum / sum of squares
+        // ---- BatchNorm statistics of the stored values: column sum / sum of squares
         if (p.stats != nullptr) {
           const int col = et & 63, hf = et >> 6;
           float s = 0.f, ss = 0.f;
           const uint8_t* sp = staging + (hf * 64) * kStgPitch + col * 2;
-#pragma unroll 8
+#pragma unroll 16
           for (int r = 0; r < 64; ++r) {
             const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sp + r * kStgPitch));
             s += x;
@@ -251,18 +266,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           colpart[(hf * 64 + col) * 2 + 0] = s;
           colpart[(hf * 64 + col) * 2 + 1] = ss;
           named_bar_sync(2, 128);
-          if (et < 64 && col0 + et < p.n_extent) {
+          if (et < 64) {
             const float s2 = colpart[et * 2] + colpart[(64 + et) * 2];
             const float ss2 = colpart[et * 2 + 1] + colpart[(64 + et) * 2 + 1];
-            float* st = p.stats + (size_t)(g * p.m_tiles + m_tile) * 2 * p.n_extent;
-            st[col0 + et] = s2;
-            st[p.n_extent + col0 + et] = ss2;
+            if (p.stats_per_cta) {
+              cta_s[c] += s2;
+              cta_q[c] += ss2;
+            } else if (col0 + et < p.n_extent) {
+              float* st = p.stats + (size_t)(g * p.m_tiles + m_tile) * 2 * p.n_extent;
+              st[col0 + et] = s2;
+              st[p.n_extent + col0 + et] = ss2;
+            }
           }
         }
         named_bar_sync(1, 128);  // staging is reused by the next chunk
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.stats != nullptr && p.stats_per_cta && et < 64) {
+      float* st = p.stats + (size_t)blockIdx.x * 2 * p.n_extent;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c)
+        if (c * 64 + et < p.n_extent) {
+          st[c * 64 + et] = cta_s[c];
+          st[p.n_extent + c * 64 + et] = cta_q[c];
+        }
     }
   }
 
@@ -414,7 +443,23 @@ PreparedOp* prepare_conv(const b2seg_conv_desc* d) {
   }
   const int sms = num_sms();
   L->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
+  kp.lbw = 0; while ((1 << kp.lbw) < kp.bw) ++kp.lbw;
+  kp.lbwh = 0; while ((1 << kp.lbwh) < kp.bw * kp.bh) ++kp.lbwh;
+  kp.stats_per_cta = (kp.n_tiles == 1) ? 1 : 0;
   return L;
+}
+
+// rows of the statistics buffer the kernel writes: one per CTA when a CTA always covers the same columns
+int conv_num_stat_rows(const b2seg_conv_desc* d) {
+  int bw, bh, bn, tw, th, tn;
+  const int m_tiles = conv_geometry(d, &bw, &bh, &bn, &tw, &th, &tn);
+  const int n_extent = d->out[0].C;
+  int bn_sel = d->block_n;
+  if (bn_sel == 0) bn_sel = n_extent <= 64 ? 64 : (n_extent <= 128 ? 128 : 256);
+  const int n_tiles = (n_extent + bn_sel - 1) / bn_sel;
+  const int total = d->n_groups * m_tiles * n_tiles;
+  const int sms = num_sms();
+  return n_tiles == 1 ? (total < sms ? total : sms) : d->n_groups * m_tiles;
 }
 
 }  // namespace b2

@@ -227,10 +227,11 @@ struct BnBwdK {
   int cvb, rp;       // channel vectors per block-row, pixel rows per block
 };
 
-// Computes, for one window, the masked incoming gradient dyv[a][b][8] (sum of sources, act' applied) and xhat.
-template <int PASS>
-__global__ void bn_bwd_kernel(BnBwdK k) {
-  extern __shared__ float red[];  // PASS 0: [rp][cvb*16]
+// One thread owns 8 channels of one window (WIN = ph*pw pixels, compile-time so everything stays in registers).
+// PASS 0: per-channel partial sums of g and g*xhat (g = summed incoming gradient * act'(y)).  PASS 1: writes dx.
+template <int PASS, int WIN>
+__global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdK k) {
+  extern __shared__ float red[];  // PASS 0: [256][16]
   const int cvec_total = k.x.C / 8;
   const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
   const int v = blockIdx.x * k.cvb + tcv;
@@ -259,51 +260,66 @@ __global__ void bn_bwd_kernel(BnBwdK k) {
       const int wo = (int)(t % Wo); t /= Wo;
       const int ho = (int)(t % Ho);
       const int n = (int)(t / Ho);
-      // forward recompute over the window: y and first-argmax per channel
-      float xh[4][8], yv[4][8];
+      float xv[WIN][8], g[WIN][8];
+      // issue every load of the window first (memory-level parallelism), then compute
+#pragma unroll
+      for (int q = 0; q < WIN; ++q) {
+        const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
+        load8(vaddr(k.x, n, h, w, v * 8), xv[q]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[q][e] = 0.f;
+      }
+      float pooled[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pooled[e] = 0.f;
+      for (int s = 0; s < k.n_src; ++s) {
+        if (k.src[s].kind == 0) {
+#pragma unroll
+          for (int q = 0; q < WIN; ++q) {
+            const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
+            float f[8];
+            load8(vaddr(k.src[s].g, n, h, w, v * 8), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[q][e] += f[e];
+          }
+        } else {
+          float f[8];
+          load8(vaddr(k.src[s].g, n, ho, wo, v * 8), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pooled[e] += f[e];
+        }
+      }
+      // forward recompute: y, first arg-max of the window (TF/torch tie rule), activation derivative
+      float y[WIN][8];
       int amax[8];
       float ymax[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { amax[e] = 0; ymax[e] = -INFINITY; }
-      const int nwin = k.ph * k.pw;
-      for (int q = 0; q < nwin; ++q) {
-        const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
-        float f[8];
-        load8(vaddr(k.x, n, h, w, v * 8), f);
+#pragma unroll
+      for (int q = 0; q < WIN; ++q)
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float y = act_fwd(fmaf(f[e], sc[e], sf[e]), k.act);
-          yv[q][e] = y;
-          xh[q][e] = (f[e] - mu[e]) * rs[e];
-          if (y > ymax[e]) { ymax[e] = y; amax[e] = q; }
-        }
-      }
-      for (int q = 0; q < nwin; ++q) {
-        const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
-        float g[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = 0.f;
-        for (int s = 0; s < k.n_src; ++s) {
-          float f[8];
-          if (k.src[s].kind == 0) {
-            load8(vaddr(k.src[s].g, n, h, w, v * 8), f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] += f[e];
-          } else {
-            load8(vaddr(k.src[s].g, n, ho, wo, v * 8), f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) if (amax[e] == q) g[e] += f[e];
-          }
+          y[q][e] = act_fwd(fmaf(xv[q][e], sc[e], sf[e]), k.act);
+          if (y[q][e] > ymax[e]) { ymax[e] = y[q][e]; amax[e] = q; }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] *= act_bwd_from_y(yv[q][e], k.act);
+      for (int q = 0; q < WIN; ++q) {
+        float xh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float gg = g[q][e] + (amax[e] == q ? pooled[e] : 0.f);
+          gg *= act_bwd_from_y(y[q][e], k.act);
+          g[q][e] = gg;
+          xh[e] = (xv[q][e] - mu[e]) * rs[e];
+        }
         if (PASS == 0) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { acc_b[e] += g[e]; acc_g[e] += g[e] * xh[q][e]; }
+          for (int e = 0; e < 8; ++e) { acc_b[e] += g[q][e]; acc_g[e] += g[q][e] * xh[e]; }
         } else {
+          const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
           float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = k.scale ? sc[e] * (g[e] - cb[e] - xh[q][e] * cg[e]) : g[e];
+          for (int e = 0; e < 8; ++e) o[e] = k.scale ? sc[e] * (g[q][e] - cb[e] - xh[e] * cg[e]) : g[q][e];
           store8(vaddr(k.dx, n, h, w, v * 8), o);
         }
       }
@@ -329,33 +345,49 @@ __global__ void bn_bwd_kernel(BnBwdK k) {
     }
   }
 }
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_blocks, int C, float* dgamma, float* dbeta,
-                                       const float* __restrict__ rstd_unused) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_blocks, int C, float* dgamma, float* dbeta) {
+  // one warp per 32 channels x 8 slices of the partial list
+  __shared__ double sh[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   double b = 0.0, g = 0.0;
-  for (int i = 0; i < n_blocks; ++i) {
-    b += (double)partials[(size_t)i * 2 * C + c];
-    g += (double)partials[(size_t)i * 2 * C + C + c];
+  if (c < C)
+    for (int i = ty; i < n_blocks; i += 8) {
+      b += (double)partials[(size_t)i * 2 * C + c];
+      g += (double)partials[(size_t)i * 2 * C + C + c];
+    }
+  sh[0][ty][tx] = b;
+  sh[1][ty][tx] = g;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { b += sh[0][i][tx]; g += sh[1][i][tx]; }
+    dbeta[c] = (float)b;
+    dgamma[c] = (float)g;
   }
-  dbeta[c] = (float)b;
-  dgamma[c] = (float)g;
 }
 struct BnBwdLaunch : PreparedOp {
   BnBwdK k;
   bool has_bn;
   dim3 grid0, grid1;
-  int smem0;
-  int launch(cudaStream_t s) override {
-    if (has_bn) {
-      bn_bwd_kernel<0><<<grid0, 256, smem0, s>>>(k);
-      B2_CUDA_OK(cudaGetLastError());
-      bn_bwd_finalize_kernel<<<(k.x.C + 127) / 128, 128, 0, s>>>(k.partials, k.n_blocks, k.x.C, k.dgamma, k.dbeta, nullptr);
-      B2_CUDA_OK(cudaGetLastError());
+  int smem0, win;
+  template <int PASS>
+  int go(dim3 grid, int smem, cudaStream_t s) {
+    switch (win) {
+      case 1: bn_bwd_kernel<PASS, 1><<<grid, 256, smem, s>>>(k); break;
+      case 2: bn_bwd_kernel<PASS, 2><<<grid, 256, smem, s>>>(k); break;
+      default: bn_bwd_kernel<PASS, 4><<<grid, 256, smem, s>>>(k); break;
     }
-    bn_bwd_kernel<1><<<grid1, 256, 0, s>>>(k);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
+  }
+  int launch(cudaStream_t s) override {
+    if (has_bn) {
+      int rc = go<0>(grid0, smem0, s);
+      if (rc) return rc;
+      bn_bwd_finalize_kernel<<<(k.x.C + 31) / 32, 256, 0, s>>>(k.partials, k.n_blocks, k.x.C, k.dgamma, k.dbeta);
+      B2_CUDA_OK(cudaGetLastError());
+    }
+    return go<1>(grid1, 0, s);
   }
   int num_launches() const override { return has_bn ? 3 : 1; }
 };
@@ -381,7 +413,8 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
       k.ph = ph; k.pw = pw;
     }
   }
-  if (k.ph * k.pw > 4) { set_error("bn_bwd: pool window > 4 elements unsupported"); delete L; return nullptr; }
+  L->win = k.ph * k.pw;
+  if (L->win != 1 && L->win != 2 && L->win != 4) { set_error("bn_bwd: pool window must have 1, 2 or 4 elements"); delete L; return nullptr; }
   k.inv_count = (float)(1.0 / d->count);
   k.partials = reinterpret_cast<float*>(d->partials);
   k.n_blocks = d->n_blocks;
@@ -395,6 +428,8 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
   const long long n_win = (long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw);
   L->grid0 = dim3(gx, d->n_blocks > 0 ? d->n_blocks : 1);
   long long gy1 = (n_win + k.rp - 1) / k.rp;
+  const long long cap = (long long)num_sms() * 16 / gx + 1;
+  if (gy1 > cap) gy1 = cap;
   if (gy1 > 65535) gy1 = 65535;
   if (gy1 < 1) gy1 = 1;
   L->grid1 = dim3(gx, (unsigned)gy1);
