@@ -55,6 +55,14 @@ CONV_CASES = [
     (5, 1, 32, 64, 128, 1, 5, L.ACT_NONE, False),    # 1D, kernel 5, short rows span several samples
     (2, 16, 16, 64, 64, 1, 1, L.ACT_SIGMOID, False),
     (8, 4, 4, 256, 256, 3, 3, L.ACT_NONE, True),
+    # halo-tile kernel (H % 16 == 0, W % 8 == 0 / 1D W % 128 == 0); the big ones keep the weights resident in smem
+    (16, 64, 64, 64, 64, 3, 3, L.ACT_RELU, True),
+    (16, 64, 64, 128, 64, 3, 3, L.ACT_NONE, True),
+    (16, 64, 64, 8, 64, 3, 3, L.ACT_NONE, True),
+    (4, 32, 32, 256, 256, 3, 3, L.ACT_NONE, True),
+    (2, 32, 64, 128, 320, 3, 3, L.ACT_LEAKY, False),
+    (4, 1, 1024, 64, 64, 1, 3, L.ACT_NONE, True),
+    (40, 1, 1024, 64, 128, 1, 5, L.ACT_RELU, True),
 ]
 
 
@@ -108,7 +116,7 @@ def test_conv_concat_slot_and_offsets():
     assert float((obuf[..., :128].float() - 7).abs().max()) == 0 and float((obuf[..., 192:].float() - 7).abs().max()) == 0
 
 
-DGRAD_CASES = [(2, 16, 16, 64, 64, 3, 3), (2, 8, 8, 256, 128, 3, 3), (4, 8, 8, 128, 320, 3, 3), (3, 12, 20, 24, 40, 3, 3),
+DGRAD_CASES = [(16, 64, 64, 128, 64, 3, 3), (4, 32, 32, 256, 256, 3, 3), (40, 1, 1024, 64, 128, 1, 3), (2, 16, 16, 64, 64, 3, 3), (2, 8, 8, 256, 128, 3, 3), (4, 8, 8, 128, 320, 3, 3), (3, 12, 20, 24, 40, 3, 3),
                (2, 1, 128, 64, 128, 1, 3), (2, 16, 16, 64, 64, 1, 1)]
 
 
@@ -163,7 +171,7 @@ def test_conv_wgrad(N, H, W, Cin, Cout, kh, kw, ksplit):
     assert rel_l2(dw.view(Cout, kh, kw, Cin), w.grad.permute(0, 2, 3, 1)) < 1e-4
 
 
-TCONV_CASES = [(2, 8, 8, 128, 64, 4, 4), (2, 4, 4, 256, 128, 4, 4), (2, 1, 64, 128, 64, 1, 2), (1, 6, 10, 24, 16, 4, 4)]
+TCONV_CASES = [(2, 16, 16, 128, 64, 4, 4), (8, 32, 32, 64, 64, 4, 4), (2, 8, 8, 128, 64, 4, 4), (2, 4, 4, 256, 128, 4, 4), (2, 1, 64, 128, 64, 1, 2), (1, 6, 10, 24, 16, 4, 4)]
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout,kh,kw", TCONV_CASES)

@@ -53,10 +53,53 @@ def conv_num_mtiles(N, H, W):
     return -(-W // bw) * -(-H // bh) * -(-N // bn)
 
 
+def halo_geometry(desc):
+    """Mirror of b2::halo_geometry (csrc/conv_halo.cu): (bw, bh, bn) when the halo-tile kernel applies, else None."""
+    import os
+    if os.environ.get("B2SEG_NO_HALO"):
+        return None
+    wins = {}
+    for g in range(desc.n_groups):
+        for t in range(desc.taps_per_group):
+            tp = desc.taps[g * desc.taps_per_group + t]
+            w = wins.setdefault((g, tp.src), [tp.dh, tp.dh, tp.dw, tp.dw])
+            w[0], w[1], w[2], w[3] = min(w[0], tp.dh), max(w[1], tp.dh), min(w[2], tp.dw), max(w[3], tp.dw)
+    if len(wins) > 16 or len(wins) % desc.n_groups:
+        return None
+    KH = max(w[1] - w[0] + 1 for w in wins.values())
+    KW = max(w[3] - w[2] + 1 for w in wins.values())
+    if KH * KW < 2:
+        return None
+    per_group = len(wins) // desc.n_groups
+    for g in range(desc.n_groups):
+        if sum(1 for (gg, _) in wins if gg == g) != per_group:
+            return None
+    o = desc.out[0]
+    if o.H == 1:
+        if KH != 1 or o.W % 128:
+            return None
+        bw, bh = 128, 1
+    else:
+        if o.W % 8 or o.H % 16:
+            return None
+        bw, bh = 8, 16
+    if (bh + KH - 1) * (bw + KW - 1) * 128 > 24576 or bw + KW - 1 > 256 or bh + KH - 1 > 256:
+        return None
+    for i in range(desc.n_src):
+        if desc.src[i].N != o.N:
+            return None
+    return bw, bh, 1
+
+
 def conv_stat_rows(desc, num_sms=148):
     """Mirror of b2::conv_num_stat_rows (csrc/conv_gemm.cu) for a given SM count."""
     o = desc.out[0]
-    m_tiles = conv_num_mtiles(o.N, o.H, o.W)
+    geo = halo_geometry(desc)
+    if geo is not None:
+        bw, bh, bn = geo
+        m_tiles = -(-o.W // bw) * -(-o.H // bh) * -(-o.N // bn)
+    else:
+        m_tiles = conv_num_mtiles(o.N, o.H, o.W)
     bn = desc.block_n or (64 if o.C <= 64 else (128 if o.C <= 128 else 256))
     n_tiles = -(-o.C // bn)
     total = desc.n_groups * m_tiles * n_tiles
