@@ -1,6 +1,12 @@
 // Shared pieces of the implicit-GEMM convolution kernels (conv_gemm.cu: one TMA box per tap; conv_halo.cu: one halo
 // tile per channel block reused by every tap): tile geometry, epilogue parameters and the epilogue itself
 // (TMEM -> registers -> bias/activation -> bf16 staging in smem -> coalesced, strided store + BN statistics).
+//
+// The epilogue is written to be cheap in *issued instructions* (round-1 ncu: the first version spent ~3000 SASS
+// instructions per warp per 128x64 tile and capped the high-resolution layers at 13 % tensor-pipe activity):
+// bias comes from shared memory by 128-bit broadcast loads, bounds checks are hoisted to per-tile / per-chunk
+// uniform flags, output addresses are tile-invariant offsets plus one per-tile base, and the BatchNorm statistics
+// are accumulated from the registers of the store pass and reduced with two shuffle steps.
 #pragma once
 #include "common.h"
 #include "ptx.cuh"
@@ -12,7 +18,7 @@ constexpr int kBlockK = 64;
 constexpr int kStgPitch = 144;                        // staging row pitch (64 bf16 + 16 B pad: conflict-free 16 B stores)
 constexpr int kStgBytes = kBlockM * kStgPitch;
 constexpr int kConvThreads = 192;
-constexpr int kColPartBytes = 2 * 64 * 2 * 4;
+constexpr int kColPartBytes = 4 * 64 * 2 * 4 + 256 * 4;  // [4 warps][64 cols][sum, sumsq] + bias tile [256]
 
 // everything the tile scheduler and the epilogue need (embedded as `e` in each kernel's parameter struct)
 struct ConvEpiParams {
@@ -33,41 +39,92 @@ struct ConvEpiParams {
   int stats_per_cta;   // 1: one statistics row per CTA (n_tiles == 1), else one per (group, m_tile)
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  switch (act) {
-    case B2SEG_ACT_RELU: return fmaxf(x, 0.f);
-    case B2SEG_ACT_LEAKY: return x > 0.f ? x : 0.3f * x;
-    case B2SEG_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
-    default: return x;
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  if (ACT == B2SEG_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == B2SEG_ACT_LEAKY) return fmaxf(x, 0.3f * x);
+  if (ACT == B2SEG_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
+
+template <int ACT>
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[32], const float* sb, uint32_t (&packed)[16]) {
+  const float4* b4 = reinterpret_cast<const float4*>(sb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = b4[j];  // same address in every lane: shared-memory broadcast
+    const float x0 = act_t<ACT>(__uint_as_float(v[4 * j + 0]) + b.x);
+    const float x1 = act_t<ACT>(__uint_as_float(v[4 * j + 1]) + b.y);
+    const float x2 = act_t<ACT>(__uint_as_float(v[4 * j + 2]) + b.z);
+    const float x3 = act_t<ACT>(__uint_as_float(v[4 * j + 3]) + b.w);
+    packed[2 * j] = pack_bf16x2(x0, x1);
+    packed[2 * j + 1] = pack_bf16x2(x2, x3);
   }
 }
 
 // Runs on warps 2..5 (threads 64..191).  tfull/tempty: the two-deep TMEM accumulator hand-shake with the MMA warp.
+// scratch: kColPartBytes of shared memory.
 template <int BLOCK_N>
-__device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* staging, float* colpart, uint64_t* tfull_bar,
+__device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* staging, float* scratch, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tmem_base) {
+  constexpr int kChunks = BLOCK_N / 64;
+  float* colpart = scratch;            // [4][64][2]
+  float* sbias = scratch + 4 * 64 * 2; // [BLOCK_N]
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
   const int et = threadIdx.x - 64;           // 0..127
+  const int ew = et >> 5;                    // epilogue warp 0..3
   const int row = (warp & 3) * 32 + lane;    // TMEM lane == tile row owned by this thread
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const int bwm = p.bw - 1, bhm = p.bh - 1;
-  constexpr int kChunks = BLOCK_N / 64;
+  // kernel-invariant scalars (keep them in registers instead of re-reading the constant bank)
+  const int bw = p.bw, bh = p.bh, bn = p.bn, lbw = p.lbw, lbwh = p.lbwh;
+  const int gN = p.gN, gH = p.gH, gW = p.gW, n_extent = p.n_extent, act = p.act;
+  const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, tiles_w = p.tiles_w, tiles_h = p.tiles_h, total_tiles = p.total_tiles;
+  const bool has_stats = p.stats != nullptr, per_cta = p.stats_per_cta != 0;
+  const int mul_mode = p.mul_mode, mul_c = p.mul_c;
+  const long long osn = p.out_sn, osh = p.out_sh, osw = p.out_sw;
+  const long long msn = p.mul_sn, msh = p.mul_sh, msw = p.mul_sw;
+  const float* bias = p.bias;
+  const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row of the store pass
+  // tile-invariant decomposition of this thread's rows
+  const int mdn = row >> lbwh, mdh = (row >> lbw) & (bh - 1), mdw = row & (bw - 1);
+  long long rel[8], mrel[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 16 * i;
+    const int dn = r >> lbwh, dh = (r >> lbw) & (bh - 1), dw = r & (bw - 1);
+    rel[i] = dn * osn + dh * osh + dw * osw;
+    mrel[i] = dn * msn + dh * msh + dw * msw;
+  }
   float cta_s[kChunks], cta_q[kChunks];      // per-CTA BN statistics (threads et < 64)
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) { cta_s[c] = 0.f; cta_q[c] = 0.f; }
-  const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row of the store pass
+  if (n_tiles == 1) {                         // one column range for the whole kernel: stage the bias once
+    for (int i = et; i < BLOCK_N; i += 128) sbias[i] = (bias != nullptr && i < n_extent) ? __ldg(bias + i) : 0.f;
+    named_bar_sync(1, 128);
+  }
   uint32_t acc = 0, acc_phase = 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int n_tile = tile % p.n_tiles;
-    const int rest = tile / p.n_tiles;
-    const int m_tile = rest % p.m_tiles;
-    const int g = rest / p.m_tiles;
-    const int w0 = (m_tile % p.tiles_w) * p.bw;
-    const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
-    const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.bn;
-    const bool my_valid = (n0 + (row >> p.lbwh)) < p.gN && (h0 + ((row >> p.lbw) & bhm)) < p.gH && (w0 + (row & bwm)) < p.gW;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n_tile = tile % n_tiles;
+    const int rest = tile / n_tiles;
+    const int m_tile = rest % m_tiles;
+    const int g = rest / m_tiles;
+    const int w0 = (m_tile % tiles_w) * bw;
+    const int h0 = ((m_tile / tiles_w) % tiles_h) * bh;
+    const int n0 = (m_tile / (tiles_w * tiles_h)) * bn;
+    const bool tile_full = (n0 + bn <= gN) && (h0 + bh <= gH) && (w0 + bw <= gW);
+    const bool my_valid = tile_full || ((n0 + mdn) < gN && (h0 + mdh) < gH && (w0 + mdw) < gW);
+    const long long tile_off = n0 * osn + h0 * osh + w0 * osw;
+    const long long mtile_off = n0 * msn + h0 * msh + w0 * msw;
+    __nv_bfloat16* const out_base = reinterpret_cast<__nv_bfloat16*>(p.out_ptr[g]) + tile_off;
+    if (n_tiles > 1) {
+      named_bar_sync(1, 128);                 // previous tile's readers of sbias are done
+      for (int i = et; i < BLOCK_N; i += 128) {
+        const int cc = n_tile * BLOCK_N + i;
+        sbias[i] = (bias != nullptr && cc < n_extent) ? __ldg(bias + cc) : 0.f;
+      }
+      named_bar_sync(1, 128);
+    }
 
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
@@ -75,16 +132,18 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
     for (int c = 0; c < kChunks; ++c) {
       const int col0 = n_tile * BLOCK_N + c * 64;
       const int cc_st = col0 + vq * 8;
+      const bool col_ok = cc_st < n_extent;
       // dgrad fusion: fetch the forward activations whose sign masks this chunk early, so the loads overlap the TMEM read
       uint4 yv[8];
-      if (p.mul_mode != 0) {
+      const bool do_mul = mul_mode != 0 && cc_st < mul_c;
+      if (do_mul) {
+        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(p.mul_ptr) + mtile_off + cc_st;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r0 + 16 * i;
-          const int pn = n0 + (r >> p.lbwh), ph = h0 + ((r >> p.lbw) & bhm), pw = w0 + (r & bwm);
+          const bool ok = tile_full || ((n0 + (r >> lbwh)) < gN && (h0 + ((r >> lbw) & (bh - 1))) < gH && (w0 + (r & (bw - 1))) < gW);
           yv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 -> derivative 1
-          if (pn < p.gN && ph < p.gH && pw < p.gW && cc_st < p.mul_c)
-            yv[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mul_ptr) + pn * p.mul_sn + ph * p.mul_sh + pw * p.mul_sw + cc_st));
+          if (ok) yv[i] = __ldg(reinterpret_cast<const uint4*>(mb + mrel[i]));
         }
       }
 #pragma unroll
@@ -93,19 +152,14 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
         tmem_ld32(tmem_base + lane_base + acc * BLOCK_N + c * 64 + half * 32, v);
         tmem_ld_wait();
         uint32_t packed[16];
+        const float* sb = sbias + c * 64 + half * 32;
+        if (act == B2SEG_ACT_NONE) bias_act_pack<B2SEG_ACT_NONE>(v, sb, packed);
+        else if (act == B2SEG_ACT_RELU) bias_act_pack<B2SEG_ACT_RELU>(v, sb, packed);
+        else if (act == B2SEG_ACT_LEAKY) bias_act_pack<B2SEG_ACT_LEAKY>(v, sb, packed);
+        else bias_act_pack<B2SEG_ACT_SIGMOID>(v, sb, packed);
+        if (!my_valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int cc = col0 + half * 32 + 2 * j;
-          float x0 = __uint_as_float(v[2 * j]);
-          float x1 = __uint_as_float(v[2 * j + 1]);
-          if (p.bias != nullptr) {
-            if (cc < p.n_extent) x0 += __ldg(p.bias + cc);
-            if (cc + 1 < p.n_extent) x1 += __ldg(p.bias + cc + 1);
-          }
-          x0 = apply_act(x0, p.act);
-          x1 = apply_act(x1, p.act);
-          if (!my_valid) { x0 = 0.f; x1 = 0.f; }
-          packed[j] = pack_bf16x2(x0, x1);
+          for (int j = 0; j < 16; ++j) packed[j] = 0u;
         }
         uint4* dst = reinterpret_cast<uint4*>(staging + row * kStgPitch + half * 64);
 #pragma unroll
@@ -118,64 +172,86 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
       named_bar_sync(1, 128);
-      // ---- coalesced store of the 128 x 64 chunk (+ optional derivative-mask multiply)
+      // ---- coalesced store of the 128 x 64 chunk (+ derivative mask) and column statistics from the same registers
+      float s[8], q2[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[e] = 0.f; q2[e] = 0.f; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = r0 + 16 * i;
-        const int pn = n0 + (r >> p.lbwh), ph = h0 + ((r >> p.lbw) & bhm), pw = w0 + (r & bwm);
-        if (pn < p.gN && ph < p.gH && pw < p.gW && cc_st < p.n_extent) {
-          uint4 val = *reinterpret_cast<const uint4*>(staging + r * kStgPitch + vq * 16);
-          if (p.mul_mode != 0) {
-            const __nv_bfloat16* ye = reinterpret_cast<const __nv_bfloat16*>(&yv[i]);
-            __nv_bfloat16* ve = reinterpret_cast<__nv_bfloat16*>(&val);
-            const float neg = p.mul_mode == B2SEG_ACT_LEAKY ? 0.3f : 0.f;
+        uint4 val = *reinterpret_cast<const uint4*>(staging + r * kStgPitch + vq * 16);
+        if (has_stats) {
+          const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (!(__bfloat162float(ye[e]) > 0.f)) ve[e] = __float2bfloat16(__bfloat162float(ve[e]) * neg);
+          for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(w4[e] << 16), hi = __uint_as_float(w4[e] & 0xffff0000u);
+            s[2 * e] += lo; q2[2 * e] = fmaf(lo, lo, q2[2 * e]);
+            s[2 * e + 1] += hi; q2[2 * e + 1] = fmaf(hi, hi, q2[2 * e + 1]);
           }
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out_ptr[g]) + pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + cc_st;
-          *reinterpret_cast<uint4*>(op) = val;
+        }
+        const bool ok = tile_full || ((n0 + (r >> lbwh)) < gN && (h0 + ((r >> lbw) & (bh - 1))) < gH && (w0 + (r & (bw - 1))) < gW);
+        if (ok && col_ok) {
+          if (do_mul) {
+            const uint32_t y4[4] = {yv[i].x, yv[i].y, yv[i].z, yv[i].w};
+            uint32_t o4[4] = {val.x, val.y, val.z, val.w};
+            const float neg = mul_mode == B2SEG_ACT_LEAKY ? 0.3f : 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // bf16 sign tests on the raw bits: positive and non-zero <=> (bits & 0x7fff) != 0 and sign bit clear
+              const uint32_t ylo = y4[e] & 0xffffu, yhi = y4[e] >> 16;
+              float lo = __uint_as_float(o4[e] << 16), hi = __uint_as_float(o4[e] & 0xffff0000u);
+              if (!((ylo & 0x8000u) == 0 && (ylo & 0x7fffu) != 0)) lo *= neg;
+              if (!((yhi & 0x8000u) == 0 && (yhi & 0x7fffu) != 0)) hi *= neg;
+              o4[e] = pack_bf16x2(lo, hi);
+            }
+            val = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          }
+          *reinterpret_cast<uint4*>(out_base + rel[i] + cc_st) = val;
         }
       }
-      // ---- BatchNorm statistics of the stored values: column sum / sum of squares
-      if (p.stats != nullptr) {
-        const int col = et & 63, hf = et >> 6;
-        float s = 0.f, ss = 0.f;
-        const uint8_t* sp = staging + (hf * 64) * kStgPitch + col * 2;
-#pragma unroll 16
-        for (int r = 0; r < 64; ++r) {
-          const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sp + r * kStgPitch));
-          s += x;
-          ss += x * x;
+      if (has_stats) {
+        // lanes l, l^8, l^16, l^24 own the same 8 columns
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
+          q2[e] += __shfl_xor_sync(0xffffffffu, q2[e], 8);
+          s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
+          q2[e] += __shfl_xor_sync(0xffffffffu, q2[e], 16);
         }
-        colpart[(hf * 64 + col) * 2 + 0] = s;
-        colpart[(hf * 64 + col) * 2 + 1] = ss;
+        if (lane < 8) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            colpart[(ew * 64 + lane * 8 + e) * 2 + 0] = s[e];
+            colpart[(ew * 64 + lane * 8 + e) * 2 + 1] = q2[e];
+          }
+        }
         named_bar_sync(2, 128);
         if (et < 64) {
-          const float s2 = colpart[et * 2] + colpart[(64 + et) * 2];
-          const float ss2 = colpart[et * 2 + 1] + colpart[(64 + et) * 2 + 1];
-          if (p.stats_per_cta) {
+          float s2 = 0.f, ss2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { s2 += colpart[(w * 64 + et) * 2]; ss2 += colpart[(w * 64 + et) * 2 + 1]; }
+          if (per_cta) {
             cta_s[c] += s2;
             cta_q[c] += ss2;
-          } else if (col0 + et < p.n_extent) {
-            float* st = p.stats + (size_t)(g * p.m_tiles + m_tile) * 2 * p.n_extent;
+          } else if (col0 + et < n_extent) {
+            float* st = p.stats + (size_t)(g * m_tiles + m_tile) * 2 * n_extent;
             st[col0 + et] = s2;
-            st[p.n_extent + col0 + et] = ss2;
+            st[n_extent + col0 + et] = ss2;
           }
         }
       }
-      named_bar_sync(1, 128);  // staging is reused by the next chunk
+      named_bar_sync(1, 128);  // staging / colpart are reused by the next chunk
     }
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }
-  if (p.stats != nullptr && p.stats_per_cta && et < 64) {
-    float* st = p.stats + (size_t)blockIdx.x * 2 * p.n_extent;
+  if (has_stats && per_cta && et < 64) {
+    float* st = p.stats + (size_t)blockIdx.x * 2 * n_extent;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c)
-      if (c * 64 + et < p.n_extent) {
+      if (c * 64 + et < n_extent) {
         st[c * 64 + et] = cta_s[c];
-        st[p.n_extent + c * 64 + et] = cta_q[c];
+        st[n_extent + c * 64 + et] = cta_q[c];
       }
   }
 }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* bres_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
-  float* colpart = reinterpret_cast<float*>(tmem_slot + 4);
+  float* colpart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
