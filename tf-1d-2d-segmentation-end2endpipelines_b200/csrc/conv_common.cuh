@@ -17,8 +17,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kStgPitch = 144;                        // staging row pitch (64 bf16 + 16 B pad: conflict-free 16 B stores)
 constexpr int kStgBytes = kBlockM * kStgPitch;
-constexpr int kConvThreads = 192;
-constexpr int kColPartBytes = 4 * 64 * 2 * 4 + 256 * 4;  // [4 warps][64 cols][sum, sumsq] + bias tile [256]
+constexpr int kEpiWarps = 8;                          // two per TMEM lane quadrant: (quadrant, 32-column half)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
+constexpr int kColPartBytes = kEpiWarps * 64 * 2 * 4 + 256 * 4;  // [8 warps][64 cols][sum, sumsq] + bias tile [256]
 
 // everything the tile scheduler and the epilogue need (embedded as `e` in each kernel's parameter struct)
 struct ConvEpiParams {
@@ -62,18 +64,19 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[32], const flo
   }
 }
 
-// Runs on warps 2..5 (threads 64..191).  tfull/tempty: the two-deep TMEM accumulator hand-shake with the MMA warp.
+// Runs on warps 2..9 (threads 64..319): warp w reads TMEM lanes 32*(w%4).. and the 32-column half (w-2)/4 of each chunk.  tfull/tempty: the two-deep TMEM accumulator hand-shake with the MMA warp.
 // scratch: kColPartBytes of shared memory.
 template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* staging, float* scratch, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tmem_base) {
   constexpr int kChunks = BLOCK_N / 64;
-  float* colpart = scratch;            // [4][64][2]
-  float* sbias = scratch + 4 * 64 * 2; // [BLOCK_N]
+  float* colpart = scratch;                    // [kEpiWarps][64][2]
+  float* sbias = scratch + kEpiWarps * 64 * 2; // [BLOCK_N]
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int et = threadIdx.x - 64;           // 0..127
-  const int ew = et >> 5;                    // epilogue warp 0..3
+  const int et = threadIdx.x - 64;           // 0..255
+  const int ew = et >> 5;                    // epilogue warp 0..7
+  const int half = ew >> 2;                  // which 32 columns of each 64-column chunk this warp converts
   const int row = (warp & 3) * 32 + lane;    // TMEM lane == tile row owned by this thread
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // kernel-invariant scalars (keep them in registers instead of re-reading the constant bank)
@@ -85,13 +88,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   const long long osn = p.out_sn, osh = p.out_sh, osw = p.out_sw;
   const long long msn = p.mul_sn, msh = p.mul_sh, msw = p.mul_sw;
   const float* bias = p.bias;
-  const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row of the store pass
+  const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row (of 4, stride 32) of the store pass
   // tile-invariant decomposition of this thread's rows
   const int mdn = row >> lbwh, mdh = (row >> lbw) & (bh - 1), mdw = row & (bw - 1);
-  long long rel[8], mrel[8];
+  long long rel[4], mrel[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + 16 * i;
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 32 * i;
     const int dn = r >> lbwh, dh = (r >> lbw) & (bh - 1), dw = r & (bw - 1);
     rel[i] = dn * osn + dh * osh + dw * osw;
     mrel[i] = dn * msn + dh * msh + dw * msw;
@@ -100,8 +103,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) { cta_s[c] = 0.f; cta_q[c] = 0.f; }
   if (n_tiles == 1) {                         // one column range for the whole kernel: stage the bias once
-    for (int i = et; i < BLOCK_N; i += 128) sbias[i] = (bias != nullptr && i < n_extent) ? __ldg(bias + i) : 0.f;
-    named_bar_sync(1, 128);
+    for (int i = et; i < BLOCK_N; i += kEpiThreads) sbias[i] = (bias != nullptr && i < n_extent) ? __ldg(bias + i) : 0.f;
+    named_bar_sync(1, kEpiThreads);
   }
   uint32_t acc = 0, acc_phase = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -118,12 +121,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
     const long long mtile_off = n0 * msn + h0 * msh + w0 * msw;
     __nv_bfloat16* const out_base = reinterpret_cast<__nv_bfloat16*>(p.out_ptr[g]) + tile_off;
     if (n_tiles > 1) {
-      named_bar_sync(1, 128);                 // previous tile's readers of sbias are done
-      for (int i = et; i < BLOCK_N; i += 128) {
+      named_bar_sync(1, kEpiThreads);         // previous tile's readers of sbias are done
+      for (int i = et; i < BLOCK_N; i += kEpiThreads) {
         const int cc = n_tile * BLOCK_N + i;
         sbias[i] = (bias != nullptr && cc < n_extent) ? __ldg(bias + cc) : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
     }
 
     mbar_wait(&tfull_bar[acc], acc_phase);
@@ -134,20 +137,19 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
       const int cc_st = col0 + vq * 8;
       const bool col_ok = cc_st < n_extent;
       // dgrad fusion: fetch the forward activations whose sign masks this chunk early, so the loads overlap the TMEM read
-      uint4 yv[8];
+      uint4 yv[4];
       const bool do_mul = mul_mode != 0 && cc_st < mul_c;
       if (do_mul) {
         const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(p.mul_ptr) + mtile_off + cc_st;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 32 * i;
           const bool ok = tile_full || ((n0 + (r >> lbwh)) < gN && (h0 + ((r >> lbw) & (bh - 1))) < gH && (w0 + (r & (bw - 1))) < gW);
           yv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 -> derivative 1
           if (ok) yv[i] = __ldg(reinterpret_cast<const uint4*>(mb + mrel[i]));
         }
       }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_base + acc * BLOCK_N + c * 64 + half * 32, v);
         tmem_ld_wait();
@@ -171,14 +173,14 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       // ---- coalesced store of the 128 x 64 chunk (+ derivative mask) and column statistics from the same registers
       float s[8], q2[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { s[e] = 0.f; q2[e] = 0.f; }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 16 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
         uint4 val = *reinterpret_cast<const uint4*>(staging + r * kStgPitch + vq * 16);
         if (has_stats) {
           const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
@@ -225,11 +227,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
             colpart[(ew * 64 + lane * 8 + e) * 2 + 1] = q2[e];
           }
         }
-        named_bar_sync(2, 128);
+        named_bar_sync(2, kEpiThreads);
         if (et < 64) {
           float s2 = 0.f, ss2 = 0.f;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { s2 += colpart[(w * 64 + et) * 2]; ss2 += colpart[(w * 64 + et) * 2 + 1]; }
+          for (int w = 0; w < kEpiWarps; ++w) { s2 += colpart[(w * 64 + et) * 2]; ss2 += colpart[(w * 64 + et) * 2 + 1]; }
           if (per_cta) {
             cta_s[c] += s2;
             cta_q[c] += ss2;
@@ -240,7 +242,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
           }
         }
       }
-      named_bar_sync(1, 128);  // staging / colpart are reused by the next chunk
+      named_bar_sync(1, kEpiThreads);  // staging / colpart are reused by the next chunk
     }
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -109,6 +109,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN ? 1 : 0);
+      // descriptors are built once; per MMA only the 14-bit start-address field (16-byte units) changes
+      const uint64_t adesc0 = make_smem_desc(0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 16, 1024);
+      const uint32_t smem16 = smem_u32(smem) >> 4;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -117,15 +121,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + kAStageBytes;
+          const uint32_t a16 = smem16 + stage * (Cfg::kStageBytes >> 4);
+          const uint64_t ad = adesc0 + a16;
+          const uint64_t bd = bdesc0 + (a16 + (kAStageBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                        : make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* bres_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
-  float* colpart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+  uint32_t* s_tapoff = tmem_slot + 4;           // per tap: start-row offset inside the halo tile, in 16-byte units
+  float* colpart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapoff + B2SEG_MAX_TAPS) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,8 +67,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     tma_prefetch_desc(&p.bmap);
     for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kHaloMaxBStages; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     mbar_init(bres_bar, 1);
+    for (int t = 0; t < B2SEG_MAX_TAPS; ++t) s_tapoff[t] = (uint32_t)(p.taps[t].x * p.ww + p.taps[t].y) * 8u;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -109,6 +111,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         const int w0 = (m_tile % e.tiles_w) * e.bw;
         const int h0 = ((m_tile / e.tiles_w) % e.tiles_h) * e.bh;
         const int n0 = (m_tile / (e.tiles_w * e.tiles_h)) * e.bn;
+        {
+          // pull the halo tiles this CTA needs two tiles from now into L2 (each activation byte is read from HBM once,
+          // so without this every A stage pays full HBM latency with only two stages in flight)
+          const int ptile = tile + 2 * (int)gridDim.x;
+          if (ptile < e.total_tiles && (e.n_tiles == 1 || (ptile % e.n_tiles) == 0)) {
+            const int prest = ptile / e.n_tiles;
+            const int pm = prest % e.m_tiles, pg = prest / e.m_tiles;
+            const int pw0 = (pm % e.tiles_w) * e.bw, ph0 = ((pm / e.tiles_w) % e.tiles_h) * e.bh, pn0 = (pm / (e.tiles_w * e.tiles_h)) * e.bn;
+            for (int wi = 0; wi < p.wins_per_group; ++wi) {
+              const HaloWin win = p.wins[pg * p.wins_per_group + wi];
+              for (int cb = 0; cb < p.kc_blocks; ++cb) tma_prefetch_4d(&p.amap[win.map], cb * kBlockK, pw0 + win.ow0, ph0 + win.oh0, pn0);
+            }
+          }
+        }
         for (int wi = 0; wi < p.wins_per_group; ++wi) {
           const HaloWin win = p.wins[g * p.wins_per_group + wi];
           for (int cb = 0; cb < p.kc_blocks; ++cb) {
@@ -140,46 +156,51 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN ? 1 : 0);
+      // descriptors are built once; per MMA only the 14-bit start-address field (16-byte units) changes
+      const uint64_t adesc0 = make_smem_desc(0, 16, p.sbo);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 16, 1024);
+      const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+      const int wins_per_group = p.wins_per_group, kc_blocks = p.kc_blocks, b_stages = p.b_stages;
       uint32_t sa = 0, pa = 0, sb_i = 0, pb = 0, acc = 0, acc_phase = 0;
       if (B_RES) {
         mbar_wait(bres_bar, 0);
         tc_fence_after();
       }
-      const uint32_t sB_addr = smem_u32(sB);
       for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
         const int g = (tile / e.n_tiles) / e.m_tiles;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         uint32_t accumulate = 0;
-        int res_idx = 0;
-        for (int wi = 0; wi < p.wins_per_group; ++wi) {
-          const HaloWin win = p.wins[g * p.wins_per_group + wi];
-          for (int cb = 0; cb < p.kc_blocks; ++cb) {
+        uint32_t res16 = sB16;
+        for (int wi = 0; wi < wins_per_group; ++wi) {
+          const int tap_begin = p.wins[g * wins_per_group + wi].tap_begin, tap_end = p.wins[g * wins_per_group + wi].tap_end;
+          for (int cb = 0; cb < kc_blocks; ++cb) {
             mbar_wait(&fullA[sa], pa);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + sa * kHaloABytes);
-            for (int t = win.tap_begin; t < win.tap_end; ++t) {
-              uint32_t b_addr;
+            const uint64_t ad_stage = adesc0 + (sA16 + sa * (kHaloABytes >> 4));
+            uint32_t off_next = s_tapoff[tap_begin];
+            for (int t = tap_begin; t < tap_end; ++t) {
+              const uint32_t off = off_next;
+              if (t + 1 < tap_end) off_next = s_tapoff[t + 1];
+              uint64_t bd;
               if (B_RES) {
-                b_addr = sB_addr + (res_idx++) * kBStageBytes;
+                bd = bdesc0 + res16;
+                res16 += kBStageBytes >> 4;
               } else {
                 mbar_wait(&fullB[sb_i], pb);
                 tc_fence_after();
-                b_addr = sB_addr + sb_i * kBStageBytes;
+                bd = bdesc0 + (sB16 + sb_i * (kBStageBytes >> 4));
               }
-              const uint32_t a_addr = a_base + (uint32_t)(p.taps[t].x * p.ww + p.taps[t].y) * 128u;
+              const uint64_t ad = ad_stage + off;
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
-                const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, p.sbo);
-                const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                            : make_smem_desc(b_addr + k * 32, 16, 1024);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                umma_bf16(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
                 accumulate = 1;
               }
               if (!B_RES) {
                 umma_commit(&emptyB[sb_i]);
-                if (++sb_i == (uint32_t)p.b_stages) { sb_i = 0; pb ^= 1; }
+                if (++sb_i == (uint32_t)b_stages) { sb_i = 0; pb ^= 1; }
               }
             }
             umma_commit(&emptyA[sa]);
@@ -337,7 +358,7 @@ PreparedOp* prepare_conv_halo(const b2seg_conv_desc* d) {
     if (encode_weight_map(&kp.bmap, d->weights, d->w_cout, d->w_taps, d->w_cin, 64, kBlockK) != 0) { delete L; return nullptr; }
   }
   const int b_stage = L->block_n * kBlockK * 2;
-  const int fixed = 1024 + kHaloAStages * kHaloABytes + kStgBytes + (2 * kHaloAStages + 2 * kHaloMaxBStages + 5) * 8 + 16 + kColPartBytes + 64;
+  const int fixed = 1024 + kHaloAStages * kHaloABytes + kStgBytes + (2 * kHaloAStages + 2 * kHaloMaxBStages + 5) * 8 + 16 + B2SEG_MAX_TAPS * 4 + kColPartBytes + 64;
   const int b_budget = kHaloSmemBudget - fixed;
   const int res_tiles = d->n_groups * d->taps_per_group * kp.kc_blocks;
   static const bool no_res = getenv("B2SEG_NO_BRES") != nullptr;

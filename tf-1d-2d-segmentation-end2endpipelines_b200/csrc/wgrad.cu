@@ -95,18 +95,16 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   } else if (warp == 1) {
     if (lane == 0 && n_iter > 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      const uint64_t desc0 = make_smem_desc(0, kWgPix * 128, 1024);  // both operands MN-major: LBO = one 64-channel box
+      const uint32_t smem16 = smem_u32(smem) >> 4;
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < n_iter; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + kWgABytes;
+        const uint32_t a16 = smem16 + stage * (Cfg::kStageBytes >> 4);
+        const uint64_t ad = desc0 + a16, bd = desc0 + (a16 + (kWgABytes >> 4));
 #pragma unroll
-        for (int k = 0; k < kWgPix / 16; ++k) {
-          const uint64_t adesc = make_smem_desc(a_addr + k * 2048, kWgPix * 128, 1024);
-          const uint64_t bdesc = make_smem_desc(b_addr + k * 2048, kWgPix * 128, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < kWgPix / 16; ++k) umma_bf16(tmem_base, ad + k * 128, bd + k * 128, idesc, (it | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
