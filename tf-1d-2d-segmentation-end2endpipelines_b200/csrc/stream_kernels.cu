@@ -150,7 +150,56 @@ struct BnActK {
   const float* scale; const float* shift;
   int act, n_out, ph, pw;
 };
-__global__ void bn_act_kernel(BnActK k) {
+// One thread owns 8 channels of U windows (U*WIN pixels in flight: all loads are issued before any use).
+template <int WIN, int U>
+__global__ void __launch_bounds__(256) bn_act_kernel(BnActK k) {
+  const int cv = k.x.C / 8;
+  const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
+  const long long n_win = (long long)k.x.N * Ho * Wo;
+  const long long total = ((n_win + U - 1) / U) * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    const long long wbase = (i / cv) * U;
+    float sc[8], sf[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = k.scale ? __ldg(k.scale + v * 8 + e) : 1.f;
+      sf[e] = k.shift ? __ldg(k.shift + v * 8 + e) : 0.f;
+    }
+    float f[U][WIN][8];
+    int wn[U], wh[U], ww[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      long long t = wbase + u < n_win ? wbase + u : n_win - 1;
+      ww[u] = (int)(t % Wo); t /= Wo;
+      wh[u] = (int)(t % Ho);
+      wn[u] = (int)(t / Ho);
+#pragma unroll
+      for (int q = 0; q < WIN; ++q) load8(vaddr(k.x, wn[u], wh[u] * k.ph + q / k.pw, ww[u] * k.pw + q % k.pw, v * 8), f[u][q]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (wbase + u >= n_win) break;
+      float mx[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mx[e] = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < WIN; ++q) {
+        const int h = wh[u] * k.ph + q / k.pw, w = ww[u] * k.pw + q % k.pw;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[u][q][e] = act_fwd(fmaf(f[u][q][e], sc[e], sf[e]), k.act);
+          mx[e] = fmaxf(mx[e], f[u][q][e]);
+        }
+        if (k.n_out > 0) store8(vaddr(k.out0, wn[u], h, w, v * 8), f[u][q]);
+        if (k.n_out > 1) store8(vaddr(k.out1, wn[u], h, w, v * 8), f[u][q]);
+      }
+      if (k.pooled.ptr) store8(vaddr(k.pooled, wn[u], wh[u], ww[u], v * 8), mx);
+    }
+  }
+}
+// generic window size (UNet3+ pools 4/8/16): sequential over the window
+__global__ void bn_act_generic_kernel(BnActK k) {
   const int cv = k.x.C / 8;
   const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
   const long long total = (long long)k.x.N * Ho * Wo * cv;
@@ -160,15 +209,13 @@ __global__ void bn_act_kernel(BnActK k) {
     const int wo = (int)(pix % Wo); pix /= Wo;
     const int ho = (int)(pix % Ho);
     const int n = (int)(pix / Ho);
-    float sc[8], sf[8];
+    float sc[8], sf[8], mx[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       sc[e] = k.scale ? __ldg(k.scale + v * 8 + e) : 1.f;
       sf[e] = k.shift ? __ldg(k.shift + v * 8 + e) : 0.f;
+      mx[e] = -INFINITY;
     }
-    float mx[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) mx[e] = -INFINITY;
     for (int a = 0; a < k.ph; ++a)
       for (int b = 0; b < k.pw; ++b) {
         const int h = ho * k.ph + a, w = wo * k.pw + b;
@@ -188,8 +235,23 @@ __global__ void bn_act_kernel(BnActK k) {
 struct BnActLaunch : PreparedOp {
   BnActK k;
   int launch(cudaStream_t s) override {
-    const long long work = (long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw) * (k.x.C / 8);
-    bn_act_kernel<<<grid_for(work, 256), 256, 0, s>>>(k);
+    const long long n_win = (long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw);
+    const int cv = k.x.C / 8;
+    const int win = k.ph * k.pw;
+    const int cap = num_sms() * 16;
+    if (win == 1) {
+      int g = grid_for(((n_win + 3) / 4) * cv, 256); if (g > cap) g = cap;
+      bn_act_kernel<1, 4><<<g, 256, 0, s>>>(k);
+    } else if (win == 2) {
+      int g = grid_for(((n_win + 1) / 2) * cv, 256); if (g > cap) g = cap;
+      bn_act_kernel<2, 2><<<g, 256, 0, s>>>(k);
+    } else if (win == 4) {
+      int g = grid_for(n_win * cv, 256); if (g > cap) g = cap;
+      bn_act_kernel<4, 1><<<g, 256, 0, s>>>(k);
+    } else {
+      int g = grid_for(n_win * cv, 256); if (g > cap) g = cap;
+      bn_act_generic_kernel<<<g, 256, 0, s>>>(k);
+    }
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -227,9 +289,10 @@ struct BnBwdK {
   int cvb, rp;       // channel vectors per block-row, pixel rows per block
 };
 
-// One thread owns 8 channels of one window (WIN = ph*pw pixels, compile-time so everything stays in registers).
-// PASS 0: per-channel partial sums of g and g*xhat (g = summed incoming gradient * act'(y)).  PASS 1: writes dx.
-template <int PASS, int WIN>
+// One thread owns 8 channels of U windows per iteration (WIN = ph*pw pixels each; U*WIN = 4 pixels in flight, every load
+// issued before the first use).  PASS 0: per-channel partial sums of g and g*xhat (g = summed incoming gradient * act'(y)).
+// PASS 1: writes dx.
+template <int PASS, int WIN, int U>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdK k) {
   extern __shared__ float red[];  // PASS 0: [256][16]
   const int cvec_total = k.x.C / 8;
@@ -238,6 +301,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdK k) {
   const bool active = trow < k.rp && v < cvec_total;
   const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
   const long long n_win = (long long)k.x.N * Ho * Wo;
+  const long long n_grp = (n_win + U - 1) / U;
   float sc[8], sf[8], mu[8], rs[8], cb[8], cg[8];
   float acc_b[8], acc_g[8];
 #pragma unroll
@@ -255,72 +319,80 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdK k) {
         cg[e] = __ldg(k.dgamma + c) * k.inv_count;
       } else { cb[e] = 0.f; cg[e] = 0.f; }
     }
-    for (long long win = (long long)blockIdx.y * k.rp + trow; win < n_win; win += (long long)gridDim.y * k.rp) {
-      long long t = win;
-      const int wo = (int)(t % Wo); t /= Wo;
-      const int ho = (int)(t % Ho);
-      const int n = (int)(t / Ho);
-      float xv[WIN][8], g[WIN][8];
-      // issue every load of the window first (memory-level parallelism), then compute
+    for (long long grp = (long long)blockIdx.y * k.rp + trow; grp < n_grp; grp += (long long)gridDim.y * k.rp) {
+      float xv[U][WIN][8], g[U][WIN][8], pooled[U][8];
+      int wn[U], wh[U], ww[U];
 #pragma unroll
-      for (int q = 0; q < WIN; ++q) {
-        const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
-        load8(vaddr(k.x, n, h, w, v * 8), xv[q]);
+      for (int u = 0; u < U; ++u) {
+        long long t = grp * U + u < n_win ? grp * U + u : n_win - 1;
+        ww[u] = (int)(t % Wo); t /= Wo;
+        wh[u] = (int)(t % Ho);
+        wn[u] = (int)(t / Ho);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) g[q][e] = 0.f;
+        for (int q = 0; q < WIN; ++q) {
+          load8(vaddr(k.x, wn[u], wh[u] * k.ph + q / k.pw, ww[u] * k.pw + q % k.pw, v * 8), xv[u][q]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[u][q][e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pooled[u][e] = 0.f;
       }
-      float pooled[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) pooled[e] = 0.f;
       for (int s = 0; s < k.n_src; ++s) {
         if (k.src[s].kind == 0) {
+          float f[U][WIN][8];
 #pragma unroll
-          for (int q = 0; q < WIN; ++q) {
-            const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
-            float f[8];
-            load8(vaddr(k.src[s].g, n, h, w, v * 8), f);
+          for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) g[q][e] += f[e];
-          }
+            for (int q = 0; q < WIN; ++q) load8(vaddr(k.src[s].g, wn[u], wh[u] * k.ph + q / k.pw, ww[u] * k.pw + q % k.pw, v * 8), f[u][q]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < WIN; ++q)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) g[u][q][e] += f[u][q][e];
         } else {
-          float f[8];
-          load8(vaddr(k.src[s].g, n, ho, wo, v * 8), f);
+          float f[U][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) pooled[e] += f[e];
+          for (int u = 0; u < U; ++u) load8(vaddr(k.src[s].g, wn[u], wh[u], ww[u], v * 8), f[u]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pooled[u][e] += f[u][e];
         }
       }
-      // forward recompute: y, first arg-max of the window (TF/torch tie rule), activation derivative
-      float y[WIN][8];
-      int amax[8];
-      float ymax[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { amax[e] = 0; ymax[e] = -INFINITY; }
+      for (int u = 0; u < U; ++u) {
+        if (grp * U + u >= n_win) break;
+        // forward recompute: y, first arg-max of the window (TF/torch tie rule), activation derivative
+        float y[WIN][8];
+        int amax[8];
+        float ymax[8];
 #pragma unroll
-      for (int q = 0; q < WIN; ++q)
+        for (int e = 0; e < 8; ++e) { amax[e] = 0; ymax[e] = -INFINITY; }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          y[q][e] = act_fwd(fmaf(xv[q][e], sc[e], sf[e]), k.act);
-          if (y[q][e] > ymax[e]) { ymax[e] = y[q][e]; amax[e] = q; }
-        }
+        for (int q = 0; q < WIN; ++q)
 #pragma unroll
-      for (int q = 0; q < WIN; ++q) {
-        float xh[8];
+          for (int e = 0; e < 8; ++e) {
+            y[q][e] = act_fwd(fmaf(xv[u][q][e], sc[e], sf[e]), k.act);
+            if (y[q][e] > ymax[e]) { ymax[e] = y[q][e]; amax[e] = q; }
+          }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float gg = g[q][e] + (amax[e] == q ? pooled[e] : 0.f);
-          gg *= act_bwd_from_y(y[q][e], k.act);
-          g[q][e] = gg;
-          xh[e] = (xv[q][e] - mu[e]) * rs[e];
-        }
-        if (PASS == 0) {
+        for (int q = 0; q < WIN; ++q) {
+          float xh[8], gg[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { acc_b[e] += g[q][e]; acc_g[e] += g[q][e] * xh[e]; }
-        } else {
-          const int h = ho * k.ph + q / k.pw, w = wo * k.pw + q % k.pw;
-          float o[8];
+          for (int e = 0; e < 8; ++e) {
+            gg[e] = (g[u][q][e] + (amax[e] == q ? pooled[u][e] : 0.f)) * act_bwd_from_y(y[q][e], k.act);
+            xh[e] = (xv[u][q][e] - mu[e]) * rs[e];
+          }
+          if (PASS == 0) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = k.scale ? sc[e] * (g[q][e] - cb[e] - xh[e] * cg[e]) : g[q][e];
-          store8(vaddr(k.dx, n, h, w, v * 8), o);
+            for (int e = 0; e < 8; ++e) { acc_b[e] += gg[e]; acc_g[e] = fmaf(gg[e], xh[e], acc_g[e]); }
+          } else {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = k.scale ? sc[e] * (gg[e] - cb[e] - xh[e] * cg[e]) : gg[e];
+            store8(vaddr(k.dx, wn[u], wh[u] * k.ph + q / k.pw, ww[u] * k.pw + q % k.pw, v * 8), o);
+          }
         }
       }
     }
@@ -373,9 +445,9 @@ struct BnBwdLaunch : PreparedOp {
   template <int PASS>
   int go(dim3 grid, int smem, cudaStream_t s) {
     switch (win) {
-      case 1: bn_bwd_kernel<PASS, 1><<<grid, 256, smem, s>>>(k); break;
-      case 2: bn_bwd_kernel<PASS, 2><<<grid, 256, smem, s>>>(k); break;
-      default: bn_bwd_kernel<PASS, 4><<<grid, 256, smem, s>>>(k); break;
+      case 1: bn_bwd_kernel<PASS, 1, 4><<<grid, 256, smem, s>>>(k); break;
+      case 2: bn_bwd_kernel<PASS, 2, 2><<<grid, 256, smem, s>>>(k); break;
+      default: bn_bwd_kernel<PASS, 4, 1><<<grid, 256, smem, s>>>(k); break;
     }
     B2_CUDA_OK(cudaGetLastError());
     return 0;
@@ -425,7 +497,7 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
   k.cvb = cvec < 256 ? cvec : 256;
   k.rp = 256 / k.cvb;
   const int gx = (cvec + k.cvb - 1) / k.cvb;
-  const long long n_win = (long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw);
+  const long long n_win = ((long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw) + (4 / L->win) - 1) / (4 / L->win);  // window groups
   L->grid0 = dim3(gx, d->n_blocks > 0 ? d->n_blocks : 1);
   long long gy1 = (n_win + k.rp - 1) / k.rp;
   const long long cap = (long long)num_sms() * 16 / gx + 1;
@@ -496,9 +568,11 @@ void adam_update(PreparedOp* op, float lr, int64_t step, float grad_scale) {
 }
 
 // ------------------------------------------------------------------------------------------ pointwise head
-// One group of G lanes (G = 8..32) per output pixel: each lane covers 8 channels per step.
-__global__ void head_fwd_kernel(DView x, const float* __restrict__ w, const float* __restrict__ b, int cout, int act, int stride,
-                                float* __restrict__ y, float* __restrict__ logits, int G) {
+// One group of G lanes (G = 8..32) per output pixel: each lane covers 8 channels per step.  COUT is a template
+// parameter so the per-class accumulators stay in registers and the shuffle reduction moves only live values.
+template <int COUT>
+__global__ void __launch_bounds__(256) head_fwd_kernel(DView x, const float* __restrict__ w, const float* __restrict__ b, int act, int stride,
+                                                       float* __restrict__ y, float* __restrict__ logits, int G) {
   const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
   const long long n_pix = (long long)x.N * Ho * Wo;
   const int gl = threadIdx.x % G;
@@ -513,30 +587,38 @@ __global__ void head_fwd_kernel(DView x, const float* __restrict__ w, const floa
     const int wo = (int)(t % Wo); t /= Wo;
     const int ho = (int)(t % Ho);
     const int n = (int)(t / Ho);
-    float acc[8];
+    float acc[COUT];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
     for (int v = gl; v < cvec; v += G) {
       float f[8];
       load8(vaddr(x, n, ho * stride, wo * stride, v * 8), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        for (int o = 0; o < cout; ++o) acc[o] = fmaf(f[e], __ldg(w + (size_t)(v * 8 + e) * cout + o), acc[o]);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(f[e], __ldg(w + (size_t)(v * 8 + e) * COUT + o), acc[o]);
     }
     for (int off = G / 2; off > 0; off >>= 1)
 #pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off, 32);
+      for (int o = 0; o < COUT; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off, 32);
     if (gl == 0 && valid) {
-      float z[8];
+      float z[COUT];
       float zmax = -INFINITY;
-      for (int o = 0; o < cout; ++o) { z[o] = acc[o] + b[o]; zmax = fmaxf(zmax, z[o]); }
-      if (logits) for (int o = 0; o < cout; ++o) logits[pix * cout + o] = z[o];
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) { z[o] = acc[o] + __ldg(b + o); zmax = fmaxf(zmax, z[o]); }
+      if (logits) {
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) logits[pix * COUT + o] = z[o];
+      }
       if (act == B2SEG_ACT_SOFTMAX) {
         float den = 0.f;
-        for (int o = 0; o < cout; ++o) { z[o] = __expf(z[o] - zmax); den += z[o]; }
-        for (int o = 0; o < cout; ++o) y[pix * cout + o] = z[o] / den;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) { z[o] = __expf(z[o] - zmax); den += z[o]; }
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) y[pix * COUT + o] = z[o] / den;
       } else {
-        for (int o = 0; o < cout; ++o) y[pix * cout + o] = act_fwd(z[o], act);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) y[pix * COUT + o] = act_fwd(z[o], act);
       }
     }
   }
@@ -546,6 +628,17 @@ static int head_group(int C) {
   while (g < 32 && g * 8 < C) g <<= 1;
   return g;
 }
+#define B2_COUT_SWITCH(cout, CALL)        \
+  switch (cout) {                         \
+    case 1: { constexpr int CO = 1; CALL; } break; \
+    case 2: { constexpr int CO = 2; CALL; } break; \
+    case 3: { constexpr int CO = 3; CALL; } break; \
+    case 4: { constexpr int CO = 4; CALL; } break; \
+    case 5: { constexpr int CO = 5; CALL; } break; \
+    case 6: { constexpr int CO = 6; CALL; } break; \
+    case 7: { constexpr int CO = 7; CALL; } break; \
+    default: { constexpr int CO = 8; CALL; } break; \
+  }
 struct HeadFwdLaunch : PreparedOp {
   b2seg_head_desc d;
   int launch(cudaStream_t s) override {
@@ -555,8 +648,8 @@ struct HeadFwdLaunch : PreparedOp {
     int grid = grid_for(n_pix * G, 256);
     const int cap = num_sms() * 32;
     if (grid > cap) grid = cap;
-    head_fwd_kernel<<<grid, 256, 0, s>>>(dv(d.x), reinterpret_cast<const float*>(d.w), reinterpret_cast<const float*>(d.b), d.cout, d.act, st,
-                                         reinterpret_cast<float*>(d.y), reinterpret_cast<float*>(d.logits), G);
+    B2_COUT_SWITCH(d.cout, (head_fwd_kernel<CO><<<grid, 256, 0, s>>>(dv(d.x), reinterpret_cast<const float*>(d.w), reinterpret_cast<const float*>(d.b),
+                                                                    d.act, st, reinterpret_cast<float*>(d.y), reinterpret_cast<float*>(d.logits), G)));
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -567,7 +660,8 @@ PreparedOp* prepare_head_fwd(const b2seg_head_desc* d) {
 }
 
 // backward: dx = dl . W^T (bf16); dW[c][o] += sum_pix x[c]*dl[o]; db[o] += sum_pix dl[o]
-__global__ void head_bwd_dx_kernel(DView x, DView dx, const float* __restrict__ w, int cout, int stride, const float* __restrict__ dl) {
+template <int COUT>
+__global__ void __launch_bounds__(256) head_bwd_dx_kernel(DView x, DView dx, const float* __restrict__ w, int stride, const float* __restrict__ dl) {
   const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
   const int cvec = x.C / 8;
   const long long total = (long long)x.N * x.H * x.W * cvec;
@@ -582,27 +676,29 @@ __global__ void head_bwd_dx_kernel(DView x, DView dx, const float* __restrict__ 
     for (int e = 0; e < 8; ++e) o[e] = 0.f;
     if (h % stride == 0 && wq % stride == 0) {
       const long long pix = ((long long)n * Ho + h / stride) * Wo + wq / stride;
-      for (int q = 0; q < cout; ++q) {
-        const float d = __ldg(dl + pix * cout + q);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf(d, __ldg(w + (size_t)(v * 8 + e) * cout + q), o[e]);
+      for (int q = 0; q < COUT; ++q) {
+        const float d = __ldg(dl + pix * COUT + q);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(d, __ldg(w + (size_t)(v * 8 + e) * COUT + q), o[e]);
       }
     }
     store8(vaddr(dx, n, h, wq, v * 8), o);
   }
 }
-__global__ void head_bwd_dw_kernel(DView x, int cout, int stride, const float* __restrict__ dl, float* dw, float* db, int cvb, int rp) {
-  extern __shared__ float red[];  // [256][8] per output channel pass
+template <int COUT>
+__global__ void __launch_bounds__(256) head_bwd_dw_kernel(DView x, int stride, const float* __restrict__ dl, float* dw, float* db, int cvb, int rp) {
+  extern __shared__ float red[];  // [256][9] per output channel pass
   const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
   const long long n_pix = (long long)x.N * Ho * Wo;
   const int cvec = x.C / 8;
   const int tcv = threadIdx.x % cvb, trow = threadIdx.x / cvb;
   const int v = blockIdx.x * cvb + tcv;
   const bool active = trow < rp && v < cvec;
-  float acc[8][8];
-  float accb[8];
+  float acc[COUT][8];
+  float accb[COUT];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) { accb[o] = 0.f;
+  for (int o = 0; o < COUT; ++o) { accb[o] = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[o][e] = 0.f; }
   if (active) {
@@ -614,17 +710,16 @@ __global__ void head_bwd_dw_kernel(DView x, int cout, int stride, const float* _
       float f[8];
       load8(vaddr(x, n, ho * stride, wo * stride, v * 8), f);
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        if (o < cout) {
-          const float d = __ldg(dl + pix * cout + o);
-          accb[o] += d;
+      for (int o = 0; o < COUT; ++o) {
+        const float d = __ldg(dl + pix * COUT + o);
+        accb[o] += d;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(d, f[e], acc[o][e]);
-        }
+        for (int e = 0; e < 8; ++e) acc[o][e] = fmaf(d, f[e], acc[o][e]);
       }
     }
   }
-  for (int o = 0; o < cout; ++o) {
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
     float* mine = red + (size_t)threadIdx.x * 9;
 #pragma unroll
     for (int e = 0; e < 8; ++e) mine[e] = active ? acc[o][e] : 0.f;
@@ -640,7 +735,7 @@ __global__ void head_bwd_dw_kernel(DView x, int cout, int stride, const float* _
         for (int e = 0; e < 9; ++e) s[e] += q[e];
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(dw + (size_t)(v * 8 + e) * cout + o, s[e]);
+      for (int e = 0; e < 8; ++e) atomicAdd(dw + (size_t)(v * 8 + e) * COUT + o, s[e]);
       if (v == 0) atomicAdd(db + o, s[8]);
     }
     __syncthreads();
@@ -652,8 +747,11 @@ struct HeadBwdLaunch : PreparedOp {
     const int st = d.stride > 1 ? d.stride : 1;
     if (d.dx.ptr) {
       const long long work = (long long)d.x.N * d.x.H * d.x.W * (d.x.C / 8);
-      head_bwd_dx_kernel<<<grid_for(work, 256), 256, 0, s>>>(dv(d.x), dv(d.dx), reinterpret_cast<const float*>(d.w), d.cout, st,
-                                                              reinterpret_cast<const float*>(d.dlogits));
+      int g = grid_for(work, 256);
+      const int cap = num_sms() * 32;
+      if (g > cap) g = cap;
+      B2_COUT_SWITCH(d.cout, (head_bwd_dx_kernel<CO><<<g, 256, 0, s>>>(dv(d.x), dv(d.dx), reinterpret_cast<const float*>(d.w), st,
+                                                                      reinterpret_cast<const float*>(d.dlogits))));
       B2_CUDA_OK(cudaGetLastError());
     }
     const int cvec = d.x.C / 8;
@@ -663,8 +761,8 @@ struct HeadBwdLaunch : PreparedOp {
     if (gy > 1024) gy = 1024;
     if (gy < 1) gy = 1;
     dim3 grid((cvec + cvb - 1) / cvb, (unsigned)gy);
-    head_bwd_dw_kernel<<<grid, 256, 256 * 9 * 4, s>>>(dv(d.x), d.cout, st, reinterpret_cast<const float*>(d.dlogits),
-                                                       reinterpret_cast<float*>(d.dw), reinterpret_cast<float*>(d.db), cvb, rp);
+    B2_COUT_SWITCH(d.cout, (head_bwd_dw_kernel<CO><<<grid, 256, 256 * 9 * 4, s>>>(dv(d.x), st, reinterpret_cast<const float*>(d.dlogits),
+                                                                                 reinterpret_cast<float*>(d.dw), reinterpret_cast<float*>(d.db), cvb, rp)));
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
