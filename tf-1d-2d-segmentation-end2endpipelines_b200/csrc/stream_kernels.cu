@@ -63,10 +63,10 @@ static inline int grid_for(long long work, int block) {
 // ------------------------------------------------------------------------------------------ cast input
 __global__ void cast_input_kernel(const float* __restrict__ src, int N, int H, int W, int C, DView out) {
   const int cv = out.C / 8;
-  const long long total = (long long)N * H * W * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned)N * H * W * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
-    long long pix = i / cv;
+    unsigned pix = i / cv;
     const int w = (int)(pix % W); pix /= W;
     const int h = (int)(pix % H);
     const int n = (int)(pix / H);
@@ -155,11 +155,11 @@ template <int WIN, int U>
 __global__ void __launch_bounds__(256) bn_act_kernel(BnActK k) {
   const int cv = k.x.C / 8;
   const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
-  const long long n_win = (long long)k.x.N * Ho * Wo;
-  const long long total = ((n_win + U - 1) / U) * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned n_win = (unsigned)k.x.N * Ho * Wo;
+  const unsigned total = ((n_win + U - 1) / U) * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
-    const long long wbase = (i / cv) * U;
+    const unsigned wbase = (i / cv) * U;
     float sc[8], sf[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActK k) {
     int wn[U], wh[U], ww[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      long long t = wbase + u < n_win ? wbase + u : n_win - 1;
+      unsigned t = wbase + u < n_win ? wbase + u : n_win - 1;
       ww[u] = (int)(t % Wo); t /= Wo;
       wh[u] = (int)(t % Ho);
       wn[u] = (int)(t / Ho);
@@ -202,10 +202,10 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActK k) {
 __global__ void bn_act_generic_kernel(BnActK k) {
   const int cv = k.x.C / 8;
   const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
-  const long long total = (long long)k.x.N * Ho * Wo * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned)k.x.N * Ho * Wo * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
-    long long pix = i / cv;
+    unsigned pix = i / cv;
     const int wo = (int)(pix % Wo); pix /= Wo;
     const int ho = (int)(pix % Ho);
     const int n = (int)(pix / Ho);
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdK k) {
   const int v = blockIdx.x * k.cvb + tcv;
   const bool active = trow < k.rp && v < cvec_total;
   const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
-  const long long n_win = (long long)k.x.N * Ho * Wo;
-  const long long n_grp = (n_win + U - 1) / U;
+  const unsigned n_win = (unsigned)k.x.N * Ho * Wo;
+  const unsigned n_grp = (n_win + U - 1) / U;
   float sc[8], sf[8], mu[8], rs[8], cb[8], cg[8];
   float acc_b[8], acc_g[8];
 #pragma unroll
@@ -319,12 +319,12 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdK k) {
         cg[e] = __ldg(k.dgamma + c) * k.inv_count;
       } else { cb[e] = 0.f; cg[e] = 0.f; }
     }
-    for (long long grp = (long long)blockIdx.y * k.rp + trow; grp < n_grp; grp += (long long)gridDim.y * k.rp) {
+    for (unsigned grp = blockIdx.y * k.rp + trow; grp < n_grp; grp += gridDim.y * k.rp) {
       float xv[U][WIN][8], g[U][WIN][8], pooled[U][8];
       int wn[U], wh[U], ww[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        long long t = grp * U + u < n_win ? grp * U + u : n_win - 1;
+        unsigned t = grp * U + u < n_win ? grp * U + u : n_win - 1;
         ww[u] = (int)(t % Wo); t /= Wo;
         wh[u] = (int)(t % Ho);
         wn[u] = (int)(t / Ho);
@@ -574,16 +574,16 @@ template <int COUT>
 __global__ void __launch_bounds__(256) head_fwd_kernel(DView x, const float* __restrict__ w, const float* __restrict__ b, int act, int stride,
                                                        float* __restrict__ y, float* __restrict__ logits, int G) {
   const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
-  const long long n_pix = (long long)x.N * Ho * Wo;
+  const unsigned n_pix = (unsigned)x.N * Ho * Wo;
   const int gl = threadIdx.x % G;
-  const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
-  const long long gstride = (long long)gridDim.x * blockDim.x / G;
+  const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const unsigned gstride = gridDim.x * blockDim.x / G;
   const int cvec = x.C / 8;
-  const long long n_iter = (n_pix + gstride - 1) / gstride;  // uniform trip count: the shuffles below need whole warps
-  for (long long it = 0; it < n_iter; ++it) {
-    const long long pix = gid + it * gstride;
+  const unsigned n_iter = (n_pix + gstride - 1) / gstride;  // uniform trip count: the shuffles below need whole warps
+  for (unsigned it = 0; it < n_iter; ++it) {
+    const unsigned pix = gid + it * gstride;
     const bool valid = pix < n_pix;
-    long long t = valid ? pix : 0;
+    unsigned t = valid ? pix : 0;
     const int wo = (int)(t % Wo); t /= Wo;
     const int ho = (int)(t % Ho);
     const int n = (int)(t / Ho);
@@ -664,10 +664,10 @@ template <int COUT>
 __global__ void __launch_bounds__(256) head_bwd_dx_kernel(DView x, DView dx, const float* __restrict__ w, int stride, const float* __restrict__ dl) {
   const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
   const int cvec = x.C / 8;
-  const long long total = (long long)x.N * x.H * x.W * cvec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned)x.N * x.H * x.W * cvec;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
-    long long t = i / cvec;
+    unsigned t = i / cvec;
     const int wq = (int)(t % x.W); t /= x.W;
     const int h = (int)(t % x.H);
     const int n = (int)(t / x.H);
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(256) head_bwd_dx_kernel(DView x, DView dx, con
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.f;
     if (h % stride == 0 && wq % stride == 0) {
-      const long long pix = ((long long)n * Ho + h / stride) * Wo + wq / stride;
+      const unsigned pix = ((unsigned)n * Ho + h / stride) * Wo + wq / stride;
 #pragma unroll
       for (int q = 0; q < COUT; ++q) {
         const float d = __ldg(dl + pix * COUT + q);
@@ -690,7 +690,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256) head_bwd_dw_kernel(DView x, int stride, const float* __restrict__ dl, float* dw, float* db, int cvb, int rp) {
   extern __shared__ float red[];  // [256][9] per output channel pass
   const int Ho = (x.H + stride - 1) / stride, Wo = (x.W + stride - 1) / stride;
-  const long long n_pix = (long long)x.N * Ho * Wo;
+  const unsigned n_pix = (unsigned)x.N * Ho * Wo;
   const int cvec = x.C / 8;
   const int tcv = threadIdx.x % cvb, trow = threadIdx.x / cvb;
   const int v = blockIdx.x * cvb + tcv;
@@ -702,8 +702,8 @@ __global__ void __launch_bounds__(256) head_bwd_dw_kernel(DView x, int stride, c
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[o][e] = 0.f; }
   if (active) {
-    for (long long pix = (long long)blockIdx.y * rp + trow; pix < n_pix; pix += (long long)gridDim.y * rp) {
-      long long t = pix;
+    for (unsigned pix = blockIdx.y * rp + trow; pix < n_pix; pix += gridDim.y * rp) {
+      unsigned t = pix;
       const int wo = (int)(t % Wo); t /= Wo;
       const int ho = (int)(t % Ho);
       const int n = (int)(t / Ho);
@@ -838,10 +838,10 @@ PreparedOp* prepare_loss(const b2seg_loss_desc* d) {
 struct EltK { int op; DView a, b, c, out; };
 __global__ void eltwise_kernel(EltK k) {
   const int cv = k.out.C / 8;
-  const long long total = (long long)k.out.N * k.out.H * k.out.W * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned)k.out.N * k.out.H * k.out.W * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
-    long long t = i / cv;
+    unsigned t = i / cv;
     const int w = (int)(t % k.out.W); t /= k.out.W;
     const int h = (int)(t % k.out.H);
     const int n = (int)(t / k.out.H);
@@ -890,13 +890,13 @@ __global__ void colsum_kernel(DView g, float* out, int cvb, int rp) {
   const int tcv = threadIdx.x % cvb, trow = threadIdx.x / cvb;
   const int v = blockIdx.x * cvb + tcv;
   const bool active = trow < rp && v < cvec;
-  const long long n_pix = (long long)g.N * g.H * g.W;
+  const unsigned n_pix = (unsigned)g.N * g.H * g.W;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (active)
-    for (long long pix = (long long)blockIdx.y * rp + trow; pix < n_pix; pix += (long long)gridDim.y * rp) {
-      long long t = pix;
+    for (unsigned pix = blockIdx.y * rp + trow; pix < n_pix; pix += gridDim.y * rp) {
+      unsigned t = pix;
       const int w = (int)(t % g.W); t /= g.W;
       const int h = (int)(t % g.H);
       const int n = (int)(t / g.H);
