@@ -417,7 +417,9 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(BnBwdK k) {
     }
   }
 }
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_blocks, int C, float* dgamma, float* dbeta) {
+// raw_gx = 1: partials hold (sum g, sum g*x) of the lean kernel; convert to dgamma = rstd * (sum g*x - mean * sum g)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n_blocks, int C, float* dgamma, float* dbeta,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd, int raw_gx) {
   // one warp per 32 channels x 8 slices of the partial list
   __shared__ double sh[2][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -433,21 +435,198 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
   __syncthreads();
   if (ty == 0 && c < C) {
     for (int i = 1; i < 8; ++i) { b += sh[0][i][tx]; g += sh[1][i][tx]; }
+    if (raw_gx) g = (double)rstd[c] * (g - (double)mean[c] * b);
     dbeta[c] = (float)b;
     dgamma[c] = (float)g;
   }
 }
+
+// Lean BN(+ReLU/LeakyReLU/identity) backward.  Per element: mask from the sign of t = x*scale+shift (for a pooled source the
+// window arg-max of t, which equals the arg-max of relu(t) wherever the gradient survives the mask),
+//   PASS 0:  sum g, sum g*x          PASS 1:  dx = A*g + B*x + D   with per-channel A = scale, B = -scale*cg*rstd,
+//   D = scale*(cg*rstd*mean - cb), cb = dbeta/count, cg = dgamma/count  (== scale*(g - cb - xhat*cg)).
+template <int PASS, int WIN, int U, int ACT>
+__global__ void __launch_bounds__(256, 2) bn_bwd_lean_kernel(BnBwdK k) {
+  extern __shared__ float red[];  // PASS 0: [256][16]
+  const int cvec_total = k.x.C / 8;
+  const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
+  const int v = blockIdx.x * k.cvb + tcv;
+  const bool active = trow < k.rp && v < cvec_total;
+  const unsigned Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
+  const unsigned n_win = (unsigned)k.x.N * Ho * Wo;
+  const unsigned n_grp = (n_win + U - 1) / U;
+  const bool has_bn = k.scale != nullptr;
+  float sc[8], sf[8], cB[8], cD[8];
+  float acc_b[8], acc_g[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { acc_b[e] = 0.f; acc_g[e] = 0.f; }
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e;
+      sc[e] = has_bn ? __ldg(k.scale + c) : 1.f;
+      sf[e] = has_bn ? __ldg(k.shift + c) : 0.f;
+      cB[e] = 0.f; cD[e] = 0.f;
+      if (PASS == 1 && has_bn) {
+        const float cb = __ldg(k.dbeta + c) * k.inv_count, cg = __ldg(k.dgamma + c) * k.inv_count;
+        const float rs = __ldg(k.rstd + c), mu = __ldg(k.mean + c);
+        cB[e] = -sc[e] * cg * rs;
+        cD[e] = sc[e] * (cg * rs * mu - cb);
+      }
+    }
+    for (unsigned grp = blockIdx.y * k.rp + trow; grp < n_grp; grp += gridDim.y * k.rp) {
+      uint4 xr[U][WIN];
+      float g[U][WIN][8];
+      float pooled[U][8];
+      int wn[U], wh[U], ww[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned t = grp * U + u < n_win ? grp * U + u : n_win - 1;
+        ww[u] = (int)(t % Wo); t /= Wo;
+        wh[u] = (int)(t % Ho);
+        wn[u] = (int)(t / Ho);
+#pragma unroll
+        for (int q = 0; q < WIN; ++q)
+          xr[u][q] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.x, wn[u], wh[u] * k.ph + q / k.pw, ww[u] * k.pw + q % k.pw, v * 8)));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pooled[u][e] = 0.f;
+#pragma unroll
+        for (int q = 0; q < WIN; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[u][q][e] = 0.f;
+      }
+      for (int s = 0; s < k.n_src; ++s) {
+        if (k.src[s].kind == 0) {
+          uint4 r[U][WIN];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < WIN; ++q)
+              r[u][q] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.src[s].g, wn[u], wh[u] * k.ph + q / k.pw, ww[u] * k.pw + q % k.pw, v * 8)));
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) {
+              const uint32_t w4[4] = {r[u][q].x, r[u][q].y, r[u][q].z, r[u][q].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                g[u][q][2 * e] += __uint_as_float(w4[e] << 16);
+                g[u][q][2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+              }
+            }
+        } else if (WIN > 1) {
+          uint4 r[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.src[s].g, wn[u], wh[u], ww[u], v * 8)));
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t w4[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              pooled[u][2 * e] += __uint_as_float(w4[e] << 16);
+              pooled[u][2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (grp * U + u >= n_win) break;
+        float x[WIN][8];
+#pragma unroll
+        for (int q = 0; q < WIN; ++q) {
+          const uint32_t w4[4] = {xr[u][q].x, xr[u][q].y, xr[u][q].z, xr[u][q].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            x[q][2 * e] = __uint_as_float(w4[e] << 16);
+            x[q][2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t[WIN];
+#pragma unroll
+          for (int q = 0; q < WIN; ++q) t[q] = fmaf(x[q][e], sc[e], sf[e]);
+          if (WIN > 1) {
+            float m = t[0];
+#pragma unroll
+            for (int q = 1; q < WIN; ++q) m = fmaxf(m, t[q]);
+            bool taken = false;
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) {
+              const bool hit = !taken && t[q] == m;
+              taken = taken || hit;
+              if (hit) g[u][q][e] += pooled[u][e];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < WIN; ++q) {
+            if (ACT == B2SEG_ACT_RELU) g[u][q][e] = t[q] > 0.f ? g[u][q][e] : 0.f;
+            if (ACT == B2SEG_ACT_LEAKY) g[u][q][e] = t[q] > 0.f ? g[u][q][e] : 0.3f * g[u][q][e];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < WIN; ++q) {
+          if (PASS == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { acc_b[e] += g[u][q][e]; acc_g[e] = fmaf(g[u][q][e], x[q][e], acc_g[e]); }
+          } else {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = has_bn ? fmaf(cB[e], x[q][e], fmaf(sc[e], g[u][q][e], cD[e])) : g[u][q][e];
+            store8(vaddr(k.dx, wn[u], wh[u] * k.ph + q / k.pw, ww[u] * k.pw + q % k.pw, v * 8), o);
+          }
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    float* mine = red + (size_t)threadIdx.x * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mine[e] = active ? acc_b[e] : 0.f; mine[8 + e] = active ? acc_g[e] : 0.f; }
+    __syncthreads();
+    if (trow == 0 && v < cvec_total) {
+      float sb[8], sg[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sb[e] = 0.f; sg[e] = 0.f; }
+      for (int r = 0; r < k.rp; ++r) {
+        const float* o = red + (size_t)(r * k.cvb + tcv) * 16;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sb[e] += o[e]; sg[e] += o[8 + e]; }
+      }
+      float* pp = k.partials + (size_t)blockIdx.y * 2 * k.x.C;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { pp[v * 8 + e] = sb[e]; pp[k.x.C + v * 8 + e] = sg[e]; }
+    }
+  }
+}
 struct BnBwdLaunch : PreparedOp {
   BnBwdK k;
-  bool has_bn;
+  bool has_bn, lean;
   dim3 grid0, grid1;
   int smem0, win;
   template <int PASS>
   int go(dim3 grid, int smem, cudaStream_t s) {
-    switch (win) {
-      case 1: bn_bwd_kernel<PASS, 1, 4><<<grid, 256, smem, s>>>(k); break;
-      case 2: bn_bwd_kernel<PASS, 2, 2><<<grid, 256, smem, s>>>(k); break;
-      default: bn_bwd_kernel<PASS, 4, 1><<<grid, 256, smem, s>>>(k); break;
+    if (lean) {
+#define B2_LEAN(ACT)                                                                      \
+      switch (win) {                                                                      \
+        case 1: bn_bwd_lean_kernel<PASS, 1, 2, ACT><<<grid, 256, smem, s>>>(k); break;    \
+        case 2: bn_bwd_lean_kernel<PASS, 2, 1, ACT><<<grid, 256, smem, s>>>(k); break;    \
+        default: bn_bwd_lean_kernel<PASS, 4, 1, ACT><<<grid, 256, smem, s>>>(k); break;   \
+      }
+      if (k.act == B2SEG_ACT_RELU) { B2_LEAN(B2SEG_ACT_RELU) }
+      else if (k.act == B2SEG_ACT_LEAKY) { B2_LEAN(B2SEG_ACT_LEAKY) }
+      else { B2_LEAN(B2SEG_ACT_NONE) }
+#undef B2_LEAN
+    } else {
+      switch (win) {
+        case 1: bn_bwd_kernel<PASS, 1, 4><<<grid, 256, smem, s>>>(k); break;
+        case 2: bn_bwd_kernel<PASS, 2, 2><<<grid, 256, smem, s>>>(k); break;
+        default: bn_bwd_kernel<PASS, 4, 1><<<grid, 256, smem, s>>>(k); break;
+      }
     }
     B2_CUDA_OK(cudaGetLastError());
     return 0;
@@ -456,7 +635,7 @@ struct BnBwdLaunch : PreparedOp {
     if (has_bn) {
       int rc = go<0>(grid0, smem0, s);
       if (rc) return rc;
-      bn_bwd_finalize_kernel<<<(k.x.C + 31) / 32, 256, 0, s>>>(k.partials, k.n_blocks, k.x.C, k.dgamma, k.dbeta);
+      bn_bwd_finalize_kernel<<<(k.x.C + 31) / 32, 256, 0, s>>>(k.partials, k.n_blocks, k.x.C, k.dgamma, k.dbeta, k.mean, k.rstd, lean ? 1 : 0);
       B2_CUDA_OK(cudaGetLastError());
     }
     return go<1>(grid1, 0, s);
@@ -486,6 +665,7 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
     }
   }
   L->win = k.ph * k.pw;
+  L->lean = (k.act == B2SEG_ACT_NONE || k.act == B2SEG_ACT_RELU || k.act == B2SEG_ACT_LEAKY);
   if (L->win != 1 && L->win != 2 && L->win != 4) { set_error("bn_bwd: pool window must have 1, 2 or 4 elements"); delete L; return nullptr; }
   k.inv_count = (float)(1.0 / d->count);
   k.partials = reinterpret_cast<float*>(d->partials);
@@ -497,7 +677,8 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
   k.cvb = cvec < 256 ? cvec : 256;
   k.rp = 256 / k.cvb;
   const int gx = (cvec + k.cvb - 1) / k.cvb;
-  const long long n_win = ((long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw) + (4 / L->win) - 1) / (4 / L->win);  // window groups
+  const int upt = L->lean ? (L->win == 1 ? 2 : 1) : 4 / L->win;  // windows per thread-iteration
+  const long long n_win = ((long long)k.x.N * (k.x.H / k.ph) * (k.x.W / k.pw) + upt - 1) / upt;  // window groups
   L->grid0 = dim3(gx, d->n_blocks > 0 ? d->n_blocks : 1);
   long long gy1 = (n_win + k.rp - 1) / k.rp;
   const long long cap = (long long)num_sms() * 16 / gx + 1;
