@@ -195,6 +195,7 @@ typedef struct b2seg_colsum_desc { /* bias gradient: db[c] = sum over pixels of 
 const char* b2seg_last_error(void);
 int b2seg_version(void);
 int b2seg_device_check(int device);
+int b2seg_sizeof_desc(int op);  /* sizeof the descriptor struct of a B2SEG_OP_* code (binding self-check, no GPU needed) */
 
 int b2seg_conv(const b2seg_conv_desc* d, void* stream);
 int b2seg_conv_num_mtiles(const b2seg_conv_desc* d);  /* M tiles per group */

@@ -38,6 +38,9 @@ class KerasRef:
         self.new_moving: Dict[str, torch.Tensor] = {}
         self.trainable: List[str] = []
         self.logits: Dict[str, torch.Tensor] = {}
+        self.override: Optional[Dict[str, torch.Tensor]] = None   # teacher forcing, see _rec
+        self.local_err: Dict[str, float] = {}
+        self.local_out: Dict[str, torch.Tensor] = {}
 
     # ---- naming: keras.backend.unique_object_name semantics -----------------------------------------------
     def _name(self, base: str, name: Optional[str]) -> str:
@@ -108,6 +111,18 @@ class KerasRef:
         return (int(v), int(v)) if ndim == 2 else (1, int(v))
 
     def _rec(self, name, y):
+        """Record a layer output.  Teacher forcing (`override`): when the caller supplies the tensor another implementation
+        produced for this layer, the layer-local error is recorded (this layer evaluated by the oracle on the *other
+        implementation's* inputs vs what that implementation stored) and the supplied tensor replaces the oracle's for all
+        consumers — so rounding noise does not compound through a deep random-init network and each layer is judged on
+        its own arithmetic.  `local_out[name]` keeps the graph-connected oracle output for layer-local backward checks."""
+        if self.override is not None and name in self.override:
+            dev = self.override[name].to(self.dtype)
+            if tuple(dev.shape) != tuple(y.shape):
+                raise ValueError(f"override for {name}: shape {tuple(dev.shape)} != {tuple(y.shape)}")
+            self.local_err[name] = float((dev - y.detach()).norm() / (y.detach().norm() + 1e-30))
+            self.local_out[name] = y
+            y = dev.clone().requires_grad_(self.training)
         if self.training and y.requires_grad:
             y.retain_grad()
         self.acts[name] = y

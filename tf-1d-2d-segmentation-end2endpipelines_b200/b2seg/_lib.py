@@ -116,7 +116,7 @@ OP_DESC = {OP_CONV: ConvDesc, OP_WGRAD: WgradDesc, OP_BN_FINALIZE: BnFinalizeDes
            OP_ELTWISE: EltwiseDesc, OP_CAST: CastDesc, OP_COLSUM: ColsumDesc, OP_MEMSET: MemsetDesc}
 
 # every symbol include/b2seg.h declares (the CPU test-suite checks the library exports all of them)
-EXPORTED = ["b2seg_last_error", "b2seg_version", "b2seg_device_check", "b2seg_conv", "b2seg_conv_num_mtiles", "b2seg_conv_num_stat_rows",
+EXPORTED = ["b2seg_last_error", "b2seg_version", "b2seg_device_check", "b2seg_sizeof_desc", "b2seg_conv", "b2seg_conv_num_mtiles", "b2seg_conv_num_stat_rows",
             "b2seg_wgrad", "b2seg_bn_finalize", "b2seg_bn_act", "b2seg_bn_bwd", "b2seg_adam", "b2seg_head_fwd",
             "b2seg_head_bwd", "b2seg_loss", "b2seg_eltwise", "b2seg_cast_input", "b2seg_colsum", "b2seg_plan_create",
             "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]

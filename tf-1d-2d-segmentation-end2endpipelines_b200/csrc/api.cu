@@ -141,6 +141,26 @@ extern "C" {
 const char* b2seg_last_error(void) { return b2::g_err; }
 int b2seg_version(void) { return 100; }
 
+// sizeof of each op descriptor: lets a binding verify its struct mirrors without touching the GPU
+int b2seg_sizeof_desc(int op) {
+  switch (op) {
+    case B2SEG_OP_CONV: return (int)sizeof(b2seg_conv_desc);
+    case B2SEG_OP_WGRAD: return (int)sizeof(b2seg_wgrad_desc);
+    case B2SEG_OP_BN_FINALIZE: return (int)sizeof(b2seg_bn_finalize_desc);
+    case B2SEG_OP_BN_ACT: return (int)sizeof(b2seg_bn_act_desc);
+    case B2SEG_OP_BN_BWD: return (int)sizeof(b2seg_bn_bwd_desc);
+    case B2SEG_OP_ADAM: return (int)sizeof(b2seg_adam_desc);
+    case B2SEG_OP_HEAD_FWD:
+    case B2SEG_OP_HEAD_BWD: return (int)sizeof(b2seg_head_desc);
+    case B2SEG_OP_LOSS: return (int)sizeof(b2seg_loss_desc);
+    case B2SEG_OP_ELTWISE: return (int)sizeof(b2seg_eltwise_desc);
+    case B2SEG_OP_CAST: return (int)sizeof(b2seg_cast_desc);
+    case B2SEG_OP_COLSUM: return (int)sizeof(b2seg_colsum_desc);
+    case B2SEG_OP_MEMSET: return (int)sizeof(b2seg_memset_desc);
+    default: return -1;
+  }
+}
+
 int b2seg_device_check(int device) {
   if (cudaSetDevice(device) != cudaSuccess) return b2::fail(B2SEG_ERR_DEVICE, "cudaSetDevice(%d) failed", device);
   return b2::require_sm100();
