@@ -1,0 +1,102 @@
+"""world_size-2 gloo test of the data-parallel path on the CPU: each rank runs forward + backward of the SAME
+planner program on its own batch shard through the float64 descriptor emulator, the flat gradient arena is sum-all-reduced
+(b2seg.dist.allreduce_flat_, bucketed) and Adam applies grad_scale = 1/world.  Both ranks must end with identical weights,
+equal to a single-process run that averages the two per-replica gradients by hand."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(batch):
+    from b2seg.graph import init_params
+    from b2seg.models2d import unet_model_builder
+    from b2seg.planner import Planner
+    from desc_emulator import PlanMem
+    g = unet_model_builder("UNet", 16, 16, 8, 2, num_channels=1, train_mode="from_scratch").build_graph()
+    mem = PlanMem()
+    pl = Planner(g, batch, mem.alloc_bytes, training=True, losses=["bce"], adam=dict(lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    params = init_params(g, seed=3)
+    for e in pl.params:
+        flat = torch.from_numpy(pl.to_internal(e.key, params[e.key])).double()
+        if e.trainable:
+            mem.f32(pl.w_ptr + 4 * e.offset, e.size)[:] = flat
+            wb, off = mem.resolve(pl.wb_ptr + 2 * e.offset)
+            wb[off:off + e.size] = flat
+        else:
+            mem.f32(pl.mov_ptr + 4 * e.offset, e.size)[:] = flat
+    return g, mem, pl
+
+
+def _fwd_bwd(mem, pl, x, y):
+    from desc_emulator import run_phase
+    mem.f32(pl.input_ptr, x.numel())[:] = x.reshape(-1).double()
+    mem.f32(pl.outputs[0]["target_ptr"], y.numel())[:] = y.reshape(-1).double()
+    run_phase(mem, pl, 0)
+    run_phase(mem, pl, 1)
+    return mem.f32(pl.g_ptr, max(pl.n_train, 64))
+
+
+def _data():
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.random((4, 16, 16, 1), dtype=np.float32))
+    y = (x > 0.5).float()
+    return x, y
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tf-1d-2d-segmentation-end2endpipelines_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b2seg.dist import allreduce_flat_, shard_range, wait_all
+    from desc_emulator import run_phase
+    x, y = _data()
+    b, e = shard_range(x.shape[0], rank, world)
+    g, mem, pl = _build(e - b)
+    grads = _fwd_bwd(mem, pl, x[b:e], y[b:e])
+    wait_all(allreduce_flat_(grads, bucket_elems=1000))
+    for (op, desc, _n) in pl.ops[2]:
+        desc.grad_scale = 1.0 / world
+    run_phase(mem, pl, 2)
+    torch.save(mem.f32(pl.w_ptr, max(pl.n_train, 64)).clone(), os.path.join(out, f"w{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_step(tmp_path):
+    from b2seg.dist import shard_range, shard_sizes
+    assert shard_sizes(5, 2) == [3, 2] and shard_range(5, 1, 2) == (3, 5)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    w0, w1 = torch.load(tmp_path / "w0.pt"), torch.load(tmp_path / "w1.pt")
+    assert torch.equal(w0, w1)
+    # single-process reference: average the per-replica gradients by hand
+    from desc_emulator import run_phase
+    x, y = _data()
+    gs = []
+    for r in range(2):
+        g, mem, pl = _build(2)
+        gs.append(_fwd_bwd(mem, pl, x[2 * r:2 * r + 2], y[2 * r:2 * r + 2]).clone())
+    g, mem, pl = _build(2)
+    _fwd_bwd(mem, pl, x[:2], y[:2])
+    mem.f32(pl.g_ptr, max(pl.n_train, 64))[:] = (gs[0] + gs[1]) / 2
+    run_phase(mem, pl, 2)
+    ref = mem.f32(pl.w_ptr, max(pl.n_train, 64))
+    assert torch.allclose(w0, ref, atol=1e-12)
+    assert float((w0 - ref).abs().max()) < 1e-12

@@ -248,7 +248,8 @@ class Model:
         eng.backward()
         scale = 1.0
         if self.world_size > 1:
-            self._dist.all_reduce(eng.g, group=self._pg)
+            from .dist import allreduce_flat_, wait_all
+            wait_all(allreduce_flat_(eng.g, group=self._pg, bucket_elems=32 << 20))
             scale = 1.0 / self.world_size
         eng.optimizer_step(self.optimizer.learning_rate, scale)
         if return_loss:
