@@ -122,6 +122,7 @@ typedef struct b2seg_bn_act_desc {
   b2seg_view out[2];
   int32_t pool_h, pool_w; /* 0/1 = none */
   b2seg_view pooled;
+  int32_t c_valid;        /* channels >= c_valid (padding lanes) are written as 0; 0 = all valid */
 } b2seg_bn_act_desc;
 
 typedef struct b2seg_gradsrc {
@@ -179,9 +180,50 @@ typedef struct b2seg_loss_desc {
 } b2seg_loss_desc;
 
 typedef struct b2seg_eltwise_desc {
-  int32_t op;  /* 0: out = a + b ; 1: out = a (copy) ; 2: out = a * leaky'(y=b) ; 3: out = a + b + c */
+  int32_t op;  /* 0: out = act(a + b) ; 1: out = a (copy) ; 2: out = a * leaky'(y=b) ; 3: out = act(a + b + c) */
   b2seg_view a, b, c, out;
+  int32_t act; /* B2SEG_ACT_* applied by ops 0 and 3 (Add -> Activation('relu'), unet_variants.py:73-74,96-97,110-111) */
 } b2seg_eltwise_desc;
+
+/* UpSampling2D(size, 'bilinear') / UpSampling1D(size) (unet_variants.py:37; 1DCNN :122) with an optional activation
+ * (UNet3+ applies sigmoid after the up-sampling, :363).  mode 0 = nearest (repeat), 1 = bilinear with half-pixel
+ * centres and edge clamp (tf.image.resize).  Forward: y = act(resize(x)).  Backward: dx = resize^T(dy * act'(yfwd))
+ * as a deterministic gather (no atomics). */
+typedef struct b2seg_resize_desc {
+  b2seg_view x;     /* forward: low-resolution input;   backward: dx (output) */
+  b2seg_view y;     /* forward: high-resolution output; backward: dy (input)  */
+  b2seg_view yfwd;  /* backward with act != NONE: the stored forward output */
+  int32_t fh, fw, mode, act;
+  int32_t c_valid;  /* channels >= c_valid are written as 0 (0 = all valid) */
+} b2seg_resize_desc;
+
+/* out = a * b[...,0]  (skip * resampler, the tf operator overload in Attention_Block, unet_variants.py:81).
+ * Backward: da = dout * b[...,0];  db[...,0] = sum_c dout * a, db[...,1:] = 0. */
+typedef struct b2seg_mulbc_desc {
+  b2seg_view a, b, out;
+  b2seg_view dout, da, db;
+} b2seg_mulbc_desc;
+
+/* per-channel sum and sum of squares of a bf16 view: batch statistics for a BatchNormalization whose input is not a
+ * convolution output (MultiResBlock / ResPath, unet_variants.py:96-99,108-112).  partials: fp32 [n_blocks][2][C]. */
+typedef struct b2seg_colstats_desc {
+  b2seg_view x; uint64_t partials; int32_t n_blocks;
+} b2seg_colstats_desc;
+
+/* ConvLSTM2D/1D on a length-1 sequence with zero initial state (unet_variants.py:145-149): given the input-convolution
+ * output z = [z_i | z_g | z_o] (three channel windows of width F; the forget gate and the recurrent kernel are dead),
+ *   h = hard_sigmoid(z_o) * tanh(hard_sigmoid(z_i) * tanh(z_g)),  hard_sigmoid(x) = clip(0.2 x + 0.5, 0, 1).
+ * Backward writes dz = [dz_i | dz_g | dz_o]. */
+typedef struct b2seg_lstm_desc {
+  b2seg_view z, h, dh, dz;
+  int32_t F;
+} b2seg_lstm_desc;
+
+/* MaxPooling backward for an arbitrary window (UNet3+ pools 2..16): dx = dp routed to the first maximum of each window of y */
+typedef struct b2seg_poolbwd_desc {
+  b2seg_view y, dp, dx;
+  int32_t ph, pw;
+} b2seg_poolbwd_desc;
 
 typedef struct b2seg_cast_desc { /* fp32 NHWC input -> bf16 view (channel-padded) */
   uint64_t src; int32_t N, H, W, C;
@@ -213,12 +255,21 @@ int b2seg_loss(const b2seg_loss_desc* d, void* stream);
 int b2seg_eltwise(const b2seg_eltwise_desc* d, void* stream);
 int b2seg_cast_input(const b2seg_cast_desc* d, void* stream);
 int b2seg_colsum(const b2seg_colsum_desc* d, void* stream);
+int b2seg_resize_fwd(const b2seg_resize_desc* d, void* stream);
+int b2seg_resize_bwd(const b2seg_resize_desc* d, void* stream);
+int b2seg_mulbc_fwd(const b2seg_mulbc_desc* d, void* stream);
+int b2seg_mulbc_bwd(const b2seg_mulbc_desc* d, void* stream);
+int b2seg_colstats(const b2seg_colstats_desc* d, void* stream);
+int b2seg_lstm_fwd(const b2seg_lstm_desc* d, void* stream);
+int b2seg_lstm_bwd(const b2seg_lstm_desc* d, void* stream);
+int b2seg_pool_bwd(const b2seg_poolbwd_desc* d, void* stream);
 
 /* ---- plan: a recorded sequence of the ops above, replayed per step (optionally as a CUDA graph) ---- */
 typedef struct b2seg_plan b2seg_plan;
 enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
        B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,
-       B2SEG_OP_MEMSET };
+       B2SEG_OP_MEMSET, B2SEG_OP_RESIZE_FWD, B2SEG_OP_RESIZE_BWD, B2SEG_OP_MULBC_FWD, B2SEG_OP_MULBC_BWD, B2SEG_OP_COLSTATS,
+       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD };
 typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
 
 int b2seg_plan_create(b2seg_plan** out);

@@ -122,7 +122,7 @@ def _dact_from_y(y, code):
     if code == L.ACT_RELU:
         return (y > 0).double()
     if code == L.ACT_LEAKY:
-        return torch.where(y > 0, 1.0, 0.3).double()
+        return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.3))
     if code == L.ACT_SIGMOID:
         return y * (1 - y)
     return torch.ones_like(y)
@@ -190,6 +190,8 @@ def emu_bn_act(mem, d):
     sc = mem.f32(d.scale, C) if d.scale else torch.ones(C, dtype=torch.float64)
     sf = mem.f32(d.shift, C) if d.shift else torch.zeros(C, dtype=torch.float64)
     y = _act(x * sc + sf, d.act)
+    if d.c_valid:
+        y[..., d.c_valid:] = 0
     for i in range(d.n_out):
         mem.write_view(d.out[i], y)
     ph, pw = max(d.pool_h, 1), max(d.pool_w, 1)
@@ -306,11 +308,12 @@ def emu_loss(mem, d):
 def emu_eltwise(mem, d):
     a = mem.gather_view(d.a)
     if d.op == 0:
-        o = a + mem.gather_view(d.b)
+        o = _act(a + mem.gather_view(d.b), d.act)
     elif d.op == 3:
-        o = a + mem.gather_view(d.b) + mem.gather_view(d.c)
+        o = _act(a + mem.gather_view(d.b) + mem.gather_view(d.c), d.act)
     elif d.op == 2:
-        o = a * torch.where(mem.gather_view(d.b) > 0, 1.0, 0.3)
+        bb = mem.gather_view(d.b)
+        o = a * torch.where(bb > 0, torch.ones_like(bb), torch.full_like(bb, 0.3))
     else:
         o = a
     mem.write_view(d.out, o)
@@ -334,10 +337,113 @@ def emu_memset(mem, d):
     t[off:off + d.bytes // es] = 0
 
 
+def _resize_matrix(in_size, f, mode):
+    """[out, in] interpolation matrix of one axis (nearest repeat, or half-pixel bilinear with edge clamp)"""
+    out = in_size * f
+    M = torch.zeros(out, in_size, dtype=torch.float64)
+    for o in range(out):
+        if mode == 0:
+            M[o, o // f] = 1.0
+        else:
+            src = (o + 0.5) / f - 0.5
+            fl = math.floor(src)
+            lam = src - fl
+            i0, i1 = min(max(fl, 0), in_size - 1), min(max(fl + 1, 0), in_size - 1)
+            M[o, i0] += 1.0 - lam
+            M[o, i1] += lam
+    return M
+
+
+def emu_resize_fwd(mem, d):
+    x = mem.gather_view(d.x)
+    Mh, Mw = _resize_matrix(d.x.H, d.fh, d.mode), _resize_matrix(d.x.W, d.fw, d.mode)
+    y = torch.einsum("ah,nhwc->nawc", Mh, x)
+    y = torch.einsum("bw,nawc->nabc", Mw, y)
+    y = _act(y, d.act)
+    if d.c_valid:
+        y[..., d.c_valid:] = 0
+    mem.write_view(d.y, y)
+
+
+def emu_resize_bwd(mem, d):
+    g = mem.gather_view(d.y)
+    if d.act != L.ACT_NONE:
+        g = g * _dact_from_y(mem.gather_view(d.yfwd), d.act)
+    Mh, Mw = _resize_matrix(d.x.H, d.fh, d.mode), _resize_matrix(d.x.W, d.fw, d.mode)
+    dx = torch.einsum("ah,nabc->nhbc", Mh, g)
+    dx = torch.einsum("bw,nhbc->nhwc", Mw, dx)
+    mem.write_view(d.x, dx)
+
+
+def emu_mulbc_fwd(mem, d):
+    mem.write_view(d.out, mem.gather_view(d.a) * mem.gather_view(d.b)[..., :1])
+
+
+def emu_mulbc_bwd(mem, d):
+    a, b, g = mem.gather_view(d.a), mem.gather_view(d.b), mem.gather_view(d.dout)
+    mem.write_view(d.da, g * b[..., :1])
+    db = torch.zeros(d.db.N, d.db.H, d.db.W, d.db.C, dtype=torch.float64)
+    db[..., 0] = (g * a).sum(-1)
+    mem.write_view(d.db, db)
+
+
+def emu_colstats(mem, d):
+    x = mem.gather_view(d.x).reshape(-1, d.x.C)
+    part = mem.f32(d.partials, d.n_blocks * 2 * d.x.C).view(d.n_blocks, 2, d.x.C)
+    part.zero_()
+    part[0, 0], part[0, 1] = x.sum(0), (x * x).sum(0)
+
+
+def _hs(t):
+    return torch.clamp(0.2 * t + 0.5, 0.0, 1.0)
+
+
+def _hs_grad(t):
+    u = 0.2 * t + 0.5
+    return torch.where((u >= 0) & (u <= 1), torch.full_like(u, 0.2), torch.zeros_like(u))
+
+
+def emu_lstm_fwd(mem, d):
+    z = mem.gather_view(d.z)
+    F = d.F
+    zi, zg, zo = z[..., :F], z[..., F:2 * F], z[..., 2 * F:3 * F]
+    mem.write_view(d.h, _hs(zo) * torch.tanh(_hs(zi) * torch.tanh(zg)))
+
+
+def emu_lstm_bwd(mem, d):
+    z = mem.gather_view(d.z)
+    F = d.F
+    zi, zg, zo = z[..., :F], z[..., F:2 * F], z[..., 2 * F:3 * F]
+    dh = mem.gather_view(d.dh)
+    gi, gg, go = _hs(zi), torch.tanh(zg), _hs(zo)
+    c = gi * gg
+    tc = torch.tanh(c)
+    dc = dh * go * (1 - tc * tc)
+    dz = torch.zeros_like(z)
+    dz[..., :F] = dc * gg * _hs_grad(zi)
+    dz[..., F:2 * F] = dc * gi * (1 - gg * gg)
+    dz[..., 2 * F:3 * F] = dh * tc * _hs_grad(zo)
+    mem.write_view(d.dz, dz)
+
+
+def emu_pool_bwd(mem, d):
+    y = mem.gather_view(d.y)
+    N, H, W, C = y.shape
+    ph, pw = d.ph, d.pw
+    yw = y.view(N, H // ph, ph, W // pw, pw, C).permute(0, 1, 3, 5, 2, 4).reshape(N, H // ph, W // pw, C, ph * pw)
+    first = yw.argmax(dim=-1)
+    g = mem.gather_view(d.dp)
+    onehot = torch.nn.functional.one_hot(first, ph * pw).double() * g.unsqueeze(-1)
+    dx = onehot.view(N, H // ph, W // pw, C, ph, pw).permute(0, 1, 4, 2, 5, 3).reshape(N, H, W, C)
+    mem.write_view(d.dx, dx)
+
+
 EMU = {L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_finalize, L.OP_BN_ACT: emu_bn_act,
        L.OP_BN_BWD: emu_bn_bwd, L.OP_ADAM: emu_adam, L.OP_HEAD_FWD: emu_head_fwd, L.OP_HEAD_BWD: emu_head_bwd,
        L.OP_LOSS: emu_loss, L.OP_ELTWISE: emu_eltwise, L.OP_CAST: emu_cast, L.OP_COLSUM: emu_colsum,
-       L.OP_MEMSET: emu_memset}
+       L.OP_MEMSET: emu_memset, L.OP_RESIZE_FWD: emu_resize_fwd, L.OP_RESIZE_BWD: emu_resize_bwd,
+       L.OP_MULBC_FWD: emu_mulbc_fwd, L.OP_MULBC_BWD: emu_mulbc_bwd, L.OP_COLSTATS: emu_colstats,
+       L.OP_LSTM_FWD: emu_lstm_fwd, L.OP_LSTM_BWD: emu_lstm_bwd, L.OP_POOL_BWD: emu_pool_bwd}
 
 
 def run_phase(mem, planner, phase):

@@ -341,3 +341,107 @@ def test_cast_eltwise_colsum():
     assert torch.equal(out[..., :3], src.to(torch.bfloat16)) and float(out[..., 3:].float().abs().max()) == 0
     assert torch.equal(o, (a.float() + b.float()).to(torch.bfloat16))
     assert torch.allclose(cs, a.float().view(-1, 64).sum(0), atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# kernels of the decoder variants beyond plain UNet
+@pytest.mark.parametrize("N,H,W,Cc,fh,fw,mode,act", [(2, 8, 8, 64, 2, 2, 1, L.ACT_NONE), (2, 4, 6, 16, 4, 4, 1, L.ACT_SIGMOID),
+                                                     (1, 2, 2, 8, 16, 16, 1, L.ACT_SIGMOID), (3, 1, 32, 64, 1, 2, 0, L.ACT_NONE),
+                                                     (2, 1, 16, 8, 1, 4, 0, L.ACT_SIGMOID), (2, 16, 16, 8, 2, 2, 1, L.ACT_NONE)])
+def test_resize_fwd_bwd(N, H, W, Cc, fh, fw, mode, act):
+    dev = "cuda"
+    x = bf(torch.randn(N, H, W, Cc, device=dev))
+    y = torch.zeros(N, H * fh, W * fw, Cc, device=dev, dtype=torch.bfloat16)
+    L.call("b2seg_resize_fwd", L.ResizeDesc(tv(x).to_c(), tv(y).to_c(), lw.NULL_VIEW.to_c(), fh, fw, mode, act, 0), stream())
+    torch.cuda.synchronize()
+    xt = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    if mode == 1:
+        ref = F.interpolate(xt, scale_factor=(fh, fw), mode="bilinear", align_corners=False)
+    else:
+        ref = xt.repeat_interleave(fh, 2).repeat_interleave(fw, 3)
+    if act == L.ACT_SIGMOID:
+        ref = torch.sigmoid(ref)
+    assert rel_l2(y.float(), ref.permute(0, 2, 3, 1)) < 4e-3
+    dy = bf(torch.randn_like(y.float()))
+    # backward uses the STORED (bf16) forward output for the activation derivative
+    yt = y.float().permute(0, 3, 1, 2)
+    g = dy.float().permute(0, 3, 1, 2) * (yt * (1 - yt) if act == L.ACT_SIGMOID else 1.0)
+    lin = F.interpolate(xt, scale_factor=(fh, fw), mode="bilinear", align_corners=False) if mode == 1 else xt.repeat_interleave(fh, 2).repeat_interleave(fw, 3)
+    lin.backward(g)
+    dx = torch.zeros_like(x)
+    L.call("b2seg_resize_bwd", L.ResizeDesc(tv(dx).to_c(), tv(dy).to_c(), tv(y).to_c(), fh, fw, mode, act, 0), stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dx.float(), xt.grad.permute(0, 2, 3, 1)) < 5e-3
+
+
+def test_mulbc_colstats_lstm_poolbwd_eltwise_act():
+    dev = "cuda"
+    N, H, W, Cc = 2, 16, 16, 64
+    a = bf(torch.randn(N, H, W, Cc, device=dev))
+    b = bf(torch.rand(N, H, W, 8, device=dev))
+    out = torch.zeros_like(a)
+    nv = lw.NULL_VIEW.to_c()
+    L.call("b2seg_mulbc_fwd", L.MulbcDesc(tv(a).to_c(), tv(b).to_c(), tv(out).to_c(), nv, nv, nv), stream())
+    g = bf(torch.randn_like(a.float()))
+    da, db = torch.zeros_like(a), torch.full_like(b, 3.0)
+    L.call("b2seg_mulbc_bwd", L.MulbcDesc(tv(a).to_c(), tv(b).to_c(), nv, tv(g).to_c(), tv(da).to_c(), tv(db).to_c()), stream())
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), a.float() * b.float()[..., :1]) < 4e-3
+    assert rel_l2(da.float(), g.float() * b.float()[..., :1]) < 4e-3
+    assert rel_l2(db.float()[..., 0], (g.float() * a.float()).sum(-1)) < 4e-3 and float(db.float()[..., 1:].abs().max()) == 0
+    # column statistics
+    nb = 16
+    part = torch.zeros(nb, 2, Cc, device=dev)
+    L.call("b2seg_colstats", L.ColstatsDesc(tv(a).to_c(), part.data_ptr(), nb), stream())
+    torch.cuda.synchronize()
+    af = a.float().view(-1, Cc)
+    assert torch.allclose(part[:, 0].sum(0), af.sum(0), atol=1e-2, rtol=1e-4) and torch.allclose(part[:, 1].sum(0), (af * af).sum(0), atol=1e-2, rtol=1e-4)
+    # ConvLSTM gates
+    Fg = 32
+    z = bf(torch.randn(N, H, W, 3 * Fg, device=dev) * 2)
+    h = torch.zeros(N, H, W, Fg, device=dev, dtype=torch.bfloat16)
+    L.call("b2seg_lstm_fwd", L.LstmDesc(tv(z).to_c(), tv(h).to_c(), nv, nv, Fg), stream())
+    zt = z.float().requires_grad_(True)
+    hs = lambda t: torch.clamp(0.2 * t + 0.5, 0, 1)
+    href = hs(zt[..., 2 * Fg:]) * torch.tanh(hs(zt[..., :Fg]) * torch.tanh(zt[..., Fg:2 * Fg]))
+    dh = bf(torch.randn_like(h.float()))
+    href.backward(dh.float())
+    dz = torch.zeros_like(z)
+    L.call("b2seg_lstm_bwd", L.LstmDesc(tv(z).to_c(), nv, tv(dh).to_c(), tv(dz).to_c(), Fg), stream())
+    torch.cuda.synchronize()
+    assert rel_l2(h.float(), href.detach()) < 4e-3 and rel_l2(dz.float(), zt.grad) < 5e-3
+    # max-pool backward, 4x4 window
+    y = bf(torch.randn(N, H, W, Cc, device=dev))
+    dp = bf(torch.randn(N, H // 4, W // 4, Cc, device=dev))
+    dx = torch.zeros_like(y)
+    L.call("b2seg_pool_bwd", L.PoolBwdDesc(tv(y).to_c(), tv(dp).to_c(), tv(dx).to_c(), 4, 4), stream())
+    torch.cuda.synchronize()
+    yt = y.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.max_pool2d(yt, 4).backward(dp.float().permute(0, 3, 1, 2))
+    assert rel_l2(dx.float(), yt.grad.permute(0, 2, 3, 1)) < 1e-6
+    # add + relu
+    o = torch.zeros_like(a)
+    L.call("b2seg_eltwise", L.EltwiseDesc(0, tv(a).to_c(), tv(y).to_c(), nv, tv(o).to_c(), L.ACT_RELU), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(o, torch.relu(a.float() + y.float()).to(torch.bfloat16))
+
+
+def test_strided_1x1_dgrad_and_bn_act_cvalid():
+    dev = "cuda"
+    N, H, W, Cin, Cout = 2, 16, 16, 64, 64
+    dy = bf(torch.randn(N, H // 2, W // 2, Cout, device=dev))
+    w = bf(torch.randn(Cout, 1, Cin, device=dev) * 0.1)
+    dx = torch.zeros(N, H, W, Cin, device=dev, dtype=torch.bfloat16)
+    L.call("b2seg_conv", lw.conv_dgrad(tv(dy), w.data_ptr(), Cout, 1, 1, Cin, tv(dx).parity(0, 0, 2, 2)), stream())
+    torch.cuda.synchronize()
+    x = torch.zeros(N, Cin, H, W, device=dev, requires_grad=True)
+    F.conv2d(x, w.float().view(Cout, 1, 1, Cin).permute(0, 3, 1, 2), stride=2).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(dx.float(), x.grad.permute(0, 2, 3, 1)) < 4e-3
+    z = bf(torch.randn(N, H, W, 8, device=dev))
+    o = torch.zeros_like(z)
+    d = L.BnActDesc()
+    d.x, d.act, d.n_out, d.c_valid = tv(z).to_c(), L.ACT_SIGMOID, 1, 1
+    d.out[0] = tv(o).to_c()
+    L.call("b2seg_bn_act", d, stream())
+    torch.cuda.synchronize()
+    assert rel_l2(o.float()[..., 0], torch.sigmoid(z.float()[..., 0])) < 4e-3 and float(o.float()[..., 1:].abs().max()) == 0

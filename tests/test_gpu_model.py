@@ -263,3 +263,39 @@ def test_fit_and_history_api():
     assert h.history["loss"][-1] < h.history["loss"][0]
     w = m.get_weights()
     assert len(w) == len(m.graph.param_specs())
+
+
+FAMILY_CASES = [
+    ("UNetPP", dict(ds=1, ag=1, output_nums=4, final_activation="softmax"), 64, 16, 3),   # BASELINE config 3 graph family
+    ("UNet", dict(lstm=1, dense_loop=3), 64, 16, 3),                                      # BASELINE config 5 graph family ("BCDUNet")
+    ("UNet3P", dict(ds=1), 64, 16, 3),
+    ("UNetE", dict(is_transconv=False, ag=1), 32, 16, 2),
+]
+
+
+@pytest.mark.parametrize("dec,kw,size,width,depth", FAMILY_CASES, ids=[c[0] + "-" + "-".join(f"{k}{v}" for k, v in c[1].items()) for c in FAMILY_CASES])
+def test_2d_families_per_layer(dec, kw, size, width, depth):
+    kw = dict(num_channels=3, **kw)
+    m = unet_model_builder(dec, size, size, width, depth, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(11)
+    x = rng.random((4, size, size, 3), dtype=np.float32)
+    targets, losses = [], []
+    for n in m.graph.outputs:
+        H, W, C = n.shape
+        if n.name == "out" and kw.get("final_activation") == "softmax":
+            targets.append(np.eye(C, dtype=np.float32)[rng.integers(0, C, (4, H, W))]); losses.append("cce")
+        elif n.name == "out":
+            targets.append((rng.random((4, H, W, C)) > 0.6).astype(np.float32)); losses.append("bce")
+        else:
+            targets.append(rng.standard_normal((4, H, W, C)).astype(np.float32)); losses.append("mse")
+    check_per_layer(m, Ref2D(dec, size, size, width, depth, **kw), 2, x, targets, losses, e2e_bound=1.0)
+
+
+def test_1d_bcdunet_lstm_ag_ds_per_layer():
+    from b2seg.models1d import BCDUNet
+    kw = dict(ds=1, ag=1, lstm=1, dense_loop=2)
+    m = BCDUNet(256, 3, 2, 16, 3, **kw).BCDUNet()
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((4, 256, 2)).astype(np.float32)
+    targets = [rng.standard_normal((4,) + (n.shape[1], n.shape[2])).astype(np.float32) for n in m.graph.outputs]
+    check_per_layer(m, Ref1D("BCDUNet", 256, 3, 2, 16, 3, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=1.0)

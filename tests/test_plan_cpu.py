@@ -15,7 +15,7 @@ from oracle.keras_ref import KerasRef, keras_adam_step, keras_loss
 from oracle.ref_models import Ref1D, Ref2D
 
 
-def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None):
+def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, strict=True):
     N = x.shape[0]
     params = init_params(graph, seed=7)
     # make BN affine and biases non-trivial so their handling is actually tested
@@ -45,7 +45,7 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None):
 
     # ---- oracle
     tp = {k: torch.from_numpy(v.copy()).double() for k, v in params.items()}
-    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=True)
+    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=strict)
     outs = ref(k, x.double())
     total = 0
     for i, (o, t) in enumerate(zip(outs, targets)):
@@ -61,7 +61,7 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None):
         if ndim == 1:
             got = got.squeeze(1)
         assert torch.allclose(got, want, atol=1e-8), (o["name"], float((got - want).abs().max()))
-    assert abs(float(mem.f32(pl.loss_ptr, 1)) - float(total)) < 1e-8
+    assert abs(float(mem.f32(pl.loss_ptr, 1)) - float(total.detach())) < 1e-7 * max(1.0, abs(float(total.detach())))
     # per-layer activations
     checked = 0
     for name, (view, C, kind) in pl.taps.items():

@@ -1,0 +1,80 @@
+"""Planner vs oracle (float64, CPU emulator) for the decoder families and flags beyond plain UNet:
+up-sampling decoders, attention gates, deep supervision, nested decoders (UNetE / UNet+ / UNet++), UNet3+, ConvLSTM skip
+fusion (the 2D 'BCDUNet' = lstm=1), and their 1D counterparts incl. BCDUNet."""
+import numpy as np
+import pytest
+import torch
+
+from b2seg.models1d import BCDUNet, UNet
+from b2seg.models2d import unet_model_builder
+from oracle.ref_models import Ref1D, Ref2D
+from test_plan_cpu import _run
+
+
+def _targets(graph, N, rng, ndim):
+    ts, losses = [], []
+    for n in graph.outputs:
+        H, W, C = n.shape
+        shape = (N, H, W, C) if ndim == 2 else (N, W, C)
+        if n.name == "out" and n.attrs.get("activation") == "sigmoid":
+            ts.append(torch.from_numpy((rng.random(shape) > 0.6).astype(np.float32))); losses.append("bce")
+        elif n.name == "out" and n.attrs.get("activation") == "softmax":
+            lab = rng.integers(0, C, shape[:-1])
+            ts.append(torch.from_numpy(np.eye(C, dtype=np.float32)[lab])); losses.append("cce")
+        else:
+            ts.append(torch.from_numpy(rng.standard_normal(shape).astype(np.float32))); losses.append("mse")
+    return ts, losses
+
+
+CASES_2D = [
+    ("UNet", dict(is_transconv=False)),
+    ("UNet", dict(ds=1)),
+    ("UNet", dict(ag=1)),
+    ("UNet", dict(ag=1, ds=1, is_transconv=False, output_nums=3, final_activation="softmax")),
+    ("UNet", dict(lstm=1, dense_loop=2)),
+    ("UNetE", dict(ds=1)),
+    ("UNetP", dict(ag=1)),
+    ("UNetPP", dict(ds=1, ag=1, output_nums=4, final_activation="softmax")),
+    ("UNetPP", dict(lstm=1)),
+    ("UNet3P", dict(ds=1)),
+]
+
+
+@pytest.mark.parametrize("dec,kw", CASES_2D, ids=[f"{d}-{'-'.join(f'{k}{v}' for k, v in kw.items())}" for d, kw in CASES_2D])
+def test_2d_family(dec, kw):
+    torch.manual_seed(0)
+    rng = np.random.default_rng(1)
+    depth = 2
+    W = 16 if kw.get("lstm") else 8
+    kw = dict(num_channels=2, **kw)
+    g = unet_model_builder(dec, 16, 16, W, depth, train_mode="from_scratch", **kw).build_graph()
+    x = torch.from_numpy(rng.random((2, 16, 16, 2), dtype=np.float32))
+    ts, losses = _targets(g, 2, rng, 2)
+    lw = [1.0 - 0.1 * i for i in range(len(ts))]
+    _run(g, Ref2D(dec, 16, 16, W, depth, **kw), x, ts, losses, 2, loss_weights=lw)
+
+
+CASES_1D = [
+    ("UNet", dict(ds=1, ag=1, is_transconv=False)),
+    ("UNet", dict(ds=0, lstm=1)),
+    ("UNetPP", dict(ds=1, ag=1)),
+    ("UNet3P", dict(ds=1)),
+    ("BCDUNet", dict(ds=1, lstm=1, dense_loop=2)),
+    ("BCDUNet", dict(ds=0, lstm=0, ag=1)),
+]
+
+
+@pytest.mark.parametrize("var,kw", CASES_1D, ids=[f"{d}-{'-'.join(f'{k}{v}' for k, v in kw.items())}" for d, kw in CASES_1D])
+def test_1d_family(var, kw):
+    rng = np.random.default_rng(2)
+    L_, depth, ch, ks = 32, 2, 2, 3
+    W = 16 if kw.get("lstm") else 8
+    if var == "BCDUNet":
+        g = BCDUNet(L_, depth, ch, W, ks, **kw).BCDUNet().graph
+    else:
+        g = getattr(UNet(L_, depth, ch, W, ks, **kw), var)().graph
+    x = torch.from_numpy(rng.standard_normal((2, L_, ch)).astype(np.float32))
+    ts, losses = _targets(g, 2, rng, 1)
+    # with lstm=0 the 1D BCDUNet drops its skip connections, so an attention gate built on them is a dangling branch that
+    # Keras prunes: the oracle (eager) still evaluates it with weights of its own
+    _run(g, Ref1D(var, L_, depth, ch, W, ks, **kw), x, ts, losses, 1, strict=not (var == "BCDUNet" and not kw.get("lstm")))

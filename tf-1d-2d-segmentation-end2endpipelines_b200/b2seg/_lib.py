@@ -18,7 +18,8 @@ ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_SOFTMAX = 0, 1, 2, 3, 4
 ACT_CODES = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "ReLU": ACT_RELU, "LeakyReLU": ACT_LEAKY,
              "sigmoid": ACT_SIGMOID, "softmax": ACT_SOFTMAX}
 (OP_CONV, OP_WGRAD, OP_BN_FINALIZE, OP_BN_ACT, OP_BN_BWD, OP_ADAM, OP_HEAD_FWD, OP_HEAD_BWD, OP_LOSS, OP_ELTWISE,
- OP_CAST, OP_COLSUM, OP_MEMSET) = range(1, 14)
+ OP_CAST, OP_COLSUM, OP_MEMSET, OP_RESIZE_FWD, OP_RESIZE_BWD, OP_MULBC_FWD, OP_MULBC_BWD, OP_COLSTATS, OP_LSTM_FWD,
+ OP_LSTM_BWD, OP_POOL_BWD) = range(1, 22)
 PHASE_FWD, PHASE_BWD, PHASE_OPT = 0, 1, 2
 
 
@@ -62,7 +63,7 @@ class BnFinalizeDesc(C.Structure):
 
 class BnActDesc(C.Structure):
     _fields_ = [("x", View), ("scale", C.c_uint64), ("shift", C.c_uint64), ("act", C.c_int32), ("n_out", C.c_int32),
-                ("out", View * 2), ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("pooled", View)]
+                ("out", View * 2), ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("pooled", View), ("c_valid", C.c_int32)]
 
 
 class GradSrc(C.Structure):
@@ -95,7 +96,28 @@ class LossDesc(C.Structure):
 
 
 class EltwiseDesc(C.Structure):
-    _fields_ = [("op", C.c_int32), ("a", View), ("b", View), ("c", View), ("out", View)]
+    _fields_ = [("op", C.c_int32), ("a", View), ("b", View), ("c", View), ("out", View), ("act", C.c_int32)]
+
+
+class ResizeDesc(C.Structure):
+    _fields_ = [("x", View), ("y", View), ("yfwd", View), ("fh", C.c_int32), ("fw", C.c_int32), ("mode", C.c_int32),
+                ("act", C.c_int32), ("c_valid", C.c_int32)]
+
+
+class MulbcDesc(C.Structure):
+    _fields_ = [("a", View), ("b", View), ("out", View), ("dout", View), ("da", View), ("db", View)]
+
+
+class ColstatsDesc(C.Structure):
+    _fields_ = [("x", View), ("partials", C.c_uint64), ("n_blocks", C.c_int32)]
+
+
+class LstmDesc(C.Structure):
+    _fields_ = [("z", View), ("h", View), ("dh", View), ("dz", View), ("F", C.c_int32)]
+
+
+class PoolBwdDesc(C.Structure):
+    _fields_ = [("y", View), ("dp", View), ("dx", View), ("ph", C.c_int32), ("pw", C.c_int32)]
 
 
 class CastDesc(C.Structure):
@@ -113,12 +135,16 @@ class MemsetDesc(C.Structure):
 
 OP_DESC = {OP_CONV: ConvDesc, OP_WGRAD: WgradDesc, OP_BN_FINALIZE: BnFinalizeDesc, OP_BN_ACT: BnActDesc,
            OP_BN_BWD: BnBwdDesc, OP_ADAM: AdamDesc, OP_HEAD_FWD: HeadDesc, OP_HEAD_BWD: HeadDesc, OP_LOSS: LossDesc,
-           OP_ELTWISE: EltwiseDesc, OP_CAST: CastDesc, OP_COLSUM: ColsumDesc, OP_MEMSET: MemsetDesc}
+           OP_ELTWISE: EltwiseDesc, OP_CAST: CastDesc, OP_COLSUM: ColsumDesc, OP_MEMSET: MemsetDesc,
+           OP_RESIZE_FWD: ResizeDesc, OP_RESIZE_BWD: ResizeDesc, OP_MULBC_FWD: MulbcDesc, OP_MULBC_BWD: MulbcDesc,
+           OP_COLSTATS: ColstatsDesc, OP_LSTM_FWD: LstmDesc, OP_LSTM_BWD: LstmDesc, OP_POOL_BWD: PoolBwdDesc}
 
 # every symbol include/b2seg.h declares (the CPU test-suite checks the library exports all of them)
 EXPORTED = ["b2seg_last_error", "b2seg_version", "b2seg_device_check", "b2seg_sizeof_desc", "b2seg_conv", "b2seg_conv_num_mtiles", "b2seg_conv_num_stat_rows",
             "b2seg_wgrad", "b2seg_bn_finalize", "b2seg_bn_act", "b2seg_bn_bwd", "b2seg_adam", "b2seg_head_fwd",
             "b2seg_head_bwd", "b2seg_loss", "b2seg_eltwise", "b2seg_cast_input", "b2seg_colsum", "b2seg_plan_create",
+            "b2seg_resize_fwd", "b2seg_resize_bwd", "b2seg_mulbc_fwd", "b2seg_mulbc_bwd", "b2seg_colstats", "b2seg_lstm_fwd",
+            "b2seg_lstm_bwd", "b2seg_pool_bwd",
             "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
 
 _lib = None
@@ -140,7 +166,10 @@ def load():
     for name, desc in [("b2seg_conv", ConvDesc), ("b2seg_wgrad", WgradDesc), ("b2seg_bn_finalize", BnFinalizeDesc),
                        ("b2seg_bn_act", BnActDesc), ("b2seg_bn_bwd", BnBwdDesc), ("b2seg_adam", AdamDesc),
                        ("b2seg_head_fwd", HeadDesc), ("b2seg_head_bwd", HeadDesc), ("b2seg_loss", LossDesc),
-                       ("b2seg_eltwise", EltwiseDesc), ("b2seg_cast_input", CastDesc), ("b2seg_colsum", ColsumDesc)]:
+                       ("b2seg_eltwise", EltwiseDesc), ("b2seg_cast_input", CastDesc), ("b2seg_colsum", ColsumDesc),
+                       ("b2seg_resize_fwd", ResizeDesc), ("b2seg_resize_bwd", ResizeDesc), ("b2seg_mulbc_fwd", MulbcDesc),
+                       ("b2seg_mulbc_bwd", MulbcDesc), ("b2seg_colstats", ColstatsDesc), ("b2seg_lstm_fwd", LstmDesc),
+                       ("b2seg_lstm_bwd", LstmDesc), ("b2seg_pool_bwd", PoolBwdDesc)]:
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(desc), C.c_void_p]
         fn.restype = C.c_int

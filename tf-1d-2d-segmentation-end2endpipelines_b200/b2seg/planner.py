@@ -174,6 +174,7 @@ class Planner:
         self.input_ptr = 0
         self.loss_ptr = 0
         self.units: List[dict] = []
+        self.catbuf: Dict[int, Phys] = {}
         self.act_bytes = 0
         self.op_info: Dict[Tuple[int, int], dict] = {}
         self._analyse()
@@ -218,8 +219,9 @@ class Planner:
         self.flat_concat: Dict[int, List[Node]] = {}
         self.absorbed_concat = set()
         # flatten nested concatenations (Concat_Block is a left fold of concatenate layers)
+        # a ConvLSTM's frame is the channel-concat of its inputs: it owns an input concat buffer like a concatenate layer
         for n in g.nodes:
-            if n.op == "concat":
+            if n.op in ("concat", "convlstm"):
                 parts = []
                 for i in n.inputs:
                     if i.op == "concat" and len(self.cons[id(i)]) == 1 and i not in g.outputs:
@@ -266,7 +268,36 @@ class Planner:
             elif n.op == "concat":
                 self.units.append(dict(kind="concat", node=n, out=n, parts=self.flat_concat[id(n)]))
             elif n.op == "add":
-                self.units.append(dict(kind="add", node=n, out=n))
+                u = dict(kind="add", node=n, out=n, act=None)
+                c = self._sole(n, "act")
+                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU"):
+                    u["act"], u["out"] = c, c
+                    absorbed.add(id(c))
+                self.units.append(u)
+            elif n.op == "up":
+                u = dict(kind="up", node=n, out=n, act=None)
+                c = self._sole(n, "act")
+                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                    u["act"], u["out"] = c, c
+                    absorbed.add(id(c))
+                self.units.append(u)
+            elif n.op == "pool":
+                self.units.append(dict(kind="pool", node=n, out=n))
+            elif n.op == "bn":
+                u = dict(kind="bn", node=n, out=n, act=None)
+                c = self._sole(n, "act")
+                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                    u["act"], u["out"] = c, c
+                    absorbed.add(id(c))
+                self.units.append(u)
+            elif n.op == "act":
+                if n.attrs["fn"] not in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                    raise PlanError(f"standalone activation '{n.attrs['fn']}' ({n.name}) is not lowered")
+                self.units.append(dict(kind="act", node=n, out=n))
+            elif n.op == "mul":
+                self.units.append(dict(kind="mul", node=n, out=n))
+            elif n.op == "convlstm":
+                self.units.append(dict(kind="convlstm", node=n, out=n, parts=self.flat_concat[id(n)]))
             else:
                 raise PlanError(f"layer type '{n.op}' ({n.name}) is not lowered yet")
         self.unit_of_out = {id(u["out"]): u for u in self.units}
@@ -313,6 +344,18 @@ class Planner:
                 self._add_param(f"{n.name}/beta", (n.C,), "vec", cp, True, C=n.C)
                 self._add_param(f"{n.name}/moving_mean", (n.C,), "vec", cp, False, C=n.C)
                 self._add_param(f"{n.name}/moving_variance", (n.C,), "vec", cp, False, C=n.C, fill=1.0)
+            elif n.op == "convlstm":
+                kh, kw = n.attrs["kernel"]
+                F = n.attrs["filters"]
+                if F % 8:
+                    raise PlanError(f"{n.name}: ConvLSTM filters must be a multiple of 8 (got {F})")
+                cin_p = sum(self._cphys(p) for p in self.flat_concat[id(n)])
+                # rows ordered [i | g | o | f]: the three live gates form a contiguous [3F][taps][cin] GEMM operand
+                self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], "lstm", 4 * F * kh * kw * cin_p, True,
+                                F=F, taps=kh * kw, cin_p=cin_p, kh=kh, kw=kw)
+                self._add_param(f"{n.name}/recurrent_kernel", specs[(n.name, "recurrent_kernel")][0], "blob",
+                                int(np.prod(specs[(n.name, "recurrent_kernel")][0])), True)
+                self._add_param(f"{n.name}/bias", (4 * F,), "lstm_bias", 4 * F, True, F=F)
 
     def _segs(self, t: Node) -> List[Tuple[int, int]]:
         """logical->physical channel segments a tensor will have once materialised (pure function of the graph)."""
@@ -379,17 +422,27 @@ class Planner:
         return c
 
     def _concat_buffer(self, c: Node) -> TView:
-        if id(c) not in self.phys:
-            H, W, _ = c.shape
-            view = self.new_act(H, W, self._cphys(c))
-            self.phys[id(c)] = Phys(view, c.C, self._segs(c))
-        return self.phys[id(c)].view
+        """the NHWC buffer holding the channel-concatenation consumed by a concatenate layer (= its output) or a ConvLSTM
+        (= its input frame); producers write channel windows of it"""
+        if id(c) not in self.catbuf:
+            parts = self.flat_concat[id(c)]
+            H, W, _ = parts[0].shape
+            segs, off = [], 0
+            for p in parts:
+                for (o, cc) in self._segs(p):
+                    segs.append((off + o, cc))
+                off += self._cphys(p)
+            view = self.new_act(H, W, off)
+            self.catbuf[id(c)] = Phys(view, sum(p.C for p in parts), segs)
+            if c.op == "concat":
+                self.phys[id(c)] = self.catbuf[id(c)]
+        return self.catbuf[id(c)].view
 
     def _dests(self, t: Node) -> List[TView]:
-        """views the producer of t should write: one slot per consuming concat, else one dense buffer"""
+        """views the producer of t should write: one slot per consuming concat / ConvLSTM frame, else one dense buffer"""
         dests = []
         for c in self.cons[id(t)]:
-            if c.op == "concat":
+            if c.op in ("concat", "convlstm"):
                 root = self._concat_root(c)
                 parts = self.flat_concat[id(root)]
                 buf = self._concat_buffer(root)
@@ -476,6 +529,7 @@ class Planner:
         d.n_out = min(len(dests), 2)
         for i in range(d.n_out):
             d.out[i] = dests[i].to_c()
+        d.c_valid = self._cvalid(co)
         if u["pool"] is not None:
             pn = u["pool"]
             pd = self._dests(pn)
@@ -495,15 +549,136 @@ class Planner:
         self._concat_buffer(n)  # producers already wrote their slots
         self.taps[n.name] = (self.phys[id(n)].view, n.C, "concat")
 
+    def _cvalid(self, C):
+        """channel count to pass as c_valid so padding lanes are forced to zero (0 = nothing to mask)"""
+        return C if C % 8 else 0
+
     def _fwd_add(self, u):
         n = u["node"]
-        if len(n.inputs) != 2:
-            raise PlanError("add with != 2 inputs")
-        a, b = self.phys[id(n.inputs[0])], self.phys[id(n.inputs[1])]
+        if len(n.inputs) not in (2, 3):
+            raise PlanError("add with != 2 or 3 inputs")
+        ins = [self.phys[id(i)] for i in n.inputs]
+        for p in ins[1:]:
+            if p.segs != ins[0].segs:
+                raise PlanError(f"{n.name}: operands of add have different channel layouts (odd-channel concat; not lowered yet)")
+        out_node = u["out"]
+        dests = self._dests(out_node)
+        self.phys[id(out_node)] = Phys(dests[0], out_node.C, list(ins[0].segs))
+        c = ins[2].view.to_c() if len(ins) == 3 else lw.NULL_VIEW.to_c()
+        self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(0 if len(ins) == 2 else 3, ins[0].view.to_c(), ins[1].view.to_c(), c, dests[0].to_c(),
+                                                 self._act_code(u["act"])), out_node.name)
+        self._copy_extra(dests[0], dests[1:])
+        u["y"] = dests[0]
+        self.taps[out_node.name] = (dests[0], n.C, "act")
+
+    def _fwd_up(self, u):
+        n = u["node"]
+        x = self.phys[id(n.inputs[0])]
+        out_node = u["out"]
+        dests = self._dests(out_node)
+        fh, fw = n.attrs["size"]
+        mode = 1 if n.attrs["interpolation"] == "bilinear" else 0
+        act = self._act_code(u["act"])
+        d = L.ResizeDesc(x.view.to_c(), dests[0].to_c(), lw.NULL_VIEW.to_c(), fh, fw, mode, act,
+                         self._cvalid(n.C) if act == L.ACT_SIGMOID else 0)
+        self.emit(0, L.OP_RESIZE_FWD, d, out_node.name)
+        self._copy_extra(dests[0], dests[1:])
+        u["y"] = dests[0]
+        self.taps[out_node.name] = (dests[0], n.C, "act")
+
+    def _fwd_pool(self, u):
+        n = u["node"]
+        x = self.phys[id(n.inputs[0])]
         dests = self._dests(n)
-        self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(0, a.view.to_c(), b.view.to_c(), lw.NULL_VIEW.to_c(), dests[0].to_c()), n.name)
+        d = L.BnActDesc()
+        d.x, d.act, d.n_out = x.view.to_c(), L.ACT_NONE, 0
+        d.pool_h, d.pool_w = n.attrs["size"]
+        d.pooled = dests[0].to_c()
+        self.emit(0, L.OP_BN_ACT, d, n.name)
         self._copy_extra(dests[0], dests[1:])
         self.taps[n.name] = (dests[0], n.C, "act")
+
+    def _fwd_act(self, u):
+        n = u["node"]
+        x = self.phys[id(n.inputs[0])]
+        dests = self._dests(n)
+        self.phys[id(n)] = Phys(dests[0], n.C, list(x.segs))
+        d = L.BnActDesc()
+        d.x, d.act, d.n_out = x.view.to_c(), self._act_code(n), min(len(dests), 2)
+        for i in range(d.n_out):
+            d.out[i] = dests[i].to_c()
+        d.c_valid = self._cvalid(n.C) if d.act == L.ACT_SIGMOID else 0
+        self.emit(0, L.OP_BN_ACT, d, n.name)
+        self._copy_extra(dests[0], dests[2:])
+        u["x"] = x.view
+        self.taps[n.name] = (dests[0], n.C, "act")
+
+    def _fwd_bn(self, u):
+        """BatchNormalization whose input is not a convolution output (MultiResBlock / ResPath): statistics kernel first"""
+        n = u["node"]
+        x = self.phys[id(n.inputs[0])]
+        if x.segs != [(0, n.C)]:
+            raise PlanError(f"{n.name}: BatchNormalization over a gapped (odd-channel concat) layout is not lowered yet")
+        H, W, _ = n.shape
+        cp = x.Cp
+        out_node = u["out"]
+        act = self._act_code(u["act"])
+        nb = max(1, min(592, (self.N * H * W) // 64))
+        stats = self.alloc(nb * 2 * cp * 4, "scratch") if self.training else 0
+        if self.training:
+            self.emit(0, L.OP_COLSTATS, L.ColstatsDesc(x.view.to_c(), stats, nb), f"stats {n.name}")
+        vec = self.alloc(4 * cp * 4, "scratch")
+        u["scale"], u["shift"], u["mean"], u["rstd"] = vec, vec + cp * 4, vec + 2 * cp * 4, vec + 3 * cp * 4
+        self.emit(0, L.OP_BN_FINALIZE, L.BnFinalizeDesc(
+            stats, nb, cp, float(self.N * H * W), self.pw(f"{n.name}/gamma"), self.pw(f"{n.name}/beta"),
+            self.pmov(f"{n.name}/moving_mean"), self.pmov(f"{n.name}/moving_variance"),
+            1 if self.training else 0, 1 if self.ndim == 2 else 0, n.attrs["eps"], n.attrs["momentum"],
+            u["scale"], u["shift"], u["mean"], u["rstd"], 0 if self.training else 1), n.name)
+        dests = self._dests(out_node)
+        d = L.BnActDesc()
+        d.x, d.scale, d.shift, d.act = x.view.to_c(), u["scale"], u["shift"], act
+        d.n_out = min(len(dests), 2)
+        for i in range(d.n_out):
+            d.out[i] = dests[i].to_c()
+        d.c_valid = self._cvalid(n.C)
+        self.emit(0, L.OP_BN_ACT, d, out_node.name)
+        self._copy_extra(dests[0], dests[2:])
+        u["x"], u["y"] = x.view, dests[0]
+        self.taps[out_node.name] = (dests[0], n.C, "act")
+
+    def _fwd_mul(self, u):
+        n = u["node"]
+        a, b = self.phys[id(n.inputs[0])], self.phys[id(n.inputs[1])]
+        if n.inputs[1].C != 1:
+            raise PlanError(f"{n.name}: only (N,H,W,C) * (N,H,W,1) broadcast multiplies are lowered")
+        dests = self._dests(n)
+        self.phys[id(n)] = Phys(dests[0], n.C, list(a.segs))
+        nv = lw.NULL_VIEW.to_c()
+        self.emit(0, L.OP_MULBC_FWD, L.MulbcDesc(a.view.to_c(), b.view.to_c(), dests[0].to_c(), nv, nv, nv), n.name)
+        self._copy_extra(dests[0], dests[1:])
+        self.taps[n.name] = (dests[0], n.C, "act")
+
+    def _fwd_convlstm(self, u):
+        n = u["node"]
+        a = n.attrs
+        kh, kw = a["kernel"]
+        F = a["filters"]
+        self._concat_buffer(n)
+        x = self.catbuf[id(n)]
+        pe = self.pindex[f"{n.name}/kernel"]
+        pe.meta["segs"] = list(x.segs)
+        assert pe.meta["cin_p"] == x.Cp
+        H, W, _ = n.shape
+        z = self.new_act(H, W, 3 * F)
+        u["z"] = z
+        flops = 2.0 * self.N * H * W * x.C * 3 * F * kh * kw   # live gates only (SURVEY §8a: 3F, no recurrent conv)
+        self.emit(0, L.OP_CONV, lw.conv_fprop(x.view, self.pwb(pe.key), 3 * F, kh, kw, x.Cp, z, bias=self.pw(f"{n.name}/bias")),
+                  n.name, flops=flops)
+        dests = self._dests(n)
+        nv = lw.NULL_VIEW.to_c()
+        self.emit(0, L.OP_LSTM_FWD, L.LstmDesc(z.to_c(), dests[0].to_c(), nv, nv, F), f"gates {n.name}")
+        self._copy_extra(dests[0], dests[1:])
+        self.taps[n.name] = (dests[0], F, "act")
 
     def _fwd_head(self, u):
         n = u["node"]
@@ -555,11 +730,166 @@ class Planner:
     def _bwd_input(self, u):
         pass
 
+    def _grad_like(self, t: Node) -> TView:
+        """a fresh gradient buffer with the physical layout of tensor t"""
+        p = self.phys[id(t)]
+        H, W, _ = t.shape
+        return self.new_act(H, W, p.Cp, "grad")
+
+    def _direct_sources(self, t: Node, srcs: List[GSrc]) -> List[GSrc]:
+        """turn max-pool-routed sources into dense ones (generic pool backward against the stored forward tensor)"""
+        out = []
+        for s in srcs:
+            if s.kind == 0:
+                out.append(s)
+            else:
+                dx = self._grad_like(t)
+                self.emit(1, L.OP_POOL_BWD, L.PoolBwdDesc(self.phys[id(t)].view.to_c(), s.view.to_c(), dx.to_c(), s.pool[0], s.pool[1]),
+                          f"pool bwd -> {t.name}")
+                out.append(GSrc(dx))
+        return out
+
+    def _kernel_sources(self, t: Node, srcs: List[GSrc]) -> List[GSrc]:
+        """sources in the form bn_bwd accepts: pooled sources only if they share one window of 2 or 4 elements"""
+        wins = {s.pool for s in srcs if s.kind == 1}
+        if len(wins) > 1 or any(w[0] * w[1] not in (2, 4) for w in wins):
+            srcs = self._direct_sources(t, srcs)
+        return self._reduce_sources(srcs, self.phys[id(t)].view)
+
+    def _single_grad(self, t: Node) -> Optional[TView]:
+        """one dense tensor holding the total gradient w.r.t. t (None if no gradient reaches t)"""
+        srcs = self.gsrc.get(id(t), [])
+        if not srcs:
+            return None
+        srcs = self._direct_sources(t, srcs)
+        if len(srcs) == 1:
+            return srcs[0].view
+        nv = lw.NULL_VIEW.to_c()
+        acc = srcs[0].view
+        i = 1
+        while i < len(srcs):
+            tmp = self._grad_like(t)
+            if i + 1 < len(srcs):
+                self.emit(1, L.OP_ELTWISE, L.EltwiseDesc(3, acc.to_c(), srcs[i].view.to_c(), srcs[i + 1].view.to_c(), tmp.to_c(), 0), "grad sum")
+                i += 2
+            else:
+                self.emit(1, L.OP_ELTWISE, L.EltwiseDesc(0, acc.to_c(), srcs[i].view.to_c(), nv, tmp.to_c(), 0), "grad sum")
+                i += 1
+            acc = tmp
+        return acc
+
+    def _act_bwd_noBN(self, t_out: Node, x_view: TView, act: int, note: str) -> Optional[TView]:
+        """dz = (sum of gradient sources of t_out) * act'(.) through the bn_bwd kernel without BatchNorm"""
+        srcs = self.gsrc.get(id(t_out), [])
+        if not srcs:
+            return None
+        srcs = self._kernel_sources(t_out, srcs)
+        dz = self._grad_like(t_out)
+        d = L.BnBwdDesc()
+        d.x, d.act, d.n_src = x_view.to_c(), act, len(srcs)
+        for i, s in enumerate(srcs):
+            d.src[i] = L.GradSrc(s.view.to_c(), s.kind, s.pool[0], s.pool[1])
+        d.count = 1.0
+        d.dx = dz.to_c()
+        self.emit(1, L.OP_BN_BWD, d, note)
+        return dz
+
     def _bwd_add(self, u):
-        n = u["node"]
-        for s in self.gsrc.get(id(n), []):
+        n, out_node = u["node"], u["out"]
+        if u["act"] is None:
+            for s in self.gsrc.get(id(n), []):
+                for i in n.inputs:
+                    self._add_gsrc(i, s)
+            return
+        act = self._act_code(u["act"])
+        dz = self._act_bwd_noBN(out_node, u["y"], act, f"act bwd {out_node.name}")  # relu / leaky: sign(y) == sign(pre-activation)
+        if dz is not None:
             for i in n.inputs:
-                self._add_gsrc(i, s)
+                self._add_gsrc(i, GSrc(dz))
+
+    def _bwd_up(self, u):
+        n, out_node = u["node"], u["out"]
+        dy = self._single_grad(out_node)
+        if dy is None or n.inputs[0].op == "input":
+            return
+        dx = self._grad_like(n.inputs[0])
+        fh, fw = n.attrs["size"]
+        mode = 1 if n.attrs["interpolation"] == "bilinear" else 0
+        act = self._act_code(u["act"])
+        yf = u["y"].to_c() if act != L.ACT_NONE else lw.NULL_VIEW.to_c()
+        self.emit(1, L.OP_RESIZE_BWD, L.ResizeDesc(dx.to_c(), dy.to_c(), yf, fh, fw, mode, act, 0), f"up bwd {n.name}")
+        self._add_gsrc(n.inputs[0], GSrc(dx))
+
+    def _bwd_pool(self, u):
+        n = u["node"]
+        srcs = self._direct_sources(n, self.gsrc.get(id(n), []))
+        for s in srcs:
+            self._add_gsrc(n.inputs[0], GSrc(s.view, 1, tuple(n.attrs["size"])))
+
+    def _bwd_act(self, u):
+        n = u["node"]
+        dz = self._act_bwd_noBN(n, u["x"], self._act_code(n), f"act bwd {n.name}")  # x = pre-activation: exact for every activation
+        if dz is not None and n.inputs[0].op != "input":
+            self._add_gsrc(n.inputs[0], GSrc(dz))
+
+    def _bwd_bn(self, u):
+        n, out_node = u["node"], u["out"]
+        srcs = self.gsrc.get(id(out_node), [])
+        if not srcs:
+            return
+        srcs = self._kernel_sources(out_node, srcs)
+        H, W, _ = n.shape
+        cp = u["x"].C
+        dx = self._grad_like(n.inputs[0])
+        d = L.BnBwdDesc()
+        d.x, d.scale, d.shift, d.mean, d.rstd = u["x"].to_c(), u["scale"], u["shift"], u["mean"], u["rstd"]
+        d.act, d.n_src = self._act_code(u["act"]), len(srcs)
+        for i, s in enumerate(srcs):
+            d.src[i] = L.GradSrc(s.view.to_c(), s.kind, s.pool[0], s.pool[1])
+        d.count = float(self.N * H * W)
+        nb = max(1, min(1184, (self.N * H * W) // 64))
+        d.partials, d.n_blocks = self.alloc(nb * 2 * cp * 4, "scratch"), nb
+        d.dgamma, d.dbeta = self.pg(f"{n.name}/gamma"), self.pg(f"{n.name}/beta")
+        d.dx = dx.to_c()
+        self.emit(1, L.OP_BN_BWD, d, f"bn bwd {n.name}")
+        self._add_gsrc(n.inputs[0], GSrc(dx))
+
+    def _bwd_mul(self, u):
+        n = u["node"]
+        dout = self._single_grad(n)
+        if dout is None:
+            return
+        a, b = self.phys[id(n.inputs[0])], self.phys[id(n.inputs[1])]
+        da, db = self._grad_like(n.inputs[0]), self._grad_like(n.inputs[1])
+        self.emit(1, L.OP_MULBC_BWD, L.MulbcDesc(a.view.to_c(), b.view.to_c(), lw.NULL_VIEW.to_c(), dout.to_c(), da.to_c(), db.to_c()),
+                  f"mul bwd {n.name}")
+        self._add_gsrc(n.inputs[0], GSrc(da))
+        self._add_gsrc(n.inputs[1], GSrc(db))
+
+    def _bwd_convlstm(self, u):
+        n = u["node"]
+        a = n.attrs
+        kh, kw = a["kernel"]
+        F = a["filters"]
+        dh = self._single_grad(n)
+        if dh is None:
+            return
+        x = self.catbuf[id(n)]
+        pe = self.pindex[f"{n.name}/kernel"]
+        H, W, _ = n.shape
+        dz = self.new_act(H, W, 3 * F, "grad")
+        nv = lw.NULL_VIEW.to_c()
+        self.emit(1, L.OP_LSTM_BWD, L.LstmDesc(u["z"].to_c(), nv, dh.to_c(), dz.to_c(), F), f"gates bwd {n.name}")
+        flops = 2.0 * self.N * H * W * x.C * 3 * F * kh * kw
+        self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, x.view, self.pg(pe.key), 3 * F, kh, kw, x.Cp), f"wgrad {n.name}", flops=flops)
+        self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")
+        dx = self.new_act(H, W, x.Cp, "grad")
+        self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(pe.key), 3 * F, kh, kw, x.Cp, dx), f"dgrad {n.name}", flops=flops)
+        off = 0
+        for p in u["parts"]:
+            cp = self._cphys(p)
+            self._add_gsrc(p, GSrc(dx.chan(off, cp)))
+            off += cp
 
     def _bwd_concat(self, u):
         n = u["node"]
@@ -594,9 +924,7 @@ class Planner:
         srcs = list(self.gsrc.get(id(out_node), []))
         if u["pool"] is not None:
             ph, pw_ = u["pool"].attrs["size"]
-            for s in self.gsrc.get(id(u["pool"]), []):
-                if s.kind != 0:
-                    raise PlanError("pool of pool")
+            for s in self._direct_sources(u["pool"], self.gsrc.get(id(u["pool"]), [])):
                 srcs.append(GSrc(s.view, 1, (ph, pw_)))
         if not srcs:
             return  # dead branch (no gradient reaches it)
@@ -606,8 +934,7 @@ class Planner:
         H, W, _ = n.shape
         act = self._act_code(u["act"])
         y: TView = u["y"]
-        ydense = TView.dense(0, self.N, H, W, cop)
-        srcs = self._reduce_sources(srcs, ydense)
+        srcs = self._kernel_sources(out_node, srcs)
         # ---- dZ: gradient w.r.t. the raw convolution output
         if u["bn"] is not None:
             bn = u["bn"]
@@ -653,10 +980,15 @@ class Planner:
         src_node = n.inputs[0]
         if src_node.op == "input":
             return
-        if strided:
-            raise PlanError("dgrad of strided conv not lowered yet")
         Hi, Wi, _ = src_node.shape
         dx = self.new_act(Hi, Wi, cin_p, "grad")
+        if strided:
+            # 1x1 'valid' stride-s conv reads pixels (s*i, s*j): its input gradient lives on that sub-grid; the other
+            # pixels of dx are never written and stay at the zeros the buffer was allocated with
+            self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx.parity(0, 0, a["strides"][0], a["strides"][1])),
+                      f"dgrad {n.name}", flops=self._conv_flops(n))
+            self._add_gsrc(src_node, GSrc(dx))
+            return
         mul_view, mul_mode, premasked = None, 0, False
         if src_node.op == "concat" and n.op == "conv":
             first = u_first = self.flat_concat[id(src_node)][0]
@@ -702,6 +1034,23 @@ class Planner:
                 w[po:po + c] = k[src:src + c]
                 src += c
             out[:w.size] = w.reshape(-1)
+        elif e.kind == "lstm":
+            # Keras (kh,kw,Cin,4F), gate order i,f,c,o -> rows [i | c(g) | o | f] x taps x cin_p
+            F = m["F"]
+            k = arr if arr.ndim == 4 else arr[None]
+            k = np.transpose(k, (3, 0, 1, 2))                   # (4F,kh,kw,Cin)
+            k = np.concatenate([k[0:F], k[2 * F:3 * F], k[3 * F:4 * F], k[F:2 * F]], 0)
+            w = np.zeros((4 * F, m["taps"], m["cin_p"]), np.float32)
+            src = 0
+            for (po, c) in m["segs"]:
+                w[:, :, po:po + c] = k[:, :, :, src:src + c].reshape(4 * F, m["taps"], c)
+                src += c
+            out[:w.size] = w.reshape(-1)
+        elif e.kind == "lstm_bias":
+            F = m["F"]
+            out[:4 * F] = np.concatenate([arr[0:F], arr[2 * F:3 * F], arr[3 * F:4 * F], arr[F:2 * F]])
+        elif e.kind == "blob":
+            out[:arr.size] = arr.reshape(-1)
         else:
             raise PlanError(e.kind)
         return out
@@ -732,6 +1081,24 @@ class Planner:
                 k[src:src + c] = w[po:po + c]
                 src += c
             return k.reshape(e.keras_shape)
+        if e.kind == "lstm":
+            F = m["F"]
+            w = flat[:4 * F * m["taps"] * m["cin_p"]].reshape(4 * F, m["taps"], m["cin_p"])
+            cin = sum(c for _, c in m["segs"])
+            k = np.zeros((4 * F, m["taps"], cin), np.float32)
+            src = 0
+            for (po, c) in m["segs"]:
+                k[:, :, src:src + c] = w[:, :, po:po + c]
+                src += c
+            k = np.concatenate([k[0:F], k[3 * F:4 * F], k[F:2 * F], k[2 * F:3 * F]], 0)   # back to i,f,c,o
+            k = k.reshape(4 * F, m["kh"], m["kw"], cin)
+            return np.transpose(k, (1, 2, 3, 0)).reshape(e.keras_shape)
+        if e.kind == "lstm_bias":
+            F = m["F"]
+            v = flat[:4 * F]
+            return np.concatenate([v[0:F], v[3 * F:4 * F], v[F:2 * F], v[2 * F:3 * F]]).reshape(e.keras_shape)
+        if e.kind == "blob":
+            return flat[:int(np.prod(e.keras_shape))].copy().reshape(e.keras_shape)
         raise PlanError(e.kind)
 
     def num_launch_ops(self, phase):

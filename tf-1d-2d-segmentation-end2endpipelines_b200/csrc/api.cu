@@ -123,6 +123,14 @@ static PreparedOp* prepare_any(int op, const void* desc, size_t bytes) {
     B2_CASE(B2SEG_OP_CAST, b2seg_cast_desc, prepare_cast)
     B2_CASE(B2SEG_OP_COLSUM, b2seg_colsum_desc, prepare_colsum)
     B2_CASE(B2SEG_OP_MEMSET, b2seg_memset_desc, prepare_memset)
+    B2_CASE(B2SEG_OP_RESIZE_FWD, b2seg_resize_desc, prepare_resize_fwd)
+    B2_CASE(B2SEG_OP_RESIZE_BWD, b2seg_resize_desc, prepare_resize_bwd)
+    B2_CASE(B2SEG_OP_MULBC_FWD, b2seg_mulbc_desc, prepare_mulbc_fwd)
+    B2_CASE(B2SEG_OP_MULBC_BWD, b2seg_mulbc_desc, prepare_mulbc_bwd)
+    B2_CASE(B2SEG_OP_COLSTATS, b2seg_colstats_desc, prepare_colstats)
+    B2_CASE(B2SEG_OP_LSTM_FWD, b2seg_lstm_desc, prepare_lstm_fwd)
+    B2_CASE(B2SEG_OP_LSTM_BWD, b2seg_lstm_desc, prepare_lstm_bwd)
+    B2_CASE(B2SEG_OP_POOL_BWD, b2seg_poolbwd_desc, prepare_pool_bwd)
     default:
       set_error("unknown op code %d", op);
       return nullptr;
@@ -157,6 +165,14 @@ int b2seg_sizeof_desc(int op) {
     case B2SEG_OP_CAST: return (int)sizeof(b2seg_cast_desc);
     case B2SEG_OP_COLSUM: return (int)sizeof(b2seg_colsum_desc);
     case B2SEG_OP_MEMSET: return (int)sizeof(b2seg_memset_desc);
+    case B2SEG_OP_RESIZE_FWD:
+    case B2SEG_OP_RESIZE_BWD: return (int)sizeof(b2seg_resize_desc);
+    case B2SEG_OP_MULBC_FWD:
+    case B2SEG_OP_MULBC_BWD: return (int)sizeof(b2seg_mulbc_desc);
+    case B2SEG_OP_COLSTATS: return (int)sizeof(b2seg_colstats_desc);
+    case B2SEG_OP_LSTM_FWD:
+    case B2SEG_OP_LSTM_BWD: return (int)sizeof(b2seg_lstm_desc);
+    case B2SEG_OP_POOL_BWD: return (int)sizeof(b2seg_poolbwd_desc);
     default: return -1;
   }
 }
@@ -187,6 +203,14 @@ B2_ENTRY(b2seg_loss, b2seg_loss_desc, b2::prepare_loss)
 B2_ENTRY(b2seg_eltwise, b2seg_eltwise_desc, b2::prepare_eltwise)
 B2_ENTRY(b2seg_cast_input, b2seg_cast_desc, b2::prepare_cast)
 B2_ENTRY(b2seg_colsum, b2seg_colsum_desc, b2::prepare_colsum)
+B2_ENTRY(b2seg_resize_fwd, b2seg_resize_desc, b2::prepare_resize_fwd)
+B2_ENTRY(b2seg_resize_bwd, b2seg_resize_desc, b2::prepare_resize_bwd)
+B2_ENTRY(b2seg_mulbc_fwd, b2seg_mulbc_desc, b2::prepare_mulbc_fwd)
+B2_ENTRY(b2seg_mulbc_bwd, b2seg_mulbc_desc, b2::prepare_mulbc_bwd)
+B2_ENTRY(b2seg_colstats, b2seg_colstats_desc, b2::prepare_colstats)
+B2_ENTRY(b2seg_lstm_fwd, b2seg_lstm_desc, b2::prepare_lstm_fwd)
+B2_ENTRY(b2seg_lstm_bwd, b2seg_lstm_desc, b2::prepare_lstm_bwd)
+B2_ENTRY(b2seg_pool_bwd, b2seg_poolbwd_desc, b2::prepare_pool_bwd)
 
 int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
   if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");

@@ -50,6 +50,14 @@ PreparedOp* prepare_eltwise(const b2seg_eltwise_desc* d);
 PreparedOp* prepare_cast(const b2seg_cast_desc* d);
 PreparedOp* prepare_colsum(const b2seg_colsum_desc* d);
 PreparedOp* prepare_memset(const b2seg_memset_desc* d);
+PreparedOp* prepare_resize_fwd(const b2seg_resize_desc* d);
+PreparedOp* prepare_resize_bwd(const b2seg_resize_desc* d);
+PreparedOp* prepare_mulbc_fwd(const b2seg_mulbc_desc* d);
+PreparedOp* prepare_mulbc_bwd(const b2seg_mulbc_desc* d);
+PreparedOp* prepare_colstats(const b2seg_colstats_desc* d);
+PreparedOp* prepare_lstm_fwd(const b2seg_lstm_desc* d);
+PreparedOp* prepare_lstm_bwd(const b2seg_lstm_desc* d);
+PreparedOp* prepare_pool_bwd(const b2seg_poolbwd_desc* d);
 
 // adam launches expose their mutable hyper-parameters to the plan
 void adam_update(PreparedOp* op, float lr, int64_t step, float grad_scale);

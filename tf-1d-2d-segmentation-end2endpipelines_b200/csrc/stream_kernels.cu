@@ -2,63 +2,9 @@
 // fused Adam, the small-Cout pointwise heads, the loss seed, element-wise glue and input cast.
 // All activation tensors are NHWC bf16 addressed through b2seg_view; every thread moves 16-byte vectors
 // (8 channels) so global accesses are coalesced along the channel axis.
-#include "common.h"
-#include "ptx.cuh"
+#include "stream_common.cuh"
 
 namespace b2 {
-
-struct DView {
-  unsigned long long ptr;
-  int N, H, W, C;
-  long long sn, sh, sw;
-};
-static DView dv(const b2seg_view& v) { return DView{v.ptr, v.N, v.H, v.W, v.C, v.sn, v.sh, v.sw}; }
-
-__device__ __forceinline__ const __nv_bfloat16* vaddr(const DView& v, int n, int h, int w, int c) {
-  return reinterpret_cast<const __nv_bfloat16*>(v.ptr) + n * v.sn + h * v.sh + w * v.sw + c;
-}
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void store8(const __nv_bfloat16* p, const float (&f)[8]) {
-  uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]);
-  u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]);
-  u.w = pack_bf16x2(f[6], f[7]);
-  *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(p)) = u;
-}
-__device__ __forceinline__ float act_fwd(float x, int act) {
-  switch (act) {
-    case B2SEG_ACT_RELU: return fmaxf(x, 0.f);
-    case B2SEG_ACT_LEAKY: return x > 0.f ? x : 0.3f * x;
-    case B2SEG_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
-    default: return x;
-  }
-}
-// derivative of the activation given its output y
-__device__ __forceinline__ float act_bwd_from_y(float y, int act) {
-  switch (act) {
-    case B2SEG_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case B2SEG_ACT_LEAKY: return y > 0.f ? 1.f : 0.3f;
-    case B2SEG_ACT_SIGMOID: return y * (1.f - y);
-    default: return 1.f;
-  }
-}
-
-static inline int grid_for(long long work, int block) {
-  long long g = (work + block - 1) / block;
-  if (g < 1) g = 1;
-  if (g > 0x7fffffffll) g = 0x7fffffffll;
-  return (int)g;
-}
 
 // ------------------------------------------------------------------------------------------ cast input
 __global__ void cast_input_kernel(const float* __restrict__ src, int N, int H, int W, int C, DView out) {
@@ -148,7 +94,7 @@ PreparedOp* prepare_bn_finalize(const b2seg_bn_finalize_desc* d) { auto* L = new
 struct BnActK {
   DView x, out0, out1, pooled;
   const float* scale; const float* shift;
-  int act, n_out, ph, pw;
+  int act, n_out, ph, pw, c_valid;
 };
 // One thread owns 8 channels of U windows (U*WIN pixels in flight: all loads are issued before any use).
 template <int WIN, int U>
@@ -188,7 +134,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(BnActK k) {
         const int h = wh[u] * k.ph + q / k.pw, w = ww[u] * k.pw + q % k.pw;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          f[u][q][e] = act_fwd(fmaf(f[u][q][e], sc[e], sf[e]), k.act);
+          f[u][q][e] = (k.c_valid && v * 8 + e >= k.c_valid) ? 0.f : act_fwd(fmaf(f[u][q][e], sc[e], sf[e]), k.act);
           mx[e] = fmaxf(mx[e], f[u][q][e]);
         }
         if (k.n_out > 0) store8(vaddr(k.out0, wn[u], h, w, v * 8), f[u][q]);
@@ -223,7 +169,7 @@ __global__ void bn_act_generic_kernel(BnActK k) {
         load8(vaddr(k.x, n, h, w, v * 8), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          f[e] = act_fwd(fmaf(f[e], sc[e], sf[e]), k.act);
+          f[e] = (k.c_valid && v * 8 + e >= k.c_valid) ? 0.f : act_fwd(fmaf(f[e], sc[e], sf[e]), k.act);
           mx[e] = fmaxf(mx[e], f[e]);
         }
         if (k.n_out > 0) store8(vaddr(k.out0, n, h, w, v * 8), f);
@@ -271,6 +217,7 @@ PreparedOp* prepare_bn_act(const b2seg_bn_act_desc* d) {
   k.ph = d->pool_h > 1 ? d->pool_h : 1;
   k.pw = d->pool_w > 1 ? d->pool_w : 1;
   if (k.ph > 1 || k.pw > 1) k.pooled = dv(d->pooled);
+  k.c_valid = d->c_valid;
   return L;
 }
 
@@ -1016,7 +963,7 @@ PreparedOp* prepare_loss(const b2seg_loss_desc* d) {
 }
 
 // ------------------------------------------------------------------------------------------ element-wise
-struct EltK { int op; DView a, b, c, out; };
+struct EltK { int op, act; DView a, b, c, out; };
 __global__ void eltwise_kernel(EltK k) {
   const int cv = k.out.C / 8;
   const unsigned total = (unsigned)k.out.N * k.out.H * k.out.W * cv;
@@ -1037,6 +984,8 @@ __global__ void eltwise_kernel(EltK k) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] += b[e];
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = act_fwd(o[e], k.act);
     } else if (k.op == 2) {
       load8(vaddr(k.b, n, h, w, v * 8), b);
 #pragma unroll
@@ -1060,7 +1009,7 @@ struct EltLaunch : PreparedOp {
 PreparedOp* prepare_eltwise(const b2seg_eltwise_desc* d) {
   if (d->out.C % 8) { set_error("eltwise: C %% 8"); return nullptr; }
   auto* L = new EltLaunch();
-  L->k.op = d->op; L->k.a = dv(d->a); L->k.b = dv(d->b); L->k.c = dv(d->c); L->k.out = dv(d->out);
+  L->k.op = d->op; L->k.act = d->act; L->k.a = dv(d->a); L->k.b = dv(d->b); L->k.c = dv(d->c); L->k.out = dv(d->out);
   return L;
 }
 
