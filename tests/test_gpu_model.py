@@ -58,7 +58,9 @@ def _device_step(model, x, targets, losses, lr=1e-3, loss_weights=None):
 
 def _oracle(ref, ndim, params, x, targets, losses, out_names, loss_weights=None, override=None):
     tp = {k: torch.from_numpy(np.array(v)).double() for k, v in params.items()}
-    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=True)
+    # MultiResUNet builds a ResPath on the deepest encoder level that nothing consumes (Keras prunes it; the eager oracle
+    # evaluates it with weights of its own), hence strict=False for that family only
+    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict="MultiResUNet" not in (getattr(ref, "dec", ""), getattr(ref, "var", "")))
     k.override = override
     outs = ref(k, torch.from_numpy(x).double())
     total = 0
@@ -274,6 +276,8 @@ FAMILY_CASES = [
     ("UNet", dict(lstm=1, dense_loop=3), 64, 16, 3),                                      # BASELINE config 5 graph family ("BCDUNet")
     ("UNet3P", dict(ds=1), 64, 16, 3),
     ("UNetE", dict(is_transconv=False, ag=1, ds=1), 32, 16, 2),   # ds=1: without it UNetE leaves dangling nodes that Keras prunes
+    ("MultiResUNet", dict(), 64, 32, 3),                           # BASELINE config 4 graph family (odd channel counts: gapped concat layouts)
+    ("MultiResUNet", dict(is_transconv=False, ds=1), 32, 16, 2),
 ]
 
 

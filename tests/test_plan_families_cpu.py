@@ -37,6 +37,8 @@ CASES_2D = [
     ("UNetPP", dict(ds=1, ag=1, output_nums=4, final_activation="softmax")),
     ("UNetPP", dict(lstm=1)),
     ("UNet3P", dict(ds=1)),
+    ("MultiResUNet", dict()),                      # odd channel counts (w/6, w/3, w/2): gapped concat layouts
+    ("MultiResUNet", dict(ds=1, is_transconv=False)),
 ]
 
 
@@ -51,7 +53,9 @@ def test_2d_family(dec, kw):
     x = torch.from_numpy(rng.random((2, 16, 16, 2), dtype=np.float32))
     ts, losses = _targets(g, 2, rng, 2)
     lw = [1.0 - 0.1 * i for i in range(len(ts))]
-    _run(g, Ref2D(dec, 16, 16, W, depth, **kw), x, ts, losses, 2, loss_weights=lw)
+    # MultiResUNet builds a ResPath on the deepest encoder level that no decoder level consumes: Keras prunes it, the
+    # eager oracle still evaluates it with weights of its own
+    _run(g, Ref2D(dec, 16, 16, W, depth, **kw), x, ts, losses, 2, loss_weights=lw, strict=dec != "MultiResUNet")
 
 
 CASES_1D = [
@@ -61,6 +65,8 @@ CASES_1D = [
     ("UNet3P", dict(ds=1)),
     ("BCDUNet", dict(ds=1, lstm=1, dense_loop=2)),
     ("BCDUNet", dict(ds=0, lstm=0, ag=1)),
+    ("MultiResUNet", dict(ds=0)),
+    ("MultiResUNet", dict(ds=1, ag=1)),
 ]
 
 
@@ -77,4 +83,4 @@ def test_1d_family(var, kw):
     ts, losses = _targets(g, 2, rng, 1)
     # with lstm=0 the 1D BCDUNet drops its skip connections, so an attention gate built on them is a dangling branch that
     # Keras prunes: the oracle (eager) still evaluates it with weights of its own
-    _run(g, Ref1D(var, L_, depth, ch, W, ks, **kw), x, ts, losses, 1, strict=not (var == "BCDUNet" and not kw.get("lstm")))
+    _run(g, Ref1D(var, L_, depth, ch, W, ks, **kw), x, ts, losses, 1, strict=not ((var == "BCDUNet" and not kw.get("lstm")) or var == "MultiResUNet"))

@@ -142,7 +142,10 @@ class Engine:
         off = (view.ptr - base.data_ptr()) // 2
         flat = base.view(torch.bfloat16)
         out = torch.as_strided(flat, (view.N, view.H, view.W, view.C), (view.sn, view.sh, view.sw, 1), off)
-        return out[..., :Cn].float()
+        idx = p.logical_channels(name)
+        if idx == list(range(Cn)):
+            return out[..., :Cn].float()
+        return out[..., torch.tensor(idx, device=out.device)].float()
 
     def __del__(self):
         try:

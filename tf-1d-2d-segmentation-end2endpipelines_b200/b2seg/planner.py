@@ -304,6 +304,38 @@ class Planner:
         for u in self.units:
             if u.get("pool") is not None:
                 self.unit_of_out[id(u["pool"])] = u
+        # ---- channel-layout classes.  Tensors related by an element-wise layer (BN, activation, pool, up-sampling, add, the
+        # attention multiply) must share one physical channel layout.  A class containing a concatenate output inherits that
+        # concat's (possibly gapped: odd channel counts are padded per slot) layout, and the convolutions feeding the class
+        # are made to PRODUCE it by scattering their weight rows — MultiResBlock's `add([shortcut, BN(concat(...))])`.
+        parent = {id(n): id(n) for n in g.nodes}
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+
+        def union(a, b):
+            ra, rb = find(id(a)), find(id(b))
+            if ra != rb:
+                parent[ra] = rb
+
+        for n in g.nodes:
+            if n.op in ("bn", "act", "pool", "up"):
+                union(n, n.inputs[0])
+            elif n.op == "add":
+                for i in n.inputs:
+                    union(n, i)
+            elif n.op == "mul":
+                union(n, n.inputs[0])
+        self._find = find
+        self._cls_concat: Dict[int, List[Node]] = {}
+        for n in g.nodes:
+            if n.op == "concat" and id(n) not in self.absorbed_concat:
+                self._cls_concat.setdefault(find(id(n)), []).append(n)
+        self._segs_memo: Dict[int, List[Tuple[int, int]]] = {}
+        self._cphys_memo: Dict[int, int] = {}
 
     # ---------------------------------------------------------------------------------------- parameters
     def _add_param(self, key, keras_shape, kind, size, trainable, **meta):
@@ -334,16 +366,16 @@ class Planner:
                     self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], "head", cin_p * co, True, cin_p=cin_p, cout=co)
                     self._add_param(f"{n.name}/bias", (co,), "vec", co, True, C=co)
                 else:
-                    cop = ceil8(co)
+                    cop, osegs = self._cphys(n), self._segs(n)   # the conv produces the layout of its element-wise class
                     self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], n.op, cop * kh * kw * cin_p, True,
-                                    cout=co, cout_p=cop, taps=kh * kw, cin_p=cin_p, kh=kh, kw=kw)
-                    self._add_param(f"{n.name}/bias", (co,), "vec", cop, True, C=co)
+                                    cout=co, cout_p=cop, taps=kh * kw, cin_p=cin_p, kh=kh, kw=kw, out_segs=osegs)
+                    self._add_param(f"{n.name}/bias", (co,), "vec", cop, True, C=co, vsegs=osegs, Cp=cop)
             elif n.op == "bn":
-                cp = ceil8(n.C)
-                self._add_param(f"{n.name}/gamma", (n.C,), "vec", cp, True, C=n.C, fill=1.0)
-                self._add_param(f"{n.name}/beta", (n.C,), "vec", cp, True, C=n.C)
-                self._add_param(f"{n.name}/moving_mean", (n.C,), "vec", cp, False, C=n.C)
-                self._add_param(f"{n.name}/moving_variance", (n.C,), "vec", cp, False, C=n.C, fill=1.0)
+                cp, vs = self._cphys(n), self._segs(n)
+                self._add_param(f"{n.name}/gamma", (n.C,), "vec", cp, True, C=n.C, fill=1.0, vsegs=vs, Cp=cp)
+                self._add_param(f"{n.name}/beta", (n.C,), "vec", cp, True, C=n.C, vsegs=vs, Cp=cp)
+                self._add_param(f"{n.name}/moving_mean", (n.C,), "vec", cp, False, C=n.C, vsegs=vs, Cp=cp)
+                self._add_param(f"{n.name}/moving_variance", (n.C,), "vec", cp, False, C=n.C, fill=1.0, vsegs=vs, Cp=cp)
             elif n.op == "convlstm":
                 kh, kw = n.attrs["kernel"]
                 F = n.attrs["filters"]
@@ -357,24 +389,50 @@ class Planner:
                                 int(np.prod(specs[(n.name, "recurrent_kernel")][0])), True)
                 self._add_param(f"{n.name}/bias", (4 * F,), "lstm_bias", 4 * F, True, F=F)
 
+    def _concat_layout(self, c: Node) -> Tuple[List[Tuple[int, int]], int]:
+        segs, off = [], 0
+        for p in self.flat_concat[id(c)]:
+            for (o, cc) in self._segs(p):
+                segs.append((off + o, cc))
+            off += self._cphys(p)
+        return segs, off
+
+    def _class_layout(self, t: Node) -> Tuple[List[Tuple[int, int]], int]:
+        """(segments, physical channel count) shared by every tensor of t's element-wise class (pure function of the graph)"""
+        key = self._find(id(t))
+        if key not in self._segs_memo:
+            fixed = self._cls_concat.get(key, [])
+            if t.op == "concat" and id(t) in self.absorbed_concat:
+                fixed = []
+            if fixed:
+                segs, cp = self._concat_layout(fixed[0])
+                for other in fixed[1:]:
+                    if self._concat_layout(other) != (segs, cp):
+                        raise PlanError(f"{fixed[0].name} and {other.name} meet in one element-wise class with different channel layouts")
+            else:
+                segs, cp = [(0, t.C)], ceil8(t.C)
+            self._segs_memo[key], self._cphys_memo[key] = segs, cp
+        return self._segs_memo[key], self._cphys_memo[key]
+
     def _segs(self, t: Node) -> List[Tuple[int, int]]:
-        """logical->physical channel segments a tensor will have once materialised (pure function of the graph)."""
-        if t.op == "concat" and id(t) in self.flat_concat:
-            segs, off = [], 0
-            for p in self.flat_concat[id(t)]:
-                for (o, c) in self._segs(p):
-                    segs.append((off + o, c))
-                off += self._cphys(p)
-            return segs
-        return [(0, t.C)]
+        """logical->physical channel segments a tensor will have once materialised"""
+        if t.op == "concat" and id(t) in self.absorbed_concat:
+            return self._concat_layout(t)[0]
+        return self._class_layout(t)[0]
 
     def _cphys(self, t: Node) -> int:
-        if t.op == "concat" and id(t) in self.flat_concat:
-            return sum(self._cphys(p) for p in self.flat_concat[id(t)])
-        return ceil8(t.C)
+        if t.op == "concat" and id(t) in self.absorbed_concat:
+            return self._concat_layout(t)[1]
+        return self._class_layout(t)[1]
 
     def _cin_phys(self, t: Node) -> int:
         return self._cphys(t)
+
+    def logical_channels(self, name: str) -> List[int]:
+        """physical channel index of every logical channel of a tapped layer (identity unless the layout is gapped)"""
+        if not hasattr(self, "_by_name"):
+            self._by_name = {n.name: n for n in self.g.nodes}
+        return [po + i for (po, c) in self._segs(self._by_name[name]) for i in range(c)]
 
     # ---------------------------------------------------------------------------------------- arenas
     def bind_arenas(self):
@@ -449,12 +507,12 @@ class Planner:
                 off = 0
                 for p in parts:
                     if p is t:
-                        dests.append(buf.chan(off, ceil8(t.C)))
+                        dests.append(buf.chan(off, self._cphys(t)))
                     off += self._cphys(p)
         H, W, _ = t.shape
         if not dests:
-            dests.append(self.new_act(H, W, ceil8(t.C)))
-        self.phys[id(t)] = Phys(dests[0], t.C, [(0, t.C)])
+            dests.append(self.new_act(H, W, self._cphys(t)))
+        self.phys[id(t)] = Phys(dests[0], t.C, list(self._segs(t)))
         return dests
 
     def _copy_extra(self, src: TView, extra: List[TView]):
@@ -529,7 +587,7 @@ class Planner:
         d.n_out = min(len(dests), 2)
         for i in range(d.n_out):
             d.out[i] = dests[i].to_c()
-        d.c_valid = self._cvalid(co)
+        d.c_valid = self._cvalid(co, self._segs(n), act)
         if u["pool"] is not None:
             pn = u["pool"]
             pd = self._dests(pn)
@@ -549,8 +607,14 @@ class Planner:
         self._concat_buffer(n)  # producers already wrote their slots
         self.taps[n.name] = (self.phys[id(n)].view, n.C, "concat")
 
-    def _cvalid(self, C):
-        """channel count to pass as c_valid so padding lanes are forced to zero (0 = nothing to mask)"""
+    def _cvalid(self, C, segs=None, act=0):
+        """channel count to pass as c_valid so padding lanes are forced to zero (0 = nothing to mask).  In a gapped layout
+        (odd-channel concat slots) padding lanes are interleaved; they stay zero by construction for every activation
+        with f(0) = 0, so only sigmoid needs the mask and is refused there."""
+        if segs is not None and list(segs) != [(0, C)]:
+            if act == L.ACT_SIGMOID:
+                raise PlanError("sigmoid over a gapped (odd-channel concat) channel layout is not lowered")
+            return 0
         return C if C % 8 else 0
 
     def _fwd_add(self, u):
@@ -580,7 +644,7 @@ class Planner:
         mode = 1 if n.attrs["interpolation"] == "bilinear" else 0
         act = self._act_code(u["act"])
         d = L.ResizeDesc(x.view.to_c(), dests[0].to_c(), lw.NULL_VIEW.to_c(), fh, fw, mode, act,
-                         self._cvalid(n.C) if act == L.ACT_SIGMOID else 0)
+                         self._cvalid(n.C, x.segs, act) if act == L.ACT_SIGMOID else 0)
         self.emit(0, L.OP_RESIZE_FWD, d, out_node.name)
         self._copy_extra(dests[0], dests[1:])
         u["y"] = dests[0]
@@ -607,7 +671,7 @@ class Planner:
         d.x, d.act, d.n_out = x.view.to_c(), self._act_code(n), min(len(dests), 2)
         for i in range(d.n_out):
             d.out[i] = dests[i].to_c()
-        d.c_valid = self._cvalid(n.C) if d.act == L.ACT_SIGMOID else 0
+        d.c_valid = self._cvalid(n.C, x.segs, d.act) if d.act == L.ACT_SIGMOID else 0
         self.emit(0, L.OP_BN_ACT, d, n.name)
         self._copy_extra(dests[0], dests[2:])
         u["x"] = x.view
@@ -617,8 +681,6 @@ class Planner:
         """BatchNormalization whose input is not a convolution output (MultiResBlock / ResPath): statistics kernel first"""
         n = u["node"]
         x = self.phys[id(n.inputs[0])]
-        if x.segs != [(0, n.C)]:
-            raise PlanError(f"{n.name}: BatchNormalization over a gapped (odd-channel concat) layout is not lowered yet")
         H, W, _ = n.shape
         cp = x.Cp
         out_node = u["out"]
@@ -640,7 +702,7 @@ class Planner:
         d.n_out = min(len(dests), 2)
         for i in range(d.n_out):
             d.out[i] = dests[i].to_c()
-        d.c_valid = self._cvalid(n.C)
+        d.c_valid = self._cvalid(n.C, x.segs, act)
         self.emit(0, L.OP_BN_ACT, d, out_node.name)
         self._copy_extra(dests[0], dests[2:])
         u["x"], u["y"] = x.view, dests[0]
@@ -996,7 +1058,7 @@ class Planner:
             if (pu is not None and pu["kind"] == "conv" and pu["bn"] is None and pu["act"] is not None and pu["out"] is first
                     and len(self.cons[id(first)]) == 1 and len(self.cons[id(src_node)]) == 1
                     and self._act_code(pu["act"]) in (L.ACT_RELU, L.ACT_LEAKY)):
-                mul_view, mul_mode, premasked = x.view.chan(0, ceil8(first.C)), self._act_code(pu["act"]), True
+                mul_view, mul_mode, premasked = x.view.chan(0, self._cphys(first)), self._act_code(pu["act"]), True
         if n.op == "tconv":
             self.emit(1, L.OP_CONV, lw.tconv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx), f"dgrad {n.name}", flops=self._conv_flops(n))
         else:
@@ -1011,19 +1073,32 @@ class Planner:
         out = np.zeros(e.size, np.float32)
         arr = np.asarray(arr, np.float32)
         if e.kind == "vec":
-            out[:m["C"]] = arr
-            if m.get("fill") is not None:
-                out[m["C"]:ceil8(m["C"])] = m["fill"]
+            if m.get("vsegs"):
+                if m.get("fill") is not None:
+                    out[:m["Cp"]] = m["fill"]
+                src = 0
+                for (po, c) in m["vsegs"]:
+                    out[po:po + c] = arr[src:src + c]
+                    src += c
+            else:
+                out[:m["C"]] = arr
+                if m.get("fill") is not None:
+                    out[m["C"]:ceil8(m["C"])] = m["fill"]
         elif e.kind in ("conv", "tconv"):
             k = arr if arr.ndim == 4 else arr[None]            # (kh,kw,Cin,Cout) | tconv (kh,kw,Cout,Cin)
             if e.kind == "conv":
                 k = np.transpose(k, (3, 0, 1, 2))               # -> (Cout,kh,kw,Cin)
             else:
                 k = np.transpose(k, (2, 0, 1, 3))               # -> (Cout,kh,kw,Cin)
-            w = np.zeros((m["cout_p"], m["taps"], m["cin_p"]), np.float32)
+            wl = np.zeros((m["cout"], m["taps"], m["cin_p"]), np.float32)   # logical rows, physical columns
             src = 0
             for (po, c) in m["segs"]:
-                w[:m["cout"], :, po:po + c] = k[:, :, :, src:src + c].reshape(m["cout"], m["taps"], c)
+                wl[:, :, po:po + c] = k[:, :, :, src:src + c].reshape(m["cout"], m["taps"], c)
+                src += c
+            w = np.zeros((m["cout_p"], m["taps"], m["cin_p"]), np.float32)
+            src = 0
+            for (po, c) in m.get("out_segs") or [(0, m["cout"])]:
+                w[po:po + c] = wl[src:src + c]
                 src += c
             out[:w.size] = w.reshape(-1)
         elif e.kind == "head":
@@ -1060,9 +1135,12 @@ class Planner:
         m = e.meta
         flat = np.asarray(flat, np.float32)
         if e.kind == "vec":
+            if m.get("vsegs"):
+                return np.concatenate([flat[po:po + c] for (po, c) in m["vsegs"]]).reshape(e.keras_shape)
             return flat[:m["C"]].copy().reshape(e.keras_shape)
         if e.kind in ("conv", "tconv"):
             w = flat[:m["cout_p"] * m["taps"] * m["cin_p"]].reshape(m["cout_p"], m["taps"], m["cin_p"])
+            w = np.concatenate([w[po:po + c] for (po, c) in (m.get("out_segs") or [(0, m["cout"])])], 0)   # logical rows
             cin = sum(c for _, c in m["segs"])
             k = np.zeros((m["cout"], m["taps"], cin), np.float32)
             src = 0
