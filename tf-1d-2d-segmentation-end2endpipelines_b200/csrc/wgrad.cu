@@ -182,6 +182,11 @@ PreparedOp* prepare_wgrad(const b2seg_wgrad_desc* d) {
     set_error("wgrad: channel extents must be multiples of 8");
     return nullptr;
   }
+  {
+    bool hard_error = false;
+    PreparedOp* fused = prepare_wgrad_halo(d, &hard_error);  // fused-tap halo kernel (wgrad_halo.cu) when eligible
+    if (fused || hard_error) return fused;
+  }
   WgradLaunch* L = new WgradLaunch();
   WgradKParams& kp = L->kp;
   memset(&kp, 0, sizeof(kp));
