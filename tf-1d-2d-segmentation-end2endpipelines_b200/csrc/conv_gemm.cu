@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* colpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::kBarBytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler (uniform datapath)
   const int lane = threadIdx.x & 31;
   const ConvEpiParams& e = p.e;
 
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int nkb = p.taps_per_group * p.kc_blocks;
 
@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues:
+    // warp-uniform control flow keeps the descriptors in uniform registers, see conv_halo.cu)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN ? 1 : 0);
       // descriptors are built once; per MMA only the 14-bit start-address field (16-byte units) changes
       const uint64_t adesc0 = make_smem_desc(0, 16, 1024);
@@ -126,16 +127,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint64_t bd = bdesc0 + (a16 + (kAStageBytes >> 4));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            umma_bf16_elect(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_elect(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_elect(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-    __syncwarp();
   } else {
     conv_epilogue<BLOCK_N>(e, staging, colpart, tfull_bar, tempty_bar, tmem_base);
   }

@@ -17,7 +17,7 @@
 
 namespace b2 {
 
-constexpr int kHaloAStages = 2;
+constexpr int kHaloMaxAStages = 6;      // A (halo tile) pipeline depth is chosen per layer: (stages-1) x MMA time per stage must cover the TMA latency
 constexpr int kHaloABytes = 24576;          // >= (bh+kh-1)*(bw+kw-1)*128
 constexpr int kHaloMaxBStages = 16;
 constexpr int kHaloMaxWins = 16;
@@ -32,6 +32,7 @@ struct alignas(64) HaloKParams {
   int4 taps[B2SEG_MAX_TAPS];   // x = row of the tap inside the window, y = column, w = widx
   int wins_per_group, kc_blocks;
   int ww, a_bytes, sbo;        // halo width (pixels), bytes per A stage actually loaded, 8-row-group pitch in bytes
+  int a_stages;                // halo-tile pipeline stages (2..kHaloMaxAStages)
   int b_stages;                // non-resident: number of B pipeline stages
   int b_region_bytes;
   int b_resident_tiles;        // resident: number of B tiles (taps * channel blocks)
@@ -45,11 +46,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kHaloAStages * kHaloABytes;
+  const int a_stages = p.a_stages;
+  uint8_t* sB = smem + a_stages * kHaloABytes;
   uint8_t* staging = sB + p.b_region_bytes;
   uint64_t* fullA = reinterpret_cast<uint64_t*>(staging + kStgBytes);
-  uint64_t* emptyA = fullA + kHaloAStages;
-  uint64_t* fullB = emptyA + kHaloAStages;
+  uint64_t* emptyA = fullA + kHaloMaxAStages;
+  uint64_t* fullB = emptyA + kHaloMaxAStages;
   uint64_t* emptyB = fullB + kHaloMaxBStages;
   uint64_t* tfull_bar = emptyB + kHaloMaxBStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -58,14 +60,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint32_t* s_tapoff = tmem_slot + 4;           // per tap: start-row offset inside the halo tile, in 16-byte units
   float* colpart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapoff + B2SEG_MAX_TAPS) + 15) & ~uintptr_t(15));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler (uniform datapath)
   const int lane = threadIdx.x & 31;
   const ConvEpiParams& e = p.e;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B2SEG_MAX_SRC; ++i) tma_prefetch_desc(&p.amap[i]);
     tma_prefetch_desc(&p.bmap);
-    for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < a_stages; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kHaloMaxBStages; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     mbar_init(bres_bar, 1);
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             mbar_wait(&emptyA[sa], pa ^ 1);
             mbar_arrive_expect_tx(&fullA[sa], p.a_bytes);
             tma_load_4d(&p.amap[win.map], &fullA[sa], sA + sa * kHaloABytes, cb * kBlockK, w0 + win.ow0, h0 + win.oh0, n0);
-            if (++sa == kHaloAStages) { sa = 0; pa ^= 1; }
+            if (++sa == (uint32_t)a_stages) { sa = 0; pa ^= 1; }
             if (!B_RES) {
               for (int t = win.tap_begin; t < win.tap_end; ++t) {
                 mbar_wait(&emptyB[sb_i], pb ^ 1);
@@ -154,7 +156,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop with warp-uniform control flow and one elected lane issues each tcgen05 operation,
+    // so descriptors live in uniform registers (under `if (lane == 0)` every MMA paid ELECT + 8 R2UR, ~100 clocks:
+    // issue-bound for N <= 128, profiles/r1_prof_conv2d_12_issue.txt).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN ? 1 : 0);
       // descriptors are built once; per MMA only the 14-bit start-address field (16-byte units) changes
       const uint64_t adesc0 = make_smem_desc(0, 16, p.sbo);
@@ -179,10 +184,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             mbar_wait(&fullA[sa], pa);
             tc_fence_after();
             const uint64_t ad_stage = adesc0 + (sA16 + sa * (kHaloABytes >> 4));
-            uint32_t off_next = s_tapoff[tap_begin];
             for (int t = tap_begin; t < tap_end; ++t) {
-              const uint32_t off = off_next;
-              if (t + 1 < tap_end) off_next = s_tapoff[t + 1];
+              const uint32_t off = (uint32_t)(p.taps[t].x * p.ww + p.taps[t].y) * 8u;   // start row of the tap inside the halo tile
               uint64_t bd;
               if (B_RES) {
                 bd = bdesc0 + res16;
@@ -195,24 +198,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
               const uint64_t ad = ad_stage + off;
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
-                umma_bf16(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
+                umma_bf16_elect(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
                 accumulate = 1;
               }
               if (!B_RES) {
-                umma_commit(&emptyB[sb_i]);
+                umma_commit_elect(&emptyB[sb_i]);
                 if (++sb_i == (uint32_t)b_stages) { sb_i = 0; pb ^= 1; }
               }
             }
-            umma_commit(&emptyA[sa]);
-            if (++sa == kHaloAStages) { sa = 0; pa ^= 1; }
+            umma_commit_elect(&emptyA[sa]);
+            if (++sa == (uint32_t)a_stages) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_elect(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-    __syncwarp();
   } else {
     conv_epilogue<BLOCK_N>(e, staging, colpart, tfull_bar, tempty_bar, tmem_base);
   }
@@ -358,22 +360,36 @@ PreparedOp* prepare_conv_halo(const b2seg_conv_desc* d) {
     if (encode_weight_map(&kp.bmap, d->weights, d->w_cout, d->w_taps, d->w_cin, 64, kBlockK) != 0) { delete L; return nullptr; }
   }
   const int b_stage = L->block_n * kBlockK * 2;
-  const int fixed = 1024 + kHaloAStages * kHaloABytes + kStgBytes + (2 * kHaloAStages + 2 * kHaloMaxBStages + 5) * 8 + 16 + B2SEG_MAX_TAPS * 4 + kColPartBytes + 64;
-  const int b_budget = kHaloSmemBudget - fixed;
+  const int fixed = 1024 + kStgBytes + (2 * kHaloMaxAStages + 2 * kHaloMaxBStages + 5) * 8 + 16 + B2SEG_MAX_TAPS * 4 + kColPartBytes + 64;
+  const int budget = kHaloSmemBudget - fixed;   // A stages + B region
+  // A pipeline depth.  Measured (profiles/r1_convbench_astages.txt): deeper halo pipelines do not help any cfg2 layer —
+  // narrow layers are bound by re-streaming the weights through L2 -> shared memory (64 B/clk/SM needed, ~42 available),
+  // not by halo latency — and giving up resident weights for more stages costs 1.7x on the Cout = 64 layers.
+  static const int env_a = getenv("B2SEG_HALO_ASTAGES") ? atoi(getenv("B2SEG_HALO_ASTAGES")) : 0;
+  int want_a = 2;
+  if (env_a >= 2 && env_a <= kHaloMaxAStages) want_a = env_a;
   const int res_tiles = d->n_groups * d->taps_per_group * kp.kc_blocks;
   static const bool no_res = getenv("B2SEG_NO_BRES") != nullptr;
-  L->b_res = !no_res && d->n_groups == 1 && kp.e.n_tiles == 1 && res_tiles * b_stage <= b_budget && kp.e.total_tiles >= 2 * num_sms();
+  const bool res_ok = !no_res && d->n_groups == 1 && kp.e.n_tiles == 1 && kp.e.total_tiles >= 2 * num_sms();
+  // resident weights leave room for how many A stages?
+  const int a_with_res = res_ok ? std::min(want_a, (budget - res_tiles * b_stage) / kHaloABytes) : 0;
+  L->b_res = res_ok && a_with_res >= std::min(want_a, 3);
   if (L->b_res) {
+    kp.a_stages = a_with_res;
     kp.b_resident_tiles = res_tiles;
     kp.b_region_bytes = res_tiles * b_stage;
     kp.b_stages = 1;
   } else {
     int st = L->block_n == 256 ? 4 : (L->block_n == 128 ? 6 : 8);
-    while (st * b_stage > b_budget) --st;
+    const int min_st = L->block_n == 256 ? 3 : 4;
+    kp.a_stages = want_a;
+    while (st > min_st && kp.a_stages * kHaloABytes + st * b_stage > budget) --st;
+    while (kp.a_stages > 2 && kp.a_stages * kHaloABytes + st * b_stage > budget) --kp.a_stages;
+    while (st > 1 && kp.a_stages * kHaloABytes + st * b_stage > budget) --st;
     kp.b_stages = st;
     kp.b_region_bytes = st * b_stage;
   }
-  L->smem_bytes = fixed + kp.b_region_bytes;
+  L->smem_bytes = fixed + kp.a_stages * kHaloABytes + kp.b_region_bytes;
   const int sms = num_sms();
   L->grid = kp.e.total_tiles < sms ? kp.e.total_tiles : sms;
   return L;

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   // work item
   int wi = blockIdx.x;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int pair = p.taps[tap_i][0], dyh = p.taps[tap_i][1], dyw = p.taps[tap_i][2];
   const int dh = p.taps[tap_i][3], dw = p.taps[tap_i][4], widx = p.taps[tap_i][5];
@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && n_iter > 0) {
+    // whole warp, one elected lane issues (uniform-register descriptors, see conv_halo.cu)
+    if (n_iter > 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
       const uint64_t desc0 = make_smem_desc(0, kWgPix * 128, 1024);  // both operands MN-major: LBO = one 64-channel box
       const uint32_t smem16 = smem_u32(smem) >> 4;
@@ -104,11 +105,11 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
         const uint32_t a16 = smem16 + stage * (Cfg::kStageBytes >> 4);
         const uint64_t ad = desc0 + a16, bd = desc0 + (a16 + (kWgABytes >> 4));
 #pragma unroll
-        for (int k = 0; k < kWgPix / 16; ++k) umma_bf16(tmem_base, ad + k * 128, bd + k * 128, idesc, (it | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
+        for (int k = 0; k < kWgPix / 16; ++k) umma_bf16_elect(tmem_base, ad + k * 128, bd + k * 128, idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit_elect(&empty_bar[stage]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar);
+      umma_commit_elect(tfull_bar);
     }
     __syncwarp();
   }

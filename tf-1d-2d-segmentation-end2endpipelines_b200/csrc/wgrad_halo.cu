@@ -67,7 +67,7 @@ struct WhSeg { int m_tile, n_tile, group, c_begin, c_end, atomic; };
 struct alignas(64) WhParams {
   CUtensorMap ymap[B2SEG_MAX_SRC];
   CUtensorMap xmap[kWhMaxXMaps];
-  const WhGroup* groups;
+  WhGroup groups[kWhMaxGroups];   // in the parameter (constant) bank: the MMA warp reads it through the uniform datapath
   const WhSeg* segs;
   const int* cta_seg;      // [n_ctas + 1] first segment of every CTA
   int bw, bh, bn, tiles_w, tiles_h;
@@ -81,7 +81,6 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
-
 __host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) {   // matches make_smem_desc (ptx.cuh)
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
@@ -96,9 +95,8 @@ __global__ void __launch_bounds__(kWhThreads) wgrad_halo_kernel(const __grid_con
   uint64_t* tfull_bar = empty_bar + kWhMaxStages;
   uint64_t* tempty_bar = tfull_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
-  uint32_t* gm = reinterpret_cast<uint32_t*>(tail + 128);   // MMA part of the current group (kWhMmaPartBytes)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int seg_begin = p.cta_seg[blockIdx.x], seg_end = p.cta_seg[blockIdx.x + 1];
 
   if (threadIdx.x == 0) {
@@ -111,7 +109,7 @@ __global__ void __launch_bounds__(kWhThreads) wgrad_halo_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register for the MMA operands
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -120,7 +118,7 @@ __global__ void __launch_bounds__(kWhThreads) wgrad_halo_kernel(const __grid_con
       const int half_a = p.a_bytes >> 1;
       for (int si = seg_begin; si < seg_end; ++si) {
         const WhSeg sg = p.segs[si];
-        const WhGroup* G = p.groups + sg.group;
+        const WhGroup* G = &p.groups[sg.group];
         const CUtensorMap* ym = &p.ymap[G->pair];
         const CUtensorMap* xm = &p.xmap[G->xmap];
         const int dyh = G->dyh, dyw = G->dyw, hmin = G->hmin, wmin = G->wmin, xchunk = G->xchunk_bytes;
@@ -144,7 +142,7 @@ __global__ void __launch_bounds__(kWhThreads) wgrad_halo_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     // dY tile: dense MN-major, 8-pixel groups 1024 B apart, the second 64-channel chunk half a tile further
     const uint32_t a_lo0 = (uint32_t)((p.a_bytes >> 1) >> 4) << 16;
     constexpr uint32_t a_hi = smem_desc_hi(1024);
@@ -152,49 +150,37 @@ __global__ void __launch_bounds__(kWhThreads) wgrad_halo_kernel(const __grid_con
     const uint32_t stage16 = p.stage_bytes >> 4, ab16 = p.a_bytes >> 4;
     uint32_t stage = 0, phase = 0;
     for (int si = seg_begin; si < seg_end; ++si) {
-      const WhSeg sg = p.segs[si];
-      __syncwarp();
-      {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p.groups + sg.group) + kWhMmaPartOffset);
-        for (int i = lane; i < kWhMmaPartBytes / 4; i += 32) gm[i] = src[i];
-      }
-      __syncwarp();
-      if (lane == 0) {
-        if (si > seg_begin) { mbar_wait(tempty_bar, (uint32_t)(si - seg_begin - 1) & 1); tc_fence_after(); }
-        const int n_slots = (int)gm[0];
-        uint32_t kr[KSTEPS];
+      const int group = __shfl_sync(0xffffffffu, p.segs[si].group, 0);
+      const int n_iter = __shfl_sync(0xffffffffu, p.segs[si].c_end - p.segs[si].c_begin, 0);
+      const WhGroup& G = p.groups[group];
+      if (si > seg_begin) { mbar_wait(tempty_bar, (uint32_t)(si - seg_begin - 1) & 1); tc_fence_after(); }
+      const int n_slots = G.n_slots;
+      for (int it = 0; it < n_iter; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a16 = smem16 + stage * stage16;
+        const uint32_t b16 = a16 + ab16;
+        const uint32_t a_lo = a_lo0 + a16;
+        for (int s = 0; s < n_slots; ++s) {
+          const uint32_t blo = G.slot[s].blo + b16;
+          const uint32_t bhi = G.slot[s].bhi, idesc = G.slot[s].idesc;
+          const uint32_t d_tmem = tmem_base + G.slot[s].col;
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) kr[k] = gm[4 + k];
-        const uint4* slots = reinterpret_cast<const uint4*>(gm + 12);
-        const int n_iter = sg.c_end - sg.c_begin;
-        for (int it = 0; it < n_iter; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a16 = smem16 + stage * stage16;
-          const uint32_t b16 = a16 + ab16;
-          const uint32_t a_lo = a_lo0 + a16;
-          for (int s = 0; s < n_slots; ++s) {
-            const uint4 sk = slots[s];   // blo, bhi, idesc, col
-            const uint32_t blo = sk.x + b16;
-            const uint32_t d_tmem = tmem_base + sk.w;
-#pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_bf16(d_tmem, mk64(a_lo + k * 128, a_hi), mk64(blo + kr[k], sk.y), sk.z, (it | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == (uint32_t)p.n_stages) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < KSTEPS; ++k)
+            umma_bf16_elect(d_tmem, mk64(a_lo + k * 128, a_hi), mk64(blo + G.krow8[k], bhi), idesc, (it | k) != 0 ? 1u : 0u);
         }
-        umma_commit(tfull_bar);
+        umma_commit_elect(&empty_bar[stage]);
+        if (++stage == (uint32_t)p.n_stages) { stage = 0; phase ^= 1; }
       }
+      umma_commit_elect(tfull_bar);
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> dW
     const int q = warp & 3;   // TMEM lane quarter this warp may read
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     for (int si = seg_begin; si < seg_end; ++si) {
       const WhSeg sg = p.segs[si];
-      const WhGroup* G = p.groups + sg.group;
+      const WhGroup* G = &p.groups[sg.group];
       const int n32 = G->cols >> 5;
       const int co = sg.m_tile * 128 + q * 32 + lane;
       mbar_wait(tfull_bar, (uint32_t)(si - seg_begin) & 1);
@@ -544,11 +530,11 @@ PreparedOp* prepare_wgrad_halo(const b2seg_wgrad_desc* d, bool* hard_error) {
   for (size_t i = 0; i < xkeys.size(); ++i)
     if (encode_act_map(&kp.xmap[i], d->x[xkeys[i].pair], 64, xkeys[i].ww, xkeys[i].wh, kp.bn) != 0) { delete L; return nullptr; }
   for (size_t i = xkeys.size(); i < (size_t)kWhMaxXMaps; ++i) kp.xmap[i] = kp.xmap[0];
-  const size_t gbytes = (groups.size() * sizeof(WhGroup) + 255) / 256 * 256;
+  for (size_t i = 0; i < groups.size(); ++i) kp.groups[i] = groups[i];
+  const size_t gbytes = 0;
   const size_t sbytes = (segs.size() * sizeof(WhSeg) + 255) / 256 * 256;
   const size_t cbytes = cta_seg.size() * sizeof(int);
   std::vector<uint8_t> host(gbytes + sbytes + cbytes, 0);
-  memcpy(host.data(), groups.data(), groups.size() * sizeof(WhGroup));
   memcpy(host.data() + gbytes, segs.data(), segs.size() * sizeof(WhSeg));
   memcpy(host.data() + gbytes + sbytes, cta_seg.data(), cbytes);
   if (cudaMalloc(&L->d_tables, host.size()) != cudaSuccess ||
@@ -558,7 +544,6 @@ PreparedOp* prepare_wgrad_halo(const b2seg_wgrad_desc* d, bool* hard_error) {
     return nullptr;
   }
   uint8_t* base = reinterpret_cast<uint8_t*>(L->d_tables);
-  kp.groups = reinterpret_cast<const WhGroup*>(base);
   kp.segs = reinterpret_cast<const WhSeg*>(base + gbytes);
   kp.cta_seg = reinterpret_cast<const int*>(base + gbytes + sbytes);
   L->kp = kp;
