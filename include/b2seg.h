@@ -276,6 +276,9 @@ int b2seg_plan_create(b2seg_plan** out);
 /* phase: 0 forward, 1 backward, 2 optimizer. desc is copied. */
 int b2seg_plan_add(b2seg_plan* p, int phase, int op, const void* desc, size_t desc_bytes);
 int b2seg_plan_run(b2seg_plan* p, int phase, void* stream);
+/* replay ops [first_op, first_op + n_ops) of a phase: lets the host interleave the data-parallel gradient exchange
+ * (NCCL all-reduce of a finished slice of the gradient arena) with the rest of the backward pass */
+int b2seg_plan_run_range(b2seg_plan* p, int phase, int first_op, int n_ops, void* stream);
 int b2seg_plan_num_launches(const b2seg_plan* p, int phase);
 int b2seg_plan_num_ops(const b2seg_plan* p, int phase);
 /* replay one phase with a CUDA event after every op; ms_per_op[i] = device time of op i (profiling aid for bench.py) */

@@ -446,6 +446,9 @@ EMU = {L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_fina
        L.OP_LSTM_FWD: emu_lstm_fwd, L.OP_LSTM_BWD: emu_lstm_bwd, L.OP_POOL_BWD: emu_pool_bwd}
 
 
-def run_phase(mem, planner, phase):
-    for (op, desc, _note) in planner.ops[phase]:
+def run_phase(mem, planner, phase, first_op=0, n_ops=None):
+    """replay ops [first_op, first_op + n_ops) of a phase (default: the whole phase), like b2seg_plan_run_range"""
+    ops = planner.ops[phase]
+    end = len(ops) if n_ops is None else first_op + n_ops
+    for (op, desc, _note) in ops[first_op:end]:
         EMU[op](mem, desc)

@@ -1,6 +1,8 @@
 """world_size-2 gloo test of the data-parallel path on the CPU: each rank runs forward + backward of the SAME
-planner program on its own batch shard through the float64 descriptor emulator, the flat gradient arena is sum-all-reduced
-(b2seg.dist.allreduce_flat_, bucketed) and Adam applies grad_scale = 1/world.  Both ranks must end with identical weights,
+planner program on its own batch shard through the float64 descriptor emulator; the gradient exchange is interleaved with
+the backward ops exactly as Model._step does it on the GPU (Planner.exchange_schedule: a slice of the flat gradient arena
+is sum-all-reduced as soon as the ops that finish it have run, while later ops are still to come) and Adam applies
+grad_scale = 1/world.  Both ranks must end with identical weights,
 equal to a single-process run that averages the two per-replica gradients by hand."""
 import os
 import socket
@@ -70,8 +72,24 @@ def _worker(rank, world, port, out):
     x, y = _data()
     b, e = shard_range(x.shape[0], rank, world)
     g, mem, pl = _build(e - b)
-    grads = _fwd_bwd(mem, pl, x[b:e], y[b:e])
-    wait_all(allreduce_flat_(grads, bucket_elems=1000))
+    xs, ys = x[b:e], y[b:e]
+    mem.f32(pl.input_ptr, xs.numel())[:] = xs.reshape(-1).double()
+    mem.f32(pl.outputs[0]["target_ptr"], ys.numel())[:] = ys.reshape(-1).double()
+    run_phase(mem, pl, 0)
+    grads = mem.f32(pl.g_ptr, max(pl.n_train, 64))
+    sched = pl.exchange_schedule(bucket_bytes=4096)
+    assert len(sched) >= 3 and sched[0][0] < len(pl.ops[1])          # the exchange really starts before backward ends
+    covered = sorted((lo, hi) for (_, lo, hi) in sched)
+    assert covered[0][0] == 0 and covered[-1][1] == max(pl.n_train, 64) and all(a[1] == b_[0] for a, b_ in zip(covered, covered[1:]))
+    done = 0
+    for (n_ops, lo, hi) in sched:
+        run_phase(mem, pl, 1, done, n_ops - done)
+        done = n_ops
+        before = grads[lo:hi].clone()
+        wait_all(allreduce_flat_(grads[lo:hi]))
+        if world > 1 and rank == 0 and float(before.abs().max()) > 0:
+            assert not torch.equal(before, grads[lo:hi])
+    run_phase(mem, pl, 1, done, len(pl.ops[1]) - done)
     for (op, desc, _n) in pl.ops[2]:
         desc.grad_scale = 1.0 / world
     run_phase(mem, pl, 2)

@@ -119,6 +119,9 @@ class Engine:
     def run(self, phase):
         L.check(self.lib.b2seg_plan_run(self.plan, phase, C.c_void_p(self._stream())), f"plan_run[{phase}]")
 
+    def run_range(self, phase, first_op, n_ops):
+        L.check(self.lib.b2seg_plan_run_range(self.plan, phase, first_op, n_ops, C.c_void_p(self._stream())), f"plan_run_range[{phase}]")
+
     def forward(self):
         self.run(0)
 

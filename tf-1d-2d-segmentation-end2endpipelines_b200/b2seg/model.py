@@ -73,6 +73,7 @@ class Model:
         self.stop_training = False
         self.world_size = 1
         self._dist = None
+        self.exchange_bucket_bytes = 64 << 20   # gradient-exchange bucket (data parallel): overlap granularity vs launch count
 
     # ---- introspection -----------------------------------------------------------------------------------
     @property
@@ -243,14 +244,33 @@ class Model:
             o["target"].copy_(torch.from_numpy(t), non_blocking=True)
         return self._step(eng, return_loss)
 
+    def _exchange_schedule(self, eng):
+        sched = getattr(eng, "_exchange", None)
+        if sched is None:
+            sched = eng._exchange = eng.planner.exchange_schedule(self.exchange_bucket_bytes)
+        return sched
+
     def _step(self, eng, return_loss=True):
         eng.forward()
-        eng.backward()
         scale = 1.0
         if self.world_size > 1:
-            from .dist import allreduce_flat_, wait_all
-            wait_all(allreduce_flat_(eng.g, group=self._pg, bucket_elems=32 << 20))
+            # backward with the gradient exchange overlapped: as soon as the ops that finish a slice of the gradient
+            # arena are enqueued, its all-reduce starts on the collective's stream while the remaining backward ops run
+            import torch.distributed as dist
+            from .dist import wait_all
+            works, done = [], 0
+            for (n_ops, lo, hi) in self._exchange_schedule(eng):
+                if n_ops > done:
+                    eng.run_range(1, done, n_ops - done)
+                    done = n_ops
+                works.append(dist.all_reduce(eng.g[lo:hi], group=self._pg, async_op=True))
+            n_total = eng.planner.num_launch_ops(1)
+            if n_total > done:
+                eng.run_range(1, done, n_total - done)
+            wait_all(works)
             scale = 1.0 / self.world_size
+        else:
+            eng.backward()
         eng.optimizer_step(self.optimizer.learning_rate, scale)
         if return_loss:
             return float(eng.loss_buf.item())

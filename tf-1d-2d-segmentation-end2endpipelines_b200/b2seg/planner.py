@@ -177,6 +177,8 @@ class Planner:
         self.catbuf: Dict[int, Phys] = {}
         self.act_bytes = 0
         self.op_info: Dict[Tuple[int, int], dict] = {}
+        self._grad_touched = set()
+        self.grad_ready: Dict[str, int] = {}   # param key -> number of backward ops after which its gradient is final
         self._analyse()
         self._layout_params()
 
@@ -448,6 +450,7 @@ class Planner:
         return self.w_ptr + 4 * self.pindex[key].offset
 
     def pg(self, key):
+        self._grad_touched.add(key)   # the backward emitter of the current unit writes this gradient
         return self.g_ptr + 4 * self.pindex[key].offset
 
     def pwb(self, key):  # bf16 shadow address
@@ -466,7 +469,10 @@ class Planner:
             self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.g_ptr, max(self.n_train, 64) * 4), "zero grads")
             self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.loss_ptr, 256), "zero loss")
             for u in reversed(self.units):
+                self._grad_touched = set()
                 getattr(self, "_bwd_" + u["kind"])(u)
+                for key in self._grad_touched:
+                    self.grad_ready[key] = len(self.ops[1])
             a = self.adam
             self.emit(2, L.OP_ADAM, L.AdamDesc(self.w_ptr, self.g_ptr, self.m_ptr, self.v_ptr, self.wb_ptr, max(self.n_train, 64),
                                                a["lr"], a["beta1"], a["beta2"], a["eps"], 1.0, 1), "adam")
@@ -783,6 +789,7 @@ class Planner:
         x = self.phys[id(n.inputs[0])]
         H, W, _ = n.inputs[0].shape
         d2 = L.HeadDesc.from_buffer_copy(d)
+        d2.dw, d2.db = self.pg(f"{n.name}/kernel"), self.pg(f"{n.name}/bias")   # (also marks them written by this unit)
         if n.inputs[0].op != "input":
             dx = self.new_act(H, W, x.Cp, "grad")
             d2.dx = dx.to_c()
@@ -1178,6 +1185,32 @@ class Planner:
         if e.kind == "blob":
             return flat[:int(np.prod(e.keras_shape))].copy().reshape(e.keras_shape)
         raise PlanError(e.kind)
+
+    def exchange_schedule(self, bucket_bytes: int = 64 << 20) -> List[Tuple[int, int, int]]:
+        """Data-parallel gradient exchange overlapped with backward: [(n_ops, lo, hi)] in execution
+        order — once the first n_ops backward ops are enqueued, the gradient arena elements [lo, hi) are final and
+        their all-reduce may start.  Backward walks the layers in reverse, and the arena is laid out in layer order,
+        so finished gradients form a suffix of the arena that grows towards offset 0; a bucket closes when it holds
+        bucket_bytes.  Gradients no backward op writes (conv biases feeding a BatchNormalization: analytically zero) are
+        final once the two memsets that open the backward phase have run."""
+        n_total = len(self.ops[1])
+        untouched = min(2, n_total)
+        entries = sorted((e for e in self.params if e.trainable), key=lambda e: -e.offset)
+        out, hi, ready, size = [], max(self.n_train, 64), 0, 0
+        for e in entries:
+            ready = max(ready, self.grad_ready.get(e.key, untouched))
+            size += e.size * 4
+            if size >= bucket_bytes:
+                out.append((ready, e.offset, hi))
+                hi, size = e.offset, 0
+        if hi > 0:
+            out.append((max(ready, 1) if entries else n_total, 0, hi))
+        # a later bucket can never start before an earlier one (single stream of backward ops)
+        fixed, floor = [], 0
+        for (r, lo, h) in out:
+            floor = max(floor, r)
+            fixed.append((floor, lo, h))
+        return fixed
 
     def num_launch_ops(self, phase):
         return len(self.ops[phase])

@@ -250,6 +250,18 @@ int b2seg_plan_run(b2seg_plan* p, int phase, void* stream) {
   return 0;
 }
 
+int b2seg_plan_run_range(b2seg_plan* p, int phase, int first_op, int n_ops, void* stream) {
+  if (!p || phase < 0 || phase > 2) return b2::fail(B2SEG_ERR_ARG, "plan_run_range: bad arguments");
+  const int n = (int)p->phase[phase].size();
+  if (first_op < 0 || n_ops < 0 || first_op + n_ops > n) return b2::fail(B2SEG_ERR_ARG, "plan_run_range: ops [%d, %d) outside [0, %d)", first_op, first_op + n_ops, n);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = first_op; i < first_op + n_ops; ++i) {
+    int rc = p->phase[phase][i]->launch(s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int b2seg_plan_run_timed(b2seg_plan* p, int phase, void* stream, float* ms_per_op, int n_ops) {
   if (!p || phase < 0 || phase > 2 || !ms_per_op) return b2::fail(B2SEG_ERR_ARG, "plan_run_timed: bad arguments");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
