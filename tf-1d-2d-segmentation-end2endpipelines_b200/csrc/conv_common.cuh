@@ -39,7 +39,24 @@ struct ConvEpiParams {
   int mul_mode, mul_c;
   int lbw, lbwh;       // log2(bw), log2(bw*bh): tile rows -> pixel coordinates by shifts
   int stats_per_cta;   // 1: one statistics row per CTA (n_tiles == 1), else one per (group, m_tile)
+  FastDiv fd_n_tiles, fd_m_tiles, fd_tiles_w, fd_tiles_h;   // tile index -> coordinates without integer division
 };
+
+// tile -> (group, n_tile, m_tile, w0, h0, n0); the epilogue used to spend ~20 % of its instructions on these divisions
+struct TileCoord { int g, n_tile, m_tile, w0, h0, n0; };
+__device__ __forceinline__ TileCoord tile_coord(const ConvEpiParams& p, int tile) {
+  TileCoord c;
+  const uint32_t rest = fast_div((uint32_t)tile, p.fd_n_tiles);
+  c.n_tile = tile - (int)rest * p.n_tiles;
+  c.g = (int)fast_div(rest, p.fd_m_tiles);
+  c.m_tile = (int)rest - c.g * p.m_tiles;
+  const uint32_t q = fast_div((uint32_t)c.m_tile, p.fd_tiles_w);
+  c.w0 = (c.m_tile - (int)q * p.tiles_w) * p.bw;
+  const uint32_t q2 = fast_div(q, p.fd_tiles_h);
+  c.h0 = ((int)q - (int)q2 * p.tiles_h) * p.bh;
+  c.n0 = (int)q2 * p.bn;
+  return c;
+}
 
 template <int ACT>
 __device__ __forceinline__ float act_t(float x) {
@@ -50,11 +67,11 @@ __device__ __forceinline__ float act_t(float x) {
 }
 
 template <int ACT>
-__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[32], const float* sb, uint32_t (&packed)[16]) {
-  const float4* b4 = reinterpret_cast<const float4*>(sb);
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[32], uint32_t sb_addr, uint32_t (&packed)[16]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 b = b4[j];  // same address in every lane: shared-memory broadcast
+    const uint4 braw = lds128(sb_addr + 16 * j);  // same address in every lane: shared-memory broadcast
+    const float4 b = make_float4(__uint_as_float(braw.x), __uint_as_float(braw.y), __uint_as_float(braw.z), __uint_as_float(braw.w));
     const float x0 = act_t<ACT>(__uint_as_float(v[4 * j + 0]) + b.x);
     const float x1 = act_t<ACT>(__uint_as_float(v[4 * j + 1]) + b.y);
     const float x2 = act_t<ACT>(__uint_as_float(v[4 * j + 2]) + b.z);
@@ -88,6 +105,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   const long long osn = p.out_sn, osh = p.out_sh, osw = p.out_sw;
   const long long msn = p.mul_sn, msh = p.mul_sh, msw = p.mul_sw;
   const float* bias = p.bias;
+  const uint32_t stg_addr = smem_u32(staging);
   const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row (of 4, stride 32) of the store pass
   // tile-invariant decomposition of this thread's rows
   const int mdn = row >> lbwh, mdh = (row >> lbw) & (bh - 1), mdw = row & (bw - 1);
@@ -108,13 +126,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   }
   uint32_t acc = 0, acc_phase = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int n_tile = tile % n_tiles;
-    const int rest = tile / n_tiles;
-    const int m_tile = rest % m_tiles;
-    const int g = rest / m_tiles;
-    const int w0 = (m_tile % tiles_w) * bw;
-    const int h0 = ((m_tile / tiles_w) % tiles_h) * bh;
-    const int n0 = (m_tile / (tiles_w * tiles_h)) * bn;
+    const TileCoord tc = tile_coord(p, tile);
+    const int n_tile = tc.n_tile, m_tile = tc.m_tile, g = tc.g, w0 = tc.w0, h0 = tc.h0, n0 = tc.n0;
     const bool tile_full = (n0 + bn <= gN) && (h0 + bh <= gH) && (w0 + bw <= gW);
     const bool my_valid = tile_full || ((n0 + mdn) < gN && (h0 + mdh) < gH && (w0 + mdw) < gW);
     const long long tile_off = n0 * osn + h0 * osh + w0 * osw;
@@ -154,7 +167,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
         tmem_ld32(tmem_base + lane_base + acc * BLOCK_N + c * 64 + half * 32, v);
         tmem_ld_wait();
         uint32_t packed[16];
-        const float* sb = sbias + c * 64 + half * 32;
+        const uint32_t sb = smem_u32(sbias + c * 64 + half * 32);
         if (act == B2SEG_ACT_NONE) bias_act_pack<B2SEG_ACT_NONE>(v, sb, packed);
         else if (act == B2SEG_ACT_RELU) bias_act_pack<B2SEG_ACT_RELU>(v, sb, packed);
         else if (act == B2SEG_ACT_LEAKY) bias_act_pack<B2SEG_ACT_LEAKY>(v, sb, packed);
@@ -163,9 +176,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
 #pragma unroll
           for (int j = 0; j < 16; ++j) packed[j] = 0u;
         }
-        uint4* dst = reinterpret_cast<uint4*>(staging + row * kStgPitch + half * 64);
+        const uint32_t dst = stg_addr + row * kStgPitch + half * 64;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) sts128(dst + 16 * q, make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]));
       }
       if (c == kChunks - 1) {
         // accumulator fully read: hand the TMEM buffer back to the MMA warp
@@ -181,7 +194,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = r0 + 32 * i;
-        uint4 val = *reinterpret_cast<const uint4*>(staging + r * kStgPitch + vq * 16);
+        uint4 val = lds128(stg_addr + r * kStgPitch + vq * 16);
         if (has_stats) {
           const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll

@@ -77,13 +77,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % e.n_tiles;
-        const int rest = tile / e.n_tiles;
-        const int m_tile = rest % e.m_tiles;
-        const int g = rest / e.m_tiles;
-        const int w0 = (m_tile % e.tiles_w) * e.bw;
-        const int h0 = ((m_tile / e.tiles_w) % e.tiles_h) * e.bh;
-        const int n0 = (m_tile / (e.tiles_w * e.tiles_h)) * e.bn;
+        const TileCoord tc = tile_coord(e, tile);
+        const int n_tile = tc.n_tile, g = tc.g, w0 = tc.w0, h0 = tc.h0, n0 = tc.n0;
         for (int t = 0; t < p.taps_per_group; ++t) {
           const int4 tap = p.taps[g * p.taps_per_group + t];
           for (int cb = 0; cb < p.kc_blocks; ++cb) {
@@ -189,6 +184,10 @@ int fill_epi_params(const b2seg_conv_desc* d, int block_n, int bw, int bh, int b
   e->n_tiles = (o.C + block_n - 1) / block_n;
   e->n_groups = d->n_groups;
   e->total_tiles = e->n_groups * e->m_tiles * e->n_tiles;
+  e->fd_n_tiles = make_fastdiv((uint32_t)e->n_tiles);
+  e->fd_m_tiles = make_fastdiv((uint32_t)e->m_tiles);
+  e->fd_tiles_w = make_fastdiv((uint32_t)e->tiles_w);
+  e->fd_tiles_h = make_fastdiv((uint32_t)e->tiles_h);
   for (int g = 0; g < d->n_groups; ++g) {
     const b2seg_view& og = d->out[g];
     if (og.N != o.N || og.H != o.H || og.W != o.W || og.C != o.C || og.sn != o.sn || og.sh != o.sh || og.sw != o.sw)

@@ -106,13 +106,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       }
       uint32_t sa = 0, pa = 0, sb_i = 0, pb = 0;
       for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % e.n_tiles;
-        const int rest = tile / e.n_tiles;
-        const int m_tile = rest % e.m_tiles;
-        const int g = rest / e.m_tiles;
-        const int w0 = (m_tile % e.tiles_w) * e.bw;
-        const int h0 = ((m_tile / e.tiles_w) % e.tiles_h) * e.bh;
-        const int n0 = (m_tile / (e.tiles_w * e.tiles_h)) * e.bn;
+        const TileCoord tc = tile_coord(e, tile);
+        const int n_tile = tc.n_tile, g = tc.g, w0 = tc.w0, h0 = tc.h0, n0 = tc.n0;
         {
           // pull the halo tiles this CTA needs two tiles from now into L2 (each activation byte is read from HBM once,
           // so without this every A stage pays full HBM latency with only two stages in flight)
@@ -172,7 +167,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         tc_fence_after();
       }
       for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
-        const int g = (tile / e.n_tiles) / e.m_tiles;
+        const int g = (int)fast_div(fast_div((uint32_t)tile, e.fd_n_tiles), e.fd_m_tiles);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
