@@ -59,7 +59,8 @@ typedef struct b2seg_tap {
  * b_mn_major = 1: GEMM-N = w_cin, K = w_cout per tap (the same buffer read transposed).
  * Reads outside a source view return 0 (SAME padding).  stats (optional): fp32
  * [n_groups * m_tiles][2][out.C] per-tile column sums and sums of squares of the stored bf16 values —
- * the batch statistics of BatchNormalization (unet_variants.py:11). */
+ * the batch statistics of BatchNormalization (unet_variants.py:11).  With mul_view the statistics are taken after the
+ * derivative mask (column sums = bias gradient of the layer whose activation derivative was applied, see b2seg_rowsum). */
 typedef struct b2seg_conv_desc {
   int32_t n_src;
   b2seg_view src[B2SEG_MAX_SRC];
@@ -131,8 +132,10 @@ typedef struct b2seg_gradsrc {
   int32_t pool_h, pool_w;
 } b2seg_gradsrc;
 
-/* Backward of act(BN(x)): pass 0 reduces sum(dy*m) and sum(dy*m*xhat) into partials, pass 1 writes
- *   dx = scale * (dy*m - dbeta/count - xhat*dgamma/count). With scale == 0 (no BN) dx = dy*m. */
+/* Backward of act(BN(x)): pass 0 reduces dbeta = sum(dy*m) and dgamma = sum(dy*m*xhat), pass 1 writes
+ *   dx = scale * (dy*m - dbeta/count - xhat*dgamma/count). With scale == 0 (no BN) dx = dy*m.
+ * accumulate = 1: the caller guarantees dgamma / dbeta hold zeros when the op starts (a training plan zeroes the whole
+ * gradient arena once per step), which lets pass 0 add its block sums straight into them; 0: the op zeroes them itself. */
 typedef struct b2seg_bn_bwd_desc {
   b2seg_view x;                   /* stored pre-BN conv output */
   uint64_t scale, shift, mean, rstd; /* fp32 [C] (0 => no BN) */
@@ -142,8 +145,9 @@ typedef struct b2seg_bn_bwd_desc {
   double count;
   uint64_t partials;              /* fp32 [n_blocks][2][C] scratch */
   int32_t n_blocks;               /* pixel slabs used by pass 0 */
-  uint64_t dgamma, dbeta;         /* fp32 [C] outputs of the finalize step */
+  uint64_t dgamma, dbeta;         /* fp32 [C] outputs */
   b2seg_view dx;                  /* bf16 output */
+  int32_t accumulate;
 } b2seg_bn_bwd_desc;
 
 /* Fused Adam (utils/tf_optimizers.py:11; Keras-2 update rule): flat fp32 master weights, fp32 grads,
@@ -234,6 +238,15 @@ typedef struct b2seg_colsum_desc { /* bias gradient: db[c] = sum over pixels of 
   b2seg_view g; uint64_t out; uint64_t scratch; int32_t n_blocks;
 } b2seg_colsum_desc;
 
+/* out[c] (+)= sum over rows of an fp32 row list partials[r * pitch + c], c < C.  Turns the per-CTA column sums a convolution
+ * wrote into `stats` into a bias gradient: the input gradient of the decoder convolution, masked by LeakyReLU' in its epilogue
+ * (mul_view), IS dL/d(pre-activation) of the Conv2DTranspose that feeds it (unet_variants.py:17-24), so its column sums are that
+ * layer's bias gradient and no separate pass over the tensor is needed. */
+typedef struct b2seg_rowsum_desc {
+  uint64_t partials; int32_t n_rows, pitch, C;
+  uint64_t out; int32_t accumulate;
+} b2seg_rowsum_desc;
+
 const char* b2seg_last_error(void);
 int b2seg_version(void);
 int b2seg_device_check(int device);
@@ -263,13 +276,14 @@ int b2seg_colstats(const b2seg_colstats_desc* d, void* stream);
 int b2seg_lstm_fwd(const b2seg_lstm_desc* d, void* stream);
 int b2seg_lstm_bwd(const b2seg_lstm_desc* d, void* stream);
 int b2seg_pool_bwd(const b2seg_poolbwd_desc* d, void* stream);
+int b2seg_rowsum(const b2seg_rowsum_desc* d, void* stream);
 
 /* ---- plan: a recorded sequence of the ops above, replayed per step (optionally as a CUDA graph) ---- */
 typedef struct b2seg_plan b2seg_plan;
 enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
        B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,
        B2SEG_OP_MEMSET, B2SEG_OP_RESIZE_FWD, B2SEG_OP_RESIZE_BWD, B2SEG_OP_MULBC_FWD, B2SEG_OP_MULBC_BWD, B2SEG_OP_COLSTATS,
-       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD };
+       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM };
 typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
 
 int b2seg_plan_create(b2seg_plan** out);

@@ -394,6 +394,13 @@ def emu_colstats(mem, d):
     part[0, 0], part[0, 1] = x.sum(0), (x * x).sum(0)
 
 
+def emu_rowsum(mem, d):
+    part = mem.f32(d.partials, d.n_rows * d.pitch).view(d.n_rows, d.pitch)
+    out = mem.f32(d.out, d.C)
+    tot = part[:, :d.C].sum(0)
+    out[:] = out + tot if d.accumulate else tot
+
+
 def _hs(t):
     return torch.clamp(0.2 * t + 0.5, 0.0, 1.0)
 
@@ -443,7 +450,8 @@ EMU = {L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_fina
        L.OP_LOSS: emu_loss, L.OP_ELTWISE: emu_eltwise, L.OP_CAST: emu_cast, L.OP_COLSUM: emu_colsum,
        L.OP_MEMSET: emu_memset, L.OP_RESIZE_FWD: emu_resize_fwd, L.OP_RESIZE_BWD: emu_resize_bwd,
        L.OP_MULBC_FWD: emu_mulbc_fwd, L.OP_MULBC_BWD: emu_mulbc_bwd, L.OP_COLSTATS: emu_colstats,
-       L.OP_LSTM_FWD: emu_lstm_fwd, L.OP_LSTM_BWD: emu_lstm_bwd, L.OP_POOL_BWD: emu_pool_bwd}
+       L.OP_LSTM_FWD: emu_lstm_fwd, L.OP_LSTM_BWD: emu_lstm_bwd, L.OP_POOL_BWD: emu_pool_bwd,
+       L.OP_ROWSUM: emu_rowsum}
 
 
 def run_phase(mem, planner, phase, first_op=0, n_ops=None):

@@ -150,6 +150,25 @@ def test_conv_dgrad_mask_fusion():
     ref = x.grad.permute(0, 2, 3, 1).clone()
     ref[..., :64] *= torch.where(yfwd[..., :64].float() > 0, 1.0, 0.3)
     assert rel_l2(dx.float(), ref) < 6e-3
+    # statistics after the mask + row sum = bias gradient of the layer whose derivative was fused (two image sizes: the
+    # 16x16 map takes the per-tile-box kernel, 32x64 the halo kernel)
+    for (N2, H2, W2) in ((2, 16, 16), (3, 32, 64)):
+        dy = bf(torch.randn(N2, H2, W2, Cout, device=dev))
+        yfwd = bf(torch.randn(N2, H2, W2, Cin, device=dev))
+        dx = torch.zeros(N2, H2, W2, Cin, device=dev, dtype=torch.bfloat16)
+        d = lw.conv_dgrad(tv(dy), w.data_ptr(), Cout, 3, 3, Cin, tv(dx), mul_view=tv(yfwd, 0, 64), mul_mode=L.ACT_LEAKY)
+        rows = L.load().b2seg_conv_num_stat_rows(C.byref(d))
+        stats = torch.zeros(rows, 2, Cin, device=dev)
+        d.stats = stats.data_ptr()
+        L.call("b2seg_conv", d, stream())
+        db = torch.full((64,), 7.0, device=dev)
+        L.call("b2seg_rowsum", L.RowsumDesc(stats.data_ptr(), rows, 2 * Cin, 64, db.data_ptr(), 0), stream())
+        db2 = torch.ones(64, device=dev)
+        L.call("b2seg_rowsum", L.RowsumDesc(stats.data_ptr(), rows, 2 * Cin, 64, db2.data_ptr(), 1), stream())
+        torch.cuda.synchronize()
+        want = dx[..., :64].float().sum((0, 1, 2))
+        assert torch.allclose(db, want, rtol=1e-4, atol=1e-3), float((db - want).abs().max())
+        assert torch.allclose(db2, want + 1.0, rtol=1e-4, atol=1e-3)
 
 
 WGRAD_CASES = [(2, 16, 16, 64, 64, 3, 3, 0), (2, 16, 16, 64, 64, 3, 3, 1), (4, 8, 8, 128, 256, 3, 3, 0), (2, 8, 8, 320, 136, 3, 3, 0),
@@ -258,6 +277,12 @@ def test_bn_finalize_act_pool_and_backward():
     L.call("b2seg_bn_bwd", bd, stream())
     torch.cuda.synchronize()
     assert rel_l2(dz.float(), zt.grad) < 8e-3
+    # accumulate = 1 (plan mode): the caller zeroes dgamma / dbeta, the op adds into them; same results
+    dgamma_a, dbeta_a, dz_a = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev), torch.zeros_like(z)
+    bd.dgamma, bd.dbeta, bd.dx, bd.accumulate = dgamma_a.data_ptr(), dbeta_a.data_ptr(), tv(dz_a).to_c(), 1
+    L.call("b2seg_bn_bwd", bd, stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dgamma_a, dgamma) < 1e-5 and rel_l2(dbeta_a, dbeta) < 1e-5 and rel_l2(dz_a.float(), dz.float()) < 1e-3
     # dgamma/dbeta against autograd through gamma/beta
     g_ = gamma.clone().requires_grad_(True)
     b_ = beta.clone().requires_grad_(True)

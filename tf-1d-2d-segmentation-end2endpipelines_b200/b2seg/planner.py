@@ -136,6 +136,7 @@ class GSrc:
     kind: int = 0      # 0 direct, 1 pooled
     pool: Tuple[int, int] = (1, 1)
     premasked: bool = False
+    colsums: Optional[Tuple[int, int, int]] = None   # (fp32 rows ptr, n_rows, pitch): per-CTA column sums written by the producer
 
 
 class PlanError(NotImplementedError):
@@ -920,6 +921,7 @@ class Planner:
         d.partials, d.n_blocks = self.alloc(nb * 2 * cp * 4, "scratch"), nb
         d.dgamma, d.dbeta = self.pg(f"{n.name}/gamma"), self.pg(f"{n.name}/beta")
         d.dx = dx.to_c()
+        d.accumulate = 1   # "zero grads" opens the backward phase
         self.emit(1, L.OP_BN_BWD, d, f"bn bwd {n.name}")
         self._add_gsrc(n.inputs[0], GSrc(dx))
 
@@ -969,7 +971,7 @@ class Planner:
             for s in srcs:
                 if s.kind != 0:
                     raise PlanError("pooled gradient of a concat")
-                self._add_gsrc(p, GSrc(s.view.chan(off, cp), 0, (1, 1), s.premasked and off == 0))
+                self._add_gsrc(p, GSrc(s.view.chan(off, cp), 0, (1, 1), s.premasked and off == 0, s.colsums if off == 0 else None))
             off += cp
 
     def _reduce_sources(self, srcs: List[GSrc], shape_like: TView) -> List[GSrc]:
@@ -1004,6 +1006,7 @@ class Planner:
         act = self._act_code(u["act"])
         y: TView = u["y"]
         srcs = self._kernel_sources(out_node, srcs)
+        bias_rows = None
         # ---- dZ: gradient w.r.t. the raw convolution output
         if u["bn"] is not None:
             bn = u["bn"]
@@ -1018,11 +1021,13 @@ class Planner:
             d.partials, d.n_blocks = self.alloc(nb * 2 * cop * 4, "scratch"), nb
             d.dgamma, d.dbeta = self.pg(f"{bn.name}/gamma"), self.pg(f"{bn.name}/beta")
             d.dx = dz.to_c()
+            d.accumulate = 1   # "zero grads" opens the backward phase
             self.emit(1, L.OP_BN_BWD, d, f"bn bwd {bn.name}")
             has_bias_grad = False
         else:
             if len(srcs) == 1 and srcs[0].kind == 0 and (act == L.ACT_NONE or srcs[0].premasked):
                 dz = srcs[0].view
+                bias_rows = srcs[0].colsums if srcs[0].premasked else None
             else:
                 dz = self.new_act(H, W, cop, "grad")
                 d = L.BnBwdDesc()
@@ -1043,7 +1048,9 @@ class Planner:
             self.emit(1, L.OP_WGRAD, lw.tconv_wgrad(dz, x.view, self.pg(pe.key), cop, kh, kw, cin_p), f"wgrad {n.name}", flops=self._conv_flops(n))
         else:
             self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, xin, self.pg(pe.key), cop, kh, kw, cin_p), f"wgrad {n.name}", flops=self._conv_flops(n))
-        if has_bias_grad:
+        if has_bias_grad and bias_rows is not None:
+            self.emit(1, L.OP_ROWSUM, L.RowsumDesc(bias_rows[0], bias_rows[1], bias_rows[2], cop, self.pg(f"{n.name}/bias"), 0), f"bias grad {n.name}")
+        elif has_bias_grad:
             self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")
         # ---- input gradient
         src_node = n.inputs[0]
@@ -1066,11 +1073,19 @@ class Planner:
                     and len(self.cons[id(first)]) == 1 and len(self.cons[id(src_node)]) == 1
                     and self._act_code(pu["act"]) in (L.ACT_RELU, L.ACT_LEAKY)):
                 mul_view, mul_mode, premasked = x.view.chan(0, self._cphys(first)), self._act_code(pu["act"]), True
+        colsums = None
         if n.op == "tconv":
             self.emit(1, L.OP_CONV, lw.tconv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx), f"dgrad {n.name}", flops=self._conv_flops(n))
         else:
-            self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx, mul_view, mul_mode), f"dgrad {n.name}", flops=self._conv_flops(n))
-        self._add_gsrc(src_node, GSrc(dx, 0, (1, 1), premasked))
+            dd = lw.conv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx, mul_view, mul_mode)
+            if premasked:
+                # the masked channels of dx are dL/d(pre-activation) of the transposed conv: its bias gradient is their
+                # column sum, which the epilogue's statistics path produces for free (consumed by OP_ROWSUM)
+                rows = int(self.stat_rows_fn(dd))
+                dd.stats = self.alloc(rows * 2 * cin_p * 4, "scratch")
+                colsums = (dd.stats, rows, 2 * cin_p)
+            self.emit(1, L.OP_CONV, dd, f"dgrad {n.name}", flops=self._conv_flops(n))
+        self._add_gsrc(src_node, GSrc(dx, 0, (1, 1), premasked, colsums))
 
     # ---------------------------------------------------------------------------------------- weights <-> Keras
     def to_internal(self, key: str, arr: np.ndarray) -> np.ndarray:

@@ -131,6 +131,7 @@ static PreparedOp* prepare_any(int op, const void* desc, size_t bytes) {
     B2_CASE(B2SEG_OP_LSTM_FWD, b2seg_lstm_desc, prepare_lstm_fwd)
     B2_CASE(B2SEG_OP_LSTM_BWD, b2seg_lstm_desc, prepare_lstm_bwd)
     B2_CASE(B2SEG_OP_POOL_BWD, b2seg_poolbwd_desc, prepare_pool_bwd)
+    B2_CASE(B2SEG_OP_ROWSUM, b2seg_rowsum_desc, prepare_rowsum)
     default:
       set_error("unknown op code %d", op);
       return nullptr;
@@ -173,6 +174,7 @@ int b2seg_sizeof_desc(int op) {
     case B2SEG_OP_LSTM_FWD:
     case B2SEG_OP_LSTM_BWD: return (int)sizeof(b2seg_lstm_desc);
     case B2SEG_OP_POOL_BWD: return (int)sizeof(b2seg_poolbwd_desc);
+    case B2SEG_OP_ROWSUM: return (int)sizeof(b2seg_rowsum_desc);
     default: return -1;
   }
 }
@@ -211,6 +213,7 @@ B2_ENTRY(b2seg_colstats, b2seg_colstats_desc, b2::prepare_colstats)
 B2_ENTRY(b2seg_lstm_fwd, b2seg_lstm_desc, b2::prepare_lstm_fwd)
 B2_ENTRY(b2seg_lstm_bwd, b2seg_lstm_desc, b2::prepare_lstm_bwd)
 B2_ENTRY(b2seg_pool_bwd, b2seg_poolbwd_desc, b2::prepare_pool_bwd)
+B2_ENTRY(b2seg_rowsum, b2seg_rowsum_desc, b2::prepare_rowsum)
 
 int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
   if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");

@@ -43,6 +43,9 @@ PreparedOp* prepare_wgrad_halo(const b2seg_wgrad_desc* d, bool* hard_error);
 PreparedOp* prepare_bn_finalize(const b2seg_bn_finalize_desc* d);
 PreparedOp* prepare_bn_act(const b2seg_bn_act_desc* d);
 PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d);
+PreparedOp* prepare_bn_act_fast(const b2seg_bn_act_desc* d);   // nullptr (no error) when not eligible
+PreparedOp* prepare_bn_bwd_fast(const b2seg_bn_bwd_desc* d);
+PreparedOp* prepare_rowsum(const b2seg_rowsum_desc* d);
 PreparedOp* prepare_adam(const b2seg_adam_desc* d);
 PreparedOp* prepare_head_fwd(const b2seg_head_desc* d);
 PreparedOp* prepare_head_bwd(const b2seg_head_desc* d);

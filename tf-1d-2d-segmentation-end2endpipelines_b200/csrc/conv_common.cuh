@@ -39,8 +39,25 @@ struct ConvEpiParams {
   int mul_mode, mul_c;
   int lbw, lbwh;       // log2(bw), log2(bw*bh): tile rows -> pixel coordinates by shifts
   int stats_per_cta;   // 1: one statistics row per CTA (n_tiles == 1), else one per (group, m_tile)
+  int cta_groups;      // G > 1: CTA b only walks the tiles of group b % G (its weights stay resident in shared memory); gridDim.x % G == 0
   FastDiv fd_n_tiles, fd_m_tiles, fd_tiles_w, fd_tiles_h;   // tile index -> coordinates without integer division
 };
+
+// the tile indices a CTA walks: all of them round-robin, or (cta_groups) those of its own group only, with the CTAs
+// b, b+1, .. b+G-1 of a quad visiting the same m tiles in step so that the shared input tile is fetched from HBM once
+struct TileRange { int first, end, step; };
+__device__ __forceinline__ TileRange tile_range(const ConvEpiParams& p) {
+  TileRange r;
+  if (p.cta_groups > 1) {
+    const int G = p.cta_groups, per_group = p.m_tiles * p.n_tiles, g = (int)blockIdx.x % G;
+    r.first = g * per_group + (int)blockIdx.x / G;
+    r.end = (g + 1) * per_group;
+    r.step = (int)gridDim.x / G;
+  } else {
+    r.first = (int)blockIdx.x; r.end = p.total_tiles; r.step = (int)gridDim.x;
+  }
+  return r;
+}
 
 // tile -> (group, n_tile, m_tile, w0, h0, n0); the epilogue used to spend ~20 % of its instructions on these divisions
 struct TileCoord { int g, n_tile, m_tile, w0, h0, n0; };
@@ -99,7 +116,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   // kernel-invariant scalars (keep them in registers instead of re-reading the constant bank)
   const int bw = p.bw, bh = p.bh, bn = p.bn, lbw = p.lbw, lbwh = p.lbwh;
   const int gN = p.gN, gH = p.gH, gW = p.gW, n_extent = p.n_extent, act = p.act;
-  const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, tiles_w = p.tiles_w, tiles_h = p.tiles_h, total_tiles = p.total_tiles;
+  const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
   const bool has_stats = p.stats != nullptr, per_cta = p.stats_per_cta != 0;
   const int mul_mode = p.mul_mode, mul_c = p.mul_c;
   const long long osn = p.out_sn, osh = p.out_sh, osw = p.out_sw;
@@ -125,7 +142,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
     named_bar_sync(1, kEpiThreads);
   }
   uint32_t acc = 0, acc_phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  const TileRange tr = tile_range(p);
+  for (int tile = tr.first; tile < tr.end; tile += tr.step) {
     const TileCoord tc = tile_coord(p, tile);
     const int n_tile = tc.n_tile, m_tile = tc.m_tile, g = tc.g, w0 = tc.w0, h0 = tc.h0, n0 = tc.n0;
     const bool tile_full = (n0 + bn <= gN) && (h0 + bh <= gH) && (w0 + bw <= gW);
@@ -195,15 +213,6 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
       for (int i = 0; i < 4; ++i) {
         const int r = r0 + 32 * i;
         uint4 val = lds128(stg_addr + r * kStgPitch + vq * 16);
-        if (has_stats) {
-          const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = __uint_as_float(w4[e] << 16), hi = __uint_as_float(w4[e] & 0xffff0000u);
-            s[2 * e] += lo; q2[2 * e] = fmaf(lo, lo, q2[2 * e]);
-            s[2 * e + 1] += hi; q2[2 * e + 1] = fmaf(hi, hi, q2[2 * e + 1]);
-          }
-        }
         const bool ok = tile_full || ((n0 + (r >> lbwh)) < gN && (h0 + ((r >> lbw) & (bh - 1))) < gH && (w0 + (r & (bw - 1))) < gW);
         if (ok && col_ok) {
           if (do_mul) {
@@ -222,6 +231,15 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
             val = make_uint4(o4[0], o4[1], o4[2], o4[3]);
           }
           *reinterpret_cast<uint4*>(out_base + rel[i] + cc_st) = val;
+          if (has_stats) {   // statistics of exactly what was stored (rows outside the image hold zeros and add nothing)
+            const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(w4[e] << 16), hi = __uint_as_float(w4[e] & 0xffff0000u);
+              s[2 * e] += lo; q2[2 * e] = fmaf(lo, lo, q2[2 * e]);
+              s[2 * e + 1] += hi; q2[2 * e + 1] = fmaf(hi, hi, q2[2 * e + 1]);
+            }
+          }
         }
       }
       if (has_stats) {

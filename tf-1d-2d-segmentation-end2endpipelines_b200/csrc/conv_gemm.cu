@@ -71,12 +71,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int nkb = p.taps_per_group * p.kc_blocks;
+  const TileRange tr = tile_range(e);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
+      for (int tile = tr.first; tile < tr.end; tile += tr.step) {
         const TileCoord tc = tile_coord(e, tile);
         const int n_tile = tc.n_tile, g = tc.g, w0 = tc.w0, h0 = tc.h0, n0 = tc.n0;
         for (int t = 0; t < p.taps_per_group; ++t) {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint64_t bdesc0 = B_MN ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 16, 1024);
       const uint32_t smem16 = smem_u32(smem) >> 4;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < e.total_tiles; tile += gridDim.x) {
+      for (int tile = tr.first; tile < tr.end; tile += tr.step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;

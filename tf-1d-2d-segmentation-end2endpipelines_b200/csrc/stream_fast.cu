@@ -1,0 +1,464 @@
+// Instruction-lean fast paths of the two HBM-streaming kernels that dominate a training step: BN apply (+activation
+// +2x2 / 1x2 max-pool) and BN / activation / max-pool backward.
+//
+// ncu on the generic kernels (profiles/r1_prof_stream.txt): 73 % issue-slot utilisation at 56 % of HBM bandwidth and
+// ~180 thread instructions per 8-channel vector — they were bound by instruction issue, not by memory: per-element
+// runtime activation switches and channel-mask tests, 64-bit strided address arithmetic and div/mod index decoding for
+// every vector.  Here the work is walked row by row (one magic-number division per image row), offsets are 32-bit
+// element offsets, the activation / window / source configuration are template parameters, and bf16 <-> fp32 uses the
+// shift/mask form, which brings a vector down to ~40-60 instructions so the kernels run at memory speed.
+//
+// Eligibility is checked on the host (prepare_*_fast return nullptr when a view needs 64-bit offsets, the channel count
+// needs masking, the window is unusual, ...) and the generic kernels of stream_kernels.cu remain the fallback.
+#include <algorithm>
+
+#include "stream_common.cuh"
+
+namespace b2 {
+
+struct FV { unsigned long long ptr; unsigned sn, sh, sw; };   // strides in elements, all offsets < 2^31
+
+static bool fv_make(const b2seg_view& v, FV* o) {
+  if (v.ptr == 0 || (v.ptr & 15) || v.sn < 0 || v.sh < 0 || v.sw < 0 || (v.sn % 8) || (v.sh % 8) || (v.sw % 8)) return false;
+  const long long span = (long long)(v.N - 1) * v.sn + (long long)(v.H - 1) * v.sh + (long long)(v.W - 1) * v.sw + v.C;
+  if (span >= (1ll << 31)) return false;
+  o->ptr = v.ptr; o->sn = (unsigned)v.sn; o->sh = (unsigned)v.sh; o->sw = (unsigned)v.sw;
+  return true;
+}
+
+__device__ __forceinline__ uint4 ld16(const FV& v, unsigned off) {
+  return __ldg(reinterpret_cast<const uint4*>(v.ptr + (unsigned long long)off * 2ull));
+}
+__device__ __forceinline__ void st16(const FV& v, unsigned off, uint4 u) {
+  *reinterpret_cast<uint4*>(v.ptr + (unsigned long long)off * 2ull) = u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+template <int ACT>
+__device__ __forceinline__ float act_f(float x) {
+  if (ACT == B2SEG_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == B2SEG_ACT_LEAKY) return fmaxf(x, 0.3f * x);
+  if (ACT == B2SEG_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------------- BN apply
+struct BnActF {
+  FV x, out0, out1, pooled;
+  const float* scale; const float* shift;
+  int n_out, has_pool;
+  int C, Ho, Wo, rows;        // rows = N * Ho (window rows)
+  FastDiv fd_ho;
+  int cvb, rp;
+};
+
+// One thread owns 8 channels; a block covers cvb channel vectors x rp window columns; blocks walk window rows.
+template <int PH, int PW, int ACT, int U>
+__global__ void __launch_bounds__(256, PH * PW * U > 4 ? 2 : 4) bn_act_fast_kernel(const BnActF k) {
+  constexpr int WIN = PH * PW;
+  const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
+  const int v = blockIdx.x * k.cvb + tcv;
+  if (v * 8 >= k.C || trow >= k.rp) return;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = k.scale ? __ldg(k.scale + v * 8 + e) : 1.f;
+    sf[e] = k.shift ? __ldg(k.shift + v * 8 + e) : 0.f;
+  }
+  const unsigned step = (unsigned)k.rp;
+  for (int r = blockIdx.y; r < k.rows; r += gridDim.y) {
+    const unsigned n = fast_div((unsigned)r, k.fd_ho), ho = (unsigned)r - n * (unsigned)k.Ho;
+    const unsigned xrow = n * k.x.sn + ho * PH * k.x.sh + v * 8;
+    const unsigned o0row = n * k.out0.sn + ho * PH * k.out0.sh + v * 8;
+    const unsigned o1row = n * k.out1.sn + ho * PH * k.out1.sh + v * 8;
+    const unsigned prow = n * k.pooled.sn + ho * k.pooled.sh + v * 8;
+    for (unsigned wo0 = trow; wo0 < (unsigned)k.Wo; wo0 += step * U) {
+      uint4 raw[U][WIN];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned wo = wo0 + u * step;
+        if (wo < (unsigned)k.Wo) {
+#pragma unroll
+          for (int q = 0; q < WIN; ++q) raw[u][q] = ld16(k.x, xrow + (q / PW) * k.x.sh + (wo * PW + q % PW) * k.x.sw);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned wo = wo0 + u * step;
+        if (wo >= (unsigned)k.Wo) break;
+        float mx[8];
+#pragma unroll
+        for (int q = 0; q < WIN; ++q) {
+          float f[8];
+          unpack8(raw[u][q], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = act_f<ACT>(fmaf(f[e], sc[e], sf[e]));
+            mx[e] = q == 0 ? f[e] : fmaxf(mx[e], f[e]);
+          }
+          const uint4 o = pack8(f);
+          st16(k.out0, o0row + (q / PW) * k.out0.sh + (wo * PW + q % PW) * k.out0.sw, o);
+          if (k.n_out > 1) st16(k.out1, o1row + (q / PW) * k.out1.sh + (wo * PW + q % PW) * k.out1.sw, o);
+        }
+        if (WIN > 1 && k.has_pool) st16(k.pooled, prow + wo * k.pooled.sw, pack8(mx));
+      }
+    }
+  }
+}
+
+struct BnActFastLaunch : PreparedOp {
+  BnActF k;
+  int ph, pw, act;
+  dim3 grid;
+  template <int PH, int PW, int U>
+  void go(cudaStream_t s) {
+    switch (act) {
+      case B2SEG_ACT_RELU: bn_act_fast_kernel<PH, PW, B2SEG_ACT_RELU, U><<<grid, 256, 0, s>>>(k); break;
+      case B2SEG_ACT_LEAKY: bn_act_fast_kernel<PH, PW, B2SEG_ACT_LEAKY, U><<<grid, 256, 0, s>>>(k); break;
+      case B2SEG_ACT_SIGMOID: bn_act_fast_kernel<PH, PW, B2SEG_ACT_SIGMOID, U><<<grid, 256, 0, s>>>(k); break;
+      default: bn_act_fast_kernel<PH, PW, B2SEG_ACT_NONE, U><<<grid, 256, 0, s>>>(k); break;
+    }
+  }
+  int launch(cudaStream_t s) override {
+    if (ph == 2 && pw == 2) go<2, 2, 2>(s);
+    else if (ph == 1 && pw == 2) go<1, 2, 2>(s);
+    else go<1, 1, 4>(s);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+
+static void row_grid(int C, int rows, int Wo, int* cvb, int* rp, dim3* grid) {
+  const int cv = C / 8;
+  *cvb = cv < 256 ? cv : 256;
+  // threads along the window-column axis: no more than the row has columns (power of two so that cvb * rp <= 256)
+  int r = 256 / *cvb;
+  while (r > 1 && r / 2 >= Wo) r /= 2;
+  *rp = r;
+  const int gx = (cv + *cvb - 1) / *cvb;
+  long long gy = (long long)num_sms() * 16 / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  *grid = dim3(gx, (unsigned)gy);
+}
+
+PreparedOp* prepare_bn_act_fast(const b2seg_bn_act_desc* d) {
+  static const bool disabled = getenv("B2SEG_NO_FAST_STREAM") != nullptr;
+  if (disabled || d->c_valid != 0 || d->x.C % 8 || d->n_out < 1 || d->n_out > 2) return nullptr;
+  const int ph = d->pool_h > 1 ? d->pool_h : 1, pw = d->pool_w > 1 ? d->pool_w : 1;
+  if (!((ph == 1 && pw == 1) || (ph == 2 && pw == 2) || (ph == 1 && pw == 2))) return nullptr;
+  if (d->x.H % ph || d->x.W % pw) return nullptr;
+  if (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_RELU && d->act != B2SEG_ACT_LEAKY && d->act != B2SEG_ACT_SIGMOID) return nullptr;
+  auto* L = new BnActFastLaunch();
+  BnActF& k = L->k;
+  memset(&k, 0, sizeof(k));
+  bool ok = fv_make(d->x, &k.x) && fv_make(d->out[0], &k.out0);
+  k.out1 = k.out0;
+  if (ok && d->n_out > 1) ok = fv_make(d->out[1], &k.out1);
+  k.pooled = k.out0;
+  k.has_pool = (ph * pw > 1) ? 1 : 0;
+  if (ok && k.has_pool) ok = fv_make(d->pooled, &k.pooled);
+  if (!ok) { delete L; return nullptr; }
+  k.scale = reinterpret_cast<const float*>(d->scale);
+  k.shift = reinterpret_cast<const float*>(d->shift);
+  k.n_out = d->n_out;
+  k.C = d->x.C; k.Ho = d->x.H / ph; k.Wo = d->x.W / pw; k.rows = d->x.N * k.Ho;
+  k.fd_ho = make_fastdiv((uint32_t)k.Ho);
+  L->ph = ph; L->pw = pw; L->act = d->act;
+  row_grid(k.C, k.rows, k.Wo, &k.cvb, &k.rp, &L->grid);
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------------- BN backward
+struct BnBwdF {
+  FV x, dx;
+  FV src[B2SEG_MAX_GRADSRC];
+  int kind[B2SEG_MAX_GRADSRC];   // 0 direct (same pixel grid as x), 1 pooled (one value per window)
+  int n_src;
+  const float* scale; const float* shift; const float* mean; const float* rstd;
+  const float* dgamma; const float* dbeta;
+  float inv_count;
+  float* acc_dgamma; float* acc_dbeta;   // PASS 0: red.add targets (the dgamma / dbeta slots, zero before the launch)
+  int C, Ho, Wo, rows;
+  FastDiv fd_ho;
+  int cvb, rp;
+};
+
+// Same arithmetic as bn_bwd_lean_kernel (stream_kernels.cu): mask from the sign of t = x*scale + shift, pooled gradients
+// go to the first arg-max of t in the window.  PASS 0 accumulates dbeta = sum g and dgamma = sum g*xhat (xhat = (x-mean)*rstd,
+// formed per element so that no cancellation is left for a finalize step) and adds the block's sums straight into the
+// dgamma / dbeta slots with red.global.add -- there is no partials buffer and no finalize launch.
+// PASS 1 reads them back and writes dx = A*g + B*x + D.
+template <int PASS, int PH, int PW, int ACT, int U>
+__global__ void __launch_bounds__(256, PH * PW * U >= 4 ? 2 : 3) bn_bwd_fast_kernel(const BnBwdF k) {
+  constexpr int WIN = PH * PW;
+  extern __shared__ float red[];   // PASS 0: [256][16]
+  const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
+  const int v = blockIdx.x * k.cvb + tcv;
+  const bool active = v * 8 < k.C && trow < k.rp;
+  const bool has_bn = k.scale != nullptr;
+  float sc[8], sf[8], cB[8], cD[8], acc_b[8], acc_g[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { acc_b[e] = 0.f; acc_g[e] = 0.f; sc[e] = 1.f; sf[e] = 0.f; cB[e] = 0.f; cD[e] = 0.f; }
+  if (active) {
+    if (has_bn) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = v * 8 + e;
+        sc[e] = __ldg(k.scale + c);
+        sf[e] = __ldg(k.shift + c);
+        const float rs = __ldg(k.rstd + c), mu = __ldg(k.mean + c);
+        if (PASS == 1) {
+          const float cb = __ldg(k.dbeta + c) * k.inv_count, cg = __ldg(k.dgamma + c) * k.inv_count;
+          cB[e] = -sc[e] * cg * rs;
+          cD[e] = sc[e] * (cg * rs * mu - cb);
+        } else {
+          cB[e] = rs;          // PASS 0: xhat = x*cB + cD
+          cD[e] = -mu * rs;
+        }
+      }
+    }
+    const unsigned step = (unsigned)k.rp;
+    const int n_src = k.n_src;
+    for (int r = blockIdx.y; r < k.rows; r += gridDim.y) {
+      const unsigned n = fast_div((unsigned)r, k.fd_ho), ho = (unsigned)r - n * (unsigned)k.Ho;
+      const unsigned xrow = n * k.x.sn + ho * PH * k.x.sh + v * 8;
+      const unsigned drow = n * k.dx.sn + ho * PH * k.dx.sh + v * 8;
+      for (unsigned wo0 = trow; wo0 < (unsigned)k.Wo; wo0 += step * U) {
+        uint4 xr[U][WIN];
+        float g[U][WIN][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned wo = wo0 + u * step < (unsigned)k.Wo ? wo0 + u * step : (unsigned)k.Wo - 1;   // clamp: loads stay in range
+#pragma unroll
+          for (int q = 0; q < WIN; ++q) xr[u][q] = ld16(k.x, xrow + (q / PW) * k.x.sh + (wo * PW + q % PW) * k.x.sw);
+        }
+        float pooled[U][8];
+        bool any_pooled = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pooled[u][e] = 0.f;
+#pragma unroll
+          for (int q = 0; q < WIN; ++q)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[u][q][e] = 0.f;
+        }
+        for (int s = 0; s < n_src; ++s) {
+          const FV sv = k.src[s];
+          if (k.kind[s] == 0) {
+            const unsigned srow = n * sv.sn + ho * PH * sv.sh + v * 8;
+            uint4 rr[U][WIN];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const unsigned wo = wo0 + u * step < (unsigned)k.Wo ? wo0 + u * step : (unsigned)k.Wo - 1;
+#pragma unroll
+              for (int q = 0; q < WIN; ++q) rr[u][q] = ld16(sv, srow + (q / PW) * sv.sh + (wo * PW + q % PW) * sv.sw);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int q = 0; q < WIN; ++q) {
+                float f[8];
+                unpack8(rr[u][q], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[u][q][e] += f[e];
+              }
+          } else if (WIN > 1) {
+            const unsigned srow = n * sv.sn + ho * sv.sh + v * 8;
+            any_pooled = true;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const unsigned wo = wo0 + u * step < (unsigned)k.Wo ? wo0 + u * step : (unsigned)k.Wo - 1;
+              float f[8];
+              unpack8(ld16(sv, srow + wo * sv.sw), f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pooled[u][e] += f[e];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned wo = wo0 + u * step;
+          if (wo >= (unsigned)k.Wo) break;
+          float x[WIN][8];
+#pragma unroll
+          for (int q = 0; q < WIN; ++q) unpack8(xr[u][q], x[q]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t[WIN];
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) t[q] = fmaf(x[q][e], sc[e], sf[e]);
+            if (WIN > 1 && any_pooled) {
+              float m = t[0];
+#pragma unroll
+              for (int q = 1; q < WIN; ++q) m = fmaxf(m, t[q]);
+              bool taken = false;
+#pragma unroll
+              for (int q = 0; q < WIN; ++q) {
+                const bool hit = !taken && t[q] == m;
+                taken = taken || hit;
+                if (hit) g[u][q][e] += pooled[u][e];
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) {
+              if (ACT == B2SEG_ACT_RELU) g[u][q][e] = t[q] > 0.f ? g[u][q][e] : 0.f;
+              if (ACT == B2SEG_ACT_LEAKY) g[u][q][e] = t[q] > 0.f ? g[u][q][e] : 0.3f * g[u][q][e];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < WIN; ++q) {
+            if (PASS == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { acc_b[e] += g[u][q][e]; acc_g[e] = fmaf(g[u][q][e], fmaf(x[q][e], cB[e], cD[e]), acc_g[e]); }
+            } else {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = has_bn ? fmaf(cB[e], x[q][e], fmaf(sc[e], g[u][q][e], cD[e])) : g[u][q][e];
+              st16(k.dx, drow + (q / PW) * k.dx.sh + (wo * PW + q % PW) * k.dx.sw, pack8(o));
+            }
+          }
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    float* mine = red + (size_t)threadIdx.x * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mine[e] = acc_b[e]; mine[8 + e] = acc_g[e]; }
+    __syncthreads();
+    if (trow == 0 && v * 8 < k.C) {
+      float sb[8], sg[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sb[e] = 0.f; sg[e] = 0.f; }
+      for (int r = 0; r < k.rp; ++r) {
+        const float* o = red + (size_t)(r * k.cvb + tcv) * 16;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sb[e] += o[e]; sg[e] += o[8 + e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { atomicAdd(k.acc_dbeta + v * 8 + e, sb[e]); atomicAdd(k.acc_dgamma + v * 8 + e, sg[e]); }
+    }
+  }
+}
+
+struct BnBwdFastLaunch : PreparedOp {
+  BnBwdF k;
+  bool has_bn;
+  bool accumulate;
+  int ph, pw, act;
+  dim3 grid0, grid1;
+  template <int PASS, int PH, int PW, int U>
+  void go_act(dim3 grid, int smem, cudaStream_t s) {
+    switch (act) {
+      case B2SEG_ACT_RELU: bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_RELU, U><<<grid, 256, smem, s>>>(k); break;
+      case B2SEG_ACT_LEAKY: bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_LEAKY, U><<<grid, 256, smem, s>>>(k); break;
+      default: bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_NONE, U><<<grid, 256, smem, s>>>(k); break;
+    }
+  }
+  template <int PASS>
+  void go(dim3 grid, int smem, cudaStream_t s) {
+    if (ph == 2 && pw == 2) go_act<PASS, 2, 2, 1>(grid, smem, s);
+    else if (ph == 1 && pw == 2) go_act<PASS, 1, 2, 2>(grid, smem, s);
+    else go_act<PASS, 1, 1, 2>(grid, smem, s);
+  }
+  int launch(cudaStream_t s) override {
+    if (has_bn) {
+      if (!accumulate) {
+        B2_CUDA_OK(cudaMemsetAsync(k.acc_dgamma, 0, (size_t)k.C * 4, s));
+        B2_CUDA_OK(cudaMemsetAsync(k.acc_dbeta, 0, (size_t)k.C * 4, s));
+      }
+      go<0>(grid0, 256 * 16 * 4, s);
+      B2_CUDA_OK(cudaGetLastError());
+    }
+    go<1>(grid1, 0, s);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int num_launches() const override { return has_bn ? 2 : 1; }
+};
+
+PreparedOp* prepare_bn_bwd_fast(const b2seg_bn_bwd_desc* d) {
+  static const bool disabled = getenv("B2SEG_NO_FAST_STREAM") != nullptr;
+  if (disabled || d->x.C % 8 || d->n_src < 1 || d->n_src > B2SEG_MAX_GRADSRC) return nullptr;
+  if (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_RELU && d->act != B2SEG_ACT_LEAKY) return nullptr;
+  int ph = 1, pw = 1;
+  for (int i = 0; i < d->n_src; ++i)
+    if (d->src[i].kind == 1) {
+      const int a = d->src[i].pool_h > 1 ? d->src[i].pool_h : 1, b = d->src[i].pool_w > 1 ? d->src[i].pool_w : 1;
+      if ((ph != 1 || pw != 1) && (ph != a || pw != b)) return nullptr;
+      ph = a; pw = b;
+    }
+  if (!((ph == 1 && pw == 1) || (ph == 2 && pw == 2) || (ph == 1 && pw == 2))) return nullptr;
+  if (d->x.H % ph || d->x.W % pw) return nullptr;
+  const bool has_bn = d->scale != 0;
+  if (has_bn && (!d->dgamma || !d->dbeta || !d->mean || !d->rstd || !d->shift)) return nullptr;
+  auto* L = new BnBwdFastLaunch();
+  BnBwdF& k = L->k;
+  memset(&k, 0, sizeof(k));
+  bool ok = fv_make(d->x, &k.x) && fv_make(d->dx, &k.dx);
+  for (int i = 0; ok && i < d->n_src; ++i) {
+    ok = fv_make(d->src[i].g, &k.src[i]);
+    k.kind[i] = d->src[i].kind;
+    if (d->src[i].kind != 0 && d->src[i].kind != 1) ok = false;
+  }
+  if (!ok) { delete L; return nullptr; }
+  k.n_src = d->n_src;
+  k.scale = reinterpret_cast<const float*>(d->scale);
+  k.shift = reinterpret_cast<const float*>(d->shift);
+  k.mean = reinterpret_cast<const float*>(d->mean);
+  k.rstd = reinterpret_cast<const float*>(d->rstd);
+  k.dgamma = reinterpret_cast<const float*>(d->dgamma);
+  k.dbeta = reinterpret_cast<const float*>(d->dbeta);
+  k.acc_dgamma = reinterpret_cast<float*>(d->dgamma);
+  k.acc_dbeta = reinterpret_cast<float*>(d->dbeta);
+  k.inv_count = (float)(1.0 / d->count);
+  k.C = d->x.C; k.Ho = d->x.H / ph; k.Wo = d->x.W / pw; k.rows = d->x.N * k.Ho;
+  k.fd_ho = make_fastdiv((uint32_t)k.Ho);
+  L->has_bn = has_bn; L->ph = ph; L->pw = pw; L->act = d->act; L->accumulate = d->accumulate != 0;
+  row_grid(k.C, k.rows, k.Wo, &k.cvb, &k.rp, &L->grid1);
+  // PASS 0 ends with 2 * 8 * cvb atomics per block: one resident wave of blocks walking the rows keeps them few
+  L->grid0 = L->grid1;
+  const unsigned wave = (unsigned)std::max(1, num_sms() * (ph * pw > 1 ? 2 : 3) / (int)L->grid0.x);   // = blocks resident at once (launch bounds)
+  if (L->grid0.y > wave) L->grid0.y = wave;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------------- row sum
+// out[c] (+)= sum_r partials[r * pitch + c]: 32 channels x 32 row slices per block, fixed summation order.
+__global__ void __launch_bounds__(1024) rowsum_kernel(const float* __restrict__ partials, int n_rows, int pitch, int C, float* out, int accumulate) {
+  __shared__ float sh[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < C)
+    for (int r = ty; r < n_rows; r += 32) s += __ldg(partials + (size_t)r * pitch + c);
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int i = 1; i < 32; ++i) s += sh[i][tx];
+    out[c] = accumulate ? out[c] + s : s;
+  }
+}
+struct RowsumLaunch : PreparedOp {
+  b2seg_rowsum_desc d;
+  int launch(cudaStream_t s) override {
+    rowsum_kernel<<<(d.C + 31) / 32, 1024, 0, s>>>(reinterpret_cast<const float*>(d.partials), d.n_rows, d.pitch, d.C,
+                                                   reinterpret_cast<float*>(d.out), d.accumulate);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_rowsum(const b2seg_rowsum_desc* d) {
+  if (!d->partials || !d->out || d->n_rows < 1 || d->C < 1 || d->pitch < d->C) { set_error("rowsum: bad arguments"); return nullptr; }
+  auto* L = new RowsumLaunch(); L->d = *d; return L;
+}
+
+}  // namespace b2

@@ -98,7 +98,7 @@ struct BnActK {
 };
 // One thread owns 8 channels of U windows (U*WIN pixels in flight: all loads are issued before any use).
 template <int WIN, int U>
-__global__ void __launch_bounds__(256) bn_act_kernel(BnActK k) {
+__global__ void __launch_bounds__(256, 4) bn_act_kernel(BnActK k) {
   const int cv = k.x.C / 8;
   const int Ho = k.x.H / k.ph, Wo = k.x.W / k.pw;
   const unsigned n_win = (unsigned)k.x.N * Ho * Wo;
@@ -204,6 +204,7 @@ struct BnActLaunch : PreparedOp {
 };
 PreparedOp* prepare_bn_act(const b2seg_bn_act_desc* d) {
   if (d->x.C % 8) { set_error("bn_act: C %% 8"); return nullptr; }
+  if (PreparedOp* fast = prepare_bn_act_fast(d)) return fast;   // instruction-lean row walker (stream_fast.cu) when eligible
   auto* L = new BnActLaunch();
   BnActK& k = L->k;
   memset(&k, 0, sizeof(k));
@@ -388,12 +389,19 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
   }
 }
 
+int launch_bn_bwd_finalize(const float* partials, int n_blocks, int C, float* dgamma, float* dbeta, const float* mean, const float* rstd,
+                           int raw_gx, cudaStream_t s) {
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(partials, n_blocks, C, dgamma, dbeta, mean, rstd, raw_gx);
+  B2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // Lean BN(+ReLU/LeakyReLU/identity) backward.  Per element: mask from the sign of t = x*scale+shift (for a pooled source the
 // window arg-max of t, which equals the arg-max of relu(t) wherever the gradient survives the mask),
 //   PASS 0:  sum g, sum g*x          PASS 1:  dx = A*g + B*x + D   with per-channel A = scale, B = -scale*cg*rstd,
 //   D = scale*(cg*rstd*mean - cb), cb = dbeta/count, cg = dgamma/count  (== scale*(g - cb - xhat*cg)).
 template <int PASS, int WIN, int U, int ACT>
-__global__ void __launch_bounds__(256, 2) bn_bwd_lean_kernel(BnBwdK k) {
+__global__ void __launch_bounds__(256, WIN == 4 ? 2 : 4) bn_bwd_lean_kernel(BnBwdK k) {
   extern __shared__ float red[];  // PASS 0: [256][16]
   const int cvec_total = k.x.C / 8;
   const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
@@ -591,6 +599,7 @@ struct BnBwdLaunch : PreparedOp {
 };
 PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
   if (d->x.C % 8 || d->n_src < 1 || d->n_src > B2SEG_MAX_GRADSRC) { set_error("bn_bwd: bad C or n_src"); return nullptr; }
+  if (PreparedOp* fast = prepare_bn_bwd_fast(d)) return fast;   // instruction-lean row walker (stream_fast.cu) when eligible
   auto* L = new BnBwdLaunch();
   BnBwdK& k = L->k;
   memset(&k, 0, sizeof(k));
