@@ -314,7 +314,8 @@ def test_adam_keras_rule():
     assert torch.equal(wb, w.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("cout,act,kind,Cin", [(1, L.ACT_SIGMOID, 0, 64), (4, L.ACT_SOFTMAX, 1, 64), (1, L.ACT_NONE, 2, 128), (2, L.ACT_NONE, 3, 64)])
+@pytest.mark.parametrize("cout,act,kind,Cin", [(1, L.ACT_SIGMOID, 0, 64), (4, L.ACT_SOFTMAX, 1, 64), (1, L.ACT_NONE, 2, 128), (2, L.ACT_NONE, 3, 64),
+                                                (8, L.ACT_SOFTMAX, 1, 64), (3, L.ACT_NONE, 2, 256), (5, L.ACT_NONE, 2, 320), (1, L.ACT_SIGMOID, 0, 8)])
 def test_head_and_loss(cout, act, kind, Cin):
     dev = "cuda"
     N, H, W = 2, 16, 16
@@ -355,6 +356,32 @@ def test_head_and_loss(cout, act, kind, Cin):
     assert abs(float(loss) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss)))
     assert rel_l2(dx.float(), xt.grad) < 4e-3
     assert rel_l2(dw, wt.grad) < 1e-4 and rel_l2(db, bt.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cout", [1, 2, 6])
+def test_head_on_channel_window_ragged(cout):
+    """pixel-contiguous fast path on a channel window of a wider buffer (pitch > C) with a pixel count that is no multiple
+    of the thread tiling; outputs outside the window must stay untouched"""
+    dev = "cuda"
+    N, H, W, Cin = 3, 5, 7, 64
+    xb = bf(torch.randn(N, H, W, 3 * Cin, device=dev))
+    dxb = torch.full((N, H, W, 2 * Cin), 9.0, device=dev, dtype=torch.bfloat16)
+    w = torch.randn(Cin, cout, device=dev) * 0.1
+    b = torch.randn(cout, device=dev) * 0.1
+    y = torch.zeros(N, H, W, cout, device=dev)
+    dl = torch.randn(N, H, W, cout, device=dev)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    hd = L.HeadDesc()
+    hd.x, hd.w, hd.b, hd.cout, hd.act, hd.stride = tv(xb, Cin, Cin).to_c(), w.data_ptr(), b.data_ptr(), cout, L.ACT_NONE, 1
+    hd.y, hd.dlogits, hd.dx, hd.dw, hd.db = y.data_ptr(), dl.data_ptr(), tv(dxb, Cin, Cin).to_c(), dw.data_ptr(), db.data_ptr()
+    L.call("b2seg_head_fwd", hd, stream())
+    L.call("b2seg_head_bwd", hd, stream())
+    torch.cuda.synchronize()
+    x = xb[..., Cin:2 * Cin].float()
+    assert torch.allclose(y, x @ w + b, atol=2e-5, rtol=1e-4)
+    assert rel_l2(dxb[..., Cin:].float(), dl @ w.t()) < 4e-3
+    assert torch.all(dxb[..., :Cin] == 9.0)
+    assert rel_l2(dw, torch.einsum("nhwc,nhwo->co", x, dl)) < 1e-4 and rel_l2(db, dl.sum((0, 1, 2))) < 1e-4
 
 
 def test_cast_eltwise_colsum():

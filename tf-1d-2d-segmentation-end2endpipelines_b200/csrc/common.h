@@ -46,6 +46,7 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d);
 PreparedOp* prepare_bn_act_fast(const b2seg_bn_act_desc* d);   // nullptr (no error) when not eligible
 PreparedOp* prepare_bn_bwd_fast(const b2seg_bn_bwd_desc* d);
 PreparedOp* prepare_rowsum(const b2seg_rowsum_desc* d);
+PreparedOp* prepare_head_fast(const b2seg_head_desc* d, bool bwd);   // nullptr (no error) when not eligible
 PreparedOp* prepare_adam(const b2seg_adam_desc* d);
 PreparedOp* prepare_head_fwd(const b2seg_head_desc* d);
 PreparedOp* prepare_head_bwd(const b2seg_head_desc* d);

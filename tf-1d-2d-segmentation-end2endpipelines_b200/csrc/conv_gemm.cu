@@ -205,6 +205,11 @@ int fill_epi_params(const b2seg_conv_desc* d, int block_n, int bw, int bh, int b
     e->mul_sn = d->mul_view.sn; e->mul_sh = d->mul_view.sh; e->mul_sw = d->mul_view.sw;
     e->mul_c = d->mul_view.C;
   }
+  {
+    auto span = [&](long long sn, long long sh, long long sw) { return (bn - 1) * llabs(sn) + (bh - 1) * llabs(sh) + (bw - 1) * llabs(sw); };
+    if (span(o.sn, o.sh, o.sw) >= (1ll << 31) || (d->mul_mode != 0 && span(d->mul_view.sn, d->mul_view.sh, d->mul_view.sw) >= (1ll << 31)))
+      return fail(B2SEG_ERR_ARG, "conv: a tile spans more than 2^31 elements of the output view");
+  }
   e->lbw = 0; while ((1 << e->lbw) < bw) ++e->lbw;
   e->lbwh = 0; while ((1 << e->lbwh) < bw * bh) ++e->lbwh;
   e->stats_per_cta = (e->n_tiles == 1) ? 1 : 0;

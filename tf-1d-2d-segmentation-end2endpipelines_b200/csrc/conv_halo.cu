@@ -36,6 +36,8 @@ struct alignas(64) HaloKParams {
   int b_stages;                // non-resident: number of B pipeline stages
   int b_region_bytes;
   int b_resident_tiles;        // resident: number of B tiles (taps * channel blocks)
+  int k16_last;                // K = 16 steps that hold real channels in the last 64-channel block (1..4): the first layer
+                               // (3 -> 8 input channels) issues one MMA per tap instead of four on TMA zero fill
   ConvEpiParams e;
 };
 
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       const uint64_t adesc0 = make_smem_desc(0, 16, p.sbo);
       const uint64_t bdesc0 = B_MN ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 16, 1024);
       const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
-      const int wins_per_group = p.wins_per_group, kc_blocks = p.kc_blocks, b_stages = p.b_stages;
+      const int wins_per_group = p.wins_per_group, kc_blocks = p.kc_blocks, b_stages = p.b_stages, k16_last = p.k16_last;
       uint32_t sa = 0, pa = 0, sb_i = 0, pb = 0, acc = 0, acc_phase = 0;
       if (B_RES) {
         mbar_wait(bres_bar, 0);
@@ -194,10 +196,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
                 bd = bdesc0 + (sB16 + sb_i * (kBStageBytes >> 4));
               }
               const uint64_t ad = ad_stage + off;
+              if (cb + 1 < kc_blocks || k16_last == kBlockK / 16) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                umma_bf16_elect(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
-                accumulate = 1;
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  umma_bf16_elect(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
+                  accumulate = 1;
+                }
+              } else {
+                for (int k = 0; k < k16_last; ++k) {
+                  umma_bf16_elect(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
+                  accumulate = 1;
+                }
               }
               if (!B_RES) {
                 umma_commit_elect(&emptyB[sb_i]);
@@ -335,6 +344,7 @@ PreparedOp* prepare_conv_halo(const b2seg_conv_desc* d) {
   kp.sbo = (bh == 1) ? 1024 : ww * 128;
   const int k_ch = L->b_mn ? d->w_cout : d->w_cin;
   kp.kc_blocks = (k_ch + kBlockK - 1) / kBlockK;
+  kp.k16_last = (k_ch - (kp.kc_blocks - 1) * kBlockK + 15) / 16;
   kp.wins_per_group = (int)wins.size() / d->n_groups;
   // windows are created group by group, so wins[] is already ordered by group
   int tcount = 0;

@@ -431,6 +431,224 @@ PreparedOp* prepare_bn_bwd_fast(const b2seg_bn_bwd_desc* d) {
   return L;
 }
 
+// ---------------------------------------------------------------------------------------------------- pointwise heads
+// The `out` / `level{k}` 1x1 convolutions (Cout <= 8) on a pixel-contiguous view: pixel p starts p * pitch elements after
+// the first, so no coordinate decoding is needed at all.  G = C/8 lanes share a pixel (one 16-byte vector each), the head
+// weights live in registers, U pixels are in flight per thread.  The backward kernel produces dx, dW and db in ONE pass
+// over x (the generic path reads dlogits twice and runs two kernels).
+struct HeadF {
+  unsigned long long x, dx;
+  unsigned pitch, dpitch;        // elements between consecutive pixels
+  unsigned n_pix;
+  int G, act, has_dx;
+  const float* w; const float* b;
+  float* y; float* logits;
+  const float* dl; float* dw; float* db;
+};
+
+static bool pixel_contiguous(const b2seg_view& v, unsigned* pitch) {
+  if (v.ptr == 0 || (v.ptr & 15) || v.sw <= 0 || (v.sw % 8)) return false;
+  if (v.W > 1 && v.H > 1 && v.sh != (long long)v.W * v.sw) return false;
+  if (v.N > 1 && v.sn != (long long)v.H * (v.H > 1 || v.W > 1 ? (v.H > 1 ? v.sh : (long long)v.W * v.sw) : v.sw)) return false;
+  if ((long long)v.N * v.H * v.W * v.sw >= (1ll << 31)) return false;
+  *pitch = (unsigned)v.sw;
+  return true;
+}
+
+constexpr int head_fwd_minb(int cout) { return cout <= 2 ? 4 : (cout <= 4 ? 3 : 2); }
+constexpr int head_bwd_minb(int cout) { return cout == 1 ? 4 : (cout == 2 ? 3 : (cout <= 4 ? 2 : 1)); }
+
+template <int COUT, int U>
+__global__ void __launch_bounds__(256, head_fwd_minb(COUT)) head_fwd_fast_kernel(const HeadF k) {
+  const int G = k.G;
+  const int gl = threadIdx.x % G;
+  const unsigned gid = (blockIdx.x * 256u + threadIdx.x) / G;
+  const unsigned gstride = gridDim.x * 256u / G;
+  float w[8][COUT];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) w[e][o] = __ldg(k.w + (size_t)(gl * 8 + e) * COUT + o);
+  float bias[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) bias[o] = __ldg(k.b + o);
+  const unsigned n_iter = (k.n_pix + gstride * U - 1) / (gstride * U);   // uniform trip count: the shuffles need whole warps
+  for (unsigned it = 0; it < n_iter; ++it) {
+    uint4 raw[U];
+    unsigned pix[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pix[u] = gid + (it * U + u) * gstride;
+      const unsigned pc = pix[u] < k.n_pix ? pix[u] : k.n_pix - 1;
+      raw[u] = __ldg(reinterpret_cast<const uint4*>(k.x + ((unsigned long long)pc * k.pitch + gl * 8) * 2ull));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[8], acc[COUT];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        acc[o] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[o] = fmaf(f[e], w[e][o], acc[o]);
+      }
+      for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off, 32);
+      if (gl == 0 && pix[u] < k.n_pix) {
+        float z[COUT];
+        float zmax = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) { z[o] = acc[o] + bias[o]; zmax = fmaxf(zmax, z[o]); }
+        if (k.logits) {
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) k.logits[(size_t)pix[u] * COUT + o] = z[o];
+        }
+        if (k.act == B2SEG_ACT_SOFTMAX) {
+          float den = 0.f;
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) { z[o] = __expf(z[o] - zmax); den += z[o]; }
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) k.y[(size_t)pix[u] * COUT + o] = z[o] / den;
+        } else {
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) k.y[(size_t)pix[u] * COUT + o] = act_fwd(z[o], k.act);
+        }
+      }
+    }
+  }
+}
+
+template <int COUT, int U>
+__global__ void __launch_bounds__(256, head_bwd_minb(COUT)) head_bwd_fast_kernel(const HeadF k) {
+  extern __shared__ float red[];   // [256][9]
+  const int G = k.G;
+  const int gl = threadIdx.x % G;
+  const unsigned gid = (blockIdx.x * 256u + threadIdx.x) / G;
+  const unsigned gstride = gridDim.x * 256u / G;
+  float w[8][COUT], acc[COUT][8], accb[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    accb[o] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { w[e][o] = __ldg(k.w + (size_t)(gl * 8 + e) * COUT + o); acc[o][e] = 0.f; }
+  }
+  for (unsigned p0 = gid; p0 < k.n_pix; p0 += gstride * U) {
+    uint4 raw[U];
+    float d[U][COUT];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix = p0 + u * gstride;
+      const bool ok = pix < k.n_pix;
+      const unsigned pc = ok ? pix : k.n_pix - 1;
+      raw[u] = __ldg(reinterpret_cast<const uint4*>(k.x + ((unsigned long long)pc * k.pitch + gl * 8) * 2ull));
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) d[u][o] = ok ? __ldg(k.dl + (size_t)pc * COUT + o) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned pix = p0 + u * gstride;
+      float f[8], o8[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o8[e] = 0.f;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        accb[o] += d[u][o];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { acc[o][e] = fmaf(d[u][o], f[e], acc[o][e]); o8[e] = fmaf(d[u][o], w[e][o], o8[e]); }
+      }
+      if (k.has_dx && pix < k.n_pix)
+        *reinterpret_cast<uint4*>(k.dx + ((unsigned long long)pix * k.dpitch + gl * 8) * 2ull) = pack8(o8);
+    }
+  }
+  const int rows = 256 / G, trow = threadIdx.x / G;
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    float* mine = red + (size_t)threadIdx.x * 9;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mine[e] = acc[o][e];
+    mine[8] = accb[o];
+    __syncthreads();
+    if (trow == 0) {
+      float s9[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) s9[e] = 0.f;
+      for (int r = 0; r < rows; ++r) {
+        const float* q = red + (size_t)(r * G + gl) * 9;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) s9[e] += q[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(k.dw + (size_t)(gl * 8 + e) * COUT + o, s9[e]);
+      if (gl == 0) atomicAdd(k.db + o, s9[8]);
+    }
+    __syncthreads();
+  }
+}
+
+#define B2_FAST_COUT_SWITCH(cout, CALL)            \
+  switch (cout) {                                  \
+    case 1: { constexpr int CO = 1; CALL; } break; \
+    case 2: { constexpr int CO = 2; CALL; } break; \
+    case 3: { constexpr int CO = 3; CALL; } break; \
+    case 4: { constexpr int CO = 4; CALL; } break; \
+    case 5: { constexpr int CO = 5; CALL; } break; \
+    case 6: { constexpr int CO = 6; CALL; } break; \
+    case 7: { constexpr int CO = 7; CALL; } break; \
+    default: { constexpr int CO = 8; CALL; } break; \
+  }
+
+struct HeadFastLaunch : PreparedOp {
+  HeadF k;
+  int cout;
+  bool bwd;
+  int launch(cudaStream_t s) override {
+    const long long threads = (long long)k.n_pix * k.G;
+    long long grid = (threads / 4 + 255) / 256;
+    const int cap = num_sms() * (bwd ? head_bwd_minb(cout) : head_fwd_minb(cout));
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if (bwd) {
+      B2_FAST_COUT_SWITCH(cout, (head_bwd_fast_kernel<CO, 4><<<(unsigned)grid, 256, 256 * 9 * 4, s>>>(k)));
+    } else {
+      B2_FAST_COUT_SWITCH(cout, (head_fwd_fast_kernel<CO, 4><<<(unsigned)grid, 256, 0, s>>>(k)));
+    }
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+
+PreparedOp* prepare_head_fast(const b2seg_head_desc* d, bool bwd) {
+  static const bool disabled = getenv("B2SEG_NO_FAST_STREAM") != nullptr;
+  if (disabled || d->stride > 1 || d->cout < 1 || d->cout > 8 || d->x.C % 8) return nullptr;
+  const int cvec = d->x.C / 8;
+  if (cvec > 32 || (cvec & (cvec - 1))) return nullptr;
+  HeadF k;
+  memset(&k, 0, sizeof(k));
+  if (!pixel_contiguous(d->x, &k.pitch)) return nullptr;
+  k.x = d->x.ptr;
+  k.n_pix = (unsigned)((long long)d->x.N * d->x.H * d->x.W);
+  if (k.n_pix == 0) return nullptr;
+  k.G = cvec; k.act = d->act;
+  k.w = reinterpret_cast<const float*>(d->w); k.b = reinterpret_cast<const float*>(d->b);
+  k.y = reinterpret_cast<float*>(d->y); k.logits = reinterpret_cast<float*>(d->logits);
+  if (bwd) {
+    k.has_dx = d->dx.ptr != 0;
+    if (k.has_dx) {
+      if (!pixel_contiguous(d->dx, &k.dpitch) || d->dx.N != d->x.N || d->dx.H != d->x.H || d->dx.W != d->x.W) return nullptr;
+      k.dx = d->dx.ptr;
+    }
+    k.dl = reinterpret_cast<const float*>(d->dlogits); k.dw = reinterpret_cast<float*>(d->dw); k.db = reinterpret_cast<float*>(d->db);
+    if (!k.dl || !k.dw || !k.db) return nullptr;
+  } else if (!k.w || !k.b || !k.y) {
+    return nullptr;
+  }
+  auto* L = new HeadFastLaunch();
+  L->k = k; L->cout = d->cout; L->bwd = bwd;
+  return L;
+}
+
 // ---------------------------------------------------------------------------------------------------- row sum
 // out[c] (+)= sum_r partials[r * pitch + c]: 32 channels x 32 row slices per block, fixed summation order.
 __global__ void __launch_bounds__(1024) rowsum_kernel(const float* __restrict__ partials, int n_rows, int pitch, int C, float* out, int accumulate) {

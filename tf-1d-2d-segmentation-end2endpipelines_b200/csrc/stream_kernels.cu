@@ -793,6 +793,7 @@ struct HeadFwdLaunch : PreparedOp {
 };
 PreparedOp* prepare_head_fwd(const b2seg_head_desc* d) {
   if (d->cout < 1 || d->cout > 8 || d->x.C % 8) { set_error("head: cout in 1..8, C %% 8 == 0"); return nullptr; }
+  if (PreparedOp* fast = prepare_head_fast(d, false)) return fast;
   auto* L = new HeadFwdLaunch(); L->d = *d; return L;
 }
 
@@ -907,6 +908,7 @@ struct HeadBwdLaunch : PreparedOp {
 };
 PreparedOp* prepare_head_bwd(const b2seg_head_desc* d) {
   if (d->cout < 1 || d->cout > 8 || d->x.C % 8) { set_error("head: cout in 1..8, C %% 8 == 0"); return nullptr; }
+  if (PreparedOp* fast = prepare_head_fast(d, true)) return fast;
   auto* L = new HeadBwdLaunch(); L->d = *d; return L;
 }
 
