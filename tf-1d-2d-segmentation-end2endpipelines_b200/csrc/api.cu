@@ -1,5 +1,6 @@
 // C ABI (include/b2seg.h): error plumbing, tensor-map encoding, op-level entry points and the plan object.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -34,6 +35,11 @@ int num_sms() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("B2SEG_PDL") != nullptr;   // measured on cfg2: 2821 (on) vs 2848 (off) images/s -- no gain, so opt-in
+  return on;
 }
 
 int require_sm100() {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 
 #include "../../include/b2seg.h"
@@ -22,6 +23,24 @@ int fail(int code, const char* fmt, ...);
 
 int num_sms();
 int require_sm100();
+bool pdl_enabled();   // programmatic dependent launch (opt-in with B2SEG_PDL=1)
+
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute: the kernel may become resident before its predecessor in
+// the stream has drained; it must call pdl_prologue() / pdl_wait() (ptx.cuh) before its first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // 4-D activation map over a view: dims (C, W, H, N), bf16, SWIZZLE_128B, zero OOB fill.
 int encode_act_map(CUtensorMap* m, const b2seg_view& v, int box_c, int box_w, int box_h, int box_n);

@@ -139,9 +139,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   // keeps 8 running sums in registers for the whole kernel and the CTA reduces them once at the end: the per-chunk
   // shuffle + barrier reduction of the BatchNorm path cost +0.12 ms on the epilogue-bound 256x256 layer.
   const bool colsum_only = has_stats && mul_mode != 0 && n_tiles == 1 && mul_c <= 64 && per_cta;
-  float bsum[8];
+  // Same idea for the BatchNorm statistics of a one-chunk tile (BLOCK_N = 64, the epilogue-bound high-resolution layers):
+  // sum and sum of squares stay in 16 registers across all tiles of the CTA.
+  const bool reg_stats = kChunks == 1 && has_stats && per_cta && !colsum_only;
+  const bool persist = colsum_only || reg_stats;
+  float s[8], q2[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q2[e] = 0.f; }
   float cta_s[kChunks], cta_q[kChunks];      // per-CTA BN statistics (threads et < 64)
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) { cta_s[c] = 0.f; cta_q[c] = 0.f; }
@@ -214,9 +218,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
       }
       named_bar_sync(1, kEpiThreads);
       // ---- coalesced store of the 128 x 64 chunk (+ derivative mask) and column statistics from the same registers
-      float s[8], q2[8];
+      if (!persist) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] = 0.f; q2[e] = 0.f; }
+        for (int e = 0; e < 8; ++e) { s[e] = 0.f; q2[e] = 0.f; }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = r0 + 32 * i;
@@ -244,8 +249,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
               const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                bsum[2 * e] += __uint_as_float(w4[e] << 16);
-                bsum[2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+                s[2 * e] += __uint_as_float(w4[e] << 16);
+                s[2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
               }
             }
           } else if (has_stats) {   // statistics of exactly what was stored (rows outside the image hold zeros and add nothing)
@@ -259,7 +264,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
           }
         }
       }
-      if (has_stats && !colsum_only) {
+      if (has_stats && !persist) {
         // lanes l, l^8, l^16, l^24 own the same 8 columns
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -295,22 +300,28 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }
-  if (colsum_only) {
+  if (persist) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      bsum[e] += __shfl_xor_sync(0xffffffffu, bsum[e], 8);
-      bsum[e] += __shfl_xor_sync(0xffffffffu, bsum[e], 16);
+      s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
+      q2[e] += __shfl_xor_sync(0xffffffffu, q2[e], 8);
+      s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
+      q2[e] += __shfl_xor_sync(0xffffffffu, q2[e], 16);
     }
     if (lane < 8) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) colpart[(ew * 64 + lane * 8 + e) * 2] = bsum[e];
+      for (int e = 0; e < 8; ++e) {
+        colpart[(ew * 64 + lane * 8 + e) * 2 + 0] = s[e];
+        colpart[(ew * 64 + lane * 8 + e) * 2 + 1] = q2[e];
+      }
     }
     named_bar_sync(2, kEpiThreads);
     if (et < 64) {
-      float s2 = 0.f;
+      float s2 = 0.f, ss2 = 0.f;
 #pragma unroll
-      for (int w = 0; w < kEpiWarps; ++w) s2 += colpart[(w * 64 + et) * 2];
-      cta_s[0] = s2;   // sums of squares stay 0: only the column sums are consumed (b2seg_rowsum)
+      for (int w = 0; w < kEpiWarps; ++w) { s2 += colpart[(w * 64 + et) * 2]; ss2 += colpart[(w * 64 + et) * 2 + 1]; }
+      cta_s[0] = s2;    // colsum_only: sums of squares are 0 and unused (b2seg_rowsum reads the column sums)
+      cta_q[0] = ss2;
     }
   }
   if (has_stats && per_cta && et < 64) {

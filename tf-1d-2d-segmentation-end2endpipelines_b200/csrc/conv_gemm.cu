@@ -34,6 +34,7 @@ struct ConvCfg {
 template <int BLOCK_N, bool B_MN>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
+  pdl_launch_dependents();   // the next kernel of the stream may become resident as SMs drain
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                // barriers / TMEM are set up; from here on global memory of earlier kernels is read
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int nkb = p.taps_per_group * p.kc_blocks;
@@ -232,8 +234,7 @@ static int launch_conv_t(const ConvKParams& kp, int grid, cudaStream_t s) {
     B2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  conv_gemm_kernel<BLOCK_N, B_MN><<<grid, kConvThreads, Cfg::kSmemBytes, s>>>(kp);
-  B2_CUDA_OK(cudaGetLastError());
+  B2_CUDA_OK(launch_k(conv_gemm_kernel<BLOCK_N, B_MN>, dim3(grid), dim3(kConvThreads), Cfg::kSmemBytes, s, kp));
   return 0;
 }
 

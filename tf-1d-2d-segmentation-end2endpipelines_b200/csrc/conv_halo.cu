@@ -45,6 +45,7 @@ template <int BLOCK_N, bool B_MN, bool B_RES>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid_constant__ HaloKParams p) {
   constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
   constexpr int kTmemCols = 2 * BLOCK_N;
+  pdl_launch_dependents();   // the next kernel of the stream may become resident as SMs drain
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                // barriers / TMEM are set up; from here on global memory of earlier kernels is read
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
@@ -307,8 +309,7 @@ static int launch_halo_t(const HaloKParams& kp, int grid, int smem_bytes, cudaSt
     B2_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, B_MN, B_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBudget));
     attr_smem = kHaloSmemBudget;
   }
-  conv_halo_kernel<BLOCK_N, B_MN, B_RES><<<grid, kConvThreads, smem_bytes, s>>>(kp);
-  B2_CUDA_OK(cudaGetLastError());
+  B2_CUDA_OK(launch_k(conv_halo_kernel<BLOCK_N, B_MN, B_RES>, dim3(grid), dim3(kConvThreads), smem_bytes, s, kp));
   return 0;
 }
 

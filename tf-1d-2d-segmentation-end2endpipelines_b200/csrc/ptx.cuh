@@ -11,6 +11,16 @@ namespace b2 {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// Programmatic dependent launch.  Every kernel launched through b2::launch_k (common.h) starts with pdl_prologue(): it lets
+// the NEXT kernel of the stream become resident as SMs drain (its barrier / TMEM / tensor-map set-up overlaps our tail) and
+// then blocks until the PREVIOUS kernel has completed and flushed — so nothing before it may touch global memory.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // ---------------------------------------------------------------- mbarrier

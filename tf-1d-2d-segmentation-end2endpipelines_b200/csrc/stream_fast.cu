@@ -61,6 +61,7 @@ struct BnActF {
 // One thread owns 8 channels; a block covers cvb channel vectors x rp window columns; blocks walk window rows.
 template <int PH, int PW, int ACT, int U>
 __global__ void __launch_bounds__(256, PH * PW * U > 4 ? 2 : 4) bn_act_fast_kernel(const BnActF k) {
+  pdl_prologue();
   constexpr int WIN = PH * PW;
   const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
   const int v = blockIdx.x * k.cvb + tcv;
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(256, PH * PW * U > 4 ? 2 : 4) bn_act_fast_kern
     sf[e] = k.shift ? __ldg(k.shift + v * 8 + e) : 0.f;
   }
   const unsigned step = (unsigned)k.rp;
-  for (int r = blockIdx.y; r < k.rows; r += gridDim.y) {
+  for (int rr = blockIdx.y; rr < k.rows; rr += gridDim.y) {
+    // rows are walked from the END of the tensor: the convolution that produced x wrote its last tiles last, so they are
+    // still in the 126 MB L2, and the head of the output is what the next (forward-walking) convolution reads first
+    const int r = k.rows - 1 - rr;
     const unsigned n = fast_div((unsigned)r, k.fd_ho), ho = (unsigned)r - n * (unsigned)k.Ho;
     const unsigned xrow = n * k.x.sn + ho * PH * k.x.sh + v * 8;
     const unsigned o0row = n * k.out0.sn + ho * PH * k.out0.sh + v * 8;
@@ -119,10 +123,10 @@ struct BnActFastLaunch : PreparedOp {
   template <int PH, int PW, int U>
   void go(cudaStream_t s) {
     switch (act) {
-      case B2SEG_ACT_RELU: bn_act_fast_kernel<PH, PW, B2SEG_ACT_RELU, U><<<grid, 256, 0, s>>>(k); break;
-      case B2SEG_ACT_LEAKY: bn_act_fast_kernel<PH, PW, B2SEG_ACT_LEAKY, U><<<grid, 256, 0, s>>>(k); break;
-      case B2SEG_ACT_SIGMOID: bn_act_fast_kernel<PH, PW, B2SEG_ACT_SIGMOID, U><<<grid, 256, 0, s>>>(k); break;
-      default: bn_act_fast_kernel<PH, PW, B2SEG_ACT_NONE, U><<<grid, 256, 0, s>>>(k); break;
+      case B2SEG_ACT_RELU: launch_k(bn_act_fast_kernel<PH, PW, B2SEG_ACT_RELU, U>, grid, dim3(256), 0, s, k); break;
+      case B2SEG_ACT_LEAKY: launch_k(bn_act_fast_kernel<PH, PW, B2SEG_ACT_LEAKY, U>, grid, dim3(256), 0, s, k); break;
+      case B2SEG_ACT_SIGMOID: launch_k(bn_act_fast_kernel<PH, PW, B2SEG_ACT_SIGMOID, U>, grid, dim3(256), 0, s, k); break;
+      default: launch_k(bn_act_fast_kernel<PH, PW, B2SEG_ACT_NONE, U>, grid, dim3(256), 0, s, k); break;
     }
   }
   int launch(cudaStream_t s) override {
@@ -197,6 +201,7 @@ struct BnBwdF {
 // PASS 1 reads them back and writes dx = A*g + B*x + D.
 template <int PASS, int PH, int PW, int ACT, int U>
 __global__ void __launch_bounds__(256, PH * PW * U >= 4 ? 2 : 3) bn_bwd_fast_kernel(const BnBwdF k) {
+  pdl_prologue();
   constexpr int WIN = PH * PW;
   extern __shared__ float red[];   // PASS 0: [256][16]
   const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
@@ -226,7 +231,10 @@ __global__ void __launch_bounds__(256, PH * PW * U >= 4 ? 2 : 3) bn_bwd_fast_ker
     }
     const unsigned step = (unsigned)k.rp;
     const int n_src = k.n_src;
-    for (int r = blockIdx.y; r < k.rows; r += gridDim.y) {
+    for (int rr = blockIdx.y; rr < k.rows; rr += gridDim.y) {
+      // PASS 0 walks the rows backwards (the tail of the gradient its producer just wrote is still in L2) and leaves the head
+      // of x / g in L2 for PASS 1, which walks forwards
+      const int r = PASS == 0 ? k.rows - 1 - rr : rr;
       const unsigned n = fast_div((unsigned)r, k.fd_ho), ho = (unsigned)r - n * (unsigned)k.Ho;
       const unsigned xrow = n * k.x.sn + ho * PH * k.x.sh + v * 8;
       const unsigned drow = n * k.dx.sn + ho * PH * k.dx.sh + v * 8;
@@ -358,9 +366,9 @@ struct BnBwdFastLaunch : PreparedOp {
   template <int PASS, int PH, int PW, int U>
   void go_act(dim3 grid, int smem, cudaStream_t s) {
     switch (act) {
-      case B2SEG_ACT_RELU: bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_RELU, U><<<grid, 256, smem, s>>>(k); break;
-      case B2SEG_ACT_LEAKY: bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_LEAKY, U><<<grid, 256, smem, s>>>(k); break;
-      default: bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_NONE, U><<<grid, 256, smem, s>>>(k); break;
+      case B2SEG_ACT_RELU: launch_k(bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_RELU, U>, grid, dim3(256), smem, s, k); break;
+      case B2SEG_ACT_LEAKY: launch_k(bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_LEAKY, U>, grid, dim3(256), smem, s, k); break;
+      default: launch_k(bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_NONE, U>, grid, dim3(256), smem, s, k); break;
     }
   }
   template <int PASS>
@@ -460,6 +468,7 @@ constexpr int head_bwd_minb(int cout) { return cout == 1 ? 4 : (cout == 2 ? 3 : 
 
 template <int COUT, int U>
 __global__ void __launch_bounds__(256, head_fwd_minb(COUT)) head_fwd_fast_kernel(const HeadF k) {
+  pdl_prologue();
   const int G = k.G;
   const int gl = threadIdx.x % G;
   const unsigned gid = (blockIdx.x * 256u + threadIdx.x) / G;
@@ -521,6 +530,7 @@ __global__ void __launch_bounds__(256, head_fwd_minb(COUT)) head_fwd_fast_kernel
 
 template <int COUT, int U>
 __global__ void __launch_bounds__(256, head_bwd_minb(COUT)) head_bwd_fast_kernel(const HeadF k) {
+  pdl_prologue();
   extern __shared__ float red[];   // [256][9]
   const int G = k.G;
   const int gl = threadIdx.x % G;
@@ -610,9 +620,9 @@ struct HeadFastLaunch : PreparedOp {
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     if (bwd) {
-      B2_FAST_COUT_SWITCH(cout, (head_bwd_fast_kernel<CO, 4><<<(unsigned)grid, 256, 256 * 9 * 4, s>>>(k)));
+      B2_FAST_COUT_SWITCH(cout, (launch_k(head_bwd_fast_kernel<CO, 4>, dim3((unsigned)grid), dim3(256), 256 * 9 * 4, s, k)));
     } else {
-      B2_FAST_COUT_SWITCH(cout, (head_fwd_fast_kernel<CO, 4><<<(unsigned)grid, 256, 0, s>>>(k)));
+      B2_FAST_COUT_SWITCH(cout, (launch_k(head_fwd_fast_kernel<CO, 4>, dim3((unsigned)grid), dim3(256), 0, s, k)));
     }
     B2_CUDA_OK(cudaGetLastError());
     return 0;
@@ -652,6 +662,7 @@ PreparedOp* prepare_head_fast(const b2seg_head_desc* d, bool bwd) {
 // ---------------------------------------------------------------------------------------------------- row sum
 // out[c] (+)= sum_r partials[r * pitch + c]: 32 channels x 32 row slices per block, fixed summation order.
 __global__ void __launch_bounds__(1024) rowsum_kernel(const float* __restrict__ partials, int n_rows, int pitch, int C, float* out, int accumulate) {
+  pdl_prologue();
   __shared__ float sh[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -668,8 +679,8 @@ __global__ void __launch_bounds__(1024) rowsum_kernel(const float* __restrict__ 
 struct RowsumLaunch : PreparedOp {
   b2seg_rowsum_desc d;
   int launch(cudaStream_t s) override {
-    rowsum_kernel<<<(d.C + 31) / 32, 1024, 0, s>>>(reinterpret_cast<const float*>(d.partials), d.n_rows, d.pitch, d.C,
-                                                   reinterpret_cast<float*>(d.out), d.accumulate);
+    launch_k(rowsum_kernel, dim3((d.C + 31) / 32), dim3(1024), 0, s, reinterpret_cast<const float*>(d.partials), d.n_rows, d.pitch, d.C,
+             reinterpret_cast<float*>(d.out), d.accumulate);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }

@@ -39,6 +39,7 @@ PreparedOp* prepare_cast(const b2seg_cast_desc* d) {
 
 // ------------------------------------------------------------------------------------------ BN finalize
 __global__ void bn_finalize_kernel(b2seg_bn_finalize_desc d) {
+  pdl_prologue();
   __shared__ double sh_s[32][33], sh_q[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -83,7 +84,7 @@ __global__ void bn_finalize_kernel(b2seg_bn_finalize_desc d) {
 struct BnFinalizeLaunch : PreparedOp {
   b2seg_bn_finalize_desc d;
   int launch(cudaStream_t s) override {
-    bn_finalize_kernel<<<(d.C + 31) / 32, 1024, 0, s>>>(d);
+    launch_k(bn_finalize_kernel, dim3((d.C + 31) / 32), dim3(1024), 0, s, d);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -654,6 +655,7 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
 // ------------------------------------------------------------------------------------------ Adam (Keras-2 rule)
 struct AdamK { float* w; const float* g; float* m; float* v; __nv_bfloat16* wb; long long n; float alpha, b1, b2, eps, gs; };
 __global__ void adam_kernel(AdamK k) {
+  pdl_prologue();
   const long long n4 = k.n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 w = reinterpret_cast<float4*>(k.w)[i];
@@ -690,7 +692,7 @@ struct AdamLaunch : PreparedOp {
     int grid = grid_for(d.n / 4, 256);
     const int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
-    adam_kernel<<<grid, 256, 0, s>>>(k);
+    launch_k(adam_kernel, dim3(grid), dim3(256), 0, s, k);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -914,6 +916,7 @@ PreparedOp* prepare_head_bwd(const b2seg_head_desc* d) {
 
 // ------------------------------------------------------------------------------------------ loss seed
 __global__ void loss_kernel(b2seg_loss_desc d) {
+  pdl_prologue();
   const float* yp = reinterpret_cast<const float*>(d.y_pred);
   const float* yt = reinterpret_cast<const float*>(d.y_true);
   float* dl = reinterpret_cast<float*>(d.dlogits);
@@ -962,7 +965,7 @@ struct LossLaunch : PreparedOp {
   int launch(cudaStream_t s) override {
     int grid = grid_for(d.n_pix, 256);
     if (grid > 1024) grid = 1024;
-    loss_kernel<<<grid, 256, 0, s>>>(d);
+    launch_k(loss_kernel, dim3(grid), dim3(256), 0, s, d);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -976,6 +979,7 @@ PreparedOp* prepare_loss(const b2seg_loss_desc* d) {
 // ------------------------------------------------------------------------------------------ element-wise
 struct EltK { int op, act; DView a, b, c, out; };
 __global__ void eltwise_kernel(EltK k) {
+  pdl_prologue();
   const int cv = k.out.C / 8;
   const unsigned total = (unsigned)k.out.N * k.out.H * k.out.W * cv;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -1012,7 +1016,7 @@ struct EltLaunch : PreparedOp {
   EltK k;
   int launch(cudaStream_t s) override {
     const long long work = (long long)k.out.N * k.out.H * k.out.W * (k.out.C / 8);
-    eltwise_kernel<<<grid_for(work, 256), 256, 0, s>>>(k);
+    launch_k(eltwise_kernel, dim3(grid_for(work, 256)), dim3(256), 0, s, k);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }

@@ -36,6 +36,7 @@ struct WgCfg {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant__ WgradKParams p) {
   using Cfg = WgCfg<BLOCK_N>;
+  pdl_launch_dependents();   // the next kernel of the stream may become resident as SMs drain
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                // barriers / TMEM are set up; from here on global memory of earlier kernels is read
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int pair = p.taps[tap_i][0], dyh = p.taps[tap_i][1], dyw = p.taps[tap_i][2];
@@ -163,8 +165,7 @@ static int launch_wgrad_t(const WgradKParams& kp, int grid, cudaStream_t s) {
     B2_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  wgrad_kernel<BLOCK_N><<<grid, kWgThreads, Cfg::kSmemBytes, s>>>(kp);
-  B2_CUDA_OK(cudaGetLastError());
+  B2_CUDA_OK(launch_k(wgrad_kernel<BLOCK_N>, dim3(grid), dim3(kWgThreads), Cfg::kSmemBytes, s, kp));
   return 0;
 }
 

@@ -87,6 +87,7 @@ __host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) {   // m
 
 template <int KSTEPS>
 __global__ void __launch_bounds__(kWhThreads) wgrad_halo_kernel(const __grid_constant__ WhParams p) {
+  pdl_launch_dependents();   // the next kernel of the stream may become resident as SMs drain
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tail = smem + p.n_stages * p.stage_bytes;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kWhThreads) wgrad_halo_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                // barriers / TMEM are set up; from here on global memory of earlier kernels is read
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register for the MMA operands
 
   if (warp == 0) {
@@ -239,9 +241,8 @@ struct WgradHaloLaunch : PreparedOp {
       else B2_CUDA_OK(cudaFuncSetAttribute(wgrad_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       attr_bytes[which] = smem_bytes;
     }
-    if (which) wgrad_halo_kernel<8><<<grid, kWhThreads, smem_bytes, s>>>(kp);
-    else wgrad_halo_kernel<4><<<grid, kWhThreads, smem_bytes, s>>>(kp);
-    B2_CUDA_OK(cudaGetLastError());
+    if (which) B2_CUDA_OK(launch_k(wgrad_halo_kernel<8>, dim3(grid), dim3(kWhThreads), smem_bytes, s, kp));
+    else B2_CUDA_OK(launch_k(wgrad_halo_kernel<4>, dim3(grid), dim3(kWhThreads), smem_bytes, s, kp));
     return 0;
   }
 };
