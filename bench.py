@@ -265,8 +265,17 @@ def main():
         dom = max(("conv_gemm_kernel", "wgrad_kernel"), key=lambda k: agg.get(k, {"ms": 0})["ms"])
         a = agg[dom]
         achieved = a["flops"] / (a["ms"] / 1e3) / 1e12
+        # DRAM bytes per launch of the dominant family from the committed ncu capture of this same command (tools/launch_summary.py)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_launches_final.json")
+        if os.path.exists(tpath) and S == 256 and B == 32:
+            with open(tpath) as f:
+                tj = json.load(f)
+            key = "conv" if dom == "conv_gemm_kernel" else "wgrad"
+            traffic = tj[key]["dram_bytes_per_launch"]
+            traffic_src = f"profiles/r1_launches_final.json: ncu dram__bytes_read.sum + dram__bytes_write.sum over the {tj[key]['launches']} {key} launches of one step / launches"
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "peak_source": peak_src, "launches_per_step": a["launches"], "kernel_ms_per_step": a["ms"],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": a["launches"], "kernel_ms_per_step": a["ms"],
                 "kernel_share_of_step": a["ms"] / step_ms_ops,
                 "families": {k: {"ms_per_step": v["ms"], "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
                                  "launches": v["launches"]} for k, v in agg.items()},
@@ -275,9 +284,9 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        total, cores = oracle_train_step_time(2, S, 2, 1)
-        cpu = {"value": 2 * 2 / total, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"2 train steps of batch 2 at {S}x{S} after 1 warm-up (oracle: PyTorch-CPU fp32 restatement of the reference graph)"}
+        total, cores = oracle_train_step_time(4, S, 4, 1)
+        cpu = {"value": 4 * 4 / total, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"4 train steps of batch 4 at {S}x{S} after 1 warm-up (oracle: PyTorch-CPU fp32 restatement of the reference graph)"}
 
     if rank == 0:
         launches = sum(eng.launches)

@@ -16,6 +16,8 @@ from b2seg import lowering as lw  # noqa: E402
 # name, kind, N, H, W, Cin, Cout  (cfg2 at batch 32)
 SHAPES = [
     ("conv2d", "fprop", 32, 256, 256, 8, 64),
+    ("probe_64_64", "fprop", 32, 256, 256, 64, 64),
+    ("probe_16_64", "fprop", 32, 256, 256, 16, 64),
     ("conv2d_1", "fprop", 32, 128, 128, 64, 128),
     ("conv2d_2", "fprop", 32, 64, 64, 128, 256),
     ("conv2d_3", "fprop", 32, 32, 32, 256, 512),
@@ -66,7 +68,8 @@ def main():
             d = lw.conv_fprop(tv(x), w.data_ptr(), Cout, 3, 3, Cin, tv(out), bias=bias.data_ptr())
             rows = L.load().b2seg_conv_num_stat_rows(__import__("ctypes").byref(d))
             stats = torch.zeros(rows, 2, Cout, device=dev)
-            d.stats = stats.data_ptr()
+            if not os.environ.get("CONVBENCH_NO_STATS"):
+                d.stats = stats.data_ptr()
             fn, flops = "b2seg_conv", 2.0 * N * H * W * Cin * Cout * 9
         elif kind == "dgrad":
             dy = torch.randn(N, H, W, Cout, device=dev).to(torch.bfloat16)

@@ -17,10 +17,20 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kStgPitch = 144;                        // staging row pitch (64 bf16 + 16 B pad: conflict-free 16 B stores)
 constexpr int kStgBytes = kBlockM * kStgPitch;
-constexpr int kEpiWarps = 8;                          // two per TMEM lane quadrant: (quadrant, 32-column half)
+#ifndef B2_EPI_WARPS
+#define B2_EPI_WARPS 16
+#endif
+// Epilogue warps: kEpiWarps / 4 per TMEM lane quadrant, each converting kEpiCols of the 64 columns of a chunk.  ncu (source
+// view, profiles/r1_epilogue_stalls.txt): with 8 warps each scheduler holds 2 epilogue warps that issue one instruction
+// every ~5 clocks (stalls: fixed-latency dependencies 30 %, shared-memory scoreboard 18 %, barrier 9 %) -- latency-bound, so
+// the high-resolution layers took ~3300 clocks per 128x64 chunk whatever the MMA time.  16 warps double the warps per scheduler.
+constexpr int kEpiWarps = B2_EPI_WARPS;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
-constexpr int kColPartBytes = kEpiWarps * 64 * 2 * 4 + 256 * 4;  // [8 warps][64 cols][sum, sumsq] + bias tile [256]
+constexpr int kEpiCols = 64 / (kEpiWarps / 4);        // columns of a chunk converted by one warp: 32 (8 warps) or 16 (16 warps)
+constexpr int kEpiRows = kBlockM * 8 / kEpiThreads;   // rows per thread in the store pass: 4 or 2
+constexpr int kEpiRowStep = kEpiThreads / 8;          // 32 or 64
+constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
+constexpr int kColPartBytes = kEpiWarps * 64 * 2 * 4 + 256 * 4;  // [warps][64 cols][sum, sumsq] + bias tile [256]
 
 // everything the tile scheduler and the epilogue need (embedded as `e` in each kernel's parameter struct)
 struct ConvEpiParams {
@@ -83,10 +93,10 @@ __device__ __forceinline__ float act_t(float x) {
   return x;
 }
 
-template <int ACT>
-__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[32], uint32_t sb_addr, uint32_t (&packed)[16]) {
+template <int ACT, int NC>
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[NC], uint32_t sb_addr, uint32_t (&packed)[NC / 2]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NC / 4; ++j) {
     const uint4 braw = lds128(sb_addr + 16 * j);  // same address in every lane: shared-memory broadcast
     const float4 b = make_float4(__uint_as_float(braw.x), __uint_as_float(braw.y), __uint_as_float(braw.z), __uint_as_float(braw.w));
     const float x0 = act_t<ACT>(__uint_as_float(v[4 * j + 0]) + b.x);
@@ -97,8 +107,10 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[32], uint32_t 
     packed[2 * j + 1] = pack_bf16x2(x2, x3);
   }
 }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 
-// Runs on warps 2..9 (threads 64..319): warp w reads TMEM lanes 32*(w%4).. and the 32-column half (w-2)/4 of each chunk.  tfull/tempty: the two-deep TMEM accumulator hand-shake with the MMA warp.
+// Runs on warps 2.. (threads 64..): warp w reads TMEM lanes 32*(w%4).. and the kEpiCols-column slice (w-2)/4 of each chunk.  tfull/tempty: the two-deep TMEM accumulator hand-shake with the MMA warp.
 // scratch: kColPartBytes of shared memory.
 template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* staging, float* scratch, uint64_t* tfull_bar,
@@ -108,9 +120,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   float* sbias = scratch + kEpiWarps * 64 * 2; // [BLOCK_N]
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int et = threadIdx.x - 64;           // 0..255
-  const int ew = et >> 5;                    // epilogue warp 0..7
-  const int half = ew >> 2;                  // which 32 columns of each 64-column chunk this warp converts
+  const int et = threadIdx.x - 64;           // 0..kEpiThreads-1
+  const int ew = et >> 5;                    // epilogue warp
+  const int half = ew >> 2;                  // which kEpiCols columns of each 64-column chunk this warp converts
   const int row = (warp & 3) * 32 + lane;    // TMEM lane == tile row owned by this thread
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // kernel-invariant scalars (keep them in registers instead of re-reading the constant bank)
@@ -123,13 +135,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   const long long msn = p.mul_sn, msh = p.mul_sh, msw = p.mul_sw;
   const float* bias = p.bias;
   const uint32_t stg_addr = smem_u32(staging);
-  const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row (of 4, stride 32) of the store pass
+  const int vq = et & 7, r0 = et >> 3;       // this thread's 16-byte column slot and first row (of kEpiRows, stride kEpiRowStep) of the store pass
   // tile-invariant decomposition of this thread's rows
   const int mdn = row >> lbwh, mdh = (row >> lbw) & (bh - 1), mdw = row & (bw - 1);
-  int rel[4], mrel[4];                       // element offsets inside a tile: < 2^31 (checked by fill_epi_params)
+  int rel[kEpiRows], mrel[kEpiRows];         // element offsets inside a tile: < 2^31 (checked by fill_epi_params)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + 32 * i;
+  for (int i = 0; i < kEpiRows; ++i) {
+    const int r = r0 + kEpiRowStep * i;
     const int dn = r >> lbwh, dh = (r >> lbw) & (bh - 1), dw = r & (bw - 1);
     rel[i] = (int)(dn * osn + dh * osh + dw * osw);
     mrel[i] = (int)(dn * msn + dh * msh + dw * msw);
@@ -172,6 +184,22 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
       named_bar_sync(1, kEpiThreads);
     }
 
+    // dgrad fusion: the forward activations whose sign masks a chunk are fetched from global memory.  Chunk 0's loads are
+    // issued BEFORE waiting for the accumulator (their HBM latency hides behind the MMA main loop), later chunks' at the
+    // top of the chunk (overlapping the TMEM read).
+    uint4 yv[kEpiRows];
+    auto load_mask = [&](int col) {
+      const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(p.mul_ptr) + mtile_off + col;
+#pragma unroll
+      for (int i = 0; i < kEpiRows; ++i) {
+        const int r = r0 + kEpiRowStep * i;
+        const bool ok = tile_full || ((n0 + (r >> lbwh)) < gN && (h0 + ((r >> lbw) & (bh - 1))) < gH && (w0 + (r & (bw - 1))) < gW);
+        yv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 -> derivative 1
+        if (ok) yv[i] = __ldg(reinterpret_cast<const uint4*>(mb + mrel[i]));
+      }
+    };
+    if (mul_mode != 0 && n_tile * BLOCK_N + vq * 8 < mul_c) load_mask(n_tile * BLOCK_N + vq * 8);
+
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
 #pragma unroll
@@ -179,36 +207,25 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
       const int col0 = n_tile * BLOCK_N + c * 64;
       const int cc_st = col0 + vq * 8;
       const bool col_ok = cc_st < n_extent;
-      // dgrad fusion: fetch the forward activations whose sign masks this chunk early, so the loads overlap the TMEM read
-      uint4 yv[4];
       const bool do_mul = mul_mode != 0 && cc_st < mul_c;
-      if (do_mul) {
-        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(p.mul_ptr) + mtile_off + cc_st;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = r0 + 32 * i;
-          const bool ok = tile_full || ((n0 + (r >> lbwh)) < gN && (h0 + ((r >> lbw) & (bh - 1))) < gH && (w0 + (r & (bw - 1))) < gW);
-          yv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 -> derivative 1
-          if (ok) yv[i] = __ldg(reinterpret_cast<const uint4*>(mb + mrel[i]));
-        }
-      }
+      if (c > 0 && do_mul) load_mask(cc_st);
       {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_base + acc * BLOCK_N + c * 64 + half * 32, v);
+        uint32_t v[kEpiCols];
+        tmem_ld_cols(tmem_base + lane_base + acc * BLOCK_N + c * 64 + half * kEpiCols, v);
         tmem_ld_wait();
-        uint32_t packed[16];
-        const uint32_t sb = smem_u32(sbias + c * 64 + half * 32);
-        if (act == B2SEG_ACT_NONE) bias_act_pack<B2SEG_ACT_NONE>(v, sb, packed);
-        else if (act == B2SEG_ACT_RELU) bias_act_pack<B2SEG_ACT_RELU>(v, sb, packed);
-        else if (act == B2SEG_ACT_LEAKY) bias_act_pack<B2SEG_ACT_LEAKY>(v, sb, packed);
-        else bias_act_pack<B2SEG_ACT_SIGMOID>(v, sb, packed);
+        uint32_t packed[kEpiCols / 2];
+        const uint32_t sb = smem_u32(sbias + c * 64 + half * kEpiCols);
+        if (act == B2SEG_ACT_NONE) bias_act_pack<B2SEG_ACT_NONE, kEpiCols>(v, sb, packed);
+        else if (act == B2SEG_ACT_RELU) bias_act_pack<B2SEG_ACT_RELU, kEpiCols>(v, sb, packed);
+        else if (act == B2SEG_ACT_LEAKY) bias_act_pack<B2SEG_ACT_LEAKY, kEpiCols>(v, sb, packed);
+        else bias_act_pack<B2SEG_ACT_SIGMOID, kEpiCols>(v, sb, packed);
         if (!my_valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) packed[j] = 0u;
+          for (int j = 0; j < kEpiCols / 2; ++j) packed[j] = 0u;
         }
-        const uint32_t dst = stg_addr + row * kStgPitch + half * 64;
+        const uint32_t dst = stg_addr + row * kStgPitch + half * (kEpiCols * 2);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sts128(dst + 16 * q, make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]));
+        for (int q = 0; q < kEpiCols / 8; ++q) sts128(dst + 16 * q, make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]));
       }
       if (c == kChunks - 1) {
         // accumulator fully read: hand the TMEM buffer back to the MMA warp
@@ -223,8 +240,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
         for (int e = 0; e < 8; ++e) { s[e] = 0.f; q2[e] = 0.f; }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 32 * i;
+      for (int i = 0; i < kEpiRows; ++i) {
+        const int r = r0 + kEpiRowStep * i;
         uint4 val = lds128(stg_addr + r * kStgPitch + vq * 16);
         const bool ok = tile_full || ((n0 + (r >> lbwh)) < gN && (h0 + ((r >> lbw) & (bh - 1))) < gH && (w0 + (r & (bw - 1))) < gW);
         if (ok && col_ok) {
