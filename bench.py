@@ -178,6 +178,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # the backward kernels that overlap the gradient all-reduce leave B2SEG_BWD_SM_RESERVE SMs (default 16
+        # none 12.82, 24 -> 12.34, 16 -> 12.24 ms/step) to it; keep NCCL inside that budget (set before the communicator exists)
+        if int(os.environ.get("B2SEG_BWD_SM_RESERVE", "16")) > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("B2SEG_BWD_SM_RESERVE", "16"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, S = args.batch, args.size
     model = unet_model_builder("UNet", S, S, 64, 5, num_channels=3, output_nums=1, ds=0, ae=0, ag=0, lstm=0, dense_loop=1,
@@ -301,6 +305,8 @@ def main():
                         "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss")},
                 "gpu_launches": launches * args.steps, "launches_per_step": launches,
                 "device_memory_gb": eng.memory_bytes() / 2 ** 30}
+        if getattr(eng, "exchange_calibration", None):
+            line["exchange"] = eng.exchange_calibration
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

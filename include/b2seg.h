@@ -286,6 +286,9 @@ enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT,
        B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM };
 typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
 
+/* Data parallel: backward-phase ops added to a plan AFTER this call size their grids for (SMs - sms), leaving room for the
+ * CTAs of the gradient all-reduce that runs beside them (process-wide setting; 0 = use every SM). */
+int b2seg_set_backward_sm_reserve(int sms);
 int b2seg_plan_create(b2seg_plan** out);
 /* phase: 0 forward, 1 backward, 2 optimizer. desc is copied. */
 int b2seg_plan_add(b2seg_plan* p, int phase, int op, const void* desc, size_t desc_bytes);

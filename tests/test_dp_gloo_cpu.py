@@ -25,14 +25,15 @@ def _free_port():
     return p
 
 
-def _build(batch):
+def _build(batch, adam_bucket_bytes=0):
     from b2seg.graph import init_params
     from b2seg.models2d import unet_model_builder
     from b2seg.planner import Planner
     from desc_emulator import PlanMem
     g = unet_model_builder("UNet", 16, 16, 8, 2, num_channels=1, train_mode="from_scratch").build_graph()
     mem = PlanMem()
-    pl = Planner(g, batch, mem.alloc_bytes, training=True, losses=["bce"], adam=dict(lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    pl = Planner(g, batch, mem.alloc_bytes, training=True, losses=["bce"], adam=dict(lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-7),
+                 adam_bucket_bytes=adam_bucket_bytes).build()
     params = init_params(g, seed=3)
     for e in pl.params:
         flat = torch.from_numpy(pl.to_internal(e.key, params[e.key])).double()
@@ -71,7 +72,7 @@ def _worker(rank, world, port, out):
     from desc_emulator import run_phase
     x, y = _data()
     b, e = shard_range(x.shape[0], rank, world)
-    g, mem, pl = _build(e - b)
+    g, mem, pl = _build(e - b, adam_bucket_bytes=4096)   # data-parallel plan: one Adam op per exchange bucket
     xs, ys = x[b:e], y[b:e]
     mem.f32(pl.input_ptr, xs.numel())[:] = xs.reshape(-1).double()
     mem.f32(pl.outputs[0]["target_ptr"], ys.numel())[:] = ys.reshape(-1).double()
@@ -82,17 +83,19 @@ def _worker(rank, world, port, out):
     covered = sorted((lo, hi) for (_, lo, hi) in sched)
     assert covered[0][0] == 0 and covered[-1][1] == max(pl.n_train, 64) and all(a[1] == b_[0] for a, b_ in zip(covered, covered[1:]))
     done = 0
+    works = []
     for (n_ops, lo, hi) in sched:
         run_phase(mem, pl, 1, done, n_ops - done)
         done = n_ops
-        before = grads[lo:hi].clone()
-        wait_all(allreduce_flat_(grads[lo:hi]))
-        if world > 1 and rank == 0 and float(before.abs().max()) > 0:
-            assert not torch.equal(before, grads[lo:hi])
+        works.append(allreduce_flat_(grads[lo:hi]))
     run_phase(mem, pl, 1, done, len(pl.ops[1]) - done)
-    for (op, desc, _n) in pl.ops[2]:
+    # optimizer phase of a data-parallel plan: bucket i's Adam as soon as bucket i's all-reduce has landed (Model._step)
+    assert len(pl.ops[2]) == len(sched)
+    for i, ((op, desc, _n), (_ops, lo, hi)) in enumerate(zip(pl.ops[2], sched)):
+        assert desc.n == hi - lo and desc.g == pl.g_ptr + 4 * lo
         desc.grad_scale = 1.0 / world
-    run_phase(mem, pl, 2)
+        wait_all(works[i])
+        run_phase(mem, pl, 2, i, 1)
     torch.save(mem.f32(pl.w_ptr, max(pl.n_train, 64)).clone(), os.path.join(out, f"w{rank}.pt"))
     dist.destroy_process_group()
 

@@ -151,7 +151,7 @@ EXPORTED = ["b2seg_last_error", "b2seg_version", "b2seg_device_check", "b2seg_si
             "b2seg_head_bwd", "b2seg_loss", "b2seg_eltwise", "b2seg_cast_input", "b2seg_colsum", "b2seg_plan_create",
             "b2seg_resize_fwd", "b2seg_resize_bwd", "b2seg_mulbc_fwd", "b2seg_mulbc_bwd", "b2seg_colstats", "b2seg_lstm_fwd",
             "b2seg_lstm_bwd", "b2seg_pool_bwd", "b2seg_rowsum",
-            "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_run_range", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
+            "b2seg_set_backward_sm_reserve", "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_run_range", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
 
 _lib = None
 
@@ -184,6 +184,7 @@ def load():
     lib.b2seg_conv_num_stat_rows.argtypes = [C.POINTER(ConvDesc)]
     lib.b2seg_conv_num_stat_rows.restype = C.c_int
     lib.b2seg_device_check.argtypes = [C.c_int]
+    lib.b2seg_set_backward_sm_reserve.argtypes = [C.c_int]
     lib.b2seg_plan_create.argtypes = [C.POINTER(C.c_void_p)]
     lib.b2seg_plan_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.b2seg_plan_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]

@@ -7,6 +7,7 @@ There is no CPU fallback: constructing an Engine without a CUDA sm_100 device ra
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -20,7 +21,7 @@ from .planner import Planner
 class Engine:
     def __init__(self, graph: Graph, batch: int, training: bool = True, losses: Optional[List[str]] = None,
                  loss_weights: Optional[List[float]] = None, adam: Optional[dict] = None, device: Optional[int] = None,
-                 share_params_from: Optional["Engine"] = None):
+                 share_params_from: Optional["Engine"] = None, adam_bucket_bytes: int = 0):
         if not torch.cuda.is_available():
             raise L.B2SegError("b2seg needs a CUDA sm_100 (B200) device: the hot path has no CPU fallback")
         self.device = torch.cuda.current_device() if device is None else device
@@ -32,7 +33,9 @@ class Engine:
         self._shared = share_params_from
         self.dev = torch.device("cuda", self.device)
         self.planner = Planner(graph, batch, self._alloc, training=training, losses=losses, loss_weights=loss_weights, adam=adam,
-                               stat_rows_fn=lambda d: self.lib.b2seg_conv_num_stat_rows(C.byref(d))).build()
+                               stat_rows_fn=lambda d: self.lib.b2seg_conv_num_stat_rows(C.byref(d)),
+                               adam_bucket_bytes=adam_bucket_bytes).build()
+        self.adam_bucket_bytes = adam_bucket_bytes
         p = self.planner
         n = max(p.n_train, 64)
         self.w = self._typed("param_w", torch.float32, n)
@@ -52,13 +55,90 @@ class Engine:
             t = self._bufs[o["target_ptr"]].view(torch.float32)[:numel].view(o["shape"]) if training else None
             self.outputs.append(dict(name=o["name"], y=y, target=t, shape=o["shape"]))
         self.plan = C.c_void_p()
-        L.check(self.lib.b2seg_plan_create(C.byref(self.plan)), "plan_create")
-        for phase in (0, 1, 2):
-            for (op, desc, note) in p.ops[phase]:
-                rc = self.lib.b2seg_plan_add(self.plan, phase, op, C.byref(desc), C.sizeof(desc))
-                L.check(rc, f"plan_add[{note}]")
-        self.launches = [self.lib.b2seg_plan_num_launches(self.plan, ph) for ph in (0, 1, 2)]
+        self.reserved_ops = frozenset()
+        self._build_plan()
         self.step = 0
+
+    def _build_plan(self, reserved_ops=frozenset(), reserve_sms=0):
+        """(re)create the C plan; backward ops whose index is in reserved_ops size their grids for (SMs - reserve_sms)"""
+        if self.plan.value:
+            self.lib.b2seg_plan_destroy(self.plan)
+            self.plan = C.c_void_p()
+        L.check(self.lib.b2seg_plan_create(C.byref(self.plan)), "plan_create")
+        try:
+            for phase in (0, 1, 2):
+                for i, (op, desc, note) in enumerate(self.planner.ops[phase]):
+                    r = reserve_sms if (phase == 1 and i in reserved_ops) else 0
+                    L.check(self.lib.b2seg_set_backward_sm_reserve(r), "set_backward_sm_reserve")
+                    rc = self.lib.b2seg_plan_add(self.plan, phase, op, C.byref(desc), C.sizeof(desc))
+                    L.check(rc, f"plan_add[{note}]")
+        finally:
+            self.lib.b2seg_set_backward_sm_reserve(0)
+        self.reserved_ops, self.reserve_sms = frozenset(reserved_ops), reserve_sms
+        self.launches = [self.lib.b2seg_plan_num_launches(self.plan, ph) for ph in (0, 1, 2)]
+
+    def timed_phase(self, phase, reps=2):
+        """device time of every op of a phase in ms (CUDA events after each op; last of `reps` replays)"""
+        n_ops = self.lib.b2seg_plan_num_ops(self.plan, phase)
+        buf = (C.c_float * n_ops)()
+        for _ in range(reps):
+            L.check(self.lib.b2seg_plan_run_timed(self.plan, phase, C.c_void_p(self._stream()), buf, n_ops), "run_timed")
+        return [float(v) for v in buf]
+
+    def reserve_sms_for_exchange(self, schedule, group=None, reserve_sms=None):
+        """Data parallel.  Every tensor-core kernel here is persistent with one CTA per SM and a static tile split, so the SMs
+        the all-reduce's CTAs hold while it runs turn each concurrent launch into two waves (measured at 8 GPUs with NVLS'
+        24 CTAs: +1.5 ms per step).  Decide WHICH backward ops overlap the gradient exchange and give only those a grid of
+        (SMs - reserve): time the backward ops and one all-reduce once, replay the exchange schedule on those numbers
+        (bucket j starts when its last producer op has finished and the wire is free), and rebuild the plan.  The timing
+        replays run on whatever the buffers hold; kernel times do not depend on the data."""
+        import torch.distributed as dist
+        if reserve_sms is None:
+            reserve_sms = int(os.environ.get("B2SEG_BWD_SM_RESERVE", "16"))
+        if reserve_sms <= 0 or not schedule:
+            return
+        ms = self.timed_phase(1)
+        # wire speed: the largest bucket, twice, second one timed
+        (_n, lo, hi) = max(schedule, key=lambda b: b[2] - b[1])
+        probe = torch.zeros(hi - lo, dtype=torch.float32, device=self.dev)
+        dist.all_reduce(probe, group=group)
+        torch.cuda.synchronize(self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(probe, group=group)
+        e1.record()
+        torch.cuda.synchronize(self.dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)    # every rank must take the same decision
+        ms_per_byte = float(t.item()) / ((hi - lo) * 4)
+        tms = torch.tensor(ms, device=self.dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX, group=group)
+        ms = [float(v) for v in tms.tolist()]
+        self.exchange_calibration = {"allreduce_GBps": 1e-6 / ms_per_byte, "backward_ms": sum(ms)}
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        slow = sms / float(sms - reserve_sms)
+        reserved = set()
+        for _ in range(3):   # reserved ops run slower, which moves the windows: iterate to a fixed point
+            end, t_acc = [], 0.0
+            for i, d in enumerate(ms):
+                t_acc += d * (slow if i in reserved else 1.0)
+                end.append(t_acc)
+            busy, windows = 0.0, []
+            for (n_ops, lo, hi) in schedule:
+                start = max(end[n_ops - 1] if n_ops > 0 else 0.0, busy)
+                busy = start + 0.03 + (hi - lo) * 4 * ms_per_byte
+                windows.append((start, busy))
+            new = set()
+            for i in range(len(ms)):
+                s_i, e_i = (end[i - 1] if i else 0.0), end[i]
+                if any(s_i < w1 + 0.05 and e_i > w0 - 0.05 for (w0, w1) in windows):
+                    new.add(i)
+            if new == reserved:
+                break
+            reserved = new
+        self.exchange_calibration["reserved_ops"] = len(reserved)
+        self.exchange_calibration["exchange_windows_ms"] = [(round(a, 3), round(b, 3)) for (a, b) in windows]
+        self._build_plan(reserved, reserve_sms)
 
     # ---- memory ------------------------------------------------------------------------------------------
     def _alloc(self, nbytes, tag):
@@ -128,9 +208,12 @@ class Engine:
     def backward(self):
         self.run(1)
 
-    def optimizer_step(self, lr: float, grad_scale: float = 1.0):
+    def optimizer_begin(self, lr: float, grad_scale: float = 1.0):
         self.step += 1
         L.check(self.lib.b2seg_plan_set_adam(self.plan, lr, self.step, grad_scale), "set_adam")
+
+    def optimizer_step(self, lr: float, grad_scale: float = 1.0):
+        self.optimizer_begin(lr, grad_scale)
         self.run(2)
 
     def tap(self, name: str, grad=False) -> torch.Tensor:

@@ -184,11 +184,21 @@ class Model:
                     raise RuntimeError("You must compile your model before training/testing. Use `model.compile(optimizer, loss)`.")
                 o = self.optimizer
                 adam = dict(lr=o.learning_rate, beta1=o.beta_1, beta2=o.beta_2, eps=o.epsilon)
+            bucket = 0
+            if training:
+                # data parallel (a process group exists when the engine is built): one Adam op per exchange bucket
+                import torch.distributed as dist
+                if self.world_size > 1 or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+                    bucket = self.exchange_bucket_bytes
             eng = Engine(self.graph, batch, training=training, losses=self._losses, loss_weights=self._loss_weights, adam=adam,
-                         share_params_from=self._primary)
+                         share_params_from=self._primary, adam_bucket_bytes=bucket)
             if self._primary is None:
                 self._primary = eng
                 eng.set_weights(self._weights)
+            if bucket:
+                import torch.distributed as dist
+                if dist.get_backend(getattr(self, "_pg", None)) == "nccl":
+                    eng.reserve_sms_for_exchange(eng.planner.exchange_schedule(self.exchange_bucket_bytes), group=getattr(self, "_pg", None))
             self._engines[key] = eng
         return self._engines[key]
 
@@ -267,8 +277,17 @@ class Model:
             n_total = eng.planner.num_launch_ops(1)
             if n_total > done:
                 eng.run_range(1, done, n_total - done)
-            wait_all(works)
             scale = 1.0 / self.world_size
+            if eng.adam_bucket_bytes == self.exchange_bucket_bytes and len(eng.planner.ops[2]) == len(works):
+                # bucket i's Adam runs as soon as ITS all-reduce has landed; the later buckets are still on the wire
+                eng.optimizer_begin(self.optimizer.learning_rate, scale)
+                for i, w in enumerate(works):
+                    w.wait()
+                    eng.run_range(2, i, 1)
+                if return_loss:
+                    return float(eng.loss_buf.item())
+                return None
+            wait_all(works)
         else:
             eng.backward()
         eng.optimizer_step(self.optimizer.learning_rate, scale)

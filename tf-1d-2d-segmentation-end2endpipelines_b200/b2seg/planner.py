@@ -150,8 +150,11 @@ LOSS_KINDS = {"bce": 0, "binary_crossentropy": 0, "cce": 1, "categorical_crossen
 class Planner:
     def __init__(self, graph: Graph, batch: int, alloc: Callable[[int], int], training: bool = True,
                  losses: Optional[List[str]] = None, loss_weights: Optional[List[float]] = None, adam=None,
-                 stat_rows_fn: Optional[Callable] = None):
+                 stat_rows_fn: Optional[Callable] = None, adam_bucket_bytes: int = 0):
         self.stat_rows_fn = stat_rows_fn or conv_stat_rows
+        # > 0 (data parallel): the optimizer phase is one Adam op per gradient-exchange bucket, in exchange order, so the
+        # update of a bucket can run as soon as ITS all-reduce has landed while later buckets are still on the wire
+        self.adam_bucket_bytes = adam_bucket_bytes
         self.g = graph
         self.N = batch
         self.alloc_fn = alloc
@@ -475,8 +478,13 @@ class Planner:
                 for key in self._grad_touched:
                     self.grad_ready[key] = len(self.ops[1])
             a = self.adam
-            self.emit(2, L.OP_ADAM, L.AdamDesc(self.w_ptr, self.g_ptr, self.m_ptr, self.v_ptr, self.wb_ptr, max(self.n_train, 64),
-                                               a["lr"], a["beta1"], a["beta2"], a["eps"], 1.0, 1), "adam")
+            ranges = [(0, max(self.n_train, 64))]
+            if self.adam_bucket_bytes > 0:
+                ranges = [(lo, hi) for (_n, lo, hi) in self.exchange_schedule(self.adam_bucket_bytes)]
+            for (lo, hi) in ranges:
+                self.emit(2, L.OP_ADAM, L.AdamDesc(self.w_ptr + 4 * lo, self.g_ptr + 4 * lo, self.m_ptr + 4 * lo, self.v_ptr + 4 * lo,
+                                                   self.wb_ptr + 2 * lo, hi - lo, a["lr"], a["beta1"], a["beta2"], a["eps"], 1.0, 1),
+                          "adam" if len(ranges) == 1 else f"adam [{lo}, {hi})")
         return self
 
     # -- destinations: where a produced tensor must live ------------------------------------------------------
