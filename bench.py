@@ -178,8 +178,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # the backward kernels that overlap the gradient all-reduce leave B2SEG_BWD_SM_RESERVE SMs (default 16
-        # none 12.82, 24 -> 12.34, 16 -> 12.24 ms/step) to it; keep NCCL inside that budget (set before the communicator exists)
+        # the backward kernels that overlap the gradient all-reduce leave B2SEG_BWD_SM_RESERVE SMs to it (default 16; measured
+        # at 8 GPUs: no reserve 12.82, 24 -> 12.34, 16 -> 12.24 ms/step); keep NCCL inside that budget (the variable must be
+        # set before the communicator exists)
         if int(os.environ.get("B2SEG_BWD_SM_RESERVE", "16")) > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("B2SEG_BWD_SM_RESERVE", "16"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
