@@ -196,6 +196,62 @@ def test_unet2d_cfg2_graph_per_layer():
     check_per_layer(m, Ref2D("UNet", 64, 64, 64, 5, **kw), 2, x, [y], ["bce"])
 
 
+def test_unet2d_cfg2_full_resolution_per_layer():
+    """BASELINE config 2 at its full 256x256x3 resolution (batch 2 so the float64 oracle finishes in seconds): the high-resolution
+    layers take the halo-tile kernels with resident weights, register statistics and the fused bias-gradient path"""
+    kw = dict(num_channels=3, output_nums=1, dense_loop=1, is_transconv=True)
+    m = unet_model_builder("UNet", 256, 256, 64, 5, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 256, 256, 3), dtype=np.float32)
+    y = (rng.random((2, 256, 256, 1)) > 0.7).astype(np.float32)
+    check_per_layer(m, Ref2D("UNet", 256, 256, 64, 5, **kw), 2, x, [y], ["bce"])
+
+
+def test_unet2d_cfg2_full_size_properties():
+    """BASELINE config 2 at full size (256x256x3, batch 32 — the bench workload), checked through size-independent properties:
+    (1) samples are independent at inference (moving statistics): predicting a batch == predicting its halves, bit for bit;
+    (2) the forward pass is deterministic (two replays give identical bits);
+    (3) gradients are linear in the loss weight: loss_weights=[2] doubles every parameter gradient (the fp32 accumulation order
+        of the split-K weight gradients and of the red.add BatchNorm statistics is not fixed, and a changed last bit of a
+        statistic moves every bf16 rounding downstream: measured 4e-5, asserted 2e-4, instead of bit equality);
+    (4) conv biases that feed a BatchNormalization get exactly zero gradient;
+    (5) three Adam steps reduce the loss and keep it finite."""
+    kw = dict(num_channels=3, output_nums=1, dense_loop=1, is_transconv=True)
+    rng = np.random.default_rng(7)
+    x = rng.random((32, 256, 256, 3), dtype=np.float32)
+    y = (rng.random((32, 256, 256, 1)) > 0.7).astype(np.float32)
+    m = unet_model_builder("UNet", 256, 256, 64, 5, train_mode="from_scratch", **kw).ResNet50()
+    m.compile(loss="binary_crossentropy", optimizer=Adam(2e-4))
+    p_full = m.predict(x, batch_size=32)
+    assert p_full.shape == (32, 256, 256, 1) and np.isfinite(p_full).all() and p_full.min() >= 0 and p_full.max() <= 1
+    assert np.array_equal(p_full[:16], m.predict(x[:16], batch_size=16))          # (1)
+    assert np.array_equal(p_full, m.predict(x, batch_size=32))                    # (2)
+
+    def grads(model):
+        eng = model._engine(32, True)
+        eng.x_dev.copy_(torch.from_numpy(x))
+        eng.outputs[0]["target"].copy_(torch.from_numpy(y))
+        eng.forward()
+        eng.backward()
+        torch.cuda.synchronize()
+        return eng, eng.g.clone()
+
+    eng, g1 = grads(m)
+    m2 = unet_model_builder("UNet", 256, 256, 64, 5, train_mode="from_scratch", **kw).ResNet50()
+    m2.compile(loss="binary_crossentropy", optimizer=Adam(2e-4), loss_weights=[2.0])
+    m2.set_weight_dict(m.get_weight_dict())
+    _, g2 = grads(m2)
+    assert float(g1.abs().max()) > 0 and rel_l2(g2, 2.0 * g1) < 2e-4              # (3)
+    del m2
+    pl = eng.planner
+    bn_convs = {u["node"].name for u in pl.units if u["kind"] == "conv" and u["bn"] is not None}
+    for e in pl.params:
+        if e.trainable and e.key.endswith("/bias") and e.key.rsplit("/", 1)[0] in bn_convs:
+            assert float(g1[e.offset:e.offset + e.size].abs().max()) == 0.0, e.key  # (4)
+    losses = [m.train_on_batch(x, y) for _ in range(3)]
+    assert all(np.isfinite(l) for l in losses) and losses[-1] < losses[0], losses   # (5)
+
+
 def test_unet1d_cfg1_graph_per_layer():
     """BASELINE config 1: 1D UNet depth 5 width 64, 1 channel, 1024 samples, classification head (2 classes)"""
     m = UNet(1024, 5, 1, 64, 3, problem_type="Classification", output_nums=2, ds=0, is_transconv=True).UNet()

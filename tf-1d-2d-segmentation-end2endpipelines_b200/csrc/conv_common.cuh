@@ -30,7 +30,8 @@ constexpr int kEpiCols = 64 / (kEpiWarps / 4);        // columns of a chunk conv
 constexpr int kEpiRows = kBlockM * 8 / kEpiThreads;   // rows per thread in the store pass: 4 or 2
 constexpr int kEpiRowStep = kEpiThreads / 8;          // 32 or 64
 constexpr int kConvThreads = 64 + kEpiThreads;        // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
-constexpr int kColPartBytes = kEpiWarps * 64 * 2 * 4 + 256 * 4;  // [warps][64 cols][sum, sumsq] + bias tile [256]
+constexpr int kTileInfoBytes = 48;                    // per-tile scalars computed once by one epilogue thread (two slots)
+constexpr int kColPartBytes = kEpiWarps * 64 * 2 * 4 + 256 * 4 + 2 * kTileInfoBytes + 32;  // [warps][64 cols][sum, sumsq] + bias tile [256] + tile info
 
 // everything the tile scheduler and the epilogue need (embedded as `e` in each kernel's parameter struct)
 struct ConvEpiParams {
@@ -163,18 +164,42 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   for (int c = 0; c < kChunks; ++c) { cta_s[c] = 0.f; cta_q[c] = 0.f; }
   if (n_tiles == 1) {                         // one column range for the whole kernel: stage the bias once
     for (int i = et; i < BLOCK_N; i += kEpiThreads) sbias[i] = (bias != nullptr && i < n_extent) ? __ldg(bias + i) : 0.f;
-    named_bar_sync(1, kEpiThreads);
   }
+  // Per-tile scalars (tile coordinates, 64-bit output / mask offsets, "tile lies fully inside the image").  ncu's source view
+  // showed every epilogue warp spending ~100 of its ~350 instructions per tile on recomputing them (profiles/
+  // r1_epilogue_stalls.txt), which is what bounds the thin high-resolution layers.  One thread now computes them for the
+  // NEXT tile while the others wait for the accumulator, and publishes them in shared memory (two slots; the named
+  // barriers of the chunk loop order the write of slot i+1 against its readers).
+  const uint32_t tinfo = smem_u32(scratch + kEpiWarps * 64 * 2 + 256 + 4) & ~15u;
+  auto publish_tile = [&](int tile, int slot) {
+    const TileCoord tc = tile_coord(p, tile);
+    const bool full = (tc.n0 + bn <= gN) && (tc.h0 + bh <= gH) && (tc.w0 + bw <= gW);
+    const unsigned long long ob = p.out_ptr[tc.g] + 2ull * (unsigned long long)(tc.n0 * osn + tc.h0 * osh + tc.w0 * osw);
+    const unsigned long long mo = (unsigned long long)(tc.n0 * msn + tc.h0 * msh + tc.w0 * msw);
+    const uint32_t a = tinfo + slot * kTileInfoBytes;
+    sts128(a, make_uint4((uint32_t)ob, (uint32_t)(ob >> 32), (uint32_t)mo, (uint32_t)(mo >> 32)));
+    sts128(a + 16, make_uint4((uint32_t)tc.n_tile, (uint32_t)(tc.g * m_tiles + tc.m_tile), full ? 1u : 0u, 0u));
+    sts128(a + 32, make_uint4((uint32_t)tc.n0, (uint32_t)tc.h0, (uint32_t)tc.w0, 0u));
+  };
   uint32_t acc = 0, acc_phase = 0;
   const TileRange tr = tile_range(p);
-  for (int tile = tr.first; tile < tr.end; tile += tr.step) {
-    const TileCoord tc = tile_coord(p, tile);
-    const int n_tile = tc.n_tile, m_tile = tc.m_tile, g = tc.g, w0 = tc.w0, h0 = tc.h0, n0 = tc.n0;
-    const bool tile_full = (n0 + bn <= gN) && (h0 + bh <= gH) && (w0 + bw <= gW);
+  const bool publisher = et == kEpiThreads - 1;
+  if (publisher && tr.first < tr.end) publish_tile(tr.first, 0);
+  named_bar_sync(1, kEpiThreads);             // bias tile and the first tile's scalars are visible
+  uint32_t slot = 0;
+  for (int tile = tr.first; tile < tr.end; tile += tr.step, slot ^= 1) {
+    if (publisher && tile + tr.step < tr.end) publish_tile(tile + tr.step, slot ^ 1);
+    const uint4 ti0 = lds128(tinfo + slot * kTileInfoBytes), ti1 = lds128(tinfo + slot * kTileInfoBytes + 16);
+    __nv_bfloat16* const out_base = reinterpret_cast<__nv_bfloat16*>(((unsigned long long)ti0.y << 32) | ti0.x);
+    const long long mtile_off = (long long)(((unsigned long long)ti0.w << 32) | ti0.z);
+    const int n_tile = (int)ti1.x, stat_row = (int)ti1.y;
+    const bool tile_full = ti1.z != 0;
+    int n0 = 0, h0 = 0, w0 = 0;
+    if (!tile_full) {
+      const uint4 ti2 = lds128(tinfo + slot * kTileInfoBytes + 32);
+      n0 = (int)ti2.x; h0 = (int)ti2.y; w0 = (int)ti2.z;
+    }
     const bool my_valid = tile_full || ((n0 + mdn) < gN && (h0 + mdh) < gH && (w0 + mdw) < gW);
-    const long long tile_off = n0 * osn + h0 * osh + w0 * osw;
-    const long long mtile_off = n0 * msn + h0 * msh + w0 * msw;
-    __nv_bfloat16* const out_base = reinterpret_cast<__nv_bfloat16*>(p.out_ptr[g]) + tile_off;
     if (n_tiles > 1) {
       named_bar_sync(1, kEpiThreads);         // previous tile's readers of sbias are done
       for (int i = et; i < BLOCK_N; i += kEpiThreads) {
@@ -306,7 +331,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
             cta_s[c] += s2;
             cta_q[c] += ss2;
           } else if (col0 + et < n_extent) {
-            float* st = p.stats + (size_t)(g * m_tiles + m_tile) * 2 * n_extent;
+            float* st = p.stats + (size_t)stat_row * 2 * n_extent;
             st[col0 + et] = s2;
             st[n_extent + col0 + et] = ss2;
           }

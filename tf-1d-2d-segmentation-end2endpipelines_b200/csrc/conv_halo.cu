@@ -118,10 +118,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
           // pull the halo tiles this CTA needs two tiles from now into L2 (each activation byte is read from HBM once,
           // so without this every A stage pays full HBM latency with only two stages in flight)
           const int ptile = tile + 2 * tr.step;
-          if (ptile < tr.end && (e.n_tiles == 1 || (ptile % e.n_tiles) == 0)) {
-            const int prest = ptile / e.n_tiles;
-            const int pm = prest % e.m_tiles, pg = prest / e.m_tiles;
-            const int pw0 = (pm % e.tiles_w) * e.bw, ph0 = ((pm / e.tiles_w) % e.tiles_h) * e.bh, pn0 = (pm / (e.tiles_w * e.tiles_h)) * e.bn;
+          if (ptile < tr.end) {
+            // (magic-number divisions: this single thread's per-tile latency is the floor of the whole kernel on the thin
+            // high-resolution layers — with plain / and % it was ~3300 clocks per tile whatever K and the epilogue cost)
+            const TileCoord pc = tile_coord(e, ptile);
+            const int pg = pc.g, pw0 = pc.w0, ph0 = pc.h0, pn0 = pc.n0;
+            if (e.n_tiles == 1 || pc.n_tile == 0)
             for (int wi = 0; wi < p.wins_per_group; ++wi) {
               const HaloWin win = p.wins[pg * p.wins_per_group + wi];
               for (int cb = 0; cb < p.kc_blocks; ++cb) tma_prefetch_4d(&p.amap[win.map], cb * kBlockK, pw0 + win.ow0, ph0 + win.oh0, pn0);
