@@ -289,6 +289,8 @@ typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_d
 /* Data parallel: backward-phase ops added to a plan AFTER this call size their grids for (SMs - sms), leaving room for the
  * CTAs of the gradient all-reduce that runs beside them (process-wide setting; 0 = use every SM). */
 int b2seg_set_backward_sm_reserve(int sms);
+/* debug aid: with B2SEG_TRACE=1 in the environment, CTA 0 of a halo-tile convolution records clock64() stamps per tile */
+int b2seg_debug_read_trace(uint64_t* out, int n);
 int b2seg_plan_create(b2seg_plan** out);
 /* phase: 0 forward, 1 backward, 2 optimizer. desc is copied. */
 int b2seg_plan_add(b2seg_plan* p, int phase, int op, const void* desc, size_t desc_bytes);

@@ -107,6 +107,17 @@ def main():
         lib.b2seg_plan_destroy(plan)
         ms = e0.elapsed_time(e1) / reps
         print(f"{name:<18}{kind:<7} N{N} {H}x{W} {Cin}->{Cout}  {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s", flush=True)
+        if os.environ.get("B2SEG_TRACE") and fn == "b2seg_conv":
+            # per-tile clock64() stamps of CTA 0 (include/b2seg.h: b2seg_debug_read_trace), relative to the first stamp
+            buf = (C.c_uint64 * (48 * 8))()
+            lib.b2seg_debug_read_trace.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+            if lib.b2seg_debug_read_trace(buf, 48 * 8) > 0:
+                t = [[int(buf[i * 8 + j]) for j in range(8)] for i in range(48)]
+                base = min(v for row in t for v in row[:7] if v)
+                print("  tile | mma: acc free, A landed, issued | producer TMA | epi: acc full, tmem read, done   (clocks since start)")
+                for i in range(8, 24):
+                    r = [v - base if v else -1 for v in t[i][:7]]
+                    print(f"  {i:4d} | {r[0]:8d} {r[1]:8d} {r[2]:8d} | {r[3]:8d} | {r[4]:8d} {r[5]:8d} {r[6]:8d}")
 
 
 if __name__ == "__main__":

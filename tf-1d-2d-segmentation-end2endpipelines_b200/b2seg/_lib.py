@@ -151,7 +151,7 @@ EXPORTED = ["b2seg_last_error", "b2seg_version", "b2seg_device_check", "b2seg_si
             "b2seg_head_bwd", "b2seg_loss", "b2seg_eltwise", "b2seg_cast_input", "b2seg_colsum", "b2seg_plan_create",
             "b2seg_resize_fwd", "b2seg_resize_bwd", "b2seg_mulbc_fwd", "b2seg_mulbc_bwd", "b2seg_colstats", "b2seg_lstm_fwd",
             "b2seg_lstm_bwd", "b2seg_pool_bwd", "b2seg_rowsum",
-            "b2seg_set_backward_sm_reserve", "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_run_range", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
+            "b2seg_set_backward_sm_reserve", "b2seg_debug_read_trace", "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_run_range", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
 
 _lib = None
 

@@ -238,6 +238,11 @@ int b2seg_conv_num_stat_rows(const b2seg_conv_desc* d) {
   return b2::conv_num_stat_rows(d);
 }
 
+// debug aid (B2SEG_TRACE=1): per-tile clock64() stamps of CTA 0 of the last conv_halo launch, [tile][8] =
+// {mma: accumulator free, first A tile landed, all MMAs issued; producer: first TMA issued; epilogue: accumulator full,
+//  TMEM read done, tile finished, unused}
+int b2seg_debug_read_trace(uint64_t* out, int n) { return b2::read_halo_trace(reinterpret_cast<unsigned long long*>(out), n); }
+
 int b2seg_set_backward_sm_reserve(int sms) {
   if (sms < 0 || sms > 64) return b2::fail(B2SEG_ERR_ARG, "backward SM reserve must be in 0..64");
   b2::g_bwd_sm_reserve = sms;

@@ -87,6 +87,7 @@ PreparedOp* prepare_pool_bwd(const b2seg_poolbwd_desc* d);
 void adam_update(PreparedOp* op, float lr, int64_t step, float grad_scale);
 bool is_adam(PreparedOp* op);
 
+int read_halo_trace(unsigned long long* out, int n);   // conv_halo.cu (debug)
 int conv_num_mtiles(const b2seg_conv_desc* d);
 int conv_num_stat_rows(const b2seg_conv_desc* d);
 

@@ -50,6 +50,7 @@ struct ConvEpiParams {
   int mul_mode, mul_c;
   int lbw, lbwh;       // log2(bw), log2(bw*bh): tile rows -> pixel coordinates by shifts
   int stats_per_cta;   // 1: one statistics row per CTA (n_tiles == 1), else one per (group, m_tile)
+  unsigned long long* trace;   // debug (B2SEG_TRACE=1): per-tile clock64() stamps of CTA 0, [tile][8]
   int cta_groups;      // G > 1: CTA b only walks the tiles of group b % G (its weights stay resident in shared memory); gridDim.x % G == 0
   FastDiv fd_n_tiles, fd_m_tiles, fd_tiles_w, fd_tiles_h;   // tile index -> coordinates without integer division
 };
@@ -187,6 +188,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
   if (publisher && tr.first < tr.end) publish_tile(tr.first, 0);
   named_bar_sync(1, kEpiThreads);             // bias tile and the first tile's scalars are visible
   uint32_t slot = 0;
+  int trace_it = 0;
   for (int tile = tr.first; tile < tr.end; tile += tr.step, slot ^= 1) {
     if (publisher && tile + tr.step < tr.end) publish_tile(tile + tr.step, slot ^ 1);
     const uint4 ti0 = lds128(tinfo + slot * kTileInfoBytes), ti1 = lds128(tinfo + slot * kTileInfoBytes + 16);
@@ -227,6 +229,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
 
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0 && et == 0 && trace_it < 48;
+    if (tracing) p.trace[trace_it * 8 + 4] = (unsigned long long)clock64();
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
       const int col0 = n_tile * BLOCK_N + c * 64;
@@ -238,6 +242,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
         uint32_t v[kEpiCols];
         tmem_ld_cols(tmem_base + lane_base + acc * BLOCK_N + c * 64 + half * kEpiCols, v);
         tmem_ld_wait();
+        if (tracing && c == 0) p.trace[trace_it * 8 + 5] = (unsigned long long)clock64();
         uint32_t packed[kEpiCols / 2];
         const uint32_t sb = smem_u32(sbias + c * 64 + half * kEpiCols);
         if (act == B2SEG_ACT_NONE) bias_act_pack<B2SEG_ACT_NONE, kEpiCols>(v, sb, packed);
@@ -341,6 +346,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
     }
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
+    if (tracing) p.trace[trace_it * 8 + 6] = (unsigned long long)clock64();
+    ++trace_it;
   }
   if (persist) {
 #pragma unroll

@@ -23,6 +23,8 @@ constexpr int kHaloMaxBStages = 16;
 constexpr int kHaloMaxWins = 16;
 constexpr int kHaloSmemBudget = 232448;     // 227 KiB
 
+__device__ unsigned long long g_halo_trace[48 * 8];
+
 struct HaloWin { int map, oh0, ow0, tap_begin, tap_end, pad0, pad1, pad2; };
 
 struct alignas(64) HaloKParams {
@@ -130,10 +132,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             }
           }
         }
+        const int p_it = (tile - tr.first) / tr.step;
         for (int wi = 0; wi < p.wins_per_group; ++wi) {
           const HaloWin win = p.wins[g * p.wins_per_group + wi];
           for (int cb = 0; cb < p.kc_blocks; ++cb) {
             mbar_wait(&emptyA[sa], pa ^ 1);
+            if (e.trace && blockIdx.x == 0 && p_it < 48 && wi == 0 && cb == 0) e.trace[p_it * 8 + 3] = (unsigned long long)clock64();
             mbar_arrive_expect_tx(&fullA[sa], p.a_bytes);
             tma_load_4d(&p.amap[win.map], &fullA[sa], sA + sa * kHaloABytes, cb * kBlockK, w0 + win.ow0, h0 + win.oh0, n0);
             if (++sa == (uint32_t)a_stages) { sa = 0; pa ^= 1; }
@@ -168,6 +172,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       const uint64_t adesc0 = make_smem_desc(0, 16, p.sbo);
       const uint64_t bdesc0 = B_MN ? make_smem_desc(0, 8192, 1024) : make_smem_desc(0, 16, 1024);
       const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+      const uint32_t ad_lo0 = (uint32_t)adesc0, ad_hi = (uint32_t)(adesc0 >> 32), bd_lo0 = (uint32_t)bdesc0, bd_hi = (uint32_t)(bdesc0 >> 32);
+      const int ww_ = p.ww;
       const int wins_per_group = p.wins_per_group, kc_blocks = p.kc_blocks, b_stages = p.b_stages, k16_last = p.k16_last;
       uint32_t sa = 0, pa = 0, sb_i = 0, pb = 0, acc = 0, acc_phase = 0;
       if (B_RES) {
@@ -179,6 +185,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         const int g = (int)fast_div(fast_div((uint32_t)tile, e.fd_n_tiles), e.fd_m_tiles);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        const int m_it = (tile - tr.first) / tr.step;
+        const bool mtrace = e.trace != nullptr && blockIdx.x == 0 && lane == 0 && m_it < 48;
+        if (mtrace) e.trace[m_it * 8 + 0] = (unsigned long long)clock64();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         uint32_t accumulate = 0;
         uint32_t res16 = sB16;
@@ -187,28 +196,33 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
           for (int cb = 0; cb < kc_blocks; ++cb) {
             mbar_wait(&fullA[sa], pa);
             tc_fence_after();
-            const uint64_t ad_stage = adesc0 + (sA16 + sa * (kHaloABytes >> 4));
+            if (mtrace && wi == 0 && cb == 0) e.trace[m_it * 8 + 1] = (unsigned long long)clock64();
+            const uint32_t ad_stage = ad_lo0 + (sA16 + sa * (kHaloABytes >> 4));
+            // the tap's start row inside the halo tile is fetched one tap AHEAD (an indexed constant load feeding a chain
+            // of dependent uniform-datapath ops was ~265 clocks per tap: more than the 4 MMAs of an N <= 128 tap take)
+            uint32_t off_next = (uint32_t)(p.taps[tap_begin].x * ww_ + p.taps[tap_begin].y) * 8u;
             for (int t = tap_begin; t < tap_end; ++t) {
-              const uint32_t off = (uint32_t)(p.taps[t].x * p.ww + p.taps[t].y) * 8u;   // start row of the tap inside the halo tile
-              uint64_t bd;
+              const uint32_t off = off_next;
+              if (t + 1 < tap_end) off_next = (uint32_t)(p.taps[t + 1].x * ww_ + p.taps[t + 1].y) * 8u;
+              uint32_t bd;
               if (B_RES) {
-                bd = bdesc0 + res16;
+                bd = bd_lo0 + res16;
                 res16 += kBStageBytes >> 4;
               } else {
                 mbar_wait(&fullB[sb_i], pb);
                 tc_fence_after();
-                bd = bdesc0 + (sB16 + sb_i * (kBStageBytes >> 4));
+                bd = bd_lo0 + (sB16 + sb_i * (kBStageBytes >> 4));
               }
-              const uint64_t ad = ad_stage + off;
+              const uint32_t ad = ad_stage + off;
               if (cb + 1 < kc_blocks || k16_last == kBlockK / 16) {
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
-                  umma_bf16_elect(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
+                  umma_bf16_elect_lh(d_tmem, ad + k * 2, ad_hi, bd + k * (B_MN ? 128 : 2), bd_hi, idesc, accumulate);
                   accumulate = 1;
                 }
               } else {
                 for (int k = 0; k < k16_last; ++k) {
-                  umma_bf16_elect(d_tmem, ad + k * 2, bd + k * (B_MN ? 128 : 2), idesc, accumulate);
+                  umma_bf16_elect_lh(d_tmem, ad + k * 2, ad_hi, bd + k * (B_MN ? 128 : 2), bd_hi, idesc, accumulate);
                   accumulate = 1;
                 }
               }
@@ -222,6 +236,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
           }
         }
         umma_commit_elect(&tfull_bar[acc]);
+        if (mtrace) e.trace[m_it * 8 + 2] = (unsigned long long)clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -410,7 +425,17 @@ PreparedOp* prepare_conv_halo(const b2seg_conv_desc* d) {
   L->smem_bytes = fixed + kp.a_stages * kHaloABytes + kp.b_region_bytes;
   L->grid = kp.e.total_tiles < sms ? kp.e.total_tiles : sms;
   kp.e.cta_groups = (L->b_res && cta_groups) ? d->n_groups : 0;   // only together with resident weights
+  static const bool trace_on = getenv("B2SEG_TRACE") != nullptr;
+  if (trace_on) {
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, g_halo_trace) == cudaSuccess) kp.e.trace = reinterpret_cast<unsigned long long*>(sym);
+  }
   return L;
+}
+
+int read_halo_trace(unsigned long long* out, int n) {
+  if (n > 48 * 8) n = 48 * 8;
+  return cudaMemcpyFromSymbol(out, g_halo_trace, (size_t)n * 8) == cudaSuccess ? n : -1;
 }
 
 }  // namespace b2

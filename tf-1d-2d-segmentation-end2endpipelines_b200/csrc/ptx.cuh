@@ -128,6 +128,22 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t adesc,
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors given as (low, high) words: per MMA only the 14-bit start-address field in the LOW word moves and
+// it never carries out of that word, so the issue loop does 32-bit adds instead of 64-bit add-with-carry chains on the
+// uniform datapath (whose dependent-op latency, not the tensor pipe, set the ~265 clocks per filter tap measured with
+// B2SEG_TRACE on the N <= 128 layers).
+__device__ __forceinline__ void umma_bf16_elect_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                   uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
