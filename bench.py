@@ -28,6 +28,8 @@ for p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 
 TRAIN_GFLOP_PER_IMAGE = 275.088  # BASELINE.md §2, config 2 (fwd + dgrad + wgrad, first-layer dgrad omitted)
+CONV_FAM = "conv_halo_kernel+conv_gemm_kernel"      # fprop / dgrad / transposed-conv launches (b2seg_conv)
+WGRAD_FAM = "wgrad_halo_kernel+wgrad_kernel"       # weight-gradient launches (b2seg_wgrad)
 WORKLOAD = "2D UNet depth5 width64 256x256x3 from_scratch dense_loop=1 transconv, BCE + Adam(2e-4), batch 32/GPU"
 
 
@@ -257,7 +259,7 @@ def main():
             acc /= reps
             for i in range(n_ops):
                 info = eng.planner.op_info[(phase, i)]
-                fam = {L.OP_CONV: "conv_gemm_kernel", L.OP_WGRAD: "wgrad_kernel"}.get(info["op"], "streaming")
+                fam = {L.OP_CONV: CONV_FAM, L.OP_WGRAD: WGRAD_FAM}.get(info["op"], "streaming")
                 op_rows.append({"phase": phase, "i": i, "op": info["op"], "note": info["note"], "ms": float(acc[i]),
                                 "tflops": info["flops"] / (acc[i] / 1e3) / 1e12 if info["flops"] and acc[i] > 0 else None})
                 a = agg.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0))
@@ -267,7 +269,7 @@ def main():
             with open(args.ops_json, "w") as f:
                 json.dump(op_rows, f, indent=0)
         step_ms_ops = sum(a["ms"] for a in agg.values())
-        dom = max(("conv_gemm_kernel", "wgrad_kernel"), key=lambda k: agg.get(k, {"ms": 0})["ms"])
+        dom = max((CONV_FAM, WGRAD_FAM), key=lambda k: agg.get(k, {"ms": 0})["ms"])
         a = agg[dom]
         achieved = a["flops"] / (a["ms"] / 1e3) / 1e12
         # DRAM bytes per launch of the dominant family from the committed ncu capture of this same command (tools/launch_summary.py)
@@ -276,7 +278,7 @@ def main():
         if os.path.exists(tpath) and S == 256 and B == 32:
             with open(tpath) as f:
                 tj = json.load(f)
-            key = "conv" if dom == "conv_gemm_kernel" else "wgrad"
+            key = "conv" if dom == CONV_FAM else "wgrad"
             traffic = tj[key]["dram_bytes_per_launch"]
             traffic_src = f"profiles/r1_launches_final.json: ncu dram__bytes_read.sum + dram__bytes_write.sum over the {tj[key]['launches']} {key} launches of one step / launches"
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
