@@ -186,6 +186,26 @@ def test_unet1d_shallow_end_to_end():
     check_end_to_end(m, Ref1D("UNet", 256, 2, 2, 16, 3, problem_type="Regression", output_nums=1, ds=0), 1, x, [y], ["mse"])
 
 
+def test_unet2d_autoencoder_bottleneck_end_to_end():
+    """ae=1 (Flatten -> Dense('features') -> Dense -> Reshape, unet_variants.py:41-48) on a shallow model, free-running: the Dense
+    kernels' and biases' gradients are compared with the oracle like every other parameter"""
+    kw = dict(num_channels=1, output_nums=1, dense_loop=1, is_transconv=True, ae=1, feature_number=32)
+    m = unet_model_builder("UNet", 32, 32, 8, 2, train_mode="from_scratch", **kw).ResNet50()
+    assert "features/kernel" in m.get_weight_dict() and m.get_weight_dict()["features/kernel"].shape == (8 * 8 * 32, 32)
+    rng = np.random.default_rng(21)
+    x = rng.random((4, 32, 32, 1), dtype=np.float32)
+    y = (x > 0.5).astype(np.float32)
+    check_end_to_end(m, Ref2D("UNet", 32, 32, 8, 2, **kw), 2, x, [y], ["bce"])
+
+
+def test_unet1d_autoencoder_bottleneck_end_to_end():
+    m = UNet(128, 2, 1, 16, 3, problem_type="Regression", output_nums=1, ds=0, ae=1, feature_number=32).UNet()
+    rng = np.random.default_rng(22)
+    x = rng.standard_normal((4, 128, 1)).astype(np.float32)
+    y = np.tanh(x).astype(np.float32)
+    check_end_to_end(m, Ref1D("UNet", 128, 2, 1, 16, 3, problem_type="Regression", output_nums=1, ds=0, ae=1, feature_number=32), 1, x, [y], ["mse"])
+
+
 def test_unet2d_cfg2_graph_per_layer():
     """BASELINE config 2 graph (depth 5, width 64, 3 channels, transposed-conv decoder) at 64x64, batch 4"""
     kw = dict(num_channels=3, output_nums=1, dense_loop=1, is_transconv=True)
@@ -334,6 +354,7 @@ FAMILY_CASES = [
     ("UNetE", dict(is_transconv=False, ag=1, ds=1), 32, 16, 2),   # ds=1: without it UNetE leaves dangling nodes that Keras prunes
     ("MultiResUNet", dict(), 64, 32, 3),                           # BASELINE config 4 graph family (odd channel counts: gapped concat layouts)
     ("MultiResUNet", dict(is_transconv=False, ds=1), 32, 16, 2),
+    ("UNet", dict(ae=1, feature_number=64), 64, 16, 3),            # Feature_Extraction_Block: Dense layers as 1x1 convolutions on (N,1,1,F)
 ]
 
 

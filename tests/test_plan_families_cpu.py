@@ -39,6 +39,8 @@ CASES_2D = [
     ("UNet3P", dict(ds=1)),
     ("MultiResUNet", dict()),                      # odd channel counts (w/6, w/3, w/2): gapped concat layouts
     ("MultiResUNet", dict(ds=1, is_transconv=False)),
+    ("UNet", dict(ae=1, feature_number=24)),       # Feature_Extraction_Block: Flatten -> Dense('features') -> Dense -> Reshape
+    ("UNetPP", dict(ae=1, ds=1, feature_number=16)),
 ]
 
 
@@ -67,6 +69,8 @@ CASES_1D = [
     ("BCDUNet", dict(ds=0, lstm=0, ag=1)),
     ("MultiResUNet", dict(ds=0)),
     ("MultiResUNet", dict(ds=1, ag=1)),
+    ("UNet", dict(ae=1, ds=0, feature_number=24)),
+    ("BCDUNet", dict(ae=1, ds=1, lstm=1, feature_number=16)),
 ]
 
 

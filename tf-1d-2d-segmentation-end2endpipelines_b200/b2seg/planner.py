@@ -304,6 +304,12 @@ class Planner:
                 self.units.append(dict(kind="mul", node=n, out=n))
             elif n.op == "convlstm":
                 self.units.append(dict(kind="convlstm", node=n, out=n, parts=self.flat_concat[id(n)]))
+            elif n.op in ("flatten", "dense", "reshape"):
+                # Feature_Extraction_Block (ae=1; 2DCNN unet_variants.py:41-48, 1DCNN :127-135): Flatten and Reshape are views of
+                # the channels-last buffer, Dense is a 1x1 convolution over a (N, 1, 1, features) tensor on the same kernels
+                if any(c.op in ("concat", "convlstm") for c in self.cons[id(n)]):
+                    raise PlanError(f"{n.name}: a {n.op} output feeding a concatenation is not lowered")
+                self.units.append(dict(kind=n.op, node=n, out=n))
             else:
                 raise PlanError(f"layer type '{n.op}' ({n.name}) is not lowered yet")
         self.unit_of_out = {id(u["out"]): u for u in self.units}
@@ -382,6 +388,13 @@ class Planner:
                 self._add_param(f"{n.name}/beta", (n.C,), "vec", cp, True, C=n.C, vsegs=vs, Cp=cp)
                 self._add_param(f"{n.name}/moving_mean", (n.C,), "vec", cp, False, C=n.C, vsegs=vs, Cp=cp)
                 self._add_param(f"{n.name}/moving_variance", (n.C,), "vec", cp, False, C=n.C, fill=1.0, vsegs=vs, Cp=cp)
+            elif n.op == "dense":
+                fin, units = n.inputs[0].shape[2], n.attrs["units"]
+                if fin % 8 or units % 8:
+                    raise PlanError(f"{n.name}: Dense {fin} -> {units}: feature counts must be multiples of 8")
+                self._add_param(f"{n.name}/kernel", (fin, units), "conv", units * fin, True, cout=units, cout_p=units, taps=1, cin_p=fin,
+                                kh=1, kw=1, out_segs=[(0, units)], segs=[(0, fin)])
+                self._add_param(f"{n.name}/bias", (units,), "vec", units, True, C=units, vsegs=[(0, units)], Cp=units)
             elif n.op == "convlstm":
                 kh, kw = n.attrs["kernel"]
                 F = n.attrs["filters"]
@@ -757,6 +770,66 @@ class Planner:
         self._copy_extra(dests[0], dests[1:])
         self.taps[n.name] = (dests[0], F, "act")
 
+    # -- Feature_Extraction_Block: Flatten -> Dense -> Dense -> Reshape -------------------------------------------------------
+    def _flat_view(self, t: Node, what: str) -> TView:
+        """the dense channels-last buffer of t seen as (N, 1, 1, H*W*C): exactly Keras' Flatten order"""
+        p = self.phys[id(t)]
+        H, W, C = t.shape
+        v = p.view
+        if p.Cp != C or list(p.segs) != [(0, C)] or v.sw != C or (H > 1 and v.sh != W * C) or v.sn != H * W * C:
+            raise PlanError(f"{what}: needs a dense, unpadded channels-last tensor (got {t.name}: C={C}, physical {p.Cp}, strides {v.sn},{v.sh},{v.sw})")
+        return TView.dense(v.ptr, self.N, 1, 1, H * W * C)
+
+    def _fwd_flatten(self, u):
+        n = u["node"]
+        self.phys[id(n)] = Phys(self._flat_view(n.inputs[0], n.name), n.C, [(0, n.C)])
+
+    def _fwd_reshape(self, u):
+        n = u["node"]
+        H, W, C = n.shape
+        src = self.phys[id(n.inputs[0])]
+        if C % 8 or src.Cp != H * W * C:
+            raise PlanError(f"{n.name}: Reshape to {n.shape} needs C % 8 == 0 and an unpadded source")
+        self.phys[id(n)] = Phys(TView.dense(src.view.ptr, self.N, H, W, C), C, [(0, C)])
+        self.taps[n.name] = (self.phys[id(n)].view, C, "act")
+
+    def _fwd_dense(self, u):
+        n = u["node"]
+        x = self.phys[id(n.inputs[0])]
+        fin, units = n.inputs[0].shape[2], n.attrs["units"]
+        out = self.new_act(1, 1, units)
+        self.emit(0, L.OP_CONV, lw.conv_fprop(x.view, self.pwb(f"{n.name}/kernel"), units, 1, 1, fin, out, bias=self.pw(f"{n.name}/bias")),
+                  n.name, flops=2.0 * self.N * fin * units)
+        self.phys[id(n)] = Phys(out, units, [(0, units)])
+        u["x"] = x.view
+
+    def _bwd_flatten(self, u):
+        n = u["node"]
+        g = self._single_grad(n)
+        if g is not None:
+            H, W, C = n.inputs[0].shape
+            self._add_gsrc(n.inputs[0], GSrc(TView.dense(g.ptr, self.N, H, W, C)))
+
+    def _bwd_reshape(self, u):
+        n = u["node"]
+        g = self._single_grad(n)
+        if g is not None:
+            H, W, C = n.shape
+            self._add_gsrc(n.inputs[0], GSrc(TView.dense(g.ptr, self.N, 1, 1, H * W * C)))
+
+    def _bwd_dense(self, u):
+        n = u["node"]
+        dz = self._single_grad(n)
+        if dz is None:
+            return
+        fin, units = n.inputs[0].shape[2], n.attrs["units"]
+        flops = 2.0 * self.N * fin * units
+        self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, u["x"], self.pg(f"{n.name}/kernel"), units, 1, 1, fin), f"wgrad {n.name}", flops=flops)
+        self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")
+        dx = self.new_act(1, 1, fin, "grad")
+        self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(f"{n.name}/kernel"), units, 1, 1, fin, dx), f"dgrad {n.name}", flops=flops)
+        self._add_gsrc(n.inputs[0], GSrc(dx))
+
     def _fwd_head(self, u):
         n = u["node"]
         a = n.attrs
@@ -1115,7 +1188,7 @@ class Planner:
                 if m.get("fill") is not None:
                     out[m["C"]:ceil8(m["C"])] = m["fill"]
         elif e.kind in ("conv", "tconv"):
-            k = arr if arr.ndim == 4 else arr[None]            # (kh,kw,Cin,Cout) | tconv (kh,kw,Cout,Cin)
+            k = arr if arr.ndim == 4 else (arr[None, None] if arr.ndim == 2 else arr[None])   # (kh,kw,Cin,Cout) | tconv (kh,kw,Cout,Cin) | Dense (in,out)
             if e.kind == "conv":
                 k = np.transpose(k, (3, 0, 1, 2))               # -> (Cout,kh,kw,Cin)
             else:

@@ -27,9 +27,9 @@ def cfg(n):
         y = np.eye(2, dtype=np.float32)[(x[..., 0] > 0).astype(np.int64)]
         return "cfg1 1D UNet d5 w64 L1024", m, x, y, "categorical_crossentropy", None, 5.23
     kw = dict(train_mode="from_scratch", is_transconv=True)
-    if n == 2:
-        m = unet_model_builder("UNet", 256, 256, 64, 5, num_channels=3, output_nums=1, dense_loop=1, **kw).ResNet50()
-        B, S, c, loss, gf = 32, 256, 3, "binary_crossentropy", 91.77
+    if n in (2, 6):   # 6 = config 2 with the auto-encoder bottleneck (ae=1: two Dense layers of 134 M parameters each)
+        m = unet_model_builder("UNet", 256, 256, 64, 5, num_channels=3, output_nums=1, dense_loop=1, ae=1 if n == 6 else 0, **kw).ResNet50()
+        B, S, c, loss, gf = 32, 256, 3, "binary_crossentropy", 91.77 + (0.537 if n == 6 else 0.0)
     elif n == 3:
         m = unet_model_builder("UNetPP", 256, 256, 64, 5, num_channels=3, output_nums=4, ds=1, ag=1, final_activation="softmax", **kw).ResNet50()
         B, S, c, loss, gf = 8, 256, 3, None, 342.21
@@ -48,7 +48,7 @@ def cfg(n):
         loss = {"out": "categorical_crossentropy", **{name: "mse" for name in m.output_names[1:]}}
         return "cfg3 2D UNet++ DS+AG 4 classes", m, x, y, loss, None, gf
     y = (rng.random((B, S, S, 1)) > 0.7).astype(np.float32)
-    return {2: "cfg2 2D UNet d5 w64 256^2", 4: "cfg4 2D MultiResUNet 512^2x1", 5: "cfg5 2D UNet lstm=1 dense_loop=3 (BCDUNet)"}[n], m, x, y, loss, None, gf
+    return {2: "cfg2 2D UNet d5 w64 256^2", 6: "cfg2 + ae=1 (Dense 131072 -> 1024 -> 131072)", 4: "cfg4 2D MultiResUNet 512^2x1", 5: "cfg5 2D UNet lstm=1 dense_loop=3 (BCDUNet)"}[n], m, x, y, loss, None, gf
 
 
 def main():
