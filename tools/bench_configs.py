@@ -77,6 +77,21 @@ def main():
                           "train_tflops": round(3 * gf * B / ms, 1), "loss_first": round(float(l0), 5), "loss_after_9_steps": round(float(l1), 5),
                           "params": int(m.count_params()), "device_memory_gb": round(eng.memory_bytes() / 2 ** 30, 2),
                           "launches_per_step": int(sum(eng.launches)), "build_s": round(build_s, 1)}), flush=True)
+        if os.environ.get("BENCH_CONFIGS_OPS"):
+            # where the step goes: device time per op kind (CUDA events after every op of one replay)
+            import collections
+            from b2seg import _lib as L
+            names = {v: k for k, v in vars(L).items() if k.startswith("OP_") and isinstance(v, int)}
+            agg = collections.defaultdict(lambda: [0, 0.0])
+            for phase in (0, 1, 2):
+                for i, t in enumerate(eng.timed_phase(phase)):
+                    info = eng.planner.op_info[(phase, i)]
+                    key = ("fwd", "bwd", "opt")[phase] + " " + names.get(info["op"], str(info["op"]))
+                    agg[key][0] += 1
+                    agg[key][1] += t
+            tot = sum(v[1] for v in agg.values())
+            for k2, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+                print(f"    {k2:<22} x{v[0]:<4d} {v[1]:8.3f} ms  {100 * v[1] / tot:5.1f}%", flush=True)
         del m, eng
         torch.cuda.empty_cache()
 
