@@ -337,6 +337,40 @@ class Model:
             total += w * float(l)
         return total
 
+    def _train_batches_pipelined(self, batches):
+        """Train on a list of equally sized (x, [targets]) host batches with the input pipeline overlapped: batch i+1 is copied
+        host -> device on a copy stream (into one of two staging slots) while step i computes, and every step's loss is read back
+        asynchronously into pinned memory and collected at the end — what Keras' fit() does with its prefetching data adapter
+        (2DCNN/Train.py:394-415).  Pinned source arrays make the copies truly asynchronous; pageable ones still work."""
+        import torch
+        B = batches[0][0].shape[0]
+        eng = self._engine(B, True)
+        cur = torch.cuda.current_stream(eng.dev)
+        if not hasattr(eng, "_stage"):
+            eng._copy_stream = torch.cuda.Stream(device=eng.dev)
+            eng._stage = [dict(x=torch.empty_like(eng.x_dev), t=[torch.empty_like(o["target"]) for o in eng.outputs],
+                               ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        loss_host = torch.empty(len(batches), dtype=torch.float32).pin_memory()
+        for i, (bx, bys) in enumerate(batches):
+            st = eng._stage[i % 2]
+            with torch.cuda.stream(eng._copy_stream):
+                eng._copy_stream.wait_event(st["free"])          # the step that used this slot has copied it out
+                st["x"].copy_(torch.from_numpy(bx), non_blocking=True)
+                for dst, t in zip(st["t"], bys):
+                    if tuple(t.shape) != tuple(dst.shape):
+                        raise ValueError(f"target shape {t.shape} != {tuple(dst.shape)}")
+                    dst.copy_(torch.from_numpy(np.ascontiguousarray(t, np.float32)), non_blocking=True)
+                st["ready"].record(eng._copy_stream)
+            cur.wait_event(st["ready"])
+            eng.x_dev.copy_(st["x"], non_blocking=True)
+            for o, t in zip(eng.outputs, st["t"]):
+                o["target"].copy_(t, non_blocking=True)
+            st["free"].record(cur)
+            self._step(eng, return_loss=False)
+            loss_host[i].copy_(eng.loss_buf[0], non_blocking=True)
+        cur.synchronize()
+        return [float(v) for v in loss_host.tolist()]
+
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, callbacks=None, validation_data=None, shuffle=True,
             initial_epoch=0, steps_per_epoch=None, **kw):
         hist = History()
@@ -364,13 +398,20 @@ class Model:
                 if hasattr(sequence, "on_epoch_end"):
                     sequence.on_epoch_end()
             else:
-                order = rng.permutation(n) if shuffle else np.arange(n)
-                for s in range(0, n, bs):
-                    idx = order[s:s + bs]
-                    by = [t[idx][:, 0] if self.graph.ndim == 1 else t[idx] for t in ys]
-                    losses.append(self.train_on_batch(xs[idx], by if len(by) > 1 else by[0]))
-                    if steps_per_epoch and len(losses) >= steps_per_epoch:
-                        break
+                order = rng.permutation(n) if shuffle else None
+                starts = list(range(0, n, bs))
+                if steps_per_epoch:
+                    starts = starts[:int(steps_per_epoch)]
+                full = [s for s in starts if s + bs <= n]
+                xn = self._to_nhwc(xs)
+
+                def take(a, s):   # contiguous slice (keeps pinned memory pinned) unless shuffled
+                    return a[s:s + bs] if order is None else a[order[s:s + bs]]
+                if full:
+                    losses += self._train_batches_pipelined([(take(xn, s), [take(t, s) for t in ys]) for s in full])
+                for s in starts[len(full):]:    # ragged last batch: its own engine
+                    by = [take(t, s)[:, 0] if self.graph.ndim == 1 else take(t, s) for t in ys]
+                    losses.append(self.train_on_batch(take(xs, s), by if len(by) > 1 else by[0]))
             logs = {"loss": float(np.mean(losses))}
             if validation_data is not None:
                 vx, vy = validation_data[:2]
