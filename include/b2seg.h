@@ -127,9 +127,17 @@ typedef struct b2seg_bn_act_desc {
 } b2seg_bn_act_desc;
 
 typedef struct b2seg_gradsrc {
-  b2seg_view g;       /* gradient tensor view */
-  int32_t kind;       /* 0 direct (same grid), 1 max-pool routed (g is on the pooled grid) */
+  b2seg_view g;       /* gradient tensor view (kinds 0, 1) */
+  int32_t kind;       /* 0 direct (same grid), 1 max-pool routed (g is on the pooled grid), 2 pointwise head (below) */
   int32_t pool_h, pool_w;
+  /* kind 2: the consumer is a Conv 1x1 head with cout <= 2 outputs (the `out` / `level{k}` layers, unet_variants.py:1106,137).
+   * Its input gradient g[pix][c] = sum_o dlogits[pix][o] * head_w[c][o] is formed on the fly instead of being written and read
+   * back twice, and the head's own parameter gradients dW[c][o] = sum_pix act(BN(x))[pix][c] * dlogits[pix][o], db[o] = sum_pix
+   * dlogits[pix][o] are accumulated (red.add, caller-zeroed) by pass 0, which has the activation in registers anyway. */
+  uint64_t dlogits;   /* fp32 [N*H*W][cout] */
+  uint64_t head_w;    /* fp32 [C][cout] */
+  uint64_t head_dw, head_db;
+  int32_t cout;
 } b2seg_gradsrc;
 
 /* Backward of act(BN(x)): pass 0 reduces dbeta = sum(dy*m) and dgamma = sum(dy*m*xhat), pass 1 writes

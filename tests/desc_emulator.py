@@ -213,6 +213,15 @@ def emu_bn_bwd(mem, d):
     g = torch.zeros_like(x)
     for i in range(d.n_src):
         s = d.src[i]
+        if s.kind == 2:   # folded pointwise head: g = dlogits . W^T; the head's dW, db accumulate here (caller-zeroed slots)
+            dl = mem.f32(s.dlogits, N * H * W * s.cout).view(N, H, W, s.cout)
+            hw = mem.f32(s.head_w, C * s.cout).view(C, s.cout)
+            g += dl @ hw.T
+            dw = mem.f32(s.head_dw, C * s.cout).view(C, s.cout)
+            dw += torch.einsum("nhwc,nhwo->co", y, dl)
+            db = mem.f32(s.head_db, s.cout)
+            db += dl.reshape(-1, s.cout).sum(0)
+            continue
         gv = mem.gather_view(s.g)
         if s.kind == 0:
             g += gv

@@ -292,6 +292,45 @@ def test_bn_finalize_act_pool_and_backward():
     assert rel_l2(dgamma, g_.grad) < 2e-3 and rel_l2(dbeta, b_.grad) < 2e-3
 
 
+@pytest.mark.parametrize("cout,act,extra", [(1, L.ACT_RELU, False), (2, L.ACT_LEAKY, True), (1, L.ACT_RELU, True)])
+def test_bn_bwd_with_folded_head(cout, act, extra):
+    """b2seg_gradsrc kind 2: the pointwise head's input gradient is formed on the fly and its dW / db fall out of pass 0"""
+    dev = "cuda"
+    N, H, W, Cc = 3, 20, 24, 64
+    z = bf(torch.randn(N, H, W, Cc, device=dev) * 2 + 0.3)
+    gamma, beta = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.1
+    hw = torch.randn(Cc, cout, device=dev) * 0.2
+    dl = torch.randn(N, H, W, cout, device=dev) * 0.1
+    g_extra = bf(torch.randn(N, H, W, Cc, device=dev) * 0.05)
+    zt = z.float().requires_grad_(True)
+    gt, bt, hwt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True), hw.clone().requires_grad_(True)
+    mu, var = zt.view(-1, Cc).mean(0), zt.view(-1, Cc).var(0, unbiased=False)
+    pre = (zt - mu) / torch.sqrt(var + 1e-3) * gt + bt
+    a = F.relu(pre) if act == L.ACT_RELU else F.leaky_relu(pre, 0.3)
+    hb = torch.zeros(cout, device=dev, requires_grad=True)
+    loss = ((a @ hwt + hb) * dl).sum() + ((a * g_extra.float()).sum() if extra else 0.0)
+    loss.backward()
+    rstd = 1.0 / torch.sqrt(var.detach() + 1e-3)
+    scale = (gamma * rstd).contiguous()
+    shift = (beta - mu.detach() * gamma * rstd).contiguous()
+    mean = mu.detach().contiguous()
+    dgamma, dbeta, dw, db = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev), torch.zeros(Cc, cout, device=dev), torch.zeros(cout, device=dev)
+    dz = torch.zeros_like(z)
+    bd = L.BnBwdDesc()
+    bd.x, bd.scale, bd.shift, bd.mean, bd.rstd = tv(z).to_c(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    bd.act, bd.n_src = act, 2 if extra else 1
+    bd.src[0] = L.GradSrc(tv(z).to_c(), 2, 1, 1, dl.data_ptr(), hw.data_ptr(), dw.data_ptr(), db.data_ptr(), cout)
+    if extra:
+        bd.src[1] = L.GradSrc(tv(g_extra).to_c(), 0, 1, 1)
+    bd.count, bd.partials, bd.n_blocks = float(N * H * W), 0, 0
+    bd.dgamma, bd.dbeta, bd.dx, bd.accumulate = dgamma.data_ptr(), dbeta.data_ptr(), tv(dz).to_c(), 1
+    L.call("b2seg_bn_bwd", bd, stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dz.float(), zt.grad) < 8e-3
+    assert rel_l2(dgamma, gt.grad) < 2e-3 and rel_l2(dbeta, bt.grad) < 2e-3
+    assert rel_l2(dw, hwt.grad) < 2e-3 and rel_l2(db, hb.grad) < 1e-4
+
+
 def test_adam_keras_rule():
     dev = "cuda"
     n = 4096 + 8

@@ -130,6 +130,8 @@ def test_plan_unet2d_matches_oracle():
     kinds = [op for (op, _, _) in pl.ops[0]]
     assert kinds.count(11) == 1  # one input cast; concat realised without copy ops
     assert not any(note == "concat copy" for (_, _, note) in pl.ops[0])
+    # the `out` head's backward (input gradient, dW, db) is folded into batch_normalization_4's backward: no OP_HEAD_BWD (= 8) left
+    assert 8 not in [op for (op, _, _) in pl.ops[1]]
     # transposed-conv bias gradients come from the consumer dgrad's epilogue statistics (OP_ROWSUM = 22), not from a pass over dY
     assert [note for (op, _, note) in pl.ops[1] if op == 22] == ["bias grad conv2d_transpose_1", "bias grad conv2d_transpose"]
 

@@ -67,7 +67,8 @@ class BnActDesc(C.Structure):
 
 
 class GradSrc(C.Structure):
-    _fields_ = [("g", View), ("kind", C.c_int32), ("pool_h", C.c_int32), ("pool_w", C.c_int32)]
+    _fields_ = [("g", View), ("kind", C.c_int32), ("pool_h", C.c_int32), ("pool_w", C.c_int32),
+                ("dlogits", C.c_uint64), ("head_w", C.c_uint64), ("head_dw", C.c_uint64), ("head_db", C.c_uint64), ("cout", C.c_int32)]
 
 
 class BnBwdDesc(C.Structure):

@@ -16,6 +16,7 @@ device memory (b2seg.engine) or to the CPU descriptor emulator used by the CPU t
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -137,6 +138,7 @@ class GSrc:
     pool: Tuple[int, int] = (1, 1)
     premasked: bool = False
     colsums: Optional[Tuple[int, int, int]] = None   # (fp32 rows ptr, n_rows, pitch): per-CTA column sums written by the producer
+    head: Optional[dict] = None   # kind 2: a pointwise head whose backward is folded into the producer's BN backward (b2seg_gradsrc)
 
 
 class PlanError(NotImplementedError):
@@ -155,6 +157,7 @@ class Planner:
         # > 0 (data parallel): the optimizer phase is one Adam op per gradient-exchange bucket, in exchange order, so the
         # update of a bucket can run as soon as ITS all-reduce has landed while later buckets are still on the wire
         self.adam_bucket_bytes = adam_bucket_bytes
+        self.fuse_heads = os.environ.get("B2SEG_NO_HEAD_FUSION") is None
         self.g = graph
         self.N = batch
         self.alloc_fn = alloc
@@ -867,16 +870,34 @@ class Planner:
         wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
         self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr),
                   f"loss {n.name}")
+        t = n.inputs[0]
+        pu = self.unit_of_out.get(id(t))
+        x = self.phys[id(t)]
+        if (self.fuse_heads and pu is not None and pu["kind"] == "conv" and pu["bn"] is not None and pu["out"] is t and pu["pool"] is None
+                and pu["act"] is not None and self._act_code(pu["act"]) in (L.ACT_RELU, L.ACT_LEAKY) and o["cout"] <= 2
+                and n.attrs["strides"][1] == 1 and self.N * t.shape[0] * t.shape[1] * x.Cp < 2 ** 31):
+            # the head reads act(BN(conv)): its backward (input gradient, dW, db) is folded into that layer's BN backward,
+            # so the 2 x H x W x C gradient tensor is never written or read (b2seg_gradsrc kind 2)
+            self._add_gsrc(t, GSrc(x.view, 2, (1, 1), head=dict(unit=u, name=n.name, dlogits=o["dlogits"], cout=o["cout"])))
+            return
+        self._emit_head_bwd(u)
+
+    def _emit_head_bwd(self, u) -> Optional[GSrc]:
+        """stand-alone head backward: dW, db and (unless the head reads the network input) dx as a dense gradient tensor"""
+        n = u["node"]
         d: L.HeadDesc = u["desc"]
         x = self.phys[id(n.inputs[0])]
         H, W, _ = n.inputs[0].shape
         d2 = L.HeadDesc.from_buffer_copy(d)
         d2.dw, d2.db = self.pg(f"{n.name}/kernel"), self.pg(f"{n.name}/bias")   # (also marks them written by this unit)
+        src = None
         if n.inputs[0].op != "input":
             dx = self.new_act(H, W, x.Cp, "grad")
             d2.dx = dx.to_c()
-            self._add_gsrc(n.inputs[0], GSrc(dx))
+            src = GSrc(dx)
+            self._add_gsrc(n.inputs[0], src)
         self.emit(1, L.OP_HEAD_BWD, d2, f"head bwd {n.name}")
+        return src
 
     def _bwd_input(self, u):
         pass
@@ -893,6 +914,8 @@ class Planner:
         for s in srcs:
             if s.kind == 0:
                 out.append(s)
+            elif s.kind == 2:      # a head that could not be folded into a BN backward after all: run its own backward now
+                out.append(self._unfuse_head(t, s))
             else:
                 dx = self._grad_like(t)
                 self.emit(1, L.OP_POOL_BWD, L.PoolBwdDesc(self.phys[id(t)].view.to_c(), s.view.to_c(), dx.to_c(), s.pool[0], s.pool[1]),
@@ -900,8 +923,19 @@ class Planner:
                 out.append(GSrc(dx))
         return out
 
-    def _kernel_sources(self, t: Node, srcs: List[GSrc]) -> List[GSrc]:
-        """sources in the form bn_bwd accepts: pooled sources only if they share one window of 2 or 4 elements"""
+    def _unfuse_head(self, t: Node, s: GSrc) -> GSrc:
+        lst = self.gsrc.get(id(t), [])
+        n_before = len(lst)
+        src = self._emit_head_bwd(s.head["unit"])
+        del lst[n_before:]          # _emit_head_bwd registered the dense gradient on t; the caller consumes it directly
+        return src
+
+    def _kernel_sources(self, t: Node, srcs: List[GSrc], allow_head: bool = False) -> List[GSrc]:
+        """sources in the form bn_bwd accepts: pooled sources only if they share one window of 2 or 4 elements; a folded head
+        (kind 2) only next to direct sources of a BN + ReLU/LeakyReLU layer, and only one of them"""
+        heads = [s for s in srcs if s.kind == 2]
+        if heads and (not allow_head or len(heads) > 1 or any(s.kind == 1 for s in srcs)):
+            srcs = [self._unfuse_head(t, s) if s.kind == 2 else s for s in srcs]
         wins = {s.pool for s in srcs if s.kind == 1}
         if len(wins) > 1 or any(w[0] * w[1] not in (2, 4) for w in wins):
             srcs = self._direct_sources(t, srcs)
@@ -1086,7 +1120,7 @@ class Planner:
         H, W, _ = n.shape
         act = self._act_code(u["act"])
         y: TView = u["y"]
-        srcs = self._kernel_sources(out_node, srcs)
+        srcs = self._kernel_sources(out_node, srcs, allow_head=u["bn"] is not None and act in (L.ACT_RELU, L.ACT_LEAKY))
         bias_rows = None
         # ---- dZ: gradient w.r.t. the raw convolution output
         if u["bn"] is not None:
@@ -1097,6 +1131,10 @@ class Planner:
             d.act, d.n_src = act, len(srcs)
             for i, s in enumerate(srcs):
                 d.src[i] = L.GradSrc(s.view.to_c(), s.kind, s.pool[0], s.pool[1])
+                if s.kind == 2:
+                    hk, hb = f"{s.head['name']}/kernel", f"{s.head['name']}/bias"
+                    d.src[i].dlogits, d.src[i].cout = s.head["dlogits"], s.head["cout"]
+                    d.src[i].head_w, d.src[i].head_dw, d.src[i].head_db = self.pw(hk), self.pg(hk), self.pg(hb)   # pg(): written by THIS unit
             d.count = float(self.N * H * W)
             nb = max(1, min(1184, (self.N * H * W) // 64))
             d.partials, d.n_blocks = self.alloc(nb * 2 * cop * 4, "scratch"), nb

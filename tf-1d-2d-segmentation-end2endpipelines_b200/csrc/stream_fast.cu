@@ -192,6 +192,9 @@ struct BnBwdF {
   int C, Ho, Wo, rows;
   FastDiv fd_ho;
   int cvb, rp;
+  // pointwise-head source (b2seg_gradsrc kind 2): g = dlogits . head_w^T formed on the fly; PASS 0 also accumulates the head's dW, db
+  const float* dlogits; const float* head_w;
+  float* head_dw; float* head_db;
 };
 
 // Same arithmetic as bn_bwd_lean_kernel (stream_kernels.cu): mask from the sign of t = x*scale + shift, pooled gradients
@@ -357,6 +360,158 @@ __global__ void __launch_bounds__(256, PH * PW * U >= 4 ? 2 : 3) bn_bwd_fast_ker
   }
 }
 
+// BN + activation backward of the layer a pointwise head (Conv 1x1, HC <= 2 outputs) reads, with the head's backward folded in:
+// the head's input gradient g[pix][c] = sum_o dlogits[pix][o] * W[c][o] is never materialised (the separate head kernel
+// wrote it once and this kernel read it twice: 805 MB at the 256x256x64 output layer of config 2), and PASS 0, which has
+// a = act(BN(x)) in registers, also accumulates the head's dW[c][o] = sum a * dlogits and db[o] = sum dlogits.
+// Un-pooled tensors only; further direct sources (a transposed conv reading the same tensor under deep supervision) are added.
+template <int PASS, int ACT, int HC, int U>
+__global__ void __launch_bounds__(256, 2) bn_bwd_head_kernel(const BnBwdF k) {
+  pdl_prologue();
+  extern __shared__ float red[];   // PASS 0: [256][16 + 8 * HC + 1]
+  constexpr int kRed = 16 + 8 * HC + 1;
+  const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
+  const int v = blockIdx.x * k.cvb + tcv;
+  const bool active = v * 8 < k.C && trow < k.rp;
+  float sc[8], sf[8], cB[8], cD[8], acc_b[8], acc_g[8], hw[8][HC], acc_hw[HC][8], acc_hb[HC];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { acc_b[e] = 0.f; acc_g[e] = 0.f; sc[e] = 1.f; sf[e] = 0.f; cB[e] = 0.f; cD[e] = 0.f; }
+#pragma unroll
+  for (int o = 0; o < HC; ++o) {
+    acc_hb[o] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { acc_hw[o][e] = 0.f; hw[e][o] = 0.f; }
+  }
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e;
+      sc[e] = __ldg(k.scale + c);
+      sf[e] = __ldg(k.shift + c);
+      const float rs = __ldg(k.rstd + c), mu = __ldg(k.mean + c);
+      if (PASS == 1) {
+        const float cb = __ldg(k.dbeta + c) * k.inv_count, cg = __ldg(k.dgamma + c) * k.inv_count;
+        cB[e] = -sc[e] * cg * rs;
+        cD[e] = sc[e] * (cg * rs * mu - cb);
+      } else {
+        cB[e] = rs;
+        cD[e] = -mu * rs;
+      }
+#pragma unroll
+      for (int o = 0; o < HC; ++o) hw[e][o] = __ldg(k.head_w + (size_t)c * HC + o);
+    }
+    const unsigned step = (unsigned)k.rp;
+    const int n_src = k.n_src;
+    for (int rr = blockIdx.y; rr < k.rows; rr += gridDim.y) {
+      const int r = PASS == 0 ? k.rows - 1 - rr : rr;
+      const unsigned n = fast_div((unsigned)r, k.fd_ho), ho = (unsigned)r - n * (unsigned)k.Ho;
+      const unsigned xrow = n * k.x.sn + ho * k.x.sh + v * 8;
+      const unsigned drow = n * k.dx.sn + ho * k.dx.sh + v * 8;
+      const size_t prow = (size_t)r * k.Wo;      // pixel index of the row start: dlogits is dense [N*H*W][HC]
+      for (unsigned wo0 = trow; wo0 < (unsigned)k.Wo; wo0 += step * U) {
+        uint4 xr[U];
+        float g[U][8], dl[U][HC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned wo = wo0 + u * step < (unsigned)k.Wo ? wo0 + u * step : (unsigned)k.Wo - 1;
+          xr[u] = ld16(k.x, xrow + wo * k.x.sw);
+#pragma unroll
+          for (int o = 0; o < HC; ++o) dl[u][o] = wo0 + u * step < (unsigned)k.Wo ? __ldg(k.dlogits + (prow + wo) * HC + o) : 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            g[u][e] = 0.f;
+#pragma unroll
+            for (int o = 0; o < HC; ++o) g[u][e] = fmaf(dl[u][o], hw[e][o], g[u][e]);
+          }
+        }
+        for (int s = 0; s < n_src; ++s) {
+          if (k.kind[s] != 0) continue;
+          const FV sv = k.src[s];
+          const unsigned srow = n * sv.sn + ho * sv.sh + v * 8;
+          uint4 rr4[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const unsigned wo = wo0 + u * step < (unsigned)k.Wo ? wo0 + u * step : (unsigned)k.Wo - 1;
+            rr4[u] = ld16(sv, srow + wo * sv.sw);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float f[8];
+            unpack8(rr4[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[u][e] += f[e];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned wo = wo0 + u * step;
+          if (wo >= (unsigned)k.Wo) break;
+          float x[8];
+          unpack8(xr[u], x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float t = fmaf(x[e], sc[e], sf[e]);
+            if (PASS == 0) {
+              const float a = act_f<ACT>(t);
+#pragma unroll
+              for (int o = 0; o < HC; ++o) acc_hw[o][e] = fmaf(a, dl[u][o], acc_hw[o][e]);
+            }
+            if (ACT == B2SEG_ACT_RELU) g[u][e] = t > 0.f ? g[u][e] : 0.f;
+            if (ACT == B2SEG_ACT_LEAKY) g[u][e] = t > 0.f ? g[u][e] : 0.3f * g[u][e];
+          }
+          if (PASS == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { acc_b[e] += g[u][e]; acc_g[e] = fmaf(g[u][e], fmaf(x[e], cB[e], cD[e]), acc_g[e]); }
+            if (v == 0) {
+#pragma unroll
+              for (int o = 0; o < HC; ++o) acc_hb[o] += dl[u][o];
+            }
+          } else {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = fmaf(cB[e], x[e], fmaf(sc[e], g[u][e], cD[e]));
+            st16(k.dx, drow + wo * k.dx.sw, pack8(o8));
+          }
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    float* mine = red + (size_t)threadIdx.x * kRed;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mine[e] = acc_b[e]; mine[8 + e] = acc_g[e]; }
+#pragma unroll
+    for (int o = 0; o < HC; ++o) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mine[16 + o * 8 + e] = acc_hw[o][e];
+    }
+    mine[16 + 8 * HC] = 0.f;
+    __syncthreads();
+    if (trow == 0 && v * 8 < k.C) {
+      float sum[16 + 8 * HC];
+#pragma unroll
+      for (int i = 0; i < 16 + 8 * HC; ++i) sum[i] = 0.f;
+      for (int r = 0; r < k.rp; ++r) {
+        const float* o = red + (size_t)(r * k.cvb + tcv) * kRed;
+#pragma unroll
+        for (int i = 0; i < 16 + 8 * HC; ++i) sum[i] += o[i];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(k.acc_dbeta + v * 8 + e, sum[e]);
+        atomicAdd(k.acc_dgamma + v * 8 + e, sum[8 + e]);
+#pragma unroll
+        for (int o = 0; o < HC; ++o) atomicAdd(k.head_dw + (size_t)(v * 8 + e) * HC + o, sum[16 + o * 8 + e]);
+      }
+    }
+    // db: the threads of channel vector 0 hold the per-pixel sums of dlogits
+    if (v == 0 && active) {
+#pragma unroll
+      for (int o = 0; o < HC; ++o) atomicAdd(k.head_db + o, acc_hb[o]);
+    }
+  }
+}
+
 struct BnBwdFastLaunch : PreparedOp {
   BnBwdF k;
   bool has_bn;
@@ -371,8 +526,17 @@ struct BnBwdFastLaunch : PreparedOp {
       default: launch_k(bn_bwd_fast_kernel<PASS, PH, PW, B2SEG_ACT_NONE, U>, grid, dim3(256), smem, s, k); break;
     }
   }
+  int head_cout = 0;
+  template <int PASS, int HC>
+  void go_head(dim3 grid, cudaStream_t s) {
+    const int smem = PASS == 0 ? 256 * (16 + 8 * HC + 1) * 4 : 0;
+    if (act == B2SEG_ACT_LEAKY) launch_k(bn_bwd_head_kernel<PASS, B2SEG_ACT_LEAKY, HC, 2>, grid, dim3(256), smem, s, k);
+    else launch_k(bn_bwd_head_kernel<PASS, B2SEG_ACT_RELU, HC, 2>, grid, dim3(256), smem, s, k);
+  }
   template <int PASS>
   void go(dim3 grid, int smem, cudaStream_t s) {
+    if (head_cout == 1) { go_head<PASS, 1>(grid, s); return; }
+    if (head_cout == 2) { go_head<PASS, 2>(grid, s); return; }
     if (ph == 2 && pw == 2) go_act<PASS, 2, 2, 1>(grid, smem, s);
     else if (ph == 1 && pw == 2) go_act<PASS, 1, 2, 2>(grid, smem, s);
     else go_act<PASS, 1, 1, 2>(grid, smem, s);
@@ -412,10 +576,26 @@ PreparedOp* prepare_bn_bwd_fast(const b2seg_bn_bwd_desc* d) {
   BnBwdF& k = L->k;
   memset(&k, 0, sizeof(k));
   bool ok = fv_make(d->x, &k.x) && fv_make(d->dx, &k.dx);
+  int n_head = 0;
   for (int i = 0; ok && i < d->n_src; ++i) {
-    ok = fv_make(d->src[i].g, &k.src[i]);
     k.kind[i] = d->src[i].kind;
+    if (d->src[i].kind == 2) {
+      const b2seg_gradsrc& hs = d->src[i];
+      ++n_head;
+      // only what bn_bwd_head_kernel implements: BN + ReLU/LeakyReLU, no pooled source, at most 2 head outputs
+      ok = n_head == 1 && has_bn && ph == 1 && pw == 1 && (hs.cout == 1 || hs.cout == 2) && hs.dlogits && hs.head_w && hs.head_dw && hs.head_db &&
+           (d->act == B2SEG_ACT_RELU || d->act == B2SEG_ACT_LEAKY);
+      k.dlogits = reinterpret_cast<const float*>(hs.dlogits); k.head_w = reinterpret_cast<const float*>(hs.head_w);
+      k.head_dw = reinterpret_cast<float*>(hs.head_dw); k.head_db = reinterpret_cast<float*>(hs.head_db);
+      L->head_cout = hs.cout;
+      continue;
+    }
+    ok = fv_make(d->src[i].g, &k.src[i]);
     if (d->src[i].kind != 0 && d->src[i].kind != 1) ok = false;
+  }
+  if (ok && n_head) {
+    for (int i = 0; i < d->n_src; ++i)
+      if (d->src[i].kind == 1) ok = false;
   }
   if (!ok) { delete L; return nullptr; }
   k.n_src = d->n_src;
@@ -434,7 +614,7 @@ PreparedOp* prepare_bn_bwd_fast(const b2seg_bn_bwd_desc* d) {
   row_grid(k.C, k.rows, k.Wo, &k.cvb, &k.rp, &L->grid1);
   // PASS 0 ends with 2 * 8 * cvb atomics per block: one resident wave of blocks walking the rows keeps them few
   L->grid0 = L->grid1;
-  const unsigned wave = (unsigned)std::max(1, num_sms() * (ph * pw > 1 ? 2 : 3) / (int)L->grid0.x);   // = blocks resident at once (launch bounds)
+  const unsigned wave = (unsigned)std::max(1, num_sms() * ((ph * pw > 1 || L->head_cout) ? 2 : 3) / (int)L->grid0.x);   // = blocks resident at once (launch bounds)
   if (L->grid0.y > wave) L->grid0.y = wave;
   return L;
 }

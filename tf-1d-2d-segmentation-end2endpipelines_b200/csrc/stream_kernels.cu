@@ -601,6 +601,11 @@ struct BnBwdLaunch : PreparedOp {
 PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
   if (d->x.C % 8 || d->n_src < 1 || d->n_src > B2SEG_MAX_GRADSRC) { set_error("bn_bwd: bad C or n_src"); return nullptr; }
   if (PreparedOp* fast = prepare_bn_bwd_fast(d)) return fast;   // instruction-lean row walker (stream_fast.cu) when eligible
+  for (int i = 0; i < d->n_src; ++i)
+    if (d->src[i].kind == 2) {
+      set_error("bn_bwd: a pointwise-head source (kind 2) needs BN + ReLU/LeakyReLU, no pooled source, cout <= 2 and 16-byte aligned views below 2^31 elements");
+      return nullptr;
+    }
   auto* L = new BnBwdLaunch();
   BnBwdK& k = L->k;
   memset(&k, 0, sizeof(k));
