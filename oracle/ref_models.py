@@ -174,6 +174,51 @@ class Ref2D:
         return list(reversed(levels + [out])) if self.ds == 1 else [out]
 
 
+class RefFPN(Ref2D):
+    """fpn_model_builder('FPN', ...).<Encoder>() with train_mode='from_scratch' (2DCNN/models/fpn_variants.py:132-169, 302-372):
+    UNet's encoder without a latent block; per level [attention gate] [DS head] up-sample, Add (or ConvLSTM) with the skip,
+    Conv_Block; the decoder outputs of all levels are bilinearly up-sampled and concatenated in front of the `out` head."""
+
+    def __init__(self, decoder_name, length, width, model_width, model_depth, num_channels=3, output_nums=1, ds=0, ae=0, ag=0, lstm=0,
+                 feature_number=1024, is_transconv=True, alpha=1.0, final_activation="sigmoid"):
+        super().__init__(decoder_name, length, width, model_width, model_depth, num_channels, output_nums, ds, ae, ag, lstm,
+                         1, feature_number, is_transconv, alpha, final_activation)
+
+    def __call__(self, k: KerasRef, x):
+        W, d = self.W, self.d
+        pool = k.Input(x)
+        convs = []
+        for i in range(1, d + 2):                                         # encoder_block_scratch :190-203
+            conv = self.CB(k, pool, W * 2 ** (i - 1), (3, 3))
+            pool = k.MaxPooling(conv, (2, 2))
+            convs.append(conv)
+        if self.ae == 1:                                                  # :353-354
+            sh = conv.shape
+            z = k.Dense(k.Flatten(conv), self.feat, name="features")
+            conv = k.Reshape(k.Dense(z, W * 2 ** d * sh[1] * sh[2]), (sh[1], sh[2], W * 2 ** d))
+        skips = convs[:d] + [conv]
+        levels, decs, deconv = [], [], skips[-1]
+        for j in range(d):                                                # FPN :132-163
+            l = d - j - 1
+            skip = skips[l]
+            if self.ag == 1:
+                skip = self.AG(k, skips[l], deconv, W, 2 ** l)
+            if self.ds == 1:
+                levels.append(k.Conv(deconv, 1, (1, 1), name=f"level{d - j}"))
+            deconv = self.up(k, deconv, W * 2 ** l)
+            if self.lstm == 1:
+                deconv = k.ConvLSTM([skip, deconv], int(np.int32(W * (2.0 ** (l - 1)))), (3, 3))
+            else:
+                deconv = k.add([deconv, skip])
+            deconv = self.CB(k, deconv, W * 2 ** l, (3, 3))
+            decs.append(deconv)
+        tot = decs[0]                                                     # :164-169
+        for q in range(1, d):
+            tot = k.concatenate([k.UpSampling(tot, (2, 2), "bilinear"), decs[q]])
+        out = k.Conv(tot, self.out_n, (1, 1), activation=self.fa, name="out")
+        return list(reversed(levels + [out])) if self.ds == 1 else [out]
+
+
 # =============================================================================================== 1D family
 class Ref1D:
     """UNet(...).<variant>() (1DCNN/Models/unet_variants.py:222-897) and BCDUNet(...).BCDUNet() (BCDUNet.py:79-174)."""

@@ -27,7 +27,7 @@ from b2seg.model import Adam  # noqa: E402
 from b2seg.models1d import UNet  # noqa: E402
 from b2seg.models2d import unet_model_builder  # noqa: E402
 from oracle.keras_ref import KerasRef, keras_adam_step, keras_loss  # noqa: E402
-from oracle.ref_models import Ref1D, Ref2D  # noqa: E402
+from oracle.ref_models import Ref1D, Ref2D, RefFPN  # noqa: E402
 
 TOL = 1e-2        # per-layer (BASELINE.json)
 E2E_TOL = 3e-2    # free-running, shallow models (accumulated bf16 storage noise, see module docstring)
@@ -401,6 +401,24 @@ def test_2d_families_per_layer(dec, kw, size, width, depth):
         else:
             targets.append(rng.standard_normal((4, H, W, C)).astype(np.float32)); losses.append("mse")
     check_per_layer(m, Ref2D(dec, size, size, width, depth, **kw), 2, x, targets, losses, e2e_bound=1.0)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(ds=1, ag=1)], ids=["plain", "ds1-ag1"])
+def test_fpn_per_layer(kw):
+    """FPN genre (fpn_variants.py:132-169): add-merge decoder + multi-scale bilinear concat head"""
+    from b2seg.models2d import fpn_model_builder
+    kw = dict(num_channels=3, **kw)
+    m = fpn_model_builder("FPN", 64, 64, 16, 3, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(13)
+    x = rng.random((4, 64, 64, 3), dtype=np.float32)
+    targets, losses = [], []
+    for n in m.graph.outputs:
+        H, W, C = n.shape
+        if n.name == "out":
+            targets.append((rng.random((4, H, W, C)) > 0.6).astype(np.float32)); losses.append("bce")
+        else:
+            targets.append(rng.standard_normal((4, H, W, C)).astype(np.float32)); losses.append("mse")
+    check_per_layer(m, RefFPN("FPN", 64, 64, 16, 3, **kw), 2, x, targets, losses, e2e_bound=1.0)
 
 
 def test_1d_bcdunet_lstm_ag_ds_per_layer():

@@ -6,8 +6,8 @@ import pytest
 import torch
 
 from b2seg.models1d import BCDUNet, UNet
-from b2seg.models2d import unet_model_builder
-from oracle.ref_models import Ref1D, Ref2D
+from b2seg.models2d import fpn_model_builder, model_selector, unet_model_builder
+from oracle.ref_models import Ref1D, Ref2D, RefFPN
 from test_plan_cpu import _run
 
 
@@ -58,6 +58,35 @@ def test_2d_family(dec, kw):
     # MultiResUNet builds a ResPath on the deepest encoder level that no decoder level consumes: Keras prunes it, the
     # eager oracle still evaluates it with weights of its own
     _run(g, Ref2D(dec, 16, 16, W, depth, **kw), x, ts, losses, 2, loss_weights=lw, strict=dec != "MultiResUNet")
+
+
+CASES_FPN = [dict(), dict(ds=1), dict(ag=1, ds=1, output_nums=3, final_activation="softmax"), dict(lstm=1), dict(ae=1, feature_number=16)]
+
+
+@pytest.mark.parametrize("kw", CASES_FPN, ids=["-".join(f"{k}{v}" for k, v in kw.items()) or "plain" for kw in CASES_FPN])
+def test_fpn_family(kw):
+    """FPN genre (fpn_variants.py:132-169): add-merge decoder + multi-scale bilinear concat head, through the same kernels"""
+    rng = np.random.default_rng(3)
+    depth = 3
+    W = 16 if kw.get("lstm") else 8
+    kw = dict(num_channels=2, **kw)
+    g = fpn_model_builder("FPN", 32, 32, W, depth, train_mode="from_scratch", **kw).build_graph()
+    x = torch.from_numpy(rng.random((2, 32, 32, 2), dtype=np.float32))
+    ts, losses = _targets(g, 2, rng, 2)
+    _run(g, RefFPN("FPN", 32, 32, W, depth, **kw), x, ts, losses, 2, loss_weights=[1.0 - 0.1 * i for i in range(len(ts))])
+
+
+def test_fpn_builder_api():
+    with pytest.raises(ValueError):
+        fpn_model_builder("FPN", 32, 32, 8, 2, train_mode="nope")
+    with pytest.raises(ValueError):   # Keras Add() of a bilinearly up-sampled tensor and a skip with half its channels
+        fpn_model_builder("FPN", 32, 32, 8, 2, is_transconv=False, train_mode="from_scratch").build_graph()
+    g = fpn_model_builder("FPN", 64, 64, 16, 3, num_channels=3, ds=1, train_mode="from_scratch").build_graph("VGG16")
+    assert g.name == "VGG16_FPN" and [n.name for n in g.outputs] == ["out", "level1", "level2", "level3"]
+    assert g.outputs[0].inputs[0].C == 16 * (4 + 2 + 1)          # the head reads the concat of all decoder levels
+    m = model_selector("FPN", "resnet50", "FPN", 64, 64, 16, 3, train_mode="from_scratch").segmentation_model()   # model_selector.py:717
+    assert m.name == "ResNet50_FPN" and m.output_names == ["out"]
+    assert model_selector("fpn", "chexnet", "FPN", 64, 64, 16, 3, train_mode="from_scratch").segmentation_model().name == "DenseNet121(CheXNet)_FPN"
 
 
 CASES_1D = [

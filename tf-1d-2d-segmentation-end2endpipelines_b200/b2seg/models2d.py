@@ -1,5 +1,6 @@
 """2D builder API — drop-in for the reference's TensorFlow/2DCNN/models/unet_variants.py:977-3502
-(class unet_model_builder) and model_selector.py:8-73 for the `from_scratch` UNet-family path.
+(class unet_model_builder), fpn_variants.py:132-372 (class fpn_model_builder, decoder 'FPN') and model_selector.py:8-73 for the
+`from_scratch` path.
 
 Same constructor arguments, same method names, same ValueError behaviour; instead of a tf.keras.Model the
 methods return a b2seg.model.Model (compile / fit / predict / train_on_batch / load_weights / summary) whose
@@ -271,6 +272,99 @@ class unet_model_builder:
         return Model(self.build_graph(encoder_name))
 
 
+# ---- FPN genre (reference: TensorFlow/2DCNN/models/fpn_variants.py) ---------------------------------------------
+def decoder_fpn(g: Graph, skips, W, d, D_S, A_G, LSTM, is_transconv):                    # FPN :132-169
+    levels, deconvs = [], []
+    deconv = skips[-1]
+    for j in range(d):
+        l = d - j - 1
+        skip = skips[l]
+        if A_G == 1:
+            skip = attention_block(g, skips[l], deconv, W, 2 ** l)                       # :141
+        if D_S == 1:
+            levels.append(g.conv(deconv, 1, (1, 1), name=f"level{d - j}"))              # :144
+        deconv = trans_conv2d(g, deconv, W * 2 ** l) if is_transconv else up_conv_block(g, deconv)   # :146-149
+        if LSTM == 1:
+            if skip.C != W * 2 ** l or deconv.C != W * 2 ** l:
+                raise ValueError(f"total size of new array must be unchanged, input_shape = {list(deconv.shape)}, "
+                                 f"output_shape = [1, {deconv.shape[0]}, {deconv.shape[1]}, {W * 2 ** l}]")
+            deconv = g.convlstm([skip, deconv], int(np.int32(W * 2 ** (l - 1) if l > 0 else W / 2)), (3, 3))   # :150-157
+        else:
+            if skip.C != deconv.C:   # Keras Add() on tensors of different channel counts (is_transconv=False)
+                raise ValueError(f"Inputs have incompatible shapes. Received shapes {tuple(deconv.shape)} and {tuple(skip.shape)}")
+            deconv = g.add([deconv, skip])                                               # Add_Block :160
+        deconv = conv_block(g, deconv, W * 2 ** l, (3, 3))                               # :161
+        deconvs.append(deconv)
+    tot = deconvs[0]                                                                     # :164-169: multi-scale concat head
+    for k in range(1, d):
+        tot = g.concat([up_conv_block(g, tot), deconvs[k]])
+    return tot, levels
+
+
+class fpn_model_builder:
+    """Reference signature: fpn_variants.py:222-300 (no `dense_loop`: the FPN genre has no latent dense block)."""
+
+    def __init__(self, decoder_name, length, width, model_width, model_depth, num_channels=3, output_nums=1, ds=0, ae=0, ag=0,
+                 lstm=0, feature_number=1024, is_transconv=True, alpha=1.0, q=3, final_activation="sigmoid",
+                 train_mode="pretrained_encoder", is_base_model_trainable=False):
+        self.decoder_name = decoder_name
+        self.length = length
+        self.width = width
+        self.model_depth = model_depth
+        self.model_width = model_width
+        self.num_channels = num_channels
+        self.output_nums = output_nums
+        self.D_S = ds
+        self.A_E = ae
+        self.A_G = ag
+        self.LSTM = lstm
+        self.feature_number = feature_number
+        self.is_transconv = is_transconv
+        self.final_activation = final_activation
+        self.train_mode = train_mode
+        self.is_base_model_trainable = is_base_model_trainable
+        self.alpha = alpha
+        self.q = q
+        if self.train_mode == "pretrained_encoder":
+            if (self.model_depth > 5) or (self.model_depth < 1):
+                raise ValueError("The depth of a TF-ImageNet Pretrained model can only be discretely varied from 1 to 5")
+        elif self.train_mode == "from_scratch":
+            if self.model_depth < 1:
+                raise ValueError("The depth of the model cannot be less than 1")
+        else:
+            raise ValueError('The Train Mode can only be: "pretrained_encoder" or "from_scratch"')
+
+    def build_graph(self, encoder_name="ResNet50") -> Graph:
+        """The template every encoder-named method follows (ResNet50, fpn_variants.py:302-372)."""
+        if self.length == 0:
+            raise ValueError("Please Check the Values of the Input Parameters!")
+        if self.train_mode == "pretrained_encoder":
+            raise NotImplementedError("train_mode='pretrained_encoder' needs tf.keras.applications ImageNet weights; "
+                                      "only the 'from_scratch' hot path is implemented")
+        if str(self.decoder_name).startswith("Self"):
+            raise NotImplementedError(f"decoder '{self.decoder_name}' (Self-ONN layers) is outside the hot-path scope (SURVEY §8)")
+        if self.decoder_name != "FPN":
+            raise UnboundLocalError("local variable 'deconv' referenced before assignment")   # decoder_block :214-219
+        d, W = self.model_depth, self.model_width
+        g = Graph(2)
+        inputs = g.input(self.length, self.width, self.num_channels)
+        convs, conv = encoder_block_scratch(g, inputs, self.decoder_name, W, d, self.alpha)   # :190-203 (no latent block)
+        if self.A_E == 1:
+            conv = feature_extraction_block(g, conv, W * 2 ** d, self.feature_number)
+        skips = convs[:d] + [conv]
+        deconv, levels = decoder_fpn(g, skips, W, d, self.D_S, self.A_G, self.LSTM, self.is_transconv)
+        out = g.conv(deconv, self.output_nums, (1, 1), activation=self.final_activation, name="out")
+        outputs = [out]
+        if self.D_S == 1:
+            outputs = list(reversed(levels + [out]))
+        model_name = ("DenseNet121(CheXNet)" if encoder_name == "CheXNet" else encoder_name) + "_" + str(self.decoder_name)   # :2626
+        return g.finalize(outputs, model_name)
+
+    def _build(self, encoder_name):
+        from .model import Model
+        return Model(self.build_graph(encoder_name))
+
+
 def _make_encoder_method(enc):
     def method(self):
         return self._build(enc)
@@ -281,6 +375,7 @@ def _make_encoder_method(enc):
 
 for _enc in _ENCODERS:
     setattr(unet_model_builder, _enc, _make_encoder_method(_enc))
+    setattr(fpn_model_builder, _enc, _make_encoder_method(_enc))
 
 
 class model_selector:
@@ -316,13 +411,20 @@ class model_selector:
         self.q = q
 
     def segmentation_model(self):
-        if self.model_genre in ("FPN", "fpn"):
-            raise NotImplementedError("the FPN genre (fpn_variants.py) is outside the hot-path scope (SURVEY §8(f) rank 2)")
-        if self.model_genre not in ("UNet", "unet", "U-Net"):
+        if self.model_genre not in ("UNet", "unet", "U-Net", "FPN", "fpn"):
             return None  # the reference falls through its if/elif ladder and returns None
         enc = self._ALIASES.get(str(self.encoder_name).lower()) if self.encoder_name in _ENCODERS or isinstance(self.encoder_name, str) else None
         if enc is None:
             return None
+        if self.model_genre in ("FPN", "fpn"):                       # model_selector.py:717-1040 (no dense_loop argument)
+            if not hasattr(fpn_model_builder, enc):
+                return None
+            b = fpn_model_builder(self.decoder_name, self.imlength, self.imwidth, self.model_width, self.model_depth,
+                                  num_channels=self.num_channels, output_nums=self.output_nums, ds=self.D_S, ae=self.A_E, ag=self.A_G,
+                                  lstm=self.LSTM, feature_number=self.feature_number, is_transconv=self.is_transconv, alpha=self.alpha,
+                                  q=self.q, final_activation=self.final_activation, train_mode=self.train_mode,
+                                  is_base_model_trainable=self.is_base_model_trainable)
+            return getattr(b, enc)()
         b = unet_model_builder(self.decoder_name, self.imlength, self.imwidth, self.model_width, self.model_depth,
                                num_channels=self.num_channels, output_nums=self.output_nums, ds=self.D_S, ae=self.A_E, ag=self.A_G,
                                lstm=self.LSTM, dense_loop=self.dense_loop, feature_number=self.feature_number,
