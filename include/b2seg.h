@@ -207,6 +207,10 @@ typedef struct b2seg_resize_desc {
   b2seg_view yfwd;  /* backward with act != NONE: the stored forward output */
   int32_t fh, fw, mode, act;
   int32_t c_valid;  /* channels >= c_valid are written as 0 (0 = all valid) */
+  /* n_vseg > 0: the channel layout is gapped (odd-channel concat slots, MultiResBlock :85-100): only channels inside one of the
+   * segments [vseg_off, vseg_off + vseg_cnt) are real; the padding lanes between them are written as 0 (sigmoid(0) != 0) */
+  int32_t n_vseg;
+  int32_t vseg_off[8], vseg_cnt[8];
 } b2seg_resize_desc;
 
 /* out = a * b[...,0]  (skip * resampler, the tf operator overload in Attention_Block, unet_variants.py:81).

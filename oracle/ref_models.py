@@ -92,7 +92,7 @@ class Ref2D:
         levels = []
         if self.ds == 1:
             levels.append(k.Conv(skips[0], 1, (1, 1), name=f"level{d}"))
-        D = {}
+        D, skipdiag = {}, {}
         for i in range(1, d + 1):
             for j in range(0, d - i + 1):
                 low = skips[j + 1] if i == 1 else D[j + 1, i - 1]
@@ -108,7 +108,18 @@ class Ref2D:
                         tot = k.concatenate([tot, att(D[j, q])])
                     skip = att(skips[j])
                 up = self.up(k, low, W * 2 ** j)
-                D[j, i] = self.CB(k, self.fuse(k, skip, up, tot, W * (2.0 ** (j - 1))), W * 2 ** j, (3, 3))
+                merged = self.fuse(k, skip, up, tot, W * (2.0 ** (j - 1)))
+                if self.dec in ("UNet4P", "AHNet") and i > 1 and (i + j) == d and j != d - 1:
+                    # UNet4P :440-444 / AHNet :584-589: earlier anti-diagonal nodes, up-sampled to this level, sigmoid
+                    for m in range(1, i - 1):
+                        t = skipdiag[m]
+                        if self.dec == "AHNet":
+                            t = self.RP(k, t, j, W, (3, 3))
+                        t = k.Activation(k.UpSampling(t, (2 ** (i - m), 2 ** (i - m)), "bilinear"), "sigmoid")
+                        merged = k.concatenate([merged, t])
+                D[j, i] = self.CB(k, merged, W * 2 ** j, (3, 3))
+                if (i + j) == d:
+                    skipdiag[i] = D[j, i]
                 if self.ds == 1 and j == 0 and i < d:
                     levels.append(k.Conv(D[j, i], 1, (1, 1), name=f"level{d - i}"))
         return D[0, d], levels
@@ -133,21 +144,75 @@ class Ref2D:
                 levels.append(k.Conv(deconv, 1, (1, 1), strides=(2, 2), name=f"level{d - j}"))
         return deconv, levels
 
+    def dec_mres3p(self, k, skips):                                       # MultiResUNet3P :490-520
+        W, d = self.W, self.d
+        levels, outs, deconv = [], {}, skips[-1]
+        for j in range(d):
+            same = self.MRB(k, skips[d - j - 1], W, (3, 3))
+            for q in range(0, d - j - 1):
+                win = 2 ** ((d - j) - q - 1)
+                same = k.concatenate([same, self.MRB(k, k.MaxPooling(skips[q], (win, win)), W, (3, 3))])
+            below = k.Activation(k.UpSampling(self.MRB(k, deconv, W, (3, 3)), (2, 2), "bilinear"), "sigmoid")
+            tot = k.concatenate([same, below])
+            if j > 0:
+                for m in range(0, j):
+                    t = k.UpSampling(self.RP(k, outs[m], j, W, (3, 3)), (2 ** (j - m), 2 ** (j - m)), "bilinear")
+                    tot = k.concatenate([tot, k.Activation(t, "sigmoid")])
+            deconv = self.MRB(k, tot, W * d, (3, 3))
+            outs[j] = deconv
+            if self.ds == 1:
+                levels.append(k.Conv(deconv, 1, (1, 1), strides=(2, 2), name=f"level{d - j}"))
+        return deconv, levels
+
+    def dec_kssnet(self, k, skips):                                       # KSSNet :603-641 (LSTM branch is broken in the reference)
+        W, d = self.W, self.d
+        levels, outs, deconv = [], {}, skips[-1]
+        for j in range(d):
+            lvl = d - j - 1
+            skip = self.AG(k, skips[lvl], deconv, W, 2 ** lvl) if self.ag == 1 else skips[lvl]
+            if self.ds == 1:
+                levels.append(k.Conv(deconv, 1, (1, 1), name=f"level{d - j}"))
+            deconv = k.concatenate([self.up(k, deconv, W * 2 ** lvl), skip])
+            for m in range(0, j + 1):
+                src = skips[-1] if m == 0 else outs[m]
+                f = 2 ** (j - m + 1)
+                deconv = k.concatenate([deconv, k.Activation(k.UpSampling(src, (f, f), "bilinear"), "sigmoid")])
+            deconv = self.MRB(k, deconv, W * 2 ** lvl, (3, 3))
+            outs[j + 1] = deconv
+        return deconv, levels
+
     # whole model ------------------------------------------------------------------------------------------
     def __call__(self, k: KerasRef, x):
         W, d = self.W, self.d
         pool = k.Input(x)
         convs = []
         mres = self.dec in ("MultiResUNet", "MultiResUNet3P")
+        linked = self.dec in ("KSSNet", "UNet4P", "UNet4PV2", "AHNet")    # dense encoder links :758-781
         for i in range(1, d + 2):                                         # encoder_block_scratch :750-792
             if mres:
                 conv = self.MRB(k, pool, W * 2 ** (i - 1), (3, 3))
                 pool = k.MaxPooling(conv, (2, 2))
                 convs.append(self.RP(k, conv, d - i + 1, W * 2 ** (i - 1), (3, 3)))
+            elif linked:
+                if i > 1:
+                    for q in range(1, i):
+                        link = convs[q - 1]
+                        if self.dec == "AHNet":
+                            link = self.RP(k, link, d - q, W, (3, 3))
+                        link = k.Activation(k.MaxPooling(link, (2 ** (i - q), 2 ** (i - q))), "sigmoid")
+                        pool = k.concatenate([pool, link])
+                if self.dec == "KSSNet":
+                    conv = self.MRB(k, pool, W * 2 ** (i - 1), (3, 3))
+                    convs.append(self.RP(k, conv, d - i + 1, W * 2 ** (i - 1), (3, 3)))
+                else:
+                    conv = self.CB(k, pool, W * 2 ** (i - 1), (3, 3))
+                    convs.append(conv)
+                pool = k.MaxPooling(conv, (2, 2))
             else:
                 conv = self.CB(k, pool, W * 2 ** (i - 1), (3, 3))
                 pool = k.MaxPooling(conv, (2, 2))
                 convs.append(conv)
+        mres = mres or self.dec == "KSSNet"
         if mres:                                                          # latent_layer :966-974
             conv = self.MRB(k, conv, W * 2 ** d, (3, 3))
         else:                                                             # dense_block :51-56
@@ -162,8 +227,12 @@ class Ref2D:
         skips = convs[:d] + [conv]
         if self.dec == "UNet":
             deconv, levels = self.dec_unet(k, skips)
-        elif self.dec in ("UNetE", "UNetP", "UNetPP"):
+        elif self.dec in ("UNetE", "UNetP", "UNetPP", "UNet4P", "AHNet"):
             deconv, levels = self.dec_nested(k, skips)
+        elif self.dec == "MultiResUNet3P":
+            deconv, levels = self.dec_mres3p(k, skips)
+        elif self.dec == "KSSNet":
+            deconv, levels = self.dec_kssnet(k, skips)
         elif self.dec in ("UNet3P", "UNet4PV2"):
             deconv, levels = self.dec_unet3p(k, skips)
         elif self.dec == "MultiResUNet":

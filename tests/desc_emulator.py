@@ -369,7 +369,12 @@ def emu_resize_fwd(mem, d):
     y = torch.einsum("ah,nhwc->nawc", Mh, x)
     y = torch.einsum("bw,nawc->nabc", Mw, y)
     y = _act(y, d.act)
-    if d.c_valid:
+    if d.n_vseg:
+        real = torch.zeros(y.shape[-1], dtype=torch.bool)
+        for i in range(d.n_vseg):
+            real[d.vseg_off[i]:d.vseg_off[i] + d.vseg_cnt[i]] = True
+        y[..., ~real] = 0
+    elif d.c_valid:
         y[..., d.c_valid:] = 0
     mem.write_view(d.y, y)
 

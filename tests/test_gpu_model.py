@@ -58,9 +58,9 @@ def _device_step(model, x, targets, losses, lr=1e-3, loss_weights=None):
 
 def _oracle(ref, ndim, params, x, targets, losses, out_names, loss_weights=None, override=None):
     tp = {k: torch.from_numpy(np.array(v)).double() for k, v in params.items()}
-    # MultiResUNet builds a ResPath on the deepest encoder level that nothing consumes (Keras prunes it; the eager oracle
-    # evaluates it with weights of its own), hence strict=False for that family only
-    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict="MultiResUNet" not in (getattr(ref, "dec", ""), getattr(ref, "var", "")))
+    # the MultiRes / ResPath families build ResPaths on the deepest encoder level that nothing consumes (Keras prunes them; the
+    # eager oracle evaluates them with weights of its own), hence strict=False for those families only
+    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=not ({getattr(ref, "dec", ""), getattr(ref, "var", "")} & {"MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet"}))
     k.override = override
     outs = ref(k, torch.from_numpy(x).double())
     total = 0
@@ -382,6 +382,10 @@ FAMILY_CASES = [
     ("MultiResUNet", dict(), 64, 32, 3),                           # BASELINE config 4 graph family (odd channel counts: gapped concat layouts)
     ("MultiResUNet", dict(is_transconv=False, ds=1), 32, 16, 2),
     ("UNet", dict(ae=1, feature_number=64), 64, 16, 3),            # Feature_Extraction_Block: Dense layers as 1x1 convolutions on (N,1,1,F)
+    ("UNet4P", dict(ds=1), 64, 16, 3),                             # dense sigmoid-pooled encoder links, anti-diagonal up-links
+    ("AHNet", dict(), 64, 16, 3),
+    ("MultiResUNet3P", dict(ds=1), 64, 32, 3),                     # sigmoid over gapped channel layouts (segment-masked resize)
+    ("KSSNet", dict(ag=1), 64, 32, 3),
 ]
 
 

@@ -60,6 +60,31 @@ def test_2d_family(dec, kw):
     _run(g, Ref2D(dec, 16, 16, W, depth, **kw), x, ts, losses, 2, loss_weights=lw, strict=dec != "MultiResUNet")
 
 
+CASES_2D_DEEP = [
+    ("UNet4P", dict()),                             # UNet++ grid + dense sigmoid-pooled encoder links + anti-diagonal up-links (:379, :758-781)
+    ("UNet4P", dict(ds=1, ag=1)),
+    ("UNet4PV2", dict(ds=1)),                       # UNet3+ decoder on the dense-link encoder
+    ("AHNet", dict(ds=1)),                          # UNet4P with ResPaths on every link (:523)
+    ("MultiResUNet3P", dict(ds=1)),                 # :490
+    ("KSSNet", dict(ds=1, ag=1)),                   # :603
+    ("KSSNet", dict(is_transconv=False)),
+]
+
+
+@pytest.mark.parametrize("dec,kw", CASES_2D_DEEP, ids=[f"{d}-{'-'.join(f'{k}{v}' for k, v in kw.items())}" for d, kw in CASES_2D_DEEP])
+def test_2d_family_depth3(dec, kw):
+    """the remaining decoders of unet_variants.py at depth 3, where their extra links first appear"""
+    rng = np.random.default_rng(4)
+    kw = dict(num_channels=2, **kw)
+    g = unet_model_builder(dec, 32, 32, 8, 3, train_mode="from_scratch", **kw).build_graph()
+    x = torch.from_numpy(rng.random((2, 32, 32, 2), dtype=np.float32))
+    ts, losses = _targets(g, 2, rng, 2)
+    strict = dec not in ("MultiResUNet3P", "KSSNet", "AHNet")   # dangling ResPath branches that Keras prunes (see test_2d_family)
+    # descriptors carry eps / momentum as float32 (relative 6e-8): through these 60-90 layer graphs a pre-activation within 1e-7 of
+    # zero can land on the other side of the ReLU, hence 2e-7 instead of 1e-8 on the activations
+    _run(g, Ref2D(dec, 32, 32, 8, 3, **kw), x, ts, losses, 2, loss_weights=[1.0 - 0.1 * i for i in range(len(ts))], strict=strict, act_atol=2e-7)
+
+
 CASES_FPN = [dict(), dict(ds=1), dict(ag=1, ds=1, output_nums=3, final_activation="softmax"), dict(lstm=1), dict(ae=1, feature_number=16)]
 
 

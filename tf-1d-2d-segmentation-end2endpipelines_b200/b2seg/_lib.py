@@ -102,7 +102,7 @@ class EltwiseDesc(C.Structure):
 
 class ResizeDesc(C.Structure):
     _fields_ = [("x", View), ("y", View), ("yfwd", View), ("fh", C.c_int32), ("fw", C.c_int32), ("mode", C.c_int32),
-                ("act", C.c_int32), ("c_valid", C.c_int32)]
+                ("act", C.c_int32), ("c_valid", C.c_int32), ("n_vseg", C.c_int32), ("vseg_off", C.c_int32 * 8), ("vseg_cnt", C.c_int32 * 8)]
 
 
 class MulbcDesc(C.Structure):

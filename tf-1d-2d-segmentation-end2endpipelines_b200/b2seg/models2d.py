@@ -12,8 +12,8 @@ import numpy as np
 
 from .graph import Graph, Node
 
-IN_SCOPE_DECODERS = ("UNet", "UNetE", "UNetP", "UNetPP", "UNet3P", "UNet4PV2", "MultiResUNet")
-_OUT_OF_SCOPE = ("UNet4P", "MultiResUNet3P", "KSSNet", "AHNet", "SelfUNet", "SelfUNetPP", "SelfUNet3P")
+IN_SCOPE_DECODERS = ("UNet", "UNetE", "UNetP", "UNetPP", "UNet3P", "UNet4P", "UNet4PV2", "MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet")
+_OUT_OF_SCOPE = ("SelfUNet", "SelfUNetPP", "SelfUNet3P")   # Self-ONN layers (onn_layers.py): SURVEY 8(f) rank 4
 
 
 # ---- block library (reference unet_variants.py:7-122) ------------------------------------------------------
@@ -118,11 +118,12 @@ def decoder_unet(g: Graph, skips, W, d, D_S, A_G, LSTM, is_transconv, multires=N
     return deconv, levels
 
 
-def decoder_nested(g: Graph, variant, skips, W, d, D_S, A_G, LSTM, is_transconv):       # UNetE :157, UNetP :217, UNetPP :277
+def decoder_nested(g: Graph, variant, skips, W, d, D_S, A_G, LSTM, is_transconv):       # UNetE :157, UNetP :217, UNetPP :277, UNet4P :379, AHNet :523
     levels = []
     if D_S == 1:
         levels.append(g.conv(skips[0], 1, (1, 1), name=f"level{d}"))
     X = {}
+    diag = {}                     # UNet4P / AHNet: the node of every column that sits on the anti-diagonal i + j == d (`deconvs_skip`)
     for i in range(1, d + 1):
         for j in range(0, d - i + 1):
             below = skips[j + 1] if i == 1 else X[(j + 1, i - 1)]
@@ -132,7 +133,7 @@ def decoder_nested(g: Graph, variant, skips, W, d, D_S, A_G, LSTM, is_transconv)
                 skip = gated(skips[j])
             elif variant == "UNetP":
                 skip = gated(X[(j, i - 1)])
-            else:  # UNetPP: all earlier nodes of the row, then the encoder skip
+            else:  # UNetPP / UNet4P / AHNet: all earlier nodes of the row, then the encoder skip
                 parts = [gated(X[(j, k)]) for k in range(1, i)]
                 extra = parts[0] if len(parts) == 1 else g.concat(parts)
                 skip = gated(skips[j])
@@ -141,7 +142,16 @@ def decoder_nested(g: Graph, variant, skips, W, d, D_S, A_G, LSTM, is_transconv)
                 raise ValueError(f"total size of new array must be unchanged, input_shape = {list(up.shape)}, "
                                  f"output_shape = [1, {up.shape[0]}, {up.shape[1]}, {W * 2 ** j}]")
             merged = _merge(g, skip, up, extra, LSTM, W * 2 ** (j - 1) if j > 0 else W / 2)
+            if variant in ("UNet4P", "AHNet") and i > 1 and i + j == d and j != d - 1:     # :440-444 / :584-589
+                for m in range(1, i - 1):
+                    t = diag[m]
+                    if variant == "AHNet":
+                        t = res_path(g, t, j, W, (3, 3))
+                    f = 2 ** (i - m)
+                    merged = g.concat([merged, g.act(up_conv_block(g, t, (f, f)), "sigmoid")])
             X[(j, i)] = conv_block(g, merged, W * 2 ** j, (3, 3))
+            if i + j == d:
+                diag[i] = X[(j, i)]
             if D_S == 1 and j == 0 and i < d:
                 levels.append(g.conv(X[(j, i)], 1, (1, 1), name=f"level{d - i}"))
     return X[(0, d)], levels
@@ -169,6 +179,49 @@ def decoder_unet3p(g: Graph, skips, W, d, D_S):                                 
     return deconv, levels
 
 
+def decoder_multires_unet3p(g: Graph, skips, W, d, D_S, kernel, alpha):                 # MultiResUNet3P :490-520
+    levels, decs = [], {}
+    deconv = skips[-1]
+    for j in range(d):
+        allc = multires_block(g, skips[d - j - 1], W, kernel, alpha)
+        for k in range(0, d - j - 1):
+            p = 2 ** ((d - j) - k - 1)
+            allc = g.concat([allc, multires_block(g, g.pool(skips[k], (p, p)), W, kernel, alpha)])
+        t = g.act(up_conv_block(g, multires_block(g, deconv, W, kernel, alpha), (2, 2)), "sigmoid")
+        tot = g.concat([allc, t])
+        for m in range(j):
+            f = 2 ** (j - m)
+            tot = g.concat([tot, g.act(up_conv_block(g, res_path(g, decs[m], j, W, kernel), (f, f)), "sigmoid")])
+        deconv = multires_block(g, tot, W * d, kernel, alpha)
+        decs[j] = deconv
+        if D_S == 1:
+            levels.append(g.conv(deconv, 1, (1, 1), strides=(2, 2), name=f"level{d - j}"))
+    return deconv, levels
+
+
+def decoder_kssnet(g: Graph, skips, W, d, D_S, A_G, LSTM, is_transconv, kernel, alpha):   # KSSNet :603-641
+    levels, decs = [], {}
+    deconv = skips[-1]
+    for j in range(d):
+        l = d - j - 1
+        skip = skips[l]
+        if A_G == 1:
+            skip = attention_block(g, skips[l], deconv, W, 2 ** l)
+        if D_S == 1:
+            levels.append(g.conv(deconv, 1, (1, 1), name=f"level{d - j}"))
+        deconv = trans_conv2d(g, deconv, W * 2 ** l) if is_transconv else up_conv_block(g, deconv)
+        if LSTM == 1:
+            raise NameError("name 'length' is not defined")   # the reference path is broken here (:621-626)
+        deconv = g.concat([deconv, skip])
+        for m in range(0, j + 1):
+            t = skips[-1] if m == 0 else decs[m]
+            f = 2 ** (j - m + 1)
+            deconv = g.concat([deconv, g.act(up_conv_block(g, t, (f, f)), "sigmoid")])
+        deconv = multires_block(g, deconv, W * 2 ** l, kernel, alpha)
+        decs[j + 1] = deconv
+    return deconv, levels
+
+
 def encoder_block_scratch(g: Graph, x, decoder_name, W, d, alpha):                       # :750-792
     convs = []
     pool = x
@@ -178,6 +231,21 @@ def encoder_block_scratch(g: Graph, x, decoder_name, W, d, alpha):              
             conv = multires_block(g, pool, W * 2 ** (i - 1), (3, 3), alpha)
             pool = g.pool(conv, (2, 2))
             convs.append(res_path(g, conv, d - i + 1, W * 2 ** (i - 1), (3, 3)))
+        elif decoder_name in ("KSSNet", "UNet4P", "UNet4PV2", "AHNet"):
+            # dense encoder links (:758-781): every earlier skip, max-pooled to this level and squashed by a sigmoid, joins the input
+            for k in range(1, i):
+                t = convs[k - 1]
+                if decoder_name == "AHNet":
+                    t = res_path(g, t, d - k, W, (3, 3))
+                p = 2 ** (i - k)
+                pool = g.concat([pool, g.act(g.pool(t, (p, p)), "sigmoid")])
+            if decoder_name == "KSSNet":
+                conv = multires_block(g, pool, W * 2 ** (i - 1), (3, 3), alpha)
+                convs.append(res_path(g, conv, d - i + 1, W * 2 ** (i - 1), (3, 3)))
+            else:
+                conv = conv_block(g, pool, W * 2 ** (i - 1), (3, 3))
+                convs.append(conv)
+            pool = g.pool(conv, (2, 2))
         else:
             conv = conv_block(g, pool, W * 2 ** (i - 1), (3, 3))
             pool = g.pool(conv, (2, 2))
@@ -251,8 +319,12 @@ class unet_model_builder:
         name = self.decoder_name
         if name == "UNet":
             deconv, levels = decoder_unet(g, skips, W, d, self.D_S, self.A_G, self.LSTM, self.is_transconv)
-        elif name in ("UNetE", "UNetP", "UNetPP"):
+        elif name in ("UNetE", "UNetP", "UNetPP", "UNet4P", "AHNet"):
             deconv, levels = decoder_nested(g, name, skips, W, d, self.D_S, self.A_G, self.LSTM, self.is_transconv)
+        elif name == "MultiResUNet3P":
+            deconv, levels = decoder_multires_unet3p(g, skips, W, d, self.D_S, (3, 3), self.alpha)
+        elif name == "KSSNet":
+            deconv, levels = decoder_kssnet(g, skips, W, d, self.D_S, self.A_G, self.LSTM, self.is_transconv, (3, 3), self.alpha)
         elif name in ("UNet3P", "UNet4PV2"):
             deconv, levels = decoder_unet3p(g, skips, W, d, self.D_S)
         elif name == "MultiResUNet":

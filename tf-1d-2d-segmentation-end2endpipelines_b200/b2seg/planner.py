@@ -674,8 +674,17 @@ class Planner:
         fh, fw = n.attrs["size"]
         mode = 1 if n.attrs["interpolation"] == "bilinear" else 0
         act = self._act_code(u["act"])
-        d = L.ResizeDesc(x.view.to_c(), dests[0].to_c(), lw.NULL_VIEW.to_c(), fh, fw, mode, act,
-                         self._cvalid(n.C, x.segs, act) if act == L.ACT_SIGMOID else 0)
+        d = L.ResizeDesc(x.view.to_c(), dests[0].to_c(), lw.NULL_VIEW.to_c(), fh, fw, mode, act, 0)
+        if act == L.ACT_SIGMOID:
+            if list(x.segs) != [(0, n.C)]:
+                # gapped layout (MultiResBlock outputs in MultiResUNet3P / KSSNet): sigmoid(0) = 0.5 must not leak into the padding lanes
+                if len(x.segs) > 8:
+                    raise PlanError(f"{out_node.name}: sigmoid over a channel layout with {len(x.segs)} segments (max 8)")
+                d.n_vseg = len(x.segs)
+                for i, (po, c) in enumerate(x.segs):
+                    d.vseg_off[i], d.vseg_cnt[i] = po, c
+            else:
+                d.c_valid = self._cvalid(n.C, x.segs, act)
         self.emit(0, L.OP_RESIZE_FWD, d, out_node.name)
         self._copy_extra(dests[0], dests[1:])
         u["y"] = dests[0]

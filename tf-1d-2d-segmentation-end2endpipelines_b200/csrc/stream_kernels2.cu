@@ -7,7 +7,7 @@
 namespace b2 {
 
 // ------------------------------------------------------------------------------------------ resize (UpSampling)
-struct ResizeK { DView x, y, yfwd; int fh, fw, mode, act, c_valid; };
+struct ResizeK { DView x, y, yfwd; int fh, fw, mode, act, c_valid; int n_vseg; int vseg_off[8], vseg_cnt[8]; };
 
 // half-pixel bilinear source coordinates for output index o at integer scale f: src = (o + 0.5)/f - 0.5, edge-clamped taps
 __device__ __forceinline__ void bil_taps(int o, int f, int in_size, int& i0, int& i1, float& lam) {
@@ -50,8 +50,18 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(ResizeK k) {
         o[e] = top + (bot - top) * lh;
       }
     }
+    if (k.n_vseg > 0) {      // gapped channel layout: a lane is real only inside one of the segments
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = (k.c_valid && v * 8 + e >= k.c_valid) ? 0.f : act_fwd(o[e], k.act);
+      for (int e = 0; e < 8; ++e) {
+        const int c = v * 8 + e;
+        bool real = false;
+        for (int sgi = 0; sgi < k.n_vseg; ++sgi) real = real || (c >= k.vseg_off[sgi] && c < k.vseg_off[sgi] + k.vseg_cnt[sgi]);
+        o[e] = real ? act_fwd(o[e], k.act) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (k.c_valid && v * 8 + e >= k.c_valid) ? 0.f : act_fwd(o[e], k.act);
+    }
     store8(vaddr(k.y, n, ho, wo, v * 8), o);
   }
 }
@@ -129,8 +139,10 @@ static PreparedOp* prep_resize(const b2seg_resize_desc* d, bool bwd) {
     set_error("resize: bad geometry (x %dx%dx%d, y %dx%dx%d, f %dx%d)", d->x.H, d->x.W, d->x.C, d->y.H, d->y.W, d->y.C, d->fh, d->fw);
     return nullptr;
   }
+  if (d->n_vseg < 0 || d->n_vseg > 8) { set_error("resize: at most 8 valid-channel segments"); return nullptr; }
   auto* L = new ResizeLaunch();
-  L->k = ResizeK{dv(d->x), dv(d->y), dv(d->yfwd), d->fh, d->fw, d->mode, d->act, d->c_valid};
+  L->k = ResizeK{dv(d->x), dv(d->y), dv(d->yfwd), d->fh, d->fw, d->mode, d->act, d->c_valid, d->n_vseg, {0}, {0}};
+  for (int i = 0; i < d->n_vseg; ++i) { L->k.vseg_off[i] = d->vseg_off[i]; L->k.vseg_cnt[i] = d->vseg_cnt[i]; }
   L->bwd = bwd;
   return L;
 }
