@@ -293,7 +293,8 @@ class Ref1D:
     """UNet(...).<variant>() (1DCNN/Models/unet_variants.py:222-897) and BCDUNet(...).BCDUNet() (BCDUNet.py:79-174)."""
 
     def __init__(self, variant, length, model_depth, num_channel, model_width, kernel_size, problem_type="Regression", output_nums=1,
-                 ds=1, ae=0, ag=0, lstm=0, alpha=1, feature_number=1024, is_transconv=True, dense_loop=1):
+                 ds=1, ae=0, ag=0, lstm=0, alpha=1, feature_number=1024, is_transconv=True, dense_loop=1, t=2):
+        self.t = t
         self.var, self.L, self.d, self.W, self.ks = variant, length, model_depth, model_width, kernel_size
         self.pt, self.out_n, self.ds, self.ae, self.ag, self.lstm = problem_type, output_nums, ds, ae, ag, lstm
         self.alpha, self.feat, self.tc, self.dense_loop = alpha, feature_number, is_transconv, dense_loop
@@ -349,6 +350,23 @@ class Ref1D:
     def two(self, k, x, mult):
         return self.CB(k, self.CB(k, x, self.W, self.ks, mult), self.W, self.ks, mult)
 
+    def RCB(self, k, x, mult):                                            # Recurrent_Conv_Block uv:63-72
+        h = x
+        for _ in range(self.t):
+            h = k.concatenate([self.CB(k, h, self.W, self.ks, mult), x])
+        return self.CB(k, h, self.W, self.ks, mult)
+
+    def rpair(self, k, x, mult):                                          # RUNet :992-993 / R2UNet :1060-1063
+        y = self.RCB(k, self.RCB(k, x, mult), mult)
+        if self.var == "R2UNet":
+            # Keras creates the 1x1 shortcut FIRST (layer names / weights are drawn in call order)
+            raise AssertionError("use rpair_r2")
+        return y
+
+    def rpair_r2(self, k, x, mult):
+        raw = self.CB(k, x, self.W, 1, mult)
+        return k.add([raw, self.RCB(k, self.RCB(k, x, mult), mult)])
+
     def head(self, k, deconv, levels):
         act = "softmax" if self.pt == "Classification" else "linear"
         out = k.Conv(deconv, self.out_n, 1, activation=act, name="out")
@@ -373,6 +391,24 @@ class Ref1D:
                 if self.ds == 1:
                     levels.append(k.Conv(deconv, 1, 1, name=f"level{d - j}"))
                 deconv = self.MRB(k, self.fuse(k, skip, self.up(k, deconv, 2 ** l), None, l), 2 ** l)
+            return self.head(k, deconv, levels)
+
+        if self.var in ("RUNet", "R2UNet"):                               # uv:979-1044, 1046-1117
+            blk = self.rpair_r2 if self.var == "R2UNet" else self.rpair
+            stack = []
+            for i in range(1, d + 1):
+                conv = blk(k, pool, 2 ** (i - 1))
+                pool = k.MaxPooling(conv, 2)
+                stack.append(conv)
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            deconv = blk(k, pool, 2 ** d)
+            for j in range(d):
+                l = d - j - 1
+                skip = self.AG(k, stack[l], deconv, W, 2 ** l) if self.ag == 1 else stack[l]
+                if self.ds == 1:
+                    levels.append(k.Conv(deconv, 1, 1, name=f"level{d - j}"))
+                deconv = blk(k, self.fuse(k, skip, self.up(k, deconv, 2 ** l), None, l), 2 ** l)
             return self.head(k, deconv, levels)
 
         convs = []

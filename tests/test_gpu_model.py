@@ -425,6 +425,17 @@ def test_fpn_per_layer(kw):
     check_per_layer(m, RefFPN("FPN", 64, 64, 16, 3, **kw), 2, x, targets, losses, e2e_bound=1.0)
 
 
+@pytest.mark.parametrize("var,kw", [("RUNet", dict(ds=1, t=2)), ("R2UNet", dict(ds=1, ag=1, t=2))], ids=["RUNet", "R2UNet-ag1"])
+def test_1d_recurrent_unets_per_layer(var, kw):
+    """RUNet / R2UNet (1DCNN/Models/unet_variants.py:63-72, 979-1117): recurrent conv blocks re-concatenate the block input, R2 adds a
+    1x1 shortcut and pools the un-activated sum"""
+    m = getattr(UNet(256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), var)()
+    rng = np.random.default_rng(14)
+    x = rng.standard_normal((4, 256, 2)).astype(np.float32)
+    targets = [rng.standard_normal((4,) + tuple(n.shape[1:])).astype(np.float32) for n in m.graph.outputs]
+    check_per_layer(m, Ref1D(var, 256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=1.0)
+
+
 def test_1d_bcdunet_lstm_ag_ds_per_layer():
     from b2seg.models1d import BCDUNet
     kw = dict(ds=1, ag=1, lstm=1, dense_loop=2)

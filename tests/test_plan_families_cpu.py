@@ -125,6 +125,9 @@ CASES_1D = [
     ("MultiResUNet", dict(ds=1, ag=1)),
     ("UNet", dict(ae=1, ds=0, feature_number=24)),
     ("BCDUNet", dict(ae=1, ds=1, lstm=1, feature_number=16)),
+    ("RUNet", dict(ds=1, t=2)),                    # Recurrent_Conv_Block (uv.py:63-72): t rounds of conv + concat with the block input
+    ("R2UNet", dict(ds=0, ag=1, t=1)),             # + 1x1 Conv_Block shortcut and Add around each pair
+    ("R2UNet", dict(ds=1, lstm=1, t=2)),
 ]
 
 
@@ -137,6 +140,7 @@ def test_1d_family(var, kw):
         g = BCDUNet(L_, depth, ch, W, ks, **kw).BCDUNet().graph
     else:
         g = getattr(UNet(L_, depth, ch, W, ks, **kw), var)().graph
+    kw = {k_: v for k_, v in kw.items() if k_ != "t" or var in ("RUNet", "R2UNet")}
     x = torch.from_numpy(rng.standard_normal((2, L_, ch)).astype(np.float32))
     ts, losses = _targets(g, 2, rng, 1)
     # with lstm=0 the 1D BCDUNet drops its skip connections, so an attention gate built on them is a dangling branch that

@@ -1,5 +1,5 @@
-"""1D builder API — drop-in for the reference's TensorFlow/1DCNN/Models/unet_variants.py:222-897 (class UNet:
-UNet, UNetE, UNetP, UNetPP, UNet3P, MultiResUNet) and TensorFlow/1DCNN/Models/BCDUNet.py:79-174 (class BCDUNet).
+"""1D builder API — drop-in for the reference's TensorFlow/1DCNN/Models/unet_variants.py:222-1117 (class UNet:
+UNet, UNetE, UNetP, UNetPP, UNet3P, MultiResUNet, RUNet, R2UNet) and TensorFlow/1DCNN/Models/BCDUNet.py:79-174 (class BCDUNet).
 
 Same constructor arguments and method names; the methods return a b2seg.model.Model.  1D tensors (L, C) are held
 as (H=1, W=L, C).  Differences from the 2D family that matter for parity: two Conv-BN-ReLU per level,
@@ -17,6 +17,13 @@ def conv_block(g: Graph, x, model_width, kernel, multiplier, use_batchnorm=True)
     if use_batchnorm:
         x = g.bn(x)
     return g.act(x, "relu")
+
+
+def recurrent_conv_block(g: Graph, x, model_width, kernel, multiplier, t):                   # uv.py:63-72
+    inputs = x
+    for _ in range(t):
+        x = g.concat([conv_block(g, x, model_width, kernel, multiplier), inputs])
+    return conv_block(g, x, model_width, kernel, multiplier)
 
 
 def trans_conv1d(g: Graph, x, model_width, multiplier):                                      # uv.py:102-108
@@ -180,6 +187,45 @@ class UNet:
                 if self.D_S == 1 and j == 0 and i < d:
                     levels.append(g.conv(node, 1, 1, name=f"level{d - i}"))
         return self._finish(g, X[(0, d)], levels)
+
+    def _recurrent_unet(self, residual):
+        """RUNet (uv.py:979-1044) and R2UNet (:1046-1117): UNet whose double Conv_Block is a double Recurrent_Conv_Block (t rounds of
+        conv + concat with the block input); R2 adds a 1x1 Conv_Block shortcut around each pair"""
+        self._check()
+        W, k, d, t = self.model_width, self.kernel_size, self.model_depth, self.t
+        g = Graph(1)
+
+        def pair(x, mult):
+            raw = conv_block(g, x, W, 1, mult) if residual else None
+            y = recurrent_conv_block(g, x, W, k, mult, t)
+            y = recurrent_conv_block(g, y, W, k, mult, t)
+            return g.add([raw, y]) if residual else y
+        pool, convs = g.input(1, self.length, self.num_channel), []
+        for i in range(1, d + 1):
+            conv = pair(pool, 2 ** (i - 1))
+            pool = g.pool(conv, 2)
+            convs.append(conv)
+        if self.A_E == 1:
+            pool = feature_extraction_block(g, pool, W, self.feature_number)
+        deconv = pair(pool, 2 ** d)
+        levels = []
+        for j in range(d):
+            l = d - j - 1
+            skip = convs[l]
+            if self.A_G == 1:
+                skip = attention_block(g, convs[l], deconv, W, 2 ** l)
+            if self.D_S == 1:
+                levels.append(g.conv(deconv, 1, 1, name=f"level{d - j}"))
+            deconv = self._up(g, deconv, 2 ** l)
+            deconv = _merge(g, skip, deconv, None, self.LSTM, W * 2.0 ** (l - 1), W * 2 ** l)
+            deconv = pair(deconv, 2 ** l)
+        return self._finish(g, deconv, levels)
+
+    def RUNet(self):                                                                          # uv.py:979-1044
+        return self._recurrent_unet(False)
+
+    def R2UNet(self):                                                                         # uv.py:1046-1117
+        return self._recurrent_unet(True)
 
     def UNetE(self):
         return self._nested("UNetE")

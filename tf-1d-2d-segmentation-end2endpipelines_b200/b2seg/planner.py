@@ -637,6 +637,20 @@ class Planner:
         n = u["node"]
         self._concat_buffer(n)  # producers already wrote their slots
         self.taps[n.name] = (self.phys[id(n)].view, n.C, "concat")
+        # A concatenation with several consumers is not folded into an outer concatenation that also consumes it (the recurrent
+        # blocks of RUNet / R2UNet concatenate the block input — itself a concat in the decoder — again and again,
+        # 1DCNN/Models/unet_variants.py:63-72): its buffer is complete here, copy it into the outer slots.
+        slots = []
+        for c in self.cons[id(n)]:
+            if c.op in ("concat", "convlstm"):
+                root = self._concat_root(c)
+                buf = self._concat_buffer(root)
+                off = 0
+                for p in self.flat_concat[id(root)]:
+                    if p is n:
+                        slots.append(buf.chan(off, self._cphys(n)))
+                    off += self._cphys(p)
+        self._copy_extra(self.phys[id(n)].view, slots)
 
     def _cvalid(self, C, segs=None, act=0):
         """channel count to pass as c_valid so padding lanes are forced to zero (0 = nothing to mask).  In a gapped layout
@@ -991,7 +1005,9 @@ class Planner:
     def _bwd_add(self, u):
         n, out_node = u["node"], u["out"]
         if u["act"] is None:
-            for s in self.gsrc.get(id(n), []):
+            # a max-pool-routed gradient must be routed against the SUM (the tensor that was pooled), not against each addend:
+            # make it dense here (R2UNet pools `Add([shortcut, recurrent pair])`, 1DCNN/Models/unet_variants.py:1060-1064)
+            for s in self._direct_sources(n, self.gsrc.get(id(n), [])):
                 for i in n.inputs:
                     self._add_gsrc(i, s)
             return
