@@ -121,3 +121,21 @@ def test_two_rank_data_parallel_step(tmp_path):
     ref = mem.f32(pl.w_ptr, max(pl.n_train, 64))
     assert torch.allclose(w0, ref, atol=1e-12)
     assert float((w0 - ref).abs().max()) < 1e-12
+
+
+def test_ops_overlapping_exchange_replay():
+    """host-side replay that decides which backward ops leave SMs to the all-reduce (Engine.reserve_sms_for_exchange)"""
+    from b2seg.dist import ops_overlapping_exchange
+    op_ms = [1.0] * 10                                    # ten 1 ms ops
+    # one 1 MB bucket ready after op 3 has finished (t = 4 ms) at 1 ms per MB -> on the wire during [4, 5.03]: ops 4 and 5, and op 3
+    # whose end touches the window within the 0.05 ms margin
+    res, win = ops_overlapping_exchange(op_ms, [(4, 0, 262144)], 1.0 / (1 << 20), 1.0)
+    assert abs(win[0][0] - 4.0) < 1e-9 and abs(win[0][1] - 5.03) < 1e-6
+    assert res == [3, 4, 5]
+    # a second bucket ready at the same time queues behind the first; the slowdown stretches the reserved ops (op 3 now ends at 4.25,
+    # which is when the wire starts) and the fixed point is stable
+    res2, win2 = ops_overlapping_exchange(op_ms, [(4, 0, 262144), (4, 262144, 524288)], 1.0 / (1 << 20), 1.25)
+    assert abs(win2[0][0] - 4.25) < 1e-9 and win2[1][0] == win2[0][1] and res2 == [3, 4, 5]
+    # nothing to exchange -> nothing reserved; a bucket that is only ready after the last op reserves nothing but the tail
+    assert ops_overlapping_exchange(op_ms, [], 1e-6, 1.2)[0] == []
+    assert ops_overlapping_exchange(op_ms, [(10, 0, 1024)], 1e-9, 1.2)[0] == [9]

@@ -35,3 +35,33 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 def shard_sizes(n: int, world: int) -> List[int]:
     return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+
+
+def ops_overlapping_exchange(op_ms, schedule, ms_per_byte, slowdown, launch_ms=0.03, margin_ms=0.05):
+    """Which backward ops run while the gradient exchange is on the wire (host-side replay used by
+    Engine.reserve_sms_for_exchange).  op_ms[i]: device time of backward op i; schedule: [(n_ops, lo, hi)] from
+    Planner.exchange_schedule (bucket [lo, hi) of fp32 gradients may start once the first n_ops ops have run);
+    ms_per_byte: measured all-reduce speed; slowdown: factor by which an op that leaves SMs to the collective gets slower.
+    Bucket j starts when its last producer op has finished and the wire is free; an op is reserved if its interval
+    touches any bucket's interval (+- margin).  Reserved ops run slower, which moves the windows: iterate to a fixed point.
+    Returns (sorted op indices, [(start_ms, end_ms)] per bucket)."""
+    reserved, windows = set(), []
+    for _ in range(4):
+        end, t = [], 0.0
+        for i, d in enumerate(op_ms):
+            t += d * (slowdown if i in reserved else 1.0)
+            end.append(t)
+        busy, windows = 0.0, []
+        for (n_ops, lo, hi) in schedule:
+            start = max(end[n_ops - 1] if n_ops > 0 else 0.0, busy)
+            busy = start + launch_ms + (hi - lo) * 4 * ms_per_byte
+            windows.append((start, busy))
+        new = set()
+        for i in range(len(op_ms)):
+            s_i, e_i = (end[i - 1] if i else 0.0), end[i]
+            if any(s_i < w1 + margin_ms and e_i > w0 - margin_ms for (w0, w1) in windows):
+                new.add(i)
+        if new == reserved:
+            break
+        reserved = new
+    return sorted(reserved), windows

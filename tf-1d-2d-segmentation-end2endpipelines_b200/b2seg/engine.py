@@ -115,27 +115,9 @@ class Engine:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX, group=group)
         ms = [float(v) for v in tms.tolist()]
         self.exchange_calibration = {"allreduce_GBps": 1e-6 / ms_per_byte, "backward_ms": sum(ms)}
+        from .dist import ops_overlapping_exchange
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
-        slow = sms / float(sms - reserve_sms)
-        reserved = set()
-        for _ in range(3):   # reserved ops run slower, which moves the windows: iterate to a fixed point
-            end, t_acc = [], 0.0
-            for i, d in enumerate(ms):
-                t_acc += d * (slow if i in reserved else 1.0)
-                end.append(t_acc)
-            busy, windows = 0.0, []
-            for (n_ops, lo, hi) in schedule:
-                start = max(end[n_ops - 1] if n_ops > 0 else 0.0, busy)
-                busy = start + 0.03 + (hi - lo) * 4 * ms_per_byte
-                windows.append((start, busy))
-            new = set()
-            for i in range(len(ms)):
-                s_i, e_i = (end[i - 1] if i else 0.0), end[i]
-                if any(s_i < w1 + 0.05 and e_i > w0 - 0.05 for (w0, w1) in windows):
-                    new.add(i)
-            if new == reserved:
-                break
-            reserved = new
+        reserved, windows = ops_overlapping_exchange(ms, schedule, ms_per_byte, sms / float(sms - reserve_sms))
         self.exchange_calibration["reserved_ops"] = len(reserved)
         self.exchange_calibration["exchange_windows_ms"] = [(round(a, 3), round(b, 3)) for (a, b) in windows]
         self._build_plan(reserved, reserve_sms)
