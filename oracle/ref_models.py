@@ -411,6 +411,127 @@ class Ref1D:
                 deconv = blk(k, self.fuse(k, skip, self.up(k, deconv, 2 ** l), None, l), 2 ** l)
             return self.head(k, deconv, levels)
 
+        if self.var == "R2UNetPP":                                        # uv:1119-1224: UNet++ grid, every node = shortcut + ONE recurrent block
+            def node(x, mult):
+                shortcut = self.CB(k, x, W, 1, mult)
+                return k.add([shortcut, self.RCB(k, x, mult)])
+            enc = []
+            for i in range(1, d + 1):
+                c = node(pool, 2 ** (i - 1))
+                pool = k.MaxPooling(c, 2)
+                enc.append(c)
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            enc.append(node(pool, 2 ** d))
+            if self.ds == 1:
+                levels.append(k.Conv(enc[0], 1, 1, name=f"level{d}"))
+            G = {}
+            for i in range(1, d + 1):
+                for j in range(0, d - i + 1):
+                    low = enc[j + 1] if i == 1 else G[j + 1, i - 1]
+                    gate = (lambda t: self.AG(k, t, low, W, 2 ** j)) if self.ag == 1 else (lambda t: t)
+                    tot = None
+                    if i > 1:
+                        tot = gate(G[j, 1])
+                        for q in range(2, i):
+                            tot = k.concatenate([tot, gate(G[j, q])])
+                    skip = gate(enc[j])
+                    G[j, i] = node(self.fuse(k, skip, self.up(k, low, 2 ** j), tot, j), 2 ** j)
+                    if self.ds == 1 and j == 0 and i < d:
+                        levels.append(k.Conv(G[j, i], 1, 1, name=f"level{d - i}"))
+            return self.head(k, G[0, d], levels)
+
+        if self.var == "MultiResUNet3P":                                  # uv:899-977 (restated with its overwrites and its dead block)
+            rp = {}
+            for i in range(1, d + 2):
+                if i > 1:
+                    for q in range(1, i):
+                        c = k.MaxPooling(rp[q], 2 ** (i - q))
+                        pool = k.Activation(c, "sigmoid")
+                        pool = k.concatenate([pool, c])                   # overwritten on every round: only q = i - 1 survives
+                blk = self.MRB(k, pool, 2 ** (i - 1))
+                rp[i] = self.RP(k, blk, d - i + 1, 2 ** i)
+                pool = k.MaxPooling(blk, 2)
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            self.MRB(k, pool, 2 ** d)                                     # :926 built, never used
+            chain = [rp[i] for i in range(1, d + 2)]
+            deconv, outs = chain[-1], {}
+            for j in range(d):
+                lvl = d - j - 1
+                skip = self.AG(k, chain[lvl], deconv, W, 2 ** lvl) if self.ag == 1 else chain[lvl]
+                deconv = k.concatenate([self.up(k, deconv, 2 ** lvl), skip])
+                for m in range(0, j + 1):
+                    src = chain[-1] if m == 0 else outs[m]
+                    deconv = k.concatenate([deconv, k.Activation(k.UpSampling(src, 2 ** (j - m + 1)), "sigmoid")])
+                deconv = self.MRB(k, deconv, 2 ** lvl)
+                outs[j + 1] = deconv
+                if self.ds == 1:
+                    levels.append(k.Conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
+            return self.head(k, deconv, levels)
+
+        if self.var == "UNet4P":                                          # uv:717-834
+            enc = []
+            for i in range(0, d):                                         # dense links from levels 1 .. i-1 (keys are shifted by one, :728-736)
+                if i > 0:
+                    for q in range(1, i):
+                        pool = k.concatenate([pool, k.MaxPooling(enc[q], 2 ** (i - q))])
+                c = self.two(k, pool, 2 ** i)
+                enc.append(c)
+                pool = k.MaxPooling(c, 2)
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            enc.append(self.two(k, pool, 2 ** d))
+            if self.ds == 1:
+                levels.append(k.Conv(enc[0], 1, 1, name=f"level{d}"))
+            G, onDiag = {}, {}
+            for i in range(1, d + 1):
+                for j in range(0, d - i + 1):
+                    low = enc[j + 1] if i == 1 else G[j + 1, i - 1]
+                    gate = (lambda t: self.AG(k, t, low, W, 2 ** j)) if self.ag == 1 else (lambda t: t)
+                    tot = None
+                    if i > 1:
+                        tot = gate(G[j, 1])
+                        for q in range(2, i):
+                            tot = k.concatenate([tot, gate(G[j, q])])
+                    merged = self.fuse(k, gate(enc[j]), self.up(k, low, 2 ** j), tot, j)
+                    if i > 1 and (i + j) == d and j != d - 1:
+                        for m in range(1, i - 1):
+                            merged = k.concatenate([merged, k.UpSampling(onDiag[m], 2 ** (i - m))])
+                    G[j, i] = self.two(k, merged, 2 ** j)
+                    if (i + j) == d:
+                        onDiag[i] = G[j, i]
+                    if self.ds == 1 and j == 0 and i < d:
+                        levels.append(k.Conv(G[j, i], 1, 1, name=f"level{d - i}"))
+            return self.head(k, G[0, d], levels)
+
+        if self.var == "R2UNet3P":                                        # uv:1226-1310
+            def r2(x, mult, drop_first=False):
+                shortcut = self.CB(k, x, W, 1, mult)
+                first = self.RCB(k, x, mult)
+                second = self.RCB(k, x if drop_first else first, mult)    # :1277-1278 overwrite the first block's output
+                return k.add([shortcut, second])
+            enc = []
+            for i in range(1, d + 1):
+                c = r2(pool, 2 ** (i - 1))
+                pool = k.MaxPooling(c, 2)
+                enc.append(c)
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            deconv, outs = r2(pool, 2 ** d), {}
+            for j in range(d):
+                same = self.CB(k, enc[d - j - 1], W, self.ks, 1)
+                for q in range(0, d - j - 1):
+                    same = k.concatenate([same, r2(k.MaxPooling(enc[q], 2 ** ((d - j) - q - 1)), 1)])
+                tot = k.concatenate([same, k.Activation(k.UpSampling(r2(deconv, 1), 2), "sigmoid")])
+                for m in range(0, j):
+                    tot = k.concatenate([tot, k.Activation(k.UpSampling(r2(outs[m], 1, drop_first=True), 2 ** (j - m)), "sigmoid")])
+                deconv = r2(tot, d + 1)
+                outs[j] = deconv
+                if self.ds == 1:
+                    levels.append(k.Conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
+            return self.head(k, deconv, levels)
+
         convs = []
         for i in range(1, d + 1):                                         # encoder uv:267-271
             conv = self.two(k, pool, 2 ** (i - 1))

@@ -60,7 +60,7 @@ def _oracle(ref, ndim, params, x, targets, losses, out_names, loss_weights=None,
     tp = {k: torch.from_numpy(np.array(v)).double() for k, v in params.items()}
     # the MultiRes / ResPath families build ResPaths on the deepest encoder level that nothing consumes (Keras prunes them; the
     # eager oracle evaluates them with weights of its own), hence strict=False for those families only
-    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=not ({getattr(ref, "dec", ""), getattr(ref, "var", "")} & {"MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet"}))
+    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=not ({getattr(ref, "dec", ""), getattr(ref, "var", "")} & {"MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet", "R2UNet3P"}))
     k.override = override
     outs = ref(k, torch.from_numpy(x).double())
     total = 0
@@ -425,7 +425,9 @@ def test_fpn_per_layer(kw):
     check_per_layer(m, RefFPN("FPN", 64, 64, 16, 3, **kw), 2, x, targets, losses, e2e_bound=1.0)
 
 
-@pytest.mark.parametrize("var,kw", [("RUNet", dict(ds=1, t=2)), ("R2UNet", dict(ds=1, ag=1, t=2))], ids=["RUNet", "R2UNet-ag1"])
+@pytest.mark.parametrize("var,kw", [("RUNet", dict(ds=1, t=2)), ("R2UNet", dict(ds=1, ag=1, t=2)), ("R2UNetPP", dict(ds=1, t=1)),
+                                    ("R2UNet3P", dict(ds=1, t=1)), ("UNet4P", dict(ds=1, ag=1)), ("MultiResUNet3P", dict(ds=1))],
+                         ids=["RUNet", "R2UNet-ag1", "R2UNetPP", "R2UNet3P", "UNet4P-ag1", "MultiResUNet3P"])
 def test_1d_recurrent_unets_per_layer(var, kw):
     """RUNet / R2UNet (1DCNN/Models/unet_variants.py:63-72, 979-1117): recurrent conv blocks re-concatenate the block input, R2 adds a
     1x1 shortcut and pools the un-activated sum"""

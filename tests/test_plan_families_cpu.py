@@ -128,6 +128,10 @@ CASES_1D = [
     ("RUNet", dict(ds=1, t=2)),                    # Recurrent_Conv_Block (uv.py:63-72): t rounds of conv + concat with the block input
     ("R2UNet", dict(ds=0, ag=1, t=1)),             # + 1x1 Conv_Block shortcut and Add around each pair
     ("R2UNet", dict(ds=1, lstm=1, t=2)),
+    ("R2UNetPP", dict(ds=1, ag=1, t=1)),           # UNet++ grid of shortcut + ONE recurrent block nodes (:1119)
+    ("R2UNet3P", dict(ds=1, t=1)),                 # :1226; the m-loop drops its first recurrent block (names still consumed)
+    ("MultiResUNet3P", dict(ds=1, ag=1)),          # :899, with its overwritten dense links and its dead bottleneck block
+    ("MultiResUNet3P", dict(ds=0, is_transconv=False)),
 ]
 
 
@@ -140,9 +144,19 @@ def test_1d_family(var, kw):
         g = BCDUNet(L_, depth, ch, W, ks, **kw).BCDUNet().graph
     else:
         g = getattr(UNet(L_, depth, ch, W, ks, **kw), var)().graph
-    kw = {k_: v for k_, v in kw.items() if k_ != "t" or var in ("RUNet", "R2UNet")}
+    kw = {k_: v for k_, v in kw.items() if k_ != "t" or var in ("RUNet", "R2UNet", "R2UNetPP", "R2UNet3P")}
     x = torch.from_numpy(rng.standard_normal((2, L_, ch)).astype(np.float32))
     ts, losses = _targets(g, 2, rng, 1)
     # with lstm=0 the 1D BCDUNet drops its skip connections, so an attention gate built on them is a dangling branch that
     # Keras prunes: the oracle (eager) still evaluates it with weights of its own
-    _run(g, Ref1D(var, L_, depth, ch, W, ks, **kw), x, ts, losses, 1, strict=not ((var == "BCDUNet" and not kw.get("lstm")) or var == "MultiResUNet"))
+    _run(g, Ref1D(var, L_, depth, ch, W, ks, **kw), x, ts, losses, 1, strict=not ((var == "BCDUNet" and not kw.get("lstm")) or var in ("MultiResUNet", "R2UNet3P", "MultiResUNet3P")))
+
+
+@pytest.mark.parametrize("kw", [dict(ds=1), dict(ds=1, ag=1, is_transconv=False)], ids=["ds1", "ds1-ag1-upsample"])
+def test_1d_unet4p_depth3(kw):
+    """1D UNet4+ (uv.py:717-834) at depth 3, where its dense encoder links (levels 1 .. i-1) and anti-diagonal up-links first appear"""
+    rng = np.random.default_rng(5)
+    g = UNet(64, 3, 2, 8, 3, **kw).UNet4P().graph
+    x = torch.from_numpy(rng.standard_normal((2, 64, 2)).astype(np.float32))
+    ts, losses = _targets(g, 2, rng, 1)
+    _run(g, Ref1D("UNet4P", 64, 3, 2, 8, 3, **kw), x, ts, losses, 1, act_atol=2e-7)

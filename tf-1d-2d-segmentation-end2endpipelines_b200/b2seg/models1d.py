@@ -1,5 +1,5 @@
 """1D builder API — drop-in for the reference's TensorFlow/1DCNN/Models/unet_variants.py:222-1117 (class UNet:
-UNet, UNetE, UNetP, UNetPP, UNet3P, MultiResUNet, RUNet, R2UNet) and TensorFlow/1DCNN/Models/BCDUNet.py:79-174 (class BCDUNet).
+UNet, UNetE, UNetP, UNetPP, UNet3P, UNet4P, MultiResUNet, MultiResUNet3P, RUNet, R2UNet, R2UNetPP, R2UNet3P) and TensorFlow/1DCNN/Models/BCDUNet.py:79-174 (class BCDUNet).
 
 Same constructor arguments and method names; the methods return a b2seg.model.Model.  1D tensors (L, C) are held
 as (H=1, W=L, C).  Differences from the 2D family that matter for parity: two Conv-BN-ReLU per level,
@@ -156,16 +156,43 @@ class UNet:
             deconv = conv_block(g, deconv, W, k, 2 ** l)
         return self._finish(g, deconv, levels)
 
-    def _nested(self, variant):                                                               # uv.py:321-645
+    def _nested(self, variant, r2=False):                                                     # uv.py:321-645; R2UNetPP :1119-1224
         self._check()
         W, k, d = self.model_width, self.kernel_size, self.model_depth
         g = Graph(1)
-        convs, bottom = self._encoder(g)
+
+        def r2_block(x, mult):     # R2UNet++ node: 1x1 Conv_Block shortcut + ONE Recurrent_Conv_Block, added (:1132-1134)
+            raw = conv_block(g, x, W, 1, mult)
+            return g.add([raw, recurrent_conv_block(g, x, W, k, mult, self.t)])
+        if r2:
+            pool, convs = g.input(1, self.length, self.num_channel), []
+            for i in range(1, d + 1):
+                conv = r2_block(pool, 2 ** (i - 1))
+                pool = g.pool(conv, 2)
+                convs.append(conv)
+            if self.A_E == 1:
+                pool = feature_extraction_block(g, pool, W, self.feature_number)
+            bottom = r2_block(pool, 2 ** d)
+        elif variant == "UNet4P":
+            # uv.py:727-746: from level 2 on, the outputs of levels 1 .. i-1 (NOT level 0: the loop reads convs[k-1] for k = 1 .. i-1
+            # and level i is stored under key i-1), max-pooled to this level, join the input (no sigmoid in the 1D file)
+            pool, convs = g.input(1, self.length, self.num_channel), []
+            for i in range(0, d):
+                for q in range(1, i):
+                    pool = g.concat([pool, g.pool(convs[q], 2 ** (i - q))])
+                conv = conv_block(g, conv_block(g, pool, W, k, 2 ** i), W, k, 2 ** i)
+                convs.append(conv)
+                pool = g.pool(conv, 2)
+            if self.A_E == 1:
+                pool = feature_extraction_block(g, pool, W, self.feature_number)
+            bottom = conv_block(g, conv_block(g, pool, W, k, 2 ** d), W, k, 2 ** d)
+        else:
+            convs, bottom = self._encoder(g)
         skips = convs + [bottom]
         levels = []
         if self.D_S == 1:
             levels.append(g.conv(convs[0], 1, 1, name=f"level{d}"))
-        X = {}
+        X, diag = {}, {}
         for i in range(1, d + 1):
             for j in range(0, d - i + 1):
                 below = skips[j + 1] if i == 1 else X[(j + 1, i - 1)]
@@ -181,9 +208,17 @@ class UNet:
                     skip = gated(skips[j])
                 up = self._up(g, below, 2 ** j)
                 node = _merge(g, skip, up, extra, self.LSTM, W * 2.0 ** (j - 1), W * 2 ** j)
-                node = conv_block(g, node, W, k, 2 ** j)
-                node = conv_block(g, node, W, k, 2 ** j)
+                if variant == "UNet4P" and i > 1 and i + j == d and j != d - 1:            # :810-813: anti-diagonal up-links
+                    for m in range(1, i - 1):
+                        node = g.concat([node, up_conv_block(g, diag[m], 2 ** (i - m))])
+                if r2:
+                    node = r2_block(node, 2 ** j)
+                else:
+                    node = conv_block(g, node, W, k, 2 ** j)
+                    node = conv_block(g, node, W, k, 2 ** j)
                 X[(j, i)] = node
+                if i + j == d:
+                    diag[i] = node
                 if self.D_S == 1 and j == 0 and i < d:
                     levels.append(g.conv(node, 1, 1, name=f"level{d - i}"))
         return self._finish(g, X[(0, d)], levels)
@@ -226,6 +261,46 @@ class UNet:
 
     def R2UNet(self):                                                                         # uv.py:1046-1117
         return self._recurrent_unet(True)
+
+    def UNet4P(self):                                                                         # uv.py:717-834
+        return self._nested("UNet4P")
+
+    def R2UNetPP(self):                                                                       # uv.py:1119-1224
+        return self._nested("UNetPP", r2=True)
+
+    def R2UNet3P(self):                                                                       # uv.py:1226-1310
+        self._check()
+        W, k, d, t = self.model_width, self.kernel_size, self.model_depth, self.t
+        g = Graph(1)
+
+        def pair(x, mult, first_from=None):
+            raw = conv_block(g, x, W, 1, mult)
+            y = recurrent_conv_block(g, x, W, k, mult, t)
+            # :1277-1278 feed BOTH recurrent blocks with deconvs[m]: the first one's output is dropped (Keras prunes it, its layer
+            # names are still consumed); everywhere else the second block reads the first
+            y = recurrent_conv_block(g, x if first_from == "dropped" else y, W, k, mult, t)
+            return g.add([raw, y])
+        pool, convs = g.input(1, self.length, self.num_channel), []
+        for i in range(1, d + 1):
+            conv = pair(pool, 2 ** (i - 1))
+            pool = g.pool(conv, 2)
+            convs.append(conv)
+        if self.A_E == 1:
+            pool = feature_extraction_block(g, pool, W, self.feature_number)
+        deconv = pair(pool, 2 ** d)
+        levels, decs = [], {}
+        for j in range(d):
+            allc = conv_block(g, convs[d - j - 1], W, k, 1)
+            for q in range(0, d - j - 1):
+                allc = g.concat([allc, pair(g.pool(convs[q], 2 ** ((d - j) - q - 1)), 1)])
+            tot = g.concat([allc, g.act(up_conv_block(g, pair(deconv, 1), 2), "sigmoid")])
+            for m in range(j):
+                tot = g.concat([tot, g.act(up_conv_block(g, pair(decs[m], 1, first_from="dropped"), 2 ** (j - m)), "sigmoid")])
+            deconv = pair(tot, d + 1)
+            decs[j] = deconv
+            if self.D_S == 1:
+                levels.append(g.conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
+        return self._finish(g, deconv, levels)
 
     def UNetE(self):
         return self._nested("UNetE")
@@ -279,6 +354,45 @@ class UNet:
             deconv = self._up(g, deconv, 2 ** l)
             deconv = _merge(g, skip, deconv, None, self.LSTM, W * 2.0 ** (l - 1), W * 2 ** l)
             deconv = multires_block(g, deconv, W, k, 2 ** l, self.alpha)
+        return self._finish(g, deconv, levels)
+
+
+    def MultiResUNet3P(self):                                                                 # uv.py:899-977
+        """As written in the reference, quirks included: the dense-link loop of the encoder overwrites `pool` on every round, so only
+        the previous level's ResPath output survives ([sigmoid(pooled), pooled]); the MultiResBlock built after the encoder loop is
+        never used (the decoder starts from the last ResPath); the earlier rounds and that block are created (layer names are
+        consumed) and pruned."""
+        self._check()
+        W, k, d = self.model_width, self.kernel_size, self.model_depth
+        g = Graph(1)
+        pool, paths = g.input(1, self.length, self.num_channel), []
+        for i in range(1, d + 2):
+            for q in range(1, i):
+                t = g.pool(paths[q - 1], 2 ** (i - q))
+                pool = g.concat([g.act(t, "sigmoid"), t])
+            blk = multires_block(g, pool, W, k, 2 ** (i - 1), self.alpha)
+            paths.append(res_path(g, blk, d - i + 1, W, k, 2 ** i))
+            pool = g.pool(blk, 2)
+        if self.A_E == 1:
+            pool = feature_extraction_block(g, pool, W, self.feature_number)
+        multires_block(g, pool, W, k, 2 ** d, self.alpha)       # :926 dangling
+        deconv, decs, levels = paths[-1], {}, []
+        for j in range(d):
+            l = d - j - 1
+            skip = paths[l]
+            if self.A_G == 1:
+                skip = attention_block(g, paths[l], deconv, W, 2 ** l)
+            deconv = self._up(g, deconv, 2 ** l)
+            if self.LSTM == 1:
+                raise NameError("name 'model_depth' is not defined")   # the reference path is broken here (:942)
+            deconv = g.concat([deconv, skip])
+            for m in range(0, j + 1):
+                t = paths[-1] if m == 0 else decs[m]
+                deconv = g.concat([deconv, g.act(up_conv_block(g, t, 2 ** (j - m + 1)), "sigmoid")])
+            deconv = multires_block(g, deconv, W, k, 2 ** l, self.alpha)
+            decs[j + 1] = deconv
+            if self.D_S == 1:
+                levels.append(g.conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
         return self._finish(g, deconv, levels)
 
 
