@@ -385,6 +385,16 @@ class Model:
             xs = np.asarray(x, np.float32)
             ys = self._targets(y)
             bs = int(batch_size or 32)
+            split = float(kw.get("validation_split") or 0.0)
+            if split and validation_data is None:
+                # Keras holds out the LAST fraction of the samples, before any shuffling (Train.py:411-415)
+                if not 0.0 < split < 1.0:
+                    raise ValueError(f"`validation_split` must be between 0 and 1, received: {split}")
+                cut = int(xs.shape[0] * (1.0 - split))
+                validation_data = (xs[cut:], [t[cut:][:, 0] if self.graph.ndim == 1 else t[cut:] for t in ys])
+                if len(ys) == 1:
+                    validation_data = (validation_data[0], validation_data[1][0])
+                xs, ys = xs[:cut], [t[:cut] for t in ys]
             n = xs.shape[0]
         rng = np.random.default_rng(0)
         self.stop_training = False
