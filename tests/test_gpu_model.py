@@ -347,6 +347,28 @@ def test_fit_and_history_api():
     assert len(w) == len(m.graph.param_specs())
 
 
+def test_fit_with_reference_callbacks_and_validation_split(tmp_path):
+    """the training call of the reference's script (Train.py:372-415): EarlyStopping + best-only ModelCheckpoint + ReduceLROnPlateau on
+    val_loss, validation_split hold-out"""
+    from b2seg.callbacks import EarlyStopping, ModelCheckpoint, ReduceLROnPlateau
+    kw = dict(num_channels=1, output_nums=1, dense_loop=1, is_transconv=True)
+    m = unet_model_builder("UNet", 32, 32, 8, 2, train_mode="from_scratch", **kw).ResNet50()
+    m.compile(loss="binary_crossentropy", optimizer=Adam(2e-3))
+    rng = np.random.default_rng(8)
+    x = rng.random((20, 32, 32, 1), dtype=np.float32)
+    y = (x > 0.5).astype(np.float32)
+    ck = ModelCheckpoint(str(tmp_path / "best_{epoch:02d}.keras"), monitor="val_loss", save_best_only=True, mode="min")
+    cbs = [EarlyStopping(monitor="val_loss", patience=30, mode="min"), ck,
+           ReduceLROnPlateau(monitor="val_loss", factor=0.5, patience=1, mode="min", min_delta=10.0, cooldown=0, min_lr=0)]
+    h = m.fit(x, y, batch_size=8, epochs=4, validation_split=0.2, callbacks=cbs, verbose=0)
+    assert set(h.history) == {"loss", "val_loss", "lr"} and len(h.history["val_loss"]) == 4
+    assert h.history["lr"][0] == pytest.approx(2e-3) and m.optimizer.learning_rate < 2e-3     # min_delta 10 is never beaten -> lr halves
+    assert ck.last_saved is not None and (tmp_path / (ck.last_saved.split("/")[-1] + ".npz")).exists()
+    m2 = unet_model_builder("UNet", 32, 32, 8, 2, train_mode="from_scratch", **kw).ResNet50()
+    m2.load_weights(ck.last_saved)
+    assert all(np.isfinite(v).all() for v in m2.get_weight_dict().values())
+
+
 def test_fit_pipelined_input_matches_train_on_batch():
     """fit() overlaps the host->device copy of batch i+1 with step i and reads the losses back asynchronously: the per-epoch loss
     and the trained weights must equal a plain train_on_batch loop over the same batches (incl. the ragged last batch and a

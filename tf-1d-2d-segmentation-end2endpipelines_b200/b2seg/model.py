@@ -426,14 +426,15 @@ class Model:
             if validation_data is not None:
                 vx, vy = validation_data[:2]
                 logs["val_loss"] = self.evaluate(vx, vy, batch_size=batch_size or 32)
-            for k, v in logs.items():
-                hist.history.setdefault(k, []).append(v)
-            hist.epoch.append(ep)
             if verbose:
                 print(f"Epoch {ep + 1}/{epochs} - {time.time() - t0:.1f}s - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
             for cb in callbacks:
                 if hasattr(cb, "on_epoch_end"):
                     cb.on_epoch_end(ep, logs)
+            # Keras' History callback runs after the user's callbacks: what they add to `logs` (ReduceLROnPlateau's `lr`) is recorded
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            hist.epoch.append(ep)
             if self.stop_training:
                 break
         for cb in callbacks:
