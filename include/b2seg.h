@@ -36,7 +36,8 @@ extern "C" {
 #define B2SEG_MAX_GRADSRC 6
 
 /* activation codes (Keras Activation strings: 2DCNN/models/unet_variants.py:7-24,67-82) */
-enum { B2SEG_ACT_NONE = 0, B2SEG_ACT_RELU = 1, B2SEG_ACT_LEAKY = 2 /* slope 0.3 */, B2SEG_ACT_SIGMOID = 3, B2SEG_ACT_SOFTMAX = 4 };
+enum { B2SEG_ACT_NONE = 0, B2SEG_ACT_RELU = 1, B2SEG_ACT_LEAKY = 2 /* slope 0.3 */, B2SEG_ACT_SIGMOID = 3, B2SEG_ACT_SOFTMAX = 4,
+       B2SEG_ACT_TANH = 5 /* Self-ONN decoders (unet_variants.py:656,663); streaming kernels only, not the conv epilogue */ };
 
 typedef struct b2seg_view {
   uint64_t ptr;          /* address of element (n=0,h=0,w=0,c=0); 16-byte aligned */
@@ -192,9 +193,12 @@ typedef struct b2seg_loss_desc {
 } b2seg_loss_desc;
 
 typedef struct b2seg_eltwise_desc {
-  int32_t op;  /* 0: out = act(a + b) ; 1: out = a (copy) ; 2: out = a * leaky'(y=b) ; 3: out = act(a + b + c) */
+  int32_t op;  /* 0: out = act(a + b) ; 1: out = a (copy) ; 2: out = a * leaky'(y=b) ; 3: out = act(a + b + c) ;
+                * 4: out = a^p           (tf.math.pow(input, p) of the operational layers, onn_layers.py:19,41) ;
+                * 5: out = p * a^(p-1) * b (its backward: a = the forward input, b = the gradient w.r.t. a^p) ; p = `act`, 2..8 */
   b2seg_view a, b, c, out;
-  int32_t act; /* B2SEG_ACT_* applied by ops 0 and 3 (Add -> Activation('relu'), unet_variants.py:73-74,96-97,110-111) */
+  int32_t act; /* B2SEG_ACT_* applied by ops 0 and 3 (Add -> Activation('relu'), unet_variants.py:73-74,96-97,110-111);
+                * the exponent p for ops 4 and 5 */
 } b2seg_eltwise_desc;
 
 /* UpSampling2D(size, 'bilinear') / UpSampling1D(size) (unet_variants.py:37; 1DCNN :122) with an optional activation
@@ -259,6 +263,19 @@ typedef struct b2seg_rowsum_desc {
   uint64_t out; int32_t accumulate;
 } b2seg_rowsum_desc;
 
+/* A model output that is an Activation over a tensor instead of a pointwise convolution with a fused activation: the Self-ONN
+ * builders end in Oper2D(output_nums, (1,1), activation=final_activation, q) = activation(sum of q pointwise convolutions)
+ * (unet_variants.py:1107-1108; deep-supervision levels :653 are the same without activation).
+ * Forward: y[pix][o] = act(x[pix][o]), o < cout <= 8, fp32 (the layout b2seg_loss reads).  Backward: dx[pix][o] = dlogits[pix][o]
+ * as bf16, channels >= cout zero (b2seg_loss has already applied the activation's derivative). */
+typedef struct b2seg_outact_desc {
+  b2seg_view x;        /* bf16 logits, C = 8 (cout real channels) */
+  int32_t cout, act;   /* act: NONE, SIGMOID or SOFTMAX */
+  uint64_t y;          /* fp32 [N,H,W,cout] */
+  uint64_t dlogits;    /* fp32 [N,H,W,cout] (backward input) */
+  b2seg_view dx;       /* bf16 (backward output) */
+} b2seg_outact_desc;
+
 const char* b2seg_last_error(void);
 int b2seg_version(void);
 int b2seg_device_check(int device);
@@ -289,13 +306,15 @@ int b2seg_lstm_fwd(const b2seg_lstm_desc* d, void* stream);
 int b2seg_lstm_bwd(const b2seg_lstm_desc* d, void* stream);
 int b2seg_pool_bwd(const b2seg_poolbwd_desc* d, void* stream);
 int b2seg_rowsum(const b2seg_rowsum_desc* d, void* stream);
+int b2seg_outact_fwd(const b2seg_outact_desc* d, void* stream);
+int b2seg_outact_bwd(const b2seg_outact_desc* d, void* stream);
 
 /* ---- plan: a recorded sequence of the ops above, replayed per step (optionally as a CUDA graph) ---- */
 typedef struct b2seg_plan b2seg_plan;
 enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
        B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,
        B2SEG_OP_MEMSET, B2SEG_OP_RESIZE_FWD, B2SEG_OP_RESIZE_BWD, B2SEG_OP_MULBC_FWD, B2SEG_OP_MULBC_BWD, B2SEG_OP_COLSTATS,
-       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM };
+       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM, B2SEG_OP_OUTACT_FWD, B2SEG_OP_OUTACT_BWD };
 typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
 
 /* Data parallel: backward-phase ops added to a plan AFTER this call size their grids for (SMs - sms), leaving room for the

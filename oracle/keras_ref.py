@@ -191,11 +191,11 @@ class KerasRef:
         y = F.conv_transpose2d(self._cf(x), w4.permute(3, 2, 0, 1), b, stride=(sh, sw), padding=(ph, pw))
         return self._rec(name, self._cl(y))
 
-    def BatchNormalization(self, x):
+    def BatchNormalization(self, x, name=None):
         """tf.keras.layers.BatchNormalization() (unet_variants.py:11): axis -1, eps 1e-3, momentum 0.99; training uses the
         batch mean and biased variance; moving variance takes the Bessel-corrected batch variance on 4-D inputs
         (fused op) and the biased one on 3-D inputs †."""
-        name = self._name("batch_normalization", None)
+        name = self._name("batch_normalization", name)
         c = x.shape[-1]
         gamma = self._weight(name, "gamma", (c,), "ones")
         beta = self._weight(name, "beta", (c,), "zeros")
@@ -214,9 +214,35 @@ class KerasRef:
         y = (x - mean) * torch.rsqrt(var + 1e-3) * gamma + beta
         return self._rec(name, y)
 
-    def Activation(self, x, fn):
-        name = self._name("activation", None)
+    def Activation(self, x, fn, name=None):
+        name = self._name("activation", name)
         return self._rec(name, self.activation_fn(fn, x))
+
+    def Oper(self, x, filters, kernel, q=1, strides=1, padding="same", activation=None, transpose=False):
+        """Self-ONN operational layer: Oper2D / Oper2DTranspose (2DCNN/models/onn_layers.py:6-25, 29-48) and their 1D twins
+        (1DCNN/Models/ONN_layers.py).  A nested tf.keras.Model `oper2d[_k]` with q explicitly named convolutions:
+            y = ONN_Conv_1(x) + sum_{i=1}^{q-1} ONN_Conv_{i+1}(tf.math.pow(x, i+1));  y = Activation(activation)(y) if given.
+        Recorded tensors: every convolution (`<model>/ONN_Conv_i`), every power (`<model>/tf_math_pow{i}`), the running sum after
+        terms 3, 5, ... (`<model>/add[_k]`), and the model output under the model's own name.  Weight names
+        `<model>/ONN_Conv_i/{kernel,bias}` †(the nesting of variable names under the sub-model is unverified)."""
+        base = self._name("oper" + self._sfx() + ("_transpose" if transpose else ""), None)
+        stem = "ONN_TransConv" if transpose else "ONN_Conv"
+        one = (lambda t, nm: self.ConvTranspose(t, filters, kernel, strides, padding=padding, name=nm)) if transpose else \
+              (lambda t, nm: self.Conv(t, filters, kernel, strides=strides, padding=padding, name=nm))
+        y = one(x, f"{base}/{stem}_1")
+        k = 0
+        for i in range(1, int(q)):
+            xp = self._rec(f"{base}/tf_math_pow{i}", torch.pow(x, i + 1))
+            y = y + one(xp, f"{base}/{stem}_{i + 1}")
+            if (i + 1) % 2 == 1 or i + 1 == q:        # the product sums three terms per pass; same check points
+                last = (i + 1 == q) and activation is None
+                y = self._rec(base if last else f"{base}/add" + (f"_{k}" if k else ""), y)
+                k += 1
+        if activation is not None:
+            if activation in ("sigmoid", "softmax"):
+                self.logits[base] = y
+            y = self._rec(base, self.activation_fn(activation, y))
+        return y
 
     def MaxPooling(self, x, size):
         """MaxPooling2D((p,p)) / MaxPooling1D(p): stride = pool, 'valid' (unet_variants.py:357,790)."""

@@ -17,7 +17,8 @@ class Ref2D:
     """unet_model_builder(...).<Encoder>() with train_mode='from_scratch' (2DCNN/models/unet_variants.py:1045-1115)."""
 
     def __init__(self, decoder_name, length, width, model_width, model_depth, num_channels=3, output_nums=1, ds=0, ae=0, ag=0, lstm=0,
-                 dense_loop=1, feature_number=1024, is_transconv=True, alpha=1.0, final_activation="sigmoid"):
+                 dense_loop=1, feature_number=1024, is_transconv=True, alpha=1.0, final_activation="sigmoid", q=3):
+        self.q = q
         self.dec, self.W, self.d = decoder_name, model_width, model_depth
         self.out_n, self.ds, self.ae, self.ag, self.lstm = output_nums, ds, ae, ag, lstm
         self.dense_loop, self.feat, self.tc, self.alpha, self.fa = dense_loop, feature_number, is_transconv, alpha, final_activation
@@ -182,7 +183,96 @@ class Ref2D:
         return deconv, levels
 
     # whole model ------------------------------------------------------------------------------------------
+    # Self-ONN decoders ----------------------------------------------------------------------------------
+    def OP(self, k, x, f, ks, **kw):                                      # Oper2D(f, ks, q=q)(x), onn_layers.py:6-25
+        return k.Oper(x, f, ks, q=self.q, **kw)
+
+    def self_up(self, k, x, f):                                           # :655-658
+        if self.tc:
+            return k.Oper(x, f, (4, 4), q=self.q, strides=(2, 2), padding="same", activation="tanh", transpose=True)
+        return k.UpSampling(x, (2, 2), "bilinear")
+
+    def bn_tanh(self, k, x, tag):                                         # explicitly named pair, e.g. :662-663
+        return k.Activation(k.BatchNormalization(x, name=f"bn_layer_{tag}"), "tanh", name=f"activ_func_{tag}")
+
+    def dec_self_unet(self, k, skips):                                    # SelfUNet :644-664
+        W, d = self.W, self.d
+        levels, deconv = [], skips[-1]
+        for j in range(d):
+            f = W * 2 ** (d - j - 1)
+            if self.ds == 1:
+                levels.append(self.OP(k, deconv, 1, (1, 1)))
+            deconv = self.self_up(k, deconv, f)
+            deconv = k.concatenate([deconv, skips[d - j - 1]])
+            deconv = self.bn_tanh(k, self.OP(k, deconv, f, (3, 3)), f"{j}")
+        return deconv, levels
+
+    def dec_self_unetpp(self, k, skips):                                  # SelfUNetPP :667-710
+        W, d = self.W, self.d
+        levels, X = [], {}
+        if self.ds == 1:
+            levels.append(self.OP(k, skips[0], 1, (1, 1)))
+        for i in range(1, d + 1):
+            for j in range(0, d - i + 1):
+                f = W * 2 ** j
+                if i == 1:
+                    cat = k.concatenate([self.self_up(k, skips[j + 1], f), skips[j]])
+                else:
+                    tot = X[(j, 1)]
+                    for m in range(2, i):
+                        tot = k.concatenate([tot, X[(j, m)]])
+                    cat = k.concatenate([k.concatenate([self.self_up(k, X[(j + 1, i - 1)], f), tot]), skips[j]])
+                X[(j, i)] = self.bn_tanh(k, self.OP(k, cat, f, (3, 3)), f"{i}_{j}")
+                if self.ds == 1 and j == 0 and i < d:
+                    levels.append(self.OP(k, X[(j, i)], 1, (1, 1)))
+        return X[(0, d)], levels
+
+    def dec_self_unet3p(self, k, skips):                                  # SelfUNet3P :713-747
+        W, d = self.W, self.d
+        levels, deconv, D = [], skips[-1], {}
+        for j in range(d):
+            allc = self.bn_tanh(k, self.OP(k, skips[d - j - 1], W, (3, 3)), f"{j}")
+            for m in range(0, d - j - 1):
+                p = 2 ** ((d - j) - m - 1)
+                t = self.bn_tanh(k, self.OP(k, k.MaxPooling(skips[m], (p, p)), W, (3, 3)), f"{j}_{m}")
+                allc = k.concatenate([allc, t])
+            t = k.Activation(k.UpSampling(self.OP(k, deconv, W, (3, 3)), (2, 2), "bilinear"), "tanh")
+            tot = k.concatenate([allc, t])
+            for m in range(j):
+                fct = 2 ** (j - m)
+                t = k.Activation(k.UpSampling(self.OP(k, D[m], W, (3, 3)), (fct, fct), "bilinear"), "tanh")
+                tot = k.concatenate([tot, t])
+            deconv = self.OP(k, tot, W * (d + 1), (3, 3))
+            D[j] = deconv
+            if self.ds == 1:
+                levels.append(self.OP(k, deconv, 1, (1, 1), strides=(2, 2)))
+        return deconv, levels
+
+    def call_self(self, k: KerasRef, x):
+        """decoder_name[0:4] == 'Self': encoder :782-786, latent operational_dense_block :59-64, head :1107-1108"""
+        W, d = self.W, self.d
+        pool = k.Input(x)
+        convs = []
+        for i in range(1, d + 2):
+            conv = self.OP(k, pool, W * 2 ** (i - 1), (3, 3))
+            pool = k.MaxPooling(conv, (2, 2))
+            convs.append(conv)
+        conv = self.OP(k, conv, W * 2 ** d, (3, 3))
+        for _ in range(self.dense_loop):
+            conv = k.add([conv, self.OP(k, conv, W * 2 ** d, (3, 3))])
+        if self.ae == 1:
+            sh = conv.shape
+            z = k.Dense(k.Flatten(conv), self.feat, name="features")
+            z = k.Dense(z, W * 2 ** d * sh[1] * sh[2])
+            conv = k.Reshape(z, (sh[1], sh[2], W * 2 ** d))
+        skips = convs[:d] + [conv]
+        deconv, levels = {"SelfUNet": self.dec_self_unet, "SelfUNetPP": self.dec_self_unetpp, "SelfUNet3P": self.dec_self_unet3p}[self.dec](k, skips)
+        out = self.OP(k, deconv, self.out_n, (1, 1), activation=self.fa)
+        return list(reversed(levels + [out])) if self.ds == 1 else [out]
+
     def __call__(self, k: KerasRef, x):
+        if str(self.dec).startswith("Self"):
+            return self.call_self(k, x)
         W, d = self.W, self.d
         pool = k.Input(x)
         convs = []
@@ -293,8 +383,9 @@ class Ref1D:
     """UNet(...).<variant>() (1DCNN/Models/unet_variants.py:222-897) and BCDUNet(...).BCDUNet() (BCDUNet.py:79-174)."""
 
     def __init__(self, variant, length, model_depth, num_channel, model_width, kernel_size, problem_type="Regression", output_nums=1,
-                 ds=1, ae=0, ag=0, lstm=0, alpha=1, feature_number=1024, is_transconv=True, dense_loop=1, t=2):
+                 ds=1, ae=0, ag=0, lstm=0, alpha=1, feature_number=1024, is_transconv=True, dense_loop=1, t=2, q=3):
         self.t = t
+        self.q = q
         self.var, self.L, self.d, self.W, self.ks = variant, length, model_depth, model_width, kernel_size
         self.pt, self.out_n, self.ds, self.ae, self.ag, self.lstm = problem_type, output_nums, ds, ae, ag, lstm
         self.alpha, self.feat, self.tc, self.dense_loop = alpha, feature_number, is_transconv, dense_loop
@@ -409,6 +500,71 @@ class Ref1D:
                 if self.ds == 1:
                     levels.append(k.Conv(deconv, 1, 1, name=f"level{d - j}"))
                 deconv = blk(k, self.fuse(k, skip, self.up(k, deconv, 2 ** l), None, l), 2 ** l)
+            return self.head(k, deconv, levels)
+
+        if self.var in ("SelfUNetPP", "SelfR2UNetPP"):                    # uv:1412-1513, 1312-1410: UNet++ grid of operational layers
+            O = lambda t, mult, q=None: k.Oper(t, W * mult, self.ks, q=self.q if q is None else q)     # Oper1D, ONN_layers.py:7-28
+
+            def srcb(t, mult, q):                                         # Self_Recurrent_Conv_Block uv:75-84
+                h = t
+                for _ in range(self.t):
+                    h = k.concatenate([O(h, mult, q), t])
+                return self.CB(k, h, W, self.ks, mult)
+            r2 = self.var == "SelfR2UNetPP"
+            enc = []
+            for i in range(1, d + 1):
+                c = srcb(pool, 2 ** (i - 1), self.q) if r2 else O(O(pool, 2 ** (i - 1)), 2 ** (i - 1))
+                pool = k.MaxPooling(c, 2)
+                enc.append(c)
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            enc.append(srcb(pool, 2 ** d, 1) if r2 else O(O(pool, 2 ** d), 2 ** d))                  # :1332 passes q=1
+            if self.ds == 1:
+                levels.append(k.Conv(enc[0], 1, 1, name=f"level{d}"))
+
+            def rise(t, mult):                                            # :1352 / :1453
+                if self.tc:
+                    return k.Oper(t, W * mult, 4, q=self.q, strides=2, padding="same", activation="tanh", transpose=True)
+                return k.UpSampling(t, 2)
+            G = {}
+            for i in range(1, d + 1):
+                for j in range(0, d - i + 1):
+                    low = enc[j + 1] if i == 1 else G[j + 1, i - 1]
+                    gate = (lambda t: self.AG(k, t, low, W, 2 ** j)) if self.ag == 1 else (lambda t: t)
+                    tot = None
+                    if i > 1:
+                        tot = gate(G[j, 1])
+                        for m in range(2, i):
+                            tot = k.concatenate([tot, gate(G[j, m])])
+                    skip = gate(enc[j])
+                    merged = self.fuse(k, skip, rise(low, 2 ** j), tot, j)
+                    G[j, i] = O(merged, 2 ** j) if r2 else O(O(merged, 2 ** j), 2 ** j)
+                    if self.ds == 1 and j == 0 and i < d:
+                        levels.append(k.Conv(G[j, i], 1, 1, name=f"level{d - i}"))
+            return self.head(k, G[0, d], levels)
+
+        if self.var == "SelfUNet3P":                                      # uv:1515-1583 (sigmoid after the up-sampling, no BatchNorm anywhere)
+            O = lambda t, f: k.Oper(t, f, self.ks, q=self.q)
+            enc = []
+            for i in range(1, d + 1):
+                c = O(O(pool, W * 2 ** (i - 1)), W * 2 ** (i - 1))
+                pool = k.MaxPooling(c, 2)
+                enc.append(c)
+            if self.ae == 1:
+                pool = self.FE(k, pool)
+            deconv = O(O(pool, W * 2 ** d), W * 2 ** d)
+            D = {}
+            for j in range(d):
+                allc = O(enc[d - j - 1], W)
+                for m in range(0, d - j - 1):
+                    allc = k.concatenate([allc, O(k.MaxPooling(enc[m], 2 ** ((d - j) - m - 1)), W)])
+                tot = k.concatenate([allc, k.Activation(k.UpSampling(O(deconv, W), 2), "sigmoid")])
+                for m in range(j):
+                    tot = k.concatenate([tot, k.Activation(k.UpSampling(O(D[m], W), 2 ** (j - m)), "sigmoid")])
+                deconv = O(tot, W * (d + 1))
+                D[j] = deconv
+                if self.ds == 1:
+                    levels.append(k.Conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
             return self.head(k, deconv, levels)
 
         if self.var == "R2UNetPP":                                        # uv:1119-1224: UNet++ grid, every node = shortcut + ONE recurrent block

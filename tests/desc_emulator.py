@@ -115,6 +115,8 @@ def _act(x, code):
         return torch.where(x > 0, x, 0.3 * x)
     if code == L.ACT_SIGMOID:
         return torch.sigmoid(x)
+    if code == L.ACT_TANH:
+        return torch.tanh(x)
     return x
 
 
@@ -125,6 +127,8 @@ def _dact_from_y(y, code):
         return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.3))
     if code == L.ACT_SIGMOID:
         return y * (1 - y)
+    if code == L.ACT_TANH:
+        return 1 - y * y
     return torch.ones_like(y)
 
 
@@ -291,6 +295,21 @@ def emu_head_bwd(mem, d):
     mem.f32(d.db, d.cout)[:] += dl.reshape(-1, d.cout).sum(0)
 
 
+def emu_outact_fwd(mem, d):
+    assert d.x.C == 8 and 1 <= d.cout <= 8
+    z = mem.gather_view(d.x)[..., :d.cout]
+    y = torch.softmax(z, -1) if d.act == L.ACT_SOFTMAX else _act(z, d.act)
+    mem.f32(d.y, y.numel())[:] = y.reshape(-1)
+
+
+def emu_outact_bwd(mem, d):
+    assert d.dx.C == 8 and 1 <= d.cout <= 8
+    n = d.dx.N * d.dx.H * d.dx.W
+    dx = torch.zeros(d.dx.N, d.dx.H, d.dx.W, 8, dtype=torch.float64)
+    dx[..., :d.cout] = mem.f32(d.dlogits, n * d.cout).view(d.dx.N, d.dx.H, d.dx.W, d.cout)
+    mem.write_view(d.dx, dx)
+
+
 def emu_loss(mem, d):
     n = d.n_pix * d.cout
     p, t = mem.f32(d.y_pred, n).view(d.n_pix, d.cout), mem.f32(d.y_true, n).view(d.n_pix, d.cout)
@@ -323,7 +342,12 @@ def emu_eltwise(mem, d):
     elif d.op == 2:
         bb = mem.gather_view(d.b)
         o = a * torch.where(bb > 0, torch.ones_like(bb), torch.full_like(bb, 0.3))
+    elif d.op == 4:            # a^p, p = d.act
+        o = a ** int(d.act)
+    elif d.op == 5:            # p * a^(p-1) * b
+        o = int(d.act) * a ** (int(d.act) - 1) * mem.gather_view(d.b)
     else:
+        assert d.op == 1, d.op
         o = a
     mem.write_view(d.out, o)
 
@@ -465,7 +489,7 @@ EMU = {L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_fina
        L.OP_MEMSET: emu_memset, L.OP_RESIZE_FWD: emu_resize_fwd, L.OP_RESIZE_BWD: emu_resize_bwd,
        L.OP_MULBC_FWD: emu_mulbc_fwd, L.OP_MULBC_BWD: emu_mulbc_bwd, L.OP_COLSTATS: emu_colstats,
        L.OP_LSTM_FWD: emu_lstm_fwd, L.OP_LSTM_BWD: emu_lstm_bwd, L.OP_POOL_BWD: emu_pool_bwd,
-       L.OP_ROWSUM: emu_rowsum}
+       L.OP_ROWSUM: emu_rowsum, L.OP_OUTACT_FWD: emu_outact_fwd, L.OP_OUTACT_BWD: emu_outact_bwd}
 
 
 def run_phase(mem, planner, phase, first_op=0, n_ops=None):

@@ -15,7 +15,7 @@ from oracle.keras_ref import KerasRef, keras_adam_step, keras_loss
 from oracle.ref_models import Ref1D, Ref2D
 
 
-def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, strict=True, act_atol=1e-8):
+def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, strict=True, act_atol=1e-8, loss_rtol=1e-7, adam_atol=2e-6, act_rtol=0.0, grad_rtol=1e-6):
     N = x.shape[0]
     params = init_params(graph, seed=7)
     # make BN affine and biases non-trivial so their handling is actually tested
@@ -60,8 +60,8 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, stric
         want = outs[o["index"]].detach()
         if ndim == 1:
             got = got.squeeze(1)
-        assert torch.allclose(got, want, atol=1e-8), (o["name"], float((got - want).abs().max()))
-    assert abs(float(mem.f32(pl.loss_ptr, 1)) - float(total.detach())) < 1e-7 * max(1.0, abs(float(total.detach())))
+        assert torch.allclose(got, want, atol=1e-8 + act_rtol * float(want.abs().max())), (o["name"], float((got - want).abs().max()))
+    assert abs(float(mem.f32(pl.loss_ptr, 1)) - float(total.detach())) < loss_rtol * max(1.0, abs(float(total.detach())))
     # per-layer activations
     checked = 0
     for name, (view, C, kind) in pl.taps.items():
@@ -73,7 +73,8 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, stric
         want = k.acts[name].detach()
         if ndim == 1:
             got = got.squeeze(1)
-        assert torch.allclose(got, want, atol=act_atol), (name, float((got - want).abs().max()))
+        # act_rtol is relative to the tensor's largest value (sums of large cancelling terms in the un-normalised Self-ONN graphs)
+        assert torch.allclose(got, want, atol=act_atol + act_rtol * float(want.abs().max())), (name, float((got - want).abs().max()))
         checked += 1
     assert checked > 3
     # activation gradients (w.r.t. raw conv outputs)
@@ -86,6 +87,8 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, stric
             gtol = 1e-9 + 5e-7 * float(k.acts[name].grad.abs().max())
             assert torch.allclose(got, k.acts[name].grad, atol=gtol), ("grad", name, float((got - k.acts[name].grad).abs().max()))
     # parameter gradients
+    bn_convs = {u["node"].name for u in pl.units if u["kind"] == "conv" and u["bn"] is not None}
+    gmax = max([float(v.grad.abs().max()) for v in tp.values() if v.grad is not None] + [1.0])   # "analytically zero" is relative to this
     for e in pl.params:
         if not e.trainable:
             continue
@@ -98,10 +101,10 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, stric
         gi = torch.from_numpy(pl.to_internal(e.key, want.numpy().astype(np.float32))).double()  # layout round trip of the oracle grad
         if e.key.endswith("/bias") and e.key.rsplit("/", 1)[0] in [u["node"].name for u in pl.units if u["kind"] == "conv" and u["bn"] is not None]:
             # conv bias followed by BN: gradient is analytically zero; the product emits exact zeros
-            assert float(got64.abs().max()) == 0 and float(want.abs().max()) < 1e-9, e.key
+            assert float(got64.abs().max()) == 0 and float(want.abs().max()) < 1e-9 * gmax, e.key
             continue
         scale = float(want.abs().max()) + 1e-12
-        assert float((got - want).abs().max()) < 1e-6 * scale + 1e-7 * 0 + 1e-9, (e.key, float((got - want).abs().max()), scale)
+        assert float((got - want).abs().max()) < grad_rtol * scale + 1e-9, (e.key, float((got - want).abs().max()), scale)
         assert got.shape == want.shape and gi.numel() == e.size
     # Adam + moving statistics
     run_phase(mem, pl, 2)
@@ -109,11 +112,11 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, stric
         if e.trainable:
             w = tp[e.key].detach().clone()
             g = tp[e.key].grad if tp[e.key].grad is not None else torch.zeros_like(w)
-            if e.key.endswith("/bias") and float(g.abs().max()) < 1e-9:
+            if e.key.endswith("/bias") and e.key.rsplit("/", 1)[0] in bn_convs and float(g.abs().max()) < 1e-9 * gmax:
                 g = torch.zeros_like(w)
             keras_adam_step(w, g, torch.zeros_like(w), torch.zeros_like(w), 1, lr=lr)
             got = torch.from_numpy(pl.from_internal(e.key, mem.f32(pl.w_ptr + 4 * e.offset, e.size).numpy().astype(np.float32))).double()
-            assert torch.allclose(got, w, atol=2e-6), (e.key, float((got - w).abs().max()))
+            assert torch.allclose(got, w, atol=adam_atol), (e.key, float((got - w).abs().max()))
         else:
             got = torch.from_numpy(pl.from_internal(e.key, mem.f32(pl.mov_ptr + 4 * e.offset, e.size).numpy().astype(np.float32))).double()
             assert torch.allclose(got, k.new_moving[e.key], atol=1e-6), e.key

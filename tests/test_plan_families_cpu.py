@@ -16,9 +16,10 @@ def _targets(graph, N, rng, ndim):
     for n in graph.outputs:
         H, W, C = n.shape
         shape = (N, H, W, C) if ndim == 2 else (N, W, C)
-        if n.name == "out" and n.attrs.get("activation") == "sigmoid":
+        final = n.attrs.get("activation") if n.name == "out" else (n.attrs.get("fn") if n.op == "act" else None)   # Self-ONN head: an Activation
+        if final == "sigmoid":
             ts.append(torch.from_numpy((rng.random(shape) > 0.6).astype(np.float32))); losses.append("bce")
-        elif n.name == "out" and n.attrs.get("activation") == "softmax":
+        elif final == "softmax":
             lab = rng.integers(0, C, shape[:-1])
             ts.append(torch.from_numpy(np.eye(C, dtype=np.float32)[lab])); losses.append("cce")
         else:
@@ -83,6 +84,35 @@ def test_2d_family_depth3(dec, kw):
     # descriptors carry eps / momentum as float32 (relative 6e-8): through these 60-90 layer graphs a pre-activation within 1e-7 of
     # zero can land on the other side of the ReLU, hence 2e-7 instead of 1e-8 on the activations
     _run(g, Ref2D(dec, 32, 32, 8, 3, **kw), x, ts, losses, 2, loss_weights=[1.0 - 0.1 * i for i in range(len(ts))], strict=strict, act_atol=2e-7)
+
+
+CASES_SELF = [
+    ("SelfUNet", dict()),                                              # :644 operational layers, transposed operational up-sampling
+    ("SelfUNet", dict(ds=1, is_transconv=False, q=4)),                 # two sum passes: (c1 + c2 + c3), (+ c4)
+    ("SelfUNet", dict(ds=1, output_nums=3, final_activation="softmax", dense_loop=2)),
+    ("SelfUNetPP", dict(ds=1)),                                        # :667
+    ("SelfUNetPP", dict(is_transconv=False, q=2)),
+    ("SelfUNet3P", dict(ds=1)),                                        # :713 (stride-2 operational deep-supervision heads)
+    ("SelfUNet", dict(ae=1, feature_number=16, q=1)),                  # q = 1: an operational layer is a plain convolution
+]
+
+
+@pytest.mark.parametrize("dec,kw", CASES_SELF, ids=[f"{d}-{'-'.join(f'{k}{v}' for k, v in kw.items())}" for d, kw in CASES_SELF])
+def test_2d_self_onn_family(dec, kw):
+    """Self-ONN decoders (unet_variants.py:59-64, 644-747, 782-786, 1107-1108; onn_layers.py:6-48)"""
+    rng = np.random.default_rng(5)
+    depth = 3 if dec == "SelfUNetPP" else 2     # (deeper un-normalised cubic encoders make the Adam check ill-conditioned)
+    S = 8 * 2 ** depth // 2
+    kw = dict(num_channels=2, **kw)
+    g = unet_model_builder(dec, S, S, 8, depth, train_mode="from_scratch", **kw).build_graph()
+    # the Self-ONN encoder is linear and un-normalised (:782-786): powers of powers overflow quickly, keep the input small
+    x = torch.from_numpy(0.5 * (rng.random((2, S, S, 2), dtype=np.float32) - 0.3))
+    ts, losses = _targets(g, 2, rng, 2)
+    # SelfUNet3P feeds un-normalised cubic features to the sigmoid head (:741, :1108): at random init the logits saturate, where the
+    # REPORTED loss scalar (probabilities clipped to [1e-7, 1 - 1e-7] by b2seg_loss) departs from Keras' from-logits value; the
+    # gradient seed (p - y) / n and every tensor below are still held to the tight tolerances
+    _run(g, Ref2D(dec, S, S, 8, depth, **kw), x, ts, losses, 2, loss_weights=[1.0 - 0.1 * i for i in range(len(ts))], act_atol=2e-7,
+         loss_rtol=1e-2 if dec == "SelfUNet3P" else 1e-7)
 
 
 CASES_FPN = [dict(), dict(ds=1), dict(ag=1, ds=1, output_nums=3, final_activation="softmax"), dict(lstm=1), dict(ae=1, feature_number=16)]
@@ -150,6 +180,33 @@ def test_1d_family(var, kw):
     # with lstm=0 the 1D BCDUNet drops its skip connections, so an attention gate built on them is a dangling branch that
     # Keras prunes: the oracle (eager) still evaluates it with weights of its own
     _run(g, Ref1D(var, L_, depth, ch, W, ks, **kw), x, ts, losses, 1, strict=not ((var == "BCDUNet" and not kw.get("lstm")) or var in ("MultiResUNet", "R2UNet3P", "MultiResUNet3P")))
+
+
+CASES_1D_SELF = [
+    ("SelfUNetPP", dict(ds=1)),                        # uv.py:1412: Oper1D pairs + Oper1DTranspose(kernel 4, tanh)
+    ("SelfUNetPP", dict(ds=0, ag=1, is_transconv=False, q=2)),
+    ("SelfUNetPP", dict(ds=1, lstm=1, q=2, ae=1, feature_number=16)),
+    ("SelfR2UNetPP", dict(ds=1, t=2)),                 # :1312: Self_Recurrent_Conv_Block encoder (bottom level with q=1), single Oper1D nodes
+    ("SelfR2UNetPP", dict(ds=0, t=1, ag=1)),
+    ("SelfUNet3P", dict(ds=1)),                        # :1515
+]
+
+
+@pytest.mark.parametrize("var,kw", CASES_1D_SELF, ids=[f"{d}-{'-'.join(f'{k}{v}' for k, v in kw.items())}" for d, kw in CASES_1D_SELF])
+def test_1d_self_onn_family(var, kw):
+    """1D Self-ONN variants (1DCNN/Models/unet_variants.py:75-84, 1312-1583; ONN_layers.py:7-52)"""
+    rng = np.random.default_rng(6)
+    L_, depth, ch, ks = 32, 2, 2, 3
+    W = 16 if kw.get("lstm") else 8
+    g = getattr(UNet(L_, depth, ch, W, ks, **kw), var)().graph
+    # two un-normalised operational layers per level: powers of powers (3^12 at depth 2) overflow for |x| > 1 — keep the signal small
+    x = torch.from_numpy((0.3 * (rng.random((2, L_, ch)) - 0.5)).astype(np.float32))
+    ts, losses = _targets(g, 2, rng, 1)
+    # Adam's first step is lr * g / (|g| + eps): an element 1e-6 below its tensor's largest gradient (these cubic networks spread
+    # gradients over six decades) turns the float32 descriptor rounding the gradient check allows into a visible step difference
+    # ... and activations reach 1e4 (cubes of cubes), so the float32-descriptor noise (relative 5e-8, amplified 3x per cube) is
+    # judged relative to the value
+    _run(g, Ref1D(var, L_, depth, ch, W, ks, **kw), x, ts, losses, 1, act_atol=2e-7, act_rtol=2e-6, grad_rtol=1e-5, adam_atol=1e-4, loss_rtol=1e-6)
 
 
 @pytest.mark.parametrize("kw", [dict(ds=1), dict(ds=1, ag=1, is_transconv=False)], ids=["ds1", "ds1-ag1-upsample"])

@@ -15,7 +15,7 @@ import numpy as np
 
 @dataclass(eq=False)
 class Node:
-    op: str                      # input conv tconv bn act pool up concat add mul convlstm flatten dense reshape
+    op: str                      # input conv tconv bn act pool up concat add mul pow convlstm flatten dense reshape
     name: str
     inputs: List["Node"]
     shape: Tuple[int, int, int]  # (H, W, C) of the output, batch excluded
@@ -36,6 +36,7 @@ _BASE_NAMES = {
     ("up", 2): "up_sampling2d", ("up", 1): "up_sampling1d", ("concat", 0): "concatenate", ("add", 0): "add",
     ("mul", 0): "tf.math.multiply", ("convlstm", 2): "conv_lstm2d", ("convlstm", 1): "conv_lstm1d", ("flatten", 0): "flatten",
     ("dense", 0): "dense", ("reshape", 0): "reshape", ("input", 0): "input",
+    ("oper", 2): "oper2d", ("oper", 1): "oper1d", ("opert", 2): "oper2d_transpose", ("opert", 1): "oper1d_transpose",
 }
 
 
@@ -99,11 +100,11 @@ class Graph:
         return self._add("tconv", [x], (H * sh, W * sw, filters), name, filters=int(filters), kernel=(kh, kw), strides=(sh, sw),
                          padding=padding, init="glorot_uniform")
 
-    def bn(self, x: Node) -> Node:
-        return self._add("bn", [x], x.shape, eps=1e-3, momentum=0.99)
+    def bn(self, x: Node, name=None) -> Node:
+        return self._add("bn", [x], x.shape, name, eps=1e-3, momentum=0.99)
 
-    def act(self, x: Node, fn: str) -> Node:
-        return self._add("act", [x], x.shape, fn=fn)
+    def act(self, x: Node, fn: str, name=None) -> Node:
+        return self._add("act", [x], x.shape, name, fn=fn)
 
     def pool(self, x: Node, size) -> Node:
         ph, pw = self._pair(size, self.ndim)
@@ -133,6 +134,41 @@ class Graph:
         if a.shape[:2] != b.shape[:2] or b.C not in (1, a.C):
             raise ValueError(f"Incompatible shapes for multiply: {a.shape} vs {b.shape}")
         return self._add("mul", [a, b], a.shape)
+
+    def pow(self, x: Node, p: int, name=None) -> Node:
+        """tf.math.pow(x, p), integer p >= 2 (operational layers, 2DCNN/models/onn_layers.py:19,41)"""
+        if not 2 <= int(p) <= 8:
+            raise ValueError(f"power {p} outside 2..8")
+        return self._add("pow", [x], x.shape, name, p=int(p))
+
+    def oper(self, x: Node, filters, kernel, q=1, strides=1, padding="same", activation=None, transpose=False) -> Node:
+        """Self-ONN operational layer Oper2D / Oper1D / Oper2DTranspose / Oper1DTranspose (2DCNN/models/onn_layers.py:6-48,
+        1DCNN/Models/ONN_layers.py): a nested tf.keras.Model named oper2d[_k] holding q convolutions ONN_Conv_1..q
+        (ONN_TransConv_1..q); call() = conv_1(x) + sum_{p=2..q} conv_p(x ** p), then an optional Activation.
+        Lowered as what it is: q convolutions, q-1 element-wise powers and the running sum.  Only the nested model consumes an
+        auto-name counter (its convolutions and its Activation are explicitly named)."""
+        base = self._auto_name("opert" if transpose else "oper")
+        stem = "ONN_TransConv" if transpose else "ONN_Conv"
+        terms = []
+        for i in range(1, int(q) + 1):
+            xi = x if i == 1 else self.pow(x, i, name=f"{base}/tf_math_pow{i - 1}")
+            if transpose:
+                terms.append(self.tconv(xi, filters, kernel, strides, padding=padding, name=f"{base}/{stem}_{i}"))
+            else:
+                terms.append(self.conv(xi, filters, kernel, strides=strides, padding=padding, name=f"{base}/{stem}_{i}"))
+        acc = terms[0]
+        rest = terms[1:]
+        k = 0
+        while rest:                      # `x += ...` (onn_layers.py:19): a left fold; three-way sums keep it to one pass for q = 3
+            take, rest = rest[:2], rest[2:]
+            last = not rest and activation is None
+            acc = self._add("add", [acc] + take, acc.shape, base if last else f"{base}/add" + (f"_{k}" if k else ""))
+            k += 1
+        if activation is not None:
+            acc = self._add("act", [acc], acc.shape, base, fn=activation)
+        # the node called `base` is the nested model's output (what Keras reports as the output of layer oper2d[_k]);
+        # with q = 1 and no activation that is the convolution itself, which keeps its ONN_Conv_1 name
+        return acc
 
     def convlstm(self, xs: List[Node], filters, kernel, name=None) -> Node:
         """ConvLSTM over a length-1 sequence whose single frame is the channel-concat of xs

@@ -156,15 +156,35 @@ class UNet:
             deconv = conv_block(g, deconv, W, k, 2 ** l)
         return self._finish(g, deconv, levels)
 
-    def _nested(self, variant, r2=False):                                                     # uv.py:321-645; R2UNetPP :1119-1224
+    def _nested(self, variant, r2=False, onn=None):                                           # uv.py:321-645; R2UNetPP :1119-1224
         self._check()
         W, k, d = self.model_width, self.kernel_size, self.model_depth
         g = Graph(1)
 
+        # Self-ONN grids (SelfUNetPP :1412-1513, SelfR2UNetPP :1312-1410): operational layers (no BatchNorm, no activation) take the
+        # place of the Conv_Blocks and a tanh operational transposed layer (kernel 4) the place of trans_conv1D
+        def oper2(x, mult):
+            return g.oper(g.oper(x, W * mult, k, q=self.q), W * mult, k, q=self.q)
+
+        def self_recurrent(x, mult, q):                                                      # Self_Recurrent_Conv_Block :75-84
+            h = x
+            for _ in range(self.t):
+                h = g.concat([g.oper(h, W * mult, k, q=q), x])
+            return conv_block(g, h, W, k, mult)
+
         def r2_block(x, mult):     # R2UNet++ node: 1x1 Conv_Block shortcut + ONE Recurrent_Conv_Block, added (:1132-1134)
             raw = conv_block(g, x, W, 1, mult)
             return g.add([raw, recurrent_conv_block(g, x, W, k, mult, self.t)])
-        if r2:
+        if onn is not None:
+            pool, convs = g.input(1, self.length, self.num_channel), []
+            for i in range(1, d + 1):
+                conv = self_recurrent(pool, 2 ** (i - 1), self.q) if onn == "r2" else oper2(pool, 2 ** (i - 1))
+                pool = g.pool(conv, 2)
+                convs.append(conv)
+            if self.A_E == 1:
+                pool = feature_extraction_block(g, pool, W, self.feature_number)
+            bottom = self_recurrent(pool, 2 ** d, 1) if onn == "r2" else oper2(pool, 2 ** d)   # (:1332 passes q=1 at the bottom)
+        elif r2:
             pool, convs = g.input(1, self.length, self.num_channel), []
             for i in range(1, d + 1):
                 conv = r2_block(pool, 2 ** (i - 1))
@@ -206,12 +226,17 @@ class UNet:
                     parts = [gated(X[(j, q)]) for q in range(1, i)]
                     extra = parts[0] if len(parts) == 1 else g.concat(parts)
                     skip = gated(skips[j])
-                up = self._up(g, below, 2 ** j)
+                if onn is not None and self.is_transconv:
+                    up = g.oper(below, W * 2 ** j, 4, q=self.q, strides=2, activation="tanh", transpose=True)
+                else:
+                    up = self._up(g, below, 2 ** j)
                 node = _merge(g, skip, up, extra, self.LSTM, W * 2.0 ** (j - 1), W * 2 ** j)
                 if variant == "UNet4P" and i > 1 and i + j == d and j != d - 1:            # :810-813: anti-diagonal up-links
                     for m in range(1, i - 1):
                         node = g.concat([node, up_conv_block(g, diag[m], 2 ** (i - m))])
-                if r2:
+                if onn is not None:
+                    node = g.oper(node, W * 2 ** j, k, q=self.q) if onn == "r2" else oper2(node, 2 ** j)
+                elif r2:
                     node = r2_block(node, 2 ** j)
                 else:
                     node = conv_block(g, node, W, k, 2 ** j)
@@ -311,11 +336,34 @@ class UNet:
     def UNetPP(self):
         return self._nested("UNetPP")
 
-    def UNet3P(self):                                                                         # uv.py:647-715
+    def SelfUNetPP(self):                                                                     # uv.py:1412-1513
+        return self._nested("UNetPP", onn="plain")
+
+    def SelfR2UNetPP(self):                                                                   # uv.py:1312-1410
+        return self._nested("UNetPP", onn="r2")
+
+    def SelfUNet3P(self):                                                                     # uv.py:1515-1583
+        return self.UNet3P(onn=True)
+
+    def UNet3P(self, onn=False):                                                              # uv.py:647-715
         self._check()
         W, k, d = self.model_width, self.kernel_size, self.model_depth
         g = Graph(1)
-        convs, deconv = self._encoder(g)
+        if onn:
+            # every Conv_Block becomes one operational layer (two per encoder level), nothing is normalised
+            def conv_block(g, x, W, k, mult):
+                return g.oper(x, W * mult, k, q=self.q)
+            pool, convs = g.input(1, self.length, self.num_channel), []
+            for i in range(1, d + 1):
+                conv = conv_block(g, conv_block(g, pool, W, k, 2 ** (i - 1)), W, k, 2 ** (i - 1))
+                pool = g.pool(conv, 2)
+                convs.append(conv)
+            if self.A_E == 1:
+                pool = feature_extraction_block(g, pool, W, self.feature_number)
+            deconv = conv_block(g, conv_block(g, pool, W, k, 2 ** d), W, k, 2 ** d)
+        else:
+            conv_block = globals()["conv_block"]
+            convs, deconv = self._encoder(g)
         levels, decs = [], {}
         for j in range(d):
             parts = [conv_block(g, convs[d - j - 1], W, k, 1)]

@@ -12,8 +12,9 @@ import numpy as np
 
 from .graph import Graph, Node
 
-IN_SCOPE_DECODERS = ("UNet", "UNetE", "UNetP", "UNetPP", "UNet3P", "UNet4P", "UNet4PV2", "MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet")
-_OUT_OF_SCOPE = ("SelfUNet", "SelfUNetPP", "SelfUNet3P")   # Self-ONN layers (onn_layers.py): SURVEY 8(f) rank 4
+IN_SCOPE_DECODERS = ("UNet", "UNetE", "UNetP", "UNetPP", "UNet3P", "UNet4P", "UNet4PV2", "MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet",
+                     "SelfUNet", "SelfUNetPP", "SelfUNet3P")
+SELF_ONN_DECODERS = ("SelfUNet", "SelfUNetPP", "SelfUNet3P")   # operational layers (onn_layers.py): SURVEY 8(f) rank 4
 
 
 # ---- block library (reference unet_variants.py:7-122) ------------------------------------------------------
@@ -222,12 +223,91 @@ def decoder_kssnet(g: Graph, skips, W, d, D_S, A_G, LSTM, is_transconv, kernel, 
     return deconv, levels
 
 
-def encoder_block_scratch(g: Graph, x, decoder_name, W, d, alpha):                       # :750-792
+# ---- Self-ONN decoders (:644-747): operational layers = sums of convolutions over element-wise powers of the input ----------
+def _self_up(g: Graph, x, filters, is_transconv, q):
+    if is_transconv:                                                                     # Oper2DTranspose(..., activation='tanh') :656
+        return g.oper(x, filters, (4, 4), q=q, strides=(2, 2), activation="tanh", transpose=True)
+    return up_conv_block(g, x)
+
+
+def _bn_tanh(g: Graph, x, tag):
+    return g.act(g.bn(x, name=f"bn_layer_{tag}"), "tanh", name=f"activ_func_{tag}")
+
+
+def decoder_self_unet(g: Graph, skips, W, d, D_S, is_transconv, q):                      # SelfUNet :644-664
+    levels = []
+    deconv = skips[-1]
+    for j in range(d):
+        l = d - j - 1
+        if D_S == 1:
+            levels.append(g.oper(deconv, 1, (1, 1), q=q))                                # :653 (unnamed: the output is called oper2d_k)
+        deconv = _self_up(g, deconv, W * 2 ** l, is_transconv, q)
+        deconv = g.concat([deconv, skips[l]])
+        deconv = _bn_tanh(g, g.oper(deconv, W * 2 ** l, (3, 3), q=q), j)                  # :660-663
+    return deconv, levels
+
+
+def decoder_self_unetpp(g: Graph, skips, W, d, D_S, is_transconv, q):                    # SelfUNetPP :667-710
+    levels = []
+    if D_S == 1:
+        levels.append(g.oper(skips[0], 1, (1, 1), q=q))                                  # :672
+    node = {}
+    for i in range(1, d + 1):
+        for j in range(d - i + 1):
+            below = skips[j + 1] if i == 1 else node[j + 1, i - 1]
+            parts = [_self_up(g, below, W * 2 ** j, is_transconv, q)]
+            if i > 1:
+                tot = node[j, 1]
+                for k in range(2, i):
+                    tot = g.concat([tot, node[j, k]])
+                parts.append(tot)
+            parts.append(skips[j])
+            cat = parts[0]
+            for t in parts[1:]:                                                          # Concat_Block: a left fold (:27-32)
+                cat = g.concat([cat, t])
+            node[j, i] = _bn_tanh(g, g.oper(cat, W * 2 ** j, (3, 3), q=q), f"{i}_{j}")
+            if D_S == 1 and j == 0 and i < d:
+                levels.append(g.oper(node[j, i], 1, (1, 1), q=q))                        # :707
+    return node[0, d], levels
+
+
+def decoder_self_unet3p(g: Graph, skips, W, d, D_S, q):                                  # SelfUNet3P :713-747
+    levels = []
+    deconv = skips[-1]
+    done = []
+    for j in range(d):
+        row = _bn_tanh(g, g.oper(skips[d - j - 1], W, (3, 3), q=q), j)
+        for k in range(d - j - 1):
+            p = 2 ** (d - j - k - 1)
+            row = g.concat([row, _bn_tanh(g, g.oper(g.pool(skips[k], (p, p)), W, (3, 3), q=q), f"{j}_{k}")])
+        tot = g.concat([row, g.act(up_conv_block(g, g.oper(deconv, W, (3, 3), q=q), (2, 2)), "tanh")])
+        for m in range(j):
+            f = 2 ** (j - m)
+            tot = g.concat([tot, g.act(up_conv_block(g, g.oper(done[m], W, (3, 3), q=q), (f, f)), "tanh")])
+        deconv = g.oper(tot, W * (d + 1), (3, 3), q=q)                                   # :741 (no BN, no activation)
+        done.append(deconv)
+        if D_S == 1:
+            levels.append(g.oper(deconv, 1, (1, 1), q=q, strides=(2, 2)))                # :745
+    return deconv, levels
+
+
+def operational_dense_block(g: Graph, x, filters, kernel, num_layers, q):                # :59-64
+    x = g.oper(x, filters, kernel, q=q)
+    for _ in range(num_layers):
+        x = g.add([x, g.oper(x, filters, kernel, q=q)])
+    return x
+
+
+def encoder_block_scratch(g: Graph, x, decoder_name, W, d, alpha, q=3):                  # :750-792
     convs = []
     pool = x
     conv = x
     for i in range(1, d + 2):
-        if decoder_name in ("MultiResUNet", "MultiResUNet3P"):
+        if str(decoder_name).startswith("Self"):                                         # :782-786 (linear: no BN, no activation)
+            conv = g.oper(pool, W * 2 ** (i - 1), (3, 3), q=q)
+            pool = g.pool(conv, (2, 2))
+            convs.append(conv)
+        elif decoder_name in ("MultiResUNet", "MultiResUNet3P"):
             conv = multires_block(g, pool, W * 2 ** (i - 1), (3, 3), alpha)
             pool = g.pool(conv, (2, 2))
             convs.append(res_path(g, conv, d - i + 1, W * 2 ** (i - 1), (3, 3)))
@@ -253,9 +333,11 @@ def encoder_block_scratch(g: Graph, x, decoder_name, W, d, alpha):              
     return convs, conv
 
 
-def latent_layer(g: Graph, x, decoder_name, W, d, alpha, dense_loop):                    # :966-974
+def latent_layer(g: Graph, x, decoder_name, W, d, alpha, dense_loop, q=3):               # :966-974
     if decoder_name in ("MultiResUNet", "MultiResUNet3P", "KSSNet"):
         return multires_block(g, x, W * 2 ** d, (3, 3), alpha)
+    if str(decoder_name).startswith("Self"):
+        return operational_dense_block(g, x, W * 2 ** d, (3, 3), dense_loop, q)
     return dense_block(g, x, W * 2 ** d, (3, 3), dense_loop)
 
 
@@ -306,13 +388,11 @@ class unet_model_builder:
         if self.train_mode == "pretrained_encoder":
             raise NotImplementedError("train_mode='pretrained_encoder' needs tf.keras.applications ImageNet weights; "
                                       "only the 'from_scratch' hot path is implemented")
-        if self.decoder_name in _OUT_OF_SCOPE or str(self.decoder_name).startswith("Self"):
-            raise NotImplementedError(f"decoder '{self.decoder_name}' is outside the hot-path scope (SURVEY §8)")
         d, W = self.model_depth, self.model_width
         g = Graph(2)
         inputs = g.input(self.length, self.width, self.num_channels)
-        convs, conv = encoder_block_scratch(g, inputs, self.decoder_name, W, d, self.alpha)
-        conv = latent_layer(g, conv, self.decoder_name, W, d, self.alpha, self.dense_loop)
+        convs, conv = encoder_block_scratch(g, inputs, self.decoder_name, W, d, self.alpha, self.q)
+        conv = latent_layer(g, conv, self.decoder_name, W, d, self.alpha, self.dense_loop, self.q)
         if self.A_E == 1:
             conv = feature_extraction_block(g, conv, W * 2 ** d, self.feature_number)
         skips = convs[:d] + [conv]
@@ -329,10 +409,20 @@ class unet_model_builder:
             deconv, levels = decoder_unet3p(g, skips, W, d, self.D_S)
         elif name == "MultiResUNet":
             deconv, levels = decoder_unet(g, skips, W, d, self.D_S, self.A_G, self.LSTM, self.is_transconv, multires=((3, 3), self.alpha))
+        elif name == "SelfUNet":
+            deconv, levels = decoder_self_unet(g, skips, W, d, self.D_S, self.is_transconv, self.q)
+        elif name == "SelfUNetPP":
+            deconv, levels = decoder_self_unetpp(g, skips, W, d, self.D_S, self.is_transconv, self.q)
+        elif name == "SelfUNet3P":
+            deconv, levels = decoder_self_unet3p(g, skips, W, d, self.D_S, self.q)
         else:
             # decoder_block() (:936-963) leaves `deconv` unbound for an unknown name
             raise UnboundLocalError("local variable 'deconv' referenced before assignment")
         out = g.conv(deconv, self.output_nums, (1, 1), activation=self.final_activation, name="out")
+        if str(name).startswith("Self"):
+            # :1107-1108 replaces `out` by an operational layer (the Conv2D above is left dangling and pruned); its
+            # output carries the nested model's auto-name, not 'out'
+            out = g.oper(deconv, self.output_nums, (1, 1), q=self.q, activation=self.final_activation)
         model_name = ("DenseNet121(CheXNet)" if encoder_name == "CheXNet" else encoder_name) + "_" + str(self.decoder_name)
         outputs = [out]
         if self.D_S == 1:

@@ -261,7 +261,9 @@ class Planner:
                     absorbed.add(id(b))
                     last = b
                 c = self._sole(last, "act")
-                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                # tanh (Self-ONN decoders) lives in the streaming kernels only: fused when a BatchNorm sits in between
+                if c is not None and c not in g.outputs and (c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid")
+                                                             or (c.attrs["fn"] == "tanh" and u["bn"] is not None)):
                     u["act"] = c
                     absorbed.add(id(c))
                     last = c
@@ -279,14 +281,14 @@ class Planner:
             elif n.op == "add":
                 u = dict(kind="add", node=n, out=n, act=None)
                 c = self._sole(n, "act")
-                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU"):
+                if c is not None and c not in g.outputs and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU"):
                     u["act"], u["out"] = c, c
                     absorbed.add(id(c))
                 self.units.append(u)
             elif n.op == "up":
                 u = dict(kind="up", node=n, out=n, act=None)
                 c = self._sole(n, "act")
-                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                if c is not None and c not in g.outputs and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid", "tanh"):
                     u["act"], u["out"] = c, c
                     absorbed.add(id(c))
                 self.units.append(u)
@@ -295,14 +297,21 @@ class Planner:
             elif n.op == "bn":
                 u = dict(kind="bn", node=n, out=n, act=None)
                 c = self._sole(n, "act")
-                if c is not None and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                if c is not None and c not in g.outputs and c.attrs["fn"] in ("relu", "ReLU", "LeakyReLU", "sigmoid", "tanh"):
                     u["act"], u["out"] = c, c
                     absorbed.add(id(c))
                 self.units.append(u)
             elif n.op == "act":
-                if n.attrs["fn"] not in ("relu", "ReLU", "LeakyReLU", "sigmoid"):
+                if n in g.outputs and n.attrs["fn"] in ("sigmoid", "softmax", "linear") and n.C <= 8:
+                    # a model output that is an Activation over a tensor (the Self-ONN head, unet_variants.py:1107-1108):
+                    # fp32 probabilities for the loss straight from the bf16 logits
+                    self.units.append(dict(kind="outact", node=n, out=n, src=n.inputs[0], fn=n.attrs["fn"]))
+                    continue
+                if n.attrs["fn"] not in ("relu", "ReLU", "LeakyReLU", "sigmoid", "tanh"):
                     raise PlanError(f"standalone activation '{n.attrs['fn']}' ({n.name}) is not lowered")
                 self.units.append(dict(kind="act", node=n, out=n))
+            elif n.op == "pow":
+                self.units.append(dict(kind="pow", node=n, out=n))
             elif n.op == "mul":
                 self.units.append(dict(kind="mul", node=n, out=n))
             elif n.op == "convlstm":
@@ -315,7 +324,14 @@ class Planner:
                 self.units.append(dict(kind=n.op, node=n, out=n))
             else:
                 raise PlanError(f"layer type '{n.op}' ({n.name}) is not lowered yet")
-        self.unit_of_out = {id(u["out"]): u for u in self.units}
+            if n in g.outputs and self.units[-1]["kind"] not in ("head", "outact"):
+                # any other tensor used as a model output (a Self-ONN deep-supervision level is the bare sum of q pointwise
+                # convolutions, :653): produced by its own unit, then exported as a linear output
+                last = self.units[-1]
+                if last["out"] is not n or n.C > 8:
+                    raise PlanError(f"output {n.name} ({n.op}, {n.C} channels) is not lowered")
+                self.units.append(dict(kind="outact", node=n, out=None, src=n, fn="linear"))
+        self.unit_of_out = {id(u["out"]): u for u in self.units if u["out"] is not None}
         for u in self.units:
             if u.get("pool") is not None:
                 self.unit_of_out[id(u["pool"])] = u
@@ -337,7 +353,7 @@ class Planner:
                 parent[ra] = rb
 
         for n in g.nodes:
-            if n.op in ("bn", "act", "pool", "up"):
+            if n.op in ("bn", "act", "pool", "up", "pow"):
                 union(n, n.inputs[0])
             elif n.op == "add":
                 for i in n.inputs:
@@ -576,8 +592,10 @@ class Planner:
         act = self._act_code(u["act"])
         bias = self.pw(f"{n.name}/bias")
         strided = n.op == "conv" and a["strides"] != (1, 1)
-        if strided and not (a["kernel"] == (1, 1) and a["padding"] == "valid"):
-            raise PlanError(f"{n.name}: only 1x1 'valid' strided convolutions are lowered")
+        if strided and not (a["kernel"] == (1, 1) and (a["padding"] == "valid" or (n.inputs[0].shape[0] % a["strides"][0] == 0
+                                                                                  and n.inputs[0].shape[1] % a["strides"][1] == 0))):
+            # ('same' pads nothing for a 1x1 kernel when the stride divides the map: Oper2D(1, (1,1), strides=(2,2)), :745)
+            raise PlanError(f"{n.name}: only 1x1 strided convolutions without padding are lowered")
 
         def conv_desc(out_view, act_code, stats_ptr):
             if n.op == "tconv":
@@ -856,6 +874,60 @@ class Planner:
         self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(f"{n.name}/kernel"), units, 1, 1, fin, dx), f"dgrad {n.name}", flops=flops)
         self._add_gsrc(n.inputs[0], GSrc(dx))
 
+    def _fwd_pow(self, u):
+        """tf.math.pow(x, p) of an operational layer (onn_layers.py:19): one element-wise pass (padding lanes stay 0)"""
+        n = u["node"]
+        x = self.phys[id(n.inputs[0])]
+        dests = self._dests(n)
+        self.phys[id(n)] = Phys(dests[0], n.C, list(x.segs))
+        nv = lw.NULL_VIEW.to_c()
+        self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(4, x.view.to_c(), nv, nv, dests[0].to_c(), n.attrs["p"]), n.name)
+        self._copy_extra(dests[0], dests[1:])
+        self.taps[n.name] = (dests[0], n.C, "act")
+
+    def _bwd_pow(self, u):
+        n = u["node"]
+        if n.inputs[0].op == "input":
+            return
+        dy = self._single_grad(n)
+        if dy is None:
+            return
+        x = self.phys[id(n.inputs[0])]
+        dx = self._grad_like(n.inputs[0])
+        nv = lw.NULL_VIEW.to_c()
+        self.emit(1, L.OP_ELTWISE, L.EltwiseDesc(5, x.view.to_c(), dy.to_c(), nv, dx.to_c(), n.attrs["p"]), f"pow bwd {n.name}")
+        self._add_gsrc(n.inputs[0], GSrc(dx))
+
+    def _fwd_outact(self, u):
+        n, src = u["node"], u["src"]
+        x = self.phys[id(src)]
+        if x.Cp != 8 or list(x.segs) != [(0, src.C)]:
+            raise PlanError(f"output {n.name}: expected one dense 8-channel block, got {x.Cp} channels / {x.segs}")
+        H, W, co = n.shape
+        npix = self.N * H * W
+        y = self.alloc(npix * co * 4, "output")
+        dl = self.alloc(npix * co * 4, "grad") if self.training else 0
+        tgt = self.alloc(npix * co * 4, "target") if self.training else 0
+        act = L.ACT_CODES[u["fn"]]
+        u["desc"] = L.OutActDesc(x.view.to_c(), co, act, y, dl, lw.NULL_VIEW.to_c())
+        self.emit(0, L.OP_OUTACT_FWD, u["desc"], f"output {n.name}")
+        self.outputs.append(dict(index=self.g.outputs.index(n), name=n.name, ptr=y, shape=(self.N, H, W, co), target_ptr=tgt, act=act,
+                                 dlogits=dl, npix=npix, cout=co))
+
+    def _bwd_outact(self, u):
+        n, src = u["node"], u["src"]
+        o = next(o for o in self.outputs if o["name"] == n.name)
+        idx = o["index"]
+        kind = LOSS_KINDS[(self.losses[idx] if self.losses else "bce")]
+        wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
+        self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr),
+                  f"loss {n.name}")
+        dx = self._grad_like(src)
+        d = L.OutActDesc.from_buffer_copy(u["desc"])
+        d.dx = dx.to_c()
+        self.emit(1, L.OP_OUTACT_BWD, d, f"output bwd {n.name}")
+        self._add_gsrc(src, GSrc(dx))
+
     def _fwd_head(self, u):
         n = u["node"]
         a = n.attrs
@@ -1030,9 +1102,18 @@ class Planner:
         self.emit(1, L.OP_RESIZE_BWD, L.ResizeDesc(dx.to_c(), dy.to_c(), yf, fh, fw, mode, act, 0), f"up bwd {n.name}")
         self._add_gsrc(n.inputs[0], GSrc(dx))
 
+    def _pool_sources(self, pool_node: Node) -> List[GSrc]:
+        """dense gradient sources of a max-pool output; many of them (an operational layer consumes its input q times, a
+        recurrent block t + 1 times) are summed first so that the pooled tensor's backward sees one routed source, not a dozen"""
+        srcs = self._direct_sources(pool_node, self.gsrc.get(id(pool_node), []))
+        if len(srcs) > L.MAX_GRADSRC - 2:
+            self.gsrc[id(pool_node)] = srcs
+            srcs = [GSrc(self._single_grad(pool_node))]
+        return srcs
+
     def _bwd_pool(self, u):
         n = u["node"]
-        srcs = self._direct_sources(n, self.gsrc.get(id(n), []))
+        srcs = self._pool_sources(n)
         for s in srcs:
             self._add_gsrc(n.inputs[0], GSrc(s.view, 1, tuple(n.attrs["size"])))
 
@@ -1135,7 +1216,7 @@ class Planner:
         srcs = list(self.gsrc.get(id(out_node), []))
         if u["pool"] is not None:
             ph, pw_ = u["pool"].attrs["size"]
-            for s in self._direct_sources(u["pool"], self.gsrc.get(id(u["pool"]), [])):
+            for s in self._pool_sources(u["pool"]):
                 srcs.append(GSrc(s.view, 1, (ph, pw_)))
         if not srcs:
             return  # dead branch (no gradient reaches it)

@@ -145,6 +145,8 @@ static PreparedOp* prepare_any(int op, const void* desc, size_t bytes) {
     B2_CASE(B2SEG_OP_LSTM_BWD, b2seg_lstm_desc, prepare_lstm_bwd)
     B2_CASE(B2SEG_OP_POOL_BWD, b2seg_poolbwd_desc, prepare_pool_bwd)
     B2_CASE(B2SEG_OP_ROWSUM, b2seg_rowsum_desc, prepare_rowsum)
+    B2_CASE(B2SEG_OP_OUTACT_FWD, b2seg_outact_desc, prepare_outact_fwd)
+    B2_CASE(B2SEG_OP_OUTACT_BWD, b2seg_outact_desc, prepare_outact_bwd)
     default:
       set_error("unknown op code %d", op);
       return nullptr;
@@ -188,6 +190,8 @@ int b2seg_sizeof_desc(int op) {
     case B2SEG_OP_LSTM_BWD: return (int)sizeof(b2seg_lstm_desc);
     case B2SEG_OP_POOL_BWD: return (int)sizeof(b2seg_poolbwd_desc);
     case B2SEG_OP_ROWSUM: return (int)sizeof(b2seg_rowsum_desc);
+    case B2SEG_OP_OUTACT_FWD:
+    case B2SEG_OP_OUTACT_BWD: return (int)sizeof(b2seg_outact_desc);
     default: return -1;
   }
 }
@@ -227,6 +231,8 @@ B2_ENTRY(b2seg_lstm_fwd, b2seg_lstm_desc, b2::prepare_lstm_fwd)
 B2_ENTRY(b2seg_lstm_bwd, b2seg_lstm_desc, b2::prepare_lstm_bwd)
 B2_ENTRY(b2seg_pool_bwd, b2seg_poolbwd_desc, b2::prepare_pool_bwd)
 B2_ENTRY(b2seg_rowsum, b2seg_rowsum_desc, b2::prepare_rowsum)
+B2_ENTRY(b2seg_outact_fwd, b2seg_outact_desc, b2::prepare_outact_fwd)
+B2_ENTRY(b2seg_outact_bwd, b2seg_outact_desc, b2::prepare_outact_bwd)
 
 int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
   if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");

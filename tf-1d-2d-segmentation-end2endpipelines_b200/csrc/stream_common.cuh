@@ -38,6 +38,7 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
     case B2SEG_ACT_RELU: return fmaxf(x, 0.f);
     case B2SEG_ACT_LEAKY: return x > 0.f ? x : 0.3f * x;
     case B2SEG_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    case B2SEG_ACT_TANH: return tanhf(x);
     default: return x;
   }
 }
@@ -47,6 +48,7 @@ __device__ __forceinline__ float act_bwd_from_y(float y, int act) {
     case B2SEG_ACT_RELU: return y > 0.f ? 1.f : 0.f;
     case B2SEG_ACT_LEAKY: return y > 0.f ? 1.f : 0.3f;
     case B2SEG_ACT_SIGMOID: return y * (1.f - y);
+    case B2SEG_ACT_TANH: return 1.f - y * y;
     default: return 1.f;
   }
 }

@@ -1010,6 +1010,21 @@ __global__ void eltwise_kernel(EltK k) {
       load8(vaddr(k.b, n, h, w, v * 8), b);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = a[e] * (b[e] > 0.f ? 1.f : 0.3f);
+    } else if (k.op == 4 || k.op == 5) {
+      // operational layers (onn_layers.py:19): 4: a^p ; 5: p * a^(p-1) * b, p = k.act >= 2 (repeated products, exact in fp32)
+      const int reps = k.op == 4 ? k.act - 1 : k.act - 2;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = a[e];
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] *= a[e];
+      }
+      if (k.op == 5) {
+        load8(vaddr(k.b, n, h, w, v * 8), b);
+        const float p = (float)k.act;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = p * o[e] * b[e];
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = a[e];
@@ -1028,6 +1043,8 @@ struct EltLaunch : PreparedOp {
 };
 PreparedOp* prepare_eltwise(const b2seg_eltwise_desc* d) {
   if (d->out.C % 8) { set_error("eltwise: C %% 8"); return nullptr; }
+  if (d->op < 0 || d->op > 5) { set_error("eltwise: unknown op %d", d->op); return nullptr; }
+  if ((d->op == 4 || d->op == 5) && (d->act < 2 || d->act > 8)) { set_error("eltwise: power %d outside 2..8", d->act); return nullptr; }
   auto* L = new EltLaunch();
   L->k.op = d->op; L->k.act = d->act; L->k.a = dv(d->a); L->k.b = dv(d->b); L->k.c = dv(d->c); L->k.out = dv(d->out);
   return L;

@@ -414,4 +414,70 @@ PreparedOp* prepare_pool_bwd(const b2seg_poolbwd_desc* d) {
   return L;
 }
 
+// ------------------------------------------------------------------------------------------ activation as a model output
+// Oper2D(output_nums, (1,1), activation=final_activation, q) (unet_variants.py:1107-1108): the logits are a bf16 tensor (the sum
+// of q pointwise convolutions); the loss kernels read fp32 [pixel][cout].  One thread per pixel, one 16-byte load / store.
+struct OutActK { DView x, dx; float* y; const float* dlogits; int cout, act; };
+__global__ void __launch_bounds__(256) outact_fwd_kernel(OutActK k) {
+  const unsigned total = (unsigned)k.x.N * k.x.H * k.x.W;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned t = i;
+    const int w = (int)(t % k.x.W); t /= k.x.W;
+    const int h = (int)(t % k.x.H);
+    const int n = (int)(t / k.x.H);
+    float z[8];
+    load8(vaddr(k.x, n, h, w, 0), z);
+    if (k.act == B2SEG_ACT_SOFTMAX) {
+      float m = z[0];
+      for (int o = 1; o < k.cout; ++o) m = fmaxf(m, z[o]);
+      float sum = 0.f;
+      for (int o = 0; o < k.cout; ++o) { z[o] = __expf(z[o] - m); sum += z[o]; }
+      const float inv = 1.f / sum;
+      for (int o = 0; o < k.cout; ++o) k.y[(size_t)i * k.cout + o] = z[o] * inv;
+    } else {
+      for (int o = 0; o < k.cout; ++o) k.y[(size_t)i * k.cout + o] = act_fwd(z[o], k.act);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) outact_bwd_kernel(OutActK k) {
+  const unsigned total = (unsigned)k.dx.N * k.dx.H * k.dx.W;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned t = i;
+    const int w = (int)(t % k.dx.W); t /= k.dx.W;
+    const int h = (int)(t % k.dx.H);
+    const int n = (int)(t / k.dx.H);
+    float g[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) g[o] = o < k.cout ? k.dlogits[(size_t)i * k.cout + o] : 0.f;
+    store8(vaddr(k.dx, n, h, w, 0), g);
+  }
+}
+struct OutActLaunch : PreparedOp {
+  OutActK k;
+  bool bwd;
+  int launch(cudaStream_t s) override {
+    const DView& v = bwd ? k.dx : k.x;
+    int grid = grid_for((long long)v.N * v.H * v.W, 256);
+    const int cap = num_sms() * 32;
+    if (grid > cap) grid = cap;
+    if (bwd) outact_bwd_kernel<<<grid, 256, 0, s>>>(k);
+    else outact_fwd_kernel<<<grid, 256, 0, s>>>(k);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+static PreparedOp* prep_outact(const b2seg_outact_desc* d, bool bwd) {
+  const b2seg_view& v = bwd ? d->dx : d->x;
+  if (v.C != 8 || d->cout < 1 || d->cout > 8) { set_error("outact: needs an 8-channel view and 1 <= cout <= 8"); return nullptr; }
+  if (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_SIGMOID && d->act != B2SEG_ACT_SOFTMAX) { set_error("outact: activation %d", d->act); return nullptr; }
+  if ((long long)v.N * v.H * v.W >= (1ll << 31)) { set_error("outact: too many pixels"); return nullptr; }
+  if (bwd ? !d->dlogits : !d->y) { set_error("outact: null fp32 buffer"); return nullptr; }
+  auto* L = new OutActLaunch();
+  L->k = OutActK{dv(d->x), dv(d->dx), reinterpret_cast<float*>(d->y), reinterpret_cast<const float*>(d->dlogits), d->cout, d->act};
+  L->bwd = bwd;
+  return L;
+}
+PreparedOp* prepare_outact_fwd(const b2seg_outact_desc* d) { return prep_outact(d, false); }
+PreparedOp* prepare_outact_bwd(const b2seg_outact_desc* d) { return prep_outact(d, true); }
+
 }  // namespace b2
