@@ -118,7 +118,7 @@ def check_end_to_end(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights
             assert rel_l2(g, want) < E2E_GRAD_TOL, ("param grad", key, rel_l2(g, want))
 
 
-def check_per_layer(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=None, tol=TOL, e2e_bound=0.5):
+def check_per_layer(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=None, tol=TOL, e2e_bound=0.5, mask_outputs=None):
     """teacher-forced per-layer parity (forward of every materialised layer, weight gradient of every conv layer)"""
     params, loss, eng = _device_step(model, x, targets, losses, lr, loss_weights)
     override = {}
@@ -154,7 +154,7 @@ def check_per_layer(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=
     assert abs(loss - float(total2)) < 0.1 * max(1.0, abs(float(total2)))
     # masks on the teacher-forced head (the last layer's own decision given identical inputs)
     for o, want in zip(eng.outputs, outs):
-        if not o["name"].startswith("level"):
+        if (not o["name"].startswith("level")) if mask_outputs is None else (o["name"] in mask_outputs):
             got = _squeeze(o["y"].cpu(), ndim)
             w_local = k.local_out[o["name"]].detach()
             assert _mask_agreement(got, w_local) >= 0.999, o["name"]
