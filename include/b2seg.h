@@ -276,6 +276,15 @@ typedef struct b2seg_outact_desc {
   b2seg_view dx;       /* bf16 (backward output) */
 } b2seg_outact_desc;
 
+/* Deep-supervision target pyramid on the device (the reference builds it on the host for every batch:
+ * 2DCNN/utils/helper_functions.py:359-380 = MaxPooling2D(2^k) of the mask, called from DataGenerator.py:113;
+ * 1DCNN/1D_Segmentation.ipynb cell 31 = window MEAN over 2^k samples).  fp32 [N,H,W,C] -> fp32 [N,H/ph,W/pw,C]. */
+typedef struct b2seg_tpool_desc {
+  uint64_t src, dst;
+  int32_t N, H, W, C, ph, pw;
+  int32_t mode;        /* 0 = max, 1 = mean */
+} b2seg_tpool_desc;
+
 const char* b2seg_last_error(void);
 int b2seg_version(void);
 int b2seg_device_check(int device);
@@ -308,13 +317,14 @@ int b2seg_pool_bwd(const b2seg_poolbwd_desc* d, void* stream);
 int b2seg_rowsum(const b2seg_rowsum_desc* d, void* stream);
 int b2seg_outact_fwd(const b2seg_outact_desc* d, void* stream);
 int b2seg_outact_bwd(const b2seg_outact_desc* d, void* stream);
+int b2seg_target_pool(const b2seg_tpool_desc* d, void* stream);
 
 /* ---- plan: a recorded sequence of the ops above, replayed per step (optionally as a CUDA graph) ---- */
 typedef struct b2seg_plan b2seg_plan;
 enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
        B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,
        B2SEG_OP_MEMSET, B2SEG_OP_RESIZE_FWD, B2SEG_OP_RESIZE_BWD, B2SEG_OP_MULBC_FWD, B2SEG_OP_MULBC_BWD, B2SEG_OP_COLSTATS,
-       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM, B2SEG_OP_OUTACT_FWD, B2SEG_OP_OUTACT_BWD };
+       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM, B2SEG_OP_OUTACT_FWD, B2SEG_OP_OUTACT_BWD, B2SEG_OP_TARGET_POOL };
 typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
 
 /* Data parallel: backward-phase ops added to a plan AFTER this call size their grids for (SMs - sms), leaving room for the

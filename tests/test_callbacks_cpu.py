@@ -90,3 +90,57 @@ def test_reduce_lr_on_plateau_cooldown_and_floor():
     with pytest.raises(ValueError):
         ReduceLROnPlateau(factor=1.0)
     assert ReduceLROnPlateau(monitor="val_acc").mode == "max"
+
+
+# ---- deep-supervision target pyramids (b2seg.helpers; the device version is checked in tests/test_gpu_zz_self_onn.py) ----------------
+def test_prepare_train_dict_matches_reference_semantics():
+    """2D: MaxPooling2D(2^i) of the mask for 'UNet', the mask for 'UNetPP' (helper_functions.py:359-380);
+    1D: window mean, restated as the notebook's explicit loops (1D_Segmentation.ipynb cell 31)"""
+    import torch
+    import torch.nn.functional as F
+    from b2seg.helpers import derive_targets_host, prepareTrainDict, prepareTrainDict1D
+    rng = np.random.default_rng(0)
+    m = (rng.random((3, 32, 48)) > 0.7).astype(np.float32)          # rank 3: a channel axis is appended (:367-368)
+    d = prepareTrainDict(m, 3, "UNet")
+    assert list(d) == ["out", "level1", "level2", "level3"] and d["out"].shape == (3, 32, 48, 1)
+    for i in (1, 2, 3):
+        want = F.max_pool2d(torch.from_numpy(m)[:, None], 2 ** i)[:, 0, :, :, None].numpy()
+        assert np.array_equal(d[f"level{i}"], want)
+    dpp = prepareTrainDict(m, 2, "UNetPP")
+    assert all(np.array_equal(dpp[k], dpp["out"]) for k in ("level1", "level2"))
+    with pytest.raises(KeyError):
+        prepareTrainDict(m, 2, "FPN")
+    y = rng.standard_normal((4, 64, 2))
+    d1 = prepareTrainDict1D(y, 3, 64, "UNet", num_channel=2)
+    for i in (1, 2, 3):
+        w = 2 ** i
+        want = np.zeros((4, 64 // w, 2))
+        for j in range(2):
+            for s in range(0, 64, w):
+                want[:, s // w, j] = np.mean(y[:, s:s + w, j], axis=1)
+        assert np.allclose(d1[f"level{i}"], want, atol=1e-12)
+    # what Model.evaluate / the device path derive from a bare mask: same arrays, picked by output shape
+    mask = d["out"]
+    got = derive_targets_host(mask, [(3, 32, 48, 1), (3, 16, 24, 1), (3, 32, 48, 1), (3, 4, 6, 1)], 2)
+    assert np.array_equal(got[1], d["level1"]) and np.array_equal(got[3], d["level3"]) and got[0] is mask and got[2] is mask
+    with pytest.raises(ValueError):
+        derive_targets_host(mask, [(3, 5, 48, 1)], 2)
+
+
+def test_compile_ds_targets_target_lists():
+    """compile(ds_targets=...): a bare mask becomes [mask, None, ...] for the device path and a full host pyramid for evaluate()"""
+    from b2seg.models2d import unet_model_builder
+    m = unet_model_builder("UNet", 32, 32, 8, 2, ds=1, train_mode="from_scratch").ResNet50()
+    m.compile(loss="mse", optimizer="adam", ds_targets="UNet")
+    mask = (np.random.default_rng(1).random((2, 32, 32, 1)) > 0.5).astype(np.float32)
+    dev = m._targets(mask)
+    assert dev[0].shape == (2, 32, 32, 1) and dev[1:] == [None, None]
+    host = m._targets(mask, host=True)
+    assert [t.shape for t in host] == [(2, 32, 32, 1), (2, 16, 16, 1), (2, 8, 8, 1)]     # outputs: out, level1 (/2), level2 (/4)
+    from b2seg.helpers import prepareTrainDict
+    d = prepareTrainDict(mask, 2, "UNet")
+    assert all(np.array_equal(h, d[n]) for h, n in zip(host, m.output_names))
+    # explicit dicts / lists keep working unchanged
+    assert all(t is not None for t in m._targets(d))
+    with pytest.raises(ValueError):
+        m.compile(loss="mse", ds_targets="pyramid")

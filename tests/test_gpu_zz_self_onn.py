@@ -114,3 +114,31 @@ def test_1d_self_onn_per_layer(var, kw):
     targets = [rng.standard_normal((4,) + tuple(n.shape[1:])).astype(np.float32) for n in m.graph.outputs]
     check_per_layer(m, Ref1D(var, 256, 2, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), 1, x, targets, ["mse"] * len(targets),
                     e2e_bound=1.0)
+
+
+def test_ds_target_pyramid_on_device():
+    """compile(ds_targets=...) (input pipeline): b2seg_target_pool against torch, and a training step fed the bare
+    mask against the same step fed the reference's host-built dictionary (helper_functions.py:359-380)"""
+    import torch.nn.functional as F
+    from b2seg.helpers import prepareTrainDict
+    from b2seg.model import Adam
+    dev = "cuda"
+    src = torch.randn(3, 32, 48, 2, device=dev)
+    for (ph, pw, mode) in ((2, 2, 0), (8, 8, 0), (1, 4, 1)):
+        dst = torch.zeros(3, 32 // ph, 48 // pw, 2, device=dev)
+        L.call("b2seg_target_pool", L.TPoolDesc(src.data_ptr(), dst.data_ptr(), 3, 32, 48, 2, ph, pw, mode), stream())
+        torch.cuda.synchronize()
+        t = src.permute(0, 3, 1, 2)
+        want = (F.max_pool2d(t, (ph, pw)) if mode == 0 else F.avg_pool2d(t, (ph, pw))).permute(0, 2, 3, 1)
+        assert torch.allclose(dst, want, atol=1e-6)
+    rng = np.random.default_rng(23)
+    x = rng.random((4, 64, 64, 3), dtype=np.float32)
+    mask = (rng.random((4, 64, 64, 1)) > 0.6).astype(np.float32)
+    losses = {}
+    for how in ("host", "device"):
+        m = unet_model_builder("UNet", 64, 64, 16, 3, ds=1, train_mode="from_scratch").ResNet50()
+        m.compile(loss={"out": "binary_crossentropy", "level1": "mse", "level2": "mse", "level3": "mse"}, optimizer=Adam(1e-3),
+                  ds_targets="UNet" if how == "device" else None)
+        losses[how] = m.train_on_batch(x, mask if how == "device" else prepareTrainDict(mask, 3, "UNet"))
+    # same weights, same targets: equal up to the summation order of the loss kernel's atomics
+    assert abs(losses["host"] - losses["device"]) < 1e-5 * max(1.0, abs(losses["host"])), losses

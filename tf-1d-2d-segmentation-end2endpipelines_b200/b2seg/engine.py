@@ -59,6 +59,22 @@ class Engine:
         self._build_plan()
         self.step = 0
 
+    def derive_targets(self):
+        """compile(ds_targets=...): fill the targets of outputs 1.. from the mask in output 0's target buffer, on the device —
+        a copy where the shapes agree (UNet++-style full-resolution levels), else b2seg_target_pool: window max in 2D
+        (helper_functions.py:359-380), window mean in 1D (1D_Segmentation.ipynb cell 31)"""
+        src = self.outputs[0]
+        N, H, W, Cm = src["shape"]
+        for o in self.outputs[1:]:
+            n, h, w, c = o["shape"]
+            if (n, h, w, c) == (N, H, W, Cm):
+                o["target"].copy_(src["target"], non_blocking=True)
+                continue
+            if c != Cm or h < 1 or w < 1 or H % h or W % w:
+                raise ValueError(f"cannot derive the target of '{o['name']}' {o['shape']} from a mask of shape {src['shape']}")
+            d = L.TPoolDesc(src["target"].data_ptr(), o["target"].data_ptr(), N, H, W, Cm, H // h, W // w, 0 if self.graph.ndim == 2 else 1)
+            L.call("b2seg_target_pool", d, self._stream())
+
     def _build_plan(self, reserved_ops=frozenset(), reserve_sms=0):
         """(re)create the C plan; backward ops whose index is in reserved_ops size their grids for (SMs - reserve_sms)"""
         if self.plan.value:

@@ -74,6 +74,7 @@ class Model:
         self.world_size = 1
         self._dist = None
         self.exchange_bucket_bytes = 64 << 20   # gradient-exchange bucket (data parallel): overlap granularity vs launch count
+        self._ds_targets = None
 
     # ---- introspection -----------------------------------------------------------------------------------
     @property
@@ -147,7 +148,14 @@ class Model:
             self.set_weight_dict({k.replace("::", "/"): z[k] for k in z.files})
 
     # ---- compile -----------------------------------------------------------------------------------------
-    def compile(self, loss=None, optimizer=None, metrics=None, loss_weights=None, **kw):
+    def compile(self, loss=None, optimizer=None, metrics=None, loss_weights=None, ds_targets=None, **kw):
+        """ds_targets (extension; None = Keras behaviour): 'UNet' or 'UNetPP' — fit / train_on_batch / evaluate then take the mask
+        alone and the deep-supervision targets of the other outputs are derived from it ON THE DEVICE (the reference's
+        prepareTrainDict, helper_functions.py:359-380 / notebook cell 31, run per batch on the host): an output of the mask's
+        shape gets the mask, a smaller one its window max (2D) / window mean (1D)."""
+        if ds_targets not in (None, "UNet", "UNetPP"):
+            raise ValueError("ds_targets must be None, 'UNet' or 'UNetPP'")
+        self._ds_targets = ds_targets
         names = self.output_names
         if isinstance(loss, dict):
             self._losses = [_loss_name(loss[n]) for n in names]
@@ -212,7 +220,16 @@ class Model:
             raise ValueError(f"expected input of rank 4 (N, H, W, channels), got shape {a.shape}")
         return a
 
-    def _targets(self, y) -> List[np.ndarray]:
+    def _targets(self, y, host=False) -> List[np.ndarray]:
+        """target arrays in output order; with compile(ds_targets=...) and a bare mask: [mask, None, ...] (None = derived from the
+        mask on the device by Engine.derive_targets), or all of them derived on the host when `host` is set"""
+        if self._ds_targets is not None and not isinstance(y, (dict, list, tuple)) and len(self.output_names) > 1:
+            mask = self._to_nhwc(y)
+            if not host:
+                return [mask] + [None] * (len(self.output_names) - 1)
+            from .helpers import derive_targets_host
+            shapes = [(mask.shape[0],) + tuple(n.shape) for n in self.graph.outputs]
+            return derive_targets_host(mask, shapes, self.graph.ndim)
         if isinstance(y, dict):
             ys = [y[n] for n in self.output_names]
         elif isinstance(y, (list, tuple)):
@@ -249,9 +266,13 @@ class Model:
         eng = self._engine(xs.shape[0], True)
         eng.x_dev.copy_(torch.from_numpy(xs), non_blocking=True)
         for o, t in zip(eng.outputs, ys):
+            if t is None:
+                continue
             if tuple(t.shape) != tuple(o["shape"]):
                 raise ValueError(f"target for '{o['name']}' has shape {t.shape}, expected {o['shape']}")
             o["target"].copy_(torch.from_numpy(t), non_blocking=True)
+        if any(t is None for t in ys):
+            eng.derive_targets()
         return self._step(eng, return_loss)
 
     def _exchange_schedule(self, eng):
@@ -318,7 +339,7 @@ class Model:
 
     def evaluate(self, x, y, batch_size=32, verbose=0, **kw):
         """mean of the compiled (weighted) loss over batches, computed on the host from predict()"""
-        ys = self._targets(y)
+        ys = self._targets(y, host=True)
         pred = self.predict(x, batch_size=batch_size)
         pred = pred if isinstance(pred, list) else [pred]
         total = 0.0
@@ -350,6 +371,7 @@ class Model:
             eng._copy_stream = torch.cuda.Stream(device=eng.dev)
             eng._stage = [dict(x=torch.empty_like(eng.x_dev), t=[torch.empty_like(o["target"]) for o in eng.outputs],
                                ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        derive = any(t is None for t in batches[0][1])    # compile(ds_targets=...): only the mask is staged
         loss_host = torch.empty(len(batches), dtype=torch.float32).pin_memory()
         for i, (bx, bys) in enumerate(batches):
             st = eng._stage[i % 2]
@@ -357,14 +379,19 @@ class Model:
                 eng._copy_stream.wait_event(st["free"])          # the step that used this slot has copied it out
                 st["x"].copy_(torch.from_numpy(bx), non_blocking=True)
                 for dst, t in zip(st["t"], bys):
+                    if t is None:
+                        continue
                     if tuple(t.shape) != tuple(dst.shape):
                         raise ValueError(f"target shape {t.shape} != {tuple(dst.shape)}")
                     dst.copy_(torch.from_numpy(np.ascontiguousarray(t, np.float32)), non_blocking=True)
                 st["ready"].record(eng._copy_stream)
             cur.wait_event(st["ready"])
             eng.x_dev.copy_(st["x"], non_blocking=True)
-            for o, t in zip(eng.outputs, st["t"]):
-                o["target"].copy_(t, non_blocking=True)
+            for o, t, src in zip(eng.outputs, st["t"], bys):
+                if src is not None:
+                    o["target"].copy_(t, non_blocking=True)
+            if derive:
+                eng.derive_targets()
             st["free"].record(cur)
             self._step(eng, return_loss=False)
             loss_host[i].copy_(eng.loss_buf[0], non_blocking=True)
@@ -391,10 +418,11 @@ class Model:
                 if not 0.0 < split < 1.0:
                     raise ValueError(f"`validation_split` must be between 0 and 1, received: {split}")
                 cut = int(xs.shape[0] * (1.0 - split))
-                validation_data = (xs[cut:], [t[cut:][:, 0] if self.graph.ndim == 1 else t[cut:] for t in ys])
-                if len(ys) == 1:
+                held = [t for t in ys if t is not None]          # (ds_targets: the mask alone; evaluate() derives the rest)
+                validation_data = (xs[cut:], [t[cut:][:, 0] if self.graph.ndim == 1 else t[cut:] for t in held])
+                if len(held) == 1:
                     validation_data = (validation_data[0], validation_data[1][0])
-                xs, ys = xs[:cut], [t[:cut] for t in ys]
+                xs, ys = xs[:cut], [None if t is None else t[:cut] for t in ys]
             n = xs.shape[0]
         rng = np.random.default_rng(0)
         self.stop_training = False
@@ -416,11 +444,13 @@ class Model:
                 xn = self._to_nhwc(xs)
 
                 def take(a, s):   # contiguous slice (keeps pinned memory pinned) unless shuffled
+                    if a is None:
+                        return None
                     return a[s:s + bs] if order is None else a[order[s:s + bs]]
                 if full:
                     losses += self._train_batches_pipelined([(take(xn, s), [take(t, s) for t in ys]) for s in full])
                 for s in starts[len(full):]:    # ragged last batch: its own engine
-                    by = [take(t, s)[:, 0] if self.graph.ndim == 1 else take(t, s) for t in ys]
+                    by = [take(t, s)[:, 0] if self.graph.ndim == 1 else take(t, s) for t in ys if t is not None]
                     losses.append(self.train_on_batch(take(xs, s), by if len(by) > 1 else by[0]))
             logs = {"loss": float(np.mean(losses))}
             if validation_data is not None:

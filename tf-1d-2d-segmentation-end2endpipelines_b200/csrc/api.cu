@@ -147,6 +147,7 @@ static PreparedOp* prepare_any(int op, const void* desc, size_t bytes) {
     B2_CASE(B2SEG_OP_ROWSUM, b2seg_rowsum_desc, prepare_rowsum)
     B2_CASE(B2SEG_OP_OUTACT_FWD, b2seg_outact_desc, prepare_outact_fwd)
     B2_CASE(B2SEG_OP_OUTACT_BWD, b2seg_outact_desc, prepare_outact_bwd)
+    B2_CASE(B2SEG_OP_TARGET_POOL, b2seg_tpool_desc, prepare_target_pool)
     default:
       set_error("unknown op code %d", op);
       return nullptr;
@@ -192,6 +193,7 @@ int b2seg_sizeof_desc(int op) {
     case B2SEG_OP_ROWSUM: return (int)sizeof(b2seg_rowsum_desc);
     case B2SEG_OP_OUTACT_FWD:
     case B2SEG_OP_OUTACT_BWD: return (int)sizeof(b2seg_outact_desc);
+    case B2SEG_OP_TARGET_POOL: return (int)sizeof(b2seg_tpool_desc);
     default: return -1;
   }
 }
@@ -233,6 +235,7 @@ B2_ENTRY(b2seg_pool_bwd, b2seg_poolbwd_desc, b2::prepare_pool_bwd)
 B2_ENTRY(b2seg_rowsum, b2seg_rowsum_desc, b2::prepare_rowsum)
 B2_ENTRY(b2seg_outact_fwd, b2seg_outact_desc, b2::prepare_outact_fwd)
 B2_ENTRY(b2seg_outact_bwd, b2seg_outact_desc, b2::prepare_outact_bwd)
+B2_ENTRY(b2seg_target_pool, b2seg_tpool_desc, b2::prepare_target_pool)
 
 int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
   if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");

@@ -480,4 +480,49 @@ static PreparedOp* prep_outact(const b2seg_outact_desc* d, bool bwd) {
 PreparedOp* prepare_outact_fwd(const b2seg_outact_desc* d) { return prep_outact(d, false); }
 PreparedOp* prepare_outact_bwd(const b2seg_outact_desc* d) { return prep_outact(d, true); }
 
+// ------------------------------------------------------------------------------------------ deep-supervision target pyramid
+// level-k target = MaxPooling2D(2^k) of the mask (helper_functions.py:359-380) / window mean in 1D (notebook cell 31), fp32.
+struct TPoolK { const float* src; float* dst; int N, H, W, C, ph, pw, mode; };
+__global__ void __launch_bounds__(256) target_pool_kernel(TPoolK k) {
+  const int Ho = k.H / k.ph, Wo = k.W / k.pw;
+  const unsigned total = (unsigned)k.N * Ho * Wo * k.C;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % k.C);
+    unsigned t = i / k.C;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best = -INFINITY, sum = 0.f;
+    for (int a = 0; a < k.ph; ++a)
+      for (int b = 0; b < k.pw; ++b) {
+        const float v = __ldg(k.src + (((size_t)n * k.H + ho * k.ph + a) * k.W + wo * k.pw + b) * k.C + c);
+        best = fmaxf(best, v);
+        sum += v;
+      }
+    k.dst[i] = k.mode == 0 ? best : sum / (float)(k.ph * k.pw);
+  }
+}
+struct TPoolLaunch : PreparedOp {
+  TPoolK k;
+  int launch(cudaStream_t s) override {
+    int grid = grid_for((long long)k.N * (k.H / k.ph) * (k.W / k.pw) * k.C, 256);
+    const int cap = num_sms() * 32;
+    if (grid > cap) grid = cap;
+    target_pool_kernel<<<grid, 256, 0, s>>>(k);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_target_pool(const b2seg_tpool_desc* d) {
+  if (!d->src || !d->dst || d->N < 1 || d->C < 1 || d->ph < 1 || d->pw < 1 || d->H < d->ph || d->W < d->pw || d->H % d->ph || d->W % d->pw ||
+      (d->mode != 0 && d->mode != 1)) {
+    set_error("target_pool: bad arguments");
+    return nullptr;
+  }
+  if ((long long)d->N * (d->H / d->ph) * (d->W / d->pw) * d->C >= (1ll << 31)) { set_error("target_pool: too many elements"); return nullptr; }
+  auto* L = new TPoolLaunch();
+  L->k = TPoolK{reinterpret_cast<const float*>(d->src), reinterpret_cast<float*>(d->dst), d->N, d->H, d->W, d->C, d->ph, d->pw, d->mode};
+  return L;
+}
+
 }  // namespace b2
