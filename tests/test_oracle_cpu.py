@@ -93,6 +93,46 @@ def test_conv1d_transpose_k2_s2():
     assert np.allclose(y.detach().numpy(), want, atol=1e-12)
 
 
+def test_operational_layers_against_numpy_loops():
+    """Oper2D / Oper2DTranspose / Oper1DTranspose(kernel 4) (onn_layers.py:6-48, ONN_layers.py:31-52): y = sum_p conv_p(x ** p), then the
+    optional activation — restated with the NumPy loop convolutions above, one power at a time"""
+    q = 3
+    x = 0.7 * rng.standard_normal((2, 5, 6, 3))
+    ws = [rng.standard_normal((3, 3, 3, 4)) for _ in range(q)]
+    bs = [rng.standard_normal(4) for _ in range(q)]
+    params = {}
+    for i in range(q):
+        params[f"oper2d/ONN_Conv_{i + 1}/kernel"], params[f"oper2d/ONN_Conv_{i + 1}/bias"] = torch.from_numpy(ws[i]), torch.from_numpy(bs[i])
+    k = KerasRef(2, params=params, dtype=torch.float64, strict=True)
+    y = k.Oper(torch.from_numpy(x), 4, (3, 3), q=q, activation="tanh")
+    want = np.tanh(sum(_conv_same_np(x ** (i + 1), ws[i], bs[i]) for i in range(q)))
+    assert np.allclose(y.detach().numpy(), want, atol=1e-12)
+    assert set(k.acts) >= {"oper2d/ONN_Conv_1", "oper2d/ONN_Conv_3", "oper2d/tf_math_pow1", "oper2d/tf_math_pow2", "oper2d/add", "oper2d"}
+    # second instance: the nested model takes the next auto-name, its sub-layers keep their explicit names
+    wt = [rng.standard_normal((4, 4, 2, 4)) for _ in range(2)]
+    params2 = {f"oper2d_transpose/ONN_TransConv_{i + 1}/kernel": torch.from_numpy(wt[i]) for i in range(2)}
+    params2.update({f"oper2d_transpose/ONN_TransConv_{i + 1}/bias": torch.zeros(2, dtype=torch.float64) for i in range(2)})
+    k2 = KerasRef(2, params=params2, dtype=torch.float64, strict=True)
+    x2 = torch.from_numpy(want)
+    y2 = k2.Oper(x2, 2, (4, 4), q=2, strides=(2, 2), transpose=True)
+    want2 = _tconv_np(want, wt[0], 0.0, 2) + _tconv_np(want ** 2, wt[1], 0.0, 2)
+    assert y2.shape == (2, 10, 12, 2) and np.allclose(y2.detach().numpy(), want2, atol=1e-12)
+    # 1D, transposed, kernel 4, stride 2, 'same': output position 2i - 1 + a
+    x1 = rng.standard_normal((2, 5, 3))
+    w1 = rng.standard_normal((4, 2, 3))
+    k3 = KerasRef(1, params={"oper1d_transpose/ONN_TransConv_1/kernel": torch.from_numpy(w1),
+                             "oper1d_transpose/ONN_TransConv_1/bias": torch.zeros(2, dtype=torch.float64)}, dtype=torch.float64, strict=True)
+    y3 = k3.Oper(torch.from_numpy(x1), 2, 4, q=1, strides=2, transpose=True)
+    want3 = np.zeros((2, 10, 2))
+    for n in range(2):
+        for i in range(5):
+            for a in range(4):
+                o = 2 * i - 1 + a
+                if 0 <= o < 10:
+                    want3[n, o] += w1[a] @ x1[n, i]
+    assert np.allclose(y3.detach().numpy(), want3, atol=1e-12)
+
+
 @pytest.mark.parametrize("ndim", [1, 2])
 def test_batchnorm_training_and_moving_statistics(ndim):
     shape = (3, 4, 5, 6) if ndim == 2 else (3, 7, 6)
