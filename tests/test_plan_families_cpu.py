@@ -162,6 +162,8 @@ CASES_1D = [
     ("R2UNet3P", dict(ds=1, t=1)),                 # :1226; the m-loop drops its first recurrent block (names still consumed)
     ("MultiResUNet3P", dict(ds=1, ag=1)),          # :899, with its overwritten dense links and its dead bottleneck block
     ("MultiResUNet3P", dict(ds=0, is_transconv=False)),
+    ("R2UNet", dict(ds=1, ae=1, feature_number=16, t=2)),   # the bottleneck's recurrent blocks concatenate the Feature_Extraction_Block's Reshape output
+    ("RUNet", dict(ds=0, ae=1, feature_number=16, t=1)),
 ]
 
 
@@ -188,6 +190,7 @@ CASES_1D_SELF = [
     ("SelfUNetPP", dict(ds=1, lstm=1, q=2, ae=1, feature_number=16)),
     ("SelfR2UNetPP", dict(ds=1, t=2)),                 # :1312: Self_Recurrent_Conv_Block encoder (bottom level with q=1), single Oper1D nodes
     ("SelfR2UNetPP", dict(ds=0, t=1, ag=1)),
+    ("SelfR2UNetPP", dict(ds=1, t=2, ae=1, feature_number=16)),
     ("SelfUNet3P", dict(ds=1)),                        # :1515
 ]
 

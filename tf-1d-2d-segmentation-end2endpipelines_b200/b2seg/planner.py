@@ -319,7 +319,9 @@ class Planner:
             elif n.op in ("flatten", "dense", "reshape"):
                 # Feature_Extraction_Block (ae=1; 2DCNN unet_variants.py:41-48, 1DCNN :127-135): Flatten and Reshape are views of
                 # the channels-last buffer, Dense is a 1x1 convolution over a (N, 1, 1, features) tensor on the same kernels
-                if any(c.op in ("concat", "convlstm") for c in self.cons[id(n)]):
+                # (a Reshape output may feed a concatenation — the recurrent blocks re-concatenate their input, which with ae=1 is
+                # the Feature_Extraction_Block's Reshape, 1DCNN unet_variants.py:63-72,1008 — it is then copied into the slot)
+                if n.op != "reshape" and any(c.op in ("concat", "convlstm") for c in self.cons[id(n)]):
                     raise PlanError(f"{n.name}: a {n.op} output feeding a concatenation is not lowered")
                 self.units.append(dict(kind=n.op, node=n, out=n))
             else:
@@ -834,8 +836,13 @@ class Planner:
         src = self.phys[id(n.inputs[0])]
         if C % 8 or src.Cp != H * W * C:
             raise PlanError(f"{n.name}: Reshape to {n.shape} needs C % 8 == 0 and an unpadded source")
-        self.phys[id(n)] = Phys(TView.dense(src.view.ptr, self.N, H, W, C), C, [(0, C)])
-        self.taps[n.name] = (self.phys[id(n)].view, C, "act")
+        view = TView.dense(src.view.ptr, self.N, H, W, C)
+        if any(c.op in ("concat", "convlstm") for c in self.cons[id(n)]):
+            # a view cannot live inside a concat buffer: copy it into every slot; direct consumers keep reading the view
+            for d in self._dests(n):
+                self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(1, view.to_c(), lw.NULL_VIEW.to_c(), lw.NULL_VIEW.to_c(), d.to_c()), f"concat copy {n.name}")
+        self.phys[id(n)] = Phys(view, C, [(0, C)])
+        self.taps[n.name] = (view, C, "act")
 
     def _fwd_dense(self, u):
         n = u["node"]
@@ -859,6 +866,11 @@ class Planner:
         g = self._single_grad(n)
         if g is not None:
             H, W, C = n.shape
+            if (g.C, g.sw, g.sh, g.sn) != (C, C, W * C, H * W * C):
+                # the only gradient is a channel window of a concat gradient buffer: make it dense before re-viewing it as (N,1,1,F)
+                dense = self._grad_like(n)
+                self.emit(1, L.OP_ELTWISE, L.EltwiseDesc(1, g.to_c(), lw.NULL_VIEW.to_c(), lw.NULL_VIEW.to_c(), dense.to_c()), f"dense grad {n.name}")
+                g = dense
             self._add_gsrc(n.inputs[0], GSrc(TView.dense(g.ptr, self.N, 1, 1, H * W * C)))
 
     def _bwd_dense(self, u):
