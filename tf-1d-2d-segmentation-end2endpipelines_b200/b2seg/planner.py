@@ -411,10 +411,15 @@ class Planner:
                 self._add_param(f"{n.name}/moving_variance", (n.C,), "vec", cp, False, C=n.C, fill=1.0, vsegs=vs, Cp=cp)
             elif n.op == "dense":
                 fin, units = n.inputs[0].shape[2], n.attrs["units"]
-                if fin % 8 or units % 8:
+                fin_p, isegs = fin, [(0, fin)]
+                if n.inputs[0].op == "flatten":      # Flatten of a padded / gapped tensor: the kernel rows follow its physical layout
+                    t = n.inputs[0].inputs[0]
+                    fin_p = t.shape[0] * t.shape[1] * self._cphys(t)
+                    isegs = self._flat_segs(t.shape[0], t.shape[1], self._cphys(t), self._segs(t))
+                if fin_p % 8 or units % 8:
                     raise PlanError(f"{n.name}: Dense {fin} -> {units}: feature counts must be multiples of 8")
-                self._add_param(f"{n.name}/kernel", (fin, units), "conv", units * fin, True, cout=units, cout_p=units, taps=1, cin_p=fin,
-                                kh=1, kw=1, out_segs=[(0, units)], segs=[(0, fin)])
+                self._add_param(f"{n.name}/kernel", (fin, units), "conv", units * fin_p, True, cout=units, cout_p=units, taps=1, cin_p=fin_p,
+                                kh=1, kw=1, out_segs=[(0, units)], segs=isegs)
                 self._add_param(f"{n.name}/bias", (units,), "vec", units, True, C=units, vsegs=[(0, units)], Cp=units)
             elif n.op == "convlstm":
                 kh, kw = n.attrs["kernel"]
@@ -817,18 +822,31 @@ class Planner:
         self.taps[n.name] = (dests[0], F, "act")
 
     # -- Feature_Extraction_Block: Flatten -> Dense -> Dense -> Reshape -------------------------------------------------------
+    @staticmethod
+    def _flat_segs(H, W, Cp, segs):
+        """logical -> physical segments of Flatten over an (H, W, Cp) buffer whose pixels carry `segs`: Keras' Flatten order is
+        (h, w, logical channel), the buffer's is (h, w, physical channel) — identical when the tensor is unpadded"""
+        if list(segs) == [(0, Cp)]:
+            return [(0, H * W * Cp)]
+        return [(pix * Cp + o, c) for pix in range(H * W) for (o, c) in segs]
+
     def _flat_view(self, t: Node, what: str) -> TView:
-        """the dense channels-last buffer of t seen as (N, 1, 1, H*W*C): exactly Keras' Flatten order"""
+        """the channels-last buffer of t seen as (N, 1, 1, H*W*Cp).  Padding lanes and gaps (odd MultiRes channel counts) stay in
+        the flattened vector: they hold zeros and the Dense layer that reads it keeps zero weights there (segments in its
+        parameter layout), exactly like a convolution reading a gapped concat buffer."""
         p = self.phys[id(t)]
         H, W, C = t.shape
         v = p.view
-        if p.Cp != C or list(p.segs) != [(0, C)] or v.sw != C or (H > 1 and v.sh != W * C) or v.sn != H * W * C:
-            raise PlanError(f"{what}: needs a dense, unpadded channels-last tensor (got {t.name}: C={C}, physical {p.Cp}, strides {v.sn},{v.sh},{v.sw})")
-        return TView.dense(v.ptr, self.N, 1, 1, H * W * C)
+        if v.C != p.Cp or v.sw != p.Cp or (H > 1 and v.sh != W * p.Cp) or v.sn != H * W * p.Cp:
+            raise PlanError(f"{what}: needs a contiguous channels-last tensor (got {t.name}: C={C}, physical {p.Cp}, strides {v.sn},{v.sh},{v.sw})")
+        return TView.dense(v.ptr, self.N, 1, 1, H * W * p.Cp)
 
     def _fwd_flatten(self, u):
         n = u["node"]
-        self.phys[id(n)] = Phys(self._flat_view(n.inputs[0], n.name), n.C, [(0, n.C)])
+        t = n.inputs[0]
+        H, W, _ = t.shape
+        p = self.phys[id(t)]
+        self.phys[id(n)] = Phys(self._flat_view(t, n.name), n.C, self._flat_segs(H, W, p.Cp, p.segs))
 
     def _fwd_reshape(self, u):
         n = u["node"]
@@ -848,8 +866,11 @@ class Planner:
         n = u["node"]
         x = self.phys[id(n.inputs[0])]
         fin, units = n.inputs[0].shape[2], n.attrs["units"]
+        pe = self.pindex[f"{n.name}/kernel"]
+        if (pe.meta["cin_p"], list(pe.meta["segs"])) != (x.Cp, list(x.segs)):
+            raise PlanError(f"{n.name}: input layout {x.Cp} / {len(x.segs)} segments differs from the parameter layout {pe.meta['cin_p']}")
         out = self.new_act(1, 1, units)
-        self.emit(0, L.OP_CONV, lw.conv_fprop(x.view, self.pwb(f"{n.name}/kernel"), units, 1, 1, fin, out, bias=self.pw(f"{n.name}/bias")),
+        self.emit(0, L.OP_CONV, lw.conv_fprop(x.view, self.pwb(f"{n.name}/kernel"), units, 1, 1, x.Cp, out, bias=self.pw(f"{n.name}/bias")),
                   n.name, flops=2.0 * self.N * fin * units)
         self.phys[id(n)] = Phys(out, units, [(0, units)])
         u["x"] = x.view
@@ -858,8 +879,8 @@ class Planner:
         n = u["node"]
         g = self._single_grad(n)
         if g is not None:
-            H, W, C = n.inputs[0].shape
-            self._add_gsrc(n.inputs[0], GSrc(TView.dense(g.ptr, self.N, H, W, C)))
+            H, W, _ = n.inputs[0].shape
+            self._add_gsrc(n.inputs[0], GSrc(TView.dense(g.ptr, self.N, H, W, self.phys[id(n.inputs[0])].Cp)))
 
     def _bwd_reshape(self, u):
         n = u["node"]
@@ -879,11 +900,12 @@ class Planner:
         if dz is None:
             return
         fin, units = n.inputs[0].shape[2], n.attrs["units"]
+        fin_p = u["x"].C                      # physical width of the input (a flattened padded tensor keeps its zero lanes)
         flops = 2.0 * self.N * fin * units
-        self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, u["x"], self.pg(f"{n.name}/kernel"), units, 1, 1, fin), f"wgrad {n.name}", flops=flops)
+        self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, u["x"], self.pg(f"{n.name}/kernel"), units, 1, 1, fin_p), f"wgrad {n.name}", flops=flops)
         self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")
-        dx = self.new_act(1, 1, fin, "grad")
-        self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(f"{n.name}/kernel"), units, 1, 1, fin, dx), f"dgrad {n.name}", flops=flops)
+        dx = self.new_act(1, 1, fin_p, "grad")
+        self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(f"{n.name}/kernel"), units, 1, 1, fin_p, dx), f"dgrad {n.name}", flops=flops)
         self._add_gsrc(n.inputs[0], GSrc(dx))
 
     def _fwd_pow(self, u):
