@@ -266,10 +266,12 @@ typedef struct b2seg_rowsum_desc {
 /* A model output that is an Activation over a tensor instead of a pointwise convolution with a fused activation: the Self-ONN
  * builders end in Oper2D(output_nums, (1,1), activation=final_activation, q) = activation(sum of q pointwise convolutions)
  * (unet_variants.py:1107-1108; deep-supervision levels :653 are the same without activation).
- * Forward: y[pix][o] = act(x[pix][o]), o < cout <= 8, fp32 (the layout b2seg_loss reads).  Backward: dx[pix][o] = dlogits[pix][o]
+ * Also used for a pointwise head with more than 8 classes (the b2seg_head_* kernels stop at 8): the convolution runs on the
+ * tensor-core kernels and this op applies the activation.
+ * Forward: y[pix][o] = act(x[pix][o]), o < cout, fp32 (the layout b2seg_loss reads).  Backward: dx[pix][o] = dlogits[pix][o]
  * as bf16, channels >= cout zero (b2seg_loss has already applied the activation's derivative). */
 typedef struct b2seg_outact_desc {
-  b2seg_view x;        /* bf16 logits, C = 8 (cout real channels) */
+  b2seg_view x;        /* bf16 logits, C % 8 == 0, the first cout channels are real */
   int32_t cout, act;   /* act: NONE, SIGMOID or SOFTMAX */
   uint64_t y;          /* fp32 [N,H,W,cout] */
   uint64_t dlogits;    /* fp32 [N,H,W,cout] (backward input) */
@@ -319,7 +321,7 @@ int b2seg_outact_fwd(const b2seg_outact_desc* d, void* stream);
 int b2seg_outact_bwd(const b2seg_outact_desc* d, void* stream);
 int b2seg_target_pool(const b2seg_tpool_desc* d, void* stream);
 
-/* ---- plan: a recorded sequence of the ops above, replayed per step (optionally as a CUDA graph) ---- */
+/* ---- plan: a recorded sequence of the ops above, replayed per step ---- */
 typedef struct b2seg_plan b2seg_plan;
 enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
        B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,

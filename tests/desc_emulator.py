@@ -296,16 +296,16 @@ def emu_head_bwd(mem, d):
 
 
 def emu_outact_fwd(mem, d):
-    assert d.x.C == 8 and 1 <= d.cout <= 8
+    assert d.x.C % 8 == 0 and 1 <= d.cout <= d.x.C
     z = mem.gather_view(d.x)[..., :d.cout]
     y = torch.softmax(z, -1) if d.act == L.ACT_SOFTMAX else _act(z, d.act)
     mem.f32(d.y, y.numel())[:] = y.reshape(-1)
 
 
 def emu_outact_bwd(mem, d):
-    assert d.dx.C == 8 and 1 <= d.cout <= 8
+    assert d.dx.C % 8 == 0 and 1 <= d.cout <= d.dx.C
     n = d.dx.N * d.dx.H * d.dx.W
-    dx = torch.zeros(d.dx.N, d.dx.H, d.dx.W, 8, dtype=torch.float64)
+    dx = torch.zeros(d.dx.N, d.dx.H, d.dx.W, d.dx.C, dtype=torch.float64)
     dx[..., :d.cout] = mem.f32(d.dlogits, n * d.cout).view(d.dx.N, d.dx.H, d.dx.W, d.cout)
     mem.write_view(d.dx, dx)
 

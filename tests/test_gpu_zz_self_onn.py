@@ -64,8 +64,8 @@ def test_self_onn_pow_tanh_outact():
     assert rel_l2(o.float(), t) < 4e-3
     assert rel_l2(dz.float(), g.float() * (1 - t * t)) < 5e-3
     # Activation as a model output: fp32 [pixel][cout] from an 8-channel bf16 block, and the bf16 gradient back
-    for cout, act in ((1, L.ACT_SIGMOID), (4, L.ACT_SOFTMAX), (3, L.ACT_NONE)):
-        z = bf(torch.randn(N, H, W, 8, device=dev) * 3)
+    for cout, act, cp in ((1, L.ACT_SIGMOID, 8), (4, L.ACT_SOFTMAX, 8), (3, L.ACT_NONE, 8), (11, L.ACT_SOFTMAX, 16), (9, L.ACT_SIGMOID, 16)):
+        z = bf(torch.randn(N, H, W, cp, device=dev) * 3)
         yv = torch.full((N, H, W, cout), -7.0, device=dev)
         dl = torch.randn(N, H, W, cout, device=dev)
         dzo = torch.full_like(z, 5.0)

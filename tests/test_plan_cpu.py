@@ -162,3 +162,16 @@ def test_plan_unet1d_regression_k5():
     x = torch.randn(2, 32, 2)
     y = torch.randn(2, 32, 1)
     _run(m.graph, Ref1D("UNet", 32, 2, 2, 8, 5, problem_type="Regression", output_nums=1, ds=0), x, [y], ["mae"], 1)
+
+
+def test_unsupported_loss_head_pairs_are_refused():
+    """b2seg_loss seeds the backward pass with dL/dlogits; pairs it cannot form that for must fail at plan time, not train wrongly"""
+    from b2seg.planner import PlanError
+    g = unet_model_builder("UNet", 16, 16, 8, 2, ds=1, train_mode="from_scratch").build_graph()       # out: sigmoid, levels: linear
+    for losses in (["cce", "mse", "mse"], ["bce", "bce", "mse"], ["mse", "cce", "mse"]):
+        with pytest.raises(PlanError, match="is not lowered"):
+            Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=losses, adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse", "mae", "mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    g = unet_model_builder("UNet", 16, 16, 8, 2, final_activation="tanh", train_mode="from_scratch").build_graph()
+    with pytest.raises(PlanError, match="is not lowered"):
+        Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()

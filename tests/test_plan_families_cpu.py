@@ -42,6 +42,8 @@ CASES_2D = [
     ("MultiResUNet", dict(ds=1, is_transconv=False)),
     ("UNet", dict(ae=1, feature_number=24)),       # Feature_Extraction_Block: Flatten -> Dense('features') -> Dense -> Reshape
     ("UNetPP", dict(ae=1, ds=1, feature_number=16)),
+    ("UNet", dict(ds=1, output_nums=11, final_activation="softmax")),   # more than 8 classes: tensor-core 1x1 convolution + output activation op
+    ("UNetPP", dict(output_nums=9, final_activation="sigmoid")),
     ("MultiResUNet", dict(ae=1, feature_number=16)),   # Flatten of an odd-channel (gapped, padded) tensor: the Dense kernel rows follow its physical layout
 ]
 
@@ -165,6 +167,7 @@ CASES_1D = [
     ("MultiResUNet3P", dict(ds=0, is_transconv=False)),
     ("R2UNet", dict(ds=1, ae=1, feature_number=16, t=2)),   # the bottleneck's recurrent blocks concatenate the Feature_Extraction_Block's Reshape output
     ("RUNet", dict(ds=0, ae=1, feature_number=16, t=1)),
+    ("UNet", dict(ds=1, problem_type="Classification", output_nums=12)),   # 12-class softmax head
     ("MultiResUNet", dict(ds=1, ae=1, feature_number=16)),                 # Flatten of a pooled 60-channel tensor stored in 64 lanes
     ("BCDUNet", dict(ae=1, ds=0, lstm=1, dense_loop=2, feature_number=16)),   # Flatten of a concatenation (concat-dense block, BCDUNet.py:70-76)
 ]

@@ -251,9 +251,20 @@ class Planner:
                 if is_head:
                     self.units.append(dict(kind="head", node=n, out=n))
                     continue
+                wide_head = None
                 if a.get("activation") not in (None, "linear"):
-                    raise PlanError(f"conv {n.name}: fused activation only supported on output heads")
+                    if not (n in g.outputs and a["activation"] in ("sigmoid", "softmax")):
+                        raise PlanError(f"conv {n.name}: fused activation only supported on output heads")
+                    # an output head the pointwise-head kernels do not take (more than 8 classes, or a k > 1 kernel): the
+                    # convolution runs on the tensor-core kernels, its activation in the output op
+                    wide_head = a["activation"]
                 u = dict(kind="conv", node=n, bn=None, act=None, pool=None)
+                if wide_head is not None:
+                    u["out"] = n
+                    u["no_tap"] = True        # the tensor called `n.name` is the activated output, not these logits
+                    self.units.append(u)
+                    self.units.append(dict(kind="outact", node=n, out=None, src=n, fn=wide_head))
+                    continue
                 last = n
                 b = self._sole(last, "bn")
                 if b is not None:
@@ -302,7 +313,7 @@ class Planner:
                     absorbed.add(id(c))
                 self.units.append(u)
             elif n.op == "act":
-                if n in g.outputs and n.attrs["fn"] in ("sigmoid", "softmax", "linear") and n.C <= 8:
+                if n in g.outputs and n.attrs["fn"] in ("sigmoid", "softmax", "linear"):
                     # a model output that is an Activation over a tensor (the Self-ONN head, unet_variants.py:1107-1108):
                     # fp32 probabilities for the loss straight from the bf16 logits
                     self.units.append(dict(kind="outact", node=n, out=n, src=n.inputs[0], fn=n.attrs["fn"]))
@@ -330,8 +341,8 @@ class Planner:
                 # any other tensor used as a model output (a Self-ONN deep-supervision level is the bare sum of q pointwise
                 # convolutions, :653): produced by its own unit, then exported as a linear output
                 last = self.units[-1]
-                if last["out"] is not n or n.C > 8:
-                    raise PlanError(f"output {n.name} ({n.op}, {n.C} channels) is not lowered")
+                if last["out"] is not n:
+                    raise PlanError(f"output {n.name} ({n.op}) is not lowered")
                 self.units.append(dict(kind="outact", node=n, out=None, src=n, fn="linear"))
         self.unit_of_out = {id(u["out"]): u for u in self.units if u["out"] is not None}
         for u in self.units:
@@ -617,7 +628,8 @@ class Planner:
             self.emit(0, L.OP_CONV, conv_desc(dests[0], act, 0), n.name, flops=self._conv_flops(n))
             self._copy_extra(dests[0], dests[1:])
             u["y"] = dests[0]
-            self.taps[out_node.name] = (dests[0], co, "act")
+            if not u.get("no_tap"):
+                self.taps[out_node.name] = (dests[0], co, "act")
             if u["act"] is not None:
                 self.taps[n.name] = (dests[0], co, "post")  # pre-activation is not materialised
             return
@@ -935,8 +947,8 @@ class Planner:
     def _fwd_outact(self, u):
         n, src = u["node"], u["src"]
         x = self.phys[id(src)]
-        if x.Cp != 8 or list(x.segs) != [(0, src.C)]:
-            raise PlanError(f"output {n.name}: expected one dense 8-channel block, got {x.Cp} channels / {x.segs}")
+        if x.Cp != ceil8(src.C) or list(x.segs) != [(0, src.C)]:
+            raise PlanError(f"output {n.name}: expected one dense channel block, got {x.Cp} channels / {x.segs}")
         H, W, co = n.shape
         npix = self.N * H * W
         y = self.alloc(npix * co * 4, "output")
@@ -948,11 +960,21 @@ class Planner:
         self.outputs.append(dict(index=self.g.outputs.index(n), name=n.name, ptr=y, shape=(self.N, H, W, co), target_ptr=tgt, act=act,
                                  dlogits=dl, npix=npix, cout=co))
 
+    def _loss_kind(self, o) -> int:
+        """loss code of output o; b2seg_loss seeds the backward pass with dL/dlogits, which it can form for these pairs only"""
+        name = self.losses[o["index"]] if self.losses else "bce"
+        kind, act = LOSS_KINDS[name], o["act"]
+        ok = (kind == 0 and act == L.ACT_SIGMOID) or (kind == 1 and act == L.ACT_SOFTMAX) or (kind >= 2 and act in (L.ACT_NONE, L.ACT_SIGMOID))
+        if not ok:
+            raise PlanError(f"output {o['name']}: loss '{name}' on a head with activation code {act} is not lowered (binary cross-entropy "
+                            f"needs a sigmoid head, categorical cross-entropy a softmax head, MSE / MAE a linear or sigmoid head)")
+        return kind
+
     def _bwd_outact(self, u):
         n, src = u["node"], u["src"]
         o = next(o for o in self.outputs if o["name"] == n.name)
         idx = o["index"]
-        kind = LOSS_KINDS[(self.losses[idx] if self.losses else "bce")]
+        kind = self._loss_kind(o)
         wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
         self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr),
                   f"loss {n.name}")
@@ -995,7 +1017,7 @@ class Planner:
         n = u["node"]
         o = next(o for o in self.outputs if o["name"] == n.name)
         idx = o["index"]
-        kind = LOSS_KINDS[(self.losses[idx] if self.losses else "bce")]
+        kind = self._loss_kind(o)
         wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
         self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr),
                   f"loss {n.name}")

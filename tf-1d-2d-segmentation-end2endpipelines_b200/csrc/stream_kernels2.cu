@@ -416,40 +416,66 @@ PreparedOp* prepare_pool_bwd(const b2seg_poolbwd_desc* d) {
 
 // ------------------------------------------------------------------------------------------ activation as a model output
 // Oper2D(output_nums, (1,1), activation=final_activation, q) (unet_variants.py:1107-1108): the logits are a bf16 tensor (the sum
-// of q pointwise convolutions); the loss kernels read fp32 [pixel][cout].  One thread per pixel, one 16-byte load / store.
+// of q pointwise convolutions; also a softmax / sigmoid head with more than 8 classes, whose convolution runs on the tensor-core
+// kernels); the loss kernels read fp32 [pixel][cout].  One thread per pixel, 16-byte loads / stores.
 struct OutActK { DView x, dx; float* y; const float* dlogits; int cout, act; };
 __global__ void __launch_bounds__(256) outact_fwd_kernel(OutActK k) {
   const unsigned total = (unsigned)k.x.N * k.x.H * k.x.W;
+  const int nvec = (k.cout + 7) / 8;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     unsigned t = i;
     const int w = (int)(t % k.x.W); t /= k.x.W;
     const int h = (int)(t % k.x.H);
     const int n = (int)(t / k.x.H);
+    float* yp = k.y + (size_t)i * k.cout;
     float z[8];
-    load8(vaddr(k.x, n, h, w, 0), z);
     if (k.act == B2SEG_ACT_SOFTMAX) {
-      float m = z[0];
-      for (int o = 1; o < k.cout; ++o) m = fmaxf(m, z[o]);
-      float sum = 0.f;
-      for (int o = 0; o < k.cout; ++o) { z[o] = __expf(z[o] - m); sum += z[o]; }
+      // three short passes over the pixel's logits (the re-reads hit L1): max, sum of exponentials, normalised write
+      float m = -INFINITY, sum = 0.f;
+      for (int v = 0; v < nvec; ++v) {
+        load8(vaddr(k.x, n, h, w, v * 8), z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (v * 8 + e < k.cout) m = fmaxf(m, z[e]);
+      }
+      for (int v = 0; v < nvec; ++v) {
+        load8(vaddr(k.x, n, h, w, v * 8), z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (v * 8 + e < k.cout) sum += __expf(z[e] - m);
+      }
       const float inv = 1.f / sum;
-      for (int o = 0; o < k.cout; ++o) k.y[(size_t)i * k.cout + o] = z[o] * inv;
+      for (int v = 0; v < nvec; ++v) {
+        load8(vaddr(k.x, n, h, w, v * 8), z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (v * 8 + e < k.cout) yp[v * 8 + e] = __expf(z[e] - m) * inv;
+      }
     } else {
-      for (int o = 0; o < k.cout; ++o) k.y[(size_t)i * k.cout + o] = act_fwd(z[o], k.act);
+      for (int v = 0; v < nvec; ++v) {
+        load8(vaddr(k.x, n, h, w, v * 8), z);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (v * 8 + e < k.cout) yp[v * 8 + e] = act_fwd(z[e], k.act);
+      }
     }
   }
 }
 __global__ void __launch_bounds__(256) outact_bwd_kernel(OutActK k) {
   const unsigned total = (unsigned)k.dx.N * k.dx.H * k.dx.W;
+  const int nvec = k.dx.C / 8;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     unsigned t = i;
     const int w = (int)(t % k.dx.W); t /= k.dx.W;
     const int h = (int)(t % k.dx.H);
     const int n = (int)(t / k.dx.H);
-    float g[8];
+    const float* gp = k.dlogits + (size_t)i * k.cout;
+    for (int v = 0; v < nvec; ++v) {
+      float g[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) g[o] = o < k.cout ? k.dlogits[(size_t)i * k.cout + o] : 0.f;
-    store8(vaddr(k.dx, n, h, w, 0), g);
+      for (int e = 0; e < 8; ++e) g[e] = v * 8 + e < k.cout ? gp[v * 8 + e] : 0.f;
+      store8(vaddr(k.dx, n, h, w, v * 8), g);
+    }
   }
 }
 struct OutActLaunch : PreparedOp {
@@ -468,7 +494,7 @@ struct OutActLaunch : PreparedOp {
 };
 static PreparedOp* prep_outact(const b2seg_outact_desc* d, bool bwd) {
   const b2seg_view& v = bwd ? d->dx : d->x;
-  if (v.C != 8 || d->cout < 1 || d->cout > 8) { set_error("outact: needs an 8-channel view and 1 <= cout <= 8"); return nullptr; }
+  if (v.C < 8 || v.C % 8 || d->cout < 1 || d->cout > v.C) { set_error("outact: needs a view of C %% 8 == 0 channels and 1 <= cout <= C"); return nullptr; }
   if (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_SIGMOID && d->act != B2SEG_ACT_SOFTMAX) { set_error("outact: activation %d", d->act); return nullptr; }
   if ((long long)v.N * v.H * v.W >= (1ll << 31)) { set_error("outact: too many pixels"); return nullptr; }
   if (bwd ? !d->dlogits : !d->y) { set_error("outact: null fp32 buffer"); return nullptr; }
