@@ -350,29 +350,30 @@ class UNet:
         W, k, d = self.model_width, self.kernel_size, self.model_depth
         g = Graph(1)
         if onn:
-            # every Conv_Block becomes one operational layer (two per encoder level), nothing is normalised
-            def conv_block(g, x, W, k, mult):
+            # SelfUNet3P: every Conv_Block becomes one operational layer (two per encoder level), nothing is normalised
+            def block(x, mult):
                 return g.oper(x, W * mult, k, q=self.q)
             pool, convs = g.input(1, self.length, self.num_channel), []
             for i in range(1, d + 1):
-                conv = conv_block(g, conv_block(g, pool, W, k, 2 ** (i - 1)), W, k, 2 ** (i - 1))
+                conv = block(block(pool, 2 ** (i - 1)), 2 ** (i - 1))
                 pool = g.pool(conv, 2)
                 convs.append(conv)
             if self.A_E == 1:
                 pool = feature_extraction_block(g, pool, W, self.feature_number)
-            deconv = conv_block(g, conv_block(g, pool, W, k, 2 ** d), W, k, 2 ** d)
+            deconv = block(block(pool, 2 ** d), 2 ** d)
         else:
-            conv_block = globals()["conv_block"]
+            def block(x, mult):
+                return conv_block(g, x, W, k, mult)
             convs, deconv = self._encoder(g)
         levels, decs = [], {}
         for j in range(d):
-            parts = [conv_block(g, convs[d - j - 1], W, k, 1)]
+            parts = [block(convs[d - j - 1], 1)]
             for q in range(0, d - j - 1):
-                parts.append(conv_block(g, g.pool(convs[q], 2 ** ((d - j) - q - 1)), W, k, 1))
-            parts.append(g.act(up_conv_block(g, conv_block(g, deconv, W, k, 1), 2), "sigmoid"))
+                parts.append(block(g.pool(convs[q], 2 ** ((d - j) - q - 1)), 1))
+            parts.append(g.act(up_conv_block(g, block(deconv, 1), 2), "sigmoid"))
             for m in range(j):
-                parts.append(g.act(up_conv_block(g, conv_block(g, decs[m], W, k, 1), 2 ** (j - m)), "sigmoid"))
-            deconv = conv_block(g, g.concat(parts), W, k, d + 1)
+                parts.append(g.act(up_conv_block(g, block(decs[m], 1), 2 ** (j - m)), "sigmoid"))
+            deconv = block(g.concat(parts), d + 1)
             decs[j] = deconv
             if self.D_S == 1:
                 levels.append(g.conv(deconv, 1, 1, strides=2, name=f"level{d - j}"))
