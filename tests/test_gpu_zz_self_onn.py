@@ -74,7 +74,7 @@ def test_self_onn_pow_tanh_outact():
         torch.cuda.synchronize()
         zf = z.float()[..., :cout]
         want = torch.sigmoid(zf) if act == L.ACT_SIGMOID else (torch.softmax(zf, -1) if act == L.ACT_SOFTMAX else zf)
-        assert rel_l2(yv, want) < 1e-5
+        assert rel_l2(yv, want) < 1e-4      # __expf
         assert torch.equal(dzo[..., :cout], dl.to(torch.bfloat16)) and float(dzo.float()[..., cout:].abs().max()) == 0
 
 
