@@ -142,3 +142,20 @@ def test_ds_target_pyramid_on_device():
         losses[how] = m.train_on_batch(x, mask if how == "device" else prepareTrainDict(mask, 3, "UNet"))
     # same weights, same targets: equal up to the summation order of the loss kernel's atomics
     assert abs(losses["host"] - losses["device"]) < 1e-5 * max(1.0, abs(losses["host"])), losses
+
+
+def test_wide_softmax_head_per_layer():
+    """an 11-class softmax head: above the 8 classes of the pointwise-head kernels the 1x1 convolution runs on the tensor-core
+    kernels and b2seg_outact applies the softmax (unet_variants.py:1106 with output_nums = 11)"""
+    kw = dict(num_channels=3, ds=1, output_nums=11, final_activation="softmax")
+    m = unet_model_builder("UNet", 64, 64, 16, 3, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(24)
+    x = rng.random((4, 64, 64, 3), dtype=np.float32)
+    targets, losses = [], []
+    for n in m.graph.outputs:
+        H, W, C = n.shape
+        if n.name == "out":
+            targets.append(np.eye(C, dtype=np.float32)[rng.integers(0, C, (4, H, W))]); losses.append("cce")
+        else:
+            targets.append(rng.standard_normal((4, H, W, C)).astype(np.float32)); losses.append("mse")
+    check_per_layer(m, Ref2D("UNet", 64, 64, 16, 3, **kw), 2, x, targets, losses, e2e_bound=1.0)

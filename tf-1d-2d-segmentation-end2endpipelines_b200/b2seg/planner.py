@@ -1321,7 +1321,8 @@ class Planner:
                 d.dx = dz.to_c()
                 self.emit(1, L.OP_BN_BWD, d, f"act bwd {out_node.name}")
             has_bias_grad = True
-        self.grad_taps[n.name] = (dz, co)
+        if not u.get("no_tap"):
+            self.grad_taps[n.name] = (dz, co)
         # ---- weight / bias gradients
         strided = n.op == "conv" and a["strides"] != (1, 1)
         xin = x.view.parity(0, 0, a["strides"][0], a["strides"][1]) if strided else x.view
