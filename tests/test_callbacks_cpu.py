@@ -144,3 +144,46 @@ def test_compile_ds_targets_target_lists():
     assert all(t is not None for t in m._targets(d))
     with pytest.raises(ValueError):
         m.compile(loss="mse", ds_targets="pyramid")
+
+
+def test_fit_host_batching_with_ds_targets(monkeypatch):
+    """fit()'s host-side slicing with compile(ds_targets=...): only the mask travels (None marks the device-derived targets) through
+    the full batches, the ragged last batch and the validation split; evaluate() rebuilds the pyramid on the host.  The device
+    side is replaced by recorders here (the real path is exercised by tests/test_gpu_zz_self_onn.py)."""
+    from b2seg.models2d import unet_model_builder
+    m = unet_model_builder("UNet", 32, 32, 8, 2, ds=1, train_mode="from_scratch").ResNet50()
+    m.compile(loss={"out": "bce", "level1": "mse", "level2": "mse"}, optimizer="adam", ds_targets="UNet")
+    seen = {"pipelined": [], "single": [], "eval": []}
+
+    def fake_pipelined(batches):
+        seen["pipelined"] += batches
+        return [0.5] * len(batches)
+
+    def fake_train_on_batch(x, y, return_loss=True):
+        seen["single"].append((x, y))
+        return 0.25
+
+    def fake_evaluate(x, y, batch_size=32, **kw):
+        seen["eval"].append((x, m._targets(y, host=True)))
+        return 0.125
+    monkeypatch.setattr(m, "_train_batches_pipelined", fake_pipelined)
+    monkeypatch.setattr(m, "train_on_batch", fake_train_on_batch)
+    monkeypatch.setattr(m, "evaluate", fake_evaluate)
+    rng = np.random.default_rng(3)
+    x = rng.random((25, 32, 32, 3), dtype=np.float32)
+    mask = (rng.random((25, 32, 32, 1)) > 0.5).astype(np.float32)
+    h = m.fit(x, mask, batch_size=8, epochs=1, shuffle=False, verbose=0, validation_split=0.2)
+    # 25 samples, 20 % held out -> 20 for training: two full batches of 8 and a ragged one of 4
+    assert len(seen["pipelined"]) == 2 and len(seen["single"]) == 1
+    for bi, (bx, bys) in enumerate(seen["pipelined"]):
+        assert bx.shape == (8, 32, 32, 3) and np.array_equal(bx, x[8 * bi:8 * bi + 8])
+        assert np.array_equal(bys[0], mask[8 * bi:8 * bi + 8]) and bys[1:] == [None, None]
+    rx, ry = seen["single"][0]
+    assert rx.shape == (4, 32, 32, 3) and isinstance(ry, np.ndarray) and np.array_equal(ry, mask[16:20])
+    (vx, vt), = seen["eval"]
+    assert vx.shape == (5, 32, 32, 3) and [t.shape for t in vt] == [(5, 32, 32, 1), (5, 16, 16, 1), (5, 8, 8, 1)]
+    assert np.array_equal(vt[0], mask[20:]) and h.history["loss"] == [pytest.approx((0.5 + 0.5 + 0.25) / 3)] and h.history["val_loss"] == [0.125]
+    # without ds_targets the same call is refused: three outputs need three target arrays
+    m.compile(loss={"out": "bce", "level1": "mse", "level2": "mse"}, optimizer="adam")
+    with pytest.raises(ValueError, match="expected 3 target arrays"):
+        m.fit(x, mask, batch_size=8, epochs=1, verbose=0)
