@@ -139,7 +139,7 @@ class KerasRef:
             return F.leaky_relu(x, 0.3)
         if fn == "sigmoid":
             return torch.sigmoid(x)
-        if fn == "softmax":
+        if fn in ("softmax", "Softmax"):          # 'Softmax' resolves to the Softmax layer (axis -1), like 'ReLU' / 'LeakyReLU'
             return torch.softmax(x, dim=-1)
         if fn == "tanh":
             return torch.tanh(x)
@@ -239,7 +239,7 @@ class KerasRef:
                 y = self._rec(base if last else f"{base}/add" + (f"_{k}" if k else ""), y)
                 k += 1
         if activation is not None:
-            if activation in ("sigmoid", "softmax"):
+            if activation in ("sigmoid", "softmax", "Softmax"):
                 self.logits[base] = y
             y = self._rec(base, self.activation_fn(activation, y))
         return y

@@ -175,3 +175,17 @@ def test_unsupported_loss_head_pairs_are_refused():
     g = unet_model_builder("UNet", 16, 16, 8, 2, final_activation="tanh", train_mode="from_scratch").build_graph()
     with pytest.raises(PlanError, match="is not lowered"):
         Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+
+
+def test_activation_identifiers_resolve_like_keras2():
+    """Activation('ReLU') / ('LeakyReLU') / final_activation='Softmax' name advanced-activation LAYERS; 'Sigmoid' and 'Linear' name nothing"""
+    g = unet_model_builder("UNet", 16, 16, 8, 2, output_nums=3, final_activation="Softmax", train_mode="from_scratch").build_graph()
+    assert g.outputs[0].attrs["activation"] == "softmax"
+    for bad in ("Sigmoid", "Linear", "softMax"):
+        with pytest.raises(ValueError, match="Unknown activation function"):
+            unet_model_builder("UNet", 16, 16, 8, 2, final_activation=bad, train_mode="from_scratch").build_graph()
+    k = KerasRef(2, dtype=torch.float64)
+    x = torch.randn(2, 3, 3, 4, dtype=torch.float64)
+    assert torch.equal(k.activation_fn("Softmax", x), torch.softmax(x, -1))
+    with pytest.raises(ValueError, match="Unknown activation function"):
+        k.activation_fn("Sigmoid", x)

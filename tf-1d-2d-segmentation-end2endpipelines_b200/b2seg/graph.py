@@ -40,6 +40,28 @@ _BASE_NAMES = {
 }
 
 
+# tf.keras.activations.get(name) in Keras 2: the functions of keras.activations by their (lower-case) names, plus the advanced
+# activation LAYER classes by their class names — which is why the reference's Activation('ReLU') / Activation('LeakyReLU')
+# (2DCNN unet_variants.py:7,17) work, why final_activation="Softmax" (Train.py:54 suggests that spelling) works, and why
+# "Sigmoid" or "Linear" raise.
+_KERAS_ACTIVATION_FUNCTIONS = {"linear", "relu", "sigmoid", "softmax", "tanh", "elu", "selu", "gelu", "swish", "softplus", "softsign",
+                               "exponential", "hard_sigmoid", "leaky_relu", "relu6", "silu", "mish", "log_softmax"}
+_KERAS_ACTIVATION_LAYERS = {"ReLU": "ReLU", "LeakyReLU": "LeakyReLU", "Softmax": "softmax", "PReLU": "PReLU", "ELU": "elu",
+                            "ThresholdedReLU": "ThresholdedReLU"}
+
+
+def keras_activation_name(name):
+    """canonical name of a Keras-2 activation identifier; ValueError for what tf.keras.activations.get would not resolve"""
+    if name is None or callable(name):
+        return name
+    if name in _KERAS_ACTIVATION_FUNCTIONS:
+        return name
+    if name in _KERAS_ACTIVATION_LAYERS:
+        return _KERAS_ACTIVATION_LAYERS[name]
+    raise ValueError(f"Unknown activation function: '{name}'. Please ensure you are using a `keras.utils.custom_object_scope` "
+                     f"and that this object is included in the scope.")
+
+
 class Graph:
     """Builder-side graph: layer factory methods mirror the tf.keras.layers calls the reference makes."""
 
@@ -90,7 +112,7 @@ class Graph:
         else:
             Ho, Wo = (H - kh) // sh + 1, (W - kw) // sw + 1
         return self._add("conv", [x], (Ho, Wo, filters), name, filters=int(filters), kernel=(kh, kw), strides=(sh, sw), padding=padding,
-                         activation=activation, init=kernel_initializer)
+                         activation=keras_activation_name(activation), init=kernel_initializer)
 
     def tconv(self, x: Node, filters, kernel, strides, padding="same", name=None) -> Node:
         kh, kw = self._pair(kernel, self.ndim)
@@ -104,7 +126,7 @@ class Graph:
         return self._add("bn", [x], x.shape, name, eps=1e-3, momentum=0.99)
 
     def act(self, x: Node, fn: str, name=None) -> Node:
-        return self._add("act", [x], x.shape, name, fn=fn)
+        return self._add("act", [x], x.shape, name, fn=keras_activation_name(fn))
 
     def pool(self, x: Node, size) -> Node:
         ph, pw = self._pair(size, self.ndim)
@@ -165,7 +187,7 @@ class Graph:
             acc = self._add("add", [acc] + take, acc.shape, base if last else f"{base}/add" + (f"_{k}" if k else ""))
             k += 1
         if activation is not None:
-            acc = self._add("act", [acc], acc.shape, base, fn=activation)
+            acc = self._add("act", [acc], acc.shape, base, fn=keras_activation_name(activation))
         # the node called `base` is the nested model's output (what Keras reports as the output of layer oper2d[_k]);
         # with q = 1 and no activation that is the convolution itself, which keeps its ONN_Conv_1 name
         return acc
