@@ -187,3 +187,75 @@ def test_fit_host_batching_with_ds_targets(monkeypatch):
     m.compile(loss={"out": "bce", "level1": "mse", "level2": "mse"}, optimizer="adam")
     with pytest.raises(ValueError, match="expected 3 target arrays"):
         m.fit(x, mask, batch_size=8, epochs=1, verbose=0)
+
+
+# ---- Keras weight-file layouts (b2seg.keras_io) on an h5py-shaped fake: the build image has no HDF5 library ---------------------------
+class _FakeGroup(dict):
+    """quacks like an h5py group: mapping with .attrs, nested paths through '/'"""
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.attrs = {}
+
+    def __getitem__(self, key):
+        node = self
+        for part in str(key).split("/"):
+            node = dict.__getitem__(node, part)
+        return node
+
+    def put(self, path, value):
+        node = self
+        parts = path.split("/")
+        for part in parts[:-1]:
+            if part not in node.keys():
+                dict.__setitem__(node, part, _FakeGroup())
+            node = dict.__getitem__(node, part)
+        dict.__setitem__(node, parts[-1], value)
+
+
+def test_keras_weight_file_layouts():
+    from b2seg.keras_io import select_for_model, weight_order, weights_from_tree
+    from b2seg.models2d import unet_model_builder
+    m = unet_model_builder("UNet", 16, 16, 8, 1, train_mode="from_scratch").ResNet50()
+    specs = m.graph.param_specs()
+    w = m.get_weight_dict()
+    order = weight_order(specs)
+    assert order["conv2d"] == ["kernel", "bias"] and order["batch_normalization"] == ["gamma", "beta", "moving_mean", "moving_variance"]
+    # Keras-2 save_weights layout, plain and nested under model_weights (model.save)
+    legacy = _FakeGroup()
+    legacy.attrs["layer_names"] = [l.encode() for l in order] + [b"max_pooling2d"]
+    for layer, names in order.items():
+        legacy.put(layer, _FakeGroup())
+        legacy[layer].attrs["weight_names"] = [f"{layer}/{n}:0".encode() for n in names]
+        for n in names:
+            legacy[layer].put(f"{layer}/{n}:0", w[f"{layer}/{n}"])
+    legacy.put("max_pooling2d", _FakeGroup())                      # parameter-free layers have empty groups
+    legacy["max_pooling2d"].attrs["weight_names"] = []
+    for root in (legacy, _FakeGroup(model_weights=legacy)):
+        got, extra = select_for_model(weights_from_tree(root, order), specs)
+        assert extra == [] and set(got) == set(w) and all(np.array_equal(got[k], w[k]) for k in w)
+    # .keras (v3) layout: unnamed variables in creation order
+    v3 = _FakeGroup()
+    for layer, names in order.items():
+        for i, n in enumerate(names):
+            v3.put(f"layers/{layer}/vars/{i}", w[f"{layer}/{n}"])
+    v3.put("layers/max_pooling2d/vars", _FakeGroup())
+    got, _ = select_for_model(weights_from_tree(v3, order), specs)
+    assert all(np.array_equal(got[k], w[k]) for k in w)
+    # errors: a missing weight, a wrong shape, an unknown layout, a variable-count mismatch
+    broken = dict(got)
+    del broken["out/bias"]
+    with pytest.raises(ValueError, match="lacks 1 of"):
+        select_for_model(broken, specs)
+    with pytest.raises(ValueError, match="shape"):
+        select_for_model(dict(got, **{"out/bias": np.zeros(3, np.float32)}), specs)
+    with pytest.raises(ValueError, match="not a Keras weight file"):
+        weights_from_tree(_FakeGroup(), order)
+    v3.put("layers/conv2d/vars/2", np.zeros(1))
+    with pytest.raises(ValueError, match="holds 3 variables"):
+        weights_from_tree(v3, order)
+    # without h5py the facade says what to do instead of failing obscurely
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(NotImplementedError, match="keras_weights_to_npz"):
+            m.load_weights("/nonexistent/best.h5")

@@ -142,8 +142,12 @@ class Model:
         p = str(path)
         if not os.path.exists(p) and os.path.exists(p + ".npz"):
             p = p + ".npz"
-        if p.endswith(".h5") or p.endswith(".keras"):
-            raise NotImplementedError("Keras .h5/.keras weight files: SURVEY §8(f) rank 1 (next); use the .npz produced by save_weights")
+        if p.endswith((".h5", ".hdf5", ".keras")):
+            # Keras weight files (Train.py:363,375): needs h5py, absent from the build image — see b2seg/keras_io.py
+            from .keras_io import read_keras_weights, select_for_model
+            weights, _extra = select_for_model(read_keras_weights(p, self.graph.param_specs()), self.graph.param_specs())
+            self.set_weight_dict(weights)
+            return
         with np.load(p) as z:
             self.set_weight_dict({k.replace("::", "/"): z[k] for k in z.files})
 
