@@ -1,0 +1,88 @@
+"""Test infrastructure: a stand-in for b2seg.engine.Engine that replays the planner's program on the float64 CPU descriptor emulator
+(tests/desc_emulator.py) instead of the GPU.  It exists so that the PYTHON side of the GPU test-suite — model facade, target
+handling, tap names, oracle teacher forcing, tolerances plumbing — can be dry-run where no GPU exists (tests/test_gpu_dryrun_cpu.py).
+It proves nothing about the CUDA kernels and is never importable from the product: the product's Engine raises without a B200."""
+from typing import Dict
+
+import numpy as np
+import torch
+
+from b2seg import _lib as L
+from b2seg.helpers import derive_targets_host
+from b2seg.planner import Planner
+from desc_emulator import PlanMem, run_phase
+
+
+class CpuEngine:
+    def __init__(self, graph, batch, training=True, losses=None, loss_weights=None, adam=None, device=None, share_params_from=None,
+                 adam_bucket_bytes=0):
+        self.graph, self.batch, self.training = graph, batch, training
+        self.mem = PlanMem()
+        self.planner = p = Planner(graph, batch, self.mem.alloc_bytes, training=training, losses=losses, loss_weights=loss_weights,
+                                   adam=adam, adam_bucket_bytes=adam_bucket_bytes).build()
+        self.adam_bucket_bytes = adam_bucket_bytes
+        H, W, Cin = graph.inputs[0].shape
+        self.x_dev = torch.zeros(batch, H, W, Cin, dtype=torch.float32)
+        self.outputs = []
+        for o in sorted(p.outputs, key=lambda o: o["index"]):
+            numel = int(np.prod(o["shape"]))
+            y = self.mem.f32(o["ptr"], numel).view(o["shape"])
+            t = self.mem.f32(o["target_ptr"], numel).view(o["shape"]) if training else None
+            self.outputs.append(dict(name=o["name"], y=y, target=t, shape=o["shape"]))
+        self.loss_buf = self.mem.f32(p.loss_ptr, 1)
+        self.step = 0
+        self.dev = torch.device("cpu")
+        if share_params_from is not None:
+            self.set_weights(share_params_from.get_weights())
+
+    # ---- weights
+    def _arena(self, ptr, e):
+        return self.mem.f32(ptr + 4 * e.offset, e.size)
+
+    def set_weights(self, params: Dict[str, np.ndarray], strict=True):
+        p = self.planner
+        for e in p.params:
+            if e.key not in params:
+                if strict:
+                    raise KeyError(f"missing weight {e.key}")
+                continue
+            flat = torch.from_numpy(p.to_internal(e.key, np.asarray(params[e.key], np.float32))).double()
+            if e.trainable:
+                self._arena(p.w_ptr, e)[:] = flat
+                wb, off = self.mem.resolve(p.wb_ptr + 2 * e.offset)
+                wb[off:off + e.size] = flat
+            else:
+                self._arena(p.mov_ptr, e)[:] = flat
+
+    def get_weights(self):
+        p = self.planner
+        return {e.key: p.from_internal(e.key, self._arena(p.w_ptr if e.trainable else p.mov_ptr, e).numpy().astype(np.float32)) for e in p.params}
+
+    def get_grads(self):
+        p = self.planner
+        return {e.key: p.from_internal(e.key, self._arena(p.g_ptr, e).numpy().astype(np.float32)) for e in p.params if e.trainable}
+
+    # ---- execution
+    def forward(self):
+        self.mem.f32(self.planner.input_ptr, self.x_dev.numel())[:] = self.x_dev.reshape(-1).double()
+        run_phase(self.mem, self.planner, 0)
+
+    def backward(self):
+        run_phase(self.mem, self.planner, 1)
+
+    def optimizer_step(self, lr, grad_scale=1.0):
+        self.step += 1
+        for (op, d, _note) in self.planner.ops[2]:
+            if op == L.OP_ADAM:
+                d.lr, d.step, d.grad_scale = lr, self.step, grad_scale
+        run_phase(self.mem, self.planner, 2)
+
+    def derive_targets(self):
+        mask = self.outputs[0]["target"].numpy()
+        for o, t in zip(self.outputs[1:], derive_targets_host(mask, [o["shape"] for o in self.outputs[1:]], self.graph.ndim)):
+            o["target"].copy_(torch.from_numpy(np.ascontiguousarray(t)))
+
+    def tap(self, name, grad=False):
+        p = self.planner
+        view = (p.grad_taps[name] if grad else p.taps[name])[0]
+        return self.mem.gather_view(view.to_c())[..., p.logical_channels(name)].float()

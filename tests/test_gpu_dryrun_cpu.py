@@ -1,0 +1,53 @@
+"""Dry run (CPU) of GPU tests that could not be run on hardware yet: the same test functions, with b2seg.engine.Engine replaced by
+the float64 emulator engine (tests/cpu_engine.py).  Catches mistakes in the tests' own Python — names, shapes, targets, oracle
+plumbing — before they cost a GPU run; says nothing about the kernels (in float64 the tolerances are met by ten orders of magnitude)."""
+import pytest
+import torch
+
+import b2seg.engine
+from cpu_engine import CpuEngine
+
+
+@pytest.fixture()
+def cpu_engine(monkeypatch):
+    monkeypatch.setattr(b2seg.engine, "Engine", CpuEngine)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+
+def test_dryrun_2d_self_onn_per_layer(cpu_engine):
+    from test_gpu_zz_self_onn import SELF_CASES, test_2d_self_onn_per_layer
+    for dec, kw, _size, _width, _depth in SELF_CASES:
+        test_2d_self_onn_per_layer(dec, kw, 32, 8, 2)          # reduced sizes: the emulator is a Python interpreter of descriptors
+
+
+def test_dryrun_1d_self_onn_per_layer(cpu_engine):
+    from test_gpu_zz_self_onn import test_1d_self_onn_per_layer
+    for var, kw in (("SelfUNetPP", dict(ds=1)), ("SelfR2UNetPP", dict(ds=1, t=2)), ("SelfUNet3P", dict(ds=1, q=2))):
+        test_1d_self_onn_per_layer(var, kw)
+
+
+def test_dryrun_wide_head_and_ds_targets(cpu_engine, monkeypatch):
+    import test_gpu_zz_self_onn as z
+    z.test_wide_softmax_head_per_layer()
+    # the model half of test_ds_target_pyramid_on_device (its first half calls the CUDA kernel directly)
+    import numpy as np
+    from b2seg.helpers import prepareTrainDict
+    from b2seg.model import Adam
+    from b2seg.models2d import unet_model_builder
+    rng = np.random.default_rng(23)
+    x = rng.random((2, 32, 32, 3), dtype=np.float32)
+    mask = (rng.random((2, 32, 32, 1)) > 0.6).astype(np.float32)
+    losses = {}
+    for how in ("host", "device"):
+        m = unet_model_builder("UNet", 32, 32, 8, 2, ds=1, train_mode="from_scratch").ResNet50()
+        m.compile(loss={"out": "binary_crossentropy", "level1": "mse", "level2": "mse"}, optimizer=Adam(1e-3),
+                  ds_targets="UNet" if how == "device" else None)
+        losses[how] = m.train_on_batch(x, mask if how == "device" else prepareTrainDict(mask, 2, "UNet"))
+    assert abs(losses["host"] - losses["device"]) < 1e-12
+
+
+def test_dryrun_existing_end_to_end_tests(cpu_engine):
+    """two tests that HAVE passed on the B200, replayed here as a check of the dry-run harness itself (and of later planner changes)"""
+    import test_gpu_model as g
+    g.test_unet1d_shallow_end_to_end()
+    g.test_unet2d_multiclass_mse_end_to_end()
