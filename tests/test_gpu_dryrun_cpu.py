@@ -51,3 +51,42 @@ def test_dryrun_existing_end_to_end_tests(cpu_engine):
     import test_gpu_model as g
     g.test_unet1d_shallow_end_to_end()
     g.test_unet2d_multiclass_mse_end_to_end()
+
+
+@pytest.mark.parametrize("case", ["self2d", "wide", "self1d"])
+def test_inference_plans_match_the_oracle(cpu_engine, case):
+    """predict() (moving statistics, no backward) of the families added last — Self-ONN heads are Activations, wide heads run on
+    the convolution kernels — against the oracle in inference mode, through the facade and the emulator engine; weights perturbed so
+    that BatchNorm's moving statistics and every bias matter"""
+    import numpy as np
+    from b2seg.models1d import UNet
+    from b2seg.models2d import unet_model_builder
+    from oracle.keras_ref import KerasRef
+    from oracle.ref_models import Ref1D, Ref2D
+    rng = np.random.default_rng(31)
+    if case == "self2d":
+        kw = dict(num_channels=2, ds=1, q=3)
+        m = unet_model_builder("SelfUNet", 16, 16, 8, 2, train_mode="from_scratch", **kw).ResNet50()
+        ref, ndim, x = Ref2D("SelfUNet", 16, 16, 8, 2, **kw), 2, 0.5 * rng.random((3, 16, 16, 2), dtype=np.float32)
+    elif case == "wide":
+        kw = dict(num_channels=2, ds=1, output_nums=10, final_activation="softmax")
+        m = unet_model_builder("UNet", 16, 16, 8, 2, train_mode="from_scratch", **kw).ResNet50()
+        ref, ndim, x = Ref2D("UNet", 16, 16, 8, 2, **kw), 2, rng.random((3, 16, 16, 2), dtype=np.float32)
+    else:
+        kw = dict(ds=1, t=2, q=2)
+        m = UNet(32, 2, 2, 8, 3, **kw).SelfR2UNetPP()
+        ref, ndim, x = Ref1D("SelfR2UNetPP", 32, 2, 2, 8, 3, **kw), 1, (0.5 * rng.standard_normal((3, 32, 2))).astype(np.float32)
+    w = m.get_weight_dict()
+    for k in w:
+        if k.endswith(("/gamma", "/moving_variance")):
+            w[k] = (w[k] * (1 + 0.3 * rng.random(w[k].shape))).astype(np.float32)
+        elif k.endswith(("/beta", "/bias", "/moving_mean")):
+            w[k] = (w[k] + 0.1 * rng.standard_normal(w[k].shape)).astype(np.float32)
+    m.set_weight_dict(w)
+    got = m.predict(x, batch_size=2)                    # 3 samples in batches of 2: the ragged tail is zero-padded and cut
+    got = got if isinstance(got, list) else [got]
+    k = KerasRef(ndim, params={kk: torch.from_numpy(v).double() for kk, v in w.items()}, dtype=torch.float64, training=False, strict=True)
+    want = ref(k, torch.from_numpy(x).double())
+    assert len(got) == len(want)
+    for g_, w_ in zip(got, want):
+        assert g_.shape == tuple(w_.shape) and np.allclose(g_, w_.detach().numpy(), atol=2e-6, rtol=1e-6), float(np.abs(g_ - w_.detach().numpy()).max())
