@@ -189,3 +189,11 @@ def test_activation_identifiers_resolve_like_keras2():
     assert torch.equal(k.activation_fn("Softmax", x), torch.softmax(x, -1))
     with pytest.raises(ValueError, match="Unknown activation function"):
         k.activation_fn("Sigmoid", x)
+
+
+def test_zero_filter_convolutions_fail_like_keras():
+    """MultiResBlock's int(alpha * W * 0.167) is 0 for narrow models: Keras refuses the layer, and so does the builder"""
+    with pytest.raises(ValueError, match="strictly positive"):
+        unet_model_builder("MultiResUNet", 16, 16, 4, 2, train_mode="from_scratch").build_graph()
+    with pytest.raises(ValueError, match="strictly positive"):
+        UNet(32, 2, 1, 4, 3).MultiResUNet()

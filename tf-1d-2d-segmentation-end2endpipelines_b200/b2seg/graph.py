@@ -103,7 +103,14 @@ class Graph:
             return (int(v[0]), int(v[1])) if len(v) == 2 else (1, int(v[0]))
         return (int(v), int(v)) if ndim == 2 else (1, int(v))
 
+    @staticmethod
+    def _positive_filters(filters):
+        # Keras' Conv.__init__: MultiResBlock asks for int(alpha * W * 0.167) filters (unet_variants.py:87-89), which is 0 below W = 6
+        if int(filters) <= 0:
+            raise ValueError(f"Invalid value for argument `filters`. Expected a strictly positive value. Received filters={filters}.")
+
     def conv(self, x: Node, filters, kernel, strides=1, padding="valid", activation=None, kernel_initializer="glorot_uniform", name=None) -> Node:
+        self._positive_filters(filters)
         kh, kw = self._pair(kernel, self.ndim)
         sh, sw = self._pair(strides, self.ndim)
         H, W, _ = x.shape
@@ -115,6 +122,7 @@ class Graph:
                          activation=keras_activation_name(activation), init=kernel_initializer)
 
     def tconv(self, x: Node, filters, kernel, strides, padding="same", name=None) -> Node:
+        self._positive_filters(filters)
         kh, kw = self._pair(kernel, self.ndim)
         sh, sw = self._pair(strides, self.ndim)
         assert padding == "same"
