@@ -226,3 +226,65 @@ def test_1d_unet4p_depth3(kw):
     x = torch.from_numpy(rng.standard_normal((2, 64, 2)).astype(np.float32))
     ts, losses = _targets(g, 2, rng, 1)
     _run(g, Ref1D("UNet4P", 64, 3, 2, 8, 3, **kw), x, ts, losses, 1, act_atol=2e-7)
+
+
+EXCHANGE_CASES = [
+    ("UNetPP", dict(ds=1, ag=1, output_nums=4, final_activation="softmax")),   # BASELINE config 3 family
+    ("MultiResUNet", dict()),                                                  # config 4 family
+    ("UNet", dict(lstm=1, dense_loop=2)),                                      # config 5 family
+    ("UNet", dict(ae=1, feature_number=16, ds=1)),
+    ("UNet3P", dict(ds=1)),
+    ("SelfUNet", dict(ds=1)),
+    ("UNet", dict(output_nums=10, final_activation="softmax")),
+    ("KSSNet", dict(ag=1)),
+]
+
+
+@pytest.mark.parametrize("dec,kw", EXCHANGE_CASES, ids=[f"{d}-{'-'.join(f'{k}{v}' for k, v in kw.items())}" for d, kw in EXCHANGE_CASES])
+def test_exchange_schedule_slices_are_final_when_released(dec, kw):
+    """Data parallel: Model._step all-reduces slice [lo, hi) of the gradient arena right after backward op n_ops.  For
+    every family: the slices tile the arena, and each one already holds its FINAL value at that point (no later op adds to it) —
+    checked by replaying the backward phase in the schedule's ranges on the emulator and comparing with the finished gradient."""
+    from b2seg.graph import init_params
+    from b2seg.planner import Planner
+    from desc_emulator import PlanMem, run_phase
+    rng = np.random.default_rng(8)
+    W = 16 if kw.get("lstm") else 8
+    kw = dict(num_channels=2, **kw)
+    g = unet_model_builder(dec, 16, 16, W, 2, train_mode="from_scratch", **kw).build_graph()
+    ts, losses = _targets(g, 2, rng, 2)
+    mem = PlanMem()
+    pl = Planner(g, 2, mem.alloc_bytes, training=True, losses=losses, adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7),
+                 adam_bucket_bytes=2048).build()
+    params = init_params(g, seed=5)
+    for e in pl.params:
+        flat = torch.from_numpy(pl.to_internal(e.key, params[e.key])).double()
+        if e.trainable:
+            mem.f32(pl.w_ptr + 4 * e.offset, e.size)[:] = flat
+            wb, off = mem.resolve(pl.wb_ptr + 2 * e.offset)
+            wb[off:off + e.size] = flat
+        else:
+            mem.f32(pl.mov_ptr + 4 * e.offset, e.size)[:] = flat
+    x = 0.5 * rng.random((2, 16, 16, 2))
+    mem.f32(pl.input_ptr, x.size)[:] = torch.from_numpy(x.reshape(-1))
+    for o in pl.outputs:
+        mem.f32(o["target_ptr"], ts[o["index"]].numel())[:] = ts[o["index"]].reshape(-1).double()
+    run_phase(mem, pl, 0)
+    n = max(pl.n_train, 64)
+    grads = mem.f32(pl.g_ptr, n)
+    sched = pl.exchange_schedule(bucket_bytes=2048)
+    covered = sorted((lo, hi) for (_, lo, hi) in sched)
+    assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    assert len(sched) >= 3 and sched[0][0] < len(pl.ops[1])
+    assert len(pl.ops[2]) == len(sched)                       # one Adam op per bucket, over the same slices
+    for (op, d, _note), (_n_ops, lo, hi) in zip(pl.ops[2], sched):
+        assert (d.n, d.g) == (hi - lo, pl.g_ptr + 4 * lo)
+    done, released = 0, []
+    for (n_ops, lo, hi) in sched:
+        run_phase(mem, pl, 1, done, n_ops - done)
+        done = n_ops
+        released.append((lo, hi, grads[lo:hi].clone()))
+    run_phase(mem, pl, 1, done, len(pl.ops[1]) - done)
+    assert float(grads.abs().max()) > 0
+    for lo, hi, snap in released:
+        assert torch.equal(snap, grads[lo:hi]), (dec, lo, hi, float((snap - grads[lo:hi]).abs().max()))
