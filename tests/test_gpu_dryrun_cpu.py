@@ -90,3 +90,63 @@ def test_inference_plans_match_the_oracle(cpu_engine, case):
     assert len(got) == len(want)
     for g_, w_ in zip(got, want):
         assert g_.shape == tuple(w_.shape) and np.allclose(g_, w_.detach().numpy(), atol=2e-6, rtol=1e-6), float(np.abs(g_ - w_.detach().numpy()).max())
+
+
+@pytest.mark.parametrize("case", ["unetpp_ds_ag", "self_unet", "bcdunet1d"])
+def test_three_adam_steps_track_the_oracle(cpu_engine, case):
+    """train_on_batch x 3 through the facade on the emulator engine against the oracle's trajectory (Keras-2 Adam rule with its step
+    counter, BatchNorm moving statistics carried from step to step, several weighted outputs): losses and final weights in float64"""
+    import numpy as np
+    from b2seg.model import Adam
+    from b2seg.models1d import BCDUNet
+    from b2seg.models2d import unet_model_builder
+    from oracle.keras_ref import KerasRef, keras_adam_step, keras_loss
+    from oracle.ref_models import Ref1D, Ref2D
+    rng = np.random.default_rng(41)
+    if case == "unetpp_ds_ag":
+        kw = dict(num_channels=2, ds=1, ag=1, output_nums=3, final_activation="softmax")
+        m, ref, ndim = unet_model_builder("UNetPP", 16, 16, 8, 2, train_mode="from_scratch", **kw).ResNet50(), Ref2D("UNetPP", 16, 16, 8, 2, **kw), 2
+        x = rng.random((2, 16, 16, 2), dtype=np.float32)
+    elif case == "self_unet":
+        kw = dict(num_channels=2, ds=1, q=3)
+        m, ref, ndim = unet_model_builder("SelfUNet", 16, 16, 8, 2, train_mode="from_scratch", **kw).ResNet50(), Ref2D("SelfUNet", 16, 16, 8, 2, **kw), 2
+        x = 0.5 * rng.random((2, 16, 16, 2), dtype=np.float32)
+    else:
+        kw = dict(ds=1, lstm=1, ag=1, dense_loop=2)
+        m, ref, ndim = BCDUNet(32, 2, 2, 16, 3, **kw).BCDUNet(), Ref1D("BCDUNet", 32, 2, 2, 16, 3, **kw), 1
+        x = rng.standard_normal((2, 32, 2)).astype(np.float32)
+    targets, losses = [], []
+    for i, n in enumerate(m.graph.outputs):
+        shp = (2,) + (tuple(n.shape) if ndim == 2 else tuple(n.shape[1:]))
+        fn = n.attrs.get("activation") if n.op == "conv" else n.attrs.get("fn")
+        if fn == "softmax":
+            targets.append(np.eye(shp[-1], dtype=np.float32)[rng.integers(0, shp[-1], shp[:-1])]); losses.append("cce")
+        elif fn == "sigmoid":
+            targets.append((rng.random(shp) > 0.5).astype(np.float32)); losses.append("bce")
+        else:
+            targets.append(rng.standard_normal(shp).astype(np.float32)); losses.append("mse")
+    lw = [1.0 - 0.15 * i for i in range(len(targets))]
+    m.compile(loss=losses, optimizer=Adam(2e-3), loss_weights=lw)
+    tp = {k: torch.from_numpy(v.copy()).double() for k, v in m.get_weight_dict().items()}
+    st = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in tp.items()}
+    got, want = [], []
+    for t in range(1, 4):
+        got.append(m.train_on_batch(x, targets if len(targets) > 1 else targets[0]))
+        k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=True)
+        outs = ref(k, torch.from_numpy(x).double())
+        total = sum(w * keras_loss(kind, o, torch.from_numpy(tg).double(), logits=k.logits.get(name))
+                    for w, kind, o, tg, name in zip(lw, losses, outs, targets, m.output_names))
+        total.backward()
+        want.append(float(total))
+        with torch.no_grad():
+            for key in k.trainable:
+                if tp[key].grad is not None:
+                    keras_adam_step(tp[key], tp[key].grad, st[key][0], st[key][1], t, lr=2e-3)
+                    tp[key].grad = None
+            for key, v in k.new_moving.items():
+                tp[key] = v
+    assert np.allclose(got, want, rtol=2e-5, atol=1e-7), (got, want)
+    final = m.get_weight_dict()
+    worst = max(float(np.abs(final[key] - tp[key].detach().numpy()).max()) for key in tp)
+    # the emulator keeps float64 but the facade moves weights through float32 (as the device does): 1e-5 absolute
+    assert worst < 2e-5, worst
