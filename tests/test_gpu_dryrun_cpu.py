@@ -22,7 +22,7 @@ def test_dryrun_2d_self_onn_per_layer(cpu_engine):
 
 def test_dryrun_1d_self_onn_per_layer(cpu_engine):
     from test_gpu_zz_self_onn import test_1d_self_onn_per_layer
-    for var, kw in (("SelfUNetPP", dict(ds=1)), ("SelfR2UNetPP", dict(ds=1, t=2)), ("SelfUNet3P", dict(ds=1, q=2))):
+    for var, kw in (("SelfUNetPP", dict(ds=1)), ("SelfR2UNetPP", dict(ds=1, t=2, q=2)), ("SelfUNet3P", dict(ds=1, q=2))):
         test_1d_self_onn_per_layer(var, kw)
 
 

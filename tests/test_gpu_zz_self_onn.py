@@ -104,8 +104,8 @@ def test_2d_self_onn_per_layer(dec, kw, size, width, depth):
     check_per_layer(m, Ref2D(dec, size, size, width, depth, **kw), 2, x, targets, losses, e2e_bound=1.0, mask_outputs=[m.output_names[0]])
 
 
-@pytest.mark.parametrize("var,kw", [("SelfUNetPP", dict(ds=1)), ("SelfR2UNetPP", dict(ds=1, t=2)), ("SelfUNet3P", dict(ds=1, q=2))],
-                         ids=["SelfUNetPP", "SelfR2UNetPP", "SelfUNet3P-q2"])
+@pytest.mark.parametrize("var,kw", [("SelfUNetPP", dict(ds=1)), ("SelfR2UNetPP", dict(ds=1, t=2, q=2)), ("SelfUNet3P", dict(ds=1, q=2))],
+                         ids=["SelfUNetPP", "SelfR2UNetPP-q2", "SelfUNet3P-q2"])
 def test_1d_self_onn_per_layer(var, kw):
     """1DCNN/Models/unet_variants.py:1312-1583 (Oper1D pairs, Oper1DTranspose with kernel 4, Self_Recurrent_Conv_Block)"""
     m = getattr(UNet(256, 2, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), var)()
