@@ -172,9 +172,11 @@ def test_unsupported_loss_head_pairs_are_refused():
         with pytest.raises(PlanError, match="is not lowered"):
             Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=losses, adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
     Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse", "mae", "mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    # a tanh head is a convolution + an Activation output: MSE is fine, cross-entropy is not
     g = unet_model_builder("UNet", 16, 16, 8, 2, final_activation="tanh", train_mode="from_scratch").build_graph()
+    Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
     with pytest.raises(PlanError, match="is not lowered"):
-        Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+        Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["bce"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
 
 
 def test_activation_identifiers_resolve_like_keras2():

@@ -44,6 +44,9 @@ CASES_2D = [
     ("UNetPP", dict(ae=1, ds=1, feature_number=16)),
     ("UNet", dict(ds=1, output_nums=11, final_activation="softmax")),   # more than 8 classes: tensor-core 1x1 convolution + output activation op
     ("UNetPP", dict(output_nums=9, final_activation="sigmoid")),
+    ("UNet", dict(ds=1, final_activation="tanh")),             # regression heads: convolution + named Activation output
+    ("UNet3P", dict(output_nums=2, final_activation="relu")),
+    ("MultiResUNet", dict(final_activation="LeakyReLU")),
     ("MultiResUNet", dict(ae=1, feature_number=16)),   # Flatten of an odd-channel (gapped, padded) tensor: the Dense kernel rows follow its physical layout
 ]
 

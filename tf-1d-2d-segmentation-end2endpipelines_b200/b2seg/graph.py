@@ -118,8 +118,17 @@ class Graph:
             Ho, Wo = -(-H // sh), -(-W // sw)
         else:
             Ho, Wo = (H - kh) // sh + 1, (W - kw) // sw + 1
-        return self._add("conv", [x], (Ho, Wo, filters), name, filters=int(filters), kernel=(kh, kw), strides=(sh, sw), padding=padding,
-                         activation=keras_activation_name(activation), init=kernel_initializer)
+        act = keras_activation_name(activation)
+        fused = act if act in (None, "linear", "sigmoid", "softmax") else None
+        c = self._add("conv", [x], (Ho, Wo, filters), name, filters=int(filters), kernel=(kh, kw), strides=(sh, sw), padding=padding,
+                      activation=fused, init=kernel_initializer)
+        if fused is act:
+            return c
+        # Conv(..., activation='relu' | 'tanh' | ...) — only ever a head here (final_activation, 2DCNN unet_variants.py:1106): the layer is
+        # lowered as the convolution (which keeps the layer's name, hence its weight keys) followed by an Activation that carries
+        # the layer's name as a model output; the tensor called `name` in Keras is the activated one, so the raw one is not tapped
+        c.attrs["no_tap"] = True
+        return self._add("act", [c], c.shape, f"{c.name}/activation", fn=act, output_name=c.name)
 
     def tconv(self, x: Node, filters, kernel, strides, padding="same", name=None) -> Node:
         self._positive_filters(filters)

@@ -63,7 +63,7 @@ class Model:
     def __init__(self, graph: Graph):
         self.graph = graph
         self.name = graph.name
-        self.output_names = [n.name for n in graph.outputs]
+        self.output_names = [n.attrs.get("output_name", n.name) for n in graph.outputs]   # (a head with a non-fused activation: graph.conv)
         self._weights: Dict[str, np.ndarray] = init_params(graph)
         self._engines: Dict[tuple, object] = {}
         self._primary = None

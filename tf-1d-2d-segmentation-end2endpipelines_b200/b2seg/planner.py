@@ -259,6 +259,8 @@ class Planner:
                     # convolution runs on the tensor-core kernels, its activation in the output op
                     wide_head = a["activation"]
                 u = dict(kind="conv", node=n, bn=None, act=None, pool=None)
+                if a.get("no_tap"):
+                    u["no_tap"] = True
                 if wide_head is not None:
                     u["out"] = n
                     u["no_tap"] = True        # the tensor called `n.name` is the activated output, not these logits
