@@ -165,7 +165,7 @@ def test_fit_host_batching_with_ds_targets(monkeypatch):
 
     def fake_evaluate(x, y, batch_size=32, **kw):
         seen["eval"].append((x, m._targets(y, host=True)))
-        return 0.125
+        return {"loss": 0.125} if kw.get("return_dict") else 0.125
     monkeypatch.setattr(m, "_train_batches_pipelined", fake_pipelined)
     monkeypatch.setattr(m, "train_on_batch", fake_train_on_batch)
     monkeypatch.setattr(m, "evaluate", fake_evaluate)
@@ -259,3 +259,36 @@ def test_keras_weight_file_layouts():
     except ImportError:
         with pytest.raises(NotImplementedError, match="keras_weights_to_npz"):
             m.load_weights("/nonexistent/best.h5")
+
+
+def test_validation_metrics_of_the_reference_configuration(monkeypatch):
+    """The shipped Train_Configs.ini compiles with metrics=[MeanSquaredError] and lets its callbacks monitor val_mean_squared_error
+    (Train_Configs.ini:36,44; Train.py:324,372-391): fit() must log that key.  Metrics are computed on the host from predict()."""
+    from b2seg.models2d import unet_model_builder
+
+    class MeanSquaredError:            # stands in for tf.keras.metrics.MeanSquaredError(name='mean_squared_error')
+        name = "mean_squared_error"
+    rng = np.random.default_rng(5)
+    x = rng.random((6, 16, 16, 3), dtype=np.float32)
+    y = (rng.random((6, 16, 16, 1)) > 0.5).astype(np.float32)
+    pred = rng.random((6, 16, 16, 1)).astype(np.float32)
+    m = unet_model_builder("UNet", 16, 16, 8, 1, train_mode="from_scratch").ResNet50()
+    m.compile(loss="binary_crossentropy", optimizer="adam", metrics=[MeanSquaredError(), "BinaryAccuracy", "acc", "AUC"])
+    monkeypatch.setattr(m, "predict", lambda x_, batch_size=None, **kw: pred[:len(x_)])
+    logs = m.evaluate(x, y, return_dict=True)
+    assert set(logs) == {"loss", "mean_squared_error", "binary_accuracy", "accuracy"}          # AUC is not a host-side metric: left out
+    assert logs["mean_squared_error"] == pytest.approx(float(((pred.astype(np.float64) - y) ** 2).mean()))
+    assert logs["binary_accuracy"] == logs["accuracy"] == pytest.approx(float(((pred > 0.5) == (y > 0.5)).mean()))
+    assert isinstance(m.evaluate(x, y), float) and m.evaluate(x, y) == pytest.approx(logs["loss"])
+    monkeypatch.setattr(m, "_train_batches_pipelined", lambda batches: [0.7] * len(batches))
+    from b2seg.callbacks import EarlyStopping
+    es = EarlyStopping(monitor="val_mean_squared_error", patience=0)
+    h = m.fit(x[:4], y[:4], batch_size=2, epochs=3, verbose=0, validation_data=(x[4:], y[4:]), callbacks=[es], shuffle=False)
+    assert "val_mean_squared_error" in h.history and "val_loss" in h.history
+    assert len(h.history["loss"]) == 2                      # constant predictions: no improvement in epoch 2 -> stopped by the monitor
+    # several outputs: Keras prefixes the output name
+    m2 = unet_model_builder("UNet", 16, 16, 8, 1, ds=1, train_mode="from_scratch").ResNet50()
+    m2.compile(loss={"out": "bce", "level1": "mse"}, optimizer="adam", metrics=["mse"], ds_targets="UNet")
+    monkeypatch.setattr(m2, "predict", lambda x_, batch_size=None, **kw: [pred[:len(x_)], pred[:len(x_), ::2, ::2]])
+    logs2 = m2.evaluate(x, y, return_dict=True)
+    assert set(logs2) == {"loss", "out_mean_squared_error", "level1_mean_squared_error"}

@@ -341,7 +341,9 @@ def test_fit_and_history_api():
     x = rng.random((16, 32, 32, 1), dtype=np.float32)
     y = (x > 0.5).astype(np.float32)
     h = m.fit(x, y, batch_size=8, epochs=3, validation_data=(x[:8], y[:8]), verbose=0)
-    assert set(h.history) == {"loss", "val_loss"} and len(h.history["loss"]) == 3
+    # (validation metrics are computed on the host from predict(); per-batch training metrics are not produced)
+    assert set(h.history) == {"loss", "val_loss", "val_accuracy"} and len(h.history["loss"]) == 3
+    assert all(0.0 <= a <= 1.0 for a in h.history["val_accuracy"])
     assert h.history["loss"][-1] < h.history["loss"][0]
     w = m.get_weights()
     assert len(w) == len(m.graph.param_specs())

@@ -48,6 +48,38 @@ class History:
         self.epoch: List[int] = []
 
 
+# Keras metric identifiers the reference passes to compile(metrics=...) (2DCNN/utils/tf_metrics.py; the shipped INI uses MeanSquaredError
+# and monitors val_mean_squared_error, Train_Configs.ini:36,44).  Computed on the host from predict() for the VALIDATION logs of fit()
+# (what the reference's callbacks monitor); per-batch training metrics would need every output read back and are not produced.
+def _m_bin_acc(t, p):
+    return float(((p > 0.5) == (t > 0.5)).mean())
+
+
+def _m_cat_acc(t, p):
+    return float((p.argmax(-1) == t.argmax(-1)).mean())
+
+
+_METRICS = {
+    "mean_squared_error": lambda t, p: float(((p - t) ** 2).mean()), "mean_absolute_error": lambda t, p: float(np.abs(p - t).mean()),
+    "binary_accuracy": _m_bin_acc, "categorical_accuracy": _m_cat_acc,
+    "accuracy": lambda t, p: _m_cat_acc(t, p) if p.shape[-1] > 1 else _m_bin_acc(t, p),    # Keras picks by the output shape
+    "binary_crossentropy": lambda t, p: float(-(t * np.log(np.clip(p, 1e-7, 1 - 1e-7)) + (1 - t) * np.log(1 - np.clip(p, 1e-7, 1 - 1e-7))).mean()),
+}
+_METRIC_ALIASES = {"mse": "mean_squared_error", "mae": "mean_absolute_error", "acc": "accuracy", "meansquarederror": "mean_squared_error",
+                   "meanabsoluteerror": "mean_absolute_error", "binaryaccuracy": "binary_accuracy", "categoricalaccuracy": "categorical_accuracy",
+                   "binarycrossentropy": "binary_crossentropy"}
+
+
+def _metric_name(obj):
+    """canonical name of a metric given as a string or as an object with .name (tf.keras.metrics.MeanSquaredError(name=...)); None if
+    it is not one of the host-side metrics above"""
+    key = obj if isinstance(obj, str) else (getattr(obj, "name", None) or type(obj).__name__)
+    key = str(key)
+    low = key.lower().replace(" ", "")
+    name = key if key in _METRICS else _METRIC_ALIASES.get(low, low if low in _METRICS else None)
+    return name
+
+
 def _loss_name(obj) -> str:
     if isinstance(obj, str):
         key = obj.lower().replace(" ", "")
@@ -360,6 +392,14 @@ class Model:
             else:
                 l = np.abs(p - t).mean()
             total += w * float(l)
+        if kw.get("return_dict"):
+            logs = {"loss": total}
+            names = [n for n in (_metric_name(mt) for mt in (self.metrics or [])) if n is not None]
+            for out_name, p, t in zip(self.output_names, pred, ys):
+                t = t[:, 0] if self.graph.ndim == 1 else t
+                for n in names:        # Keras prefixes the output's name when the model has several outputs
+                    logs[n if len(pred) == 1 else f"{out_name}_{n}"] = _METRICS[n](np.asarray(t, np.float64), p.astype(np.float64))
+            return logs
         return total
 
     def _train_batches_pipelined(self, batches):
@@ -459,7 +499,8 @@ class Model:
             logs = {"loss": float(np.mean(losses))}
             if validation_data is not None:
                 vx, vy = validation_data[:2]
-                logs["val_loss"] = self.evaluate(vx, vy, batch_size=batch_size or 32)
+                for k_, v_ in self.evaluate(vx, vy, batch_size=batch_size or 32, return_dict=True).items():
+                    logs[f"val_{k_}"] = v_
             if verbose:
                 print(f"Epoch {ep + 1}/{epochs} - {time.time() - t0:.1f}s - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
             for cb in callbacks:
