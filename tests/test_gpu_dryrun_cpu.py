@@ -183,3 +183,22 @@ def test_dryrun_fit_history_and_callbacks(cpu_engine, monkeypatch, tmp_path):
     monkeypatch.setattr(Model, "__init__", init)
     g.test_fit_and_history_api()
     g.test_fit_with_reference_callbacks_and_validation_split(tmp_path)
+
+
+def test_dryrun_every_model_test_of_the_gpu_suite(cpu_engine):
+    """All train_on_batch / predict based tests of tests/test_gpu_model.py at their real sizes, on the emulator engine: after a planner
+    or facade change, the Python half of the GPU suite is known to work before a GPU is spent on it (about 40 s)."""
+    import test_gpu_model as g
+    g.test_unet2d_shallow_end_to_end()
+    g.test_unet2d_autoencoder_bottleneck_end_to_end()
+    g.test_unet1d_autoencoder_bottleneck_end_to_end()
+    g.test_training_reduces_loss_and_matches_oracle_trajectory()
+    g.test_predict_uses_moving_statistics()
+    g.test_1d_bcdunet_lstm_ag_ds_per_layer()
+    for case in g.FAMILY_CASES:
+        g.test_2d_families_per_layer(*case)
+    for kw in (dict(), dict(ds=1, ag=1)):
+        g.test_fpn_per_layer(kw)
+    for var, kw in [("RUNet", dict(ds=1, t=2)), ("R2UNet", dict(ds=1, ag=1, t=2)), ("R2UNetPP", dict(ds=1, t=1)), ("R2UNet3P", dict(ds=1, t=1)),
+                    ("UNet4P", dict(ds=1, ag=1)), ("MultiResUNet3P", dict(ds=1))]:
+        g.test_1d_recurrent_unets_per_layer(var, kw)
