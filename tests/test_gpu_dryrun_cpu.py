@@ -202,3 +202,10 @@ def test_dryrun_every_model_test_of_the_gpu_suite(cpu_engine):
     for var, kw in [("RUNet", dict(ds=1, t=2)), ("R2UNet", dict(ds=1, ag=1, t=2)), ("R2UNetPP", dict(ds=1, t=1)), ("R2UNet3P", dict(ds=1, t=1)),
                     ("UNet4P", dict(ds=1, ag=1)), ("MultiResUNet3P", dict(ds=1))]:
         g.test_1d_recurrent_unets_per_layer(var, kw)
+
+
+def test_dryrun_golden_fixture_replay(cpu_engine):
+    """tests/test_gpu_golden.py on the emulator engine: the committed fixtures still load into the product and reproduce"""
+    import test_gpu_golden as t
+    for spec in t.CASES:
+        t.test_training_step_matches_golden(spec)
