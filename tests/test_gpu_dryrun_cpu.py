@@ -209,3 +209,14 @@ def test_dryrun_golden_fixture_replay(cpu_engine):
     import test_gpu_golden as t
     for spec in t.CASES:
         t.test_training_step_matches_golden(spec)
+
+
+def test_dryrun_smoke_entry(cpu_engine, monkeypatch, capsys):
+    """__graft_entry__.smoke() (the driver's first GPU step of every round) on the emulator engine"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as entry
+    monkeypatch.setattr(CpuEngine, "launches", [0, 0, 0], raising=False)
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
