@@ -30,8 +30,14 @@ class CpuEngine:
             t = self.mem.f32(o["target_ptr"], numel).view(o["shape"]) if training else None
             self.outputs.append(dict(name=o["name"], y=y, target=t, shape=o["shape"]))
         self.loss_buf = self.mem.f32(p.loss_ptr, 1)
+        n = max(p.n_train, 64)
+        self.w, self.g = self.mem.f32(p.w_ptr, n), self.mem.f32(p.g_ptr, n)          # flat arenas (views), as Engine exposes them
+        self.m, self.v = self.mem.f32(p.m_ptr, n), self.mem.f32(p.v_ptr, n)
+        self.moving = self.mem.f32(p.mov_ptr, max(p.n_moving, 64))
+        self.wb = self.w                                                              # (no separate bf16 shadow worth modelling)
         self.step = 0
         self.dev = torch.device("cpu")
+        self._shared = share_params_from       # the real Engine aliases the primary's arenas; here they are re-read before every forward
         if share_params_from is not None:
             self.set_weights(share_params_from.get_weights())
 
@@ -64,17 +70,27 @@ class CpuEngine:
 
     # ---- execution
     def forward(self):
+        if self._shared is not None:
+            self.set_weights(self._shared.get_weights())
         self.mem.f32(self.planner.input_ptr, self.x_dev.numel())[:] = self.x_dev.reshape(-1).double()
         run_phase(self.mem, self.planner, 0)
 
     def backward(self):
         run_phase(self.mem, self.planner, 1)
 
-    def optimizer_step(self, lr, grad_scale=1.0):
+    def run_range(self, phase, first_op, n_ops):
+        if phase == 0 and first_op == 0:
+            self.mem.f32(self.planner.input_ptr, self.x_dev.numel())[:] = self.x_dev.reshape(-1).double()
+        run_phase(self.mem, self.planner, phase, first_op, n_ops)
+
+    def optimizer_begin(self, lr, grad_scale=1.0):
         self.step += 1
         for (op, d, _note) in self.planner.ops[2]:
             if op == L.OP_ADAM:
                 d.lr, d.step, d.grad_scale = lr, self.step, grad_scale
+
+    def optimizer_step(self, lr, grad_scale=1.0):
+        self.optimizer_begin(lr, grad_scale)
         run_phase(self.mem, self.planner, 2)
 
     def derive_targets(self):

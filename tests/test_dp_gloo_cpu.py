@@ -139,3 +139,62 @@ def test_ops_overlapping_exchange_replay():
     # nothing to exchange -> nothing reserved; a bucket that is only ready after the last op reserves nothing but the tail
     assert ops_overlapping_exchange(op_ms, [], 1e-6, 1.2)[0] == []
     assert ops_overlapping_exchange(op_ms, [(10, 0, 1024)], 1e-9, 1.2)[0] == [9]
+
+
+# ---- the same through the facade: Model.distribute() + Model._step's data-parallel branch (the host code that runs on 8 GPUs) ----------
+def _facade_model():
+    from b2seg.model import Adam
+    from b2seg.models2d import unet_model_builder
+    m = unet_model_builder("UNetPP", 16, 16, 8, 2, num_channels=1, ds=1, ag=1, train_mode="from_scratch").ResNet50()
+    m.compile(loss={"out": "bce", "level1": "mse", "level2": "mse"}, optimizer=Adam(1e-2), ds_targets="UNetPP")
+    m.exchange_bucket_bytes = 4096
+    return m
+
+
+def _facade_worker(rank, world, port, out):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tf-1d-2d-segmentation-end2endpipelines_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import b2seg.engine
+    from cpu_engine import CpuEngine
+    b2seg.engine.Engine = CpuEngine
+    from b2seg.dist import shard_range
+    x, y = _data()
+    b, e = shard_range(x.shape[0], rank, world)
+    m = _facade_model().distribute()
+    eng = m._engine(e - b, True)
+    assert len(eng.planner.ops[2]) == len(eng.planner.exchange_schedule(4096)) >= 3      # a data-parallel plan: one Adam op per bucket
+    if rank == 1:                                # rank 1 starts from different weights: broadcast_weights must repair that
+        eng.w.mul_(1.5)
+    m.broadcast_weights(0)
+    loss = m.train_on_batch(x[b:e].numpy(), y[b:e].numpy())
+    torch.save(dict(w=eng.w.clone(), loss=loss), os.path.join(out, f"facade{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_through_the_facade(tmp_path, monkeypatch):
+    """Model.distribute / broadcast_weights / _step with world_size 2 over gloo, each rank on the emulator engine: identical weights on
+    both ranks, equal to one process that averages the two replicas' gradients by hand and applies one Adam step"""
+    port = _free_port()
+    mp.spawn(_facade_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "facade0.pt"), torch.load(tmp_path / "facade1.pt")
+    assert torch.equal(r0["w"], r1["w"])
+    import b2seg.engine
+    from cpu_engine import CpuEngine
+    monkeypatch.setattr(b2seg.engine, "Engine", CpuEngine)
+    x, y = _data()
+    grads = []
+    for (b, e) in ((0, 2), (2, 4)):
+        m = _facade_model()
+        eng = m._engine(e - b, True)
+        eng.x_dev.copy_(x[b:e])
+        eng.outputs[0]["target"].copy_(y[b:e])
+        eng.derive_targets()
+        eng.forward()
+        eng.backward()
+        grads.append(eng.g.clone())
+    eng.g[:] = (grads[0] + grads[1]) / 2
+    eng.optimizer_step(1e-2, 1.0)
+    assert torch.allclose(r0["w"], eng.w, atol=1e-12, rtol=0), float((r0["w"] - eng.w).abs().max())
