@@ -288,7 +288,7 @@ typedef struct b2seg_tpool_desc {
 } b2seg_tpool_desc;
 
 const char* b2seg_last_error(void);
-int b2seg_version(void);
+int b2seg_version(void);   /* 101; the ctypes binding refuses a library of another version */
 int b2seg_device_check(int device);
 int b2seg_sizeof_desc(int op);  /* sizeof the descriptor struct of a B2SEG_OP_* code (binding self-check, no GPU needed) */
 

@@ -64,3 +64,14 @@ def test_builder_api_errors_match_reference():
         UNet(0, 2, 1, 8, 3).UNet()
     with pytest.raises(NameError):
         unet_model_builder("MultiResUNet", 32, 32, 8, 2, lstm=1, train_mode="from_scratch").build_graph()
+
+
+def test_binding_refuses_a_library_of_another_abi_version(monkeypatch):
+    """a stale libb2seg.so must fail loudly at load time, not with a missing symbol in the middle of a step"""
+    from b2seg import _lib as L
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "ABI_VERSION", L.ABI_VERSION + 1)
+    with pytest.raises(L.B2SegError, match="rebuild"):
+        L.load()
+    monkeypatch.setattr(L, "ABI_VERSION", L.ABI_VERSION - 1)
+    assert L.load().b2seg_version() == L.ABI_VERSION

@@ -21,6 +21,7 @@ ACT_CODES = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "ReLU": ACT_R
  OP_CAST, OP_COLSUM, OP_MEMSET, OP_RESIZE_FWD, OP_RESIZE_BWD, OP_MULBC_FWD, OP_MULBC_BWD, OP_COLSTATS, OP_LSTM_FWD,
  OP_LSTM_BWD, OP_POOL_BWD, OP_ROWSUM, OP_OUTACT_FWD, OP_OUTACT_BWD, OP_TARGET_POOL) = range(1, 26)
 PHASE_FWD, PHASE_BWD, PHASE_OPT = 0, 1, 2
+ABI_VERSION = 101    # b2seg_version() of the library this binding mirrors (include/b2seg.h)
 
 
 class View(C.Structure):
@@ -179,6 +180,9 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise B2SegError(f"{LIB_PATH} not built: run `python __graft_entry__.py` (there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
+    have = lib.b2seg_version() if hasattr(lib, "b2seg_version") else -1
+    if have != ABI_VERSION:
+        raise B2SegError(f"{LIB_PATH} implements ABI {have}, this binding needs {ABI_VERSION}: rebuild it (`python __graft_entry__.py`)")
     lib.b2seg_last_error.restype = C.c_char_p
     for name, desc in [("b2seg_conv", ConvDesc), ("b2seg_wgrad", WgradDesc), ("b2seg_bn_finalize", BnFinalizeDesc),
                        ("b2seg_bn_act", BnActDesc), ("b2seg_bn_bwd", BnBwdDesc), ("b2seg_adam", AdamDesc),
