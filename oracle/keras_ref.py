@@ -21,6 +21,20 @@ import torch
 import torch.nn.functional as F
 
 
+class _TeacherForce(torch.autograd.Function):
+    """forward: the other implementation's tensor, bit for bit; backward: the gradient goes to the oracle's own tensor.  Lets
+    the oracle differentiate ITS layers at the forward values another implementation produced (max-pool routing, ReLU masks and
+    every Jacobian are then evaluated on identical numbers)."""
+
+    @staticmethod
+    def forward(ctx, y, dev):
+        return dev.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 class KerasRef:
     """Eager mini functional API.  ndim: 1 or 2.  Tensors are channels-last like Keras: (N, L, C) / (N, H, W, C)."""
 
@@ -41,6 +55,9 @@ class KerasRef:
         self.override: Optional[Dict[str, torch.Tensor]] = None   # teacher forcing, see _rec
         self.local_err: Dict[str, float] = {}
         self.local_out: Dict[str, torch.Tensor] = {}
+        # teacher forcing with gradient flow: tensors named in `cut` are replaced by leaves (the graph is cut there), every other
+        # overridden tensor takes the supplied VALUE but stays connected to the oracle graph (straight-through), see _rec
+        self.cut: Optional[set] = None
 
     # ---- naming: keras.backend.unique_object_name semantics -----------------------------------------------
     def _name(self, base: str, name: Optional[str]) -> str:
@@ -122,7 +139,13 @@ class KerasRef:
                 raise ValueError(f"override for {name}: shape {tuple(dev.shape)} != {tuple(y.shape)}")
             self.local_err[name] = float((dev - y.detach()).norm() / (y.detach().norm() + 1e-30))
             self.local_out[name] = y
-            y = dev.clone().requires_grad_(self.training)
+            if self.cut is not None and name not in self.cut and y.requires_grad:
+                # gradient teacher forcing (tests/test_gpu_model.py check_per_layer): value of the other implementation, Jacobian
+                # of the oracle — only the tensors in `cut` start a new graph, where the caller injects the other
+                # implementation's gradient
+                y = _TeacherForce.apply(y, dev)
+            else:
+                y = dev.clone().requires_grad_(self.training)
         if self.training and y.requires_grad:
             y.retain_grad()
         self.acts[name] = y

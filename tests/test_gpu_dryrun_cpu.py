@@ -204,6 +204,17 @@ def test_dryrun_every_model_test_of_the_gpu_suite(cpu_engine):
         g.test_1d_recurrent_unets_per_layer(var, kw)
 
 
+def test_dryrun_round2_parity_tests(cpu_engine, monkeypatch):
+    """the GPU tests added in round 2 (1D nested variants; BASELINE configs 3 / 4 / 5 — here at reduced size, the emulator being a
+    Python interpreter of descriptors; float32 oracle path included)"""
+    import test_gpu_model as g
+    for var, kw in [("UNetE", dict(ds=1)), ("UNetP", dict(ds=1)), ("UNetPP", dict(ds=1)), ("UNetPP", dict(ds=1, ag=1, is_transconv=False)),
+                    ("UNet3P", dict(ds=1)), ("MultiResUNet", dict(ds=1)), ("MultiResUNet", dict(ds=0, ag=1, alpha=1.5))]:
+        g.test_1d_nested_unets_per_layer(var, kw)
+    for (cid, dec, kw, _size, _width, _depth, batch, dtype) in g.BASELINE_SHAPE_CASES:
+        g.test_baseline_configs_3_4_5_at_their_shapes_per_layer((cid, dec, kw, 32, 16, 2, 2, dtype), monkeypatch)
+
+
 def test_dryrun_golden_fixture_replay(cpu_engine):
     """tests/test_gpu_golden.py on the emulator engine: the committed fixtures still load into the product and reproduce"""
     import test_gpu_golden as t

@@ -64,6 +64,7 @@ def test_training_step_matches_golden(spec):
         e = rel_l2(grads[k[len("grad/"):]], gold[k])
         # gradients next to the loss see almost no accumulated noise; the first layers sit behind every ReLU mask of the model,
         # where bf16 storage noise flips a fraction of the masks (tests/tools_bf16_noise_sim.py): loose bound only
+        print(f"[golden {spec['name']}] {k}: rel-L2 {e:.3f}")
         assert e < (0.05 if pos in (2, 4) else 0.6), (k, e)
     after = m.get_weight_dict()
     for k in gold.files:

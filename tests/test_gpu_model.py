@@ -56,16 +56,19 @@ def _device_step(model, x, targets, losses, lr=1e-3, loss_weights=None):
     return params, loss, eng
 
 
+ORACLE_DTYPE = torch.float64    # (the BASELINE-shape tests of the 512x512 MultiResUNet switch the oracle to float32: 2 G elements per sample)
+
+
 def _oracle(ref, ndim, params, x, targets, losses, out_names, loss_weights=None, override=None):
-    tp = {k: torch.from_numpy(np.array(v)).double() for k, v in params.items()}
+    tp = {k: torch.from_numpy(np.array(v)).to(ORACLE_DTYPE) for k, v in params.items()}
     # the MultiRes / ResPath families build ResPaths on the deepest encoder level that nothing consumes (Keras prunes them; the
     # eager oracle evaluates them with weights of its own), hence strict=False for those families only
-    k = KerasRef(ndim, params=tp, dtype=torch.float64, training=True, strict=not ({getattr(ref, "dec", ""), getattr(ref, "var", "")} & {"MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet", "R2UNet3P"}))
+    k = KerasRef(ndim, params=tp, dtype=ORACLE_DTYPE, training=True, strict=not ({getattr(ref, "dec", ""), getattr(ref, "var", "")} & {"MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet", "R2UNet3P"}))
     k.override = override
-    outs = ref(k, torch.from_numpy(x).double())
+    outs = ref(k, torch.from_numpy(x).to(ORACLE_DTYPE))
     total = 0
     for i, (o, t) in enumerate(zip(outs, targets)):
-        total = total + (loss_weights[i] if loss_weights else 1.0) * keras_loss(losses[i], o, torch.from_numpy(t).double(), logits=k.logits.get(out_names[i]))
+        total = total + (loss_weights[i] if loss_weights else 1.0) * keras_loss(losses[i], o, torch.from_numpy(t).to(ORACLE_DTYPE), logits=k.logits.get(out_names[i]))
     return k, tp, outs, total
 
 
@@ -102,9 +105,11 @@ def check_end_to_end(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights
         assert e < tol, ("activation", name, e)
         n_checked += 1
     assert n_checked >= 5
+    worst_ag = worst_pg = 0.0
     for name in eng.planner.grad_taps:
         if name in k.acts and k.acts[name].grad is not None and eng.planner.taps.get(name, (0, 0, ""))[2] == "raw":
             e = rel_l2(_squeeze(eng.tap(name, grad=True).cpu(), ndim), k.acts[name].grad)
+            worst_ag = max(worst_ag, e)
             assert e < E2E_GRAD_TOL, ("activation grad", name, e)
     grads = eng.get_grads()
     gmax = max(float(tp[kk].grad.abs().max()) for kk in grads if tp[kk].grad is not None)
@@ -115,18 +120,74 @@ def check_end_to_end(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights
         elif float(want.norm()) < 1e-6 * gmax * want.numel() ** 0.5:
             assert float(np.abs(g).max()) < 1e-4 * gmax + 1e-7, ("tiny grad", key)
         else:
+            worst_pg = max(worst_pg, rel_l2(g, want))
             assert rel_l2(g, want) < E2E_GRAD_TOL, ("param grad", key, rel_l2(g, want))
+    print(f"\n[{model.name}] free-running: worst activation-gradient rel-L2 {worst_ag:.3f}, worst parameter-gradient rel-L2 {worst_pg:.3f}")
 
 
-def check_per_layer(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=None, tol=TOL, e2e_bound=0.5, mask_outputs=None):
-    """teacher-forced per-layer parity (forward of every materialised layer, weight gradient of every conv layer)"""
+def check_teacher_forced_gradients(model, ref, ndim, params, x, targets, losses, loss_weights, eng, override, tol=TOL):
+    """Activation gradients in situ (BASELINE.json: "per-layer activations AND gradients").  The oracle is evaluated at the device's
+    forward values (every stored tensor overrides the oracle's, straight-through: value of the device, Jacobian of the oracle —
+    identical ReLU masks and max-pool arg-maxes).  The graph is CUT at every raw convolution output the device keeps a gradient for
+    (dZ): there the device's own dZ is injected as the upstream gradient, so what is compared at a convolution output A is
+
+        oracle:  dZ_A = J(A -> next cut tensors B ...)^T . dZ_B(device)   vs   device: dZ_A
+
+    i.e. exactly one hop of the device's backward pass — dgrad of the consuming convolutions, BatchNorm / activation / max-pool /
+    up-sampling / attention-multiply / ConvLSTM-gate backward and the gradient-source summation in between — judged on its own
+    arithmetic.  The same backward pass yields every parameter gradient of those hops (gamma, beta, biases, head kernels)."""
+    pl = eng.planner
+    cut = {name for name in pl.grad_taps if name in override and pl.taps.get(name, (0, 0, ""))[2] in ("raw", "act")}
+    tp = {k_: torch.from_numpy(np.array(v)).to(ORACLE_DTYPE) for k_, v in params.items()}
+    k = KerasRef(ndim, params=tp, dtype=ORACLE_DTYPE, training=True, strict=not ({getattr(ref, "dec", ""), getattr(ref, "var", "")} & {"MultiResUNet", "MultiResUNet3P", "KSSNet", "AHNet", "R2UNet3P"}))
+    k.override, k.cut = override, cut
+    outs = ref(k, torch.from_numpy(x).to(ORACLE_DTYPE))
+    total = 0
+    for i, (o, t) in enumerate(zip(outs, targets)):
+        total = total + (loss_weights[i] if loss_weights else 1.0) * keras_loss(losses[i], o, torch.from_numpy(t).to(ORACLE_DTYPE), logits=k.logits.get(model.output_names[i]))
+    dz_dev = {name: _squeeze(eng.tap(name, grad=True).cpu().to(ORACLE_DTYPE), ndim) for name in cut}
+    for name in cut:
+        total = total + (k.local_out[name] * dz_dev[name]).sum()
+    total.backward()
+    worst, n = 0.0, 0
+    gmax = max(float(v.abs().max()) for v in dz_dev.values())
+    for name in sorted(cut):
+        want = k.acts[name].grad
+        if want is None:
+            continue
+        if float(want.norm()) < 1e-9 * gmax * want.numel() ** 0.5:
+            continue        # (a tensor no loss term reaches through a live path)
+        e = rel_l2(dz_dev[name], want)
+        worst, n = max(worst, e), n + 1
+        assert e < tol, ("teacher-forced activation gradient", name, e)
+    assert n >= 3, n
+    grads = eng.get_grads()
+    worst_pg = 0.0
+    pmax = max(float(tp[kk].grad.abs().max()) for kk in grads if tp[kk].grad is not None)
+    for key, g in grads.items():
+        want = tp[key].grad
+        if want is None or key.endswith("/kernel") and key.rsplit("/", 1)[0] in pl.grad_taps:
+            continue        # (kernels of tapped convolutions: checked layer by layer above)
+        if float(want.norm()) < 1e-6 * pmax * want.numel() ** 0.5:
+            assert float(np.abs(g).max()) < 1e-4 * pmax + 1e-7, ("tiny grad", key)
+            continue
+        e = rel_l2(g, want)
+        worst_pg = max(worst_pg, e)
+        assert e < tol, ("teacher-forced parameter gradient", key, e)
+    return worst, n, worst_pg
+
+
+def check_per_layer(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=None, tol=TOL, e2e_bound=0.5, mask_outputs=None,
+                    free_running=True):
+    """teacher-forced per-layer parity (forward of every materialised layer, weight gradient of every conv layer, activation
+    gradient of every convolution output and every other parameter gradient: check_teacher_forced_gradients)"""
     params, loss, eng = _device_step(model, x, targets, losses, lr, loss_weights)
     override = {}
     for name, (view, C, kind) in eng.planner.taps.items():
         if kind in ("raw", "act"):
-            override[name] = _squeeze(eng.tap(name).cpu().double(), ndim)
+            override[name] = _squeeze(eng.tap(name).cpu().to(ORACLE_DTYPE), ndim)
     for o in eng.outputs:
-        override[o["name"]] = _squeeze(o["y"].cpu().double(), ndim)
+        override[o["name"]] = _squeeze(o["y"].cpu().to(ORACLE_DTYPE), ndim)
     k, tp, outs, total = _oracle(ref, ndim, params, x, targets, losses, model.output_names, loss_weights, override=override)
     worst = max(k.local_err.values())
     bad = {n: e for n, e in k.local_err.items() if e >= tol}
@@ -138,26 +199,32 @@ def check_per_layer(model, ref, ndim, x, targets, losses, lr=1e-3, loss_weights=
     for name, (view, C) in eng.planner.grad_taps.items():
         if name not in k.local_out or f"{name}/kernel" not in tp:
             continue
-        dz = _squeeze(eng.tap(name, grad=True).cpu().double(), ndim)
+        dz = _squeeze(eng.tap(name, grad=True).cpu().to(ORACLE_DTYPE), ndim)
         (gw,) = torch.autograd.grad(k.local_out[name], [tp[f"{name}/kernel"]], grad_outputs=dz, retain_graph=True)
         e = rel_l2(grads[f"{name}/kernel"], gw)
         worst_g = max(worst_g, e)
         assert e < tol, ("per-layer weight gradient", name, e)
         checked += 1
     assert checked >= 5
+    w_local = {o["name"]: k.local_out[o["name"]].detach() for o in eng.outputs}
+    del k, outs, total          # (the 512x512 configurations hold ~10 GB per oracle pass)
+    worst_dx, n_dx, worst_pg = check_teacher_forced_gradients(model, ref, ndim, params, x, targets, losses, loss_weights, eng, override, tol)
+    # masks on the teacher-forced head (the last layer's own decision given identical inputs)
+    for o in eng.outputs:
+        if (not o["name"].startswith("level")) if mask_outputs is None else (o["name"] in mask_outputs):
+            assert _mask_agreement(_squeeze(o["y"].cpu(), ndim), w_local[o["name"]]) >= 0.999, o["name"]
+    if not free_running:
+        print(f"\n[{model.name}] per-layer fwd worst {worst:.2e}, per-layer wgrad worst {worst_g:.2e}, teacher-forced activation gradient worst "
+              f"{worst_dx:.2e} over {n_dx} layers, other parameter gradients worst {worst_pg:.2e}, loss {loss:.5f}")
+        return
     # end to end (free running), reported and loosely bounded
     k2, _, outs2, total2 = _oracle(ref, ndim, params, x, targets, losses, model.output_names, loss_weights)
     e2e = max(rel_l2(_squeeze(o["y"].cpu(), ndim), w.detach()) for o, w in zip(eng.outputs, outs2))
-    print(f"\n[{model.name}] per-layer fwd worst {worst:.2e}, per-layer wgrad worst {worst_g:.2e}, end-to-end output rel-L2 {e2e:.2e}, "
+    print(f"\n[{model.name}] per-layer fwd worst {worst:.2e}, per-layer wgrad worst {worst_g:.2e}, teacher-forced activation gradient worst "
+          f"{worst_dx:.2e} over {n_dx} layers, other parameter gradients worst {worst_pg:.2e}, end-to-end output rel-L2 {e2e:.2e}, "
           f"loss {loss:.5f} vs oracle {float(total2):.5f}")
     assert e2e < e2e_bound
     assert abs(loss - float(total2)) < 0.1 * max(1.0, abs(float(total2)))
-    # masks on the teacher-forced head (the last layer's own decision given identical inputs)
-    for o, want in zip(eng.outputs, outs):
-        if (not o["name"].startswith("level")) if mask_outputs is None else (o["name"] in mask_outputs):
-            got = _squeeze(o["y"].cpu(), ndim)
-            w_local = k.local_out[o["name"]].detach()
-            assert _mask_agreement(got, w_local) >= 0.999, o["name"]
 
 
 def test_unet2d_shallow_end_to_end():
@@ -402,6 +469,8 @@ FAMILY_CASES = [
     ("UNetPP", dict(ds=1, ag=1, output_nums=4, final_activation="softmax"), 64, 16, 3),   # BASELINE config 3 graph family
     ("UNet", dict(lstm=1, dense_loop=3), 64, 16, 3),                                      # BASELINE config 5 graph family ("BCDUNet")
     ("UNet3P", dict(ds=1), 64, 16, 3),
+    ("UNetP", dict(ds=1), 64, 16, 3),                              # UNet+ (unet_variants.py:217-274)
+    ("UNetP", dict(ds=1, ag=1, is_transconv=False), 32, 16, 2),
     ("UNetE", dict(is_transconv=False, ag=1, ds=1), 32, 16, 2),   # ds=1: without it UNetE leaves dangling nodes that Keras prunes
     ("MultiResUNet", dict(), 64, 32, 3),                           # BASELINE config 4 graph family (odd channel counts: gapped concat layouts)
     ("MultiResUNet", dict(is_transconv=False, ds=1), 32, 16, 2),
@@ -470,3 +539,52 @@ def test_1d_bcdunet_lstm_ag_ds_per_layer():
     x = rng.standard_normal((4, 256, 2)).astype(np.float32)
     targets = [rng.standard_normal((4,) + (n.shape[1], n.shape[2])).astype(np.float32) for n in m.graph.outputs]
     check_per_layer(m, Ref1D("BCDUNet", 256, 3, 2, 16, 3, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=1.0)
+
+
+@pytest.mark.parametrize("var,kw", [("UNetE", dict(ds=1)), ("UNetP", dict(ds=1)), ("UNetPP", dict(ds=1)), ("UNetPP", dict(ds=1, ag=1, is_transconv=False)),
+                                    ("UNet3P", dict(ds=1)), ("MultiResUNet", dict(ds=1)), ("MultiResUNet", dict(ds=0, ag=1, alpha=1.5))],
+                         ids=["UNetE", "UNetP", "UNetPP", "UNetPP-ag1-upsampling", "UNet3P", "MultiResUNet", "MultiResUNet-ag1-alpha1.5"])
+def test_1d_nested_unets_per_layer(var, kw):
+    """the 1D variants north_star names next to UNet: UNetE / UNet+ / UNet++ / UNet3+ / MultiResUNet
+    (1DCNN/Models/unet_variants.py:321-431, 433-542, 544-645, 647-715, 836-897)"""
+    m = getattr(UNet(256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), var)()
+    rng = np.random.default_rng(15)
+    x = rng.standard_normal((4, 256, 2)).astype(np.float32)
+    targets = [rng.standard_normal((4,) + tuple(n.shape[1:])).astype(np.float32) for n in m.graph.outputs]
+    check_per_layer(m, Ref1D(var, 256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=1.0)
+
+
+def _targets_for(m, kw, rng, batch):
+    targets, losses = [], []
+    for n in m.graph.outputs:
+        H, W, C = n.shape
+        if n.name == "out" and kw.get("final_activation") == "softmax":
+            targets.append(np.eye(C, dtype=np.float32)[rng.integers(0, C, (batch, H, W))]); losses.append("cce")
+        elif n.name == "out":
+            targets.append((rng.random((batch, H, W, C)) > 0.6).astype(np.float32)); losses.append("bce")
+        else:
+            targets.append((rng.random((batch, H, W, C)) > 0.6).astype(np.float32)); losses.append("mse")
+    return targets, losses
+
+
+BASELINE_SHAPE_CASES = [
+    # (id, decoder, builder kwargs, size, width, depth, batch, oracle dtype)
+    ("cfg3-UNetPP-ds-ag-4class-256", "UNetPP", dict(num_channels=3, output_nums=4, ds=1, ag=1, final_activation="softmax"), 256, 64, 5, 1, torch.float64),
+    ("cfg4-MultiResUNet-512x512x1", "MultiResUNet", dict(num_channels=1, alpha=1.0, is_transconv=True), 512, 64, 5, 1, torch.float32),
+    ("cfg5-BCDUNet-lstm-dense3-256", "UNet", dict(num_channels=3, lstm=1, dense_loop=3, is_transconv=True), 256, 64, 5, 2, torch.float64),
+]
+
+
+@pytest.mark.parametrize("case", BASELINE_SHAPE_CASES, ids=[c[0] for c in BASELINE_SHAPE_CASES])
+def test_baseline_configs_3_4_5_at_their_shapes_per_layer(case, monkeypatch):
+    """BASELINE.json configs 3, 4 and 5 at their own resolution, width and depth (batch 1-2 so the CPU oracle finishes in about a
+    minute): the launch mix — halo tiles, resident weights, fused taps, gapped channel layouts, attention gates at five
+    resolutions — is shape dependent, so the toy-shape family tests do not cover it.  Teacher-forced per-layer forward, weight
+    gradients, activation gradients."""
+    _id, dec, kw, size, width, depth, batch, dtype = case
+    monkeypatch.setitem(globals(), "ORACLE_DTYPE", dtype)
+    m = unet_model_builder(dec, size, size, width, depth, train_mode="from_scratch", **kw).ResNet50()
+    rng = np.random.default_rng(17)
+    x = rng.random((batch, size, size, kw["num_channels"]), dtype=np.float32)
+    targets, losses = _targets_for(m, kw, rng, batch)
+    check_per_layer(m, Ref2D(dec, size, size, width, depth, **kw), 2, x, targets, losses, free_running=False)
