@@ -58,6 +58,10 @@ class KerasRef:
         # teacher forcing with gradient flow: tensors named in `cut` are replaced by leaves (the graph is cut there), every other
         # overridden tensor takes the supplied VALUE but stays connected to the oracle graph (straight-through), see _rec
         self.cut: Optional[set] = None
+        self._own: Dict[int, tuple] = {}          # id(teacher-forced tensor) -> (tensor, the oracle's own value of it)
+        # max-pool layers whose arg-max the other implementation takes on the UNROUNDED activations it recomputes in its backward
+        # pass (see MaxPooling); every other pooling layer routes to the first maximum of the stored values
+        self.pool_argmax_unrounded: set = set()
 
     # ---- naming: keras.backend.unique_object_name semantics -----------------------------------------------
     def _name(self, base: str, name: Optional[str]) -> str:
@@ -135,6 +139,8 @@ class KerasRef:
         its own arithmetic.  `local_out[name]` keeps the graph-connected oracle output for layer-local backward checks."""
         if self.override is not None and name in self.override:
             dev = self.override[name].to(self.dtype)
+            if tuple(dev.shape) != tuple(y.shape) and dev.numel() == y.numel() and y.dim() == 2:
+                dev = dev.reshape(y.shape)       # a Dense output: (N, units) here, (N, 1, 1, units) in a channels-last implementation
             if tuple(dev.shape) != tuple(y.shape):
                 raise ValueError(f"override for {name}: shape {tuple(dev.shape)} != {tuple(y.shape)}")
             self.local_err[name] = float((dev - y.detach()).norm() / (y.detach().norm() + 1e-30))
@@ -143,7 +149,9 @@ class KerasRef:
                 # gradient teacher forcing (tests/test_gpu_model.py check_per_layer): value of the other implementation, Jacobian
                 # of the oracle — only the tensors in `cut` start a new graph, where the caller injects the other
                 # implementation's gradient
+                own = y.detach()
                 y = _TeacherForce.apply(y, dev)
+                self._own[id(y)] = (y, own)
             else:
                 y = dev.clone().requires_grad_(self.training)
         if self.training and y.requires_grad:
@@ -271,6 +279,21 @@ class KerasRef:
         """MaxPooling2D((p,p)) / MaxPooling1D(p): stride = pool, 'valid' (unet_variants.py:357,790)."""
         name = self._name("max_pooling" + self._sfx(), None)
         ph, pw = self._pair(size, self.ndim)
+        if name in self.pool_argmax_unrounded and id(x) in self._own and self._own[id(x)][0] is x:
+            # Teacher-forced gradient check of an implementation that stores activations in bf16 but routes the pooling gradient
+            # to the arg-max of the activations it RECOMPUTES in fp32 (b2seg's fused BatchNorm/pool backward): bf16 rounding makes
+            # ~1 % of the windows tie, and the implementation breaks those ties by the unrounded values — which is also what an
+            # fp32 reference does.  Same rule here: maximum of the stored values, ties broken by the oracle's own (unrounded)
+            # values of the same tensor, then first in scan order.
+            xt, own = self._cf(x), self._cf(self._own[id(x)][1])
+            N, C, H, W = xt.shape
+
+            def win(t):
+                return t[:, :, :H // ph * ph, :W // pw * pw].reshape(N, C, H // ph, ph, W // pw, pw).permute(0, 1, 2, 4, 3, 5).reshape(N, C, H // ph, W // pw, ph * pw)
+            xw, ow = win(xt), win(own)
+            top = xw.detach().max(-1, keepdim=True).values
+            idx = torch.where(xw.detach() == top, ow, torch.full_like(ow, -float("inf"))).argmax(-1, keepdim=True)
+            return self._rec(name, self._cl(xw.gather(-1, idx).squeeze(-1)))
         return self._rec(name, self._cl(F.max_pool2d(self._cf(x), (ph, pw))))
 
     def UpSampling(self, x, size, interpolation="nearest"):
@@ -324,6 +347,10 @@ class KerasRef:
         h0 = torch.zeros(xt.shape[0], filters, xt.shape[2], xt.shape[3], dtype=self.dtype)
         z = z + F.conv2d(F.pad(h0, ((kw - 1) // 2, kw - 1 - (kw - 1) // 2, (kh - 1) // 2, kh - 1 - (kh - 1) // 2)), u4.permute(3, 2, 0, 1))
         zi, zf, zc, zo = torch.split(z, filters, dim=1)
+        # the three live gate pre-activations [i | c | o] as one recorded tensor (teacher forcing / gradient cut point: an
+        # implementation that stores them in bf16 evaluates the gate non-linearities on the stored values)
+        live = self._cf(self._rec(f"{name}/gates", self._cl(torch.cat([zi, zc, zo], dim=1))))
+        zi, zc, zo = torch.split(live, filters, dim=1)
         hs = lambda t: torch.clamp(0.2 * t + 0.5, 0.0, 1.0)
         c0 = torch.zeros_like(zi)
         c1 = hs(zf) * c0 + hs(zi) * torch.tanh(zc)

@@ -13,12 +13,32 @@ from b2seg.planner import Planner
 from desc_emulator import PlanMem, run_phase
 
 
+_PARAM_TAGS = ("param_w", "param_g", "param_m", "param_v", "param_wb", "moving")
+
+
 class CpuEngine:
     def __init__(self, graph, batch, training=True, losses=None, loss_weights=None, adam=None, device=None, share_params_from=None,
                  adam_bucket_bytes=0):
         self.graph, self.batch, self.training = graph, batch, training
         self.mem = PlanMem()
-        self.planner = p = Planner(graph, batch, self.mem.alloc_bytes, training=training, losses=losses, loss_weights=loss_weights,
+        self._tag_ptr = {}
+        share = share_params_from
+        if share is not None:
+            # like the real Engine, alias the primary's parameter / gradient / Adam-moment / moving-statistics arenas: same addresses,
+            # same storage; this engine's own buffers live above the primary's address range
+            self.mem.next = share.mem.next + (1 << 32)
+            for tag in _PARAM_TAGS:
+                ptr = share._tag_ptr[tag]
+                self.mem.bufs.append(next(b for b in share.mem.bufs if b[0] == ptr))
+
+        def alloc(nbytes, tag="act"):
+            if share is not None and tag in _PARAM_TAGS:
+                return share._tag_ptr[tag]
+            ptr = self.mem.alloc_bytes(nbytes, tag)
+            if tag in _PARAM_TAGS:
+                self._tag_ptr[tag] = ptr
+            return ptr
+        self.planner = p = Planner(graph, batch, alloc, training=training, losses=losses, loss_weights=loss_weights,
                                    adam=adam, adam_bucket_bytes=adam_bucket_bytes).build()
         self.adam_bucket_bytes = adam_bucket_bytes
         H, W, Cin = graph.inputs[0].shape
@@ -37,9 +57,7 @@ class CpuEngine:
         self.wb = self.w                                                              # (no separate bf16 shadow worth modelling)
         self.step = 0
         self.dev = torch.device("cpu")
-        self._shared = share_params_from       # the real Engine aliases the primary's arenas; here they are re-read before every forward
-        if share_params_from is not None:
-            self.set_weights(share_params_from.get_weights())
+        self._shared = share_params_from
 
     # ---- weights
     def _arena(self, ptr, e):
@@ -70,8 +88,6 @@ class CpuEngine:
 
     # ---- execution
     def forward(self):
-        if self._shared is not None:
-            self.set_weights(self._shared.get_weights())
         self.mem.f32(self.planner.input_ptr, self.x_dev.numel())[:] = self.x_dev.reshape(-1).double()
         run_phase(self.mem, self.planner, 0)
 
@@ -83,14 +99,19 @@ class CpuEngine:
             self.mem.f32(self.planner.input_ptr, self.x_dev.numel())[:] = self.x_dev.reshape(-1).double()
         run_phase(self.mem, self.planner, phase, first_op, n_ops)
 
-    def optimizer_begin(self, lr, grad_scale=1.0):
-        self.step += 1
+    def reset_optimizer(self):
+        self.m.zero_()
+        self.v.zero_()
+        self.step = 0
+
+    def optimizer_begin(self, lr, grad_scale=1.0, step=None):
+        self.step = self.step + 1 if step is None else int(step)
         for (op, d, _note) in self.planner.ops[2]:
             if op == L.OP_ADAM:
                 d.lr, d.step, d.grad_scale = lr, self.step, grad_scale
 
-    def optimizer_step(self, lr, grad_scale=1.0):
-        self.optimizer_begin(lr, grad_scale)
+    def optimizer_step(self, lr, grad_scale=1.0, step=None):
+        self.optimizer_begin(lr, grad_scale, step)
         run_phase(self.mem, self.planner, 2)
 
     def derive_targets(self):

@@ -73,6 +73,7 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, stric
         want = k.acts[name].detach()
         if ndim == 1:
             got = got.squeeze(1)
+        got = got.reshape(want.shape)        # (a Dense output is (N, 1, 1, units) in the plan, (N, units) in the oracle)
         # act_rtol is relative to the tensor's largest value (sums of large cancelling terms in the un-normalised Self-ONN graphs)
         assert torch.allclose(got, want, atol=act_atol + act_rtol * float(want.abs().max())), (name, float((got - want).abs().max()))
         checked += 1
@@ -83,6 +84,7 @@ def _run(graph, ref, x, targets, losses, ndim, lr=1e-2, loss_weights=None, stric
             got = mem.gather_view(view.to_c())[..., pl.logical_channels(name)]
             if ndim == 1:
                 got = got.squeeze(1)
+            got = got.reshape(k.acts[name].grad.shape)
             # descriptors carry eps / loss weights as float32 (relative 5e-8): tolerance relative to the gradient's scale
             gtol = 1e-9 + 5e-7 * float(k.acts[name].grad.abs().max())
             assert torch.allclose(got, k.acts[name].grad, atol=gtol), ("grad", name, float((got - k.acts[name].grad).abs().max()))

@@ -206,12 +206,14 @@ class Engine:
     def backward(self):
         self.run(1)
 
-    def optimizer_begin(self, lr: float, grad_scale: float = 1.0):
-        self.step += 1
+    def optimizer_begin(self, lr: float, grad_scale: float = 1.0, step: Optional[int] = None):
+        """step: Adam's t for this update.  The moments live in arenas that several engines of one Model share (one engine per
+        batch size), so the Model owns the counter and passes it in; a stand-alone engine counts its own steps."""
+        self.step = self.step + 1 if step is None else int(step)
         L.check(self.lib.b2seg_plan_set_adam(self.plan, lr, self.step, grad_scale), "set_adam")
 
-    def optimizer_step(self, lr: float, grad_scale: float = 1.0):
-        self.optimizer_begin(lr, grad_scale)
+    def optimizer_step(self, lr: float, grad_scale: float = 1.0, step: Optional[int] = None):
+        self.optimizer_begin(lr, grad_scale, step)
         self.run(2)
 
     def tap(self, name: str, grad=False) -> torch.Tensor:

@@ -139,6 +139,7 @@ class GSrc:
     premasked: bool = False
     colsums: Optional[Tuple[int, int, int]] = None   # (fp32 rows ptr, n_rows, pitch): per-CTA column sums written by the producer
     head: Optional[dict] = None   # kind 2: a pointwise head whose backward is folded into the producer's BN backward (b2seg_gradsrc)
+    pool_name: Optional[str] = None   # kind 1: the MaxPooling layer the gradient is routed through (bookkeeping for the parity tests)
 
 
 class PlanError(NotImplementedError):
@@ -185,6 +186,7 @@ class Planner:
         self.act_bytes = 0
         self.op_info: Dict[Tuple[int, int], dict] = {}
         self._grad_touched = set()
+        self.pool_routing: Dict[str, str] = {}   # max-pool layer -> "recomputed" (see _bwd_conv); absent = routed on the stored tensor
         self.grad_ready: Dict[str, int] = {}   # param key -> number of backward ops after which its gradient is final
         self._analyse()
         self._layout_params()
@@ -490,6 +492,8 @@ class Planner:
         """physical channel index of every logical channel of a tapped layer (identity unless the layout is gapped)"""
         if not hasattr(self, "_by_name"):
             self._by_name = {n.name: n for n in self.g.nodes}
+        if name.endswith("/gates"):      # ConvLSTM gate pre-activations: a dense 3F-channel buffer of its own
+            return list(range(3 * self._by_name[name[:-6]].attrs["filters"]))
         return [po + i for (po, c) in self._segs(self._by_name[name]) for i in range(c)]
 
     # ---------------------------------------------------------------------------------------- arenas
@@ -834,6 +838,7 @@ class Planner:
         self.emit(0, L.OP_LSTM_FWD, L.LstmDesc(z.to_c(), dests[0].to_c(), nv, nv, F), f"gates {n.name}")
         self._copy_extra(dests[0], dests[1:])
         self.taps[n.name] = (dests[0], F, "act")
+        self.taps[f"{n.name}/gates"] = (z, 3 * F, "raw")      # live gate pre-activations [i | g | o]
 
     # -- Feature_Extraction_Block: Flatten -> Dense -> Dense -> Reshape -------------------------------------------------------
     @staticmethod
@@ -888,6 +893,8 @@ class Planner:
                   n.name, flops=2.0 * self.N * fin * units)
         self.phys[id(n)] = Phys(out, units, [(0, units)])
         u["x"] = x.view
+        if n.name not in self.taps:
+            self.taps[n.name] = (out, units, "act")
 
     def _bwd_flatten(self, u):
         n = u["node"]
@@ -915,6 +922,7 @@ class Planner:
             return
         fin, units = n.inputs[0].shape[2], n.attrs["units"]
         fin_p = u["x"].C                      # physical width of the input (a flattened padded tensor keeps its zero lanes)
+        self.grad_taps[n.name] = (dz, units)
         flops = 2.0 * self.N * fin * units
         self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, u["x"], self.pg(f"{n.name}/kernel"), units, 1, 1, fin_p), f"wgrad {n.name}", flops=flops)
         self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")
@@ -1092,6 +1100,12 @@ class Planner:
         wins = {s.pool for s in srcs if s.kind == 1}
         if len(wins) > 1 or any(w[0] * w[1] not in (2, 4) for w in wins):
             srcs = self._direct_sources(t, srcs)
+        for s in srcs:
+            if s.kind == 1 and s.pool_name:
+                # the BatchNorm / activation / pooling backward kernel recomputes the activations in fp32 and routes the pooled
+                # gradient to THEIR first maximum (not to the first maximum of the bf16-rounded stored tensor, which is what
+                # b2seg_pool_bwd does); recorded for the parity tests
+                self.pool_routing[s.pool_name] = "recomputed"
         return self._reduce_sources(srcs, self.phys[id(t)].view)
 
     def _single_grad(self, t: Node) -> Optional[TView]:
@@ -1173,7 +1187,7 @@ class Planner:
         n = u["node"]
         srcs = self._pool_sources(n)
         for s in srcs:
-            self._add_gsrc(n.inputs[0], GSrc(s.view, 1, tuple(n.attrs["size"])))
+            self._add_gsrc(n.inputs[0], GSrc(s.view, 1, tuple(n.attrs["size"]), pool_name=n.name))
 
     def _bwd_act(self, u):
         n = u["node"]
@@ -1230,6 +1244,7 @@ class Planner:
         dz = self.new_act(H, W, 3 * F, "grad")
         nv = lw.NULL_VIEW.to_c()
         self.emit(1, L.OP_LSTM_BWD, L.LstmDesc(u["z"].to_c(), nv, dh.to_c(), dz.to_c(), F), f"gates bwd {n.name}")
+        self.grad_taps[f"{n.name}/gates"] = (dz, 3 * F)
         flops = 2.0 * self.N * H * W * x.C * 3 * F * kh * kw
         self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, x.view, self.pg(pe.key), 3 * F, kh, kw, x.Cp), f"wgrad {n.name}", flops=flops)
         self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")
@@ -1275,7 +1290,7 @@ class Planner:
         if u["pool"] is not None:
             ph, pw_ = u["pool"].attrs["size"]
             for s in self._pool_sources(u["pool"]):
-                srcs.append(GSrc(s.view, 1, (ph, pw_)))
+                srcs.append(GSrc(s.view, 1, (ph, pw_), pool_name=u["pool"].name))
         if not srcs:
             return  # dead branch (no gradient reaches it)
         x = self.phys[id(n.inputs[0])]
