@@ -181,15 +181,25 @@ typedef struct b2seg_head_desc {
   uint64_t logits;      /* optional fp32 [N,H',W',cout] pre-activation output of the forward */
 } b2seg_head_desc;
 
-/* Loss seed. kind: 0 = binary cross-entropy on sigmoid probs (Keras evaluates from logits: d = (p-y)/count),
- * 1 = categorical CE on softmax (d = (p-y)/pixels), 2 = MSE, 3 = MAE. */
+/* Loss value and backward seed dL/dlogits of one model output (tf.keras.losses.* as listed by 2DCNN/utils/tf_losses.py:8-46;
+ * reduction SUM_OVER_BATCH_SIZE = mean over every element, or over every pixel for the losses that sum over the channel axis).
+ * kind: 0 BinaryCrossentropy, 1 CategoricalCrossentropy, 2 MeanSquaredError, 3 MeanAbsoluteError, 4 MeanSquaredLogarithmicError
+ * (the shipped Train_Configs.ini:42), 5 Huber(delta 1), 6 LogCosh, 7 BinaryFocalCrossentropy(gamma 2), 8 Poisson, 9 KLDivergence,
+ * 10 Hinge, 11 SquaredHinge, 12 MeanAbsolutePercentageError, 13 CategoricalHinge, 14 CosineSimilarity.
+ * act = activation of the head (NONE / SIGMOID / SOFTMAX).  Cross-entropies on their own activation (0 or 7 on sigmoid, 1 on
+ * softmax) are evaluated like Keras 2 from the cached logits: seed (p - y) / count; on any other head from the clipped
+ * probabilities; every other loss differentiates through the activation. */
 typedef struct b2seg_loss_desc {
   uint64_t y_pred;   /* fp32 activated outputs */
   uint64_t y_true;   /* fp32 targets */
   int64_t n_pix; int32_t cout; int32_t kind; int32_t act;
   float weight;      /* loss_weights entry */
-  uint64_t dlogits;  /* fp32 out */
+  uint64_t dlogits;  /* fp32 out (0 = value only) */
   uint64_t loss;     /* fp32[1] accumulates weight*loss */
+  /* optional fp32[5], accumulated (caller-zeroed): {unweighted loss of this output, sum (p-y)^2, sum |p-y|,
+   * #elements with (p > .5) == (y > .5), #pixels with argmax p == argmax y} -- the per-output loss and the training metrics of
+   * Keras' fit() logs (Train.py:394-419 reads history.history) without a second pass over the outputs */
+  uint64_t metrics;
 } b2seg_loss_desc;
 
 typedef struct b2seg_eltwise_desc {
@@ -288,7 +298,7 @@ typedef struct b2seg_tpool_desc {
 } b2seg_tpool_desc;
 
 const char* b2seg_last_error(void);
-int b2seg_version(void);   /* 101; the ctypes binding refuses a library of another version */
+int b2seg_version(void);   /* 102; the ctypes binding refuses a library of another version */
 int b2seg_device_check(int device);
 int b2seg_sizeof_desc(int op);  /* sizeof the descriptor struct of a B2SEG_OP_* code (binding self-check, no GPU needed) */
 

@@ -373,23 +373,67 @@ class KerasRef:
 
 
 # ---- losses (SUM_OVER_BATCH_SIZE reduction = mean over all elements / pixels) and Keras Adam ----------------
+def _maybe_convert_labels(y_true):
+    """keras.losses._maybe_convert_labels: labels that are all 0 / 1 become -1 / 1 (hinge family)"""
+    if bool(((y_true == 0) | (y_true == 1)).all()):
+        return 2.0 * y_true - 1.0
+    return y_true
+
+
 def keras_loss(kind: str, y_pred, y_true, logits=None):
-    """kind in {'bce','cce','mse','mae'} (utils/tf_losses.py:10-14).  With a sigmoid/softmax head Keras 2 evaluates
-    BCE/CCE from the cached logits † (SURVEY hazard 19); pass them via `logits`."""
+    """tf.keras.losses.<X>()(y_true, y_pred) with the default SUM_OVER_BATCH_SIZE reduction, for the classes 2DCNN/utils/tf_losses.py:8-46
+    offers (Keras 2.13-2.15 `keras/losses.py` + `keras/backend.py`, restated †).  With a sigmoid/softmax head Keras 2 evaluates the
+    cross-entropies from the cached logits † (SURVEY hazard 19); pass them via `logits`."""
+    eps = 1e-7
     if kind == "bce":
         if logits is not None:
             return F.binary_cross_entropy_with_logits(logits, y_true)
-        p = y_pred.clamp(1e-7, 1 - 1e-7)
-        return -(y_true * p.log() + (1 - y_true) * (1 - p).log()).mean()
+        p = y_pred.clamp(eps, 1 - eps)                     # backend.binary_crossentropy: clip, then log(p + eps)
+        return -(y_true * (p + eps).log() + (1 - y_true) * (1 - p + eps).log()).mean()
     if kind == "cce":
         if logits is not None:
             return -(y_true * torch.log_softmax(logits, -1)).sum(-1).mean()
         p = y_pred / y_pred.sum(-1, keepdim=True)
-        return -(y_true * p.clamp(1e-7, 1).log()).sum(-1).mean()
+        return -(y_true * p.clamp(eps, 1 - eps).log()).sum(-1).mean()
     if kind == "mse":
         return ((y_pred - y_true) ** 2).mean()
     if kind == "mae":
         return (y_pred - y_true).abs().mean()
+    if kind == "msle":                                     # log(max(., eps) + 1)
+        return ((torch.log(y_pred.clamp_min(eps) + 1.0) - torch.log(y_true.clamp_min(eps) + 1.0)) ** 2).mean()
+    if kind == "huber":                                    # delta = 1 (tf_losses.py:23)
+        d = y_pred - y_true
+        return torch.where(d.abs() <= 1.0, 0.5 * d * d, d.abs() - 0.5).mean()
+    if kind == "logcosh":
+        d = y_pred - y_true
+        return (d + F.softplus(-2.0 * d) - math.log(2.0)).mean()
+    if kind == "focal":                                    # BinaryFocalCrossentropy(gamma=2, apply_class_balancing=False)
+        p_t = y_true * y_pred + (1 - y_true) * (1 - y_pred)
+        if logits is not None:
+            bce = F.binary_cross_entropy_with_logits(logits, y_true, reduction="none")
+        else:
+            p = y_pred.clamp(eps, 1 - eps)
+            bce = -(y_true * (p + eps).log() + (1 - y_true) * (1 - p + eps).log())
+        return ((1.0 - p_t) ** 2 * bce).mean()
+    if kind == "poisson":
+        return (y_pred - y_true * torch.log(y_pred + eps)).mean()
+    if kind == "kld":
+        t, p = y_true.clamp(eps, 1.0), y_pred.clamp(eps, 1.0)
+        return (t * torch.log(t / p)).sum(-1).mean()
+    if kind == "hinge":
+        return (1.0 - _maybe_convert_labels(y_true) * y_pred).clamp_min(0).mean()
+    if kind == "squared_hinge":
+        return ((1.0 - _maybe_convert_labels(y_true) * y_pred).clamp_min(0) ** 2).mean()
+    if kind == "mape":
+        return (100.0 * ((y_true - y_pred) / y_true.abs().clamp_min(eps)).abs()).mean()
+    if kind == "categorical_hinge":
+        pos = (y_true * y_pred).sum(-1)
+        neg = ((1.0 - y_true) * y_pred).max(-1).values
+        return (neg - pos + 1.0).clamp_min(0).mean()
+    if kind == "cosine":
+        def l2n(v):
+            return v * torch.rsqrt((v * v).sum(-1, keepdim=True).clamp_min(1e-12))
+        return -(l2n(y_true) * l2n(y_pred)).sum(-1).mean()
     raise ValueError(kind)
 
 

@@ -50,6 +50,8 @@ class CpuEngine:
             t = self.mem.f32(o["target_ptr"], numel).view(o["shape"]) if training else None
             self.outputs.append(dict(name=o["name"], y=y, target=t, shape=o["shape"]))
         self.loss_buf = self.mem.f32(p.loss_ptr, 1)
+        from b2seg.planner import LOSS_BUF_FLOATS
+        self.logs_buf = self.mem.f32(p.loss_ptr, LOSS_BUF_FLOATS)
         n = max(p.n_train, 64)
         self.w, self.g = self.mem.f32(p.w_ptr, n), self.mem.f32(p.g_ptr, n)          # flat arenas (views), as Engine exposes them
         self.m, self.v = self.mem.f32(p.m_ptr, n), self.mem.f32(p.v_ptr, n)

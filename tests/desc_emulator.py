@@ -337,26 +337,102 @@ def emu_outact_bwd(mem, d):
 
 
 def emu_loss(mem, d):
+    """float64 mirror of loss_kernel (csrc/stream_kernels.cu): explicit derivative formulas, no autograd"""
     n = d.n_pix * d.cout
     p, t = mem.f32(d.y_pred, n).view(d.n_pix, d.cout), mem.f32(d.y_true, n).view(d.n_pix, d.cout)
-    if d.kind == 1:
-        loss = -(t * p.clamp_min(1e-7).log()).sum(-1).mean()
-        dl = (p - t) / d.n_pix
-    elif d.kind == 0:
-        pc = p.clamp(1e-7, 1 - 1e-7)
-        loss = -(t * pc.log() + (1 - t) * (1 - pc).log()).mean()
-        dl = (p - t) / n
-    else:
-        diff = p - t
-        if d.kind == 2:
-            loss, dp = (diff ** 2).mean(), 2 * diff / n
+    eps, kind, act = 1e-7, d.kind, d.act
+    own = (kind in (0, 7) and act == L.ACT_SIGMOID) or (kind == 1 and act == L.ACT_SOFTMAX)
+    chan_sum = kind in (1, 9, 13, 14)
+    scale = 1.0 / d.n_pix if chan_sum else 1.0 / n
+    inside = (p > eps) & (p < 1 - eps)
+    pc = p.clamp(eps, 1 - eps)
+    if kind == 0:
+        if own:
+            l, g = -(t * pc.log() + (1 - t) * (1 - pc).log()), torch.zeros_like(p)
         else:
-            loss, dp = diff.abs().mean(), torch.sign(diff) / n
-        dl = dp * (p * (1 - p) if d.act == L.ACT_SIGMOID else 1.0)
+            l = -(t * (pc + eps).log() + (1 - t) * (1 - pc + eps).log())
+            g = torch.where(inside, -(t / (pc + eps) - (1 - t) / (1 - pc + eps)), torch.zeros_like(p))
+    elif kind == 1:
+        if own:
+            l, g = -t * p.clamp_min(eps).log(), torch.zeros_like(p)
+        else:
+            S = p.sum(-1, keepdim=True)
+            q = p / S
+            qin = (q > eps) & (q < 1 - eps)
+            l = -t * q.clamp(eps, 1 - eps).log()
+            g = -torch.where(qin, t / p, torch.zeros_like(p)) + (t * qin).sum(-1, keepdim=True) / S
+    elif kind == 2:
+        l, g = (p - t) ** 2, 2 * (p - t)
+    elif kind == 3:
+        l, g = (p - t).abs(), torch.sign(p - t)
+    elif kind == 4:
+        a, b = (p.clamp_min(eps) + 1).log(), (t.clamp_min(eps) + 1).log()
+        l, g = (a - b) ** 2, torch.where(p > eps, 2 * (a - b) / (p + 1), torch.zeros_like(p))
+    elif kind == 5:
+        dd = p - t
+        l = torch.where(dd.abs() <= 1, 0.5 * dd * dd, dd.abs() - 0.5)
+        g = torch.where(dd.abs() <= 1, dd, torch.sign(dd))
+    elif kind == 6:
+        dd = p - t
+        l, g = dd + torch.nn.functional.softplus(-2 * dd) - math.log(2.0), torch.tanh(dd)
+    elif kind == 7:
+        om = 1 - (t * p + (1 - t) * (1 - p))
+        if own:
+            bce = -(t * pc.log() + (1 - t) * (1 - pc).log())
+            l = om * om * bce
+            g = -2 * om * (2 * t - 1) * bce + om * om * (p - t) / (p * (1 - p)).clamp_min(1e-30)
+        else:
+            bce = -(t * (pc + eps).log() + (1 - t) * (1 - pc + eps).log())
+            dbce = torch.where(inside, -(t / (pc + eps) - (1 - t) / (1 - pc + eps)), torch.zeros_like(p))
+            l, g = om * om * bce, -2 * om * (2 * t - 1) * bce + om * om * dbce
+    elif kind == 8:
+        l, g = p - t * (p + eps).log(), 1 - t / (p + eps)
+    elif kind == 9:
+        tc, pk = t.clamp(eps, 1.0), p.clamp(eps, 1.0)
+        l, g = tc * (tc / pk).log(), torch.where((p > eps) & (p < 1), -tc / pk, torch.zeros_like(p))
+    elif kind in (10, 11):
+        y = torch.where((t == 0) | (t == 1), 2 * t - 1, t)
+        m = (1 - y * p).clamp_min(0)
+        l, g = (m, torch.where(m > 0, -y, torch.zeros_like(p))) if kind == 10 else (m * m, -2 * m * y)
+    elif kind == 12:
+        den = t.abs().clamp_min(eps)
+        dd = (t - p) / den
+        l, g = 100 * dd.abs(), -100 * torch.sign(dd) / den
+    elif kind == 13:
+        pos, (neg, j) = (t * p).sum(-1), ((1 - t) * p).max(-1)
+        margin = (neg - pos + 1).unsqueeze(-1)
+        l = torch.zeros_like(p)
+        l[:, 0] = margin[:, 0].clamp_min(0)
+        hot = torch.nn.functional.one_hot(j, d.cout).double()
+        g = torch.where(margin > 0, hot * (1 - t) - t, torch.zeros_like(p))
+    else:
+        a = torch.rsqrt((t * t).sum(-1, keepdim=True).clamp_min(1e-12))
+        b = torch.rsqrt((p * p).sum(-1, keepdim=True).clamp_min(1e-12))
+        c = (t * p).sum(-1, keepdim=True)
+        l = torch.zeros_like(p)
+        l[:, 0] = (-c * a * b)[:, 0]
+        g = -a * (t * b - torch.where(b > 9.9e5, torch.zeros_like(c), c * p * b ** 3))
+    if kind in (0, 1) and own:
+        dz = p - t
+    elif act == L.ACT_SIGMOID:
+        dz = g * p * (1 - p)
+    elif act == L.ACT_SOFTMAX:
+        dz = p * (g - (g * p).sum(-1, keepdim=True))
+    else:
+        dz = g
+    loss = l.sum() * scale
     if d.dlogits:
-        mem.f32(d.dlogits, n)[:] = (d.weight * dl).reshape(-1)
+        mem.f32(d.dlogits, n)[:] = (d.weight * dz * scale).reshape(-1)
     if d.loss:
         mem.f32(d.loss, 1)[:] += d.weight * loss
+    if d.metrics:
+        mt = mem.f32(d.metrics, 5)
+        e = p - t
+        mt[0] += loss
+        mt[1] += (e * e).sum()
+        mt[2] += e.abs().sum()
+        mt[3] += ((p > 0.5) == (t > 0.5)).double().sum()
+        mt[4] += (p.argmax(-1) == t.argmax(-1)).double().sum()
 
 
 def emu_eltwise(mem, d):

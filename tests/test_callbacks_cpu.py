@@ -147,44 +147,46 @@ def test_compile_ds_targets_target_lists():
 
 
 def test_fit_host_batching_with_ds_targets(monkeypatch):
-    """fit()'s host-side slicing with compile(ds_targets=...): only the mask travels (None marks the device-derived targets) through
+    """fit()'s host-side slicing with compile(ds_targets=...): only the mask travels (the device derives the other targets) through
     the full batches, the ragged last batch and the validation split; evaluate() rebuilds the pyramid on the host.  The device
-    side is replaced by recorders here (the real path is exercised by tests/test_gpu_zz_self_onn.py)."""
+    side is replaced by recorders here (the real path is exercised by tests/test_gpu_zz_self_onn.py and tests/test_facade_cpu.py)."""
     from b2seg.models2d import unet_model_builder
+    from b2seg.planner import LOSS_BUF_FLOATS
     m = unet_model_builder("UNet", 32, 32, 8, 2, ds=1, train_mode="from_scratch").ResNet50()
     m.compile(loss={"out": "bce", "level1": "mse", "level2": "mse"}, optimizer="adam", ds_targets="UNet")
-    seen = {"pipelined": [], "single": [], "eval": []}
+    seen = {"stream": [], "eval": []}
 
-    def fake_pipelined(batches):
-        seen["pipelined"] += batches
-        return [0.5] * len(batches)
+    def fake_stream(batches):
+        recs = []
+        for bx, by in batches:
+            seen["stream"].append((bx, by, m._targets(by)))
+            rec = np.zeros(LOSS_BUF_FLOATS)
+            rec[0] = 0.5 if bx.shape[0] == 8 else 0.25
+            recs.append((bx.shape[0], rec))
+        return recs
 
-    def fake_train_on_batch(x, y, return_loss=True):
-        seen["single"].append((x, y))
-        return 0.25
-
-    def fake_evaluate(x, y, batch_size=32, **kw):
-        seen["eval"].append((x, m._targets(y, host=True)))
+    def fake_evaluate(x, y=None, batch_size=32, **kw):
+        vx, vy = x
+        seen["eval"].append((vx, m._targets(vy, host=True)))
         return {"loss": 0.125} if kw.get("return_dict") else 0.125
-    monkeypatch.setattr(m, "_train_batches_pipelined", fake_pipelined)
-    monkeypatch.setattr(m, "train_on_batch", fake_train_on_batch)
+    monkeypatch.setattr(m, "_train_stream", fake_stream)
     monkeypatch.setattr(m, "evaluate", fake_evaluate)
     rng = np.random.default_rng(3)
     x = rng.random((25, 32, 32, 3), dtype=np.float32)
     mask = (rng.random((25, 32, 32, 1)) > 0.5).astype(np.float32)
     h = m.fit(x, mask, batch_size=8, epochs=1, shuffle=False, verbose=0, validation_split=0.2)
     # 25 samples, 20 % held out -> 20 for training: two full batches of 8 and a ragged one of 4
-    assert len(seen["pipelined"]) == 2 and len(seen["single"]) == 1
-    for bi, (bx, bys) in enumerate(seen["pipelined"]):
-        assert bx.shape == (8, 32, 32, 3) and np.array_equal(bx, x[8 * bi:8 * bi + 8])
-        assert np.array_equal(bys[0], mask[8 * bi:8 * bi + 8]) and bys[1:] == [None, None]
-    rx, ry = seen["single"][0]
-    assert rx.shape == (4, 32, 32, 3) and isinstance(ry, np.ndarray) and np.array_equal(ry, mask[16:20])
+    assert [bx.shape[0] for bx, _, _ in seen["stream"]] == [8, 8, 4]
+    for bi, (bx, by, bys) in enumerate(seen["stream"]):
+        assert np.array_equal(bx, x[:20][8 * bi:8 * bi + 8]) and np.array_equal(by, mask[:20][8 * bi:8 * bi + 8])
+        assert np.array_equal(bys[0], mask[:20][8 * bi:8 * bi + 8]) and bys[1:] == [None, None]
     (vx, vt), = seen["eval"]
     assert vx.shape == (5, 32, 32, 3) and [t.shape for t in vt] == [(5, 32, 32, 1), (5, 16, 16, 1), (5, 8, 8, 1)]
-    assert np.array_equal(vt[0], mask[20:]) and h.history["loss"] == [pytest.approx((0.5 + 0.5 + 0.25) / 3)] and h.history["val_loss"] == [0.125]
+    # Keras weights the batch losses by their sample counts
+    assert np.array_equal(vt[0], mask[20:]) and h.history["loss"] == [pytest.approx((8 * 0.5 + 8 * 0.5 + 4 * 0.25) / 20)] and h.history["val_loss"] == [0.125]
     # without ds_targets the same call is refused: three outputs need three target arrays
     m.compile(loss={"out": "bce", "level1": "mse", "level2": "mse"}, optimizer="adam")
+    monkeypatch.setattr(m, "_train_stream", lambda batches: [(bx.shape[0], m._targets(by)) for bx, by in batches])
     with pytest.raises(ValueError, match="expected 3 target arrays"):
         m.fit(x, mask, batch_size=8, epochs=1, verbose=0)
 
@@ -280,7 +282,8 @@ def test_validation_metrics_of_the_reference_configuration(monkeypatch):
     assert logs["mean_squared_error"] == pytest.approx(float(((pred.astype(np.float64) - y) ** 2).mean()))
     assert logs["binary_accuracy"] == logs["accuracy"] == pytest.approx(float(((pred > 0.5) == (y > 0.5)).mean()))
     assert isinstance(m.evaluate(x, y), float) and m.evaluate(x, y) == pytest.approx(logs["loss"])
-    monkeypatch.setattr(m, "_train_batches_pipelined", lambda batches: [0.7] * len(batches))
+    from b2seg.planner import LOSS_BUF_FLOATS
+    monkeypatch.setattr(m, "_train_stream", lambda batches: [(bx.shape[0], np.full(LOSS_BUF_FLOATS, 0.7)) for bx, _ in batches])
     from b2seg.callbacks import EarlyStopping
     es = EarlyStopping(monitor="val_mean_squared_error", patience=0)
     h = m.fit(x[:4], y[:4], batch_size=2, epochs=3, verbose=0, validation_data=(x[4:], y[4:]), callbacks=[es], shuffle=False)
@@ -291,4 +294,4 @@ def test_validation_metrics_of_the_reference_configuration(monkeypatch):
     m2.compile(loss={"out": "bce", "level1": "mse"}, optimizer="adam", metrics=["mse"], ds_targets="UNet")
     monkeypatch.setattr(m2, "predict", lambda x_, batch_size=None, **kw: [pred[:len(x_)], pred[:len(x_), ::2, ::2]])
     logs2 = m2.evaluate(x, y, return_dict=True)
-    assert set(logs2) == {"loss", "out_mean_squared_error", "level1_mean_squared_error"}
+    assert set(logs2) == {"loss", "out_loss", "level1_loss", "out_mean_squared_error", "level1_mean_squared_error"}

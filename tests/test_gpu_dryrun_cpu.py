@@ -152,37 +152,13 @@ def test_three_adam_steps_track_the_oracle(cpu_engine, case):
     assert worst < 2e-5, worst
 
 
-def _pipelined_on_cpu(model):
-    """what Model._train_batches_pipelined does, minus the CUDA streams: same slots, same order, synchronous copies"""
-    def run(batches):
-        import numpy as np
-        eng = model._engine(batches[0][0].shape[0], True)
-        losses = []
-        for bx, bys in batches:
-            eng.x_dev.copy_(torch.from_numpy(np.ascontiguousarray(bx)))
-            for o, t in zip(eng.outputs, bys):
-                if t is not None:
-                    o["target"].copy_(torch.from_numpy(np.ascontiguousarray(t, np.float32)))
-            if any(t is None for t in bys):
-                eng.derive_targets()
-            model._step(eng, return_loss=False)
-            losses.append(float(eng.loss_buf[0]))
-        return losses
-    return run
-
-
-def test_dryrun_fit_history_and_callbacks(cpu_engine, monkeypatch, tmp_path):
-    """the fit()-level GPU tests (history keys incl. the host-side validation metric, callbacks, validation_split, checkpoint files)"""
+def test_dryrun_fit_history_and_callbacks(cpu_engine, tmp_path, monkeypatch):
+    """the fit()-level GPU tests (history keys incl. training and validation metrics, callbacks, validation_split, checkpoint files)"""
     import test_gpu_model as g
-    from b2seg.model import Model
-    orig_init = Model.__init__
-
-    def init(self, graph):
-        orig_init(self, graph)
-        self._train_batches_pipelined = _pipelined_on_cpu(self)
-    monkeypatch.setattr(Model, "__init__", init)
     g.test_fit_and_history_api()
     g.test_fit_with_reference_callbacks_and_validation_split(tmp_path)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    g.test_fit_pipelined_input_matches_train_on_batch()
 
 
 def test_dryrun_every_model_test_of_the_gpu_suite(cpu_engine):

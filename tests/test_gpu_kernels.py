@@ -545,3 +545,49 @@ def test_strided_1x1_dgrad_and_bn_act_cvalid():
     L.call("b2seg_bn_act", d, stream())
     torch.cuda.synchronize()
     assert rel_l2(o.float()[..., 0], torch.sigmoid(z.float()[..., 0])) < 4e-3 and float(o.float()[..., 1:].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# every loss of utils/tf_losses.py on every head activation: value, seed dL/dlogits and the metric sums vs autograd through the oracle
+_LOSS_NAMES = ["bce", "cce", "mse", "mae", "msle", "huber", "logcosh", "focal", "poisson", "kld", "hinge", "squared_hinge", "mape",
+               "categorical_hinge", "cosine"]
+
+
+@pytest.mark.parametrize("kind", range(15), ids=_LOSS_NAMES)
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_SIGMOID, L.ACT_SOFTMAX], ids=["linear", "sigmoid", "softmax"])
+def test_loss_kinds_and_metrics(kind, act):
+    from oracle.keras_ref import keras_loss
+    name = _LOSS_NAMES[kind]
+    if (kind in (0, 7) and act == L.ACT_SOFTMAX) or (kind == 1 and act == L.ACT_SIGMOID):
+        with pytest.raises(L.B2SegError):
+            L.call("b2seg_loss", L.LossDesc(0, 0, 4, 2, kind, act, 1.0, 0, 0, 0), stream())
+        return
+    if kind == 8 and act == L.ACT_NONE:
+        pytest.skip("Poisson of negative predictions is NaN in Keras too")
+    dev, npix, co = "cuda", 3 * 37 * 5, 4
+    g = torch.Generator(device="cpu").manual_seed(100 + 3 * kind + act)
+    z = (torch.randn(npix, co, generator=g) * 1.5).double().requires_grad_(True)
+    if name in ("cce", "categorical_hinge", "kld"):
+        t = F.one_hot(torch.randint(0, co, (npix,), generator=g), co).double()
+    elif name in ("bce", "focal", "hinge", "squared_hinge"):
+        t = (torch.rand(npix, co, generator=g) > 0.6).double()
+    elif name in ("msle", "poisson", "mape"):
+        t = torch.rand(npix, co, generator=g).double() * 2 + 0.25
+    else:
+        t = torch.randn(npix, co, generator=g).double()
+    p = z if act == L.ACT_NONE else (torch.sigmoid(z) if act == L.ACT_SIGMOID else torch.softmax(z, -1))
+    own = (kind in (0, 7) and act == L.ACT_SIGMOID) or (kind == 1 and act == L.ACT_SOFTMAX)
+    want = keras_loss(name, p, t, logits=z if own else None)
+    (dz,) = torch.autograd.grad(want, z)
+    y, tt = p.detach().float().to(dev).contiguous(), t.float().to(dev).contiguous()
+    dl, loss, met = torch.zeros_like(y), torch.zeros(1, device=dev), torch.zeros(8, device=dev)
+    L.call("b2seg_loss", L.LossDesc(y.data_ptr(), tt.data_ptr(), npix, co, kind, act, 0.7, dl.data_ptr(), loss.data_ptr(), met.data_ptr()), stream())
+    torch.cuda.synchronize()
+    assert abs(float(loss) - 0.7 * float(want)) < 2e-5 * max(1.0, abs(float(want))), (float(loss), 0.7 * float(want))
+    assert abs(float(met[0]) - float(want)) < 2e-5 * max(1.0, abs(float(want)))
+    assert rel_l2(dl.cpu().double(), 0.7 * dz) < 2e-4, rel_l2(dl.cpu().double(), 0.7 * dz)
+    pe, te = p.detach(), t
+    assert abs(float(met[1]) - float(((pe - te) ** 2).sum())) < 1e-4 * float(((pe - te) ** 2).sum()) + 1e-3
+    assert abs(float(met[2]) - float((pe - te).abs().sum())) < 1e-4 * float((pe - te).abs().sum()) + 1e-3
+    assert abs(float(met[3]) - float(((y.cpu() > 0.5) == (te > 0.5)).sum())) <= 2      # (a prediction within float32 rounding of 0.5)
+    assert abs(float(met[4]) - float((y.cpu().argmax(-1) == te.argmax(-1)).sum())) <= 2

@@ -170,15 +170,16 @@ def test_unsupported_loss_head_pairs_are_refused():
     """b2seg_loss seeds the backward pass with dL/dlogits; pairs it cannot form that for must fail at plan time, not train wrongly"""
     from b2seg.planner import PlanError
     g = unet_model_builder("UNet", 16, 16, 8, 2, ds=1, train_mode="from_scratch").build_graph()       # out: sigmoid, levels: linear
-    for losses in (["cce", "mse", "mse"], ["bce", "bce", "mse"], ["mse", "cce", "mse"]):
-        with pytest.raises(PlanError, match="is not lowered"):
-            Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=losses, adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
-    Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse", "mae", "mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
-    # a tanh head is a convolution + an Activation output: MSE is fine, cross-entropy is not
+    with pytest.raises(PlanError, match="is not lowered"):      # categorical cross-entropy on the sigmoid head
+        Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["cce", "mse", "mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    # cross-entropies on the LINEAR deep-supervision heads are what Keras accepts (clipped probabilities), and so does the planner
+    for losses in (["bce", "bce", "mse"], ["mse", "cce", "mse"], ["mse", "mae", "mse"], ["msle", "huber", "logcosh"]):
+        Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=losses, adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    # a tanh head is a convolution + an Activation output, i.e. a "linear" output for the loss (the Activation has its own backward):
+    # tanh caches no logits in Keras, so even a cross-entropy is the clipped-probability form
     g = unet_model_builder("UNet", 16, 16, 8, 2, final_activation="tanh", train_mode="from_scratch").build_graph()
-    Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["mse"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
-    with pytest.raises(PlanError, match="is not lowered"):
-        Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=["bce"], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
+    for loss in ("mse", "bce"):
+        Planner(g, 2, PlanMem().alloc_bytes, training=True, losses=[loss], adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)).build()
 
 
 def test_activation_identifiers_resolve_like_keras2():

@@ -21,7 +21,7 @@ ACT_CODES = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "ReLU": ACT_R
  OP_CAST, OP_COLSUM, OP_MEMSET, OP_RESIZE_FWD, OP_RESIZE_BWD, OP_MULBC_FWD, OP_MULBC_BWD, OP_COLSTATS, OP_LSTM_FWD,
  OP_LSTM_BWD, OP_POOL_BWD, OP_ROWSUM, OP_OUTACT_FWD, OP_OUTACT_BWD, OP_TARGET_POOL) = range(1, 26)
 PHASE_FWD, PHASE_BWD, PHASE_OPT = 0, 1, 2
-ABI_VERSION = 101    # b2seg_version() of the library this binding mirrors (include/b2seg.h)
+ABI_VERSION = 102    # b2seg_version() of the library this binding mirrors (include/b2seg.h)
 
 
 class View(C.Structure):
@@ -94,7 +94,7 @@ class HeadDesc(C.Structure):
 class LossDesc(C.Structure):
     _fields_ = [("y_pred", C.c_uint64), ("y_true", C.c_uint64), ("n_pix", C.c_int64), ("cout", C.c_int32),
                 ("kind", C.c_int32), ("act", C.c_int32), ("weight", C.c_float), ("dlogits", C.c_uint64),
-                ("loss", C.c_uint64)]
+                ("loss", C.c_uint64), ("metrics", C.c_uint64)]
 
 
 class EltwiseDesc(C.Structure):

@@ -45,6 +45,8 @@ class Engine:
         self.wb = self._typed("param_wb", torch.bfloat16, n)
         self.moving = self._typed("moving", torch.float32, max(p.n_moving, 64))
         self.loss_buf = self._typed("loss", torch.float32, 1)
+        from .planner import LOSS_BUF_FLOATS
+        self.logs_buf = self._typed("loss", torch.float32, LOSS_BUF_FLOATS)   # [0] total loss, [8 + 8 i ..] per-output loss + metric sums
         H, W, Cin = graph.inputs[0].shape
         self.input_shape = (batch, H, W, Cin)
         self.x_dev = self._typed("input", torch.float32, batch * H * W * Cin).view(batch, H, W, Cin)

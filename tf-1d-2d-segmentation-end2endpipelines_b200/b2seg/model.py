@@ -16,12 +16,27 @@ import numpy as np
 
 from .graph import Graph, init_params
 
-_LOSS_ALIASES = {
-    "binary_crossentropy": "bce", "bce": "bce", "binarycrossentropy": "bce",
-    "categorical_crossentropy": "cce", "cce": "cce", "categoricalcrossentropy": "cce",
-    "mean_squared_error": "mse", "mse": "mse", "meansquarederror": "mse",
-    "mean_absolute_error": "mae", "mae": "mae", "meanabsoluteerror": "mae",
-}
+# Keras identifiers (class names of 2DCNN/utils/tf_losses.py:8-46, their `name=` strings and the usual short forms) -> canonical
+# loss names of the planner (b2seg.planner.LOSS_KINDS)
+_LOSS_ALIASES = {}
+for _canon, _names in {
+        "bce": ("binary_crossentropy", "bce", "binarycrossentropy"),
+        "cce": ("categorical_crossentropy", "cce", "categoricalcrossentropy"),
+        "mse": ("mean_squared_error", "mse", "meansquarederror"),
+        "mae": ("mean_absolute_error", "mae", "meanabsoluteerror"),
+        "msle": ("mean_squared_logarithmic_error", "msle", "meansquaredlogarithmicerror"),
+        "huber": ("huber_loss", "huber"),
+        "logcosh": ("log_cosh", "logcosh"),
+        "focal": ("binary_focal_crossentropy", "binaryfocalcrossentropy"),
+        "poisson": ("poisson",),
+        "kld": ("kl_divergence", "kld", "kldivergence", "kullback_leibler_divergence"),
+        "hinge": ("hinge",),
+        "squared_hinge": ("squared_hinge", "squaredhinge"),
+        "mape": ("mean_absolute_percentage_error", "mape", "meanabsolutepercentageerror"),
+        "categorical_hinge": ("categorical_hinge", "categoricalhinge"),
+        "cosine": ("cosine_similarity", "cosinesimilarity")}.items():
+    for _n in _names:
+        _LOSS_ALIASES[_n] = _canon
 
 
 class Adam:
@@ -62,12 +77,66 @@ def _m_cat_acc(t, p):
 _METRICS = {
     "mean_squared_error": lambda t, p: float(((p - t) ** 2).mean()), "mean_absolute_error": lambda t, p: float(np.abs(p - t).mean()),
     "binary_accuracy": _m_bin_acc, "categorical_accuracy": _m_cat_acc,
-    "accuracy": lambda t, p: _m_cat_acc(t, p) if p.shape[-1] > 1 else _m_bin_acc(t, p),    # Keras picks by the output shape
     "binary_crossentropy": lambda t, p: float(-(t * np.log(np.clip(p, 1e-7, 1 - 1e-7)) + (1 - t) * np.log(1 - np.clip(p, 1e-7, 1 - 1e-7))).mean()),
 }
 _METRIC_ALIASES = {"mse": "mean_squared_error", "mae": "mean_absolute_error", "acc": "accuracy", "meansquarederror": "mean_squared_error",
                    "meanabsoluteerror": "mean_absolute_error", "binaryaccuracy": "binary_accuracy", "categoricalaccuracy": "categorical_accuracy",
                    "binarycrossentropy": "binary_crossentropy"}
+
+
+def _accuracy_kind(loss_kind, cout):
+    """what the string 'accuracy' means for one output (keras/engine/compile_utils.py get_metric_function): binary accuracy for a
+    one-channel output or a binary cross-entropy loss, else categorical accuracy"""
+    return "binary_accuracy" if (cout == 1 or loss_kind in ("bce", "focal")) else "categorical_accuracy"
+
+
+def _metric_value(name, loss_kind, t, p):
+    if name == "accuracy":
+        name = _accuracy_kind(loss_kind, p.shape[-1])
+    return _METRICS[name](t, p)
+
+
+def _host_loss(kind, t, p):
+    """float64 NumPy value of a compiled loss on activated outputs (evaluate / validation logs; the training path uses b2seg_loss)"""
+    eps = 1e-7
+    if kind in ("bce", "focal"):
+        pc = np.clip(p, eps, 1 - eps)
+        bce = -(t * np.log(pc) + (1 - t) * np.log(1 - pc))
+        if kind == "focal":
+            bce = (1 - (t * p + (1 - t) * (1 - p))) ** 2 * bce
+        return float(bce.mean())
+    if kind == "cce":
+        return float(-(t * np.log(np.clip(p / p.sum(-1, keepdims=True), eps, 1))).sum(-1).mean())
+    if kind == "mse":
+        return float(((p - t) ** 2).mean())
+    if kind == "mae":
+        return float(np.abs(p - t).mean())
+    if kind == "msle":
+        return float(((np.log(np.maximum(p, eps) + 1) - np.log(np.maximum(t, eps) + 1)) ** 2).mean())
+    if kind == "huber":
+        d = np.abs(p - t)
+        return float(np.where(d <= 1, 0.5 * d * d, d - 0.5).mean())
+    if kind == "logcosh":
+        d = p - t
+        return float((d + np.logaddexp(0.0, -2 * d) - np.log(2.0)).mean())
+    if kind == "poisson":
+        return float((p - t * np.log(p + eps)).mean())
+    if kind == "kld":
+        tc, pk = np.clip(t, eps, 1), np.clip(p, eps, 1)
+        return float((tc * np.log(tc / pk)).sum(-1).mean())
+    if kind in ("hinge", "squared_hinge"):
+        y = 2 * t - 1 if np.isin(t, (0.0, 1.0)).all() else t
+        m = np.maximum(1 - y * p, 0)
+        return float((m if kind == "hinge" else m * m).mean())
+    if kind == "mape":
+        return float((100 * np.abs((t - p) / np.maximum(np.abs(t), eps))).mean())
+    if kind == "categorical_hinge":
+        return float(np.maximum(((1 - t) * p).max(-1) - (t * p).sum(-1) + 1, 0).mean())
+    if kind == "cosine":
+        def l2n(v):
+            return v / np.sqrt(np.maximum((v * v).sum(-1, keepdims=True), 1e-12))
+        return float(-(l2n(t) * l2n(p)).sum(-1).mean())
+    raise ValueError(kind)
 
 
 def _metric_name(obj):
@@ -76,6 +145,8 @@ def _metric_name(obj):
     key = obj if isinstance(obj, str) else (getattr(obj, "name", None) or type(obj).__name__)
     key = str(key)
     low = key.lower().replace(" ", "")
+    if low == "accuracy":
+        return "accuracy"
     name = key if key in _METRICS else _METRIC_ALIASES.get(low, low if low in _METRICS else None)
     return name
 
@@ -87,7 +158,8 @@ def _loss_name(obj) -> str:
         key = getattr(obj, "name", None) or type(obj).__name__
         key = key.lower()
     if key not in _LOSS_ALIASES:
-        raise NotImplementedError(f"loss '{obj}' is outside the hot-path scope (supported: bce, cce, mse, mae)")
+        raise NotImplementedError(f"loss '{obj}' is not lowered (supported: every loss of utils/tf_losses.py except SparseCategoricalCrossentropy: "
+                                  f"{sorted(set(_LOSS_ALIASES.values()))})")
     return _LOSS_ALIASES[key]
 
 
@@ -107,6 +179,7 @@ class Model:
         self._dist = None
         self.exchange_bucket_bytes = 64 << 20   # gradient-exchange bucket (data parallel): overlap granularity vs launch count
         self._ds_targets = None
+        self._adam_step = 0             # Adam's t: one counter per model (the moments are shared by the engines of every batch size)
 
     # ---- introspection -----------------------------------------------------------------------------------
     @property
@@ -147,6 +220,7 @@ class Model:
         return {k: v.copy() for k, v in self._weights.items()}
 
     def set_weight_dict(self, params: Dict[str, np.ndarray]):
+        self._sync_from_device()       # a partial update must not push stale host copies of the OTHER weights back to the device
         for k, v in params.items():
             if k not in self._weights:
                 raise KeyError(f"unknown weight {k}")
@@ -216,6 +290,11 @@ class Model:
         self.optimizer = optimizer
         self.metrics = metrics or []
         self._engines = {k: e for k, e in self._engines.items() if not k[1]}
+        # Keras builds a fresh optimizer on every compile (the reference recompiles the same model for every fold, Train.py:320-325):
+        # zero moments, t = 0.  The weights stay.
+        self._adam_step = 0
+        if self._primary is not None:
+            self._primary.reset_optimizer()
 
     # ---- engines -----------------------------------------------------------------------------------------
     def _engine(self, batch: int, training: bool):
@@ -337,7 +416,8 @@ class Model:
             scale = 1.0 / self.world_size
             if eng.adam_bucket_bytes == self.exchange_bucket_bytes and len(eng.planner.ops[2]) == len(works):
                 # bucket i's Adam runs as soon as ITS all-reduce has landed; the later buckets are still on the wire
-                eng.optimizer_begin(self.optimizer.learning_rate, scale)
+                self._adam_step += 1
+                eng.optimizer_begin(self.optimizer.learning_rate, scale, step=self._adam_step)
                 for i, w in enumerate(works):
                     w.wait()
                     eng.run_range(2, i, 1)
@@ -347,7 +427,8 @@ class Model:
             wait_all(works)
         else:
             eng.backward()
-        eng.optimizer_step(self.optimizer.learning_rate, scale)
+        self._adam_step += 1
+        eng.optimizer_step(self.optimizer.learning_rate, scale, step=self._adam_step)
         if return_loss:
             return float(eng.loss_buf.item())
         return None
@@ -373,77 +454,242 @@ class Model:
             outs = [o[:, 0] for o in outs]
         return outs if len(outs) > 1 else outs[0]
 
-    def evaluate(self, x, y, batch_size=32, verbose=0, **kw):
-        """mean of the compiled (weighted) loss over batches, computed on the host from predict()"""
-        ys = self._targets(y, host=True)
-        pred = self.predict(x, batch_size=batch_size)
-        pred = pred if isinstance(pred, list) else [pred]
-        total = 0.0
-        for p, t, kind, w in zip(pred, ys, self._losses, self._loss_weights):
-            t = t[:, 0] if self.graph.ndim == 1 else t
-            p = p.astype(np.float64)
-            if kind == "bce":
-                pc = np.clip(p, 1e-7, 1 - 1e-7)
-                l = -(t * np.log(pc) + (1 - t) * np.log(1 - pc)).mean()
-            elif kind == "cce":
-                l = -(t * np.log(np.clip(p, 1e-7, 1))).sum(-1).mean()
-            elif kind == "mse":
-                l = ((p - t) ** 2).mean()
-            else:
-                l = np.abs(p - t).mean()
-            total += w * float(l)
-        if kw.get("return_dict"):
-            logs = {"loss": total}
-            names = [n for n in (_metric_name(mt) for mt in (self.metrics or [])) if n is not None]
-            for out_name, p, t in zip(self.output_names, pred, ys):
-                t = t[:, 0] if self.graph.ndim == 1 else t
-                for n in names:        # Keras prefixes the output's name when the model has several outputs
-                    logs[n if len(pred) == 1 else f"{out_name}_{n}"] = _METRICS[n](np.asarray(t, np.float64), p.astype(np.float64))
-            return logs
-        return total
+    def evaluate(self, x, y=None, batch_size=32, verbose=0, steps=None, **kw):
+        """the compiled (weighted) loss and metrics over x, y — arrays, a Sequence or an iterator of (x, y) batches (2DCNN/Train.py:216,
+        281-300 passes a CustomDataGenerator or zip(generators) as validation_data).  Every batch runs predict() on the device; the
+        loss / metric values are formed on the host and averaged with the batch sizes as weights, like Keras."""
+        tot_w, acc = 0, {}
+        for bx, by in self._host_batches(x, y, batch_size or 32, steps):
+            ys = self._targets(by, host=True)
+            pred = self.predict(bx, batch_size=batch_size or 32)
+            pred = pred if isinstance(pred, list) else [pred]
+            n = pred[0].shape[0]
+            logs = {"loss": 0.0}
+            names = [nm for nm in (_metric_name(mt) for mt in (self.metrics or [])) if nm is not None]
+            for out_name, p, t, kind, w in zip(self.output_names, pred, ys, self._losses, self._loss_weights):
+                t = np.asarray(t[:, 0] if self.graph.ndim == 1 else t, np.float64)
+                p = p.astype(np.float64)
+                l = _host_loss(kind, t, p)
+                logs["loss"] += w * l
+                if len(pred) > 1:
+                    logs[f"{out_name}_loss"] = l
+                for nm in names:        # Keras prefixes the output's name when the model has several outputs
+                    logs[nm if len(pred) == 1 else f"{out_name}_{nm}"] = _metric_value(nm, kind, t, p)
+            for k_, v_ in logs.items():
+                acc[k_] = acc.get(k_, 0.0) + n * v_
+            tot_w += n
+        if not tot_w:
+            raise ValueError("evaluate: no data")
+        logs = {k_: v_ / tot_w for k_, v_ in acc.items()}
+        return logs if kw.get("return_dict") else logs["loss"]
 
-    def _train_batches_pipelined(self, batches):
-        """Train on a list of equally sized (x, [targets]) host batches with the input pipeline overlapped: batch i+1 is copied
-        host -> device on a copy stream (into one of two staging slots) while step i computes, and every step's loss is read back
-        asynchronously into pinned memory and collected at the end — what Keras' fit() does with its prefetching data adapter
-        (2DCNN/Train.py:394-415).  Pinned source arrays make the copies truly asynchronous; pageable ones still work."""
+    # ---- input handling: arrays, keras.utils.Sequence-like objects, iterators / generators / zip(generators) ------------------
+    @staticmethod
+    def _is_sequence(x):
+        return hasattr(x, "__getitem__") and hasattr(x, "__len__") and not isinstance(x, (np.ndarray, list, tuple, dict))
+
+    @staticmethod
+    def _is_iterator(x):
+        return hasattr(x, "__next__") or (hasattr(x, "__iter__") and not isinstance(x, (np.ndarray, list, tuple, dict)) and not hasattr(x, "__getitem__"))
+
+    @staticmethod
+    def _split_item(item):
+        """(x, y) of one generator / Sequence item; sample weights (a third element) are not supported"""
+        if not isinstance(item, (tuple, list)) or len(item) < 2:
+            raise ValueError("a data generator must yield (inputs, targets) tuples")
+        if len(item) > 2 and item[2] is not None:
+            raise NotImplementedError("per-sample weights from a generator are outside the hot-path scope")
+        return item[0], item[1]
+
+    def _host_batches(self, x, y, batch_size, steps=None, order=None):
+        """(x batch, y batch) pairs of one pass over the data, whatever its form"""
+        if isinstance(x, (tuple, list)) and y is None and len(x) in (2, 3) and not self._is_sequence(x):
+            x, y = self._split_item(tuple(x))          # validation_data=(x, y[, sample_weight])
+        if y is None and self._is_sequence(x):
+            n = len(x) if steps is None else min(len(x), int(steps))
+            for i in range(n):
+                yield self._split_item(x[i])
+            return
+        if y is None and self._is_iterator(x):
+            it = iter(x)
+            i = 0
+            while steps is None or i < int(steps):
+                try:
+                    item = next(it)
+                except StopIteration:
+                    return
+                yield self._split_item(item)
+                i += 1
+            return
+        xs = np.asarray(x)
+        n = xs.shape[0]
+        starts = list(range(0, n, batch_size))
+        if steps is not None:
+            starts = starts[:int(steps)]
+
+        def take(a, s_):
+            if isinstance(a, dict):
+                return {k_: take(v_, s_) for k_, v_ in a.items()}
+            if isinstance(a, (list, tuple)):
+                return [take(v_, s_) for v_ in a]
+            return a[s_:s_ + batch_size] if order is None else a[order[s_:s_ + batch_size]]      # contiguous slices keep pinned memory pinned
+        for s_ in starts:
+            yield take(xs, s_), take(y, s_)
+
+    def _train_stream(self, batches):
+        """Train on a stream of (x, y) host batches with the input pipeline overlapped, the way Keras' fit() drives its data adapter
+        (2DCNN/Train.py:281,394-415): a producer thread pulls the next batch from the caller's arrays / Sequence / generator, stages it
+        host -> device on a copy stream (two slots per batch shape; pinned sources copy asynchronously, pageable ones block only
+        the producer) while the main thread keeps the device busy with the previous step.  No host synchronisation per batch: every
+        step's 1 KB log record (loss, per-output losses, metric sums) is copied back asynchronously and read once at the end.
+        Returns [(n_samples, log record)]."""
+        import queue
+        import threading
         import torch
-        B = batches[0][0].shape[0]
-        eng = self._engine(B, True)
-        cur = torch.cuda.current_stream(eng.dev)
-        if not hasattr(eng, "_stage"):
-            eng._copy_stream = torch.cuda.Stream(device=eng.dev)
-            eng._stage = [dict(x=torch.empty_like(eng.x_dev), t=[torch.empty_like(o["target"]) for o in eng.outputs],
-                               ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
-        derive = any(t is None for t in batches[0][1])    # compile(ds_targets=...): only the mask is staged
-        loss_host = torch.empty(len(batches), dtype=torch.float32).pin_memory()
-        for i, (bx, bys) in enumerate(batches):
-            st = eng._stage[i % 2]
-            with torch.cuda.stream(eng._copy_stream):
-                eng._copy_stream.wait_event(st["free"])          # the step that used this slot has copied it out
-                st["x"].copy_(torch.from_numpy(bx), non_blocking=True)
-                for dst, t in zip(st["t"], bys):
-                    if t is None:
-                        continue
-                    if tuple(t.shape) != tuple(dst.shape):
-                        raise ValueError(f"target shape {t.shape} != {tuple(dst.shape)}")
-                    dst.copy_(torch.from_numpy(np.ascontiguousarray(t, np.float32)), non_blocking=True)
-                st["ready"].record(eng._copy_stream)
+        from .planner import LOSS_BUF_FLOATS
+        state = {"slots": {}, "err": None}
+        ready_q: "queue.Queue" = queue.Queue(maxsize=2)
+        out_shapes = [tuple(n.shape) for n in self.graph.outputs]
+        dev = None
+        # the first batch decides the device path: engines are built lazily per batch size on the main thread
+        it = iter(batches)
+
+        def normalise(bx, by):
+            xs = self._to_nhwc(bx)
+            ys = self._targets(by)
+            ys = [None if t is None else np.ascontiguousarray(t, np.float32) for t in ys]
+            for t, shp in zip(ys, out_shapes):
+                if t is not None and tuple(t.shape[1:]) != shp:
+                    raise ValueError(f"target shape {t.shape} does not match the output shape (None,) + {shp}")
+            return xs, ys
+
+        try:
+            bx, by = next(it)
+        except StopIteration:
+            return []
+        xs0, ys0 = normalise(bx, by)
+        eng0 = self._engine(xs0.shape[0], True)
+        on_gpu = eng0.dev.type == "cuda"
+        records = []
+        if not on_gpu:
+            # (emulator engine of the CPU test-suite: same order of operations, synchronous copies)
+            def run_sync(xs, ys):
+                eng = self._engine(xs.shape[0], True)
+                eng.x_dev.copy_(torch.from_numpy(xs))
+                for o, t in zip(eng.outputs, ys):
+                    if t is not None:
+                        o["target"].copy_(torch.from_numpy(t))
+                if any(t is None for t in ys):
+                    eng.derive_targets()
+                self._step(eng, return_loss=False)
+                records.append((xs.shape[0], eng.logs_buf.clone().double().numpy()))
+            run_sync(xs0, ys0)
+            for bx, by in it:
+                run_sync(*normalise(bx, by))
+            return records
+
+        dev = eng0.dev
+        cur = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def slots_for(B):
+            if B not in state["slots"]:
+                H, W, Cin = self.graph.inputs[0].shape
+                sl = [dict(x=torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev),
+                           t=[torch.empty((B,) + shp, dtype=torch.float32, device=dev) for shp in out_shapes],
+                           ready=torch.cuda.Event(), free=torch.cuda.Event(), B=B, idx=i) for i in range(2)]
+                fq: "queue.Queue" = queue.Queue()
+                for sl_ in sl:
+                    fq.put(sl_)
+                state["slots"][B] = fq
+            return state["slots"][B]
+
+        def stage(xs, ys):
+            st = slots_for(xs.shape[0]).get()             # blocks until the main thread has released a slot of this shape
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(st["free"])
+                st["x"].copy_(torch.from_numpy(xs), non_blocking=True)
+                for dst, t in zip(st["t"], ys):
+                    if t is not None:
+                        dst.copy_(torch.from_numpy(t), non_blocking=True)
+                st["ready"].record(copy_stream)
+            st["src"] = (xs, ys)                            # keep the host arrays alive until the copy has been consumed
+            return st
+
+        def producer():
+            try:
+                torch.cuda.set_device(dev)
+                ready_q.put(stage(xs0, ys0))
+                for bx_, by_ in it:
+                    ready_q.put(stage(*normalise(bx_, by_)))
+            except BaseException as e:      # noqa: BLE001 - re-raised on the main thread
+                state["err"] = e
+            ready_q.put(None)
+
+        th = threading.Thread(target=producer, daemon=True)
+        th.start()
+        ring = 256
+        log_host = torch.empty((ring, LOSS_BUF_FLOATS), dtype=torch.float32).pin_memory()
+        pending = []
+        i = 0
+        while True:
+            st = ready_q.get()
+            if st is None:
+                break
+            eng = self._engine(st["B"], True)
             cur.wait_event(st["ready"])
             eng.x_dev.copy_(st["x"], non_blocking=True)
-            for o, t, src in zip(eng.outputs, st["t"], bys):
+            derive = False
+            for o, t, src in zip(eng.outputs, st["t"], st["src"][1]):
                 if src is not None:
                     o["target"].copy_(t, non_blocking=True)
+                else:
+                    derive = True
             if derive:
                 eng.derive_targets()
             st["free"].record(cur)
+            state["slots"][st["B"]].put(st)
             self._step(eng, return_loss=False)
-            loss_host[i].copy_(eng.loss_buf[0], non_blocking=True)
+            if i and i % ring == 0:         # the ring of pinned log records is about to wrap: collect what is in flight
+                cur.synchronize()
+                records += [(n_, log_host[j % ring].double().numpy().copy()) for (j, n_) in pending]
+                pending = []
+            log_host[i % ring].copy_(eng.logs_buf, non_blocking=True)
+            pending.append((i, st["B"]))
+            i += 1
+        th.join()
         cur.synchronize()
-        return [float(v) for v in loss_host.tolist()]
+        if state["err"] is not None:
+            raise state["err"]
+        records += [(n_, log_host[j % ring].double().numpy().copy()) for (j, n_) in pending]
+        return records
+
+    def _train_logs(self, records):
+        """Keras' epoch logs from the per-step device records: sample-weighted means of the total loss, the per-output losses (models
+        with several outputs) and the compiled metrics, under Keras' key names"""
+        tot = float(sum(n for n, _ in records))
+        logs = {"loss": sum(n * float(r[0]) for n, r in records) / tot}
+        names = [nm for nm in (_metric_name(mt) for mt in (self.metrics or [])) if nm is not None]
+        multi = len(self.output_names) > 1
+        for oi, (out_name, node, kind) in enumerate(zip(self.output_names, self.graph.outputs, self._losses)):
+            H, W, C = node.shape
+            base = 8 + 8 * oi
+            if multi:
+                logs[f"{out_name}_loss"] = sum(n * float(r[base]) for n, r in records) / tot
+            for nm in names:
+                which = _accuracy_kind(kind, C) if nm == "accuracy" else nm
+                col, per = {"mean_squared_error": (1, H * W * C), "mean_absolute_error": (2, H * W * C), "binary_accuracy": (3, H * W * C),
+                            "categorical_accuracy": (4, H * W)}.get(which, (None, None))
+                if col is None:
+                    continue        # (a metric the training pass does not accumulate: reported for validation only)
+                logs[nm if not multi else f"{out_name}_{nm}"] = sum(float(r[base + col]) for n, r in records) / (tot * per)
+        return logs
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, callbacks=None, validation_data=None, shuffle=True,
-            initial_epoch=0, steps_per_epoch=None, **kw):
+            initial_epoch=0, steps_per_epoch=None, validation_steps=None, validation_batch_size=None, **kw):
+        """tf.keras.Model.fit for the call forms of the reference (2DCNN/Train.py:281-300, 394-415; 1D notebook cells 36-40): NumPy
+        arrays with dict / list targets, a keras.utils.Sequence (CustomDataGenerator), or a generator / zip(generators) with
+        steps_per_epoch; validation_data as a tuple, a Sequence or a generator (+ validation_steps); validation_split on arrays."""
         hist = History()
         callbacks = list(callbacks or [])
         for cb in callbacks:
@@ -451,56 +697,57 @@ class Model:
                 cb.set_model(self)
             if hasattr(cb, "on_train_begin"):
                 cb.on_train_begin({})
-        sequence = x if (y is None and hasattr(x, "__getitem__") and hasattr(x, "__len__") and not isinstance(x, np.ndarray)) else None
-        if sequence is None:
-            xs = np.asarray(x, np.float32)
-            ys = self._targets(y)
-            bs = int(batch_size or 32)
-            split = float(kw.get("validation_split") or 0.0)
+        arrays = not (y is None and (self._is_sequence(x) or self._is_iterator(x)))
+        split = float(kw.get("validation_split") or 0.0)
+        if split and not arrays:
+            raise ValueError("`validation_split` is only supported for Tensors or NumPy arrays, found following types in the input: "
+                             f"{type(x)}")
+        if not arrays and self._is_iterator(x) and not self._is_sequence(x) and steps_per_epoch is None and epochs - initial_epoch > 1:
+            raise ValueError("When passing a generator that is consumed once, specify `steps_per_epoch` (the same generator is iterated "
+                             "across epochs, as Keras does)")
+        bs = int(batch_size or 32)
+        if arrays:
+            xs = np.asarray(x) if not isinstance(x, np.ndarray) else x
+            ys = y
             if split and validation_data is None:
                 # Keras holds out the LAST fraction of the samples, before any shuffling (Train.py:411-415)
                 if not 0.0 < split < 1.0:
                     raise ValueError(f"`validation_split` must be between 0 and 1, received: {split}")
                 cut = int(xs.shape[0] * (1.0 - split))
-                held = [t for t in ys if t is not None]          # (ds_targets: the mask alone; evaluate() derives the rest)
-                validation_data = (xs[cut:], [t[cut:][:, 0] if self.graph.ndim == 1 else t[cut:] for t in held])
-                if len(held) == 1:
-                    validation_data = (validation_data[0], validation_data[1][0])
-                xs, ys = xs[:cut], [None if t is None else t[:cut] for t in ys]
+
+                def part(a, lo, hi):
+                    if isinstance(a, dict):
+                        return {k_: v_[lo:hi] for k_, v_ in a.items()}
+                    if isinstance(a, (list, tuple)):
+                        return [v_[lo:hi] for v_ in a]
+                    return a[lo:hi]
+                validation_data = (xs[cut:], part(ys, cut, None))
+                xs, ys = xs[:cut], part(ys, 0, cut)
             n = xs.shape[0]
         rng = np.random.default_rng(0)
         self.stop_training = False
+        gen_iter = iter(x) if (not arrays and not self._is_sequence(x)) else None
         for ep in range(initial_epoch, epochs):
             t0 = time.time()
-            losses = []
-            if sequence is not None:
-                for bi in range(len(sequence)):
-                    bx, by = sequence[bi][:2]
-                    losses.append(self.train_on_batch(bx, by))
-                if hasattr(sequence, "on_epoch_end"):
-                    sequence.on_epoch_end()
-            else:
+            if arrays:
                 order = rng.permutation(n) if shuffle else None
-                starts = list(range(0, n, bs))
-                if steps_per_epoch:
-                    starts = starts[:int(steps_per_epoch)]
-                full = [s for s in starts if s + bs <= n]
-                xn = self._to_nhwc(xs)
-
-                def take(a, s):   # contiguous slice (keeps pinned memory pinned) unless shuffled
-                    if a is None:
-                        return None
-                    return a[s:s + bs] if order is None else a[order[s:s + bs]]
-                if full:
-                    losses += self._train_batches_pipelined([(take(xn, s), [take(t, s) for t in ys]) for s in full])
-                for s in starts[len(full):]:    # ragged last batch: its own engine
-                    by = [take(t, s)[:, 0] if self.graph.ndim == 1 else take(t, s) for t in ys if t is not None]
-                    losses.append(self.train_on_batch(take(xs, s), by if len(by) > 1 else by[0]))
-            logs = {"loss": float(np.mean(losses))}
+                stream = self._host_batches(xs, ys, bs, steps_per_epoch, order)
+            elif gen_iter is not None:
+                stream = self._host_batches(gen_iter, None, bs, steps_per_epoch)
+            else:
+                stream = self._host_batches(x, None, bs, steps_per_epoch)
+            records = self._train_stream(stream)
+            if not records:
+                raise ValueError("fit: the data source produced no batches")
+            if not arrays and hasattr(x, "on_epoch_end"):
+                x.on_epoch_end()
+            logs = self._train_logs(records)
             if validation_data is not None:
-                vx, vy = validation_data[:2]
-                for k_, v_ in self.evaluate(vx, vy, batch_size=batch_size or 32, return_dict=True).items():
+                for k_, v_ in self.evaluate(validation_data, None, batch_size=validation_batch_size or batch_size or 32,
+                                            steps=validation_steps, return_dict=True).items():
                     logs[f"val_{k_}"] = v_
+                if hasattr(validation_data, "on_epoch_end"):
+                    validation_data.on_epoch_end()
             if verbose:
                 print(f"Epoch {ep + 1}/{epochs} - {time.time() - t0:.1f}s - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
             for cb in callbacks:

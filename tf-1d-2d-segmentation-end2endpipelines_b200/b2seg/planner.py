@@ -146,8 +146,12 @@ class PlanError(NotImplementedError):
     pass
 
 
+# canonical loss names (b2seg.model._LOSS_ALIASES maps the Keras identifiers onto them) -> b2seg_loss_desc.kind
 LOSS_KINDS = {"bce": 0, "binary_crossentropy": 0, "cce": 1, "categorical_crossentropy": 1, "mse": 2, "mean_squared_error": 2,
-              "mae": 3, "mean_absolute_error": 3}
+              "mae": 3, "mean_absolute_error": 3, "msle": 4, "huber": 5, "logcosh": 6, "focal": 7, "poisson": 8, "kld": 9, "hinge": 10,
+              "squared_hinge": 11, "mape": 12, "categorical_hinge": 13, "cosine": 14}
+LOSS_BUF_FLOATS = 256          # [0] total weighted loss; [8 + 8 i ..] per-output {loss, sum sq err, sum abs err, binary hits, arg-max hits}
+MAX_OUTPUTS = (LOSS_BUF_FLOATS - 8) // 8
 
 
 class Planner:
@@ -522,12 +526,14 @@ class Planner:
     # ---------------------------------------------------------------------------------------- build
     def build(self):
         self.bind_arenas()
-        self.loss_ptr = self.alloc(256, "loss")
+        self.loss_ptr = self.alloc(LOSS_BUF_FLOATS * 4, "loss")
+        if len(self.g.outputs) > MAX_OUTPUTS:
+            raise PlanError(f"{len(self.g.outputs)} model outputs (max {MAX_OUTPUTS})")
         for u in self.units:
             getattr(self, "_fwd_" + u["kind"])(u)
         if self.training:
             self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.g_ptr, max(self.n_train, 64) * 4), "zero grads")
-            self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.loss_ptr, 256), "zero loss")
+            self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.loss_ptr, LOSS_BUF_FLOATS * 4), "zero loss")
             for u in reversed(self.units):
                 self._grad_touched = set()
                 getattr(self, "_bwd_" + u["kind"])(u)
@@ -971,23 +977,29 @@ class Planner:
                                  dlogits=dl, npix=npix, cout=co))
 
     def _loss_kind(self, o) -> int:
-        """loss code of output o; b2seg_loss seeds the backward pass with dL/dlogits, which it can form for these pairs only"""
+        """loss code of output o (b2seg_loss_desc.kind).  Every loss of 2DCNN/utils/tf_losses.py except the sparse one is lowered, on
+        linear / sigmoid / softmax heads alike (cross-entropies on their own activation from the cached logits like Keras 2, else
+        from clipped probabilities).  Refused: a cross-entropy on the OTHER activation — binary (focal) cross-entropy on a softmax
+        head, categorical on a sigmoid head: Keras 2 finds the cached `_keras_logits` of whichever activation ran and feeds them to
+        the wrong *_cross_entropy_with_logits, a quirk nobody means — and SparseCategoricalCrossentropy (integer targets)."""
         name = self.losses[o["index"]] if self.losses else "bce"
         kind, act = LOSS_KINDS[name], o["act"]
-        ok = (kind == 0 and act == L.ACT_SIGMOID) or (kind == 1 and act == L.ACT_SOFTMAX) or (kind >= 2 and act in (L.ACT_NONE, L.ACT_SIGMOID))
-        if not ok:
-            raise PlanError(f"output {o['name']}: loss '{name}' on a head with activation code {act} is not lowered (binary cross-entropy "
-                            f"needs a sigmoid head, categorical cross-entropy a softmax head, MSE / MAE a linear or sigmoid head)")
+        if act not in (L.ACT_NONE, L.ACT_SIGMOID, L.ACT_SOFTMAX) or (kind in (0, 7) and act == L.ACT_SOFTMAX) or (kind == 1 and act == L.ACT_SIGMOID):
+            raise PlanError(f"output {o['name']}: loss '{name}' on a head with activation code {act} is not lowered (a cross-entropy needs "
+                            f"its own activation or a linear head)")
         return kind
+
+    def _emit_loss(self, o, note):
+        idx = o["index"]
+        kind = self._loss_kind(o)
+        wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
+        self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr,
+                                           self.loss_ptr + 4 * (8 + 8 * idx)), note)
 
     def _bwd_outact(self, u):
         n, src = u["node"], u["src"]
         o = next(o for o in self.outputs if o["name"] == n.name)
-        idx = o["index"]
-        kind = self._loss_kind(o)
-        wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
-        self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr),
-                  f"loss {n.name}")
+        self._emit_loss(o, f"loss {n.name}")
         dx = self._grad_like(src)
         d = L.OutActDesc.from_buffer_copy(u["desc"])
         d.dx = dx.to_c()
@@ -1026,11 +1038,7 @@ class Planner:
     def _bwd_head(self, u):
         n = u["node"]
         o = next(o for o in self.outputs if o["name"] == n.name)
-        idx = o["index"]
-        kind = self._loss_kind(o)
-        wgt = float(self.loss_weights[idx]) if self.loss_weights else 1.0
-        self.emit(1, L.OP_LOSS, L.LossDesc(o["ptr"], o["target_ptr"], o["npix"], o["cout"], kind, o["act"], wgt, o["dlogits"], self.loss_ptr),
-                  f"loss {n.name}")
+        self._emit_loss(o, f"loss {n.name}")
         t = n.inputs[0]
         pu = self.unit_of_out.get(id(t))
         x = self.phys[id(t)]
@@ -1245,6 +1253,8 @@ class Planner:
         nv = lw.NULL_VIEW.to_c()
         self.emit(1, L.OP_LSTM_BWD, L.LstmDesc(u["z"].to_c(), nv, dh.to_c(), dz.to_c(), F), f"gates bwd {n.name}")
         self.grad_taps[f"{n.name}/gates"] = (dz, 3 * F)
+        if (dh.C, dh.sw) == (F, F):
+            self.grad_taps[n.name] = (dh, F)          # gradient w.r.t. the ConvLSTM output h (when it is one dense tensor)
         flops = 2.0 * self.N * H * W * x.C * 3 * F * kh * kw
         self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, x.view, self.pg(pe.key), 3 * F, kh, kw, x.Cp), f"wgrad {n.name}", flops=flops)
         self.emit(1, L.OP_COLSUM, L.ColsumDesc(dz.to_c(), self.pg(f"{n.name}/bias"), 0, 0), f"bias grad {n.name}")

@@ -164,7 +164,7 @@ struct b2seg_plan {
 extern "C" {
 
 const char* b2seg_last_error(void) { return b2::g_err; }
-int b2seg_version(void) { return 101; }   // 101: eltwise ops 4/5, B2SEG_ACT_TANH, b2seg_outact_fwd/bwd, b2seg_target_pool (additive)
+int b2seg_version(void) { return 102; }   // 102: b2seg_loss kinds 4..14 + metrics; 101: eltwise ops 4/5, B2SEG_ACT_TANH, b2seg_outact_fwd/bwd, b2seg_target_pool (additive)
 
 // sizeof of each op descriptor: lets a binding verify its struct mirrors without touching the GPU
 int b2seg_sizeof_desc(int op) {

@@ -920,49 +920,162 @@ PreparedOp* prepare_head_bwd(const b2seg_head_desc* d) {
 }
 
 // ------------------------------------------------------------------------------------------ loss seed
+// One thread per pixel, a loop over the (few) output channels.  Every loss is written as  L = scale * sum_pix sum_o l(p, t)  with
+// g = dl/dp the derivative with respect to the ACTIVATED output p; the seed dL/dlogits follows from the head's activation
+// (none: g; sigmoid: g p (1 - p); softmax: p_j (g_j - sum_k g_k p_k)), except for the cross-entropies on their own activation,
+// which Keras evaluates from the cached logits: seed (p - t).  Losses that reduce over the channel axis first (categorical
+// hinge, cosine similarity, cross-entropy on un-normalised outputs) get their per-pixel reductions in `LossPix`.
+struct LossPix { float a, b, c; int j; };
+
+__device__ __forceinline__ float keras_label(float t) { return (t == 0.f || t == 1.f) ? 2.f * t - 1.f : t; }   // losses.py _maybe_convert_labels
+
+// per-element loss and derivative; `prob` = cross-entropy on probabilities (the head is not the matching activation)
+__device__ __forceinline__ void loss_elem(int kind, bool prob, float p, float t, const LossPix& px, int o, float* l, float* g) {
+  const float eps = 1e-7f;
+  switch (kind) {
+    case 0: {   // binary cross-entropy
+      if (!prob) {   // from the logits of the sigmoid head: only the value is needed here (seed = p - t)
+        const float pc = fminf(fmaxf(p, eps), 1.f - eps);
+        *l = -(t * logf(pc) + (1.f - t) * logf(1.f - pc)); *g = 0.f;
+      } else {       // backend.binary_crossentropy on probabilities: clip, log(p + eps)
+        const float pc = fminf(fmaxf(p, eps), 1.f - eps);
+        *l = -(t * logf(pc + eps) + (1.f - t) * logf(1.f - pc + eps));
+        *g = (p > eps && p < 1.f - eps) ? -(t / (pc + eps) - (1.f - t) / (1.f - pc + eps)) : 0.f;
+      }
+      break;
+    }
+    case 1: {   // categorical cross-entropy
+      if (!prob) { *l = -t * logf(fmaxf(p, eps)); *g = 0.f; }
+      else {      // output / sum(output), clipped: px.a = sum p
+        const float q = p / px.a, qc = fminf(fmaxf(q, eps), 1.f - eps);
+        *l = -t * logf(qc);
+        *g = -((q > eps && q < 1.f - eps) ? t / p : 0.f) + px.c / px.a;     // px.c = sum of t over the unclipped channels
+      }
+      break;
+    }
+    case 2: { const float d = p - t; *l = d * d; *g = 2.f * d; break; }
+    case 3: { const float d = p - t; *l = fabsf(d); *g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); break; }
+    case 4: {   // mean squared logarithmic error
+      const float a = logf(fmaxf(p, eps) + 1.f), b = logf(fmaxf(t, eps) + 1.f);
+      *l = (a - b) * (a - b); *g = p > eps ? 2.f * (a - b) / (p + 1.f) : 0.f; break;
+    }
+    case 5: {   // Huber, delta = 1
+      const float d = p - t, ad = fabsf(d);
+      if (ad <= 1.f) { *l = 0.5f * d * d; *g = d; } else { *l = ad - 0.5f; *g = d > 0.f ? 1.f : -1.f; }
+      break;
+    }
+    case 6: {   // log-cosh: x + softplus(-2x) - log 2
+      const float d = p - t, m2 = -2.f * d;
+      const float sp = m2 > 15.f ? m2 : log1pf(__expf(m2));
+      *l = d + sp - 0.69314718056f; *g = tanhf(d); break;
+    }
+    case 7: {   // binary focal cross-entropy, gamma = 2: (1 - p_t)^2 * bce
+      const float pt = t * p + (1.f - t) * (1.f - p), om = 1.f - pt;
+      const float pc = fminf(fmaxf(p, eps), 1.f - eps);
+      if (!prob) {
+        const float bce = -(t * logf(pc) + (1.f - t) * logf(1.f - pc));
+        *l = om * om * bce;
+        // caller multiplies g by p (1 - p) (sigmoid head): d/dz = -2 om (2t - 1) p(1-p) bce + om^2 (p - t)
+        *g = -2.f * om * (2.f * t - 1.f) * bce + om * om * (p - t) / fmaxf(p * (1.f - p), 1e-30f);
+      } else {
+        const float bce = -(t * logf(pc + eps) + (1.f - t) * logf(1.f - pc + eps));
+        const float dbce = (p > eps && p < 1.f - eps) ? -(t / (pc + eps) - (1.f - t) / (1.f - pc + eps)) : 0.f;
+        *l = om * om * bce;
+        *g = -2.f * om * (2.f * t - 1.f) * bce + om * om * dbce;
+      }
+      break;
+    }
+    case 8: { *l = p - t * logf(p + eps); *g = 1.f - t / (p + eps); break; }              // Poisson
+    case 9: {   // Kullback-Leibler divergence (sum over channels)
+      const float tc = fminf(fmaxf(t, eps), 1.f), pc = fminf(fmaxf(p, eps), 1.f);
+      *l = tc * logf(tc / pc); *g = (p > eps && p < 1.f) ? -tc / pc : 0.f; break;
+    }
+    case 10: { const float y = keras_label(t), m = 1.f - y * p; *l = fmaxf(m, 0.f); *g = m > 0.f ? -y : 0.f; break; }                 // hinge
+    case 11: { const float y = keras_label(t), m = fmaxf(1.f - y * p, 0.f); *l = m * m; *g = -2.f * m * y; break; }                    // squared hinge
+    case 12: {  // mean absolute percentage error
+      const float den = fmaxf(fabsf(t), eps), d = (t - p) / den;
+      *l = 100.f * fabsf(d); *g = 100.f * (d > 0.f ? -1.f : (d < 0.f ? 1.f : 0.f)) / den; break;
+    }
+    case 13: {  // categorical hinge: max(neg - pos + 1, 0), pos = sum t p, neg = max (1 - t) p   (px.a = margin, px.j = arg max)
+      *l = o == 0 ? fmaxf(px.a, 0.f) : 0.f;
+      *g = px.a > 0.f ? ((o == px.j ? 1.f - t : 0.f) - t) : 0.f; break;
+    }
+    default: {  // 14: cosine similarity: -sum(l2norm(t) l2norm(p)); px.a = rsqrt(max(sum t^2, 1e-12)), px.b = rsqrt(max(sum p^2, 1e-12)), px.c = sum t p
+      *l = o == 0 ? -px.c * px.a * px.b : 0.f;
+      *g = -px.a * (t * px.b - (px.b > 9.9e5f ? 0.f : px.c * p * px.b * px.b * px.b)); break;
+    }
+  }
+}
+
 __global__ void loss_kernel(b2seg_loss_desc d) {
   pdl_prologue();
   const float* yp = reinterpret_cast<const float*>(d.y_pred);
   const float* yt = reinterpret_cast<const float*>(d.y_true);
   float* dl = reinterpret_cast<float*>(d.dlogits);
-  const int co = d.cout;
-  const float inv_elems = 1.f / ((float)d.n_pix * (float)co);
-  const float inv_pix = 1.f / (float)d.n_pix;
-  float local = 0.f;
+  const int co = d.cout, kind = d.kind, act = d.act;
+  const bool chan_sum = kind == 1 || kind == 9 || kind == 13 || kind == 14;       // reduce_sum / one value per pixel, then mean over pixels
+  const float scale = chan_sum ? 1.f / (float)d.n_pix : 1.f / ((float)d.n_pix * (float)co);
+  const bool own_act = (kind == 0 && act == B2SEG_ACT_SIGMOID) || (kind == 1 && act == B2SEG_ACT_SOFTMAX) || (kind == 7 && act == B2SEG_ACT_SIGMOID);
+  const bool prob = !own_act;
+  float local = 0.f, m_sse = 0.f, m_sae = 0.f, m_bin = 0.f, m_cat = 0.f;
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < d.n_pix; pix += (long long)gridDim.x * blockDim.x) {
-    if (d.kind == 1) {  // categorical CE on softmax probabilities
-      for (int o = 0; o < co; ++o) {
-        const float p = yp[pix * co + o], t = yt[pix * co + o];
-        local -= t * logf(fmaxf(p, 1e-7f)) * inv_pix;
-        if (dl) dl[pix * co + o] = d.weight * (p - t) * inv_pix;
-      }
-    } else {
-      for (int o = 0; o < co; ++o) {
-        const float p = yp[pix * co + o], t = yt[pix * co + o];
-        float dldz;
-        if (d.kind == 0) {  // binary CE, evaluated like Keras from the logits of the sigmoid head
-          const float pc = fminf(fmaxf(p, 1e-7f), 1.f - 1e-7f);
-          local -= (t * logf(pc) + (1.f - t) * logf(1.f - pc)) * inv_elems;
-          dldz = (p - t) * inv_elems;
-        } else {
-          const float diff = p - t;
-          float dldp;
-          if (d.kind == 2) { local += diff * diff * inv_elems; dldp = 2.f * diff * inv_elems; }
-          else { local += fabsf(diff) * inv_elems; dldp = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * inv_elems; }
-          dldz = dldp * (d.act == B2SEG_ACT_SIGMOID ? p * (1.f - p) : 1.f);
-        }
-        if (dl) dl[pix * co + o] = d.weight * dldz;
-      }
+    const float* pp = yp + pix * co;
+    const float* tt = yt + pix * co;
+    LossPix px = {0.f, 0.f, 0.f, 0};
+    if (kind == 1 && prob) {
+      for (int o = 0; o < co; ++o) px.a += pp[o];
+      for (int o = 0; o < co; ++o) { const float q = pp[o] / px.a; if (q > 1e-7f && q < 1.f - 1e-7f) px.c += tt[o]; }   // channels the clip leaves alone
+    } else if (kind == 13) {
+      float pos = 0.f, neg = -3.0e38f;
+      for (int o = 0; o < co; ++o) { pos += tt[o] * pp[o]; const float v = (1.f - tt[o]) * pp[o]; if (v > neg) { neg = v; px.j = o; } }
+      px.a = neg - pos + 1.f;
+    } else if (kind == 14) {
+      float st = 0.f, sp = 0.f;
+      for (int o = 0; o < co; ++o) { st += tt[o] * tt[o]; sp += pp[o] * pp[o]; px.c += tt[o] * pp[o]; }
+      px.a = rsqrtf(fmaxf(st, 1e-12f)); px.b = rsqrtf(fmaxf(sp, 1e-12f));
     }
+    float gp = 0.f;     // softmax head under a generic loss: sum_k g_k p_k
+    if (act == B2SEG_ACT_SOFTMAX && !(kind == 1 && own_act))
+      for (int o = 0; o < co; ++o) { float l, g; loss_elem(kind, prob, pp[o], tt[o], px, o, &l, &g); gp += g * pp[o]; }
+    int arg_p = 0, arg_t = 0;
+    for (int o = 0; o < co; ++o) {
+      const float p = pp[o], t = tt[o];
+      float l, g;
+      loss_elem(kind, prob, p, t, px, o, &l, &g);
+      local += l * scale;
+      float dz;
+      if ((kind == 0 || kind == 1) && own_act) dz = p - t;                                 // cross-entropy from the cached logits
+      else if (act == B2SEG_ACT_SIGMOID) dz = g * p * (1.f - p);
+      else if (act == B2SEG_ACT_SOFTMAX) dz = p * (g - gp);
+      else dz = g;
+      if (dl) dl[pix * co + o] = d.weight * dz * scale;
+      const float e = p - t;
+      m_sse += e * e; m_sae += fabsf(e);
+      m_bin += ((p > 0.5f) == (t > 0.5f)) ? 1.f : 0.f;
+      if (p > pp[arg_p]) arg_p = o;
+      if (t > tt[arg_t]) arg_t = o;
+    }
+    m_cat += arg_p == arg_t ? 1.f : 0.f;
   }
-  __shared__ float sh[32];
-  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  // block reduction of {loss, sum sq err, sum abs err, binary hits, arg-max hits}
+  __shared__ float sh[5][32];
+  float v[5] = {local, m_sse, m_sae, m_bin, m_cat};
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v[q];
+  }
   __syncthreads();
   if (threadIdx.x < 32) {
-    float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
-    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-    if (threadIdx.x == 0 && d.loss) atomicAdd(reinterpret_cast<float*>(d.loss), d.weight * t);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float t = threadIdx.x < (blockDim.x >> 5) ? sh[q][threadIdx.x] : 0.f;
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (threadIdx.x == 0) {
+        if (q == 0 && d.loss) atomicAdd(reinterpret_cast<float*>(d.loss), d.weight * t);
+        if (d.metrics) atomicAdd(reinterpret_cast<float*>(d.metrics) + q, t);
+      }
+    }
   }
 }
 struct LossLaunch : PreparedOp {
@@ -976,8 +1089,11 @@ struct LossLaunch : PreparedOp {
   }
 };
 PreparedOp* prepare_loss(const b2seg_loss_desc* d) {
-  if (d->kind < 0 || d->kind > 3) { set_error("loss: kind 0..3"); return nullptr; }
-  if (d->kind >= 2 && d->act == B2SEG_ACT_SOFTMAX) { set_error("loss: MSE/MAE through softmax unsupported"); return nullptr; }
+  if (d->kind < 0 || d->kind > 14) { set_error("loss: kind 0..14"); return nullptr; }
+  if (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_SIGMOID && d->act != B2SEG_ACT_SOFTMAX) { set_error("loss: head activation %d", d->act); return nullptr; }
+  if (((d->kind == 0 || d->kind == 7) && d->act == B2SEG_ACT_SOFTMAX) || (d->kind == 1 && d->act == B2SEG_ACT_SIGMOID)) {
+    set_error("loss: a cross-entropy on the other activation (binary on softmax, categorical on sigmoid) is not lowered"); return nullptr;
+  }
   auto* L = new LossLaunch(); L->d = *d; return L;
 }
 
