@@ -92,13 +92,63 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+SPEC_BF16_TFLOPS = 2250.0     # B200 dense bf16 datasheet figure (north_star's ">= 50 % of dense bf16 tensor-core peak")
+
+
 def measured_peaks():
+    """(burst bf16 TF/s, sustained bf16 TF/s, HBM GB/s, source).  The per-op kernel times come from event-timed replays of single
+    kernels and the timed region lasts a fraction of a second at full clocks: that is the BURST regime, so `frac` divides by the
+    burst figure; `frac_sustained` and `frac_spec` are reported beside it."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        return float(p["bf16_tflops"]), float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json: bf16_tflops = burst)"
     except Exception:
-        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def op_bytes(L, op, d):
+    """algorithmic HBM bytes of one streaming op (what it must read + write once; bf16 tensors 2 B, fp32 4 B), from its descriptor"""
+    def vb(v, es=2):
+        return 0 if not v.ptr else es * v.N * v.H * v.W * v.C
+    if op == L.OP_BN_ACT:
+        return vb(d.x) + sum(vb(d.out[i]) for i in range(d.n_out)) + (vb(d.pooled) if d.pool_h > 1 or d.pool_w > 1 else 0)
+    if op == L.OP_BN_BWD:
+        src = 0
+        for i in range(d.n_src):
+            s_ = d.src[i]
+            src += 4 * s_.cout * d.x.N * d.x.H * d.x.W if s_.kind == 2 else vb(s_.g)
+        passes = 2 if d.scale else 1          # statistics pass + apply pass both read x and the gradient sources
+        return passes * (vb(d.x) + src) + vb(d.dx)
+    if op == L.OP_ADAM:
+        return 30 * d.n                        # 4 reads + 3 writes fp32 + bf16 shadow
+    if op == L.OP_MEMSET:
+        return d.bytes
+    if op in (L.OP_HEAD_FWD, L.OP_HEAD_BWD):
+        npix = d.x.N * (d.x.H // max(d.stride, 1)) * (d.x.W // max(d.stride, 1))
+        return vb(d.x) + 4 * npix * d.cout + (vb(d.dx) if op == L.OP_HEAD_BWD else 0)
+    if op == L.OP_LOSS:
+        return 3 * 4 * d.n_pix * d.cout
+    if op == L.OP_ELTWISE:
+        return vb(d.a) + vb(d.b) + vb(d.c) + vb(d.out)
+    if op == L.OP_CAST:
+        return 4 * d.N * d.H * d.W * d.C + vb(d.out)
+    if op in (L.OP_RESIZE_FWD, L.OP_RESIZE_BWD):
+        return vb(d.x) + vb(d.y) + vb(d.yfwd)
+    if op == L.OP_MULBC_FWD:
+        return vb(d.a) + vb(d.b) + vb(d.out)
+    if op == L.OP_MULBC_BWD:
+        return vb(d.a) + vb(d.b) + vb(d.dout) + vb(d.da) + vb(d.db)
+    if op in (L.OP_COLSTATS, L.OP_COLSUM):
+        return vb(d.x if op == L.OP_COLSTATS else d.g)
+    if op in (L.OP_LSTM_FWD, L.OP_LSTM_BWD):
+        return vb(d.z) + vb(d.h) + vb(d.dh) + vb(d.dz)
+    if op == L.OP_POOL_BWD:
+        return vb(d.y) + vb(d.dp) + vb(d.dx)
+    if op in (L.OP_OUTACT_FWD, L.OP_OUTACT_BWD):
+        return vb(d.x) + 4 * d.x.N * d.x.H * d.x.W * d.cout
+    extra = getattr(L, "OP_EXTRA_BYTES", {}).get(op)
+    return extra(d) if extra else 0
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle leg
@@ -136,21 +186,68 @@ def oracle_train_step_time(batch, size, steps, warmup, depth=5, width=64):
     return float(np.sum(times)), cores
 
 
+L2_POLICY = "per-step working set (activations+weights+Adam state, >5 GB) exceeds the 126 MB L2; no flush needed"
+
+
 def run_reference(args):
+    """the reference's own CPU path for the workload (oracle port: TensorFlow is not installable here, DESIGN.md §5), all host cores;
+    each step is a bounded sample of the workload (batch 2 of the batch-32 step) so the run ends within a few minutes"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     batch = 2
     total, cores = oracle_train_step_time(batch, args.size, args.steps, args.warmup)
     ips = batch * args.steps / total
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {"impl": "reference", "metric": "2D UNet 256^2 train images/s", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference arm = oracle port of the reference's TF/Keras CPU path (TensorFlow is not installable in this image)"},
+            "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "parallelism": f"dp{world}", "l2_policy": L2_POLICY},
+            "note": "reference arm = oracle port of the reference's TF/Keras CPU path (TensorFlow is not installable in this image); "
+                    f"each timed step is a bounded sample of the workload: batch {batch} of the batch-{args.batch} step",
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} train steps of batch {batch} at {args.size}x{args.size} (same graph, fp32, PyTorch CPU)"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def other_config(n, batch, rank):
+    """BASELINE.json configs 1, 3, 4, 5: (model, x, targets, workload string, algorithmic train GFLOP / sample, batch)"""
+    from b2seg.model import Adam
+    from b2seg.models1d import UNet
+    from b2seg.models2d import unet_model_builder
+    rng = np.random.default_rng(10 * n + rank)
+    if n == 1:
+        B = batch or 32
+        m = UNet(1024, 5, 1, 64, 3, problem_type="Classification", output_nums=2, ds=0, ae=0, ag=0, lstm=0, is_transconv=True).UNet()
+        m.compile(loss="categorical_crossentropy", optimizer=Adam(2e-4))
+        x = rng.standard_normal((B, 1024, 1)).astype(np.float32)
+        y = np.eye(2, dtype=np.float32)[(x[..., 0] > 0).astype(np.int64)]
+        return m, x, y, f"1D UNet depth5 width64 L=1024 1 channel, 2 classes CCE + Adam(2e-4), batch {B}/GPU", 15.68, B
+    kw = dict(train_mode="from_scratch", is_transconv=True)
+    if n == 3:
+        B = batch or 32
+        m = unet_model_builder("UNetPP", 256, 256, 64, 5, num_channels=3, output_nums=4, ds=1, ag=1, final_activation="softmax", **kw).ResNet50()
+        x = rng.random((B, 256, 256, 3), dtype=np.float32)
+        lab = rng.integers(0, 4, (B, 256, 256))
+        y = {"out": np.eye(4, dtype=np.float32)[lab]}
+        for name in m.output_names[1:]:
+            y[name] = (lab > 0).astype(np.float32)[..., None]
+        m.compile(loss={"out": "categorical_crossentropy", **{name: "mse" for name in m.output_names[1:]}}, optimizer=Adam(2e-4))
+        return m, x, y, f"2D UNet++ DS+AG depth5 width64 256x256x3, 4 classes (CCE + 5 MSE levels) + Adam(2e-4), batch {B}/GPU", 1026.4, B
+    if n == 4:
+        B = batch or 8
+        m = unet_model_builder("MultiResUNet", 512, 512, 64, 5, num_channels=1, output_nums=1, alpha=1.0, **kw).ResNet50()
+        x = rng.random((B, 512, 512, 1), dtype=np.float32)
+        wl, gf = f"2D MultiResUNet alpha=1 transconv depth5 width64 512x512x1, BCE + Adam(2e-4), batch {B}/GPU", 1589.3
+    else:
+        B = batch or 32
+        m = unet_model_builder("UNet", 256, 256, 64, 5, num_channels=3, output_nums=1, lstm=1, dense_loop=3, **kw).ResNet50()
+        x = rng.random((B, 256, 256, 3), dtype=np.float32)
+        wl, gf = f"2D BCDUNet (UNet lstm=1 dense_loop=3) depth5 width64 256x256x3, BCE + Adam(2e-4), batch {B}/GPU; FLOPs = live gates only", 413.0
+    m.compile(loss="binary_crossentropy", optimizer=Adam(2e-4))
+    y = (rng.random(x.shape[:3] + (1,)) > 0.7).astype(np.float32)
+    return m, x, y, wl, gf, B
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -164,6 +261,8 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default="", help="dump per-op device times (profiling aid)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json config (1-based). 2 = the headline workload; 3 / 4 / 5 are measured with the same machinery on request")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2seg" else args.warmup
     if args.impl == "reference":
@@ -188,17 +287,27 @@ def main():
             os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("B2SEG_BWD_SM_RESERVE", "16"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, S = args.batch, args.size
-    model = unet_model_builder("UNet", S, S, 64, 5, num_channels=3, output_nums=1, ds=0, ae=0, ag=0, lstm=0, dense_loop=1,
-                               is_transconv=True, final_activation="sigmoid", train_mode="from_scratch").ResNet50()
-    model.compile(loss="binary_crossentropy", optimizer=Adam(2e-4))
-    x, y = synth_batch(B, S, 2 + rank)
-    xp, yp = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    workload, train_gflop = WORKLOAD, TRAIN_GFLOP_PER_IMAGE * (S * S) / (256 * 256)
+    if args.config == 2:
+        model = unet_model_builder("UNet", S, S, 64, 5, num_channels=3, output_nums=1, ds=0, ae=0, ag=0, lstm=0, dense_loop=1,
+                                   is_transconv=True, final_activation="sigmoid", train_mode="from_scratch").ResNet50()
+        model.compile(loss="binary_crossentropy", optimizer=Adam(2e-4))
+        x, y = synth_batch(B, S, 2 + rank)
+        ydict = y
+    else:
+        model, x, ydict, workload, train_gflop, B = other_config(args.config, args.batch if "--batch" in " ".join(sys.argv) else None, rank)
+        S = x.shape[1]
+    ylist = [ydict[n] for n in model.output_names] if isinstance(ydict, dict) else [ydict]
+    xp = torch.from_numpy(x).pin_memory()
+    yps = [torch.from_numpy(np.ascontiguousarray(t)).pin_memory() for t in ylist]
+    y = ylist[0]
     eng = model._engine(B, True)
     if world > 1:
         model.distribute()
         model.broadcast_weights(0)
-    eng.x_dev.copy_(xp)
-    eng.outputs[0]["target"].copy_(yp)
+    eng.x_dev.copy_(xp if model.graph.ndim == 2 else xp[:, None])
+    for o, t in zip(eng.outputs, yps):
+        o["target"].copy_(t if model.graph.ndim == 2 else t[:, None])
     torch.cuda.synchronize()
 
     def barrier():
@@ -236,9 +345,13 @@ def main():
     # fit() overlaps the copy of batch i+1 with the compute of step i (two staging slots + a copy stream).
     ns = args.steps
     xe = torch.from_numpy(np.concatenate([x] * ns, 0)).pin_memory()
-    ye = torch.from_numpy(np.concatenate([y] * ns, 0)).pin_memory()
-    xh, yh = xe.numpy(), ye.numpy()
-    model.fit(xh[:2 * B], yh[:2 * B], batch_size=B, epochs=1, shuffle=False, verbose=0)   # warm-up (staging buffers, streams)
+    yes = [torch.from_numpy(np.concatenate([t] * ns, 0)).pin_memory() for t in ylist]
+    xh = xe.numpy()
+    yh = {n: t.numpy() for n, t in zip(model.output_names, yes)} if len(yes) > 1 else yes[0].numpy()
+
+    def ycut(n_):
+        return {k_: v_[:n_] for k_, v_ in yh.items()} if isinstance(yh, dict) else yh[:n_]
+    model.fit(xh[:2 * B], ycut(2 * B), batch_size=B, epochs=1, shuffle=False, verbose=0)   # warm-up (staging buffers, streams)
     last = {}
 
     def e2e_run():
@@ -251,7 +364,7 @@ def main():
     # ---- per-op device times (one extra, untimed-for-throughput replay with an event after every op)
     roof = None
     if rank == 0:
-        peak_tf, peak_gbs, peak_src = measured_peaks()
+        peak_tf, peak_sus, peak_gbs, peak_src = measured_peaks()
         agg = {}
         op_rows = []
         for phase in (0, 1, 2):
@@ -265,11 +378,14 @@ def main():
             acc /= reps
             for i in range(n_ops):
                 info = eng.planner.op_info[(phase, i)]
+                op, desc, _note = eng.planner.ops[phase][i]
                 fam = {L.OP_CONV: CONV_FAM, L.OP_WGRAD: WGRAD_FAM}.get(info["op"], "streaming")
+                nbytes = float(op_bytes(L, op, desc)) if fam == "streaming" else 0.0
                 op_rows.append({"phase": phase, "i": i, "op": info["op"], "note": info["note"], "ms": float(acc[i]),
-                                "tflops": info["flops"] / (acc[i] / 1e3) / 1e12 if info["flops"] and acc[i] > 0 else None})
-                a = agg.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0))
-                a["ms"] += float(acc[i]); a["flops"] += info["flops"]; a["launches"] += 1
+                                "tflops": info["flops"] / (acc[i] / 1e3) / 1e12 if info["flops"] and acc[i] > 0 else None,
+                                "gbs": nbytes / (acc[i] / 1e3) / 1e9 if nbytes and acc[i] > 0 else None})
+                a = agg.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0, bytes=0.0))
+                a["ms"] += float(acc[i]); a["flops"] += info["flops"]; a["launches"] += 1; a["bytes"] += nbytes
         if args.ops_json:
             os.makedirs(os.path.dirname(os.path.abspath(args.ops_json)), exist_ok=True)
             with open(args.ops_json, "w") as f:
@@ -280,39 +396,52 @@ def main():
         achieved = a["flops"] / (a["ms"] / 1e3) / 1e12
         # DRAM bytes per launch of the dominant family from the committed ncu capture of this same command (tools/launch_summary.py)
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_launches_final.json")
-        if os.path.exists(tpath) and S == 256 and B == 32:
-            with open(tpath) as f:
-                tj = json.load(f)
-            key = "conv" if dom == CONV_FAM else "wgrad"
-            traffic = tj[key]["dram_bytes_per_launch"]
-            traffic_src = f"profiles/r1_launches_final.json: ncu dram__bytes_read.sum + dram__bytes_write.sum over the {tj[key]['launches']} {key} launches of one step / launches"
+        for tname in ("r2_launches_final.json", "r1_launches_final.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath) and S == 256 and B == 32 and args.config == 2:
+                with open(tpath) as f:
+                    tj = json.load(f)
+                key = "conv" if dom == CONV_FAM else "wgrad"
+                traffic = tj[key]["dram_bytes_per_launch"]
+                traffic_src = f"profiles/{tname}: ncu dram__bytes_read.sum + dram__bytes_write.sum over the {tj[key]['launches']} {key} launches of one step / launches"
+                break
+        step_tf = value / world * train_gflop / 1e3
+        fams = {}
+        for k, v in agg.items():
+            row = {"ms_per_step": v["ms"], "launches": v["launches"], "share_of_step": v["ms"] / step_ms_ops}
+            if v["flops"]:
+                tf = v["flops"] / (v["ms"] / 1e3) / 1e12
+                row.update(tflops=tf, frac=tf / peak_tf, frac_sustained=tf / peak_sus, frac_spec=tf / SPEC_BF16_TFLOPS)
+            else:
+                gbs = v["bytes"] / (v["ms"] / 1e3) / 1e9
+                row.update(algorithmic_gb_per_step=v["bytes"] / 1e9, gbs=gbs, hbm_frac=gbs / peak_gbs, hbm_peak_gbs=peak_gbs)
+            fams[k] = row
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "frac_sustained": achieved / peak_sus, "frac_spec": achieved / SPEC_BF16_TFLOPS,
+                "peaks": {"bf16_tflops_burst": peak_tf, "bf16_tflops_sustained": peak_sus, "bf16_tflops_spec": SPEC_BF16_TFLOPS, "hbm_gbs": peak_gbs},
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": a["launches"], "kernel_ms_per_step": a["ms"],
-                "kernel_share_of_step": a["ms"] / step_ms_ops,
-                "families": {k: {"ms_per_step": v["ms"], "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
-                                 "launches": v["launches"]} for k, v in agg.items()},
-                "whole_step_tflops": value / world * TRAIN_GFLOP_PER_IMAGE / 1e3 * (S * S) / (256 * 256),
-                "whole_step_frac_of_peak": value / world * TRAIN_GFLOP_PER_IMAGE / 1e3 * (S * S) / (256 * 256) / peak_tf}
+                "kernel_share_of_step": a["ms"] / step_ms_ops, "families": fams,
+                "whole_step": {"tflops": step_tf, "frac": step_tf / peak_tf, "frac_sustained": step_tf / peak_sus, "frac_spec": step_tf / SPEC_BF16_TFLOPS,
+                               "algorithmic_train_gflop_per_sample": train_gflop}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        total, cores = oracle_train_step_time(4, S, 4, 1)
+        total, cores = oracle_train_step_time(4, 256 if args.config != 2 else S, 4, 1)
         cpu = {"value": 4 * 4 / total, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": f"4 train steps of batch 4 at {S}x{S} after 1 warm-up (oracle: PyTorch-CPU fp32 restatement of the reference graph)"}
 
     if rank == 0:
         launches = sum(eng.launches)
-        line = {"metric": "2D UNet 256^2 train images/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": "2D UNet 256^2 train images/s" if args.config == 2 else f"BASELINE config {args.config} train samples/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD if S == 256 and B == 32 else f"{WORKLOAD} [overridden: size {S}, batch {B}]",
-                           "global_batch": B * world, "parallelism": f"dp{world}",
-                           "l2_policy": "per-step working set (activations+weights+Adam state, >5 GB) exceeds the 126 MB L2; no flush needed"},
+                "config": {"workload": workload if (args.config != 2 or (S == 256 and B == 32)) else f"{WORKLOAD} [overridden: size {S}, batch {B}]",
+                           "global_batch": B * world, "parallelism": f"dp{world}", "l2_policy": L2_POLICY},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(x.nbytes + y.nbytes), "d2h_bytes_per_step": 4,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(x.nbytes + sum(t.nbytes for t in ylist)), "d2h_bytes_per_step": 1024,
                         "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss"),
-                        "api": "Model.fit(x, y, batch_size, epochs=1, shuffle=False) over steps x batch samples in pinned host memory"},
+                        "api": "Model.fit(x, y, batch_size, epochs=1, shuffle=False) over steps x batch samples in pinned host memory (producer thread "
+                               "stages batch i+1 on a copy stream; one 1 KB log record per step read back asynchronously)"},
                 "gpu_launches": launches * args.steps, "launches_per_step": launches,
                 "device_memory_gb": eng.memory_bytes() / 2 ** 30}
         if getattr(eng, "exchange_calibration", None):
