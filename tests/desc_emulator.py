@@ -73,7 +73,7 @@ class FakeMem:
 
     def write_view(self, v, data):
         t, off = self.resolve(v.ptr)
-        if ROUND_BF16 and self.esize_of(v.ptr) == 2 and ROUND_BF16 in ("1", self.tag_of(v.ptr)):
+        if ROUND_BF16 and self.esize_of(v.ptr) == 2 and (ROUND_BF16 == "1" or ROUND_BF16 == self.tag_of(v.ptr)):
             data = data.to(torch.float32).to(torch.bfloat16)    # numerics model of the device: stored activations / gradients are bf16
         idx = (off + torch.arange(v.N).view(-1, 1, 1, 1) * v.sn + torch.arange(v.H).view(1, -1, 1, 1) * v.sh
                + torch.arange(v.W).view(1, 1, -1, 1) * v.sw + torch.arange(v.C).view(1, 1, 1, -1))
@@ -115,7 +115,7 @@ import numpy as np
 
 from b2seg import _lib as L
 
-_ESIZE = {"act": 2, "grad": 2, "param_wb": 2}
+_ESIZE = {"act": 2, "grad": 2, "param_wb": 2, "arena": 2}
 
 
 class PlanMem(FakeMem):

@@ -559,22 +559,25 @@ def test_loss_kinds_and_metrics(kind, act):
     from oracle.keras_ref import keras_loss
     name = _LOSS_NAMES[kind]
     if (kind in (0, 7) and act == L.ACT_SOFTMAX) or (kind == 1 and act == L.ACT_SIGMOID):
+        buf = torch.zeros(64, device="cuda")          # (valid memory: a library that failed to refuse must not fault)
         with pytest.raises(L.B2SegError):
-            L.call("b2seg_loss", L.LossDesc(0, 0, 4, 2, kind, act, 1.0, 0, 0, 0), stream())
+            L.call("b2seg_loss", L.LossDesc(buf.data_ptr(), buf.data_ptr(), 4, 2, kind, act, 1.0, 0, 0, 0), stream())
         return
     if kind == 8 and act == L.ACT_NONE:
         pytest.skip("Poisson of negative predictions is NaN in Keras too")
     dev, npix, co = "cuda", 3 * 37 * 5, 4
     g = torch.Generator(device="cpu").manual_seed(100 + 3 * kind + act)
-    z = (torch.randn(npix, co, generator=g) * 1.5).double().requires_grad_(True)
+    # float32 reference: the clipped-probability branches differ visibly between float32 and float64 (1 - (1 - 1e-7) is 1.19e-7 in
+    # float32), and TensorFlow computes them in float32 like the kernel
+    z = (torch.randn(npix, co, generator=g) * 1.5).requires_grad_(True)
     if name in ("cce", "categorical_hinge", "kld"):
-        t = F.one_hot(torch.randint(0, co, (npix,), generator=g), co).double()
+        t = F.one_hot(torch.randint(0, co, (npix,), generator=g), co).float()
     elif name in ("bce", "focal", "hinge", "squared_hinge"):
-        t = (torch.rand(npix, co, generator=g) > 0.6).double()
+        t = (torch.rand(npix, co, generator=g) > 0.6).float()
     elif name in ("msle", "poisson", "mape"):
-        t = torch.rand(npix, co, generator=g).double() * 2 + 0.25
+        t = torch.rand(npix, co, generator=g) * 2 + 0.25
     else:
-        t = torch.randn(npix, co, generator=g).double()
+        t = torch.randn(npix, co, generator=g)
     p = z if act == L.ACT_NONE else (torch.sigmoid(z) if act == L.ACT_SIGMOID else torch.softmax(z, -1))
     own = (kind in (0, 7) and act == L.ACT_SIGMOID) or (kind == 1 and act == L.ACT_SOFTMAX)
     want = keras_loss(name, p, t, logits=z if own else None)
@@ -583,10 +586,10 @@ def test_loss_kinds_and_metrics(kind, act):
     dl, loss, met = torch.zeros_like(y), torch.zeros(1, device=dev), torch.zeros(8, device=dev)
     L.call("b2seg_loss", L.LossDesc(y.data_ptr(), tt.data_ptr(), npix, co, kind, act, 0.7, dl.data_ptr(), loss.data_ptr(), met.data_ptr()), stream())
     torch.cuda.synchronize()
-    assert abs(float(loss) - 0.7 * float(want)) < 2e-5 * max(1.0, abs(float(want))), (float(loss), 0.7 * float(want))
-    assert abs(float(met[0]) - float(want)) < 2e-5 * max(1.0, abs(float(want)))
-    assert rel_l2(dl.cpu().double(), 0.7 * dz) < 2e-4, rel_l2(dl.cpu().double(), 0.7 * dz)
-    pe, te = p.detach(), t
+    assert abs(float(loss) - 0.7 * float(want)) < 1e-4 * max(1.0, abs(float(want))), (float(loss), 0.7 * float(want))
+    assert abs(float(met[0]) - float(want)) < 1e-4 * max(1.0, abs(float(want)))
+    assert rel_l2(dl.cpu().double(), 0.7 * dz.double()) < 1e-3, rel_l2(dl.cpu().double(), 0.7 * dz.double())
+    pe, te = p.detach().double(), t.double()
     assert abs(float(met[1]) - float(((pe - te) ** 2).sum())) < 1e-4 * float(((pe - te) ** 2).sum()) + 1e-3
     assert abs(float(met[2]) - float((pe - te).abs().sum())) < 1e-4 * float((pe - te).abs().sum()) + 1e-3
     assert abs(float(met[3]) - float(((y.cpu() > 0.5) == (te > 0.5)).sum())) <= 2      # (a prediction within float32 rounding of 0.5)

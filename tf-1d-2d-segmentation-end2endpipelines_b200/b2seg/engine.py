@@ -21,7 +21,7 @@ from .planner import Planner
 class Engine:
     def __init__(self, graph: Graph, batch: int, training: bool = True, losses: Optional[List[str]] = None,
                  loss_weights: Optional[List[float]] = None, adam: Optional[dict] = None, device: Optional[int] = None,
-                 share_params_from: Optional["Engine"] = None, adam_bucket_bytes: int = 0):
+                 share_params_from: Optional["Engine"] = None, adam_bucket_bytes: int = 0, reuse: bool = False):
         if not torch.cuda.is_available():
             raise L.B2SegError("b2seg needs a CUDA sm_100 (B200) device: the hot path has no CPU fallback")
         self.device = torch.cuda.current_device() if device is None else device
@@ -34,7 +34,8 @@ class Engine:
         self.dev = torch.device("cuda", self.device)
         self.planner = Planner(graph, batch, self._alloc, training=training, losses=losses, loss_weights=loss_weights, adam=adam,
                                stat_rows_fn=lambda d: self.lib.b2seg_conv_num_stat_rows(C.byref(d)),
-                               adam_bucket_bytes=adam_bucket_bytes).build()
+                               adam_bucket_bytes=adam_bucket_bytes, reuse=reuse).build()
+        self.reuse = reuse
         self.adam_bucket_bytes = adam_bucket_bytes
         p = self.planner
         n = max(p.n_train, 64)
@@ -220,6 +221,9 @@ class Engine:
 
     def tap(self, name: str, grad=False) -> torch.Tensor:
         """activation (or raw-conv-output gradient) of a layer as an fp32 NHWC tensor with logical channels"""
+        if self.reuse:
+            raise L.B2SegError("this engine reuses activation memory (a tensor's bytes are overwritten once nothing in the step needs them): "
+                               "build the model with keep_activations=True (or B2SEG_KEEP_ACTIVATIONS=1) to tap layers")
         p = self.planner
         view, Cn = (p.grad_taps[name] if grad else p.taps[name][:2])
         base = None

@@ -179,6 +179,9 @@ class Model:
         self._dist = None
         self.exchange_bucket_bytes = 64 << 20   # gradient-exchange bucket (data parallel): overlap granularity vs launch count
         self._ds_targets = None
+        # False (default): activation / gradient buffers share one arena by liveness (Planner._assign_memory).  True: every layer's
+        # tensors stay readable after a step (layer_output / the per-layer parity tests); B2SEG_KEEP_ACTIVATIONS=1 forces it.
+        self.keep_activations = bool(os.environ.get("B2SEG_KEEP_ACTIVATIONS"))
         self._adam_step = 0             # Adam's t: one counter per model (the moments are shared by the engines of every batch size)
 
     # ---- introspection -----------------------------------------------------------------------------------
@@ -314,7 +317,7 @@ class Model:
                 if self.world_size > 1 or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
                     bucket = self.exchange_bucket_bytes
             eng = Engine(self.graph, batch, training=training, losses=self._losses, loss_weights=self._loss_weights, adam=adam,
-                         share_params_from=self._primary, adam_bucket_bytes=bucket)
+                         share_params_from=self._primary, adam_bucket_bytes=bucket, reuse=not self.keep_activations)
             if self._primary is None:
                 self._primary = eng
                 eng.set_weights(self._weights)

@@ -154,11 +154,20 @@ LOSS_BUF_FLOATS = 256          # [0] total weighted loss; [8 + 8 i ..] per-outpu
 MAX_OUTPUTS = (LOSS_BUF_FLOATS - 8) // 8
 
 
+VBASE = 1 << 60          # virtual addresses handed out while planning with reuse=True (no real pointer or size lives up there)
+ARENA_ALIGN = 1024
+
+
 class Planner:
     def __init__(self, graph: Graph, batch: int, alloc: Callable[[int], int], training: bool = True,
                  losses: Optional[List[str]] = None, loss_weights: Optional[List[float]] = None, adam=None,
-                 stat_rows_fn: Optional[Callable] = None, adam_bucket_bytes: int = 0):
+                 stat_rows_fn: Optional[Callable] = None, adam_bucket_bytes: int = 0, reuse: bool = False):
         self.stat_rows_fn = stat_rows_fn or conv_stat_rows
+        # reuse: activation / gradient buffers share one arena by liveness (see _assign_memory); off = one allocation per tensor,
+        # every tensor stays readable after the step (what the per-layer parity tests tap)
+        self.reuse = reuse
+        self._vbufs: List[list] = []        # [virtual address, nbytes, tag]
+        self._vnext = VBASE
         # > 0 (data parallel): the optimizer phase is one Adam op per gradient-exchange bucket, in exchange order, so the
         # update of a bucket can run as soon as ITS all-reduce has landed while later buckets are still on the wire
         self.adam_bucket_bytes = adam_bucket_bytes
@@ -198,11 +207,130 @@ class Planner:
     # ---------------------------------------------------------------------------------------- memory helpers
     def alloc(self, nbytes, tag="act"):
         nbytes = (int(nbytes) + 255) // 256 * 256
-        ptr = self.alloc_fn(nbytes, tag)
-        self.buffers.append((tag, ptr, nbytes))
         if tag in ("act", "grad"):
             self.act_bytes += nbytes
+            if self.reuse:
+                nbytes = (nbytes + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+                ptr = self._vnext
+                self._vbufs.append([ptr, nbytes, tag])
+                self._vnext += nbytes
+                return ptr
+        ptr = self.alloc_fn(nbytes, tag)
+        self.buffers.append((tag, ptr, nbytes))
         return ptr
+
+    # ---------------------------------------------------------------------------------------- liveness / buffer reuse
+    @staticmethod
+    def _walk_ptrs(obj, fn):
+        """apply fn to every c_uint64 field (device addresses; sizes and strides are signed) of a ctypes structure, recursively"""
+        import ctypes as C
+        if isinstance(obj, C.Structure):
+            for name, typ in obj._fields_:
+                if typ is C.c_uint64:
+                    new = fn(getattr(obj, name))
+                    if new is not None:
+                        setattr(obj, name, new)
+                elif isinstance(typ, type) and issubclass(typ, (C.Structure, C.Array)):
+                    Planner._walk_ptrs(getattr(obj, name), fn)
+        elif isinstance(obj, C.Array):
+            if obj._type_ is C.c_uint64:
+                for i in range(len(obj)):
+                    new = fn(obj[i])
+                    if new is not None:
+                        obj[i] = new
+            elif isinstance(obj._type_, type) and issubclass(obj._type_, (C.Structure, C.Array)):
+                for i in range(len(obj)):
+                    Planner._walk_ptrs(obj[i], fn)
+
+    def _assign_memory(self):
+        """Buffer reuse by liveness.  Every op runs on one stream in program order (forward, backward, optimizer), so a tensor is live
+        from the first op that touches it to the last; the forward activations the backward pass re-reads stay live across the two
+        phases, gradients and streaming-only intermediates die within a few ops, and an inference plan keeps almost nothing.
+        Planning hands out virtual addresses; here the program is scanned for the first / last use of every virtual buffer, the
+        buffers are packed into one arena (time-ordered best fit; a buffer that dies at op t cannot share memory with one born at
+        op t: no op ever reads and writes aliased tensors) and every address in every descriptor is relocated."""
+        import bisect
+        bufs = self._vbufs
+        starts = [b[0] for b in bufs]
+
+        def find(addr):
+            i = bisect.bisect_right(starts, addr) - 1
+            assert i >= 0 and addr < bufs[i][0] + bufs[i][1], hex(addr)
+            return i
+        first, last = {}, {}
+        t = 0
+        for phase in (0, 1, 2):
+            for (_op, desc, _note) in self.ops[phase]:
+                def see(v, t=t):
+                    if v >= VBASE:
+                        i = find(v)
+                        first.setdefault(i, t)
+                        last[i] = t
+                    return None
+                self._walk_ptrs(desc, see)
+                t += 1
+        # pack: events in time order, allocations of time t before the releases of time t
+        order = sorted(first, key=lambda i: (first[i], -bufs[i][1]))
+        by_end: Dict[int, List[int]] = {}
+        for i in order:
+            by_end.setdefault(last[i], []).append(i)
+        free: List[List[int]] = []          # [offset, size], sorted by offset
+        top = 0
+        offset: Dict[int, int] = {}
+        released_upto = -1
+        for i in order:
+            # release everything that died strictly before this buffer is born
+            while released_upto < first[i] - 1:
+                released_upto += 1
+                for j in by_end.get(released_upto, []):
+                    o, n = offset[j], bufs[j][1]
+                    k = bisect.bisect_left([f[0] for f in free], o)
+                    free.insert(k, [o, n])
+                    if k + 1 < len(free) and free[k][0] + free[k][1] == free[k + 1][0]:
+                        free[k][1] += free[k + 1][1]
+                        del free[k + 1]
+                    if k > 0 and free[k - 1][0] + free[k - 1][1] == free[k][0]:
+                        free[k - 1][1] += free[k][1]
+                        del free[k]
+            need = bufs[i][1]
+            best = None
+            for k, (o, n) in enumerate(free):
+                if n >= need and (best is None or n < free[best][1]):
+                    best = k
+            if best is not None:
+                o, n = free[best]
+                offset[i] = o
+                if n == need:
+                    del free[best]
+                else:
+                    free[best] = [o + need, n - need]
+            elif free and free[-1][0] + free[-1][1] == top:       # grow the arena from its last free block
+                o, n = free.pop()
+                offset[i] = o
+                top = o + need
+            else:
+                offset[i] = top
+                top += need
+        self.arena_bytes = max(top, ARENA_ALIGN)
+        base = self.alloc_fn(self.arena_bytes, "arena")
+        self.buffers.append(("arena", base, self.arena_bytes))
+        assert base % 256 == 0
+
+        def reloc(v):
+            if v < VBASE:
+                return None
+            i = find(v)
+            return base + offset.get(i, 0) + (v - bufs[i][0])
+        for phase in (0, 1, 2):
+            for (_op, desc, _note) in self.ops[phase]:
+                self._walk_ptrs(desc, reloc)
+        from dataclasses import replace as _replace
+
+        def rv(view):
+            return _replace(view, ptr=reloc(view.ptr)) if view.ptr >= VBASE else view
+        self.taps = {k: (rv(v[0]),) + tuple(v[1:]) for k, v in self.taps.items()}
+        self.grad_taps = {k: (rv(v[0]),) + tuple(v[1:]) for k, v in self.grad_taps.items()}
+        self.reuse_stats = dict(tensors=len(bufs), tensor_bytes=sum(b[1] for b in bufs), arena_bytes=self.arena_bytes)
 
     def new_act(self, H, W, Cp, tag="act") -> TView:
         return TView.dense(self.alloc(self.N * H * W * Cp * 2, tag), self.N, H, W, Cp)
@@ -547,6 +675,8 @@ class Planner:
                 self.emit(2, L.OP_ADAM, L.AdamDesc(self.w_ptr + 4 * lo, self.g_ptr + 4 * lo, self.m_ptr + 4 * lo, self.v_ptr + 4 * lo,
                                                    self.wb_ptr + 2 * lo, hi - lo, a["lr"], a["beta1"], a["beta2"], a["eps"], 1.0, 1),
                           "adam" if len(ranges) == 1 else f"adam [{lo}, {hi})")
+        if self.reuse:
+            self._assign_memory()
         return self
 
     # -- destinations: where a produced tensor must live ------------------------------------------------------
@@ -1369,7 +1499,10 @@ class Planner:
         dx = self.new_act(Hi, Wi, cin_p, "grad")
         if strided:
             # 1x1 'valid' stride-s conv reads pixels (s*i, s*j): its input gradient lives on that sub-grid; the other
-            # pixels of dx are never written and stay at the zeros the buffer was allocated with
+            # pixels of dx are never written and stay at the zeros the buffer was allocated with (with buffer reuse the
+            # memory has had other tenants: zero it first)
+            if self.reuse:
+                self.emit(1, L.OP_MEMSET, L.MemsetDesc(dx.ptr, self.N * Hi * Wi * cin_p * 2), f"zero dx {n.name}")
             self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, dx.parity(0, 0, a["strides"][0], a["strides"][1])),
                       f"dgrad {n.name}", flops=self._conv_flops(n))
             self._add_gsrc(src_node, GSrc(dx))
