@@ -78,6 +78,8 @@ typedef struct b2seg_conv_desc {
   b2seg_view mul_view;              /* dgrad fusion: out *= act'(mul_view) with mul_mode = B2SEG_ACT_*; 0 = off */
   int32_t mul_mode;
   int32_t block_n;                  /* 0 = auto; else 64 / 128 / 256 */
+  int32_t stats_atomic;             /* 1: `stats` is ONE caller-zeroed [2][out.C] row every CTA adds its sums into (red.add) instead of one row
+                                     * per CTA / tile: consumers read final sums without a finalize launch (b2seg_gate_fwd) */
 } b2seg_conv_desc;
 
 /* Weight gradient (Conv2DBackpropFilter) on tcgen05: dW[co][widx][ci] (+)= sum_{n,h,w} dy[tap.src](n,h+dyh,w+dyw,co) * x[tap.src](n,h+dh,w+dw,ci)
@@ -297,8 +299,43 @@ typedef struct b2seg_tpool_desc {
   int32_t mode;        /* 0 = max, 1 = mean */
 } b2seg_tpool_desc;
 
+/* Additive attention gate (2DCNN/models/unet_variants.py:67-82 Attention_Block), everything between the two 1x1 projections and
+ * the concat slot, fused (north_star: "the additive attention gate (1x1 convs + sigmoid multiply) fused into one kernel"; in
+ * training mode its three BatchNormalizations are grid-wide reductions, i.e. kernel boundaries: two streaming launches forward,
+ * four backward, csrc/gate.cu):
+ *   a = BN_a(za), b = BN_b(zb)           za = Conv1x1 stride 2 (skip), zb = Conv1x1 (gating signal): b2seg_conv with stats_atomic
+ *   z = Conv1x1 -> 1 (ReLU(a + b)),  m = sigmoid(BN_3(z))
+ *   out = skip * (UpSampling2D(2, bilinear)(m) + LeakyReLU(Conv2DTranspose(1, 4x4, stride 2)(m)))
+ * b2seg_gate_fwd also produces the BatchNorm coefficients of both branches (vec_a / vec_b), updates the three pairs of moving
+ * statistics and leaves z for the backward pass; b2seg_gate_bwd produces dskip (through the multiply only: the stride-2
+ * projection's own input gradient is a b2seg_conv dgrad), dza, dzb and every parameter gradient of the gate except the two
+ * projection kernels. */
+typedef struct b2seg_gate_desc {
+  b2seg_view za, zb;            /* (N,h,w,C) bf16 raw projection outputs; C = 8 * 2^k */
+  uint64_t sums_a, sums_b;      /* fp32 [2][C]: column sums and sums of squares added up by the projection kernels (caller-zeroed per step) */
+  uint64_t gamma_a, beta_a, mm_a, mv_a, gamma_b, beta_b, mm_b, mv_b;   /* fp32 [C]; moving statistics updated in place when training */
+  uint64_t vec_a, vec_b;        /* fp32 [4][C] out: scale, shift, mean, rstd of each branch */
+  uint64_t w3, b3;              /* fp32 [C], [1]: the C -> 1 convolution */
+  uint64_t z;                   /* fp32 [N*h*w] out */
+  uint64_t sums3;               /* fp32 [2]: sum z, sum z^2 (caller-zeroed per step) */
+  uint64_t gamma3, beta3, mm3, mv3;   /* fp32 [1] */
+  uint64_t wt, bt;              /* transposed-conv kernel element (ky,kx) at wt[(ky*4+kx)*wt_stride] (fp32), its bias */
+  int32_t wt_stride;
+  int32_t training, bessel;
+  float eps, momentum;
+  double count;                 /* N*h*w */
+  b2seg_view skip, out;         /* (N,2h,2w,Cs) bf16, Cs = 8 * 2^k */
+  /* ---- backward ---- */
+  b2seg_view dout, dskip;       /* gradient of out (in), of skip through the multiply (out) */
+  uint64_t dr, g3;              /* fp32 scratch [N*2h*2w], [N*h*w] */
+  uint64_t bsums3, bsums_ab;    /* fp32 scratch [2], [3][C] (zeroed by the op) */
+  b2seg_view dza, dzb;          /* bf16 out */
+  uint64_t dgamma_a, dbeta_a, dgamma_b, dbeta_b, dgamma3, dbeta3;   /* fp32 out (stored) */
+  uint64_t dw3, db3, dwt, dbt;  /* fp32, accumulated (caller-zeroed): [C], [1], 16 elements of stride wt_stride, [1] */
+} b2seg_gate_desc;
+
 const char* b2seg_last_error(void);
-int b2seg_version(void);   /* 102; the ctypes binding refuses a library of another version */
+int b2seg_version(void);   /* 103; the ctypes binding refuses a library of another version */
 int b2seg_device_check(int device);
 int b2seg_sizeof_desc(int op);  /* sizeof the descriptor struct of a B2SEG_OP_* code (binding self-check, no GPU needed) */
 
@@ -330,13 +367,15 @@ int b2seg_rowsum(const b2seg_rowsum_desc* d, void* stream);
 int b2seg_outact_fwd(const b2seg_outact_desc* d, void* stream);
 int b2seg_outact_bwd(const b2seg_outact_desc* d, void* stream);
 int b2seg_target_pool(const b2seg_tpool_desc* d, void* stream);
+int b2seg_gate_fwd(const b2seg_gate_desc* d, void* stream);
+int b2seg_gate_bwd(const b2seg_gate_desc* d, void* stream);
 
 /* ---- plan: a recorded sequence of the ops above, replayed per step ---- */
 typedef struct b2seg_plan b2seg_plan;
 enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
        B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,
        B2SEG_OP_MEMSET, B2SEG_OP_RESIZE_FWD, B2SEG_OP_RESIZE_BWD, B2SEG_OP_MULBC_FWD, B2SEG_OP_MULBC_BWD, B2SEG_OP_COLSTATS,
-       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM, B2SEG_OP_OUTACT_FWD, B2SEG_OP_OUTACT_BWD, B2SEG_OP_TARGET_POOL };
+       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM, B2SEG_OP_OUTACT_FWD, B2SEG_OP_OUTACT_BWD, B2SEG_OP_TARGET_POOL, B2SEG_OP_GATE_FWD, B2SEG_OP_GATE_BWD };
 typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
 
 /* Data parallel: backward-phase ops added to a plan AFTER this call size their grids for (SMs - sms), leaving room for the

@@ -187,7 +187,11 @@ def emu_conv(mem, d):
     if d.stats:
         C = d.out[0].C
         st = mem.f32(d.stats, 2 * C)   # emulator writes totals into partial 0; the rest stay zero
-        st[:C], st[C:] = tot_s, tot_q
+        if d.stats_atomic:             # one caller-zeroed row every CTA adds into
+            st[:C] += tot_s
+            st[C:] += tot_q
+        else:
+            st[:C], st[C:] = tot_s, tot_q
 
 
 def emu_bn_finalize(mem, d):
@@ -585,7 +589,94 @@ def emu_pool_bwd(mem, d):
     mem.write_view(d.dx, dx)
 
 
-EMU = {L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_finalize, L.OP_BN_ACT: emu_bn_act,
+def _gate_forward(mem, d, za, zb, skip, prm):
+    """float64 restatement of csrc/gate.cu's forward on torch tensors (channels-last); prm: dict of parameter tensors.  Returns
+    (out, z, batch statistics)"""
+    import torch.nn.functional as F
+    N, h, w, C = za.shape
+
+    def bn(x, gamma, beta, mm, mv):
+        if d.training:
+            mean = x.reshape(-1, x.shape[-1]).mean(0)
+            var = ((x.reshape(-1, x.shape[-1]) - mean) ** 2).mean(0)
+        else:
+            mean, var = mm, mv
+        return (x - mean) * torch.rsqrt(var + d.eps) * gamma + beta, mean, var
+    a, mean_a, var_a = bn(za, prm["gamma_a"], prm["beta_a"], prm["mm_a"], prm["mv_a"])
+    b, mean_b, var_b = bn(zb, prm["gamma_b"], prm["beta_b"], prm["mm_b"], prm["mv_b"])
+    z = (torch.relu(a + b) * prm["w3"]).sum(-1, keepdim=True) + prm["b3"]
+    zn, mean3, var3 = bn(z, prm["gamma3"], prm["beta3"], prm["mm3"], prm["mv3"])
+    m = torch.sigmoid(zn).permute(0, 3, 1, 2)                                     # N,1,h,w
+    r1 = F.interpolate(m, scale_factor=2, mode="bilinear", align_corners=False)
+    pre = F.conv_transpose2d(m, prm["wt"].view(1, 1, 4, 4), prm["bt"], stride=2, padding=1)
+    r = (r1 + torch.where(pre > 0, pre, 0.3 * pre)).permute(0, 2, 3, 1)
+    return skip * r, z, dict(a=(mean_a, var_a), b=(mean_b, var_b), c=(mean3, var3))
+
+
+def _gate_params(mem, d, C, grad=False):
+    prm = dict(gamma_a=mem.f32(d.gamma_a, C), beta_a=mem.f32(d.beta_a, C), mm_a=mem.f32(d.mm_a, C), mv_a=mem.f32(d.mv_a, C),
+               gamma_b=mem.f32(d.gamma_b, C), beta_b=mem.f32(d.beta_b, C), mm_b=mem.f32(d.mm_b, C), mv_b=mem.f32(d.mv_b, C),
+               w3=mem.f32(d.w3, C), b3=mem.f32(d.b3, 1), gamma3=mem.f32(d.gamma3, 1), beta3=mem.f32(d.beta3, 1), mm3=mem.f32(d.mm3, 1),
+               mv3=mem.f32(d.mv3, 1), wt=mem.f32(d.wt, 16 * d.wt_stride)[::d.wt_stride], bt=mem.f32(d.bt, 1))
+    if grad:
+        prm = {k: v.clone().requires_grad_(not k.startswith("m")) for k, v in prm.items()}
+    return prm
+
+
+def emu_gate_fwd(mem, d):
+    za, zb, skip = mem.gather_view(d.za), mem.gather_view(d.zb), mem.gather_view(d.skip)
+    N, h, w, C = za.shape
+    prm = _gate_params(mem, d, C)
+    out, z, st = _gate_forward(mem, d, za, zb, skip, prm)
+    mem.f32(d.z, N * h * w)[:] = z.reshape(-1)
+    mem.write_view(d.out, out)
+    if d.training:
+        # the kernel derives the branch statistics from the accumulated column sums: they must agree with the direct ones
+        for tag, x in (("a", za), ("b", zb)):
+            sums = mem.f32(getattr(d, "sums_" + tag), 2 * C)
+            flat = x.reshape(-1, C)
+            assert torch.allclose(sums[:C], flat.sum(0), rtol=1e-9, atol=1e-9) and torch.allclose(sums[C:], (flat * flat).sum(0), rtol=1e-9, atol=1e-9), \
+                "gate: projection statistics accumulators do not hold the column sums"
+        s3 = mem.f32(d.sums3, 2)
+        s3[0] += z.sum()
+        s3[1] += (z * z).sum()
+        n = d.count
+        for tag, key in (("a", "a"), ("b", "b"), ("3", "c")):
+            mean, var = st[key]
+            uv = var * n / (n - 1) if (d.bessel and n > 1) else var
+            mm, mv = prm["mm_" + tag if tag != "3" else "mm3"], prm["mv_" + tag if tag != "3" else "mv3"]
+            mm[:] = mm * d.momentum + mean * (1 - d.momentum)
+            mv[:] = mv * d.momentum + uv * (1 - d.momentum)
+    for tag in ("a", "b"):
+        mean, var = st[tag] if d.training else (prm["mm_" + tag], prm["mv_" + tag])
+        rstd = torch.rsqrt(var + d.eps)
+        vec = mem.f32(getattr(d, "vec_" + tag), 4 * C)
+        vec[:C], vec[C:2 * C] = prm["gamma_" + tag] * rstd, prm["beta_" + tag] - mean * prm["gamma_" + tag] * rstd
+        vec[2 * C:3 * C], vec[3 * C:] = mean, rstd
+
+
+def emu_gate_bwd(mem, d):
+    za = mem.gather_view(d.za).clone().requires_grad_(True)
+    zb = mem.gather_view(d.zb).clone().requires_grad_(True)
+    skip = mem.gather_view(d.skip).clone().requires_grad_(True)      # (a leaf here: gradient through the multiply only)
+    N, h, w, C = za.shape
+    prm = _gate_params(mem, d, C, grad=True)
+    out, _z, _st = _gate_forward(mem, d, za, zb, skip, prm)
+    out.backward(mem.gather_view(d.dout))
+    mem.write_view(d.dskip, skip.grad)
+    mem.write_view(d.dza, za.grad)
+    mem.write_view(d.dzb, zb.grad)
+    for name in ("gamma_a", "beta_a", "gamma_b", "beta_b"):
+        mem.f32(getattr(d, "d" + name), C)[:] = prm[name].grad
+    mem.f32(d.dgamma3, 1)[:] = prm["gamma3"].grad
+    mem.f32(d.dbeta3, 1)[:] = prm["beta3"].grad
+    mem.f32(d.dw3, C)[:] += prm["w3"].grad
+    mem.f32(d.db3, 1)[:] += prm["b3"].grad
+    mem.f32(d.dwt, 16 * d.wt_stride)[::d.wt_stride] += prm["wt"].grad
+    mem.f32(d.dbt, 1)[:] += prm["bt"].grad
+
+
+EMU = {L.OP_GATE_FWD: emu_gate_fwd, L.OP_GATE_BWD: emu_gate_bwd, L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_finalize, L.OP_BN_ACT: emu_bn_act,
        L.OP_BN_BWD: emu_bn_bwd, L.OP_ADAM: emu_adam, L.OP_HEAD_FWD: emu_head_fwd, L.OP_HEAD_BWD: emu_head_bwd,
        L.OP_LOSS: emu_loss, L.OP_ELTWISE: emu_eltwise, L.OP_CAST: emu_cast, L.OP_COLSUM: emu_colsum,
        L.OP_MEMSET: emu_memset, L.OP_RESIZE_FWD: emu_resize_fwd, L.OP_RESIZE_BWD: emu_resize_bwd,

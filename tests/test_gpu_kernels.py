@@ -594,3 +594,89 @@ def test_loss_kinds_and_metrics(kind, act):
     assert abs(float(met[2]) - float((pe - te).abs().sum())) < 1e-4 * float((pe - te).abs().sum()) + 1e-3
     assert abs(float(met[3]) - float(((y.cpu() > 0.5) == (te > 0.5)).sum())) <= 2      # (a prediction within float32 rounding of 0.5)
     assert abs(float(met[4]) - float((y.cpu().argmax(-1) == te.argmax(-1)).sum())) <= 2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused attention gate (csrc/gate.cu) against the float64 restatement the CPU emulator uses (tests/desc_emulator.py:_gate_forward)
+@pytest.mark.parametrize("N,h,w,C,Cs,training", [(2, 8, 8, 64, 64, 1), (3, 5, 7, 16, 8, 1), (2, 16, 12, 128, 256, 1), (1, 4, 4, 1024, 512, 1),
+                                                  (2, 33, 9, 8, 32, 1), (2, 8, 8, 64, 64, 0)])
+def test_fused_attention_gate(N, h, w, C, Cs, training):
+    import types
+    from desc_emulator import _gate_forward
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(7 * C + h)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    za, zb = bf(rnd(N, h, w, C).to(dev)), bf((rnd(N, h, w, C) * 0.7 + 0.2).to(dev))
+    skipb = bf(rnd(N, 2 * h, 2 * w, 3 * Cs).to(dev))             # the skip and the output are channel windows of wider buffers
+    outb = torch.full((N, 2 * h, 2 * w, 2 * Cs), 7.0, device=dev, dtype=torch.bfloat16)
+    prm = dict(gamma_a=1 + 0.2 * rnd(C), beta_a=0.1 * rnd(C), mm_a=0.1 * rnd(C), mv_a=1 + 0.2 * torch.rand(C, generator=g),
+               gamma_b=1 + 0.2 * rnd(C), beta_b=0.1 * rnd(C), mm_b=0.1 * rnd(C), mv_b=1 + 0.2 * torch.rand(C, generator=g),
+               w3=rnd(C) / C ** 0.5, b3=0.1 * rnd(1), gamma3=1 + 0.2 * rnd(1), beta3=0.1 * rnd(1), mm3=0.1 * rnd(1),
+               mv3=1 + 0.2 * torch.rand(1, generator=g), wt=0.5 * rnd(16), bt=0.1 * rnd(1))
+    stride = 8
+    P = {k: v.to(dev).float().contiguous() for k, v in prm.items()}
+    wt_dev = torch.zeros(16 * stride, device=dev)
+    wt_dev[::stride] = P["wt"]
+    moving0 = {k: P[k].clone() for k in ("mm_a", "mv_a", "mm_b", "mv_b", "mm3", "mv3")}
+    sums_a = torch.cat([za.float().reshape(-1, C).sum(0), (za.float() ** 2).reshape(-1, C).sum(0)]).contiguous()
+    sums_b = torch.cat([zb.float().reshape(-1, C).sum(0), (zb.float() ** 2).reshape(-1, C).sum(0)]).contiguous()
+    sums3 = torch.zeros(8, device=dev)
+    vec = torch.zeros(8 * C, device=dev)
+    z = torch.zeros(N * h * w, device=dev)
+    d = L.GateDesc()
+    d.za, d.zb = tv(za).to_c(), tv(zb).to_c()
+    d.sums_a, d.sums_b, d.sums3 = sums_a.data_ptr(), sums_b.data_ptr(), sums3.data_ptr()
+    for k_ in ("gamma_a", "beta_a", "mm_a", "mv_a", "gamma_b", "beta_b", "mm_b", "mv_b", "w3", "b3", "gamma3", "beta3", "mm3", "mv3", "bt"):
+        setattr(d, k_, P[k_].data_ptr())
+    d.wt, d.wt_stride = wt_dev.data_ptr(), stride
+    d.vec_a, d.vec_b, d.z = vec.data_ptr(), vec.data_ptr() + 16 * C, z.data_ptr()
+    d.training, d.bessel, d.eps, d.momentum, d.count = training, 1, 1e-3, 0.99, float(N * h * w)
+    d.skip, d.out = tv(skipb, Cs, Cs).to_c(), tv(outb, Cs, Cs).to_c()
+    L.call("b2seg_gate_fwd", d, stream())
+    torch.cuda.synchronize()
+    # ---- reference
+    cfg = types.SimpleNamespace(training=training, eps=1e-3)
+    R = {k: v.double().clone().requires_grad_(not k.startswith("m")) for k, v in prm.items()}
+    za64 = za.cpu().double().requires_grad_(True)
+    zb64 = zb.cpu().double().requires_grad_(True)
+    sk64 = skipb[..., Cs:2 * Cs].cpu().double().requires_grad_(True)
+    out64, z64, st = _gate_forward(None, cfg, za64, zb64, sk64, R)
+    assert rel_l2(z.cpu().double(), z64.detach().reshape(-1)) < 2e-5
+    assert rel_l2(outb[..., Cs:].float().cpu().double(), out64.detach()) < 3e-3
+    assert torch.all(outb[..., :Cs] == 7.0)
+    if training:
+        n = N * h * w
+        for tag, key in (("_a", "a"), ("_b", "b"), ("3", "c")):
+            mean, var = st[key]
+            assert torch.allclose(P["mm" + tag].cpu().double(), moving0["mm" + tag].cpu().double() * 0.99 + mean.detach() * 0.01, atol=1e-5)
+            assert torch.allclose(P["mv" + tag].cpu().double(), moving0["mv" + tag].cpu().double() * 0.99 + var.detach() * n / (n - 1) * 0.01, atol=1e-5)
+        assert abs(float(sums3[0]) - float(z64.sum())) < 1e-3 * (1 + abs(float(z64.sum()))) and abs(float(sums3[1]) - float((z64 ** 2).sum())) < 1e-3 * float((z64 ** 2).sum())
+    else:
+        assert all(torch.equal(P[k_], moving0[k_]) for k_ in moving0)
+        return
+    # ---- backward
+    doutb = bf(rnd(N, 2 * h, 2 * w, 2 * Cs).to(dev))
+    dskipb = torch.full((N, 2 * h, 2 * w, Cs), 3.0, device=dev, dtype=torch.bfloat16)
+    dza, dzb = torch.zeros_like(za), torch.zeros_like(zb)
+    G = {k_: torch.zeros_like(P[k_]) for k_ in ("gamma_a", "beta_a", "gamma_b", "beta_b", "gamma3", "beta3", "w3", "b3", "bt")}
+    dwt = torch.zeros(16 * stride, device=dev)
+    scr = torch.zeros(N * 4 * h * w + N * h * w + 8 + 3 * C, device=dev)
+    d.dout, d.dskip, d.dza, d.dzb = tv(doutb, 0, Cs).to_c(), tv(dskipb).to_c(), tv(dza).to_c(), tv(dzb).to_c()
+    d.dr, d.g3 = scr.data_ptr(), scr.data_ptr() + 4 * N * 4 * h * w
+    d.bsums3 = d.g3 + 4 * N * h * w
+    d.bsums_ab = d.bsums3 + 32
+    for k_ in ("gamma_a", "beta_a", "gamma_b", "beta_b", "gamma3", "beta3"):
+        setattr(d, "d" + k_, G[k_].data_ptr())
+    d.dw3, d.db3, d.dwt, d.dbt = G["w3"].data_ptr(), G["b3"].data_ptr(), dwt.data_ptr(), G["bt"].data_ptr()
+    for rep in range(2):              # the scratch sums are zeroed by the op itself; dw3 / db3 / dwt / dbt accumulate
+        L.call("b2seg_gate_bwd", d, stream())
+    torch.cuda.synchronize()
+    out64.backward(doutb[..., :Cs].cpu().double())
+    assert rel_l2(dskipb.float().cpu().double(), sk64.grad) < 4e-3
+    assert rel_l2(dza.float().cpu().double(), za64.grad) < 6e-3, rel_l2(dza.float().cpu().double(), za64.grad)
+    assert rel_l2(dzb.float().cpu().double(), zb64.grad) < 6e-3, rel_l2(dzb.float().cpu().double(), zb64.grad)
+    for k_ in ("gamma_a", "beta_a", "gamma_b", "beta_b", "gamma3", "beta3"):
+        assert rel_l2(G[k_].cpu().double(), R[k_].grad) < 2e-3, (k_, rel_l2(G[k_].cpu().double(), R[k_].grad))
+    for k_ in ("w3", "b3", "bt"):
+        assert rel_l2(G[k_].cpu().double(), 2 * R[k_].grad) < 2e-3, (k_, rel_l2(G[k_].cpu().double(), 2 * R[k_].grad))
+    assert rel_l2(dwt[::stride].cpu().double(), 2 * R["wt"].grad) < 2e-3 and float(dwt.view(16, stride)[:, 1:].abs().max()) == 0

@@ -653,8 +653,10 @@ def test_buffer_reuse_changes_nothing(dec, kw, size, width, depth):
     ga, gb = ea.get_grads(), eb.get_grads()
     gmax = max(float(np.abs(v).max()) for v in ga.values())
     for key in ga:
-        if float(np.linalg.norm(ga[key])) > 1e-4 * gmax * ga[key].size ** 0.5:
+        if key.endswith("/kernel"):
             assert rel_l2(gb[key], ga[key]) < 5e-2, (key, rel_l2(gb[key], ga[key]))
+        else:       # per-channel sums (gamma, beta, bias) may cancel down to rounding noise: absolute criterion on the model's gradient scale
+            assert float(np.abs(gb[key] - ga[key]).max()) < 2e-2 * gmax, (key, float(np.abs(gb[key] - ga[key]).max()), gmax)
     with pytest.raises(Exception, match="keep_activations"):
         eb.tap(next(iter(eb.planner.taps)))
     for _ in range(2):

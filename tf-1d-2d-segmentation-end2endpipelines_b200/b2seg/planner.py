@@ -374,11 +374,47 @@ class Planner:
                     else:
                         parts.append(i)
                 self.flat_concat[id(n)] = parts
+        # ---- channel-layout classes.  Tensors related by an element-wise layer (BN, activation, pool, up-sampling, add, the
+        # attention multiply) must share one physical channel layout.  A class containing a concatenate output inherits that
+        # concat's (possibly gapped: odd channel counts are padded per slot) layout, and the convolutions feeding the class
+        # are made to PRODUCE it by scattering their weight rows — MultiResBlock's `add([shortcut, BN(concat(...))])`.
+        parent = {id(n): id(n) for n in g.nodes}
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+
+        def union(a, b):
+            ra, rb = find(id(a)), find(id(b))
+            if ra != rb:
+                parent[ra] = rb
+
+        for n in g.nodes:
+            if n.op in ("bn", "act", "pool", "up", "pow"):
+                union(n, n.inputs[0])
+            elif n.op == "add":
+                for i in n.inputs:
+                    union(n, i)
+            elif n.op == "mul":
+                union(n, n.inputs[0])
+        self._find = find
+        self._cls_concat: Dict[int, List[Node]] = {}
+        for n in g.nodes:
+            if n.op == "concat" and id(n) not in self.absorbed_concat:
+                self._cls_concat.setdefault(find(id(n)), []).append(n)
+        self._segs_memo: Dict[int, List[Tuple[int, int]]] = {}
+        self._cphys_memo: Dict[int, int] = {}
+        self._match_gates(absorbed)
         for n in g.nodes:
             if id(n) in absorbed:
                 continue
             if n.op == "input":
                 self.units.append(dict(kind="input", node=n, out=n))
+            elif n.op in ("conv", "tconv") and id(n) in self.gate_proj:
+                # a 1x1 projection of a fused attention gate: convolution + atomic column sums only (b2seg_gate_fwd does the rest)
+                self.units.append(dict(kind="conv", node=n, bn=None, act=None, pool=None, out=n, gate=self.gate_proj[id(n)]))
             elif n.op in ("conv", "tconv"):
                 a = n.attrs
                 is_head = (n.op == "conv" and a["kernel"] == (1, 1) and a["filters"] <= 8 and n in g.outputs)
@@ -459,6 +495,8 @@ class Planner:
                 self.units.append(dict(kind="act", node=n, out=n))
             elif n.op == "pow":
                 self.units.append(dict(kind="pow", node=n, out=n))
+            elif n.op == "mul" and id(n) in self.gates:
+                self.units.append(dict(kind="gate", node=n, out=n, gate=self.gates[id(n)]))
             elif n.op == "mul":
                 self.units.append(dict(kind="mul", node=n, out=n))
             elif n.op == "convlstm":
@@ -484,38 +522,176 @@ class Planner:
         for u in self.units:
             if u.get("pool") is not None:
                 self.unit_of_out[id(u["pool"])] = u
-        # ---- channel-layout classes.  Tensors related by an element-wise layer (BN, activation, pool, up-sampling, add, the
-        # attention multiply) must share one physical channel layout.  A class containing a concatenate output inherits that
-        # concat's (possibly gapped: odd channel counts are padded per slot) layout, and the convolutions feeding the class
-        # are made to PRODUCE it by scattering their weight rows — MultiResBlock's `add([shortcut, BN(concat(...))])`.
-        parent = {id(n): id(n) for n in g.nodes}
+    # ---------------------------------------------------------------------------------------- fused attention gates
+    def _match_gates(self, absorbed):
+        """Recognise Attention_Block (2DCNN/models/unet_variants.py:67-82) by structure:
+              mul(skip, add(up2x_bilinear(m), LeakyReLU(tconv4x4s2(m) -> 1)))  with
+              m = sigmoid(bn(conv1x1 -> 1 (relu(add(bn(conv1x1 s2 (skip)), bn(conv1x1(gate)))))))
+        and lower it onto b2seg_gate_fwd / b2seg_gate_bwd (csrc/gate.cu).  Every interior tensor must have the gate as its only
+        consumer; channel counts must be 8 * 2^k with dense layouts.  Anything else (the 1D gate, whose transposed-conv branch has a
+        fourth BatchNorm; odd MultiRes widths) keeps the op-by-op lowering.  B2SEG_NO_GATE_FUSION=1 disables the fusion."""
+        self.gates: Dict[int, dict] = {}
+        self.gate_proj: Dict[int, dict] = {}
+        self._acc_floats = 0
+        if self.ndim != 2 or os.environ.get("B2SEG_NO_GATE_FUSION"):
+            return
+        g, cons = self.g, self.cons
 
-        def find(a):
-            while parent[a] != a:
-                parent[a] = parent[parent[a]]
-                a = parent[a]
-            return a
+        def sole(t, op=None):
+            c = cons[id(t)]
+            return len(c) == 1 and t not in g.outputs and (op is None or c[0].op == op)
 
-        def union(a, b):
-            ra, rb = find(id(a)), find(id(b))
-            if ra != rb:
-                parent[ra] = rb
+        def p2(c):
+            return c % 8 == 0 and (c // 8) & (c // 8 - 1) == 0
 
         for n in g.nodes:
-            if n.op in ("bn", "act", "pool", "up", "pow"):
-                union(n, n.inputs[0])
-            elif n.op == "add":
-                for i in n.inputs:
-                    union(n, i)
-            elif n.op == "mul":
-                union(n, n.inputs[0])
-        self._find = find
-        self._cls_concat: Dict[int, List[Node]] = {}
-        for n in g.nodes:
-            if n.op == "concat" and id(n) not in self.absorbed_concat:
-                self._cls_concat.setdefault(find(id(n)), []).append(n)
-        self._segs_memo: Dict[int, List[Tuple[int, int]]] = {}
-        self._cphys_memo: Dict[int, int] = {}
+            if n.op != "mul" or n.inputs[1].C != 1:
+                continue
+            skip, r = n.inputs
+            if r.op != "add" or len(r.inputs) != 2 or not sole(r):
+                continue
+            r1, r2 = r.inputs
+            if not (r1.op == "up" and r1.attrs["size"] == (2, 2) and r1.attrs["interpolation"] == "bilinear" and sole(r1)):
+                continue
+            if not (r2.op == "act" and r2.attrs["fn"] == "LeakyReLU" and sole(r2)):
+                continue
+            tc = r2.inputs[0]
+            if not (tc.op == "tconv" and tc.attrs["filters"] == 1 and tc.attrs["kernel"] == (4, 4) and tc.attrs["strides"] == (2, 2) and sole(tc)):
+                continue
+            m = r1.inputs[0]
+            if tc.inputs[0] is not m or not (m.op == "act" and m.attrs["fn"] == "sigmoid") or m in g.outputs or len(cons[id(m)]) != 2:
+                continue
+            bn3 = m.inputs[0]
+            if not (bn3.op == "bn" and sole(bn3)):
+                continue
+            c3 = bn3.inputs[0]
+            if not (c3.op == "conv" and c3.attrs["filters"] == 1 and c3.attrs["kernel"] == (1, 1) and c3.attrs["strides"] == (1, 1)
+                    and c3.attrs.get("activation") in (None, "linear") and sole(c3)):
+                continue
+            relu = c3.inputs[0]
+            if not (relu.op == "act" and relu.attrs["fn"] in ("relu", "ReLU") and sole(relu)):
+                continue
+            ab = relu.inputs[0]
+            if not (ab.op == "add" and len(ab.inputs) == 2 and sole(ab)):
+                continue
+            bna, bnb = ab.inputs
+            if not (bna.op == "bn" and bnb.op == "bn" and sole(bna) and sole(bnb)):
+                continue
+            ca, cb = bna.inputs[0], bnb.inputs[0]
+            ok = all(c.op == "conv" and c.attrs["kernel"] == (1, 1) and c.attrs.get("activation") in (None, "linear") and sole(c) for c in (ca, cb))
+            if not ok or ca.attrs["strides"] != (2, 2) or cb.attrs["strides"] != (1, 1) or ca.inputs[0] is not skip:
+                continue
+            C, Cs = ca.attrs["filters"], skip.C
+            if cb.attrs["filters"] != C or not p2(C) or not p2(Cs) or C > 4096 or skip.shape[0] % 2 or skip.shape[1] % 2:
+                continue
+            if self._cphys(skip) != Cs or list(self._segs(skip)) != [(0, Cs)] or self._cphys(n) != Cs:
+                continue
+            gate = dict(mul=n, skip=skip, gating=cb.inputs[0], conv_a=ca, conv_b=cb, bn_a=bna, bn_b=bnb, conv3=c3, bn3=bn3, tconv=tc, C=C, Cs=Cs,
+                        interior=[bna, bnb, ab, relu, c3, bn3, m, r1, tc, r2, r])
+            self.gates[id(n)] = gate
+            self.gate_proj[id(ca)] = gate
+            self.gate_proj[id(cb)] = gate
+            for t in gate["interior"]:
+                absorbed.add(id(t))
+        self._acc_floats = sum(4 * gt["C"] + 8 for gt in self.gates.values())   # per gate: sums_a [2][C], sums_b [2][C], sums3 [2] (+ pad)
+
+    def _fwd_gate_proj(self, u):
+        """one of the two 1x1 projections of a fused gate: raw output + column sums added into the gate's accumulators"""
+        n, gt = u["node"], u["gate"]
+        a = n.attrs
+        x = self.phys[id(n.inputs[0])]
+        pe = self.pindex[f"{n.name}/kernel"]
+        pe.meta["segs"] = list(x.segs)
+        assert pe.meta["cin_p"] == x.Cp, (n.name, pe.meta["cin_p"], x.Cp)
+        C = gt["C"]
+        H, W, _ = n.shape
+        z = self.new_act(H, W, C)
+        self.phys[id(n)] = Phys(z, C, [(0, C)])
+        strided = a["strides"] != (1, 1)
+        xin = x.view.parity(0, 0, a["strides"][0], a["strides"][1]) if strided else x.view
+        cd = lw.conv_fprop(xin, self.pwb(pe.key), C, 1, 1, x.Cp, z, bias=self.pw(f"{n.name}/bias"), act=L.ACT_NONE, stats=0)
+        if self.training:
+            which = "sums_a" if n is gt["conv_a"] else "sums_b"
+            cd.stats, cd.stats_atomic = self._gate_acc(gt)[which], 1
+        self.emit(0, L.OP_CONV, cd, n.name, flops=self._conv_flops(n))
+        u["y"] = z
+        self.taps[n.name] = (z, C, "raw")
+
+    def _gate_acc(self, gt):
+        """addresses of the gate's statistics accumulators inside the per-step zeroed region"""
+        if "acc" not in gt:
+            C = gt["C"]
+            base = self._acc_ptr + 4 * self._acc_used
+            gt["acc"] = dict(sums_a=base, sums_b=base + 8 * C, sums3=base + 16 * C)
+            self._acc_used += 4 * C + 8
+        return gt["acc"]
+
+    def _gate_desc(self, gt) -> "L.GateDesc":
+        if "desc" in gt:
+            return gt["desc"]
+        C, Cs = gt["C"], gt["Cs"]
+        h, w, _ = gt["conv_a"].shape
+        d = L.GateDesc()
+        d.za, d.zb = self.phys[id(gt["conv_a"])].view.to_c(), self.phys[id(gt["conv_b"])].view.to_c()
+        if self.training:
+            acc = self._gate_acc(gt)
+            d.sums_a, d.sums_b, d.sums3 = acc["sums_a"], acc["sums_b"], acc["sums3"]
+        for tag, bn in (("a", gt["bn_a"]), ("b", gt["bn_b"]), ("3", gt["bn3"])):
+            setattr(d, "gamma" + ("_" + tag if tag != "3" else "3"), self.pw(f"{bn.name}/gamma"))
+            setattr(d, "beta" + ("_" + tag if tag != "3" else "3"), self.pw(f"{bn.name}/beta"))
+            setattr(d, "mm" + ("_" + tag if tag != "3" else "3"), self.pmov(f"{bn.name}/moving_mean"))
+            setattr(d, "mv" + ("_" + tag if tag != "3" else "3"), self.pmov(f"{bn.name}/moving_variance"))
+        vec = self.alloc(8 * C * 4, "scratch")
+        d.vec_a, d.vec_b = vec, vec + 4 * C * 4
+        c3, tc = gt["conv3"], gt["tconv"]
+        self.pindex[f"{c3.name}/kernel"].meta["segs"] = [(0, C)]
+        self.pindex[f"{tc.name}/kernel"].meta["segs"] = [(0, 1)]
+        assert self.pindex[f"{c3.name}/kernel"].meta["cin_p"] == C and self.pindex[f"{tc.name}/kernel"].meta["taps"] == 16
+        d.w3, d.b3 = self.pw(f"{c3.name}/kernel"), self.pw(f"{c3.name}/bias")
+        d.wt, d.bt, d.wt_stride = self.pw(f"{tc.name}/kernel"), self.pw(f"{tc.name}/bias"), self.pindex[f"{tc.name}/kernel"].meta["cin_p"]
+        d.z = self.alloc(self.N * h * w * 4, "scratch")
+        d.training, d.bessel = (1 if self.training else 0), 1
+        d.eps, d.momentum, d.count = gt["bn3"].attrs["eps"], gt["bn3"].attrs["momentum"], float(self.N * h * w)
+        d.skip = self.phys[id(gt["skip"])].view.to_c()
+        gt["desc"] = d
+        return d
+
+    def _fwd_gate(self, u):
+        n, gt = u["node"], u["gate"]
+        skip = self.phys[id(gt["skip"])]
+        dests = self._dests(n)
+        self.phys[id(n)] = Phys(dests[0], n.C, list(skip.segs))
+        d = L.GateDesc.from_buffer_copy(self._gate_desc(gt))
+        d.out = dests[0].to_c()
+        flops = 0.0
+        self.emit(0, L.OP_GATE_FWD, d, n.name, flops=flops)
+        self._copy_extra(dests[0], dests[1:])
+        self.taps[n.name] = (dests[0], n.C, "act")
+
+    def _bwd_gate(self, u):
+        n, gt = u["node"], u["gate"]
+        dout = self._single_grad(n)
+        if dout is None:
+            return
+        C = gt["C"]
+        h, w, _ = gt["conv_a"].shape
+        d = L.GateDesc.from_buffer_copy(self._gate_desc(gt))
+        dskip = self._grad_like(gt["skip"])
+        dza, dzb = self.new_act(h, w, C, "grad"), self.new_act(h, w, C, "grad")
+        d.dout, d.dskip, d.dza, d.dzb = dout.to_c(), dskip.to_c(), dza.to_c(), dzb.to_c()
+        scr = self.alloc((self.N * 4 * h * w + self.N * h * w + 8 + 3 * C) * 4, "scratch")
+        d.dr, d.g3 = scr, scr + self.N * 4 * h * w * 4
+        d.bsums3 = d.g3 + self.N * h * w * 4
+        d.bsums_ab = d.bsums3 + 32
+        for tag, bn in (("_a", gt["bn_a"]), ("_b", gt["bn_b"]), ("3", gt["bn3"])):
+            setattr(d, "dgamma" + tag, self.pg(f"{bn.name}/gamma"))
+            setattr(d, "dbeta" + tag, self.pg(f"{bn.name}/beta"))
+        d.dw3, d.db3 = self.pg(f"{gt['conv3'].name}/kernel"), self.pg(f"{gt['conv3'].name}/bias")
+        d.dwt, d.dbt = self.pg(f"{gt['tconv'].name}/kernel"), self.pg(f"{gt['tconv'].name}/bias")
+        self.emit(1, L.OP_GATE_BWD, d, f"gate bwd {n.name}")
+        self._add_gsrc(gt["skip"], GSrc(dskip))
+        self._add_gsrc(gt["conv_a"], GSrc(dza))
+        self._add_gsrc(gt["conv_b"], GSrc(dzb))
 
     # ---------------------------------------------------------------------------------------- parameters
     def _add_param(self, key, keras_shape, kind, size, trainable, **meta):
@@ -654,6 +830,11 @@ class Planner:
     # ---------------------------------------------------------------------------------------- build
     def build(self):
         self.bind_arenas()
+        self._acc_used = 0
+        self._acc_ptr = self.alloc(self._acc_floats * 4, "scratch") if (self._acc_floats and self.training) else 0
+        if self._acc_ptr:
+            # BatchNorm sum accumulators of the fused gates: zeroed once per step, then added into by the projection kernels
+            self.emit(0, L.OP_MEMSET, L.MemsetDesc(self._acc_ptr, self._acc_floats * 4), "zero gate statistics")
         self.loss_ptr = self.alloc(LOSS_BUF_FLOATS * 4, "loss")
         if len(self.g.outputs) > MAX_OUTPUTS:
             raise PlanError(f"{len(self.g.outputs)} model outputs (max {MAX_OUTPUTS})")
@@ -739,6 +920,8 @@ class Planner:
         return L.ACT_NONE if node is None else L.ACT_CODES[node.attrs["fn"]]
 
     def _fwd_conv(self, u):
+        if u.get("gate") is not None:
+            return self._fwd_gate_proj(u)
         n: Node = u["node"]
         a = n.attrs
         kh, kw = a["kernel"]
@@ -1487,6 +1670,8 @@ class Planner:
             self.emit(1, L.OP_WGRAD, lw.tconv_wgrad(dz, x.view, self.pg(pe.key), cop, kh, kw, cin_p), f"wgrad {n.name}", flops=self._conv_flops(n))
         else:
             self.emit(1, L.OP_WGRAD, lw.conv_wgrad(dz, xin, self.pg(pe.key), cop, kh, kw, cin_p), f"wgrad {n.name}", flops=self._conv_flops(n))
+        if u.get("gate") is not None:
+            has_bias_grad = False       # the projection feeds a BatchNormalization: its bias gradient is analytically zero (exact 0 emitted)
         if has_bias_grad and bias_rows is not None:
             self.emit(1, L.OP_ROWSUM, L.RowsumDesc(bias_rows[0], bias_rows[1], bias_rows[2], cop, self.pg(f"{n.name}/bias"), 0), f"bias grad {n.name}")
         elif has_bias_grad:

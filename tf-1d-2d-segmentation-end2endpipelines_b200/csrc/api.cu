@@ -148,6 +148,8 @@ static PreparedOp* prepare_any(int op, const void* desc, size_t bytes) {
     B2_CASE(B2SEG_OP_OUTACT_FWD, b2seg_outact_desc, prepare_outact_fwd)
     B2_CASE(B2SEG_OP_OUTACT_BWD, b2seg_outact_desc, prepare_outact_bwd)
     B2_CASE(B2SEG_OP_TARGET_POOL, b2seg_tpool_desc, prepare_target_pool)
+    B2_CASE(B2SEG_OP_GATE_FWD, b2seg_gate_desc, prepare_gate_fwd)
+    B2_CASE(B2SEG_OP_GATE_BWD, b2seg_gate_desc, prepare_gate_bwd)
     default:
       set_error("unknown op code %d", op);
       return nullptr;
@@ -164,7 +166,7 @@ struct b2seg_plan {
 extern "C" {
 
 const char* b2seg_last_error(void) { return b2::g_err; }
-int b2seg_version(void) { return 102; }   // 102: b2seg_loss kinds 4..14 + metrics; 101: eltwise ops 4/5, B2SEG_ACT_TANH, b2seg_outact_fwd/bwd, b2seg_target_pool (additive)
+int b2seg_version(void) { return 103; }   // 103: b2seg_gate_fwd/bwd, b2seg_conv_desc.stats_atomic; 102: b2seg_loss kinds 4..14 + metrics; 101: eltwise ops 4/5, B2SEG_ACT_TANH, b2seg_outact_fwd/bwd, b2seg_target_pool (additive)
 
 // sizeof of each op descriptor: lets a binding verify its struct mirrors without touching the GPU
 int b2seg_sizeof_desc(int op) {
@@ -194,6 +196,8 @@ int b2seg_sizeof_desc(int op) {
     case B2SEG_OP_OUTACT_FWD:
     case B2SEG_OP_OUTACT_BWD: return (int)sizeof(b2seg_outact_desc);
     case B2SEG_OP_TARGET_POOL: return (int)sizeof(b2seg_tpool_desc);
+    case B2SEG_OP_GATE_FWD:
+    case B2SEG_OP_GATE_BWD: return (int)sizeof(b2seg_gate_desc);
     default: return -1;
   }
 }
@@ -236,6 +240,8 @@ B2_ENTRY(b2seg_rowsum, b2seg_rowsum_desc, b2::prepare_rowsum)
 B2_ENTRY(b2seg_outact_fwd, b2seg_outact_desc, b2::prepare_outact_fwd)
 B2_ENTRY(b2seg_outact_bwd, b2seg_outact_desc, b2::prepare_outact_bwd)
 B2_ENTRY(b2seg_target_pool, b2seg_tpool_desc, b2::prepare_target_pool)
+B2_ENTRY(b2seg_gate_fwd, b2seg_gate_desc, b2::prepare_gate_fwd)
+B2_ENTRY(b2seg_gate_bwd, b2seg_gate_desc, b2::prepare_gate_bwd)
 
 int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
   if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");

@@ -50,6 +50,7 @@ struct ConvEpiParams {
   int mul_mode, mul_c;
   int lbw, lbwh;       // log2(bw), log2(bw*bh): tile rows -> pixel coordinates by shifts
   int stats_per_cta;   // 1: one statistics row per CTA (n_tiles == 1), else one per (group, m_tile)
+  int stats_atomic;    // 1: every CTA adds its sums into ONE caller-zeroed row (red.add) instead of writing its own
   unsigned long long* trace;   // debug (B2SEG_TRACE=1): per-tile clock64() stamps of CTA 0, [tile][8]
   int cta_groups;      // G > 1: CTA b only walks the tiles of group b % G (its weights stay resident in shared memory); gridDim.x % G == 0
   FastDiv fd_n_tiles, fd_m_tiles, fd_tiles_w, fd_tiles_h;   // tile index -> coordinates without integer division
@@ -336,9 +337,14 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
             cta_s[c] += s2;
             cta_q[c] += ss2;
           } else if (col0 + et < n_extent) {
-            float* st = p.stats + (size_t)stat_row * 2 * n_extent;
-            st[col0 + et] = s2;
-            st[n_extent + col0 + et] = ss2;
+            if (p.stats_atomic) {
+              atomicAdd(p.stats + col0 + et, s2);
+              atomicAdd(p.stats + n_extent + col0 + et, ss2);
+            } else {
+              float* st = p.stats + (size_t)stat_row * 2 * n_extent;
+              st[col0 + et] = s2;
+              st[n_extent + col0 + et] = ss2;
+            }
           }
         }
       }
@@ -374,12 +380,17 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiParams& p, uint8_t* s
     }
   }
   if (has_stats && per_cta && et < 64) {
-    float* st = p.stats + (size_t)blockIdx.x * 2 * n_extent;
+    float* st = p.stats + (p.stats_atomic ? (size_t)0 : (size_t)blockIdx.x * 2 * n_extent);
 #pragma unroll
     for (int c = 0; c < kChunks; ++c)
       if (c * 64 + et < n_extent) {
-        st[c * 64 + et] = cta_s[c];
-        st[n_extent + c * 64 + et] = cta_q[c];
+        if (p.stats_atomic) {
+          atomicAdd(st + c * 64 + et, cta_s[c]);
+          atomicAdd(st + n_extent + c * 64 + et, cta_q[c]);
+        } else {
+          st[c * 64 + et] = cta_s[c];
+          st[n_extent + c * 64 + et] = cta_q[c];
+        }
       }
   }
 }

@@ -201,6 +201,7 @@ int fill_epi_params(const b2seg_conv_desc* d, int block_n, int bw, int bh, int b
   e->bias = reinterpret_cast<const float*>(d->bias);
   e->act = d->act;
   e->stats = reinterpret_cast<float*>(d->stats);
+  e->stats_atomic = d->stats_atomic;
   e->mul_mode = d->mul_mode;
   if (d->mul_mode != 0) {
     e->mul_ptr = d->mul_view.ptr;
@@ -258,6 +259,7 @@ int conv_num_mtiles(const b2seg_conv_desc* d) {
 
 // rows of the statistics buffer the kernel writes: one per CTA when a CTA always covers the same columns
 int conv_num_stat_rows(const b2seg_conv_desc* d) {
+  if (d->stats_atomic) return 1;
   const int m_tiles = conv_num_mtiles(d);
   const int bn_sel = select_block_n(d);
   const int n_tiles = (d->out[0].C + bn_sel - 1) / bn_sel;

@@ -1,0 +1,513 @@
+// Fused additive attention gate for sm_100a (include/b2seg.h: b2seg_gate_fwd / b2seg_gate_bwd) — the streaming half of
+// 2DCNN/models/unet_variants.py:67-82 Attention_Block.  The two 1x1 projections run on the tcgen05 convolution kernels and add
+// their BatchNorm column sums into [2][C] accumulators (stats_atomic); everything between them and the concat slot is here:
+//
+//   forward   gate_mid_fwd :  scale/shift of both BatchNorms from the sums, c = ReLU(BN(za) + BN(zb)), z = c . w3 + b3 per pixel,
+//                             sum z / sum z^2 (the third BatchNorm's statistics)                     reads za, zb once; writes N*h*w floats
+//             gate_out_fwd :  m = sigmoid(BN(z)); r = bilinear_x2(m) + LeakyReLU(ConvT4x4s2(m));  out = skip * r   reads skip, writes out
+//   backward  gate_out_bwd :  dskip = dout * r,  dr = sum_c dout * skip                              reads dout, skip; writes dskip
+//             gate_low_bwd :  dm = (bilinear^T + ConvT^T LeakyReLU')(dr), g3 = dm m (1 - m), its two BatchNorm sums,
+//                             the 16 + 1 transposed-conv gradients                                    low-resolution maps only
+//             gate_mid_bwd0:  dz3 = BN3'(g3); g = dz3 w3 ReLU'(c): per-channel sums of g, g zhat_a, g zhat_b, dz3 c  reads za, zb
+//             gate_mid_bwd1:  dza, dzb (BatchNorm backward of both branches)                          reads za, zb; writes dza, dzb
+//
+// None of BN(za), BN(zb), their sum, the one-channel maps at either resolution or the resampler is ever written as a tensor: the
+// unfused lowering moved ~14 tensors per gate through HBM in 14 forward and ~25 backward launches.  Grid-wide BatchNorm
+// reductions are the kernel boundaries (three in each direction); no further fusion is possible in training mode.
+#include <math.h>
+
+#include "stream_common.cuh"
+
+namespace b2 {
+
+struct GateK {
+  DView za, zb, skip, out, dout, dskip, dza, dzb;
+  const float *sums_a, *sums_b, *gamma_a, *beta_a, *gamma_b, *beta_b;
+  float *mm_a, *mv_a, *mm_b, *mv_b, *vec_a, *vec_b;
+  const float *w3, *b3;
+  float* z;
+  float* sums3;
+  const float *gamma3, *beta3;
+  float *mm3, *mv3;
+  const float *wt, *bt;
+  int wt_stride;
+  float inv_count, count, eps, momentum;
+  int training, bessel;
+  int C, h, w, npix;      // low-resolution grid, npix = N*h*w
+  float *dr, *g3, *bsums3, *bsums_ab;
+  float *dgamma_a, *dbeta_a, *dgamma_b, *dbeta_b, *dw3, *db3, *dgamma3, *dbeta3, *dwt, *dbt;
+  FastDiv fd_w, fd_h, fd_w2, fd_h2;
+};
+
+// BatchNorm scale / shift / mean / rstd of channel c from column sums (training) or moving statistics (inference)
+__device__ __forceinline__ void bn_coeffs(const GateK& k, const float* sums, const float* gamma, const float* beta, const float* mm, const float* mv,
+                                          int c, float* sc, float* sh, float* mu, float* rs) {
+  float mean, var;
+  if (k.training) {
+    mean = sums[c] * k.inv_count;
+    var = fmaxf(sums[k.C + c] * k.inv_count - mean * mean, 0.f);
+  } else {
+    mean = mm[c]; var = mv[c];
+  }
+  const float r = rsqrtf(var + k.eps);
+  *sc = gamma[c] * r; *sh = beta[c] - mean * gamma[c] * r; *mu = mean; *rs = r;
+}
+__device__ __forceinline__ void update_moving(const GateK& k, float* mm, float* mv, int c, float mean, float var) {
+  const float uv = (k.bessel && k.count > 1.f) ? var * k.count / (k.count - 1.f) : var;
+  mm[c] = mm[c] * k.momentum + mean * (1.f - k.momentum);
+  mv[c] = mv[c] * k.momentum + uv * (1.f - k.momentum);
+}
+
+// ------------------------------------------------------------------------------------------ forward, low resolution
+// One warp handles 32 / LPP pixels at a time: LPP = min(C / 8, 32) lanes per pixel, each lane C / 8 / LPP 8-channel vectors.
+// Shared memory: [5][C] floats (scale_a, shift_a, scale_b, shift_b, w3).
+__global__ void __launch_bounds__(256) gate_mid_fwd_kernel(const GateK k) {
+  pdl_prologue();
+  extern __shared__ float sm[];
+  const int C = k.C;
+  float *s_sa = sm, *s_ta = sm + C, *s_sb = sm + 2 * C, *s_tb = sm + 3 * C, *s_w3 = sm + 4 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc, sh, mu, rs;
+    bn_coeffs(k, k.sums_a, k.gamma_a, k.beta_a, k.mm_a, k.mv_a, c, &sc, &sh, &mu, &rs);
+    s_sa[c] = sc; s_ta[c] = sh;
+    if (blockIdx.x == 0) {
+      k.vec_a[c] = sc; k.vec_a[C + c] = sh; k.vec_a[2 * C + c] = mu; k.vec_a[3 * C + c] = rs;
+      if (k.training) update_moving(k, k.mm_a, k.mv_a, c, mu, fmaxf(k.sums_a[C + c] * k.inv_count - mu * mu, 0.f));
+    }
+    bn_coeffs(k, k.sums_b, k.gamma_b, k.beta_b, k.mm_b, k.mv_b, c, &sc, &sh, &mu, &rs);
+    s_sb[c] = sc; s_tb[c] = sh;
+    if (blockIdx.x == 0) {
+      k.vec_b[c] = sc; k.vec_b[C + c] = sh; k.vec_b[2 * C + c] = mu; k.vec_b[3 * C + c] = rs;
+      if (k.training) update_moving(k, k.mm_b, k.mv_b, c, mu, fmaxf(k.sums_b[C + c] * k.inv_count - mu * mu, 0.f));
+    }
+    s_w3[c] = k.w3[c];
+  }
+  __syncthreads();
+  const int vpp = C >> 3;
+  const int lpp = vpp < 32 ? vpp : 32;
+  const int vpl = vpp / lpp;
+  const int ppw = 32 / lpp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / lpp, lv = lane % lpp;
+  const float b3 = k.b3[0];
+  float acc_s = 0.f, acc_q = 0.f;
+  const int groups = (k.npix + ppw - 1) / ppw;
+  for (int g = blockIdx.x * 8 + warp; g < groups; g += gridDim.x * 8) {
+    const int pix = g * ppw + sub;
+    float dot = 0.f;
+    if (pix < k.npix) {
+      const uint32_t q = fast_div((uint32_t)pix, k.fd_w);
+      const int x = pix - (int)q * k.w;
+      const uint32_t n = fast_div(q, k.fd_h);
+      const int y = (int)q - (int)n * k.h;
+      for (int i = 0; i < vpl; ++i) {
+        const int c0 = (lv + i * lpp) * 8;
+        float a[8], b[8];
+        load8(vaddr(k.za, (int)n, y, x, c0), a);
+        load8(vaddr(k.zb, (int)n, y, x, c0), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float c = fmaxf(fmaf(a[e], s_sa[c0 + e], s_ta[c0 + e]) + fmaf(b[e], s_sb[c0 + e], s_tb[c0 + e]), 0.f);
+          dot = fmaf(c, s_w3[c0 + e], dot);
+        }
+      }
+    }
+    for (int off = lpp >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if (lv == 0 && pix < k.npix) {
+      const float z = dot + b3;
+      k.z[pix] = z;
+      acc_s += z; acc_q = fmaf(z, z, acc_q);
+    }
+  }
+  if (k.training) {
+    __shared__ float red[2][8];
+    for (int off = 16; off > 0; off >>= 1) {
+      acc_s += __shfl_xor_sync(0xffffffffu, acc_s, off);
+      acc_q += __shfl_xor_sync(0xffffffffu, acc_q, off);
+    }
+    if (lane == 0) { red[0][warp] = acc_s; red[1][warp] = acc_q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f, q = 0.f;
+      for (int i = 0; i < 8; ++i) { s += red[0][i]; q += red[1][i]; }
+      atomicAdd(k.sums3, s);
+      atomicAdd(k.sums3 + 1, q);
+    }
+  }
+}
+
+// third BatchNorm: (scale, shift, mean, rstd) from the two sums (training) or the moving statistics
+__device__ __forceinline__ void bn3_coeffs(const GateK& k, float* sc, float* sh, float* mu, float* rs) {
+  float mean, var;
+  if (k.training) {
+    mean = k.sums3[0] * k.inv_count;
+    var = fmaxf(k.sums3[1] * k.inv_count - mean * mean, 0.f);
+  } else {
+    mean = k.mm3[0]; var = k.mv3[0];
+  }
+  const float r = rsqrtf(var + k.eps);
+  *sc = k.gamma3[0] * r; *sh = k.beta3[0] - mean * k.gamma3[0] * r; *mu = mean; *rs = r;
+}
+
+struct Resampler {
+  float r;      // bilinear + LeakyReLU(transposed conv)
+  float lk;     // LeakyReLU'(pre-activation of the transposed conv): 1 or 0.3
+};
+// m(y, x) = sigmoid(z * sc + sh) of image n with edge clamp (bilinear) or zero outside (transposed conv) handled by the caller
+__device__ __forceinline__ float gate_m(const GateK& k, int n, int y, int x, float sc, float sh) {
+  return 1.f / (1.f + __expf(-fmaf(k.z[(n * k.h + y) * k.w + x], sc, sh)));
+}
+// resampler value at high-resolution pixel (oy, ox) of image n.
+//   bilinear x2, half-pixel centres, edge clamp (tf.image.resize): even o = 2i: 0.25 m[i-1] + 0.75 m[i]; odd o = 2i+1: 0.75 m[i] + 0.25 m[i+1]
+//   Conv2DTranspose(4x4, s2, 'same') == ConvTranspose2d(k4, s2, p1): o = 2i - 1 + ky: even o: (ky=1, i), (ky=3, i-1); odd o: (ky=2, i), (ky=0, i+1)
+__device__ __forceinline__ Resampler gate_resample(const GateK& k, int n, int oy, int ox, float sc, float sh, const float (&wt)[16], float bt) {
+  const int iy = oy >> 1, ix = ox >> 1;
+  const int py = oy & 1, px = ox & 1;
+  const int y2 = py ? iy + 1 : iy - 1, x2 = px ? ix + 1 : ix - 1;      // the second source row / column
+  const bool vy2 = y2 >= 0 && y2 < k.h, vx2 = x2 >= 0 && x2 < k.w;
+  const int yc = vy2 ? y2 : iy, xc = vx2 ? x2 : ix;                     // clamped (bilinear)
+  const float m00 = gate_m(k, n, iy, ix, sc, sh);
+  const float m01 = gate_m(k, n, iy, xc, sc, sh);
+  const float m10 = gate_m(k, n, yc, ix, sc, sh);
+  const float m11 = gate_m(k, n, yc, xc, sc, sh);
+  const float bil = 0.75f * (0.75f * m00 + 0.25f * m01) + 0.25f * (0.75f * m10 + 0.25f * m11);
+  const int ky1 = py ? 2 : 1, ky2 = py ? 0 : 3, kx1 = px ? 2 : 1, kx2 = px ? 0 : 3;
+  float pre = bt + m00 * wt[ky1 * 4 + kx1];
+  if (vx2) pre = fmaf(m01, wt[ky1 * 4 + kx2], pre);
+  if (vy2) pre = fmaf(m10, wt[ky2 * 4 + kx1], pre);
+  if (vy2 && vx2) pre = fmaf(m11, wt[ky2 * 4 + kx2], pre);
+  Resampler o;
+  o.lk = pre > 0.f ? 1.f : 0.3f;
+  o.r = bil + pre * o.lk;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------ forward / backward, high resolution
+// Block = 256 threads = one segment of GP pixels of one high-resolution row; r per pixel is computed once into shared memory,
+// then the (pixel, 8-channel vector) pairs are streamed.  BWD: dskip = dout * r and dr = sum_c dout * skip (per-pixel reduction).
+constexpr int kGateSeg = 64;
+template <bool BWD>
+__global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
+  pdl_prologue();
+  __shared__ float s_r[kGateSeg];
+  __shared__ float s_dr[kGateSeg];
+  float sc, sh, mu, rs;
+  bn3_coeffs(k, &sc, &sh, &mu, &rs);
+  float wt[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) wt[i] = k.wt[i * k.wt_stride];
+  const float bt = k.bt[0];
+  const int W2 = 2 * k.w, H2 = 2 * k.h;
+  const int segs_per_row = (W2 + kGateSeg - 1) / kGateSeg;
+  const int total_segs = k.skip.N * H2 * segs_per_row;
+  const int vpp = k.skip.C >> 3;
+  if (!BWD && blockIdx.x == 0 && threadIdx.x == 0 && k.training) {
+    const float var = fmaxf(k.sums3[1] * k.inv_count - mu * mu, 0.f);
+    const float uv = (k.bessel && k.count > 1.f) ? var * k.count / (k.count - 1.f) : var;
+    k.mm3[0] = k.mm3[0] * k.momentum + mu * (1.f - k.momentum);
+    k.mv3[0] = k.mv3[0] * k.momentum + uv * (1.f - k.momentum);
+  }
+  for (int seg = blockIdx.x; seg < total_segs; seg += gridDim.x) {
+    const uint32_t rowi = (uint32_t)seg / (uint32_t)segs_per_row;
+    const int x0 = (seg - (int)rowi * segs_per_row) * kGateSeg;
+    const uint32_t n = fast_div(rowi, k.fd_h2);
+    const int oy = (int)rowi - (int)n * H2;
+    const int npx = W2 - x0 < kGateSeg ? W2 - x0 : kGateSeg;
+    __syncthreads();
+    if ((int)threadIdx.x < npx) {
+      s_r[threadIdx.x] = gate_resample(k, (int)n, oy, x0 + threadIdx.x, sc, sh, wt, bt).r;
+      if (BWD) s_dr[threadIdx.x] = 0.f;
+    }
+    __syncthreads();
+    const int work = npx * vpp;
+    for (int i = threadIdx.x; i < work; i += 256) {
+      const int p = i / vpp, v = i - p * vpp;
+      float s[8], o[8];
+      load8(vaddr(k.skip, (int)n, oy, x0 + p, v * 8), s);
+      const float r = s_r[p];
+      if (!BWD) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = s[e] * r;
+        store8(vaddr(k.out, (int)n, oy, x0 + p, v * 8), o);
+      } else {
+        float d[8];
+        load8(vaddr(k.dout, (int)n, oy, x0 + p, v * 8), d);
+        float part = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { o[e] = d[e] * r; part = fmaf(d[e], s[e], part); }
+        store8(vaddr(k.dskip, (int)n, oy, x0 + p, v * 8), o);
+        // lanes holding the same pixel are adjacent (vpp is a power of two): reduce within the warp first
+        const int span = vpp < 32 ? vpp : 32;
+        for (int off = span >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if ((threadIdx.x & (span - 1)) == 0) atomicAdd(&s_dr[p], part);
+      }
+    }
+    if (BWD) {
+      __syncthreads();
+      if ((int)threadIdx.x < npx) k.dr[((size_t)n * H2 + oy) * W2 + x0 + threadIdx.x] = s_dr[threadIdx.x];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward, low-resolution maps
+// One thread per low-resolution pixel: dm = adjoint of (bilinear + ConvT with LeakyReLU') applied to dr over the 4x4 high-resolution
+// window this pixel feeds; g3 = dm * m * (1 - m); block sums of g3, g3 * zhat3 and of the 16 + 1 transposed-conv gradients.
+__global__ void __launch_bounds__(256) gate_low_bwd_kernel(const GateK k) {
+  pdl_prologue();
+  float sc, sh, mu, rs;
+  bn3_coeffs(k, &sc, &sh, &mu, &rs);
+  float wt[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) wt[i] = k.wt[i * k.wt_stride];
+  const float bt = k.bt[0];
+  const int W2 = 2 * k.w, H2 = 2 * k.h;
+  float acc[19];      // [0..15] dwt, [16] dbt, [17] sum g3, [18] sum g3 * zhat3
+#pragma unroll
+  for (int i = 0; i < 19; ++i) acc[i] = 0.f;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < k.npix; pix += gridDim.x * blockDim.x) {
+    const uint32_t q = fast_div((uint32_t)pix, k.fd_w);
+    const int x = pix - (int)q * k.w;
+    const uint32_t n = fast_div(q, k.fd_h);
+    const int y = (int)q - (int)n * k.h;
+    const float zv = k.z[pix];
+    const float m = 1.f / (1.f + __expf(-fmaf(zv, sc, sh)));
+    float dm = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int oy = 2 * y - 1 + ky;
+      if (oy < 0 || oy >= H2) continue;
+      // bilinear weight of m[y] in output row oy: rows 2y, 2y+1 take 0.75; rows 2y-1, 2y+2 take 0.25; the clamped edge rows
+      // (oy = 0 from y = 0, oy = H2-1 from y = h-1) take the clamped source's share as well
+      float wy = (ky == 1 || ky == 2) ? 0.75f : 0.25f;
+      if ((oy == 0 && y == 0) || (oy == H2 - 1 && y == k.h - 1)) wy = 1.f;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ox = 2 * x - 1 + kx;
+        if (ox < 0 || ox >= W2) continue;
+        float wx = (kx == 1 || kx == 2) ? 0.75f : 0.25f;
+        if ((ox == 0 && x == 0) || (ox == W2 - 1 && x == k.w - 1)) wx = 1.f;
+        const float d = k.dr[((size_t)n * H2 + oy) * W2 + ox];
+        const float lk = gate_resample(k, (int)n, oy, ox, sc, sh, wt, bt).lk;
+        dm = fmaf(d, fmaf(lk, wt[ky * 4 + kx], wy * wx), dm);
+        acc[ky * 4 + kx] = fmaf(d * lk, m, acc[ky * 4 + kx]);
+        if ((ky == 1 || ky == 2) && (kx == 1 || kx == 2)) acc[16] = fmaf(d, lk, acc[16]);   // each high-resolution pixel counted once (by its 2x2 owner)
+      }
+    }
+    const float g = dm * m * (1.f - m);
+    k.g3[pix] = g;
+    acc[17] += g;
+    acc[18] = fmaf(g, (zv - mu) * rs, acc[18]);
+  }
+  __shared__ float red[19][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 19; ++i) {
+    float v = acc[i];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 19) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += red[threadIdx.x][i];
+    if (threadIdx.x < 16) atomicAdd(k.dwt + threadIdx.x * k.wt_stride, v);
+    else if (threadIdx.x == 16) atomicAdd(k.dbt, v);
+    else atomicAdd(k.bsums3 + (threadIdx.x - 17), v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward, projections
+// Thread = one 8-channel vector (tcv) of a strided set of pixels (trow); blockIdx.x = vector group, blockIdx.y strides the pixels.
+// PASS 0: per-channel sums {g, g zhat_a, g zhat_b, dz3 c}; PASS 1: dza, dzb.
+template <int PASS>
+__global__ void __launch_bounds__(256) gate_mid_bwd_kernel(const GateK k, int cvb) {
+  pdl_prologue();
+  const int C = k.C;
+  const int tcv = threadIdx.x % cvb, trow = threadIdx.x / cvb, rows = 256 / cvb;
+  const int c0 = (blockIdx.x * cvb + tcv) * 8;
+  float sc3, sh3, mu3, rs3;
+  bn3_coeffs(k, &sc3, &sh3, &mu3, &rs3);
+  const float mg = k.bsums3[0] * k.inv_count, mgz = k.bsums3[1] * k.inv_count;     // mean g3, mean g3 zhat3
+  float sa[8], ta[8], sb[8], tb[8], w3[8], ma[8], ra[8], mb[8], rb[8], cg[8], cga[8], cgb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    sa[e] = k.vec_a[c]; ta[e] = k.vec_a[C + c]; ma[e] = k.vec_a[2 * C + c]; ra[e] = k.vec_a[3 * C + c];
+    sb[e] = k.vec_b[c]; tb[e] = k.vec_b[C + c]; mb[e] = k.vec_b[2 * C + c]; rb[e] = k.vec_b[3 * C + c];
+    w3[e] = k.w3[c];
+    if (PASS == 1) {
+      cg[e] = k.bsums_ab[c] * k.inv_count; cga[e] = k.bsums_ab[C + c] * k.inv_count; cgb[e] = k.bsums_ab[2 * C + c] * k.inv_count;
+    }
+  }
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+  float acc_db3 = 0.f;
+  for (int pix = blockIdx.y * rows + trow; pix < k.npix; pix += gridDim.y * rows) {
+    const uint32_t q = fast_div((uint32_t)pix, k.fd_w);
+    const int x = pix - (int)q * k.w;
+    const uint32_t n = fast_div(q, k.fd_h);
+    const int y = (int)q - (int)n * k.h;
+    const float zh3 = (k.z[pix] - mu3) * rs3;
+    const float dz3 = sc3 * (k.g3[pix] - mg - zh3 * mgz);
+    float a[8], b[8];
+    load8(vaddr(k.za, (int)n, y, x, c0), a);
+    load8(vaddr(k.zb, (int)n, y, x, c0), b);
+    if (PASS == 0) {
+      if (blockIdx.x == 0 && tcv == 0) acc_db3 += dz3;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float c = fmaf(a[e], sa[e], ta[e]) + fmaf(b[e], sb[e], tb[e]);
+        const float g = c > 0.f ? dz3 * w3[e] : 0.f;
+        acc[0][e] += g;
+        acc[1][e] = fmaf(g, (a[e] - ma[e]) * ra[e], acc[1][e]);
+        acc[2][e] = fmaf(g, (b[e] - mb[e]) * rb[e], acc[2][e]);
+        acc[3][e] = fmaf(dz3, fmaxf(c, 0.f), acc[3][e]);
+      }
+    } else {
+      float da[8], db[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float c = fmaf(a[e], sa[e], ta[e]) + fmaf(b[e], sb[e], tb[e]);
+        const float g = c > 0.f ? dz3 * w3[e] : 0.f;
+        da[e] = sa[e] * (g - cg[e] - (a[e] - ma[e]) * ra[e] * cga[e]);
+        db[e] = sb[e] * (g - cg[e] - (b[e] - mb[e]) * rb[e] * cgb[e]);
+      }
+      store8(vaddr(k.dza, (int)n, y, x, c0), da);
+      store8(vaddr(k.dzb, (int)n, y, x, c0), db);
+    }
+  }
+  if (PASS == 0) {
+    extern __shared__ float red[];      // [256][33]
+    float* mine = red + threadIdx.x * 33;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mine[a * 8 + e] = acc[a][e];
+    mine[32] = acc_db3;
+    __syncthreads();
+    // thread t < cvb * 32 sums slot (t % 32) of vector (t / 32) over the rows
+    for (int t = threadIdx.x; t < cvb * 32; t += 256) {
+      const int v = t >> 5, slot = t & 31;
+      float s = 0.f;
+      for (int r = 0; r < rows; ++r) s += red[(r * cvb + v) * 33 + slot];
+      const int c = (blockIdx.x * cvb + v) * 8 + (slot & 7);
+      const int which = slot >> 3;
+      if (which < 3) atomicAdd(k.bsums_ab + which * C + c, s);
+      else atomicAdd(k.dw3 + c, s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float s = 0.f;
+      for (int r = 0; r < rows; ++r) s += red[(r * cvb) * 33 + 32];
+      atomicAdd(k.db3, s);
+    }
+  } else if (blockIdx.y == 0 && trow == 0) {
+    // BatchNorm parameter gradients of the two branches and of the one-channel map (plain stores: each belongs to this gate only)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      k.dbeta_a[c] = k.bsums_ab[c]; k.dgamma_a[c] = k.bsums_ab[C + c];
+      k.dbeta_b[c] = k.bsums_ab[c]; k.dgamma_b[c] = k.bsums_ab[2 * C + c];
+    }
+    if (blockIdx.x == 0 && tcv == 0) { k.dbeta3[0] = k.bsums3[0]; k.dgamma3[0] = k.bsums3[1]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int fill_gate(const b2seg_gate_desc* d, GateK* k, bool bwd) {
+  memset(k, 0, sizeof(*k));
+  const b2seg_view& za = d->za;
+  if (za.C % 8 || !pow2(za.C / 8) || za.C > 4096) { set_error("gate: projection channels %d (need 8 * 2^k <= 4096)", za.C); return -1; }
+  if (d->zb.N != za.N || d->zb.H != za.H || d->zb.W != za.W || d->zb.C != za.C) { set_error("gate: projection shapes differ"); return -1; }
+  if (d->skip.N != za.N || d->skip.H != 2 * za.H || d->skip.W != 2 * za.W || d->skip.C % 8 || !pow2(d->skip.C / 8)) {
+    set_error("gate: skip (%d,%d,%d,%d) must be (N, 2h, 2w, 8 * 2^k) for projections (%d,%d,%d)", d->skip.N, d->skip.H, d->skip.W, d->skip.C, za.N, za.H, za.W);
+    return -1;
+  }
+  if ((long long)za.N * za.H * za.W * 4 >= (1ll << 31)) { set_error("gate: map too large"); return -1; }
+  if (!d->w3 || !d->b3 || !d->z || !d->wt || !d->bt || !d->gamma3 || !d->beta3 || !d->mm3 || !d->mv3 || !d->vec_a || !d->vec_b) { set_error("gate: null parameter"); return -1; }
+  if (d->training && (!d->sums_a || !d->sums_b || !d->sums3)) { set_error("gate: training needs the statistics accumulators"); return -1; }
+  k->za = dv(d->za); k->zb = dv(d->zb); k->skip = dv(d->skip); k->out = dv(d->out);
+  k->dout = dv(d->dout); k->dskip = dv(d->dskip); k->dza = dv(d->dza); k->dzb = dv(d->dzb);
+#define P(f) k->f = reinterpret_cast<decltype(k->f)>(d->f)
+  P(sums_a); P(sums_b); P(gamma_a); P(beta_a); P(gamma_b); P(beta_b); P(mm_a); P(mv_a); P(mm_b); P(mv_b); P(vec_a); P(vec_b);
+  P(w3); P(b3); P(z); P(sums3); P(gamma3); P(beta3); P(mm3); P(mv3); P(wt); P(bt);
+  P(dr); P(g3); P(bsums3); P(bsums_ab); P(dgamma_a); P(dbeta_a); P(dgamma_b); P(dbeta_b); P(dw3); P(db3); P(dgamma3); P(dbeta3); P(dwt); P(dbt);
+#undef P
+  k->wt_stride = d->wt_stride;
+  k->count = (float)d->count; k->inv_count = (float)(1.0 / d->count); k->eps = d->eps; k->momentum = d->momentum;
+  k->training = d->training; k->bessel = d->bessel;
+  k->C = za.C; k->h = za.H; k->w = za.W; k->npix = za.N * za.H * za.W;
+  k->fd_w = make_fastdiv((uint32_t)za.W); k->fd_h = make_fastdiv((uint32_t)za.H);
+  k->fd_w2 = make_fastdiv((uint32_t)(2 * za.W)); k->fd_h2 = make_fastdiv((uint32_t)(2 * za.H));
+  if (!bwd) {
+    if (!d->out.ptr || d->out.C != d->skip.C || d->out.H != d->skip.H || d->out.W != d->skip.W) { set_error("gate: bad output view"); return -1; }
+  } else {
+    if (!d->training) { set_error("gate: backward of an inference plan"); return -1; }
+    if (!d->dout.ptr || !d->dskip.ptr || !d->dza.ptr || !d->dzb.ptr || !d->dr || !d->g3 || !d->bsums3 || !d->bsums_ab || !d->dgamma_a || !d->dbeta_a ||
+        !d->dgamma_b || !d->dbeta_b || !d->dw3 || !d->db3 || !d->dgamma3 || !d->dbeta3 || !d->dwt || !d->dbt) { set_error("gate: null backward pointer"); return -1; }
+  }
+  return 0;
+}
+
+struct GateLaunch : PreparedOp {
+  GateK k;
+  bool bwd;
+  int launch(cudaStream_t s) override {
+    const int sms = num_sms();
+    const int W2 = 2 * k.w, H2 = 2 * k.h;
+    const int segs = k.skip.N * H2 * ((W2 + kGateSeg - 1) / kGateSeg);
+    const int grid_out = segs < sms * 8 ? segs : sms * 8;
+    const int vpp = k.C / 8;
+    if (!bwd) {
+      const int lpp = vpp < 32 ? vpp : 32, ppw = 32 / lpp;
+      const int groups = (k.npix + ppw - 1) / ppw;
+      int grid = (groups + 7) / 8;
+      if (grid > sms * 4) grid = sms * 4;
+      const int smem = 5 * k.C * 4;
+      if (smem > 48 * 1024) B2_CUDA_OK(cudaFuncSetAttribute(gate_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      B2_CUDA_OK(launch_k(gate_mid_fwd_kernel, dim3(grid), dim3(256), smem, s, k));
+      B2_CUDA_OK(launch_k(gate_out_kernel<false>, dim3(grid_out), dim3(256), 0, s, k));
+    } else {
+      B2_CUDA_OK(cudaMemsetAsync(k.bsums3, 0, 8, s));
+      B2_CUDA_OK(cudaMemsetAsync(k.bsums_ab, 0, (size_t)3 * k.C * 4, s));
+      B2_CUDA_OK(launch_k(gate_out_kernel<true>, dim3(grid_out), dim3(256), 0, s, k));
+      int grid_low = (k.npix + 255) / 256;
+      if (grid_low > sms * 4) grid_low = sms * 4;
+      B2_CUDA_OK(launch_k(gate_low_bwd_kernel, dim3(grid_low), dim3(256), 0, s, k));
+      const int cvb = vpp < 32 ? vpp : 32, rows = 256 / cvb;
+      const int gx = vpp / cvb;
+      int gy = (k.npix + rows - 1) / rows;
+      const int cap = (sms * 4 + gx - 1) / gx;
+      if (gy > cap) gy = cap;
+      static bool attr_set = false;
+      if (!attr_set) {
+        B2_CUDA_OK(cudaFuncSetAttribute(gate_mid_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * 4));
+        attr_set = true;
+      }
+      B2_CUDA_OK(launch_k(gate_mid_bwd_kernel<0>, dim3(gx, gy), dim3(256), 256 * 33 * 4, s, k, cvb));
+      B2_CUDA_OK(launch_k(gate_mid_bwd_kernel<1>, dim3(gx, gy), dim3(256), 0, s, k, cvb));
+    }
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int num_launches() const override { return bwd ? 4 : 2; }
+};
+
+PreparedOp* prepare_gate_fwd(const b2seg_gate_desc* d) {
+  auto* L = new GateLaunch();
+  L->bwd = false;
+  if (fill_gate(d, &L->k, false) != 0) { delete L; return nullptr; }
+  return L;
+}
+PreparedOp* prepare_gate_bwd(const b2seg_gate_desc* d) {
+  auto* L = new GateLaunch();
+  L->bwd = true;
+  if (fill_gate(d, &L->k, true) != 0) { delete L; return nullptr; }
+  return L;
+}
+
+}  // namespace b2

@@ -294,8 +294,13 @@ PreparedOp* prepare_colstats(const b2seg_colstats_desc* d) {
 }
 
 // ------------------------------------------------------------------------------------------ ConvLSTM gates (T = 1)
-__device__ __forceinline__ float hard_sigmoid(float x) { return fminf(fmaxf(0.2f * x + 0.5f, 0.f), 1.f); }
-__device__ __forceinline__ float hard_sigmoid_grad(float x) { const float t = 0.2f * x + 0.5f; return (t >= 0.f && t <= 1.f) ? 0.2f : 0.f; }
+// Keras-2 hard_sigmoid = clip(x * 0.2 + 0.5, 0, 1) as separate float32 ops; clip_by_value passes the gradient on [0, 1] inclusive.
+// The multiply and the add must NOT contract into an FMA: gate pre-activations are stored in bf16, so x = -2.5 exactly is common
+// (~3e-4 of all elements), and fma(0.2f, -2.5f, 0.5f) = -7.5e-9 < 0 puts it outside the clip range while mul-then-add gives exactly 0
+// (inside): the teacher-forced gradient check measured 2-4 % rel-L2 on the input / output gates from this alone.
+__device__ __forceinline__ float hard_sigmoid_lin(float x) { return __fadd_rn(__fmul_rn(0.2f, x), 0.5f); }
+__device__ __forceinline__ float hard_sigmoid(float x) { return fminf(fmaxf(hard_sigmoid_lin(x), 0.f), 1.f); }
+__device__ __forceinline__ float hard_sigmoid_grad(float x) { const float t = hard_sigmoid_lin(x); return (t >= 0.f && t <= 1.f) ? 0.2f : 0.f; }
 struct LstmK { DView z, h, dh, dz; int F; };
 template <bool BWD>
 __global__ void __launch_bounds__(256) lstm_kernel(LstmK k) {
