@@ -181,6 +181,11 @@ typedef struct b2seg_head_desc {
   b2seg_view dx;         /* bf16 (backward output) */
   uint64_t dw, db;       /* fp32 outputs */
   uint64_t logits;      /* optional fp32 [N,H',W',cout] pre-activation output of the forward */
+  /* forward, optional: x is the RAW output of the last Conv_Block and the head consumes bn_act(x * bn_scale + bn_shift) computed on the
+   * fly (fp32 [C] each; bn_act NONE / RELU / LEAKY).  With the head's backward folded into that layer's BatchNorm backward
+   * (b2seg_gradsrc kind 2) the activated tensor of the last layer is never written or read (unet_variants.py:1104-1106). */
+  uint64_t bn_scale, bn_shift;
+  int32_t bn_act;
 } b2seg_head_desc;
 
 /* Loss value and backward seed dL/dlogits of one model output (tf.keras.losses.* as listed by 2DCNN/utils/tf_losses.py:8-46;
@@ -260,6 +265,9 @@ typedef struct b2seg_poolbwd_desc {
 typedef struct b2seg_cast_desc { /* fp32 NHWC input -> bf16 view (channel-padded) */
   uint64_t src; int32_t N, H, W, C;
   b2seg_view out;
+  /* kh * kw > 1: K-packed im2col, out(n,h,w,(i*kw+j)*C + c) = src(n, h+i-(kh-1)/2, w+j-(kw-1)/2, c) (zero outside): a kh x kw
+   * 'same' convolution of the thin network input becomes a 1x1 convolution over out (one tensor-core tap instead of kh*kw) */
+  int32_t kh, kw;
 } b2seg_cast_desc;
 
 typedef struct b2seg_colsum_desc { /* bias gradient: db[c] = sum over pixels of g (bf16 view) */

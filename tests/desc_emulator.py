@@ -302,6 +302,8 @@ def _head_geom(d):
 def emu_head_fwd(mem, d):
     st, Ho, Wo = _head_geom(d)
     x = mem.gather_view(d.x)[:, ::st, ::st]
+    if d.bn_scale:          # BatchNorm + activation of the last Conv_Block applied by the head itself
+        x = _act(x * mem.f32(d.bn_scale, d.x.C) + mem.f32(d.bn_shift, d.x.C), d.bn_act)
     w = mem.f32(d.w, d.x.C * d.cout).view(d.x.C, d.cout)
     z = x @ w + mem.f32(d.b, d.cout)
     n = z.numel()
@@ -461,7 +463,15 @@ def emu_eltwise(mem, d):
 def emu_cast(mem, d):
     src = mem.f32(d.src, d.N * d.H * d.W * d.C).view(d.N, d.H, d.W, d.C)
     o = torch.zeros(d.N, d.H, d.W, d.out.C, dtype=torch.float64)
-    o[..., :d.C] = src
+    if d.kh * d.kw > 1:          # K-packed im2col of the input
+        ph, pw = (d.kh - 1) // 2, (d.kw - 1) // 2
+        pad = torch.nn.functional.pad(src, (0, 0, pw, d.kw - 1 - pw, ph, d.kh - 1 - ph))
+        for i in range(d.kh):
+            for j in range(d.kw):
+                t = i * d.kw + j
+                o[..., t * d.C:(t + 1) * d.C] = pad[:, i:i + d.H, j:j + d.W, :]
+    else:
+        o[..., :d.C] = src
     mem.write_view(d.out, o)
 
 

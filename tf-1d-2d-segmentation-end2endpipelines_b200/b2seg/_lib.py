@@ -89,7 +89,8 @@ class AdamDesc(C.Structure):
 class HeadDesc(C.Structure):
     _fields_ = [("x", View), ("w", C.c_uint64), ("b", C.c_uint64), ("cout", C.c_int32), ("act", C.c_int32),
                 ("stride", C.c_int32), ("y", C.c_uint64), ("dlogits", C.c_uint64), ("dx", View),
-                ("dw", C.c_uint64), ("db", C.c_uint64), ("logits", C.c_uint64)]
+                ("dw", C.c_uint64), ("db", C.c_uint64), ("logits", C.c_uint64),
+                ("bn_scale", C.c_uint64), ("bn_shift", C.c_uint64), ("bn_act", C.c_int32)]
 
 
 class LossDesc(C.Structure):
@@ -125,7 +126,7 @@ class PoolBwdDesc(C.Structure):
 
 class CastDesc(C.Structure):
     _fields_ = [("src", C.c_uint64), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
-                ("out", View)]
+                ("out", View), ("kh", C.c_int32), ("kw", C.c_int32)]
 
 
 class ColsumDesc(C.Structure):

@@ -199,6 +199,7 @@ class Planner:
         self.act_bytes = 0
         self.op_info: Dict[Tuple[int, int], dict] = {}
         self._grad_touched = set()
+        self.head_prologue: Dict[int, Tuple[int, int, int]] = {}   # tensor id -> (scale ptr, shift ptr, activation) applied by its head
         self.pool_routing: Dict[str, str] = {}   # max-pool layer -> "recomputed" (see _bwd_conv); absent = routed on the stored tensor
         self.grad_ready: Dict[str, int] = {}   # param key -> number of backward ops after which its gradient is final
         self._analyse()
@@ -707,6 +708,21 @@ class Planner:
         self.pindex[key] = e
         return e
 
+    def _im2col_of(self, n: Node):
+        """(kh, kw, Cin) when convolution n reads the network input through a K-packed im2col copy (a 1x1 convolution over kh*kw*Cin
+        channels: ONE tensor-core tap instead of kh*kw taps of 8 mostly-padding channels), else None"""
+        if os.environ.get("B2SEG_NO_IM2COL") or n.op != "conv" or n.inputs[0].op != "input" or id(n) in self.gate_proj:
+            return None
+        a = n.attrs
+        kh, kw = a["kernel"]
+        cin = n.inputs[0].C
+        if kh * kw < 2 or a["strides"] != (1, 1) or a["padding"] != "same" or kh * kw * cin > 64:
+            return None
+        u = self.unit_of_out.get(id(n))
+        if u is not None and u["kind"] == "head":
+            return None
+        return kh, kw, cin
+
     def _layout_params(self):
         """Assign arena offsets in layer creation order.  Input-channel maps are resolved at emission time."""
         specs = {}
@@ -721,6 +737,13 @@ class Planner:
                 if u is not None and u["kind"] == "head":
                     self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], "head", cin_p * co, True, cin_p=cin_p, cout=co)
                     self._add_param(f"{n.name}/bias", (co,), "vec", co, True, C=co)
+                elif self._im2col_of(n) is not None:
+                    ikh, ikw, icin = self._im2col_of(n)
+                    cop, osegs = self._cphys(n), self._segs(n)
+                    kp = ceil8(ikh * ikw * icin)
+                    self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], "conv", cop * kp, True, cout=co, cout_p=cop, taps=1, cin_p=kp,
+                                    kh=1, kw=1, out_segs=osegs, segs=[(0, ikh * ikw * icin)], im2col=(ikh, ikw, icin))
+                    self._add_param(f"{n.name}/bias", (co,), "vec", cop, True, C=co, vsegs=osegs, Cp=cop)
                 else:
                     cop, osegs = self._cphys(n), self._segs(n)   # the conv produces the layout of its element-wise class
                     self._add_param(f"{n.name}/kernel", specs[(n.name, "kernel")][0], n.op, cop * kh * kw * cin_p, True,
@@ -912,9 +935,18 @@ class Planner:
         n = u["node"]
         H, W, C = n.shape
         self.input_ptr = self.alloc(self.N * H * W * C * 4, "input")
-        dests = self._dests(n)
-        self.emit(0, L.OP_CAST, L.CastDesc(self.input_ptr, self.N, H, W, C, dests[0].to_c()), n.name)
-        self._copy_extra(dests[0], dests[1:])
+        self._im2col_views: Dict[Tuple[int, int], TView] = {}
+        windows = [self._im2col_of(c) for c in self.cons[id(n)]]
+        for win in windows:
+            if win is not None and win[:2] not in self._im2col_views:
+                kh, kw, _ = win
+                col = self.new_act(H, W, ceil8(kh * kw * C))
+                self.emit(0, L.OP_CAST, L.CastDesc(self.input_ptr, self.N, H, W, C, col.to_c(), kh, kw), f"{n.name} im2col {kh}x{kw}")
+                self._im2col_views[(kh, kw)] = col
+        if any(win is None for win in windows) or not windows:
+            dests = self._dests(n)      # consumers that read the input as it is
+            self.emit(0, L.OP_CAST, L.CastDesc(self.input_ptr, self.N, H, W, C, dests[0].to_c(), 0, 0), n.name)
+            self._copy_extra(dests[0], dests[1:])
 
     def _act_code(self, node: Optional[Node]):
         return L.ACT_NONE if node is None else L.ACT_CODES[node.attrs["fn"]]
@@ -925,9 +957,14 @@ class Planner:
         n: Node = u["node"]
         a = n.attrs
         kh, kw = a["kernel"]
-        x = self.phys[id(n.inputs[0])]
         pe = self.pindex[f"{n.name}/kernel"]
-        pe.meta["segs"] = list(x.segs)
+        ic = self._im2col_of(n)
+        if ic is not None:      # a 1x1 convolution over the K-packed im2col copy of the network input
+            x = Phys(self._im2col_views[ic[:2]], ic[0] * ic[1] * ic[2], [(0, ic[0] * ic[1] * ic[2])])
+            kh, kw = 1, 1
+        else:
+            x = self.phys[id(n.inputs[0])]
+            pe.meta["segs"] = list(x.segs)
         assert pe.meta["cin_p"] == x.Cp, (n.name, pe.meta["cin_p"], x.Cp)
         co, cop, cin_p = a["filters"], pe.meta["cout_p"], x.Cp
         H, W, _ = n.shape
@@ -974,6 +1011,13 @@ class Planner:
             self.pmov(f"{bn.name}/moving_mean"), self.pmov(f"{bn.name}/moving_variance"),
             1 if self.training else 0, 1 if self.ndim == 2 else 0, bn.attrs["eps"], bn.attrs["momentum"],
             u["scale"], u["shift"], u["mean"], u["rstd"], 0 if self.training else 1), bn.name)
+        if self._head_prologue_ok(u):
+            # the head applies BatchNorm + activation itself and its backward is folded into this layer's: no activated tensor
+            self.phys[id(out_node)] = Phys(z, co, list(self._segs(n)))
+            self.head_prologue[id(out_node)] = (u["scale"], u["shift"], act)
+            u["y"] = z
+            self.taps[n.name] = (z, co, "raw")
+            return
         dests = self._dests(out_node)
         d = L.BnActDesc()
         d.x, d.scale, d.shift, d.act = z.to_c(), u["scale"], u["shift"], act
@@ -1022,7 +1066,10 @@ class Planner:
             if act == L.ACT_SIGMOID:
                 raise PlanError("sigmoid over a gapped (odd-channel concat) channel layout is not lowered")
             return 0
-        return C if C % 8 else 0
+        # Padding lanes need no mask for an activation with f(0) = 0: their pre-activation is exactly 0 (zero weight rows, zero bias;
+        # BatchNorm of an all-zero channel has mean 0 and beta 0), and an unmasked descriptor takes the row-walking fast kernels
+        # (MultiResUNet's 10 / 21-channel branches used to fall back to the generic ones).  Only sigmoid(0) = 0.5 must be forced to 0.
+        return C if (C % 8 and act == L.ACT_SIGMOID) else 0
 
     def _fwd_add(self, u):
         n = u["node"]
@@ -1339,6 +1386,8 @@ class Planner:
         d.x, d.w, d.b, d.cout, d.act, d.stride = x.view.to_c(), self.pw(pe.key), self.pw(f"{n.name}/bias"), co, act, st
         d.y, d.dlogits = y, dl
         d.dw, d.db = self.pg(pe.key), self.pg(f"{n.name}/bias")
+        if id(n.inputs[0]) in self.head_prologue:
+            d.bn_scale, d.bn_shift, d.bn_act = self.head_prologue[id(n.inputs[0])]
         u["desc"] = d
         self.emit(0, L.OP_HEAD_FWD, d, n.name)
         idx = self.g.outputs.index(n)
@@ -1353,16 +1402,32 @@ class Planner:
         o = next(o for o in self.outputs if o["name"] == n.name)
         self._emit_loss(o, f"loss {n.name}")
         t = n.inputs[0]
-        pu = self.unit_of_out.get(id(t))
         x = self.phys[id(t)]
-        if (self.fuse_heads and pu is not None and pu["kind"] == "conv" and pu["bn"] is not None and pu["out"] is t and pu["pool"] is None
-                and pu["act"] is not None and self._act_code(pu["act"]) in (L.ACT_RELU, L.ACT_LEAKY) and o["cout"] <= 2
-                and n.attrs["strides"][1] == 1 and self.N * t.shape[0] * t.shape[1] * x.Cp < 2 ** 31):
+        if self._head_foldable(n):
             # the head reads act(BN(conv)): its backward (input gradient, dW, db) is folded into that layer's BN backward,
             # so the 2 x H x W x C gradient tensor is never written or read (b2seg_gradsrc kind 2)
             self._add_gsrc(t, GSrc(x.view, 2, (1, 1), head=dict(unit=u, name=n.name, dlogits=o["dlogits"], cout=o["cout"])))
             return
         self._emit_head_bwd(u)
+
+    def _head_foldable(self, n: Node) -> bool:
+        """head n reads act(BN(conv)) of a Conv_Block whose backward can take the head's backward in (b2seg_gradsrc kind 2)"""
+        t = n.inputs[0]
+        pu = self.unit_of_out.get(id(t))
+        return bool(self.fuse_heads and pu is not None and pu["kind"] == "conv" and pu.get("gate") is None and pu["bn"] is not None and pu["out"] is t
+                    and pu["pool"] is None and pu["act"] is not None and self._act_code(pu["act"]) in (L.ACT_RELU, L.ACT_LEAKY)
+                    and n.attrs["filters"] <= 2 and n.attrs["strides"] == (1, 1) and self.N * t.shape[0] * t.shape[1] * self._cphys(t) < 2 ** 31)
+
+    def _head_prologue_ok(self, u) -> bool:
+        """the LAST Conv_Block: its activated tensor has one reader, a foldable head, whose forward can apply BatchNorm + activation
+        itself (b2seg_head_desc.bn_scale) — then neither direction of the head needs the tensor and it is not materialised"""
+        t = u["out"]
+        c = self.cons[id(t)]
+        if os.environ.get("B2SEG_NO_HEAD_PROLOGUE") or t in self.g.outputs or len(c) != 1 or self.unit_of_out.get(id(c[0]), {}).get("kind") != "head":
+            return False
+        cv = self._cphys(t) // 8
+        dense = list(self._segs(t)) == [(0, t.C)] and self._cphys(t) == t.C
+        return self.training and self._head_foldable(c[0]) and dense and cv <= 32 and cv & (cv - 1) == 0 and self.losses is not None
 
     def _emit_head_bwd(self, u) -> Optional[GSrc]:
         """stand-alone head backward: dW, db and (unless the head reads the network input) dx as a dense gradient tensor"""
@@ -1616,7 +1681,12 @@ class Planner:
                 srcs.append(GSrc(s.view, 1, (ph, pw_), pool_name=u["pool"].name))
         if not srcs:
             return  # dead branch (no gradient reaches it)
-        x = self.phys[id(n.inputs[0])]
+        ic = self._im2col_of(n)
+        if ic is not None:
+            x = Phys(self._im2col_views[ic[:2]], ic[0] * ic[1] * ic[2], [(0, ic[0] * ic[1] * ic[2])])
+            kh, kw = 1, 1
+        else:
+            x = self.phys[id(n.inputs[0])]
         pe = self.pindex[f"{n.name}/kernel"]
         co, cop, cin_p = a["filters"], pe.meta["cout_p"], x.Cp
         H, W, _ = n.shape
@@ -1735,6 +1805,8 @@ class Planner:
                     out[m["C"]:ceil8(m["C"])] = m["fill"]
         elif e.kind in ("conv", "tconv"):
             k = arr if arr.ndim == 4 else (arr[None, None] if arr.ndim == 2 else arr[None])   # (kh,kw,Cin,Cout) | tconv (kh,kw,Cout,Cin) | Dense (in,out)
+            if m.get("im2col"):
+                k = k.reshape(1, 1, -1, k.shape[-1])        # a 1x1 kernel over the K-packed window: index (i*kw + j)*Cin + c
             if e.kind == "conv":
                 k = np.transpose(k, (3, 0, 1, 2))               # -> (Cout,kh,kw,Cin)
             else:

@@ -220,26 +220,33 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
     }
     __syncthreads();
     const int work = npx * vpp;
-    for (int i = threadIdx.x; i < work; i += 256) {
-      const int p = i / vpp, v = i - p * vpp;
+    // (uniform trip count: the warp shuffles below need every lane, also in the ragged last round)
+    for (int i0 = 0; i0 < work; i0 += 256) {
+      const int i = i0 + (int)threadIdx.x;
+      const bool live = i < work;
+      const int p = live ? i / vpp : 0, v = live ? i - p * vpp : 0;
       float s[8], o[8];
-      load8(vaddr(k.skip, (int)n, oy, x0 + p, v * 8), s);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = 0.f;
+      if (live) load8(vaddr(k.skip, (int)n, oy, x0 + p, v * 8), s);
       const float r = s_r[p];
       if (!BWD) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = s[e] * r;
-        store8(vaddr(k.out, (int)n, oy, x0 + p, v * 8), o);
+        if (live) store8(vaddr(k.out, (int)n, oy, x0 + p, v * 8), o);
       } else {
         float d[8];
-        load8(vaddr(k.dout, (int)n, oy, x0 + p, v * 8), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = 0.f;
+        if (live) load8(vaddr(k.dout, (int)n, oy, x0 + p, v * 8), d);
         float part = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) { o[e] = d[e] * r; part = fmaf(d[e], s[e], part); }
-        store8(vaddr(k.dskip, (int)n, oy, x0 + p, v * 8), o);
+        if (live) store8(vaddr(k.dskip, (int)n, oy, x0 + p, v * 8), o);
         // lanes holding the same pixel are adjacent (vpp is a power of two): reduce within the warp first
         const int span = vpp < 32 ? vpp : 32;
         for (int off = span >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-        if ((threadIdx.x & (span - 1)) == 0) atomicAdd(&s_dr[p], part);
+        if (live && (threadIdx.x & (span - 1)) == 0) atomicAdd(&s_dr[p], part);
       }
     }
     if (BWD) {

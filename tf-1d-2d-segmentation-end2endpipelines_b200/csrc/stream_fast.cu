@@ -632,6 +632,7 @@ struct HeadF {
   const float* w; const float* b;
   float* y; float* logits;
   const float* dl; float* dw; float* db;
+  const float* sc; const float* sh; int pre_act;   // forward only: the head consumes act(x * sc + sh) (x = raw conv output of the last layer)
 };
 
 static bool pixel_contiguous(const b2seg_view& v, unsigned* pitch) {
@@ -661,6 +662,12 @@ __global__ void __launch_bounds__(256, head_fwd_minb(COUT)) head_fwd_fast_kernel
   float bias[COUT];
 #pragma unroll
   for (int o = 0; o < COUT; ++o) bias[o] = __ldg(k.b + o);
+  // BatchNorm + activation of the layer the head reads, applied on the fly: that layer's activated tensor (only the head and its
+  // folded backward would ever touch it) is then never written or read
+  const bool pre = k.sc != nullptr;
+  float psc[8], psh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { psc[e] = pre ? __ldg(k.sc + gl * 8 + e) : 1.f; psh[e] = pre ? __ldg(k.sh + gl * 8 + e) : 0.f; }
   const unsigned n_iter = (k.n_pix + gstride * U - 1) / (gstride * U);   // uniform trip count: the shuffles need whole warps
   for (unsigned it = 0; it < n_iter; ++it) {
     uint4 raw[U];
@@ -675,6 +682,13 @@ __global__ void __launch_bounds__(256, head_fwd_minb(COUT)) head_fwd_fast_kernel
     for (int u = 0; u < U; ++u) {
       float f[8], acc[COUT];
       unpack8(raw[u], f);
+      if (pre) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = fmaf(f[e], psc[e], psh[e]);
+          f[e] = k.pre_act == B2SEG_ACT_RELU ? fmaxf(t, 0.f) : (k.pre_act == B2SEG_ACT_LEAKY ? (t > 0.f ? t : 0.3f * t) : t);
+        }
+      }
 #pragma unroll
       for (int o = 0; o < COUT; ++o) {
         acc[o] = 0.f;
@@ -833,6 +847,10 @@ PreparedOp* prepare_head_fast(const b2seg_head_desc* d, bool bwd) {
     if (!k.dl || !k.dw || !k.db) return nullptr;
   } else if (!k.w || !k.b || !k.y) {
     return nullptr;
+  }
+  if (d->bn_scale) {
+    if (bwd || !d->bn_shift || (d->bn_act != B2SEG_ACT_NONE && d->bn_act != B2SEG_ACT_RELU && d->bn_act != B2SEG_ACT_LEAKY)) return nullptr;
+    k.sc = reinterpret_cast<const float*>(d->bn_scale); k.sh = reinterpret_cast<const float*>(d->bn_shift); k.pre_act = d->bn_act;
   }
   auto* L = new HeadFastLaunch();
   L->k = k; L->cout = d->cout; L->bwd = bwd;

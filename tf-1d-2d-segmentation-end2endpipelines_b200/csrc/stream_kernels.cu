@@ -23,17 +23,51 @@ __global__ void cast_input_kernel(const float* __restrict__ src, int N, int H, i
     store8(vaddr(out, n, h, w, v * 8), f);
   }
 }
+// K-packed im2col of the network input: out(n,h,w, (i*kw + j)*C + c) = src(n, h + i - (kh-1)/2, w + j - (kw-1)/2, c), zero outside the
+// image and in the padding lanes.  A k x k convolution that reads the (thin: 1-3 channel) input becomes a 1x1 convolution over
+// this tensor: ONE 128-byte-row tap on the tensor cores instead of kh*kw taps that each hold 8 real channels (the 3 -> 64 first
+// layer of config 2 took 0.22 ms forward + 0.25 ms weight gradient for 0.02 ms of math, profiles/r1_tile_trace.txt).
+__global__ void im2col_input_kernel(const float* __restrict__ src, int N, int H, int W, int C, int kh, int kw, DView out) {
+  const int cv = out.C / 8;
+  const int K = kh * kw * C;
+  const int ph = (kh - 1) / 2, pw = (kw - 1) / 2;
+  const unsigned total = (unsigned)N * H * W * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    unsigned pix = i / cv;
+    const int w = (int)(pix % W); pix /= W;
+    const int h = (int)(pix % H);
+    const int n = (int)(pix / H);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = v * 8 + e;
+      float val = 0.f;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+        const int hh = h + tap / kw - ph, ww = w + tap % kw - pw;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(src + (((long long)n * H + hh) * W + ww) * C + c);
+      }
+      f[e] = val;
+    }
+    store8(vaddr(out, n, h, w, v * 8), f);
+  }
+}
 struct CastLaunch : PreparedOp {
   b2seg_cast_desc d;
   int launch(cudaStream_t s) override {
     const long long work = (long long)d.N * d.H * d.W * (d.out.C / 8);
-    cast_input_kernel<<<grid_for(work, 256), 256, 0, s>>>(reinterpret_cast<const float*>(d.src), d.N, d.H, d.W, d.C, dv(d.out));
+    if (d.kh * d.kw > 1)
+      im2col_input_kernel<<<grid_for(work, 256), 256, 0, s>>>(reinterpret_cast<const float*>(d.src), d.N, d.H, d.W, d.C, d.kh, d.kw, dv(d.out));
+    else
+      cast_input_kernel<<<grid_for(work, 256), 256, 0, s>>>(reinterpret_cast<const float*>(d.src), d.N, d.H, d.W, d.C, dv(d.out));
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
 };
 PreparedOp* prepare_cast(const b2seg_cast_desc* d) {
   if (d->out.C % 8) { set_error("cast: out.C %% 8"); return nullptr; }
+  if (d->kh < 0 || d->kw < 0 || (d->kh * d->kw > 1 && d->kh * d->kw * d->C > d->out.C)) { set_error("cast: im2col window %dx%dx%d does not fit %d channels", d->kh, d->kw, d->C, d->out.C); return nullptr; }
   CastLaunch* L = new CastLaunch(); L->d = *d; return L;
 }
 
@@ -801,6 +835,7 @@ struct HeadFwdLaunch : PreparedOp {
 PreparedOp* prepare_head_fwd(const b2seg_head_desc* d) {
   if (d->cout < 1 || d->cout > 8 || d->x.C % 8) { set_error("head: cout in 1..8, C %% 8 == 0"); return nullptr; }
   if (PreparedOp* fast = prepare_head_fast(d, false)) return fast;
+  if (d->bn_scale) { set_error("head: the fused BatchNorm prologue needs the pixel-contiguous fast path (C / 8 a power of two <= 32, stride 1)"); return nullptr; }
   auto* L = new HeadFwdLaunch(); L->d = *d; return L;
 }
 
