@@ -342,6 +342,18 @@ typedef struct b2seg_gate_desc {
   uint64_t dw3, db3, dwt, dbt;  /* fp32, accumulated (caller-zeroed): [C], [1], 16 elements of stride wt_stride, [1] */
 } b2seg_gate_desc;
 
+/* Inference: BatchNormalization (moving statistics) folded into the preceding convolution's kernel and bias, so that the convolution
+ * epilogue produces act(BN(conv(x))) directly — no raw tensor, no BatchNorm pass (2DCNN/Test.py:149-164 model.predict).
+ *   w_folded[co][:] = bf16(w[co][:] * s[co]),  bias_folded[co] = bias[co] * s[co] + beta[co] - moving_mean[co] * s[co],
+ *   s = gamma / sqrt(moving_var + eps).  Replayed whenever the weights change (phase 2 of an inference plan). */
+typedef struct b2seg_fold_desc {
+  uint64_t w, bias;                 /* fp32 [cout_p][row], [cout_p] (bias may be 0) */
+  uint64_t gamma, beta, moving_mean, moving_var;   /* fp32 [cout_p] */
+  float eps;
+  int32_t cout_p, row;              /* row = taps * cin_p elements per output channel */
+  uint64_t w_folded, bias_folded;   /* bf16 [cout_p][row], fp32 [cout_p] */
+} b2seg_fold_desc;
+
 const char* b2seg_last_error(void);
 int b2seg_version(void);   /* 103; the ctypes binding refuses a library of another version */
 int b2seg_device_check(int device);
@@ -377,13 +389,14 @@ int b2seg_outact_bwd(const b2seg_outact_desc* d, void* stream);
 int b2seg_target_pool(const b2seg_tpool_desc* d, void* stream);
 int b2seg_gate_fwd(const b2seg_gate_desc* d, void* stream);
 int b2seg_gate_bwd(const b2seg_gate_desc* d, void* stream);
+int b2seg_fold_bn(const b2seg_fold_desc* d, void* stream);
 
 /* ---- plan: a recorded sequence of the ops above, replayed per step ---- */
 typedef struct b2seg_plan b2seg_plan;
 enum { B2SEG_OP_CONV = 1, B2SEG_OP_WGRAD, B2SEG_OP_BN_FINALIZE, B2SEG_OP_BN_ACT, B2SEG_OP_BN_BWD, B2SEG_OP_ADAM,
        B2SEG_OP_HEAD_FWD, B2SEG_OP_HEAD_BWD, B2SEG_OP_LOSS, B2SEG_OP_ELTWISE, B2SEG_OP_CAST, B2SEG_OP_COLSUM,
        B2SEG_OP_MEMSET, B2SEG_OP_RESIZE_FWD, B2SEG_OP_RESIZE_BWD, B2SEG_OP_MULBC_FWD, B2SEG_OP_MULBC_BWD, B2SEG_OP_COLSTATS,
-       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM, B2SEG_OP_OUTACT_FWD, B2SEG_OP_OUTACT_BWD, B2SEG_OP_TARGET_POOL, B2SEG_OP_GATE_FWD, B2SEG_OP_GATE_BWD };
+       B2SEG_OP_LSTM_FWD, B2SEG_OP_LSTM_BWD, B2SEG_OP_POOL_BWD, B2SEG_OP_ROWSUM, B2SEG_OP_OUTACT_FWD, B2SEG_OP_OUTACT_BWD, B2SEG_OP_TARGET_POOL, B2SEG_OP_GATE_FWD, B2SEG_OP_GATE_BWD, B2SEG_OP_FOLD_BN };
 typedef struct b2seg_memset_desc { uint64_t ptr; int64_t bytes; } b2seg_memset_desc;
 
 /* Data parallel: backward-phase ops added to a plan AFTER this call size their grids for (SMs - sms), leaving room for the
@@ -392,7 +405,7 @@ int b2seg_set_backward_sm_reserve(int sms);
 /* debug aid: with B2SEG_TRACE=1 in the environment, CTA 0 of a halo-tile convolution records clock64() stamps per tile */
 int b2seg_debug_read_trace(uint64_t* out, int n);
 int b2seg_plan_create(b2seg_plan** out);
-/* phase: 0 forward, 1 backward, 2 optimizer. desc is copied. */
+/* phase: 0 forward, 1 backward, 2 optimizer (training plans) / weight preparation (inference plans: B2SEG_OP_FOLD_BN). desc is copied. */
 int b2seg_plan_add(b2seg_plan* p, int phase, int op, const void* desc, size_t desc_bytes);
 int b2seg_plan_run(b2seg_plan* p, int phase, void* stream);
 /* replay ops [first_op, first_op + n_ops) of a phase: lets the host interleave the data-parallel gradient exchange

@@ -105,6 +105,11 @@ class CpuEngine:
     def backward(self):
         run_phase(self.mem, self.planner, 1)
 
+    def run(self, phase):
+        if phase == 0:
+            return self.forward()
+        run_phase(self.mem, self.planner, phase)
+
     def run_range(self, phase, first_op, n_ops):
         if phase == 0 and first_op == 0:
             self._poison()

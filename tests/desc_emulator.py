@@ -115,7 +115,7 @@ import numpy as np
 
 from b2seg import _lib as L
 
-_ESIZE = {"act": 2, "grad": 2, "param_wb": 2, "arena": 2}
+_ESIZE = {"act": 2, "grad": 2, "param_wb": 2, "arena": 2, "fold_w": 2}
 
 
 class PlanMem(FakeMem):
@@ -686,7 +686,16 @@ def emu_gate_bwd(mem, d):
     mem.f32(d.dbt, 1)[:] += prm["bt"].grad
 
 
-EMU = {L.OP_GATE_FWD: emu_gate_fwd, L.OP_GATE_BWD: emu_gate_bwd, L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_finalize, L.OP_BN_ACT: emu_bn_act,
+def emu_fold_bn(mem, d):
+    w = mem.f32(d.w, d.cout_p * d.row).view(d.cout_p, d.row)
+    s_ = mem.f32(d.gamma, d.cout_p) * torch.rsqrt(mem.f32(d.moving_var, d.cout_p) + d.eps)
+    wf, off = mem.resolve(d.w_folded)
+    wf[off:off + d.cout_p * d.row] = (w * s_[:, None]).reshape(-1)
+    b = mem.f32(d.bias, d.cout_p) if d.bias else torch.zeros(d.cout_p, dtype=torch.float64)
+    mem.f32(d.bias_folded, d.cout_p)[:] = b * s_ + mem.f32(d.beta, d.cout_p) - mem.f32(d.moving_mean, d.cout_p) * s_
+
+
+EMU = {L.OP_FOLD_BN: emu_fold_bn, L.OP_GATE_FWD: emu_gate_fwd, L.OP_GATE_BWD: emu_gate_bwd, L.OP_CONV: emu_conv, L.OP_WGRAD: emu_wgrad, L.OP_BN_FINALIZE: emu_bn_finalize, L.OP_BN_ACT: emu_bn_act,
        L.OP_BN_BWD: emu_bn_bwd, L.OP_ADAM: emu_adam, L.OP_HEAD_FWD: emu_head_fwd, L.OP_HEAD_BWD: emu_head_bwd,
        L.OP_LOSS: emu_loss, L.OP_ELTWISE: emu_eltwise, L.OP_CAST: emu_cast, L.OP_COLSUM: emu_colsum,
        L.OP_MEMSET: emu_memset, L.OP_RESIZE_FWD: emu_resize_fwd, L.OP_RESIZE_BWD: emu_resize_bwd,

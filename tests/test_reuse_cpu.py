@@ -69,7 +69,7 @@ def test_reuse_equals_no_reuse_with_poisoned_arena(cpu_engine, case):
     for qa, qb in zip(pa if isinstance(pa, list) else [pa], pb if isinstance(pb, list) else [pb]):
         assert np.array_equal(qa, qb)
     si = b._engine(2, False).planner.reuse_stats
-    assert si["arena_bytes"] <= 0.6 * si["tensor_bytes"], si
+    assert si["arena_bytes"] <= 0.7 * si["tensor_bytes"], si
 
 
 def test_arena_size_of_the_baseline_configs():

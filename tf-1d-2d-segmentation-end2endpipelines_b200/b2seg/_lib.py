@@ -19,7 +19,7 @@ ACT_CODES = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "ReLU": ACT_R
              "sigmoid": ACT_SIGMOID, "softmax": ACT_SOFTMAX, "tanh": ACT_TANH}
 (OP_CONV, OP_WGRAD, OP_BN_FINALIZE, OP_BN_ACT, OP_BN_BWD, OP_ADAM, OP_HEAD_FWD, OP_HEAD_BWD, OP_LOSS, OP_ELTWISE,
  OP_CAST, OP_COLSUM, OP_MEMSET, OP_RESIZE_FWD, OP_RESIZE_BWD, OP_MULBC_FWD, OP_MULBC_BWD, OP_COLSTATS, OP_LSTM_FWD,
- OP_LSTM_BWD, OP_POOL_BWD, OP_ROWSUM, OP_OUTACT_FWD, OP_OUTACT_BWD, OP_TARGET_POOL, OP_GATE_FWD, OP_GATE_BWD) = range(1, 28)
+ OP_LSTM_BWD, OP_POOL_BWD, OP_ROWSUM, OP_OUTACT_FWD, OP_OUTACT_BWD, OP_TARGET_POOL, OP_GATE_FWD, OP_GATE_BWD, OP_FOLD_BN) = range(1, 29)
 PHASE_FWD, PHASE_BWD, PHASE_OPT = 0, 1, 2
 ABI_VERSION = 103    # b2seg_version() of the library this binding mirrors (include/b2seg.h)
 
@@ -160,6 +160,12 @@ class GateDesc(C.Structure):
                 ("dgamma3", C.c_uint64), ("dbeta3", C.c_uint64), ("dw3", C.c_uint64), ("db3", C.c_uint64), ("dwt", C.c_uint64), ("dbt", C.c_uint64)]
 
 
+class FoldDesc(C.Structure):
+    _fields_ = [("w", C.c_uint64), ("bias", C.c_uint64), ("gamma", C.c_uint64), ("beta", C.c_uint64), ("moving_mean", C.c_uint64),
+                ("moving_var", C.c_uint64), ("eps", C.c_float), ("cout_p", C.c_int32), ("row", C.c_int32), ("w_folded", C.c_uint64),
+                ("bias_folded", C.c_uint64)]
+
+
 class MemsetDesc(C.Structure):
     _fields_ = [("ptr", C.c_uint64), ("bytes", C.c_int64)]
 
@@ -170,14 +176,14 @@ OP_DESC = {OP_CONV: ConvDesc, OP_WGRAD: WgradDesc, OP_BN_FINALIZE: BnFinalizeDes
            OP_RESIZE_FWD: ResizeDesc, OP_RESIZE_BWD: ResizeDesc, OP_MULBC_FWD: MulbcDesc, OP_MULBC_BWD: MulbcDesc,
            OP_COLSTATS: ColstatsDesc, OP_LSTM_FWD: LstmDesc, OP_LSTM_BWD: LstmDesc, OP_POOL_BWD: PoolBwdDesc,
            OP_ROWSUM: RowsumDesc, OP_OUTACT_FWD: OutActDesc, OP_OUTACT_BWD: OutActDesc,
-           OP_TARGET_POOL: TPoolDesc, OP_GATE_FWD: GateDesc, OP_GATE_BWD: GateDesc}
+           OP_TARGET_POOL: TPoolDesc, OP_GATE_FWD: GateDesc, OP_GATE_BWD: GateDesc, OP_FOLD_BN: FoldDesc}
 
 # every symbol include/b2seg.h declares (the CPU test-suite checks the library exports all of them)
 EXPORTED = ["b2seg_last_error", "b2seg_version", "b2seg_device_check", "b2seg_sizeof_desc", "b2seg_conv", "b2seg_conv_num_mtiles", "b2seg_conv_num_stat_rows",
             "b2seg_wgrad", "b2seg_bn_finalize", "b2seg_bn_act", "b2seg_bn_bwd", "b2seg_adam", "b2seg_head_fwd",
             "b2seg_head_bwd", "b2seg_loss", "b2seg_eltwise", "b2seg_cast_input", "b2seg_colsum", "b2seg_plan_create",
             "b2seg_resize_fwd", "b2seg_resize_bwd", "b2seg_mulbc_fwd", "b2seg_mulbc_bwd", "b2seg_colstats", "b2seg_lstm_fwd",
-            "b2seg_lstm_bwd", "b2seg_pool_bwd", "b2seg_rowsum", "b2seg_outact_fwd", "b2seg_outact_bwd", "b2seg_target_pool", "b2seg_gate_fwd", "b2seg_gate_bwd",
+            "b2seg_lstm_bwd", "b2seg_pool_bwd", "b2seg_rowsum", "b2seg_outact_fwd", "b2seg_outact_bwd", "b2seg_target_pool", "b2seg_gate_fwd", "b2seg_gate_bwd", "b2seg_fold_bn",
             "b2seg_set_backward_sm_reserve", "b2seg_debug_read_trace", "b2seg_plan_add", "b2seg_plan_run", "b2seg_plan_run_range", "b2seg_plan_num_launches", "b2seg_plan_num_ops", "b2seg_plan_run_timed", "b2seg_plan_set_adam", "b2seg_plan_destroy"]
 
 _lib = None
@@ -207,7 +213,7 @@ def load():
                        ("b2seg_mulbc_bwd", MulbcDesc), ("b2seg_colstats", ColstatsDesc), ("b2seg_lstm_fwd", LstmDesc),
                        ("b2seg_lstm_bwd", LstmDesc), ("b2seg_pool_bwd", PoolBwdDesc), ("b2seg_rowsum", RowsumDesc),
                        ("b2seg_outact_fwd", OutActDesc), ("b2seg_outact_bwd", OutActDesc), ("b2seg_target_pool", TPoolDesc),
-                       ("b2seg_gate_fwd", GateDesc), ("b2seg_gate_bwd", GateDesc)]:
+                       ("b2seg_gate_fwd", GateDesc), ("b2seg_gate_bwd", GateDesc), ("b2seg_fold_bn", FoldDesc)]:
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(desc), C.c_void_p]
         fn.restype = C.c_int

@@ -182,6 +182,7 @@ class Model:
         # False (default): activation / gradient buffers share one arena by liveness (Planner._assign_memory).  True: every layer's
         # tensors stay readable after a step (layer_output / the per-layer parity tests); B2SEG_KEEP_ACTIVATIONS=1 forces it.
         self.keep_activations = bool(os.environ.get("B2SEG_KEEP_ACTIVATIONS"))
+        self._wversion = 0              # bumped whenever the weights change: inference engines refold BatchNorm into their kernels lazily
         self._adam_step = 0             # Adam's t: one counter per model (the moments are shared by the engines of every batch size)
 
     # ---- introspection -----------------------------------------------------------------------------------
@@ -230,6 +231,7 @@ class Model:
             if tuple(np.shape(v)) != self._weights[k].shape:
                 raise ValueError(f"weight {k}: shape {np.shape(v)} != {self._weights[k].shape}")
             self._weights[k] = np.asarray(v, np.float32).copy()
+        self._wversion += 1
         if self._primary is not None:
             self._primary.set_weights(self._weights)
 
@@ -375,6 +377,7 @@ class Model:
         for t in (eng.w, eng.moving, eng.m, eng.v):
             self._dist.broadcast(t, src, group=self._pg)
         eng.wb.copy_(eng.w.to(eng.wb.dtype))
+        self._wversion += 1
 
     # ---- train / predict ---------------------------------------------------------------------------------
     def train_on_batch(self, x, y, return_loss=True):
@@ -400,6 +403,7 @@ class Model:
         return sched
 
     def _step(self, eng, return_loss=True):
+        self._wversion += 1
         eng.forward()
         scale = 1.0
         if self.world_size > 1:
@@ -437,22 +441,75 @@ class Model:
         return None
 
     def predict(self, x, batch_size=None, verbose=0, **kw):
+        """tf.keras.Model.predict (2DCNN/Test.py:149-164): moving-statistics BatchNorm folded into the convolution kernels (refolded
+        lazily when the weights have changed), batches pipelined: while batch i computes, batch i+1 is staged host -> device on one
+        copy stream and the outputs of batch i-1 travel device -> host on another (pinned staging on both sides)."""
         import torch
         xs = self._to_nhwc(x)
         n = xs.shape[0]
         bs = int(batch_size) if batch_size else min(n, 32)
         bs = max(1, min(bs, n))
         eng = self._engine(bs, False)
+        if getattr(eng, "_fold_version", None) != self._wversion:
+            eng.run(2)                                   # phase 2 of an inference plan: b2seg_fold_bn of every Conv + BatchNorm pair
+            eng._fold_version = self._wversion
         outs = [np.empty((n,) + tuple(o["shape"][1:]), np.float32) for o in eng.outputs]
-        for s in range(0, n, bs):
-            chunk = xs[s:s + bs]
-            m = chunk.shape[0]
-            if m < bs:
-                chunk = np.concatenate([chunk, np.zeros((bs - m,) + chunk.shape[1:], np.float32)], 0)
-            eng.x_dev.copy_(torch.from_numpy(chunk), non_blocking=True)
-            eng.forward()
-            for i, o in enumerate(eng.outputs):
-                outs[i][s:s + m] = o["y"][:m].cpu().numpy()
+        starts = list(range(0, n, bs))
+        if eng.dev.type != "cuda":                       # (emulator engine of the CPU test-suite)
+            for s in starts:
+                chunk = xs[s:s + bs]
+                m = chunk.shape[0]
+                if m < bs:
+                    chunk = np.concatenate([chunk, np.zeros((bs - m,) + chunk.shape[1:], np.float32)], 0)
+                eng.x_dev.copy_(torch.from_numpy(chunk))
+                eng.forward()
+                for i, o in enumerate(eng.outputs):
+                    outs[i][s:s + m] = o["y"][:m].cpu().numpy()
+        else:
+            st = getattr(eng, "_predict_stage", None)
+            if st is None:
+                st = eng._predict_stage = dict(
+                    h2d=torch.cuda.Stream(device=eng.dev), d2h=torch.cuda.Stream(device=eng.dev),
+                    slots=[dict(hin=torch.empty(tuple(eng.x_dev.shape), dtype=torch.float32).pin_memory(), xin=torch.empty_like(eng.x_dev),
+                                y=[torch.empty_like(o["y"]) for o in eng.outputs],
+                                hout=[torch.empty(tuple(o["y"].shape), dtype=torch.float32).pin_memory() for o in eng.outputs],
+                                ready=torch.cuda.Event(), done=torch.cuda.Event(), landed=torch.cuda.Event(), consumed=torch.cuda.Event())
+                           for _ in range(2)])
+            cur = torch.cuda.current_stream(eng.dev)
+
+            def collect(j):
+                sl = st["slots"][j % 2]
+                sl["landed"].synchronize()
+                s_ = starts[j]
+                m_ = min(bs, n - s_)
+                for i in range(len(outs)):
+                    outs[i][s_:s_ + m_] = sl["hout"][i][:m_].numpy()
+            for j, s in enumerate(starts):
+                sl = st["slots"][j % 2]
+                m = min(bs, n - s)
+                if j >= 2:
+                    collect(j - 2)                        # frees this slot's host buffers (and overlaps with batch j-1 on the device)
+                sl["hin"][:m].copy_(torch.from_numpy(xs[s:s + m]))
+                if m < bs:
+                    sl["hin"][m:].zero_()
+                with torch.cuda.stream(st["h2d"]):
+                    st["h2d"].wait_event(sl["consumed"])  # the forward that read this slot's device buffer has copied it out
+                    sl["xin"].copy_(sl["hin"], non_blocking=True)
+                    sl["ready"].record(st["h2d"])
+                cur.wait_event(sl["ready"])
+                eng.x_dev.copy_(sl["xin"], non_blocking=True)
+                sl["consumed"].record(cur)
+                eng.forward()
+                for i, o in enumerate(eng.outputs):
+                    sl["y"][i].copy_(o["y"], non_blocking=True)
+                sl["done"].record(cur)
+                with torch.cuda.stream(st["d2h"]):
+                    st["d2h"].wait_event(sl["done"])
+                    for i in range(len(outs)):
+                        sl["hout"][i].copy_(sl["y"][i], non_blocking=True)
+                    sl["landed"].record(st["d2h"])
+            for j in range(max(0, len(starts) - 2), len(starts)):
+                collect(j)
         if self.graph.ndim == 1:
             outs = [o[:, 0] for o in outs]
         return outs if len(outs) > 1 else outs[0]

@@ -977,12 +977,14 @@ class Planner:
             # ('same' pads nothing for a 1x1 kernel when the stride divides the map: Oper2D(1, (1,1), strides=(2,2)), :745)
             raise PlanError(f"{n.name}: only 1x1 strided convolutions without padding are lowered")
 
-        def conv_desc(out_view, act_code, stats_ptr):
+        def conv_desc(out_view, act_code, stats_ptr, weights=None, bias_ptr=None):
+            wts = self.pwb(pe.key) if weights is None else weights
+            bs = bias if bias_ptr is None else bias_ptr
             if n.op == "tconv":
-                return lw.tconv_fprop(x.view, self.pwb(pe.key), cop, kh, kw, cin_p, out_view, bias=bias, act=act_code, stats=stats_ptr)
+                return lw.tconv_fprop(x.view, wts, cop, kh, kw, cin_p, out_view, bias=bs, act=act_code, stats=stats_ptr)
             xin = x.view.parity(0, 0, a["strides"][0], a["strides"][1]) if strided else x.view
             if a["padding"] == "same" or (kh, kw) == (1, 1):
-                return lw.conv_fprop(xin, self.pwb(pe.key), cop, kh, kw, cin_p, out_view, bias=bias, act=act_code, stats=stats_ptr)
+                return lw.conv_fprop(xin, wts, cop, kh, kw, cin_p, out_view, bias=bs, act=act_code, stats=stats_ptr)
             raise PlanError(f"{n.name}: padding '{a['padding']}' with kernel {a['kernel']} is not lowered")
 
         if u["bn"] is None:
@@ -996,6 +998,31 @@ class Planner:
                 self.taps[n.name] = (dests[0], co, "post")  # pre-activation is not materialised
             return
         bn = u["bn"]
+        if (not self.training and not os.environ.get("B2SEG_NO_BN_FOLD") and act in (L.ACT_NONE, L.ACT_RELU, L.ACT_LEAKY, L.ACT_SIGMOID)
+                and self._cvalid(co, self._segs(n), act) == 0):
+            # Inference: BatchNorm (moving statistics) folded into the kernel and bias (b2seg_fold_bn, phase 2, replayed when the weights
+            # change); the convolution epilogue writes act(BN(conv)) straight into its destination — no raw tensor, no BatchNorm pass
+            row = pe.meta["taps"] * pe.meta["cin_p"]
+            wf, bfold = self.alloc(cop * row * 2, "fold_w"), self.alloc(cop * 4, "scratch")
+            self.emit(2, L.OP_FOLD_BN, L.FoldDesc(self.pw(pe.key), bias, self.pw(f"{bn.name}/gamma"), self.pw(f"{bn.name}/beta"),
+                                                 self.pmov(f"{bn.name}/moving_mean"), self.pmov(f"{bn.name}/moving_variance"), bn.attrs["eps"],
+                                                 cop, row, wf, bfold), f"fold {bn.name} into {n.name}")
+            dests = self._dests(out_node)
+            self.emit(0, L.OP_CONV, conv_desc(dests[0], act, 0, wf, bfold), n.name, flops=self._conv_flops(n))
+            self._copy_extra(dests[0], dests[1:])
+            if u["pool"] is not None:
+                pn = u["pool"]
+                pd = self._dests(pn)
+                d = L.BnActDesc()
+                d.x, d.act, d.n_out = dests[0].to_c(), L.ACT_NONE, 0
+                d.pool_h, d.pool_w = pn.attrs["size"]
+                d.pooled = pd[0].to_c()
+                self.emit(0, L.OP_BN_ACT, d, pn.name)
+                self._copy_extra(pd[0], pd[1:])
+                self.taps[pn.name] = (pd[0], pn.C, "act")
+            u["y"] = dests[0]
+            self.taps[out_node.name] = (dests[0], co, "act")
+            return
         z = self.new_act(H, W, cop)
         u["z"] = z
         cd = conv_desc(z, L.ACT_NONE, 0)

@@ -150,6 +150,7 @@ static PreparedOp* prepare_any(int op, const void* desc, size_t bytes) {
     B2_CASE(B2SEG_OP_TARGET_POOL, b2seg_tpool_desc, prepare_target_pool)
     B2_CASE(B2SEG_OP_GATE_FWD, b2seg_gate_desc, prepare_gate_fwd)
     B2_CASE(B2SEG_OP_GATE_BWD, b2seg_gate_desc, prepare_gate_bwd)
+    B2_CASE(B2SEG_OP_FOLD_BN, b2seg_fold_desc, prepare_fold_bn)
     default:
       set_error("unknown op code %d", op);
       return nullptr;
@@ -198,6 +199,7 @@ int b2seg_sizeof_desc(int op) {
     case B2SEG_OP_TARGET_POOL: return (int)sizeof(b2seg_tpool_desc);
     case B2SEG_OP_GATE_FWD:
     case B2SEG_OP_GATE_BWD: return (int)sizeof(b2seg_gate_desc);
+    case B2SEG_OP_FOLD_BN: return (int)sizeof(b2seg_fold_desc);
     default: return -1;
   }
 }
@@ -242,6 +244,7 @@ B2_ENTRY(b2seg_outact_bwd, b2seg_outact_desc, b2::prepare_outact_bwd)
 B2_ENTRY(b2seg_target_pool, b2seg_tpool_desc, b2::prepare_target_pool)
 B2_ENTRY(b2seg_gate_fwd, b2seg_gate_desc, b2::prepare_gate_fwd)
 B2_ENTRY(b2seg_gate_bwd, b2seg_gate_desc, b2::prepare_gate_bwd)
+B2_ENTRY(b2seg_fold_bn, b2seg_fold_desc, b2::prepare_fold_bn)
 
 int b2seg_conv_num_mtiles(const b2seg_conv_desc* d) {
   if (!d) return b2::fail(B2SEG_ERR_ARG, "null descriptor");

@@ -87,6 +87,7 @@ PreparedOp* prepare_outact_bwd(const b2seg_outact_desc* d);
 PreparedOp* prepare_target_pool(const b2seg_tpool_desc* d);
 PreparedOp* prepare_gate_fwd(const b2seg_gate_desc* d);
 PreparedOp* prepare_gate_bwd(const b2seg_gate_desc* d);
+PreparedOp* prepare_fold_bn(const b2seg_fold_desc* d);
 
 // adam launches expose their mutable hyper-parameters to the plan
 void adam_update(PreparedOp* op, float lr, int64_t step, float grad_scale);

@@ -556,4 +556,48 @@ PreparedOp* prepare_target_pool(const b2seg_tpool_desc* d) {
   return L;
 }
 
+// ------------------------------------------------------------------------------------------ BatchNorm folded into the conv weights (inference)
+// Inference normalises with the moving statistics, which are known before the convolution runs:
+//   act(BN(conv(x, W) + b)) = act(conv(x, W * s) + (b * s + t)),  s = gamma / sqrt(moving_var + eps),  t = beta - moving_mean * s
+// One thread per weight element writes the bf16 folded kernel row by row ([cout_p][row] layout, one scale per row); the first `cout_p`
+// threads also write the folded bias.  Runs once per weight change, not per predict call.
+__global__ void __launch_bounds__(256) fold_bn_kernel(b2seg_fold_desc d) {
+  const float* w = reinterpret_cast<const float*>(d.w);
+  const float* gamma = reinterpret_cast<const float*>(d.gamma);
+  const float* beta = reinterpret_cast<const float*>(d.beta);
+  const float* mm = reinterpret_cast<const float*>(d.moving_mean);
+  const float* mv = reinterpret_cast<const float*>(d.moving_var);
+  __nv_bfloat16* wo = reinterpret_cast<__nv_bfloat16*>(d.w_folded);
+  const long long total = (long long)d.cout_p * d.row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / d.row);
+    const float s = gamma[co] * rsqrtf(mv[co] + d.eps);
+    wo[i] = __float2bfloat16_rn(w[i] * s);
+    if (i < d.cout_p) {
+      const int c = (int)i;
+      const float sc = gamma[c] * rsqrtf(mv[c] + d.eps);
+      const float b = d.bias ? reinterpret_cast<const float*>(d.bias)[c] : 0.f;
+      reinterpret_cast<float*>(d.bias_folded)[c] = b * sc + (beta[c] - mm[c] * sc);
+    }
+  }
+}
+struct FoldLaunch : PreparedOp {
+  b2seg_fold_desc d;
+  int launch(cudaStream_t s) override {
+    int grid = grid_for((long long)d.cout_p * d.row, 256);
+    const int cap = num_sms() * 16;
+    if (grid > cap) grid = cap;
+    fold_bn_kernel<<<grid, 256, 0, s>>>(d);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+PreparedOp* prepare_fold_bn(const b2seg_fold_desc* d) {
+  if (!d->w || !d->gamma || !d->beta || !d->moving_mean || !d->moving_var || !d->w_folded || !d->bias_folded || d->cout_p < 1 || d->row < d->cout_p) {
+    set_error("fold_bn: bad arguments (row %d must be >= cout_p %d)", d->row, d->cout_p);
+    return nullptr;
+  }
+  auto* L = new FoldLaunch(); L->d = *d; return L;
+}
+
 }  // namespace b2
