@@ -250,6 +250,73 @@ def other_config(n, batch, rank):
     return m, x, y, wl, gf, B
 
 
+def bench_predict(args, model, x, B, S, workload, rank, world, local, barrier, timed):
+    """inference: `value` = forward passes with the batch resident in HBM; `e2e` = Model.predict over steps x B host samples (pageable
+    NumPy input, NumPy outputs: staging through pinned buffers inside predict).  Batch split across GPUs, no collective."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from b2seg import _lib as L
+    ns = args.steps
+    model.predict(x, batch_size=B)                       # builds the inference engine, folds BatchNorm into the kernels
+    eng = model._engine(B, False)
+    for _ in range(args.warmup):
+        eng.forward()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(eng.forward, ns)
+    clocks = sampler.stop()
+    value = world * B * ns / (ms / 1e3)
+    xh = np.concatenate([x] * ns, 0)
+    model.predict(xh[:2 * B], batch_size=B)
+    out = {}
+
+    def run():
+        out["y"] = model.predict(xh, batch_size=B)
+    ms_e2e = timed(run, 1)
+    e2e_value = world * B * ns / (ms_e2e / 1e3)
+    if rank != 0:
+        return
+    peak_tf, peak_sus, peak_gbs, peak_src = measured_peaks()
+    n_ops = eng.lib.b2seg_plan_num_ops(eng.plan, 0)
+    buf = (C.c_float * n_ops)()
+    acc = np.zeros(n_ops)
+    for _ in range(3):
+        L.check(eng.lib.b2seg_plan_run_timed(eng.plan, 0, C.c_void_p(eng._stream()), buf, n_ops), "run_timed")
+        acc += np.array(list(buf))
+    acc /= 3
+    agg = {}
+    for i in range(n_ops):
+        info = eng.planner.op_info[(0, i)]
+        op, desc, _n = eng.planner.ops[0][i]
+        fam = CONV_FAM if info["op"] == L.OP_CONV else "streaming"
+        a = agg.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0, bytes=0.0))
+        a["ms"] += float(acc[i]); a["flops"] += info["flops"]; a["launches"] += 1
+        a["bytes"] += float(op_bytes(L, op, desc)) if fam == "streaming" else 0.0
+    a = agg[CONV_FAM]
+    tf = a["flops"] / (a["ms"] / 1e3) / 1e12
+    tot = sum(v["ms"] for v in agg.values())
+    st = agg.get("streaming", dict(ms=0.0, bytes=0.0, launches=0))
+    outs = out["y"] if isinstance(out["y"], list) else [out["y"]]
+    line = {"metric": f"BASELINE config {args.config} inference samples/s", "mode": "predict", "value": value, "unit": "images/s", "n_gpus": world, "steps": ns,
+            "warmup": args.warmup, "ms_per_step": ms / ns, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": {"workload": workload.replace("+ Adam(2e-4)", "").replace("BCE", "predict") + " [inference]", "global_batch": B * world,
+                                            "parallelism": f"dp{world} (batch split, no collective)", "l2_policy": L2_POLICY},
+            "roofline": {"bound": "tensor", "kernel": CONV_FAM, "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "frac_sustained": tf / peak_sus, "frac_spec": tf / SPEC_BF16_TFLOPS, "peak_source": peak_src, "kernel_ms_per_step": a["ms"],
+                         "kernel_share_of_step": a["ms"] / tot, "launches_per_step": a["launches"], "traffic": None,
+                         "families": {"streaming": {"ms_per_step": st["ms"], "launches": st["launches"],
+                                                    "gbs": st["bytes"] / (st["ms"] / 1e3) / 1e9 if st["ms"] else None,
+                                                    "hbm_frac": st["bytes"] / (st["ms"] / 1e3) / 1e9 / peak_gbs if st["ms"] else None}}},
+            "clocks": clocks, "cpu_baseline": None,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(sum(o.nbytes for o in outs) // ns),
+                    "ms_per_step": ms_e2e / ns, "api": "Model.predict(x, batch_size) over steps x batch pageable NumPy samples"},
+            "gpu_launches": int(eng.launches[0]) * ns, "launches_per_step": int(eng.launches[0]), "device_memory_gb": eng.memory_bytes() / 2 ** 30}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -261,6 +328,8 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops-json", default="", help="dump per-op device times (profiling aid)")
+    ap.add_argument("--mode", default="train", choices=["train", "predict"],
+                    help="predict: inference throughput of the same configs (BatchNorm folded into the kernels, batch split across GPUs with no collective)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json config (1-based). 2 = the headline workload; 3 / 4 / 5 are measured with the same machinery on request")
     args = ap.parse_args()
@@ -330,6 +399,9 @@ def main():
             ms = float(t.item())
         barrier()
         return ms
+
+    if args.mode == "predict":
+        return bench_predict(args, model, x, B, S, workload, rank, world, local, barrier, timed)
 
     # ---- device-resident arm (value)
     for _ in range(args.warmup):

@@ -53,7 +53,7 @@ class CpuEngine:
         self.loss_buf = self.mem.f32(p.loss_ptr, 1)
         from b2seg.planner import LOSS_BUF_FLOATS
         self.logs_buf = self.mem.f32(p.loss_ptr, LOSS_BUF_FLOATS)
-        n = max(p.n_train, 64)
+        n = p.arena_elems
         self.w, self.g = self.mem.f32(p.w_ptr, n), self.mem.f32(p.g_ptr, n)          # flat arenas (views), as Engine exposes them
         self.m, self.v = self.mem.f32(p.m_ptr, n), self.mem.f32(p.v_ptr, n)
         self.moving = self.mem.f32(p.mov_ptr, max(p.n_moving, 64))

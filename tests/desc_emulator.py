@@ -681,7 +681,8 @@ def emu_gate_bwd(mem, d):
     mem.f32(d.dgamma3, 1)[:] = prm["gamma3"].grad
     mem.f32(d.dbeta3, 1)[:] = prm["beta3"].grad
     mem.f32(d.dw3, C)[:] += prm["w3"].grad
-    mem.f32(d.db3, 1)[:] += prm["b3"].grad
+    if d.db3:
+        mem.f32(d.db3, 1)[:] += prm["b3"].grad
     mem.f32(d.dwt, 16 * d.wt_stride)[::d.wt_stride] += prm["wt"].grad
     mem.f32(d.dbt, 1)[:] += prm["bt"].grad
 

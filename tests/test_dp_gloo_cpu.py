@@ -52,7 +52,7 @@ def _fwd_bwd(mem, pl, x, y):
     mem.f32(pl.outputs[0]["target_ptr"], y.numel())[:] = y.reshape(-1).double()
     run_phase(mem, pl, 0)
     run_phase(mem, pl, 1)
-    return mem.f32(pl.g_ptr, max(pl.n_train, 64))
+    return mem.f32(pl.g_ptr, pl.arena_elems)
 
 
 def _data():
@@ -77,11 +77,11 @@ def _worker(rank, world, port, out):
     mem.f32(pl.input_ptr, xs.numel())[:] = xs.reshape(-1).double()
     mem.f32(pl.outputs[0]["target_ptr"], ys.numel())[:] = ys.reshape(-1).double()
     run_phase(mem, pl, 0)
-    grads = mem.f32(pl.g_ptr, max(pl.n_train, 64))
+    grads = mem.f32(pl.g_ptr, pl.arena_elems)
     sched = pl.exchange_schedule(bucket_bytes=4096)
     assert len(sched) >= 3 and sched[0][0] < len(pl.ops[1])          # the exchange really starts before backward ends
     covered = sorted((lo, hi) for (_, lo, hi) in sched)
-    assert covered[0][0] == 0 and covered[-1][1] == max(pl.n_train, 64) and all(a[1] == b_[0] for a, b_ in zip(covered, covered[1:]))
+    assert covered[0][0] == 0 and covered[-1][1] == pl.arena_elems and all(a[1] == b_[0] for a, b_ in zip(covered, covered[1:]))
     done = 0
     works = []
     for (n_ops, lo, hi) in sched:
@@ -96,7 +96,7 @@ def _worker(rank, world, port, out):
         desc.grad_scale = 1.0 / world
         wait_all(works[i])
         run_phase(mem, pl, 2, i, 1)
-    torch.save(mem.f32(pl.w_ptr, max(pl.n_train, 64)).clone(), os.path.join(out, f"w{rank}.pt"))
+    torch.save(mem.f32(pl.w_ptr, pl.arena_elems).clone(), os.path.join(out, f"w{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -116,9 +116,9 @@ def test_two_rank_data_parallel_step(tmp_path):
         gs.append(_fwd_bwd(mem, pl, x[2 * r:2 * r + 2], y[2 * r:2 * r + 2]).clone())
     g, mem, pl = _build(2)
     _fwd_bwd(mem, pl, x[:2], y[:2])
-    mem.f32(pl.g_ptr, max(pl.n_train, 64))[:] = (gs[0] + gs[1]) / 2
+    mem.f32(pl.g_ptr, pl.arena_elems)[:] = (gs[0] + gs[1]) / 2
     run_phase(mem, pl, 2)
-    ref = mem.f32(pl.w_ptr, max(pl.n_train, 64))
+    ref = mem.f32(pl.w_ptr, pl.arena_elems)
     assert torch.allclose(w0, ref, atol=1e-12)
     assert float((w0 - ref).abs().max()) < 1e-12
 

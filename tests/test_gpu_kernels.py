@@ -677,6 +677,8 @@ def test_fused_attention_gate(N, h, w, C, Cs, training):
     assert rel_l2(dzb.float().cpu().double(), zb64.grad) < 6e-3, rel_l2(dzb.float().cpu().double(), zb64.grad)
     for k_ in ("gamma_a", "beta_a", "gamma_b", "beta_b", "gamma3", "beta3"):
         assert rel_l2(G[k_].cpu().double(), R[k_].grad) < 2e-3, (k_, rel_l2(G[k_].cpu().double(), R[k_].grad))
-    for k_ in ("w3", "b3", "bt"):
+    for k_ in ("w3", "bt"):
         assert rel_l2(G[k_].cpu().double(), 2 * R[k_].grad) < 2e-3, (k_, rel_l2(G[k_].cpu().double(), 2 * R[k_].grad))
+    # b3 sits in front of a BatchNorm: analytically zero (the sum of a BatchNorm-backward output); the kernel's value is its rounding noise
+    assert abs(float(G["b3"])) < 1e-3 * float(G["w3"].abs().max()) * C ** 0.5 + 1e-4
     assert rel_l2(dwt[::stride].cpu().double(), 2 * R["wt"].grad) < 2e-3 and float(dwt.view(16, stride)[:, 1:].abs().max()) == 0

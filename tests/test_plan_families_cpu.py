@@ -258,7 +258,7 @@ def test_exchange_schedule_slices_are_final_when_released(dec, kw):
     ts, losses = _targets(g, 2, rng, 2)
     mem = PlanMem()
     pl = Planner(g, 2, mem.alloc_bytes, training=True, losses=losses, adam=dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7),
-                 adam_bucket_bytes=2048).build()
+                 adam_bucket_bytes=16384).build()
     params = init_params(g, seed=5)
     for e in pl.params:
         flat = torch.from_numpy(pl.to_internal(e.key, params[e.key])).double()
@@ -273,9 +273,9 @@ def test_exchange_schedule_slices_are_final_when_released(dec, kw):
     for o in pl.outputs:
         mem.f32(o["target_ptr"], ts[o["index"]].numel())[:] = ts[o["index"]].reshape(-1).double()
     run_phase(mem, pl, 0)
-    n = max(pl.n_train, 64)
+    n = pl.arena_elems
     grads = mem.f32(pl.g_ptr, n)
-    sched = pl.exchange_schedule(bucket_bytes=2048)
+    sched = pl.exchange_schedule(bucket_bytes=16384)
     covered = sorted((lo, hi) for (_, lo, hi) in sched)
     assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
     assert len(sched) >= 3 and sched[0][0] < len(pl.ops[1])

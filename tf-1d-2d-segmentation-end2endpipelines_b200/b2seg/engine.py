@@ -38,7 +38,7 @@ class Engine:
         self.reuse = reuse
         self.adam_bucket_bytes = adam_bucket_bytes
         p = self.planner
-        n = max(p.n_train, 64)
+        n = p.arena_elems
         self.w = self._typed("param_w", torch.float32, n)
         self.g = self._typed("param_g", torch.float32, n)
         self.m = self._typed("param_m", torch.float32, n)

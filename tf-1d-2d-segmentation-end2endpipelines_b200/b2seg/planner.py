@@ -161,7 +161,8 @@ ARENA_ALIGN = 1024
 class Planner:
     def __init__(self, graph: Graph, batch: int, alloc: Callable[[int], int], training: bool = True,
                  losses: Optional[List[str]] = None, loss_weights: Optional[List[float]] = None, adam=None,
-                 stat_rows_fn: Optional[Callable] = None, adam_bucket_bytes: int = 0, reuse: bool = False):
+                 stat_rows_fn: Optional[Callable] = None, adam_bucket_bytes: int = 0, reuse: bool = False, shard: Tuple[int, int] = (0, 1)):
+        self.shard = shard                  # (rank, world) of a sharded-optimizer data-parallel plan; (0, 1) = every rank updates everything
         self.stat_rows_fn = stat_rows_fn or conv_stat_rows
         # reuse: activation / gradient buffers share one arena by liveness (see _assign_memory); off = one allocation per tensor,
         # every tensor stays readable after the step (what the per-layer parity tests tap)
@@ -687,7 +688,7 @@ class Planner:
         for tag, bn in (("_a", gt["bn_a"]), ("_b", gt["bn_b"]), ("3", gt["bn3"])):
             setattr(d, "dgamma" + tag, self.pg(f"{bn.name}/gamma"))
             setattr(d, "dbeta" + tag, self.pg(f"{bn.name}/beta"))
-        d.dw3, d.db3 = self.pg(f"{gt['conv3'].name}/kernel"), self.pg(f"{gt['conv3'].name}/bias")
+        d.dw3, d.db3 = self.pg(f"{gt['conv3'].name}/kernel"), 0     # (conv3's bias feeds a BatchNorm: exactly zero gradient, not accumulated)
         d.dwt, d.dbt = self.pg(f"{gt['tconv'].name}/kernel"), self.pg(f"{gt['tconv'].name}/bias")
         self.emit(1, L.OP_GATE_BWD, d, f"gate bwd {n.name}")
         self._add_gsrc(gt["skip"], GSrc(dskip))
@@ -828,8 +829,14 @@ class Planner:
         return [po + i for (po, c) in self._segs(self._by_name[name]) for i in range(c)]
 
     # ---------------------------------------------------------------------------------------- arenas
+    @property
+    def arena_elems(self) -> int:
+        """length of the flat parameter / gradient / moment arenas: the trainable elements rounded up to 4096, so that any gradient
+        exchange bucket cut at a multiple of 4096 splits evenly over 1, 2, 4 or 8 ranks (64-element aligned shards)"""
+        return (max(self.n_train, 64) + 4095) // 4096 * 4096
+
     def bind_arenas(self):
-        n = max(self.n_train, 64)
+        n = self.arena_elems
         self.w_ptr = self.alloc(n * 4, "param_w")
         self.g_ptr = self.alloc(n * 4, "param_g")
         self.m_ptr = self.alloc(n * 4, "param_m")
@@ -864,7 +871,7 @@ class Planner:
         for u in self.units:
             getattr(self, "_fwd_" + u["kind"])(u)
         if self.training:
-            self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.g_ptr, max(self.n_train, 64) * 4), "zero grads")
+            self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.g_ptr, self.arena_elems * 4), "zero grads")
             self.emit(1, L.OP_MEMSET, L.MemsetDesc(self.loss_ptr, LOSS_BUF_FLOATS * 4), "zero loss")
             for u in reversed(self.units):
                 self._grad_touched = set()
@@ -872,9 +879,14 @@ class Planner:
                 for key in self._grad_touched:
                     self.grad_ready[key] = len(self.ops[1])
             a = self.adam
-            ranges = [(0, max(self.n_train, 64))]
+            ranges = [(0, self.arena_elems)]
             if self.adam_bucket_bytes > 0:
                 ranges = [(lo, hi) for (_n, lo, hi) in self.exchange_schedule(self.adam_bucket_bytes)]
+                rank, world = self.shard
+                if world > 1:
+                    # sharded optimizer: after the bucket's reduce-scatter this rank owns (and updates) one 1/world slice of it;
+                    # the bf16 shadow of the whole bucket comes back through an all-gather (Model._step)
+                    ranges = [(lo + rank * ((hi - lo) // world), lo + (rank + 1) * ((hi - lo) // world)) for (lo, hi) in ranges]
             for (lo, hi) in ranges:
                 self.emit(2, L.OP_ADAM, L.AdamDesc(self.w_ptr + 4 * lo, self.g_ptr + 4 * lo, self.m_ptr + 4 * lo, self.v_ptr + 4 * lo,
                                                    self.wb_ptr + 2 * lo, hi - lo, a["lr"], a["beta1"], a["beta2"], a["eps"], 1.0, 1),
@@ -1930,22 +1942,27 @@ class Planner:
     def exchange_schedule(self, bucket_bytes: int = 64 << 20) -> List[Tuple[int, int, int]]:
         """Data-parallel gradient exchange overlapped with backward: [(n_ops, lo, hi)] in execution
         order — once the first n_ops backward ops are enqueued, the gradient arena elements [lo, hi) are final and
-        their all-reduce may start.  Backward walks the layers in reverse, and the arena is laid out in layer order,
-        so finished gradients form a suffix of the arena that grows towards offset 0; a bucket closes when it holds
-        bucket_bytes.  Gradients no backward op writes (conv biases feeding a BatchNormalization: analytically zero) are
-        final once the two memsets that open the backward phase have run."""
+        their exchange may start.  Backward walks the layers in reverse, and the arena is laid out in layer order,
+        so finished gradients form a suffix of the arena that grows towards offset 0.  Buckets are cut top-down at
+        multiples of 4096 elements (Adam is element-wise, so a bucket may split a tensor; 4096 makes every bucket
+        divisible into 64-aligned shards for 2, 4 or 8 ranks).  A bucket is ready when every tensor it touches is;
+        gradients no backward op writes (conv biases feeding a BatchNormalization: analytically zero) are final once
+        the two memsets that open the backward phase have run."""
         n_total = len(self.ops[1])
         untouched = min(2, n_total)
-        entries = sorted((e for e in self.params if e.trainable), key=lambda e: -e.offset)
-        out, hi, ready, size = [], max(self.n_train, 64), 0, 0
-        for e in entries:
-            ready = max(ready, self.grad_ready.get(e.key, untouched))
-            size += e.size * 4
-            if size >= bucket_bytes:
-                out.append((ready, e.offset, hi))
-                hi, size = e.offset, 0
-        if hi > 0:
-            out.append((max(ready, 1) if entries else n_total, 0, hi))
+        step = max(4096, bucket_bytes // 4 // 4096 * 4096)
+        entries = sorted((e for e in self.params if e.trainable), key=lambda e: e.offset)
+        out, hi = [], self.arena_elems
+        while hi > 0:
+            lo = max(0, hi - step)
+            if lo < step // 2:           # do not leave a sliver for the last bucket
+                lo = 0
+            ready = untouched
+            for e in entries:
+                if e.offset < hi and e.offset + e.size > lo:
+                    ready = max(ready, self.grad_ready.get(e.key, untouched))
+            out.append((ready, lo, hi))
+            hi = lo
         # a later bucket can never start before an earlier one (single stream of backward ops)
         fixed, floor = [], 0
         for (r, lo, h) in out:

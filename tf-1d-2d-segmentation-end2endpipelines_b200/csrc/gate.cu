@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) gate_mid_bwd_kernel(const GateK k, int cv
     load8(vaddr(k.za, (int)n, y, x, c0), a);
     load8(vaddr(k.zb, (int)n, y, x, c0), b);
     if (PASS == 0) {
-      if (blockIdx.x == 0 && tcv == 0) acc_db3 += dz3;
+      if (blockIdx.x == 0 && tcv == 0 && k.db3) acc_db3 += dz3;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float c = fmaf(a[e], sa[e], ta[e]) + fmaf(b[e], sb[e], tb[e]);
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) gate_mid_bwd_kernel(const GateK k, int cv
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       float s = 0.f;
       for (int r = 0; r < rows; ++r) s += red[(r * cvb) * 33 + 32];
-      atomicAdd(k.db3, s);
+      if (k.db3) atomicAdd(k.db3, s);    // (null: the bias feeds a BatchNorm, its gradient is analytically zero and the caller keeps it exactly 0)
     }
   } else if (blockIdx.y == 0 && trow == 0) {
     // BatchNorm parameter gradients of the two branches and of the one-channel map (plain stores: each belongs to this gate only)
@@ -455,7 +455,7 @@ static int fill_gate(const b2seg_gate_desc* d, GateK* k, bool bwd) {
   } else {
     if (!d->training) { set_error("gate: backward of an inference plan"); return -1; }
     if (!d->dout.ptr || !d->dskip.ptr || !d->dza.ptr || !d->dzb.ptr || !d->dr || !d->g3 || !d->bsums3 || !d->bsums_ab || !d->dgamma_a || !d->dbeta_a ||
-        !d->dgamma_b || !d->dbeta_b || !d->dw3 || !d->db3 || !d->dgamma3 || !d->dbeta3 || !d->dwt || !d->dbt) { set_error("gate: null backward pointer"); return -1; }
+        !d->dgamma_b || !d->dbeta_b || !d->dw3 || !d->dgamma3 || !d->dbeta3 || !d->dwt || !d->dbt) { set_error("gate: null backward pointer"); return -1; }
   }
   return 0;
 }

@@ -27,6 +27,42 @@ __global__ void cast_input_kernel(const float* __restrict__ src, int N, int H, i
 // image and in the padding lanes.  A k x k convolution that reads the (thin: 1-3 channel) input becomes a 1x1 convolution over
 // this tensor: ONE 128-byte-row tap on the tensor cores instead of kh*kw taps that each hold 8 real channels (the 3 -> 64 first
 // layer of config 2 took 0.22 ms forward + 0.25 ms weight gradient for 0.02 ms of math, profiles/r1_tile_trace.txt).
+// One thread per output pixel: the kh rows of its window are kw*C consecutive floats each (neighbouring threads overlap, L1 serves
+// the re-reads), written as KP/8 16-byte vectors — consecutive threads write consecutive KP*2-byte records.  (A first version with
+// one thread per output vector and per-element index arithmetic ran at 0.6 TB/s: 0.26 ms for the 134 MB of config 2.)
+template <int KH, int KW, int C, int KP>
+__global__ void __launch_bounds__(256) im2col_input_kernel_t(const float* __restrict__ src, int N, int H, int W, DView out) {
+  constexpr int PH = (KH - 1) / 2, PW = (KW - 1) / 2;
+  const unsigned total = (unsigned)N * H * W;
+  for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+    const int w = (int)(pix % W);
+    const unsigned t = pix / W;
+    const int h = (int)(t % H), n = (int)(t / H);
+    float f[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) f[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+      const int hh = h + i - PH;
+      if (hh < 0 || hh >= H) continue;
+      const float* row = src + (((long long)n * H + hh) * W + (w - PW)) * C;
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        const int ww = w + j - PW;
+        if (ww < 0 || ww >= W) continue;
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[(i * KW + j) * C + c] = __ldg(row + j * C + c);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < KP / 8; ++v) {
+      float g[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = f[v * 8 + e];
+      store8(vaddr(out, n, h, w, v * 8), g);
+    }
+  }
+}
 __global__ void im2col_input_kernel(const float* __restrict__ src, int N, int H, int W, int C, int kh, int kw, DView out) {
   const int cv = out.C / 8;
   const int K = kh * kw * C;
@@ -57,8 +93,16 @@ struct CastLaunch : PreparedOp {
   b2seg_cast_desc d;
   int launch(cudaStream_t s) override {
     const long long work = (long long)d.N * d.H * d.W * (d.out.C / 8);
-    if (d.kh * d.kw > 1)
-      im2col_input_kernel<<<grid_for(work, 256), 256, 0, s>>>(reinterpret_cast<const float*>(d.src), d.N, d.H, d.W, d.C, d.kh, d.kw, dv(d.out));
+    const float* src = reinterpret_cast<const float*>(d.src);
+    const int gp = grid_for((long long)d.N * d.H * d.W, 256);
+    if (d.kh == 3 && d.kw == 3 && d.C == 3 && d.out.C == 32)
+      im2col_input_kernel_t<3, 3, 3, 32><<<gp, 256, 0, s>>>(src, d.N, d.H, d.W, dv(d.out));
+    else if (d.kh == 3 && d.kw == 3 && d.C == 1 && d.out.C == 16)
+      im2col_input_kernel_t<3, 3, 1, 16><<<gp, 256, 0, s>>>(src, d.N, d.H, d.W, dv(d.out));
+    else if (d.kh == 1 && d.kw == 3 && d.C == 1 && d.out.C == 8)
+      im2col_input_kernel_t<1, 3, 1, 8><<<gp, 256, 0, s>>>(src, d.N, d.H, d.W, dv(d.out));
+    else if (d.kh * d.kw > 1)
+      im2col_input_kernel<<<grid_for(work, 256), 256, 0, s>>>(src, d.N, d.H, d.W, d.C, d.kh, d.kw, dv(d.out));
     else
       cast_input_kernel<<<grid_for(work, 256), 256, 0, s>>>(reinterpret_cast<const float*>(d.src), d.N, d.H, d.W, d.C, dv(d.out));
     B2_CUDA_OK(cudaGetLastError());

@@ -593,8 +593,8 @@ struct FoldLaunch : PreparedOp {
   }
 };
 PreparedOp* prepare_fold_bn(const b2seg_fold_desc* d) {
-  if (!d->w || !d->gamma || !d->beta || !d->moving_mean || !d->moving_var || !d->w_folded || !d->bias_folded || d->cout_p < 1 || d->row < d->cout_p) {
-    set_error("fold_bn: bad arguments (row %d must be >= cout_p %d)", d->row, d->cout_p);
+  if (!d->w || !d->gamma || !d->beta || !d->moving_mean || !d->moving_var || !d->w_folded || !d->bias_folded || d->cout_p < 1 || d->row < 1) {
+    set_error("fold_bn: bad arguments (cout_p %d, row %d)", d->cout_p, d->row);
     return nullptr;
   }
   auto* L = new FoldLaunch(); L->d = *d; return L;
