@@ -18,7 +18,7 @@ _PARAM_TAGS = ("param_w", "param_g", "param_m", "param_v", "param_wb", "moving")
 
 class CpuEngine:
     def __init__(self, graph, batch, training=True, losses=None, loss_weights=None, adam=None, device=None, share_params_from=None,
-                 adam_bucket_bytes=0, reuse=False):
+                 adam_bucket_bytes=0, reuse=False, shard=(0, 1)):
         self.graph, self.batch, self.training = graph, batch, training
         self.mem = PlanMem()
         self._tag_ptr = {}
@@ -39,7 +39,7 @@ class CpuEngine:
                 self._tag_ptr[tag] = ptr
             return ptr
         self.planner = p = Planner(graph, batch, alloc, training=training, losses=losses, loss_weights=loss_weights,
-                                   adam=adam, adam_bucket_bytes=adam_bucket_bytes, reuse=reuse).build()
+                                   adam=adam, adam_bucket_bytes=adam_bucket_bytes, reuse=reuse, shard=shard).build()
         self.reuse = reuse
         self.adam_bucket_bytes = adam_bucket_bytes
         H, W, Cin = graph.inputs[0].shape
@@ -57,7 +57,7 @@ class CpuEngine:
         self.w, self.g = self.mem.f32(p.w_ptr, n), self.mem.f32(p.g_ptr, n)          # flat arenas (views), as Engine exposes them
         self.m, self.v = self.mem.f32(p.m_ptr, n), self.mem.f32(p.v_ptr, n)
         self.moving = self.mem.f32(p.mov_ptr, max(p.n_moving, 64))
-        self.wb = self.w                                                              # (no separate bf16 shadow worth modelling)
+        self.wb = self.mem.f32(p.wb_ptr, n)                                           # the copy the emulated kernels read (bf16 on the device)
         self.step = 0
         self.dev = torch.device("cpu")
         self._shared = share_params_from

@@ -170,7 +170,14 @@ def _facade_worker(rank, world, port, out):
         eng.w.mul_(1.5)
     m.broadcast_weights(0)
     loss = m.train_on_batch(x[b:e].numpy(), y[b:e].numpy())
-    torch.save(dict(w=eng.w.clone(), loss=loss), os.path.join(out, f"facade{rank}.pt"))
+    assert eng.planner.shard == (rank, world)    # sharded optimizer: each rank updated its slice of every bucket, the kernels' copy was all-gathered
+    wb = eng.wb.clone()
+    own = torch.cat([eng.w[lo + rank * ((hi - lo) // world):lo + (rank + 1) * ((hi - lo) // world)] for (_n, lo, hi) in m._exchange_schedule(eng)])
+    m.gather_master_weights()                    # collective: the fp32 masters of the other ranks' slices
+    assert torch.equal(wb, eng.w)                # (the emulator's "bf16" copy is float64: identical to the gathered masters)
+    loss2 = m.train_on_batch(x[b:e].numpy(), y[b:e].numpy())    # a second step starts from the all-gathered weights
+    m.gather_master_weights()
+    torch.save(dict(w=eng.w.clone(), loss=loss, loss2=loss2, own=own), os.path.join(out, f"facade{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -197,4 +204,20 @@ def test_two_rank_step_through_the_facade(tmp_path, monkeypatch):
         grads.append(eng.g.clone())
     eng.g[:] = (grads[0] + grads[1]) / 2
     eng.optimizer_step(1e-2, 1.0)
+    # second step of the reference: both replicas from the updated weights
+    w1 = eng.w.clone()
+    grads = []
+    for (b, e) in ((0, 2), (2, 4)):
+        eng.x_dev.copy_(x[b:e])
+        eng.outputs[0]["target"].copy_(y[b:e])
+        eng.derive_targets()
+        eng.w.copy_(w1)
+        eng.wb.copy_(w1)
+        eng.forward()
+        eng.backward()
+        grads.append(eng.g.clone())
+    eng.w.copy_(w1)
+    eng.g[:] = (grads[0] + grads[1]) / 2
+    eng.optimizer_step(1e-2, 1.0)
     assert torch.allclose(r0["w"], eng.w, atol=1e-12, rtol=0), float((r0["w"] - eng.w).abs().max())
+    assert r0["loss2"] < r0["loss"] or r1["loss2"] < r1["loss"]

@@ -26,6 +26,27 @@ def wait_all(works):
         w.wait()
 
 
+def reduce_scatter_bucket_(flat, lo: int, hi: int, rank: int, world: int, group=None):
+    """sum-reduce-scatter of flat[lo:hi] in place: afterwards this rank's 1/world slice of the bucket holds the sum over ranks (the
+    other slices are scratch).  NCCL: one reduce_scatter_tensor whose output aliases the rank's slice of the input (in-place form);
+    gloo (CPU tests) has no reduce-scatter: an all-reduce of the bucket gives the same slice.  Returns the async work handle."""
+    import torch.distributed as dist
+    n = (hi - lo) // world
+    if dist.get_backend(group) == "gloo":
+        return dist.all_reduce(flat[lo:hi], group=group, async_op=True)
+    return dist.reduce_scatter_tensor(flat[lo + rank * n:lo + (rank + 1) * n], flat[lo:hi], group=group, async_op=True)
+
+
+def all_gather_bucket_(flat, lo: int, hi: int, rank: int, world: int, group=None):
+    """all-gather of the ranks' 1/world slices of flat[lo:hi] in place (every rank ends with the whole bucket)"""
+    import torch.distributed as dist
+    n = (hi - lo) // world
+    if dist.get_backend(group) == "gloo":
+        return dist.all_gather([flat[lo + r * n:lo + (r + 1) * n] for r in range(world)], flat[lo + rank * n:lo + (rank + 1) * n].clone(),
+                               group=group, async_op=True)
+    return dist.all_gather_into_tensor(flat[lo:hi], flat[lo + rank * n:lo + (rank + 1) * n], group=group, async_op=True)
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """[begin, end) of the samples rank `rank` handles when n samples are split as evenly as possible"""
     base, rem = divmod(n, world)

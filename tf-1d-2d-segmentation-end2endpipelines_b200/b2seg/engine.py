@@ -21,7 +21,7 @@ from .planner import Planner
 class Engine:
     def __init__(self, graph: Graph, batch: int, training: bool = True, losses: Optional[List[str]] = None,
                  loss_weights: Optional[List[float]] = None, adam: Optional[dict] = None, device: Optional[int] = None,
-                 share_params_from: Optional["Engine"] = None, adam_bucket_bytes: int = 0, reuse: bool = False):
+                 share_params_from: Optional["Engine"] = None, adam_bucket_bytes: int = 0, reuse: bool = False, shard=(0, 1)):
         if not torch.cuda.is_available():
             raise L.B2SegError("b2seg needs a CUDA sm_100 (B200) device: the hot path has no CPU fallback")
         self.device = torch.cuda.current_device() if device is None else device
@@ -34,7 +34,7 @@ class Engine:
         self.dev = torch.device("cuda", self.device)
         self.planner = Planner(graph, batch, self._alloc, training=training, losses=losses, loss_weights=loss_weights, adam=adam,
                                stat_rows_fn=lambda d: self.lib.b2seg_conv_num_stat_rows(C.byref(d)),
-                               adam_bucket_bytes=adam_bucket_bytes, reuse=reuse).build()
+                               adam_bucket_bytes=adam_bucket_bytes, reuse=reuse, shard=shard).build()
         self.reuse = reuse
         self.adam_bucket_bytes = adam_bucket_bytes
         p = self.planner

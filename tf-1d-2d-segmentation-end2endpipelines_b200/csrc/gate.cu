@@ -160,7 +160,7 @@ __device__ __forceinline__ float gate_m(const GateK& k, int n, int y, int x, flo
 // resampler value at high-resolution pixel (oy, ox) of image n.
 //   bilinear x2, half-pixel centres, edge clamp (tf.image.resize): even o = 2i: 0.25 m[i-1] + 0.75 m[i]; odd o = 2i+1: 0.75 m[i] + 0.25 m[i+1]
 //   Conv2DTranspose(4x4, s2, 'same') == ConvTranspose2d(k4, s2, p1): o = 2i - 1 + ky: even o: (ky=1, i), (ky=3, i-1); odd o: (ky=2, i), (ky=0, i+1)
-__device__ __forceinline__ Resampler gate_resample(const GateK& k, int n, int oy, int ox, float sc, float sh, const float (&wt)[16], float bt) {
+__device__ __forceinline__ Resampler gate_resample(const GateK& k, int n, int oy, int ox, float sc, float sh, const float* wt, float bt) {
   const int iy = oy >> 1, ix = ox >> 1;
   const int py = oy & 1, px = ox & 1;
   const int y2 = py ? iy + 1 : iy - 1, x2 = px ? ix + 1 : ix - 1;      // the second source row / column
@@ -185,22 +185,23 @@ __device__ __forceinline__ Resampler gate_resample(const GateK& k, int n, int oy
 // ------------------------------------------------------------------------------------------ forward / backward, high resolution
 // Block = 256 threads = one segment of GP pixels of one high-resolution row; r per pixel is computed once into shared memory,
 // then the (pixel, 8-channel vector) pairs are streamed.  BWD: dskip = dout * r and dr = sum_c dout * skip (per-pixel reduction).
-constexpr int kGateSeg = 64;
+constexpr int kGateSeg = 256;
+constexpr int kGateU = 4;      // (pixel, vector) items in flight per thread
 template <bool BWD>
 __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
   pdl_prologue();
   __shared__ float s_r[kGateSeg];
   __shared__ float s_dr[kGateSeg];
+  __shared__ float s_wt[16];
   float sc, sh, mu, rs;
   bn3_coeffs(k, &sc, &sh, &mu, &rs);
-  float wt[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) wt[i] = k.wt[i * k.wt_stride];
+  if (threadIdx.x < 16) s_wt[threadIdx.x] = k.wt[threadIdx.x * k.wt_stride];
   const float bt = k.bt[0];
   const int W2 = 2 * k.w, H2 = 2 * k.h;
   const int segs_per_row = (W2 + kGateSeg - 1) / kGateSeg;
   const int total_segs = k.skip.N * H2 * segs_per_row;
   const int vpp = k.skip.C >> 3;
+  const int span = vpp < 32 ? vpp : 32;
   if (!BWD && blockIdx.x == 0 && threadIdx.x == 0 && k.training) {
     const float var = fmaxf(k.sums3[1] * k.inv_count - mu * mu, 0.f);
     const float uv = (k.bessel && k.count > 1.f) ? var * k.count / (k.count - 1.f) : var;
@@ -215,38 +216,54 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
     const int npx = W2 - x0 < kGateSeg ? W2 - x0 : kGateSeg;
     __syncthreads();
     if ((int)threadIdx.x < npx) {
-      s_r[threadIdx.x] = gate_resample(k, (int)n, oy, x0 + threadIdx.x, sc, sh, wt, bt).r;
+      s_r[threadIdx.x] = gate_resample(k, (int)n, oy, x0 + threadIdx.x, sc, sh, s_wt, bt).r;
       if (BWD) s_dr[threadIdx.x] = 0.f;
     }
     __syncthreads();
     const int work = npx * vpp;
     // (uniform trip count: the warp shuffles below need every lane, also in the ragged last round)
-    for (int i0 = 0; i0 < work; i0 += 256) {
-      const int i = i0 + (int)threadIdx.x;
-      const bool live = i < work;
-      const int p = live ? i / vpp : 0, v = live ? i - p * vpp : 0;
-      float s[8], o[8];
+    for (int i0 = 0; i0 < work; i0 += 256 * kGateU) {
+      uint4 sv[kGateU], dv4[kGateU];
+      int pp[kGateU], vv[kGateU];
+      bool live[kGateU];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] = 0.f;
-      if (live) load8(vaddr(k.skip, (int)n, oy, x0 + p, v * 8), s);
-      const float r = s_r[p];
-      if (!BWD) {
+      for (int u = 0; u < kGateU; ++u) {
+        const int i = i0 + u * 256 + (int)threadIdx.x;
+        live[u] = i < work;
+        pp[u] = live[u] ? i / vpp : 0;
+        vv[u] = live[u] ? i - pp[u] * vpp : 0;
+        sv[u] = make_uint4(0u, 0u, 0u, 0u);
+        dv4[u] = sv[u];
+        if (live[u]) {
+          sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.skip, (int)n, oy, x0 + pp[u], vv[u] * 8)));
+          if (BWD) dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, (int)n, oy, x0 + pp[u], vv[u] * 8)));
+        }
+      }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = s[e] * r;
-        if (live) store8(vaddr(k.out, (int)n, oy, x0 + p, v * 8), o);
-      } else {
-        float d[8];
+      for (int u = 0; u < kGateU; ++u) {
+        if (i0 + u * 256 >= work) break;          // warp-uniform (whole 256-item rounds)
+        float s[8], o[8];
+        const __nv_bfloat162* hs = reinterpret_cast<const __nv_bfloat162*>(&sv[u]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] = 0.f;
-        if (live) load8(vaddr(k.dout, (int)n, oy, x0 + p, v * 8), d);
-        float part = 0.f;
+        for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(hs[e]); s[2 * e] = t.x; s[2 * e + 1] = t.y; }
+        const float r = s_r[pp[u]];
+        if (!BWD) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { o[e] = d[e] * r; part = fmaf(d[e], s[e], part); }
-        if (live) store8(vaddr(k.dskip, (int)n, oy, x0 + p, v * 8), o);
-        // lanes holding the same pixel are adjacent (vpp is a power of two): reduce within the warp first
-        const int span = vpp < 32 ? vpp : 32;
-        for (int off = span >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-        if (live && (threadIdx.x & (span - 1)) == 0) atomicAdd(&s_dr[p], part);
+          for (int e = 0; e < 8; ++e) o[e] = s[e] * r;
+          if (live[u]) store8(vaddr(k.out, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
+        } else {
+          float d[8];
+          const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&dv4[u]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(hd[e]); d[2 * e] = t.x; d[2 * e + 1] = t.y; }
+          float part = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { o[e] = d[e] * r; part = fmaf(d[e], s[e], part); }
+          if (live[u]) store8(vaddr(k.dskip, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
+          // lanes holding the same pixel are adjacent (vpp is a power of two): reduce within the warp first
+          for (int off = span >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+          if (live[u] && (threadIdx.x & (span - 1)) == 0) atomicAdd(&s_dr[pp[u]], part);
+        }
       }
     }
     if (BWD) {
@@ -263,9 +280,9 @@ __global__ void __launch_bounds__(256) gate_low_bwd_kernel(const GateK k) {
   pdl_prologue();
   float sc, sh, mu, rs;
   bn3_coeffs(k, &sc, &sh, &mu, &rs);
-  float wt[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) wt[i] = k.wt[i * k.wt_stride];
+  __shared__ float wt[16];
+  if (threadIdx.x < 16) wt[threadIdx.x] = k.wt[threadIdx.x * k.wt_stride];
+  __syncthreads();
   const float bt = k.bt[0];
   const int W2 = 2 * k.w, H2 = 2 * k.h;
   float acc[19];      // [0..15] dwt, [16] dbt, [17] sum g3, [18] sum g3 * zhat3
