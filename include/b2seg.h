@@ -127,6 +127,14 @@ typedef struct b2seg_bn_act_desc {
   int32_t pool_h, pool_w; /* 0/1 = none */
   b2seg_view pooled;
   int32_t c_valid;        /* channels >= c_valid (padding lanes) are written as 0; 0 = all valid */
+  /* MultiResBlock / ResPath glue fused into the apply (unet_variants.py:96-99, 108-112), both optional:
+   *   add:       y = act(x*scale + shift + add)  -- Add([shortcut, BatchNormalization(concat)]) + Activation('relu') in the BN apply
+   *   out_stats: fp32 [2][C], caller-zeroed: per-channel sum of y and y^2 (of the stored bf16 values) are added into it -- the batch
+   *              statistics of the BatchNormalization that consumes y, which then needs no statistics pass (b2seg_colstats) */
+  b2seg_view add;
+  uint64_t out_stats;
+  int32_t out_stats_pitch;   /* floats between the row of sums and the row of sums of squares (0 = C); > C when x is one channel window
+                              * of a wider tensor whose BatchNormalization owns the accumulator */
 } b2seg_bn_act_desc;
 
 typedef struct b2seg_gradsrc {
@@ -159,6 +167,8 @@ typedef struct b2seg_bn_bwd_desc {
   uint64_t dgamma, dbeta;         /* fp32 [C] outputs */
   b2seg_view dx;                  /* bf16 output */
   int32_t accumulate;
+  int32_t x_relu_mask;            /* 1: x is the output of a ReLU whose only reader is this BatchNormalization: dx *= (x > 0), i.e. dx is the
+                                   * gradient in front of that ReLU and no separate activation-backward pass runs (MultiResBlock :97-99) */
 } b2seg_bn_bwd_desc;
 
 /* Fused Adam (utils/tf_optimizers.py:11; Keras-2 update rule): flat fp32 master weights, fp32 grads,

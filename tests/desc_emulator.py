@@ -223,11 +223,20 @@ def emu_bn_act(mem, d):
     C = d.x.C
     sc = mem.f32(d.scale, C) if d.scale else torch.ones(C, dtype=torch.float64)
     sf = mem.f32(d.shift, C) if d.shift else torch.zeros(C, dtype=torch.float64)
-    y = _act(x * sc + sf, d.act)
+    pre = x * sc + sf
+    if d.add.ptr:
+        pre = pre + mem.gather_view(d.add)
+    y = _act(pre, d.act)
     if d.c_valid:
         y[..., d.c_valid:] = 0
     for i in range(d.n_out):
         mem.write_view(d.out[i], y)
+    if d.out_stats:          # sums of the values as stored (bf16 on the device), added into caller-zeroed accumulators
+        ys = mem.gather_view(d.out[0]).reshape(-1, C)
+        pitch = d.out_stats_pitch or C
+        st = mem.f32(d.out_stats, pitch + C)
+        st[:C] += ys.sum(0)
+        st[pitch:pitch + C] += (ys * ys).sum(0)
     ph, pw = max(d.pool_h, 1), max(d.pool_w, 1)
     if ph > 1 or pw > 1:
         N, H, W, _ = y.shape
@@ -275,6 +284,8 @@ def emu_bn_bwd(mem, d):
         dx = sc * (g - dbeta / d.count - xh * dgamma / d.count)
     else:
         dx = g
+    if d.x_relu_mask:
+        dx = dx * (x > 0)
     mem.write_view(d.dx, dx)
 
 

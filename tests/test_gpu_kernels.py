@@ -682,3 +682,58 @@ def test_fused_attention_gate(N, h, w, C, Cs, training):
     # b3 sits in front of a BatchNorm: analytically zero (the sum of a BatchNorm-backward output); the kernel's value is its rounding noise
     assert abs(float(G["b3"])) < 1e-3 * float(G["w3"].abs().max()) * C ** 0.5 + 1e-4
     assert rel_l2(dwt[::stride].cpu().double(), 2 * R["wt"].grad) < 2e-3 and float(dwt.view(16, stride)[:, 1:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("N,H,W,Cc,Ctot,off,use_add", [(2, 16, 16, 72, 72, 0, True), (3, 7, 9, 16, 40, 8, False), (2, 32, 8, 64, 64, 0, True), (1, 5, 5, 24, 72, 48, False)])
+def test_bn_apply_with_fused_add_and_output_statistics(N, H, W, Cc, Ctot, off, use_add):
+    """MultiResBlock / ResPath glue: y = ReLU(x * scale + shift + add) with the column sums of y (as stored) added into an accumulator
+    row pair of a WIDER tensor (pitch = Ctot, this tensor is the channel window [off, off + Cc)); then the BatchNorm backward of a
+    layer whose input is that ReLU folds the ReLU mask in (x_relu_mask)"""
+    dev = "cuda"
+    x = bf(torch.randn(N, H, W, Cc, device=dev))
+    add = bf(torch.randn(N, H, W, Cc, device=dev)) if use_add else None
+    scale, shift = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.2
+    wide = torch.full((N, H, W, Ctot), 5.0, device=dev, dtype=torch.bfloat16)
+    acc = torch.zeros(2 * Ctot, device=dev)
+    d = L.BnActDesc()
+    d.x, d.scale, d.shift, d.act, d.n_out = tv(x).to_c(), scale.data_ptr(), shift.data_ptr(), L.ACT_RELU, 1
+    d.out[0] = tv(wide, off, Cc).to_c()
+    if use_add:
+        d.add = tv(add).to_c()
+    d.out_stats, d.out_stats_pitch = acc.data_ptr() + 4 * off, Ctot
+    for _ in range(2):                      # accumulates: two launches = twice the sums
+        L.call("b2seg_bn_act", d, stream())
+    torch.cuda.synchronize()
+    y = F.relu(x.float() * scale + shift + (add.float() if use_add else 0.0))
+    got = wide[..., off:off + Cc]
+    assert rel_l2(got.float(), y) < 4e-3
+    if off:
+        assert torch.all(wide[..., :off] == 5.0)
+    gs = got.float().reshape(-1, Cc)
+    assert torch.allclose(acc[off:off + Cc], 2 * gs.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(acc[Ctot + off:Ctot + off + Cc], 2 * (gs * gs).sum(0), rtol=1e-4, atol=1e-2)
+    assert float(acc[:off].abs().max() if off else 0.0) == 0.0
+    # ---- BatchNorm backward of the layer that reads got (= ReLU output): dx masked by got > 0
+    s = got.contiguous()
+    sf = s.float().reshape(-1, Cc)
+    gamma, beta = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.1
+    mean, var = sf.mean(0), sf.var(0, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-3)
+    sc2, sh2 = (gamma * rstd).contiguous(), (beta - mean * gamma * rstd).contiguous()
+    g = bf(torch.randn(N, H, W, Cc, device=dev))
+    dgamma, dbeta, dx = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev), torch.zeros_like(s)
+    part = torch.zeros(32 * 2 * Cc, device=dev)
+    bd = L.BnBwdDesc()
+    bd.x, bd.scale, bd.shift, bd.mean, bd.rstd = tv(s).to_c(), sc2.data_ptr(), sh2.data_ptr(), mean.contiguous().data_ptr(), rstd.contiguous().data_ptr()
+    bd.act, bd.n_src = L.ACT_NONE, 1
+    bd.src[0] = L.GradSrc(tv(g).to_c(), 0, 1, 1)
+    bd.count, bd.partials, bd.n_blocks = float(N * H * W), part.data_ptr(), 32
+    bd.dgamma, bd.dbeta, bd.dx, bd.x_relu_mask = dgamma.data_ptr(), dbeta.data_ptr(), tv(dx).to_c(), 1
+    L.call("b2seg_bn_bwd", bd, stream())
+    torch.cuda.synchronize()
+    pre = (x.float() * scale + shift + (add.float() if use_add else 0.0)).requires_grad_(True)   # gradient in front of the ReLU
+    st = F.relu(pre)
+    # the forward values are the stored ones: straight-through so that the statistics match what the kernel saw
+    st = st + (s.float() - st).detach()
+    mu_, var_ = st.reshape(-1, Cc).mean(0), st.reshape(-1, Cc).var(0, unbiased=False)
+    ((st - mu_) * torch.rsqrt(var_ + 1e-3) * gamma + beta).mul(g.float()).sum().backward()
+    assert rel_l2(dx.float(), pre.grad) < 8e-3, rel_l2(dx.float(), pre.grad)

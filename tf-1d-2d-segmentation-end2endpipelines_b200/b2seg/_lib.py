@@ -65,7 +65,8 @@ class BnFinalizeDesc(C.Structure):
 
 class BnActDesc(C.Structure):
     _fields_ = [("x", View), ("scale", C.c_uint64), ("shift", C.c_uint64), ("act", C.c_int32), ("n_out", C.c_int32),
-                ("out", View * 2), ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("pooled", View), ("c_valid", C.c_int32)]
+                ("out", View * 2), ("pool_h", C.c_int32), ("pool_w", C.c_int32), ("pooled", View), ("c_valid", C.c_int32),
+                ("add", View), ("out_stats", C.c_uint64), ("out_stats_pitch", C.c_int32)]
 
 
 class GradSrc(C.Structure):
@@ -77,7 +78,7 @@ class BnBwdDesc(C.Structure):
     _fields_ = [("x", View), ("scale", C.c_uint64), ("shift", C.c_uint64), ("mean", C.c_uint64), ("rstd", C.c_uint64),
                 ("act", C.c_int32), ("n_src", C.c_int32), ("src", GradSrc * MAX_GRADSRC), ("count", C.c_double),
                 ("partials", C.c_uint64), ("n_blocks", C.c_int32), ("dgamma", C.c_uint64), ("dbeta", C.c_uint64),
-                ("dx", View), ("accumulate", C.c_int32)]
+                ("dx", View), ("accumulate", C.c_int32), ("x_relu_mask", C.c_int32)]
 
 
 class AdamDesc(C.Structure):

@@ -524,6 +524,80 @@ class Planner:
         for u in self.units:
             if u.get("pool") is not None:
                 self.unit_of_out[id(u["pool"])] = u
+        self._plan_bn_glue()
+    # ---------------------------------------------------------------------------------------- MultiResBlock / ResPath glue
+    def _plan_bn_glue(self):
+        """Per-level fusion of the MultiResBlock / ResPath chains (2DCNN/models/unet_variants.py:85-122; 1DCNN :173-219).  Every
+        BatchNormalization is a grid-wide reduction, i.e. a kernel boundary in training; what goes is every pass that only moves data:
+          * a BatchNormalization whose input is a concat of Conv_Block outputs, or the output of Add + ReLU, gets its batch
+            statistics from the kernels that WRITE that input (bn_act.out_stats) instead of a statistics pass of its own;
+          * BatchNormalization(concat) -> Add([shortcut, .]) -> ReLU is one pass (bn_act.add): the normalised tensor and the sum are
+            never written;
+          * the backward of that ReLU is folded into the backward of the BatchNormalization that reads it (bn_bwd.x_relu_mask).
+        B2SEG_NO_BN_GLUE=1 keeps the op-by-op lowering."""
+        if os.environ.get("B2SEG_NO_BN_GLUE"):
+            return
+        relu = ("relu", "ReLU")
+
+        def add_relu_unit(t):
+            """the Add + ReLU unit producing tensor t, if t has no other reader"""
+            ua = self.unit_of_out.get(id(t))
+            if ua is None or ua["kind"] != "add" or ua["act"] is None or ua["act"].attrs["fn"] not in relu or ua["out"] is not t:
+                return None
+            return ua if (len(self.cons[id(t)]) == 1 and t not in self.g.outputs and len(ua["node"].inputs) == 2) else None
+
+        for ub in self.units:
+            if ub["kind"] != "bn":
+                continue
+            t = ub["node"].inputs[0]
+            dense = list(self._segs(t)) == [(0, t.C)] or True      # (gapped layouts are fine: statistics and masks are per physical lane)
+            # ---- deferred apply: BN (no activation) whose only reader is Add + ReLU
+            if ub["act"] is None and ub["out"] not in self.g.outputs and len(self.cons[id(ub["out"])]) == 1:
+                ua = self.unit_of_out.get(id(self.cons[id(ub["out"])][0]))
+                if ua is None:       # the consumer is the add node itself (its unit's out may be the absorbed activation)
+                    ua = next((u_ for u_ in self.units if u_["kind"] == "add" and u_["node"] is self.cons[id(ub["out"])][0]), None)
+                if (ua is not None and ua["kind"] == "add" and ua["act"] is not None and ua["act"].attrs["fn"] in relu and len(ua["node"].inputs) == 2
+                        and "fused_bn" not in ua and ua["node"].inputs[0] is not ua["node"].inputs[1]):
+                    ub["defer_to"], ua["fused_bn"] = ua, ub
+            if not self.training:
+                continue
+            # ---- statistics from the producers
+            ua = add_relu_unit(t)
+            if ua is not None and "stats_for" not in ua:
+                ua["stats_for"], ub["stats_from"] = ub, "producer"
+                ub["x_relu_mask"], ua["bwd_premasked"] = True, True
+            elif t.op == "concat" and id(t) not in self.absorbed_concat and len(self.cons[id(t)]) >= 1:
+                parts = self.flat_concat[id(t)]
+                pus = [self.unit_of_out.get(id(p)) for p in parts]
+                ok = all(pu is not None and pu["kind"] == "conv" and pu.get("gate") is None and pu["bn"] is not None and pu["pool"] is None
+                         and pu["out"] is p and "stats_for" not in pu and (pu["act"] is None or pu["act"].attrs["fn"] in relu + ("LeakyReLU",))
+                         and not self._head_prologue_candidate(pu) for pu, p in zip(pus, parts)) and len(set(map(id, parts))) == len(parts)
+                if ok:
+                    off = 0
+                    for pu, p in zip(pus, parts):
+                        pu["stats_for"], pu["stats_off"] = ub, off
+                        off += self._cphys(p)
+                    ub["stats_from"] = "parts"
+            if "stats_from" in ub:
+                self._acc_floats += 2 * self._cphys(t)
+
+    def _head_prologue_candidate(self, u) -> bool:
+        t = u["out"]
+        c = self.cons[id(t)]
+        return len(c) == 1 and c[0].op == "conv" and c[0].attrs["kernel"] == (1, 1) and c[0].attrs["filters"] <= 8 and c[0] in self.g.outputs
+
+    def _acc_take(self, n_floats: int) -> int:
+        """n_floats of the per-step zeroed accumulator region (BatchNorm sums added into by the kernels that write the tensor)"""
+        ptr = self._acc_ptr + 4 * self._acc_used
+        self._acc_used += n_floats
+        assert self._acc_used <= self._acc_floats
+        return ptr
+
+    def _stats_acc(self, ub) -> int:
+        if "acc" not in ub:
+            ub["acc"] = self._acc_take(2 * self._cphys(ub["node"].inputs[0]))
+        return ub["acc"]
+
     # ---------------------------------------------------------------------------------------- fused attention gates
     def _match_gates(self, absorbed):
         """Recognise Attention_Block (2DCNN/models/unet_variants.py:67-82) by structure:
@@ -595,7 +669,7 @@ class Planner:
             self.gate_proj[id(cb)] = gate
             for t in gate["interior"]:
                 absorbed.add(id(t))
-        self._acc_floats = sum(4 * gt["C"] + 8 for gt in self.gates.values())   # per gate: sums_a [2][C], sums_b [2][C], sums3 [2] (+ pad)
+        self._acc_floats += sum(4 * gt["C"] + 8 for gt in self.gates.values())   # per gate: sums_a [2][C], sums_b [2][C], sums3 [2] (+ pad)
 
     def _fwd_gate_proj(self, u):
         """one of the two 1x1 projections of a fused gate: raw output + column sums added into the gate's accumulators"""
@@ -623,9 +697,8 @@ class Planner:
         """addresses of the gate's statistics accumulators inside the per-step zeroed region"""
         if "acc" not in gt:
             C = gt["C"]
-            base = self._acc_ptr + 4 * self._acc_used
+            base = self._acc_take(4 * C + 8)
             gt["acc"] = dict(sums_a=base, sums_b=base + 8 * C, sums3=base + 16 * C)
-            self._acc_used += 4 * C + 8
         return gt["acc"]
 
     def _gate_desc(self, gt) -> "L.GateDesc":
@@ -1064,6 +1137,10 @@ class Planner:
         for i in range(d.n_out):
             d.out[i] = dests[i].to_c()
         d.c_valid = self._cvalid(co, self._segs(n), act)
+        if self.training and u.get("stats_for") is not None and d.c_valid == 0:
+            # this tensor is one channel window of a concat a BatchNormalization reads: its sums are that layer's batch statistics
+            d.out_stats = self._stats_acc(u["stats_for"]) + 4 * u["stats_off"]
+            d.out_stats_pitch = self._cphys(u["stats_for"]["node"].inputs[0])
         if u["pool"] is not None:
             pn = u["pool"]
             pd = self._dests(pn)
@@ -1114,6 +1191,8 @@ class Planner:
         n = u["node"]
         if len(n.inputs) not in (2, 3):
             raise PlanError("add with != 2 or 3 inputs")
+        if u.get("fused_bn") is not None:
+            return self._fwd_add_fused(u)
         ins = [self.phys[id(i)] for i in n.inputs]
         for p in ins[1:]:
             if p.segs != ins[0].segs:
@@ -1122,9 +1201,45 @@ class Planner:
         dests = self._dests(out_node)
         self.phys[id(out_node)] = Phys(dests[0], out_node.C, list(ins[0].segs))
         c = ins[2].view.to_c() if len(ins) == 3 else lw.NULL_VIEW.to_c()
-        self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(0 if len(ins) == 2 else 3, ins[0].view.to_c(), ins[1].view.to_c(), c, dests[0].to_c(),
-                                                 self._act_code(u["act"])), out_node.name)
-        self._copy_extra(dests[0], dests[1:])
+        if self.training and u.get("stats_for") is not None and len(ins) == 2:
+            # Add + ReLU whose result a BatchNormalization reads (ResPath): the apply kernel with identity scale adds the operands and
+            # accumulates that layer's batch statistics on the way
+            d = L.BnActDesc()
+            d.x, d.add, d.act = ins[0].view.to_c(), ins[1].view.to_c(), self._act_code(u["act"])
+            d.n_out = min(len(dests), 2)
+            for i in range(d.n_out):
+                d.out[i] = dests[i].to_c()
+            d.out_stats = self._stats_acc(u["stats_for"])
+            self.emit(0, L.OP_BN_ACT, d, out_node.name)
+            self._copy_extra(dests[0], dests[2:])
+        else:
+            self.emit(0, L.OP_ELTWISE, L.EltwiseDesc(0 if len(ins) == 2 else 3, ins[0].view.to_c(), ins[1].view.to_c(), c, dests[0].to_c(),
+                                                     self._act_code(u["act"])), out_node.name)
+            self._copy_extra(dests[0], dests[1:])
+        u["y"] = dests[0]
+        self.taps[out_node.name] = (dests[0], n.C, "act")
+
+    def _fwd_add_fused(self, u):
+        """ReLU(shortcut + BatchNormalization(x)) in one pass over x and the shortcut (+ the column sums of the result when a
+        BatchNormalization reads it): MultiResBlock unet_variants.py:96-98, ResPath :110-111"""
+        n, ub = u["node"], u["fused_bn"]
+        other = n.inputs[0] if n.inputs[1] is ub["out"] else n.inputs[1]
+        xb, sc = ub["xphys"], self.phys[id(other)]
+        if list(xb.segs) != list(sc.segs) or xb.Cp != sc.Cp:
+            raise PlanError(f"{n.name}: operands of add have different channel layouts")
+        out_node = u["out"]
+        dests = self._dests(out_node)
+        self.phys[id(out_node)] = Phys(dests[0], out_node.C, list(sc.segs))
+        d = L.BnActDesc()
+        d.x, d.scale, d.shift, d.act = xb.view.to_c(), ub["scale"], ub["shift"], self._act_code(u["act"])
+        d.add = sc.view.to_c()
+        d.n_out = min(len(dests), 2)
+        for i in range(d.n_out):
+            d.out[i] = dests[i].to_c()
+        if self.training and u.get("stats_for") is not None:
+            d.out_stats = self._stats_acc(u["stats_for"])
+        self.emit(0, L.OP_BN_ACT, d, out_node.name)
+        self._copy_extra(dests[0], dests[2:])
         u["y"] = dests[0]
         self.taps[out_node.name] = (dests[0], n.C, "act")
 
@@ -1188,9 +1303,12 @@ class Planner:
         out_node = u["out"]
         act = self._act_code(u["act"])
         nb = max(1, min(592, (self.N * H * W) // 64))
-        stats = self.alloc(nb * 2 * cp * 4, "scratch") if self.training else 0
-        if self.training:
-            self.emit(0, L.OP_COLSTATS, L.ColstatsDesc(x.view.to_c(), stats, nb), f"stats {n.name}")
+        if self.training and u.get("stats_from"):
+            stats, nb = self._stats_acc(u), 1          # the kernels that wrote x added its column sums into this accumulator
+        else:
+            stats = self.alloc(nb * 2 * cp * 4, "scratch") if self.training else 0
+            if self.training:
+                self.emit(0, L.OP_COLSTATS, L.ColstatsDesc(x.view.to_c(), stats, nb), f"stats {n.name}")
         vec = self.alloc(4 * cp * 4, "scratch")
         u["scale"], u["shift"], u["mean"], u["rstd"] = vec, vec + cp * 4, vec + 2 * cp * 4, vec + 3 * cp * 4
         self.emit(0, L.OP_BN_FINALIZE, L.BnFinalizeDesc(
@@ -1198,6 +1316,12 @@ class Planner:
             self.pmov(f"{n.name}/moving_mean"), self.pmov(f"{n.name}/moving_variance"),
             1 if self.training else 0, 1 if self.ndim == 2 else 0, n.attrs["eps"], n.attrs["momentum"],
             u["scale"], u["shift"], u["mean"], u["rstd"], 0 if self.training else 1), n.name)
+        u["x"] = x.view
+        if u.get("defer_to") is not None:
+            # applied by the Add + ReLU that reads it (bn_act.add): the normalised tensor is not materialised
+            u["xphys"] = x
+            self.phys[id(out_node)] = Phys(x.view, n.C, list(x.segs))    # (geometry only: nothing reads the normalised tensor as data)
+            return
         dests = self._dests(out_node)
         d = L.BnActDesc()
         d.x, d.scale, d.shift, d.act = x.view.to_c(), u["scale"], u["shift"], act
@@ -1207,7 +1331,7 @@ class Planner:
         d.c_valid = self._cvalid(n.C, x.segs, act)
         self.emit(0, L.OP_BN_ACT, d, out_node.name)
         self._copy_extra(dests[0], dests[2:])
-        u["x"], u["y"] = x.view, dests[0]
+        u["y"] = dests[0]
         self.taps[out_node.name] = (dests[0], n.C, "act")
 
     def _fwd_mul(self, u):
@@ -1581,6 +1705,12 @@ class Planner:
                     self._add_gsrc(i, s)
             return
         act = self._act_code(u["act"])
+        if u.get("bwd_premasked"):
+            # the BatchNormalization that reads this ReLU applied its mask already (bn_bwd.x_relu_mask): its dx IS the gradient of the sum
+            for s in self._direct_sources(out_node, self.gsrc.get(id(out_node), [])):
+                for i in n.inputs:
+                    self._add_gsrc(i, s)
+            return
         dz = self._act_bwd_noBN(out_node, u["y"], act, f"act bwd {out_node.name}")  # relu / leaky: sign(y) == sign(pre-activation)
         if dz is not None:
             for i in n.inputs:
@@ -1640,6 +1770,7 @@ class Planner:
         d.dgamma, d.dbeta = self.pg(f"{n.name}/gamma"), self.pg(f"{n.name}/beta")
         d.dx = dx.to_c()
         d.accumulate = 1   # "zero grads" opens the backward phase
+        d.x_relu_mask = 1 if u.get("x_relu_mask") else 0
         self.emit(1, L.OP_BN_BWD, d, f"bn bwd {n.name}")
         self._add_gsrc(n.inputs[0], GSrc(dx))
 

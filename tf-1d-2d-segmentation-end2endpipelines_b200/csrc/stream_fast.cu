@@ -138,6 +138,112 @@ struct BnActFastLaunch : PreparedOp {
   }
 };
 
+// y = act(x * scale + shift + add) with the per-channel sums of y and y^2 added into caller-zeroed accumulators: MultiResBlock /
+// ResPath glue in one pass (2DCNN/models/unet_variants.py:96-99, 108-112).  `add` fuses Add([shortcut, BatchNormalization(concat)]) +
+// Activation('relu') into the BatchNorm apply; the sums are the batch statistics of the BatchNormalization that follows, so that
+// layer needs no statistics pass of its own.  The sums are taken over the bf16 values that are stored (what its apply will read).
+struct BnAct2F {
+  FV x, add, out0, out1;
+  const float* scale; const float* shift;
+  float* stats;
+  int stats_pitch;
+  int n_out;
+  int C, W, rows;
+  int cvb, rp;
+};
+template <int ACT, bool ADD, bool STATS, int U>
+__global__ void __launch_bounds__(256, 3) bn_act2_fast_kernel(const BnAct2F k) {
+  pdl_prologue();
+  extern __shared__ float red[];   // STATS: [256][16]
+  const int tcv = threadIdx.x % k.cvb, trow = threadIdx.x / k.cvb;
+  const int v = blockIdx.x * k.cvb + tcv;
+  const bool active = v * 8 < k.C && trow < k.rp;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  if (active) {
+    float sc[8], sf[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = k.scale ? __ldg(k.scale + v * 8 + e) : 1.f;
+      sf[e] = k.shift ? __ldg(k.shift + v * 8 + e) : 0.f;
+    }
+    const unsigned step = (unsigned)k.rp;
+    for (int r = blockIdx.y; r < k.rows; r += gridDim.y) {      // rows = N * H (every view is addressed by (row, w): sn == H * sh is checked on the host)
+      const unsigned xrow = (unsigned)r * k.x.sh + v * 8, arow = (unsigned)r * k.add.sh + v * 8;
+      const unsigned o0row = (unsigned)r * k.out0.sh + v * 8, o1row = (unsigned)r * k.out1.sh + v * 8;
+      for (unsigned w0 = trow; w0 < (unsigned)k.W; w0 += step * U) {
+        uint4 xr[U], ar[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned w = w0 + u * step < (unsigned)k.W ? w0 + u * step : (unsigned)k.W - 1;
+          xr[u] = ld16(k.x, xrow + w * k.x.sw);
+          if (ADD) ar[u] = ld16(k.add, arow + w * k.add.sw);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned w = w0 + u * step;
+          if (w >= (unsigned)k.W) break;
+          float f[8], a[8];
+          unpack8(xr[u], f);
+          if (ADD) unpack8(ar[u], a);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = act_f<ACT>(fmaf(f[e], sc[e], sf[e]) + (ADD ? a[e] : 0.f));
+          const uint4 o = pack8(f);
+          st16(k.out0, o0row + w * k.out0.sw, o);
+          if (k.n_out > 1) st16(k.out1, o1row + w * k.out1.sw, o);
+          if (STATS) {
+            float g[8];
+            unpack8(o, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += g[e]; q[e] = fmaf(g[e], g[e], q[e]); }
+          }
+        }
+      }
+    }
+  }
+  if (STATS) {
+    float* mine = red + (size_t)threadIdx.x * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mine[e] = s[e]; mine[8 + e] = q[e]; }
+    __syncthreads();
+    if (trow == 0 && v * 8 < k.C) {
+      float ts[8], tq[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { ts[e] = 0.f; tq[e] = 0.f; }
+      for (int r = 0; r < k.rp; ++r) {
+        const float* o = red + (size_t)(r * k.cvb + tcv) * 16;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ts[e] += o[e]; tq[e] += o[8 + e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { atomicAdd(k.stats + v * 8 + e, ts[e]); atomicAdd(k.stats + k.stats_pitch + v * 8 + e, tq[e]); }
+    }
+  }
+}
+struct BnAct2Launch : PreparedOp {
+  BnAct2F k;
+  int act;
+  bool add, stats;
+  dim3 grid;
+  template <int ACT>
+  void go(cudaStream_t s) {
+    const int smem = stats ? 256 * 16 * 4 : 0;
+    if (add && stats) launch_k(bn_act2_fast_kernel<ACT, true, true, 2>, grid, dim3(256), smem, s, k);
+    else if (add) launch_k(bn_act2_fast_kernel<ACT, true, false, 2>, grid, dim3(256), smem, s, k);
+    else launch_k(bn_act2_fast_kernel<ACT, false, true, 4>, grid, dim3(256), smem, s, k);
+  }
+  int launch(cudaStream_t s) override {
+    switch (act) {
+      case B2SEG_ACT_RELU: go<B2SEG_ACT_RELU>(s); break;
+      case B2SEG_ACT_LEAKY: go<B2SEG_ACT_LEAKY>(s); break;
+      default: go<B2SEG_ACT_NONE>(s); break;
+    }
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+};
+
 static void row_grid(int C, int rows, int Wo, int* cvb, int* rp, dim3* grid) {
   const int cv = C / 8;
   *cvb = cv < 256 ? cv : 256;
@@ -156,6 +262,30 @@ PreparedOp* prepare_bn_act_fast(const b2seg_bn_act_desc* d) {
   static const bool disabled = getenv("B2SEG_NO_FAST_STREAM") != nullptr;
   if (disabled || d->c_valid != 0 || d->x.C % 8 || d->n_out < 1 || d->n_out > 2) return nullptr;
   const int ph = d->pool_h > 1 ? d->pool_h : 1, pw = d->pool_w > 1 ? d->pool_w : 1;
+  if (d->add.ptr || d->out_stats) {
+    // fused add / output statistics (MultiResBlock, ResPath): un-pooled, ReLU / LeakyReLU / none, views addressable by (row, w)
+    if (ph * pw > 1 || (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_RELU && d->act != B2SEG_ACT_LEAKY)) return nullptr;
+    auto* L2 = new BnAct2Launch();
+    BnAct2F& k2 = L2->k;
+    memset(&k2, 0, sizeof(k2));
+    auto rowwise = [&](const b2seg_view& v) { return v.N == 1 || v.sn == (long long)v.H * v.sh; };
+    bool ok2 = fv_make(d->x, &k2.x) && fv_make(d->out[0], &k2.out0) && rowwise(d->x) && rowwise(d->out[0]);
+    k2.out1 = k2.out0; k2.add = k2.x;
+    if (ok2 && d->n_out > 1) ok2 = fv_make(d->out[1], &k2.out1) && rowwise(d->out[1]);
+    if (ok2 && d->add.ptr) ok2 = fv_make(d->add, &k2.add) && rowwise(d->add) && d->add.C == d->x.C && d->add.H == d->x.H && d->add.W == d->x.W && d->add.N == d->x.N;
+    if (!ok2) { delete L2; return nullptr; }
+    k2.scale = reinterpret_cast<const float*>(d->scale); k2.shift = reinterpret_cast<const float*>(d->shift);
+    k2.stats = reinterpret_cast<float*>(d->out_stats);
+    k2.stats_pitch = d->out_stats_pitch > 0 ? d->out_stats_pitch : d->x.C;
+    k2.n_out = d->n_out; k2.C = d->x.C; k2.W = d->x.W; k2.rows = d->x.N * d->x.H;
+    L2->act = d->act; L2->add = d->add.ptr != 0; L2->stats = d->out_stats != 0;
+    row_grid(k2.C, k2.rows, k2.W, &k2.cvb, &k2.rp, &L2->grid);
+    if (L2->stats) {   // one resident wave: the kernel ends with 16 * cvb atomics per block
+      const unsigned wave = (unsigned)std::max(1, num_sms() * 3 / (int)L2->grid.x);
+      if (L2->grid.y > wave) L2->grid.y = wave;
+    }
+    return L2;
+  }
   if (!((ph == 1 && pw == 1) || (ph == 2 && pw == 2) || (ph == 1 && pw == 2))) return nullptr;
   if (d->x.H % ph || d->x.W % pw) return nullptr;
   if (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_RELU && d->act != B2SEG_ACT_LEAKY && d->act != B2SEG_ACT_SIGMOID) return nullptr;
@@ -195,6 +325,7 @@ struct BnBwdF {
   // pointwise-head source (b2seg_gradsrc kind 2): g = dlogits . head_w^T formed on the fly; PASS 0 also accumulates the head's dW, db
   const float* dlogits; const float* head_w;
   float* head_dw; float* head_db;
+  int x_relu_mask;   // PASS 1: dx *= (x > 0)
 };
 
 // Same arithmetic as bn_bwd_lean_kernel (stream_kernels.cu): mask from the sign of t = x*scale + shift, pooled gradients
@@ -333,6 +464,10 @@ __global__ void __launch_bounds__(256, PH * PW * U >= 4 ? 2 : 3) bn_bwd_fast_ker
               float o[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) o[e] = has_bn ? fmaf(cB[e], x[q][e], fmaf(sc[e], g[u][q][e], cD[e])) : g[u][q][e];
+              if (k.x_relu_mask) {     // the BatchNorm's input is ReLU(.): its mask folded in (dx is then the gradient BEFORE that ReLU)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = x[q][e] > 0.f ? o[e] : 0.f;
+              }
               st16(k.dx, drow + (q / PW) * k.dx.sh + (wo * PW + q % PW) * k.dx.sw, pack8(o));
             }
           }
@@ -599,6 +734,8 @@ PreparedOp* prepare_bn_bwd_fast(const b2seg_bn_bwd_desc* d) {
   }
   if (!ok) { delete L; return nullptr; }
   k.n_src = d->n_src;
+  k.x_relu_mask = d->x_relu_mask;
+  if (d->x_relu_mask && (n_head || !has_bn)) { delete L; return nullptr; }
   k.scale = reinterpret_cast<const float*>(d->scale);
   k.shift = reinterpret_cast<const float*>(d->shift);
   k.mean = reinterpret_cast<const float*>(d->mean);

@@ -284,6 +284,7 @@ struct BnActLaunch : PreparedOp {
 PreparedOp* prepare_bn_act(const b2seg_bn_act_desc* d) {
   if (d->x.C % 8) { set_error("bn_act: C %% 8"); return nullptr; }
   if (PreparedOp* fast = prepare_bn_act_fast(d)) return fast;   // instruction-lean row walker (stream_fast.cu) when eligible
+  if (d->add.ptr || d->out_stats) { set_error("bn_act: the fused addend / output statistics need the row-walking fast path (no pooling, no channel mask, ReLU / LeakyReLU / none)"); return nullptr; }
   auto* L = new BnActLaunch();
   BnActK& k = L->k;
   memset(&k, 0, sizeof(k));
@@ -679,6 +680,7 @@ struct BnBwdLaunch : PreparedOp {
 PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
   if (d->x.C % 8 || d->n_src < 1 || d->n_src > B2SEG_MAX_GRADSRC) { set_error("bn_bwd: bad C or n_src"); return nullptr; }
   if (PreparedOp* fast = prepare_bn_bwd_fast(d)) return fast;   // instruction-lean row walker (stream_fast.cu) when eligible
+  if (d->x_relu_mask) { set_error("bn_bwd: x_relu_mask needs the row-walking fast path (BatchNorm present, no head source, views below 2^31 elements)"); return nullptr; }
   for (int i = 0; i < d->n_src; ++i)
     if (d->src[i].kind == 2) {
       set_error("bn_bwd: a pointwise-head source (kind 2) needs BN + ReLU/LeakyReLU, no pooled source, cout <= 2 and 16-byte aligned views below 2^31 elements");
