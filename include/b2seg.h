@@ -334,7 +334,7 @@ typedef struct b2seg_gate_desc {
   uint64_t gamma_a, beta_a, mm_a, mv_a, gamma_b, beta_b, mm_b, mv_b;   /* fp32 [C]; moving statistics updated in place when training */
   uint64_t vec_a, vec_b;        /* fp32 [4][C] out: scale, shift, mean, rstd of each branch */
   uint64_t w3, b3;              /* fp32 [C], [1]: the C -> 1 convolution */
-  uint64_t z;                   /* fp32 [N*h*w] out */
+  uint64_t z, m;                /* fp32 [N*h*w] out: the C -> 1 convolution's output and sigmoid(BN_3(z)) (both re-read by the backward) */
   uint64_t sums3;               /* fp32 [2]: sum z, sum z^2 (caller-zeroed per step) */
   uint64_t gamma3, beta3, mm3, mv3;   /* fp32 [1] */
   uint64_t wt, bt;              /* transposed-conv kernel element (ky,kx) at wt[(ky*4+kx)*wt_stride] (fp32), its bias */
@@ -350,6 +350,11 @@ typedef struct b2seg_gate_desc {
   b2seg_view dza, dzb;          /* bf16 out */
   uint64_t dgamma_a, dbeta_a, dgamma_b, dbeta_b, dgamma3, dbeta3;   /* fp32 out (stored) */
   uint64_t dw3, db3, dwt, dbt;  /* fp32, accumulated (caller-zeroed): [C], [1], 16 elements of stride wt_stride, [1] */
+  /* Two-pass form of the backward (saves a skip-sized memset, a strided write and a three-tensor sum per gate): first call with
+   * dskip.ptr == 0 (dza / dzb / parameter gradients only); the caller runs the stride-2 projection's dgrad into the DENSE
+   * low-resolution tensor da_low (N,h,w,Cs); a second call with da_low set then writes only
+   *   dskip = dout * r + (da_low at the even pixels, 0 elsewhere)  -- the skip tensor's whole gradient through this gate. */
+  b2seg_view da_low;
 } b2seg_gate_desc;
 
 /* Inference: BatchNormalization (moving statistics) folded into the preceding convolution's kernel and bias, so that the convolution

@@ -677,6 +677,13 @@ def emu_gate_fwd(mem, d):
 
 
 def emu_gate_bwd(mem, d):
+    if d.da_low.ptr:          # second pass: dskip = dout * r + the stride-2 projection's input gradient at the even pixels
+        za, zb, skip = mem.gather_view(d.za), mem.gather_view(d.zb), mem.gather_view(d.skip)
+        out, _z, _st = _gate_forward(mem, d, za, zb, torch.ones_like(skip), _gate_params(mem, d, za.shape[-1]))     # = r broadcast over channels
+        dskip = mem.gather_view(d.dout) * out
+        dskip[:, ::2, ::2] += mem.gather_view(d.da_low)
+        mem.write_view(d.dskip, dskip)
+        return
     za = mem.gather_view(d.za).clone().requires_grad_(True)
     zb = mem.gather_view(d.zb).clone().requires_grad_(True)
     skip = mem.gather_view(d.skip).clone().requires_grad_(True)      # (a leaf here: gradient through the multiply only)
@@ -684,7 +691,8 @@ def emu_gate_bwd(mem, d):
     prm = _gate_params(mem, d, C, grad=True)
     out, _z, _st = _gate_forward(mem, d, za, zb, skip, prm)
     out.backward(mem.gather_view(d.dout))
-    mem.write_view(d.dskip, skip.grad)
+    if d.dskip.ptr:
+        mem.write_view(d.dskip, skip.grad)
     mem.write_view(d.dza, za.grad)
     mem.write_view(d.dzb, zb.grad)
     for name in ("gamma_a", "beta_a", "gamma_b", "beta_b"):

@@ -23,6 +23,13 @@ from b2seg.models1d import BCDUNet, UNet  # noqa: E402
 from b2seg.models2d import unet_model_builder  # noqa: E402
 
 
+# Free-running gradient deviation from the float64 fixture on the first / middle layers: measured on the B200 (profiles/r2_gputest7_tail.txt
+# run) 0.20 / 0.51 / 0.14 / 0.53 / 0.29, reproduced TO THREE DIGITS by the CPU numerics model (float64 arithmetic, bf16 storage of
+# kernels / activations / gradients: tests/desc_emulator.py ROUND_BF16) — it is the price of bf16 storage on these tiny random-init
+# models, not kernel error.  Bound = measured x 1.5; the kernel-level statement is test_device_matches_the_bf16_numerics_model below.
+GRAD_BOUND = {"unet2d_d2_w8": 0.30, "unet1d_d3_w8_k3": 0.76, "unetpp2d_ds_ag": 0.21, "multires2d": 0.79, "bcdunet1d_lstm_ds": 0.44}
+
+
 def rel_l2(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
@@ -65,8 +72,49 @@ def test_training_step_matches_golden(spec):
         # gradients next to the loss see almost no accumulated noise; the first layers sit behind every ReLU mask of the model,
         # where bf16 storage noise flips a fraction of the masks (tests/tools_bf16_noise_sim.py): loose bound only
         print(f"[golden {spec['name']}] {k}: rel-L2 {e:.3f}")
-        assert e < (0.05 if pos in (2, 4) else 0.6), (k, e)
+        assert e < (0.05 if pos in (2, 4) else GRAD_BOUND[spec["name"]]), (k, e)
     after = m.get_weight_dict()
     for k in gold.files:
         if k.startswith("moving/"):
             assert np.allclose(after[k[len("moving/"):]], gold[k], rtol=2e-2, atol=2e-3), k
+
+
+@pytest.mark.parametrize("spec", CASES, ids=[c["name"] for c in CASES])
+def test_device_matches_the_bf16_numerics_model(spec, monkeypatch):
+    """The same training step on the B200 and on the CPU numerics model of it: the planner's program replayed by the float64
+    descriptor emulator with every activation / gradient / kernel stored in bf16 (tests/desc_emulator.py, ROUND_BF16).  Free
+    running, no teacher forcing: what is left between the two is accumulation order (fp32 tensor-core sums vs float64) and the
+    handful of ReLU masks / pool arg-maxes that differ because of it — outputs to 1e-2, every gradient to a few percent, instead
+    of the 20-50 % either of them is away from the float64 fixture."""
+    import b2seg.engine
+    import desc_emulator
+    from cpu_engine import CpuEngine
+    gold = np.load(os.path.join(GOLDEN, spec["name"] + ".npz"))
+    losses = spec["losses"]
+    params = {k[len("param/"):]: gold[k] for k in gold.files if k.startswith("param/")}
+    targets = [gold[f"target{i}"] for i in range(len(losses))]
+
+    def run():
+        m = _model(spec)
+        m.compile(loss=losses if len(losses) > 1 else losses[0], optimizer=Adam(1e-3))
+        m.set_weight_dict({k: params[k] for k in m.get_weight_dict()})
+        loss = m.train_on_batch(gold["x"], targets if len(targets) > 1 else targets[0])
+        eng = m._engine(gold["x"].shape[0], True)
+        return loss, [np.array(o["y"].cpu().float()) for o in eng.outputs], eng.get_grads()
+    loss_d, outs_d, grads_d = run()
+    torch.cuda.synchronize()
+    monkeypatch.setattr(b2seg.engine, "Engine", CpuEngine)
+    monkeypatch.setattr(desc_emulator, "ROUND_BF16", "1")
+    loss_m, outs_m, grads_m = run()
+    assert abs(loss_d - loss_m) < 5e-3 * max(1.0, abs(loss_m)), (loss_d, loss_m)
+    for a, b in zip(outs_d, outs_m):
+        assert rel_l2(a, b) < 1.5e-2, rel_l2(a, b)
+    gmax = max(float(np.abs(v).max()) for v in grads_m.values())
+    worst = 0.0
+    for key in grads_m:
+        if float(np.linalg.norm(grads_m[key])) < 1e-3 * gmax * grads_m[key].size ** 0.5:
+            continue              # (analytically zero / cancelling sums: noise on both sides)
+        e = rel_l2(grads_d[key], grads_m[key])
+        worst = max(worst, e)
+        assert e < 0.12, (key, e)
+    print(f"[numerics model {spec['name']}] loss {loss_d:.5f} vs {loss_m:.5f}, worst gradient rel-L2 between device and model {worst:.3f}")

@@ -623,13 +623,14 @@ def test_fused_attention_gate(N, h, w, C, Cs, training):
     sums3 = torch.zeros(8, device=dev)
     vec = torch.zeros(8 * C, device=dev)
     z = torch.zeros(N * h * w, device=dev)
+    mmap = torch.zeros(N * h * w, device=dev)
     d = L.GateDesc()
     d.za, d.zb = tv(za).to_c(), tv(zb).to_c()
     d.sums_a, d.sums_b, d.sums3 = sums_a.data_ptr(), sums_b.data_ptr(), sums3.data_ptr()
     for k_ in ("gamma_a", "beta_a", "mm_a", "mv_a", "gamma_b", "beta_b", "mm_b", "mv_b", "w3", "b3", "gamma3", "beta3", "mm3", "mv3", "bt"):
         setattr(d, k_, P[k_].data_ptr())
     d.wt, d.wt_stride = wt_dev.data_ptr(), stride
-    d.vec_a, d.vec_b, d.z = vec.data_ptr(), vec.data_ptr() + 16 * C, z.data_ptr()
+    d.vec_a, d.vec_b, d.z, d.m = vec.data_ptr(), vec.data_ptr() + 16 * C, z.data_ptr(), mmap.data_ptr()
     d.training, d.bessel, d.eps, d.momentum, d.count = training, 1, 1e-3, 0.99, float(N * h * w)
     d.skip, d.out = tv(skipb, Cs, Cs).to_c(), tv(outb, Cs, Cs).to_c()
     L.call("b2seg_gate_fwd", d, stream())
@@ -737,3 +738,57 @@ def test_bn_apply_with_fused_add_and_output_statistics(N, H, W, Cc, Ctot, off, u
     mu_, var_ = st.reshape(-1, Cc).mean(0), st.reshape(-1, Cc).var(0, unbiased=False)
     ((st - mu_) * torch.rsqrt(var_ + 1e-3) * gamma + beta).mul(g.float()).sum().backward()
     assert rel_l2(dx.float(), pre.grad) < 8e-3, rel_l2(dx.float(), pre.grad)
+
+
+def test_fused_attention_gate_second_backward_pass():
+    """two-pass form of b2seg_gate_bwd: pass 1 without dskip, pass 2 writes dskip = dout * r + the projection's input gradient at the
+    even pixels; must equal the one-pass dskip plus the scattered tensor"""
+    import types
+    from desc_emulator import _gate_forward
+    dev = "cuda"
+    N, h, w, C, Cs = 2, 12, 10, 32, 64
+    g = torch.Generator(device="cpu").manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    za, zb = bf(rnd(N, h, w, C).to(dev)), bf(rnd(N, h, w, C).to(dev))
+    skip = bf(rnd(N, 2 * h, 2 * w, Cs).to(dev))
+    out = torch.zeros_like(skip)
+    prm = dict(gamma_a=1 + 0.2 * rnd(C), beta_a=0.1 * rnd(C), mm_a=torch.zeros(C), mv_a=torch.ones(C), gamma_b=1 + 0.2 * rnd(C), beta_b=0.1 * rnd(C),
+               mm_b=torch.zeros(C), mv_b=torch.ones(C), w3=rnd(C) / C ** 0.5, b3=0.1 * rnd(1), gamma3=1 + 0.2 * rnd(1), beta3=0.1 * rnd(1),
+               mm3=torch.zeros(1), mv3=torch.ones(1), wt=0.5 * rnd(16), bt=0.1 * rnd(1))
+    P = {k: v.to(dev).float().contiguous() for k, v in prm.items()}
+    sums_a = torch.cat([za.float().reshape(-1, C).sum(0), (za.float() ** 2).reshape(-1, C).sum(0)]).contiguous()
+    sums_b = torch.cat([zb.float().reshape(-1, C).sum(0), (zb.float() ** 2).reshape(-1, C).sum(0)]).contiguous()
+    sums3, vec, z, mmap = torch.zeros(8, device=dev), torch.zeros(8 * C, device=dev), torch.zeros(N * h * w, device=dev), torch.zeros(N * h * w, device=dev)
+    d = L.GateDesc()
+    d.za, d.zb, d.sums_a, d.sums_b, d.sums3 = tv(za).to_c(), tv(zb).to_c(), sums_a.data_ptr(), sums_b.data_ptr(), sums3.data_ptr()
+    for k_ in ("gamma_a", "beta_a", "mm_a", "mv_a", "gamma_b", "beta_b", "mm_b", "mv_b", "w3", "b3", "gamma3", "beta3", "mm3", "mv3", "bt", "wt"):
+        setattr(d, k_, P[k_].data_ptr())
+    d.wt_stride, d.vec_a, d.vec_b, d.z, d.m = 1, vec.data_ptr(), vec.data_ptr() + 16 * C, z.data_ptr(), mmap.data_ptr()
+    d.training, d.bessel, d.eps, d.momentum, d.count = 1, 1, 1e-3, 0.99, float(N * h * w)
+    d.skip, d.out = tv(skip).to_c(), tv(out).to_c()
+    L.call("b2seg_gate_fwd", d, stream())
+    dout, da_low = bf(rnd(N, 2 * h, 2 * w, Cs).to(dev)), bf(rnd(N, h, w, Cs).to(dev))
+    dskip1, dskip2, dza, dzb = torch.zeros_like(skip), torch.zeros_like(skip), torch.zeros_like(za), torch.zeros_like(zb)
+    G = torch.zeros(6 * C + 64, device=dev)
+    scr = torch.zeros(N * 4 * h * w + N * h * w + 8 + 3 * C, device=dev)
+    d.dout, d.dza, d.dzb = tv(dout).to_c(), tv(dza).to_c(), tv(dzb).to_c()
+    d.dr, d.g3 = scr.data_ptr(), scr.data_ptr() + 4 * N * 4 * h * w
+    d.bsums3 = d.g3 + 4 * N * h * w
+    d.bsums_ab = d.bsums3 + 32
+    base = G.data_ptr()
+    d.dgamma_a, d.dbeta_a, d.dgamma_b, d.dbeta_b, d.dw3 = base, base + 4 * C, base + 8 * C, base + 12 * C, base + 16 * C
+    d.dgamma3, d.dbeta3, d.dwt, d.dbt = base + 20 * C, base + 20 * C + 4, base + 20 * C + 64, base + 20 * C + 160
+    one = L.GateDesc.from_buffer_copy(d)
+    one.dskip = tv(dskip1).to_c()
+    L.call("b2seg_gate_bwd", one, stream())                    # one-pass form
+    dza1 = dza.clone()
+    L.call("b2seg_gate_bwd", d, stream())                      # pass 1 of the two-pass form: no dskip
+    two = L.GateDesc.from_buffer_copy(d)
+    two.dskip, two.da_low = tv(dskip2).to_c(), tv(da_low).to_c()
+    L.call("b2seg_gate_bwd", two, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dza, dza1)
+    want = dskip1.float()
+    want[:, ::2, ::2] += da_low.float()
+    assert rel_l2(dskip2.float(), want) < 6e-3, rel_l2(dskip2.float(), want)
+    assert float(dskip2.float().abs().max()) > 0

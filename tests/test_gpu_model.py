@@ -526,7 +526,9 @@ def test_2d_families_per_layer(dec, kw, size, width, depth):
             targets.append((rng.random((4, H, W, C)) > 0.6).astype(np.float32)); losses.append("bce")
         else:
             targets.append(rng.standard_normal((4, H, W, C)).astype(np.float32)); losses.append("mse")
-    check_per_layer(m, Ref2D(dec, size, size, width, depth, **kw), 2, x, targets, losses, e2e_bound=1.0)
+    # free-running end-to-end output deviation, measured on the B200: 2.4e-3 .. 9.5e-2 over these families (noise of ~20 stored bf16
+    # tensors in a random-init network); bound = worst x 2
+    check_per_layer(m, Ref2D(dec, size, size, width, depth, **kw), 2, x, targets, losses, e2e_bound=0.2)
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(ds=1, ag=1)], ids=["plain", "ds1-ag1"])
@@ -544,7 +546,7 @@ def test_fpn_per_layer(kw):
             targets.append((rng.random((4, H, W, C)) > 0.6).astype(np.float32)); losses.append("bce")
         else:
             targets.append(rng.standard_normal((4, H, W, C)).astype(np.float32)); losses.append("mse")
-    check_per_layer(m, RefFPN("FPN", 64, 64, 16, 3, **kw), 2, x, targets, losses, e2e_bound=1.0)
+    check_per_layer(m, RefFPN("FPN", 64, 64, 16, 3, **kw), 2, x, targets, losses, e2e_bound=0.5)
 
 
 @pytest.mark.parametrize("var,kw", [("RUNet", dict(ds=1, t=2)), ("R2UNet", dict(ds=1, ag=1, t=2)), ("R2UNetPP", dict(ds=1, t=1)),
@@ -557,7 +559,7 @@ def test_1d_recurrent_unets_per_layer(var, kw):
     rng = np.random.default_rng(14)
     x = rng.standard_normal((4, 256, 2)).astype(np.float32)
     targets = [rng.standard_normal((4,) + tuple(n.shape[1:])).astype(np.float32) for n in m.graph.outputs]
-    check_per_layer(m, Ref1D(var, 256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=1.0)
+    check_per_layer(m, Ref1D(var, 256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=0.5)
 
 
 def test_1d_bcdunet_lstm_ag_ds_per_layer():
@@ -567,7 +569,7 @@ def test_1d_bcdunet_lstm_ag_ds_per_layer():
     rng = np.random.default_rng(12)
     x = rng.standard_normal((4, 256, 2)).astype(np.float32)
     targets = [rng.standard_normal((4,) + (n.shape[1], n.shape[2])).astype(np.float32) for n in m.graph.outputs]
-    check_per_layer(m, Ref1D("BCDUNet", 256, 3, 2, 16, 3, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=1.0)
+    check_per_layer(m, Ref1D("BCDUNet", 256, 3, 2, 16, 3, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=0.5)
 
 
 @pytest.mark.parametrize("var,kw", [("UNetE", dict(ds=1)), ("UNetP", dict(ds=1)), ("UNetPP", dict(ds=1)), ("UNetPP", dict(ds=1, ag=1, is_transconv=False)),
@@ -580,7 +582,7 @@ def test_1d_nested_unets_per_layer(var, kw):
     rng = np.random.default_rng(15)
     x = rng.standard_normal((4, 256, 2)).astype(np.float32)
     targets = [rng.standard_normal((4,) + tuple(n.shape[1:])).astype(np.float32) for n in m.graph.outputs]
-    check_per_layer(m, Ref1D(var, 256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=1.0)
+    check_per_layer(m, Ref1D(var, 256, 3, 2, 16, 3, problem_type="Regression", output_nums=1, **kw), 1, x, targets, ["mse"] * len(targets), e2e_bound=0.5)
 
 
 def _targets_for(m, kw, rng, batch):

@@ -152,13 +152,14 @@ class GateDesc(C.Structure):
     _fields_ = [("za", View), ("zb", View), ("sums_a", C.c_uint64), ("sums_b", C.c_uint64),
                 ("gamma_a", C.c_uint64), ("beta_a", C.c_uint64), ("mm_a", C.c_uint64), ("mv_a", C.c_uint64),
                 ("gamma_b", C.c_uint64), ("beta_b", C.c_uint64), ("mm_b", C.c_uint64), ("mv_b", C.c_uint64),
-                ("vec_a", C.c_uint64), ("vec_b", C.c_uint64), ("w3", C.c_uint64), ("b3", C.c_uint64), ("z", C.c_uint64), ("sums3", C.c_uint64),
+                ("vec_a", C.c_uint64), ("vec_b", C.c_uint64), ("w3", C.c_uint64), ("b3", C.c_uint64), ("z", C.c_uint64), ("m", C.c_uint64), ("sums3", C.c_uint64),
                 ("gamma3", C.c_uint64), ("beta3", C.c_uint64), ("mm3", C.c_uint64), ("mv3", C.c_uint64), ("wt", C.c_uint64), ("bt", C.c_uint64),
                 ("wt_stride", C.c_int32), ("training", C.c_int32), ("bessel", C.c_int32), ("eps", C.c_float), ("momentum", C.c_float),
                 ("count", C.c_double), ("skip", View), ("out", View), ("dout", View), ("dskip", View), ("dr", C.c_uint64), ("g3", C.c_uint64),
                 ("bsums3", C.c_uint64), ("bsums_ab", C.c_uint64), ("dza", View), ("dzb", View),
                 ("dgamma_a", C.c_uint64), ("dbeta_a", C.c_uint64), ("dgamma_b", C.c_uint64), ("dbeta_b", C.c_uint64),
-                ("dgamma3", C.c_uint64), ("dbeta3", C.c_uint64), ("dw3", C.c_uint64), ("db3", C.c_uint64), ("dwt", C.c_uint64), ("dbt", C.c_uint64)]
+                ("dgamma3", C.c_uint64), ("dbeta3", C.c_uint64), ("dw3", C.c_uint64), ("db3", C.c_uint64), ("dwt", C.c_uint64), ("dbt", C.c_uint64),
+                ("da_low", View)]
 
 
 class FoldDesc(C.Structure):

@@ -724,7 +724,8 @@ class Planner:
         assert self.pindex[f"{c3.name}/kernel"].meta["cin_p"] == C and self.pindex[f"{tc.name}/kernel"].meta["taps"] == 16
         d.w3, d.b3 = self.pw(f"{c3.name}/kernel"), self.pw(f"{c3.name}/bias")
         d.wt, d.bt, d.wt_stride = self.pw(f"{tc.name}/kernel"), self.pw(f"{tc.name}/bias"), self.pindex[f"{tc.name}/kernel"].meta["cin_p"]
-        d.z = self.alloc(self.N * h * w * 4, "scratch")
+        d.z = self.alloc(2 * self.N * h * w * 4, "scratch")
+        d.m = d.z + self.N * h * w * 4
         d.training, d.bessel = (1 if self.training else 0), 1
         d.eps, d.momentum, d.count = gt["bn3"].attrs["eps"], gt["bn3"].attrs["momentum"], float(self.N * h * w)
         d.skip = self.phys[id(gt["skip"])].view.to_c()
@@ -751,9 +752,10 @@ class Planner:
         C = gt["C"]
         h, w, _ = gt["conv_a"].shape
         d = L.GateDesc.from_buffer_copy(self._gate_desc(gt))
-        dskip = self._grad_like(gt["skip"])
         dza, dzb = self.new_act(h, w, C, "grad"), self.new_act(h, w, C, "grad")
-        d.dout, d.dskip, d.dza, d.dzb = dout.to_c(), dskip.to_c(), dza.to_c(), dzb.to_c()
+        # two-pass form: dskip is written by a second op once the stride-2 projection's dgrad exists (emitted by _bwd_conv of conv_a)
+        d.dout, d.dza, d.dzb = dout.to_c(), dza.to_c(), dzb.to_c()
+        gt["bwd_desc"] = d
         scr = self.alloc((self.N * 4 * h * w + self.N * h * w + 8 + 3 * C) * 4, "scratch")
         d.dr, d.g3 = scr, scr + self.N * 4 * h * w * 4
         d.bsums3 = d.g3 + self.N * h * w * 4
@@ -764,7 +766,6 @@ class Planner:
         d.dw3, d.db3 = self.pg(f"{gt['conv3'].name}/kernel"), 0     # (conv3's bias feeds a BatchNorm: exactly zero gradient, not accumulated)
         d.dwt, d.dbt = self.pg(f"{gt['tconv'].name}/kernel"), self.pg(f"{gt['tconv'].name}/bias")
         self.emit(1, L.OP_GATE_BWD, d, f"gate bwd {n.name}")
-        self._add_gsrc(gt["skip"], GSrc(dskip))
         self._add_gsrc(gt["conv_a"], GSrc(dza))
         self._add_gsrc(gt["conv_b"], GSrc(dzb))
 
@@ -1922,6 +1923,19 @@ class Planner:
             return
         Hi, Wi, _ = src_node.shape
         dx = self.new_act(Hi, Wi, cin_p, "grad")
+        if strided and u.get("gate") is not None and n is u["gate"]["conv_a"] and "bwd_desc" in u["gate"]:
+            # the stride-2 projection of a fused gate: dgrad into a DENSE low-resolution tensor; the gate's second backward pass adds
+            # it at the even pixels while it writes dskip = dout * r (no skip-sized memset, strided write or three-tensor sum)
+            gt = u["gate"]
+            h_, w_, _ = n.shape
+            da_low = self.new_act(h_, w_, cin_p, "grad")
+            self.emit(1, L.OP_CONV, lw.conv_dgrad(dz, self.pwb(pe.key), cop, kh, kw, cin_p, da_low), f"dgrad {n.name}", flops=self._conv_flops(n))
+            d2 = L.GateDesc.from_buffer_copy(gt["bwd_desc"])
+            dskip = self._grad_like(gt["skip"])
+            d2.dskip, d2.da_low = dskip.to_c(), da_low.to_c()
+            self.emit(1, L.OP_GATE_BWD, d2, f"gate bwd dskip {gt['mul'].name}")
+            self._add_gsrc(src_node, GSrc(dskip))
+            return
         if strided:
             # 1x1 'valid' stride-s conv reads pixels (s*i, s*j): its input gradient lives on that sub-grid; the other
             # pixels of dx are never written and stay at the zeros the buffer was allocated with (with buffer reuse the

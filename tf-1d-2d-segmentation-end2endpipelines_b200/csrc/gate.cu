@@ -21,11 +21,12 @@
 namespace b2 {
 
 struct GateK {
-  DView za, zb, skip, out, dout, dskip, dza, dzb;
+  DView za, zb, skip, out, dout, dskip, dza, dzb, da_low;
   const float *sums_a, *sums_b, *gamma_a, *beta_a, *gamma_b, *beta_b;
   float *mm_a, *mv_a, *mm_b, *mv_b, *vec_a, *vec_b;
   const float *w3, *b3;
   float* z;
+  float* m;               // sigmoid(BN3(z)), written by the forward's output kernel (one low-resolution pixel per even/even thread)
   float* sums3;
   const float *gamma3, *beta3;
   float *mm3, *mv3;
@@ -92,31 +93,42 @@ __global__ void __launch_bounds__(256) gate_mid_fwd_kernel(const GateK k) {
   const float b3 = k.b3[0];
   float acc_s = 0.f, acc_q = 0.f;
   const int groups = (k.npix + ppw - 1) / ppw;
-  for (int g = blockIdx.x * 8 + warp; g < groups; g += gridDim.x * 8) {
-    const int pix = g * ppw + sub;
-    float dot = 0.f;
-    if (pix < k.npix) {
-      const uint32_t q = fast_div((uint32_t)pix, k.fd_w);
-      const int x = pix - (int)q * k.w;
-      const uint32_t n = fast_div(q, k.fd_h);
-      const int y = (int)q - (int)n * k.h;
-      for (int i = 0; i < vpl; ++i) {
-        const int c0 = (lv + i * lpp) * 8;
-        float a[8], b[8];
-        load8(vaddr(k.za, (int)n, y, x, c0), a);
-        load8(vaddr(k.zb, (int)n, y, x, c0), b);
+  constexpr int GU = 4;     // pixel groups in flight per warp (memory-level parallelism: one group is only 32 x 2 16-byte loads)
+  for (int g0 = (blockIdx.x * 8 + warp) * GU; g0 < groups; g0 += gridDim.x * 8 * GU) {
+    float dot[GU];
+    int pixs[GU];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float c = fmaxf(fmaf(a[e], s_sa[c0 + e], s_ta[c0 + e]) + fmaf(b[e], s_sb[c0 + e], s_tb[c0 + e]), 0.f);
-          dot = fmaf(c, s_w3[c0 + e], dot);
+    for (int u = 0; u < GU; ++u) {
+      const int pix = (g0 + u) * ppw + sub;
+      pixs[u] = pix;
+      dot[u] = 0.f;
+      if (g0 + u < groups && pix < k.npix) {
+        const uint32_t q = fast_div((uint32_t)pix, k.fd_w);
+        const int x = pix - (int)q * k.w;
+        const uint32_t n = fast_div(q, k.fd_h);
+        const int y = (int)q - (int)n * k.h;
+        for (int i = 0; i < vpl; ++i) {
+          const int c0 = (lv + i * lpp) * 8;
+          float a[8], b[8];
+          load8(vaddr(k.za, (int)n, y, x, c0), a);
+          load8(vaddr(k.zb, (int)n, y, x, c0), b);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float c = fmaxf(fmaf(a[e], s_sa[c0 + e], s_ta[c0 + e]) + fmaf(b[e], s_sb[c0 + e], s_tb[c0 + e]), 0.f);
+            dot[u] = fmaf(c, s_w3[c0 + e], dot[u]);
+          }
         }
       }
     }
-    for (int off = lpp >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-    if (lv == 0 && pix < k.npix) {
-      const float z = dot + b3;
-      k.z[pix] = z;
-      acc_s += z; acc_q = fmaf(z, z, acc_q);
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      float dsum = dot[u];
+      for (int off = lpp >> 1; off > 0; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+      if (lv == 0 && g0 + u < groups && pixs[u] < k.npix) {
+        const float z = dsum + b3;
+        k.z[pixs[u]] = z;
+        acc_s += z; acc_q = fmaf(z, z, acc_q);
+      }
     }
   }
   if (k.training) {
@@ -154,22 +166,25 @@ struct Resampler {
   float lk;     // LeakyReLU'(pre-activation of the transposed conv): 1 or 0.3
 };
 // m(y, x) = sigmoid(z * sc + sh) of image n with edge clamp (bilinear) or zero outside (transposed conv) handled by the caller
+template <bool FROM_MAP>
 __device__ __forceinline__ float gate_m(const GateK& k, int n, int y, int x, float sc, float sh) {
+  if (FROM_MAP) return __ldg(k.m + (n * k.h + y) * k.w + x);
   return 1.f / (1.f + __expf(-fmaf(k.z[(n * k.h + y) * k.w + x], sc, sh)));
 }
 // resampler value at high-resolution pixel (oy, ox) of image n.
 //   bilinear x2, half-pixel centres, edge clamp (tf.image.resize): even o = 2i: 0.25 m[i-1] + 0.75 m[i]; odd o = 2i+1: 0.75 m[i] + 0.25 m[i+1]
 //   Conv2DTranspose(4x4, s2, 'same') == ConvTranspose2d(k4, s2, p1): o = 2i - 1 + ky: even o: (ky=1, i), (ky=3, i-1); odd o: (ky=2, i), (ky=0, i+1)
+template <bool FROM_MAP>
 __device__ __forceinline__ Resampler gate_resample(const GateK& k, int n, int oy, int ox, float sc, float sh, const float* wt, float bt) {
   const int iy = oy >> 1, ix = ox >> 1;
   const int py = oy & 1, px = ox & 1;
   const int y2 = py ? iy + 1 : iy - 1, x2 = px ? ix + 1 : ix - 1;      // the second source row / column
   const bool vy2 = y2 >= 0 && y2 < k.h, vx2 = x2 >= 0 && x2 < k.w;
   const int yc = vy2 ? y2 : iy, xc = vx2 ? x2 : ix;                     // clamped (bilinear)
-  const float m00 = gate_m(k, n, iy, ix, sc, sh);
-  const float m01 = gate_m(k, n, iy, xc, sc, sh);
-  const float m10 = gate_m(k, n, yc, ix, sc, sh);
-  const float m11 = gate_m(k, n, yc, xc, sc, sh);
+  const float m00 = gate_m<FROM_MAP>(k, n, iy, ix, sc, sh);
+  const float m01 = gate_m<FROM_MAP>(k, n, iy, xc, sc, sh);
+  const float m10 = gate_m<FROM_MAP>(k, n, yc, ix, sc, sh);
+  const float m11 = gate_m<FROM_MAP>(k, n, yc, xc, sc, sh);
   const float bil = 0.75f * (0.75f * m00 + 0.25f * m01) + 0.25f * (0.75f * m10 + 0.25f * m11);
   const int ky1 = py ? 2 : 1, ky2 = py ? 0 : 3, kx1 = px ? 2 : 1, kx2 = px ? 0 : 3;
   float pre = bt + m00 * wt[ky1 * 4 + kx1];
@@ -187,8 +202,10 @@ __device__ __forceinline__ Resampler gate_resample(const GateK& k, int n, int oy
 // then the (pixel, 8-channel vector) pairs are streamed.  BWD: dskip = dout * r and dr = sum_c dout * skip (per-pixel reduction).
 constexpr int kGateSeg = 256;
 constexpr int kGateU = 4;      // (pixel, vector) items in flight per thread
-template <bool BWD>
+template <int MODE>   // 0 forward: out = skip * r;  1 backward: dr = sum_c dout * skip (+ dskip = dout * r when no second pass follows);
+                      // 2 backward, second pass: dskip = dout * r + the stride-2 projection's input gradient at the even pixels
 __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
+  constexpr bool BWD = MODE == 1;
   pdl_prologue();
   __shared__ float s_r[kGateSeg];
   __shared__ float s_dr[kGateSeg];
@@ -202,7 +219,7 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
   const int total_segs = k.skip.N * H2 * segs_per_row;
   const int vpp = k.skip.C >> 3;
   const int span = vpp < 32 ? vpp : 32;
-  if (!BWD && blockIdx.x == 0 && threadIdx.x == 0 && k.training) {
+  if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0 && k.training) {
     const float var = fmaxf(k.sums3[1] * k.inv_count - mu * mu, 0.f);
     const float uv = (k.bessel && k.count > 1.f) ? var * k.count / (k.count - 1.f) : var;
     k.mm3[0] = k.mm3[0] * k.momentum + mu * (1.f - k.momentum);
@@ -216,8 +233,10 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
     const int npx = W2 - x0 < kGateSeg ? W2 - x0 : kGateSeg;
     __syncthreads();
     if ((int)threadIdx.x < npx) {
-      s_r[threadIdx.x] = gate_resample(k, (int)n, oy, x0 + threadIdx.x, sc, sh, s_wt, bt).r;
+      const int ox = x0 + (int)threadIdx.x;
+      s_r[threadIdx.x] = gate_resample<MODE != 0>(k, (int)n, oy, ox, sc, sh, s_wt, bt).r;      // backward: m from the map the forward left
       if (BWD) s_dr[threadIdx.x] = 0.f;
+      else if (MODE == 0 && !(oy & 1) && !(ox & 1)) k.m[((int)n * k.h + (oy >> 1)) * k.w + (ox >> 1)] = gate_m<false>(k, (int)n, oy >> 1, ox >> 1, sc, sh);
     }
     __syncthreads();
     const int work = npx * vpp;
@@ -235,8 +254,14 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
         sv[u] = make_uint4(0u, 0u, 0u, 0u);
         dv4[u] = sv[u];
         if (live[u]) {
-          sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.skip, (int)n, oy, x0 + pp[u], vv[u] * 8)));
-          if (BWD) dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, (int)n, oy, x0 + pp[u], vv[u] * 8)));
+          if (MODE == 2) {       // sv = the projection's input gradient (low resolution) at even pixels, else 0; dv4 = dout
+            const int ox = x0 + pp[u];
+            if (!(oy & 1) && !(ox & 1)) sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.da_low, (int)n, oy >> 1, ox >> 1, vv[u] * 8)));
+            dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, (int)n, oy, ox, vv[u] * 8)));
+          } else {
+            sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.skip, (int)n, oy, x0 + pp[u], vv[u] * 8)));
+            if (BWD) dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, (int)n, oy, x0 + pp[u], vv[u] * 8)));
+          }
         }
       }
 #pragma unroll
@@ -247,10 +272,18 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(hs[e]); s[2 * e] = t.x; s[2 * e + 1] = t.y; }
         const float r = s_r[pp[u]];
-        if (!BWD) {
+        if (MODE == 0) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = s[e] * r;
           if (live[u]) store8(vaddr(k.out, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
+        } else if (MODE == 2) {
+          float d[8];
+          const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&dv4[u]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(hd[e]); d[2 * e] = t.x; d[2 * e + 1] = t.y; }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaf(d[e], r, s[e]);
+          if (live[u]) store8(vaddr(k.dskip, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
         } else {
           float d[8];
           const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&dv4[u]);
@@ -259,7 +292,7 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
           float part = 0.f;
 #pragma unroll
           for (int e = 0; e < 8; ++e) { o[e] = d[e] * r; part = fmaf(d[e], s[e], part); }
-          if (live[u]) store8(vaddr(k.dskip, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
+          if (live[u] && k.dskip.ptr) store8(vaddr(k.dskip, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
           // lanes holding the same pixel are adjacent (vpp is a power of two): reduce within the warp first
           for (int off = span >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
           if (live[u] && (threadIdx.x & (span - 1)) == 0) atomicAdd(&s_dr[pp[u]], part);
@@ -294,7 +327,7 @@ __global__ void __launch_bounds__(256) gate_low_bwd_kernel(const GateK k) {
     const uint32_t n = fast_div(q, k.fd_h);
     const int y = (int)q - (int)n * k.h;
     const float zv = k.z[pix];
-    const float m = 1.f / (1.f + __expf(-fmaf(zv, sc, sh)));
+    const float m = __ldg(k.m + pix);
     float dm = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
@@ -311,7 +344,7 @@ __global__ void __launch_bounds__(256) gate_low_bwd_kernel(const GateK k) {
         float wx = (kx == 1 || kx == 2) ? 0.75f : 0.25f;
         if ((ox == 0 && x == 0) || (ox == W2 - 1 && x == k.w - 1)) wx = 1.f;
         const float d = k.dr[((size_t)n * H2 + oy) * W2 + ox];
-        const float lk = gate_resample(k, (int)n, oy, ox, sc, sh, wt, bt).lk;
+        const float lk = gate_resample<true>(k, (int)n, oy, ox, sc, sh, wt, bt).lk;
         dm = fmaf(d, fmaf(lk, wt[ky * 4 + kx], wy * wx), dm);
         acc[ky * 4 + kx] = fmaf(d * lk, m, acc[ky * 4 + kx]);
         if ((ky == 1 || ky == 2) && (kx == 1 || kx == 2)) acc[16] = fmaf(d, lk, acc[16]);   // each high-resolution pixel counted once (by its 2x2 owner)
@@ -344,7 +377,7 @@ __global__ void __launch_bounds__(256) gate_low_bwd_kernel(const GateK k) {
 // Thread = one 8-channel vector (tcv) of a strided set of pixels (trow); blockIdx.x = vector group, blockIdx.y strides the pixels.
 // PASS 0: per-channel sums {g, g zhat_a, g zhat_b, dz3 c}; PASS 1: dza, dzb.
 template <int PASS>
-__global__ void __launch_bounds__(256) gate_mid_bwd_kernel(const GateK k, int cvb) {
+__global__ void __launch_bounds__(256, 2) gate_mid_bwd_kernel(const GateK k, int cvb) {
   pdl_prologue();
   const int C = k.C;
   const int tcv = threadIdx.x % cvb, trow = threadIdx.x / cvb, rows = 256 / cvb;
@@ -369,16 +402,42 @@ __global__ void __launch_bounds__(256) gate_mid_bwd_kernel(const GateK k, int cv
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
   float acc_db3 = 0.f;
-  for (int pix = blockIdx.y * rows + trow; pix < k.npix; pix += gridDim.y * rows) {
-    const uint32_t q = fast_div((uint32_t)pix, k.fd_w);
-    const int x = pix - (int)q * k.w;
-    const uint32_t n = fast_div(q, k.fd_h);
-    const int y = (int)q - (int)n * k.h;
-    const float zh3 = (k.z[pix] - mu3) * rs3;
-    const float dz3 = sc3 * (k.g3[pix] - mg - zh3 * mgz);
+  constexpr int PU = 2;      // pixels in flight per thread (two blocks per SM: 128 registers)
+  const int pstride = gridDim.y * rows;
+  for (int pix0 = blockIdx.y * rows + trow; pix0 < k.npix; pix0 += pstride * PU) {
+    uint4 rawa[PU], rawb[PU];
+    float dz3s[PU];
+    int ns[PU], ys[PU], xs[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      const int pix = pix0 + u * pstride;
+      const int pc = pix < k.npix ? pix : k.npix - 1;
+      const uint32_t q = fast_div((uint32_t)pc, k.fd_w);
+      xs[u] = pc - (int)q * k.w;
+      const uint32_t n = fast_div(q, k.fd_h);
+      ys[u] = (int)q - (int)n * k.h;
+      ns[u] = (int)n;
+      const float zh3 = (k.z[pc] - mu3) * rs3;
+      dz3s[u] = pix < k.npix ? sc3 * (k.g3[pc] - mg - zh3 * mgz) : 0.f;
+      rawa[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.za, ns[u], ys[u], xs[u], c0)));
+      rawb[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.zb, ns[u], ys[u], xs[u], c0)));
+    }
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+    const int pix = pix0 + u * pstride;
+    if (pix >= k.npix) break;
+    const int n = ns[u], y = ys[u], x = xs[u];
+    const float dz3 = dz3s[u];
     float a[8], b[8];
-    load8(vaddr(k.za, (int)n, y, x, c0), a);
-    load8(vaddr(k.zb, (int)n, y, x, c0), b);
+    {
+      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&rawa[u]);
+      const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rawb[u]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 ta = __bfloat1622float2(ha[e]), tb = __bfloat1622float2(hb[e]);
+        a[2 * e] = ta.x; a[2 * e + 1] = ta.y; b[2 * e] = tb.x; b[2 * e + 1] = tb.y;
+      }
+    }
     if (PASS == 0) {
       if (blockIdx.x == 0 && tcv == 0 && k.db3) acc_db3 += dz3;
 #pragma unroll
@@ -401,6 +460,7 @@ __global__ void __launch_bounds__(256) gate_mid_bwd_kernel(const GateK k, int cv
       }
       store8(vaddr(k.dza, (int)n, y, x, c0), da);
       store8(vaddr(k.dzb, (int)n, y, x, c0), db);
+    }
     }
   }
   if (PASS == 0) {
@@ -452,13 +512,13 @@ static int fill_gate(const b2seg_gate_desc* d, GateK* k, bool bwd) {
     return -1;
   }
   if ((long long)za.N * za.H * za.W * 4 >= (1ll << 31)) { set_error("gate: map too large"); return -1; }
-  if (!d->w3 || !d->b3 || !d->z || !d->wt || !d->bt || !d->gamma3 || !d->beta3 || !d->mm3 || !d->mv3 || !d->vec_a || !d->vec_b) { set_error("gate: null parameter"); return -1; }
+  if (!d->w3 || !d->b3 || !d->z || !d->m || !d->wt || !d->bt || !d->gamma3 || !d->beta3 || !d->mm3 || !d->mv3 || !d->vec_a || !d->vec_b) { set_error("gate: null parameter"); return -1; }
   if (d->training && (!d->sums_a || !d->sums_b || !d->sums3)) { set_error("gate: training needs the statistics accumulators"); return -1; }
   k->za = dv(d->za); k->zb = dv(d->zb); k->skip = dv(d->skip); k->out = dv(d->out);
-  k->dout = dv(d->dout); k->dskip = dv(d->dskip); k->dza = dv(d->dza); k->dzb = dv(d->dzb);
+  k->dout = dv(d->dout); k->dskip = dv(d->dskip); k->dza = dv(d->dza); k->dzb = dv(d->dzb); k->da_low = dv(d->da_low);
 #define P(f) k->f = reinterpret_cast<decltype(k->f)>(d->f)
   P(sums_a); P(sums_b); P(gamma_a); P(beta_a); P(gamma_b); P(beta_b); P(mm_a); P(mv_a); P(mm_b); P(mv_b); P(vec_a); P(vec_b);
-  P(w3); P(b3); P(z); P(sums3); P(gamma3); P(beta3); P(mm3); P(mv3); P(wt); P(bt);
+  P(w3); P(b3); P(z); P(m); P(sums3); P(gamma3); P(beta3); P(mm3); P(mv3); P(wt); P(bt);
   P(dr); P(g3); P(bsums3); P(bsums_ab); P(dgamma_a); P(dbeta_a); P(dgamma_b); P(dbeta_b); P(dw3); P(db3); P(dgamma3); P(dbeta3); P(dwt); P(dbt);
 #undef P
   k->wt_stride = d->wt_stride;
@@ -471,7 +531,7 @@ static int fill_gate(const b2seg_gate_desc* d, GateK* k, bool bwd) {
     if (!d->out.ptr || d->out.C != d->skip.C || d->out.H != d->skip.H || d->out.W != d->skip.W) { set_error("gate: bad output view"); return -1; }
   } else {
     if (!d->training) { set_error("gate: backward of an inference plan"); return -1; }
-    if (!d->dout.ptr || !d->dskip.ptr || !d->dza.ptr || !d->dzb.ptr || !d->dr || !d->g3 || !d->bsums3 || !d->bsums_ab || !d->dgamma_a || !d->dbeta_a ||
+    if (!d->dout.ptr || !d->dza.ptr || !d->dzb.ptr || !d->dr || !d->g3 || !d->bsums3 || !d->bsums_ab || !d->dgamma_a || !d->dbeta_a ||
         !d->dgamma_b || !d->dbeta_b || !d->dw3 || !d->dgamma3 || !d->dbeta3 || !d->dwt || !d->dbt) { set_error("gate: null backward pointer"); return -1; }
   }
   return 0;
@@ -480,6 +540,7 @@ static int fill_gate(const b2seg_gate_desc* d, GateK* k, bool bwd) {
 struct GateLaunch : PreparedOp {
   GateK k;
   bool bwd;
+  int mode = 0;
   int launch(cudaStream_t s) override {
     const int sms = num_sms();
     const int W2 = 2 * k.w, H2 = 2 * k.h;
@@ -489,16 +550,19 @@ struct GateLaunch : PreparedOp {
     if (!bwd) {
       const int lpp = vpp < 32 ? vpp : 32, ppw = 32 / lpp;
       const int groups = (k.npix + ppw - 1) / ppw;
-      int grid = (groups + 7) / 8;
+      int grid = (groups + 31) / 32;      // 8 warps x 4 groups per block iteration
+      if (grid < 1) grid = 1;
       if (grid > sms * 4) grid = sms * 4;
       const int smem = 5 * k.C * 4;
       if (smem > 48 * 1024) B2_CUDA_OK(cudaFuncSetAttribute(gate_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       B2_CUDA_OK(launch_k(gate_mid_fwd_kernel, dim3(grid), dim3(256), smem, s, k));
-      B2_CUDA_OK(launch_k(gate_out_kernel<false>, dim3(grid_out), dim3(256), 0, s, k));
+      B2_CUDA_OK(launch_k(gate_out_kernel<0>, dim3(grid_out), dim3(256), 0, s, k));
+    } else if (mode == 2) {
+      B2_CUDA_OK(launch_k(gate_out_kernel<2>, dim3(grid_out), dim3(256), 0, s, k));
     } else {
       B2_CUDA_OK(cudaMemsetAsync(k.bsums3, 0, 8, s));
       B2_CUDA_OK(cudaMemsetAsync(k.bsums_ab, 0, (size_t)3 * k.C * 4, s));
-      B2_CUDA_OK(launch_k(gate_out_kernel<true>, dim3(grid_out), dim3(256), 0, s, k));
+      B2_CUDA_OK(launch_k(gate_out_kernel<1>, dim3(grid_out), dim3(256), 0, s, k));
       int grid_low = (k.npix + 255) / 256;
       if (grid_low > sms * 4) grid_low = sms * 4;
       B2_CUDA_OK(launch_k(gate_low_bwd_kernel, dim3(grid_low), dim3(256), 0, s, k));
@@ -518,7 +582,7 @@ struct GateLaunch : PreparedOp {
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }
-  int num_launches() const override { return bwd ? 4 : 2; }
+  int num_launches() const override { return mode == 2 ? 1 : (bwd ? 4 : 2); }
 };
 
 PreparedOp* prepare_gate_fwd(const b2seg_gate_desc* d) {
@@ -531,6 +595,11 @@ PreparedOp* prepare_gate_bwd(const b2seg_gate_desc* d) {
   auto* L = new GateLaunch();
   L->bwd = true;
   if (fill_gate(d, &L->k, true) != 0) { delete L; return nullptr; }
+  if (d->da_low.ptr) {     // second pass only: dskip = dout * r + scatter(da_low)
+    const b2seg_view& v = d->da_low;
+    if (!d->dskip.ptr || v.N != d->za.N || v.H != d->za.H || v.W != d->za.W || v.C != d->skip.C) { set_error("gate: bad da_low / dskip views"); delete L; return nullptr; }
+    L->mode = 2;
+  }
   return L;
 }
 
