@@ -1933,6 +1933,10 @@ class Planner:
             d2 = L.GateDesc.from_buffer_copy(gt["bwd_desc"])
             dskip = self._grad_like(gt["skip"])
             d2.dskip, d2.da_low = dskip.to_c(), da_low.to_c()
+            # this pass recomputes the resampler from the gate's fp32 parameters: under a sharded / per-bucket optimizer they must not
+            # be updated before it has run, so their gradients count as "written" by this unit too (exchange_schedule readiness)
+            for key in (f"{gt['tconv'].name}/kernel", f"{gt['tconv'].name}/bias", f"{gt['bn3'].name}/gamma", f"{gt['bn3'].name}/beta"):
+                self.pg(key)
             self.emit(1, L.OP_GATE_BWD, d2, f"gate bwd dskip {gt['mul'].name}")
             self._add_gsrc(src_node, GSrc(dskip))
             return
