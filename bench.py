@@ -421,13 +421,27 @@ def main():
     xh = xe.numpy()
     yh = {n: t.numpy() for n, t in zip(model.output_names, yes)} if len(yes) > 1 else yes[0].numpy()
 
-    def ycut(n_):
-        return {k_: v_[:n_] for k_, v_ in yh.items()} if isinstance(yh, dict) else yh[:n_]
-    model.fit(xh[:2 * B], ycut(2 * B), batch_size=B, epochs=1, shuffle=False, verbose=0)   # warm-up (staging buffers, streams)
+    class HostBatches:
+        """what 2DCNN/utils/DataGenerator.py:CustomDataGenerator is to Keras (Train.py:281,394): __len__ / __getitem__ -> (x, y) batches
+        in host memory, on_epoch_end; fit() pulls from it on a producer thread"""
+
+        def __init__(self, n_batches):
+            self.n = n_batches
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, i):
+            sl = slice(i * B, (i + 1) * B)
+            return xh[sl], ({k_: v_[sl] for k_, v_ in yh.items()} if isinstance(yh, dict) else yh[sl])
+
+        def on_epoch_end(self):
+            pass
+    model.fit(HostBatches(2), epochs=1, verbose=0)   # warm-up (staging buffers, streams)
     last = {}
 
     def e2e_run():
-        h = model.fit(xh, yh, batch_size=B, epochs=1, shuffle=False, verbose=0)
+        h = model.fit(HostBatches(ns), epochs=1, verbose=0)
         last["loss"] = h.history["loss"][-1]
 
     ms_e2e = timed(e2e_run, 1)
@@ -512,8 +526,9 @@ def main():
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(x.nbytes + sum(t.nbytes for t in ylist)), "d2h_bytes_per_step": 1024,
                         "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss"),
-                        "api": "Model.fit(x, y, batch_size, epochs=1, shuffle=False) over steps x batch samples in pinned host memory (producer thread "
-                               "stages batch i+1 on a copy stream; one 1 KB log record per step read back asynchronously)"},
+                        "api": "Model.fit(Sequence, epochs=1): the call form of the reference's Train.py:281,394 — a CustomDataGenerator-like object "
+                               "yielding (x, y) host batches (pinned); a producer thread pulls batch i+1 and stages it on a copy stream while step i "
+                               "runs; one 1 KB log record per step read back asynchronously"},
                 "gpu_launches": launches * args.steps, "launches_per_step": launches,
                 "device_memory_gb": eng.memory_bytes() / 2 ** 30}
         if getattr(eng, "exchange_calibration", None):

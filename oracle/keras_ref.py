@@ -351,7 +351,7 @@ class KerasRef:
         # implementation that stores them in bf16 evaluates the gate non-linearities on the stored values)
         live = self._cf(self._rec(f"{name}/gates", self._cl(torch.cat([zi, zc, zo], dim=1))))
         zi, zc, zo = torch.split(live, filters, dim=1)
-        hs = lambda t: torch.clamp(0.2 * t + 0.5, 0.0, 1.0)
+        hs = hard_sigmoid
         c0 = torch.zeros_like(zi)
         c1 = hs(zf) * c0 + hs(zi) * torch.tanh(zc)
         h1 = hs(zo) * torch.tanh(c1)
@@ -370,6 +370,12 @@ class KerasRef:
     def Reshape(self, x, shape):
         self._name("reshape", None)
         return x.reshape((x.shape[0],) + tuple(shape))
+
+
+def hard_sigmoid(x):
+    """tf.keras.activations.hard_sigmoid, Keras 2: 0 if x < -2.5, 1 if x > 2.5, else 0.2 * x + 0.5 (the recurrent activation of
+    ConvLSTM2D/1D as the reference builds it, unet_variants.py:145-149).  Pinned by the docstring example in tests/golden/keras_doc_kats.json."""
+    return torch.clamp(0.2 * x + 0.5, 0.0, 1.0)
 
 
 # ---- losses (SUM_OVER_BATCH_SIZE reduction = mean over all elements / pixels) and Keras Adam ----------------

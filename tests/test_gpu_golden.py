@@ -24,10 +24,10 @@ from b2seg.models2d import unet_model_builder  # noqa: E402
 
 
 # Free-running gradient deviation from the float64 fixture on the first / middle layers: measured on the B200 (profiles/r2_gputest7_tail.txt
-# run) 0.20 / 0.51 / 0.14 / 0.53 / 0.29, reproduced TO THREE DIGITS by the CPU numerics model (float64 arithmetic, bf16 storage of
+# run) 0.20 / 0.51 / 0.14 / 0.53 (MultiResUNet, fixture since widened: model 0.53) / 0.29, reproduced TO THREE DIGITS by the CPU numerics model (float64 arithmetic, bf16 storage of
 # kernels / activations / gradients: tests/desc_emulator.py ROUND_BF16) — it is the price of bf16 storage on these tiny random-init
 # models, not kernel error.  Bound = measured x 1.5; the kernel-level statement is test_device_matches_the_bf16_numerics_model below.
-GRAD_BOUND = {"unet2d_d2_w8": 0.30, "unet1d_d3_w8_k3": 0.76, "unetpp2d_ds_ag": 0.21, "multires2d": 0.79, "bcdunet1d_lstm_ds": 0.44}
+GRAD_BOUND = {"unet2d_d2_w8": 0.30, "unet1d_d3_w8_k3": 0.76, "unetpp2d_ds_ag": 0.21, "multires2d": 0.80, "bcdunet1d_lstm_ds": 0.44}
 
 
 def rel_l2(a, b):
@@ -112,9 +112,13 @@ def test_device_matches_the_bf16_numerics_model(spec, monkeypatch):
     gmax = max(float(np.abs(v).max()) for v in grads_m.values())
     worst = 0.0
     for key in grads_m:
-        if float(np.linalg.norm(grads_m[key])) < 1e-3 * gmax * grads_m[key].size ** 0.5:
-            continue              # (analytically zero / cancelling sums: noise on both sides)
+        if grads_m[key].size < 256 or float(np.linalg.norm(grads_m[key])) < 1e-3 * gmax * grads_m[key].size ** 0.5:
+            continue              # (a handful of numbers / analytically zero / cancelling sums: one flipped ReLU mask decides the ratio)
         e = rel_l2(grads_d[key], grads_m[key])
         worst = max(worst, e)
         assert e < 0.12, (key, e)
-    print(f"[numerics model {spec['name']}] loss {loss_d:.5f} vs {loss_m:.5f}, worst gradient rel-L2 between device and model {worst:.3f}")
+    keys = sorted(k_ for k_ in grads_m if k_.endswith("/kernel"))
+    whole = rel_l2(np.concatenate([grads_d[k_].ravel() for k_ in keys]), np.concatenate([grads_m[k_].ravel() for k_ in keys]))
+    assert whole < 0.08, whole
+    print(f"[numerics model {spec['name']}] loss {loss_d:.5f} vs {loss_m:.5f}, gradient rel-L2 between device and model: worst tensor {worst:.3f}, "
+          f"all kernels as one vector {whole:.3f}")

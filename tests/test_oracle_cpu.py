@@ -243,3 +243,74 @@ def test_oracle_reproduces_golden_fixture(case):
     assert set(got) == set(want.files)
     for key in want.files:
         assert np.allclose(got[key], want[key], rtol=1e-6, atol=1e-7), (case, key)
+
+
+# ---- known answers published by the real dependency ------------------------------------------------------------------------------
+def _kats():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "keras_doc_kats.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_reproduces_the_keras_documentation_examples():
+    """tests/golden/keras_doc_kats.json: docstring examples of tf.keras (the numbers TensorFlow itself printed).  The oracle's loss
+    definitions, hard_sigmoid, LeakyReLU slope, Adam rule, nearest up-sampling, max-pooling and BatchNorm formula must reproduce
+    every one of them to the digits quoted."""
+    from oracle.keras_ref import KerasRef, keras_adam_step, keras_loss, hard_sigmoid
+    k = _kats()
+    for case in k["losses"]:
+        yt, yp = torch.tensor(case["y_true"], dtype=torch.float64), torch.tensor(case["y_pred"], dtype=torch.float64)
+        if case.get("logits"):
+            got = float(keras_loss(case["kind"], torch.sigmoid(yp), yt, logits=yp))
+        else:
+            got = float(keras_loss(case["kind"], yp, yt))
+        assert abs(got - case["value"]) < 0.6 * 10 ** (-case["digits"]), (case["source"], got, case["value"])
+    hs = k["hard_sigmoid"]
+    assert torch.allclose(hard_sigmoid(torch.tensor(hs["x"], dtype=torch.float64)), torch.tensor(hs["y"], dtype=torch.float64), atol=1e-12)
+    lr_ = k["leaky_relu"]
+    assert torch.allclose(KerasRef.activation_fn("LeakyReLU", torch.tensor(lr_["x"], dtype=torch.float64)), torch.tensor(lr_["y"], dtype=torch.float64), atol=1e-12)
+    ad = k["adam"]
+    w = torch.tensor([ad["w0"]], dtype=torch.float64)
+    keras_adam_step(w, w.clone(), torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64), 1, lr=ad["lr"])   # d/dw (w^2 / 2) = w
+    assert abs(float(w) - ad["w1"]) < 0.6 * 10 ** (-ad["digits"])
+    u1 = k["upsampling1d"]
+    r1 = KerasRef(1, dtype=torch.float64, training=False)
+    x1 = torch.arange(12, dtype=torch.float64).reshape(u1["x_shape"])
+    assert torch.equal(r1.UpSampling(x1, u1["size"]), torch.tensor(u1["y"], dtype=torch.float64))
+    u2 = k["upsampling2d"]
+    r2 = KerasRef(2, dtype=torch.float64, training=False)
+    x2 = torch.arange(12, dtype=torch.float64).reshape(u2["x_shape"])
+    assert torch.equal(r2.UpSampling(x2, tuple(u2["size"])), torch.tensor(u2["y"], dtype=torch.float64))
+    mp = k["maxpool2d"]
+    xm = torch.tensor(mp["x"], dtype=torch.float64)[None, :, :, None]
+    assert torch.equal(r2.MaxPooling(xm, mp["pool"])[0, :, :, 0], torch.tensor(mp["y"], dtype=torch.float64))
+    bn = k["batchnorm"]
+    r3 = KerasRef(1, dtype=torch.float64, training=True)
+    yb = r3.BatchNormalization(torch.tensor(bn["x"], dtype=torch.float64)[:, None, :])          # (N, L=1, C=1)
+    assert torch.allclose(yb[:, 0, :], torch.tensor(bn["y"], dtype=torch.float64), atol=1e-12)
+    assert abs(float(r3.new_moving["batch_normalization/moving_mean"]) - bn["moving_mean_after"]) < 1e-12
+
+
+def test_loss_kernel_semantics_reproduce_the_keras_documentation_examples():
+    """the same published loss values through the float64 mirror of the CUDA loss kernel (tests/desc_emulator.py:emu_loss == csrc loss_kernel
+    formulas, which the GPU test compares with the device)"""
+    import types
+    from b2seg import _lib as L
+    from b2seg.planner import LOSS_KINDS
+    from desc_emulator import PlanMem, emu_loss
+    for case in _kats()["losses"]:
+        yt, yp = torch.tensor(case["y_true"], dtype=torch.float64), torch.tensor(case["y_pred"], dtype=torch.float64)
+        act = L.ACT_NONE
+        if case.get("logits"):
+            yp, act = torch.sigmoid(yp), L.ACT_SIGMOID      # the kernel sees probabilities + the head's activation (Keras' cached-logits path)
+        mem = PlanMem()
+        n = yp.numel()
+        p_ptr, t_ptr, l_ptr = mem.alloc_bytes(4 * n, "output"), mem.alloc_bytes(4 * n, "target"), mem.alloc_bytes(64, "loss")
+        mem.f32(p_ptr, n)[:] = yp.reshape(-1)
+        mem.f32(t_ptr, n)[:] = yt.reshape(-1)
+        d = types.SimpleNamespace(y_pred=p_ptr, y_true=t_ptr, n_pix=yp.shape[0], cout=yp.shape[1], kind=LOSS_KINDS[case["kind"]], act=act, weight=1.0,
+                                  dlogits=0, loss=l_ptr, metrics=0)
+        emu_loss(mem, d)
+        got = float(mem.f32(l_ptr, 1))
+        assert abs(got - case["value"]) < 0.6 * 10 ** (-case["digits"]), (case["source"], got, case["value"])
