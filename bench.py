@@ -403,11 +403,22 @@ def main():
     if args.mode == "predict":
         return bench_predict(args, model, x, B, S, workload, rank, world, local, barrier, timed)
 
-    # ---- device-resident arm (value)
-    for _ in range(args.warmup):
-        model._step(eng, return_loss=False)
+    # ---- device-resident arm (value).  The clock sampler starts before the warm-up steps (nvidia-smi needs a few hundred ms to come
+    # up on an 8-GPU box, longer than the timed region itself); every sample it takes is under the same load
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(args.warmup):
+        model._step(eng, return_loss=False)
+    torch.cuda.synchronize()
+    if world > 1:                    # (the same number of extra steps on every rank: they contain collectives)
+        for _ in range(max(1, int(600.0 / max(1.0, 11.0 * (S * S) / 65536.0)))):
+            model._step(eng, return_loss=False)
+        torch.cuda.synchronize()
+    elif len(sampler.rows) < 2:      # keep the GPU under the same load until the sampler has delivered
+        t_end = time.time() + 3.0
+        while len(sampler.rows) < 2 and time.time() < t_end:
+            model._step(eng, return_loss=False)
+            torch.cuda.synchronize()
     ms = timed(lambda: model._step(eng, return_loss=False), args.steps)
     clocks = sampler.stop()
     value = world * B * args.steps / (ms / 1e3)

@@ -177,7 +177,7 @@ class Model:
         self.stop_training = False
         self.world_size = 1
         self._dist = None
-        self.exchange_bucket_bytes = 64 << 20   # gradient-exchange bucket (data parallel): overlap granularity vs launch count
+        self.exchange_bucket_bytes = int(os.environ.get("B2SEG_BUCKET_MB", "64")) << 20   # gradient-exchange bucket (data parallel): overlap granularity vs launch count
         self._ds_targets = None
         # False (default): activation / gradient buffers share one arena by liveness (Planner._assign_memory).  True: every layer's
         # tensors stay readable after a step (layer_output / the per-layer parity tests); B2SEG_KEEP_ACTIVATIONS=1 forces it.
