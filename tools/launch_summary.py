@@ -27,7 +27,7 @@ def main():
         e = launches.setdefault(int(rec["ID"]), {"kernel": short(rec["Kernel Name"]), "grid": rec.get("Grid Size", "")})
         e[rec["Metric Name"]] = float(rec["Metric Value"].replace(",", ""))
     seq = list(launches.values())
-    starts = [i for i, e in enumerate(seq) if e["kernel"].startswith("cast_input_kernel")]
+    starts = [i for i, e in enumerate(seq) if e["kernel"].startswith(("cast_input_kernel", "im2col_input_kernel"))]
     step = None
     for s in starts:
         ends = [i for i in range(s, len(seq)) if seq[i]["kernel"].startswith("adam_kernel")]
