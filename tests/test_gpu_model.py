@@ -636,30 +636,41 @@ def test_buffer_reuse_changes_nothing(dec, kw, size, width, depth):
     kw = dict(num_channels=3, **kw)
     rng = np.random.default_rng(19)
     x = rng.random((4, size, size, 3), dtype=np.float32)
-    a = unet_model_builder(dec, size, size, width, depth, train_mode="from_scratch", **kw).ResNet50()
-    b = unet_model_builder(dec, size, size, width, depth, train_mode="from_scratch", **kw).ResNet50()
+    a, a2, b = (unet_model_builder(dec, size, size, width, depth, train_mode="from_scratch", **kw).ResNet50() for _ in range(3))
     targets, losses = _targets_for(a, kw, rng, 4)
-    a.keep_activations, b.keep_activations = True, False
-    for m in (a, b):
+    a.keep_activations, a2.keep_activations, b.keep_activations = True, True, False
+    for m in (a, a2, b):
         m.compile(loss=losses if len(losses) > 1 else losses[0], optimizer=Adam(1e-3))
+    a2.set_weight_dict(a.get_weight_dict())
     b.set_weight_dict(a.get_weight_dict())
     tg = targets if len(targets) > 1 else targets[0]
-    la, lb = a.train_on_batch(x, tg), b.train_on_batch(x, tg)
-    ea, eb = a._engine(4, True), b._engine(4, True)
+    la, la2, lb = a.train_on_batch(x, tg), a2.train_on_batch(x, tg), b.train_on_batch(x, tg)
+    ea, ea2, eb = a._engine(4, True), a2._engine(4, True), b._engine(4, True)
     torch.cuda.synchronize()
-    assert not ea.reuse and eb.reuse
+    assert not ea.reuse and not ea2.reuse and eb.reuse
     st = eb.planner.reuse_stats
     assert st["arena_bytes"] <= 0.75 * st["tensor_bytes"], st
-    assert abs(la - lb) < 1e-3 * max(1.0, abs(la)), (la, lb)
-    for oa, ob in zip(ea.outputs, eb.outputs):
-        assert rel_l2(ob["y"], oa["y"]) < 1.5e-2, (oa["name"], rel_l2(ob["y"], oa["y"]))
-    ga, gb = ea.get_grads(), eb.get_grads()
+    # a2 is a second engine WITHOUT reuse: what it differs from a by is the run-to-run noise of this model.  The forward pass is
+    # reproducible (per-CTA statistics rows summed in a fixed order; double-precision accumulators where a BatchNorm takes its
+    # statistics from its producer's epilogue); backward adds dgamma / dbeta / split-K partials with fp32 red.add, whose order
+    # moves the last bit of a BatchNorm-backward mean and with it bf16 roundings downstream: 3e-3 .. 3e-2 on the first layers'
+    # kernel gradients of these random-init models (printed below).  Reuse may not add to that.
+    assert abs(la - lb) < 1e-3 * max(1.0, abs(la)) + 3 * abs(la - la2), (la, la2, lb)
+    for oa, oa2, ob in zip(ea.outputs, ea2.outputs, eb.outputs):
+        noise = rel_l2(oa2["y"], oa["y"])
+        assert rel_l2(ob["y"], oa["y"]) < max(1e-2, 3 * noise), (oa["name"], rel_l2(ob["y"], oa["y"]), noise)
+    ga, ga2, gb = ea.get_grads(), ea2.get_grads(), eb.get_grads()
     gmax = max(float(np.abs(v).max()) for v in ga.values())
+    worst_noise = 0.0
     for key in ga:
         if key.endswith("/kernel"):
-            assert rel_l2(gb[key], ga[key]) < 5e-2, (key, rel_l2(gb[key], ga[key]))
+            noise = rel_l2(ga2[key], ga[key])
+            worst_noise = max(worst_noise, noise)
+            assert rel_l2(gb[key], ga[key]) < max(5e-2, 2 * noise), (key, rel_l2(gb[key], ga[key]), noise)
         else:       # per-channel sums (gamma, beta, bias) may cancel down to rounding noise: absolute criterion on the model's gradient scale
-            assert float(np.abs(gb[key] - ga[key]).max()) < 2e-2 * gmax, (key, float(np.abs(gb[key] - ga[key]).max()), gmax)
+            noise = float(np.abs(ga2[key] - ga[key]).max())
+            assert float(np.abs(gb[key] - ga[key]).max()) < max(2e-2 * gmax, 3 * noise), (key, float(np.abs(gb[key] - ga[key]).max()), noise, gmax)
+    print(f"[reuse {dec} {kw}] run-to-run noise of the kernel gradients without reuse: worst tensor {worst_noise:.2e}")
     with pytest.raises(Exception, match="keep_activations"):
         eb.tap(next(iter(eb.planner.taps)))
     for _ in range(2):

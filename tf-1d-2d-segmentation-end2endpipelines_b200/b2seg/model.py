@@ -178,6 +178,10 @@ class Model:
         self.world_size = 1
         self._dist = None
         self.exchange_bucket_bytes = int(os.environ.get("B2SEG_BUCKET_MB", "64")) << 20   # gradient-exchange bucket (data parallel): overlap granularity vs launch count
+        # one process, one GPU: Adam is cut into buckets of this size and each bucket runs on a side stream as soon as backward has
+        # finished its gradients, beside the remaining (tensor-core bound) backward kernels instead of after them.  0 = one Adam
+        # launch after backward.
+        self.adam_overlap_bytes = int(os.environ.get("B2SEG_ADAM_OVERLAP_MB", "8")) << 20
         self._ds_targets = None
         # False (default): activation / gradient buffers share one arena by liveness (Planner._assign_memory).  True: every layer's
         # tensors stay readable after a step (layer_output / the per-layer parity tests); B2SEG_KEEP_ACTIVATIONS=1 forces it.
@@ -342,12 +346,15 @@ class Model:
             if bucket and self.dp_mode == "sharded":
                 import torch.distributed as dist
                 shard = (dist.get_rank(getattr(self, "_pg", None)), dist.get_world_size(getattr(self, "_pg", None)))
+            exchange = bucket > 0
+            if training and not bucket:
+                bucket = self.adam_overlap_bytes
             eng = Engine(self.graph, batch, training=training, losses=self._losses, loss_weights=self._loss_weights, adam=adam,
                          share_params_from=self._primary, adam_bucket_bytes=bucket, reuse=not self.keep_activations, shard=shard)
             if self._primary is None:
                 self._primary = eng
                 eng.set_weights(self._weights)
-            if bucket:
+            if exchange:
                 import torch.distributed as dist
                 if dist.get_backend(getattr(self, "_pg", None)) == "nccl":
                     eng.reserve_sms_for_exchange(eng.planner.exchange_schedule(self.exchange_bucket_bytes), group=getattr(self, "_pg", None))
@@ -423,7 +430,7 @@ class Model:
     def _exchange_schedule(self, eng):
         sched = getattr(eng, "_exchange", None)
         if sched is None:
-            sched = eng._exchange = eng.planner.exchange_schedule(self.exchange_bucket_bytes)
+            sched = eng._exchange = eng.planner.exchange_schedule(eng.adam_bucket_bytes or self.exchange_bucket_bytes)
         return sched
 
     def _step(self, eng, return_loss=True):
@@ -458,10 +465,46 @@ class Model:
                     return float(eng.loss_buf.item())
                 return None
             wait_all(works)
+        elif eng.adam_bucket_bytes and len(eng.planner.ops[2]) > 1:
+            return self._step_overlapped_adam(eng, return_loss)
         else:
             eng.backward()
         self._adam_step += 1
         eng.optimizer_step(self.optimizer.learning_rate, scale, step=self._adam_step)
+        if return_loss:
+            return float(eng.loss_buf.item())
+        return None
+
+    def _step_overlapped_adam(self, eng, return_loss):
+        """One process: backward is replayed in the ranges of the bucket schedule (Planner.exchange_schedule — bucket i of the flat
+        gradient arena is final, and its weights are no longer read, once the first n_ops backward ops have run); bucket i's Adam is
+        enqueued on a side stream behind exactly those ops and runs beside the rest of backward (HBM-bound Adam under the
+        tensor-core-bound convolutions).  The step's stream rejoins the side stream before anything else runs."""
+        import torch
+        sched = self._exchange_schedule(eng)
+        cuda = eng.dev.type == "cuda"
+        self._adam_step += 1
+        eng.optimizer_begin(self.optimizer.learning_rate, 1.0, step=self._adam_step)
+        if cuda:
+            if not hasattr(eng, "_side_stream"):
+                eng._side_stream = torch.cuda.Stream(device=eng.dev)
+            main, side = torch.cuda.current_stream(eng.dev), eng._side_stream
+        done = 0
+        for i, (n_ops, _lo, _hi) in enumerate(sched):
+            if n_ops > done:
+                eng.run_range(1, done, n_ops - done)
+                done = n_ops
+            if cuda:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    eng.run_range(2, i, 1)
+            else:
+                eng.run_range(2, i, 1)
+        n_total = eng.planner.num_launch_ops(1)
+        if n_total > done:
+            eng.run_range(1, done, n_total - done)
+        if cuda:
+            main.wait_stream(side)
         if return_loss:
             return float(eng.loss_buf.item())
         return None

@@ -60,71 +60,97 @@ __device__ __forceinline__ void update_moving(const GateK& k, float* mm, float* 
 }
 
 // ------------------------------------------------------------------------------------------ forward, low resolution
-// One warp handles 32 / LPP pixels at a time: LPP = min(C / 8, 32) lanes per pixel, each lane C / 8 / LPP 8-channel vectors.
-// Shared memory: [5][C] floats (scale_a, shift_a, scale_b, shift_b, w3).
+// One warp handles 32 / LPP pixels at a time: LPP = min(C / 8, 32) lanes per pixel, each lane VPL = C / 8 / LPP 8-channel vectors.
+// Shared memory: [4][C] floats (scale_a, scale_b, shift_a + shift_b, w3).  All 2 * GU * VPL 16-byte loads of a round are issued
+// before the first use (clamped addresses instead of branches), so a warp has 4 - 8 KB in flight.
+// c = a * scale_a + (b * scale_b + (shift_a + shift_b)) — the same expression in the two backward passes (identical ReLU mask).
+template <int VPL>      // 1, 2, 4; 0 = any (run-time trip count)
 __global__ void __launch_bounds__(256) gate_mid_fwd_kernel(const GateK k) {
   pdl_prologue();
   extern __shared__ float sm[];
   const int C = k.C;
-  float *s_sa = sm, *s_ta = sm + C, *s_sb = sm + 2 * C, *s_tb = sm + 3 * C, *s_w3 = sm + 4 * C;
+  float *s_sa = sm, *s_sb = sm + C, *s_t = sm + 2 * C, *s_w3 = sm + 3 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float sc, sh, mu, rs;
-    bn_coeffs(k, k.sums_a, k.gamma_a, k.beta_a, k.mm_a, k.mv_a, c, &sc, &sh, &mu, &rs);
-    s_sa[c] = sc; s_ta[c] = sh;
+    float sca, sha, mua, rsa, scb, shb, mub, rsb;
+    bn_coeffs(k, k.sums_a, k.gamma_a, k.beta_a, k.mm_a, k.mv_a, c, &sca, &sha, &mua, &rsa);
+    bn_coeffs(k, k.sums_b, k.gamma_b, k.beta_b, k.mm_b, k.mv_b, c, &scb, &shb, &mub, &rsb);
+    s_sa[c] = sca; s_sb[c] = scb; s_t[c] = sha + shb;
     if (blockIdx.x == 0) {
-      k.vec_a[c] = sc; k.vec_a[C + c] = sh; k.vec_a[2 * C + c] = mu; k.vec_a[3 * C + c] = rs;
-      if (k.training) update_moving(k, k.mm_a, k.mv_a, c, mu, fmaxf(k.sums_a[C + c] * k.inv_count - mu * mu, 0.f));
-    }
-    bn_coeffs(k, k.sums_b, k.gamma_b, k.beta_b, k.mm_b, k.mv_b, c, &sc, &sh, &mu, &rs);
-    s_sb[c] = sc; s_tb[c] = sh;
-    if (blockIdx.x == 0) {
-      k.vec_b[c] = sc; k.vec_b[C + c] = sh; k.vec_b[2 * C + c] = mu; k.vec_b[3 * C + c] = rs;
-      if (k.training) update_moving(k, k.mm_b, k.mv_b, c, mu, fmaxf(k.sums_b[C + c] * k.inv_count - mu * mu, 0.f));
+      k.vec_a[c] = sca; k.vec_a[C + c] = sha; k.vec_a[2 * C + c] = mua; k.vec_a[3 * C + c] = rsa;
+      k.vec_b[c] = scb; k.vec_b[C + c] = shb; k.vec_b[2 * C + c] = mub; k.vec_b[3 * C + c] = rsb;
+      if (k.training) {
+        update_moving(k, k.mm_a, k.mv_a, c, mua, fmaxf(k.sums_a[C + c] * k.inv_count - mua * mua, 0.f));
+        update_moving(k, k.mm_b, k.mv_b, c, mub, fmaxf(k.sums_b[C + c] * k.inv_count - mub * mub, 0.f));
+      }
     }
     s_w3[c] = k.w3[c];
   }
   __syncthreads();
   const int vpp = C >> 3;
   const int lpp = vpp < 32 ? vpp : 32;
-  const int vpl = vpp / lpp;
+  const int vpl = VPL ? VPL : vpp / lpp;
   const int ppw = 32 / lpp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / lpp, lv = lane % lpp;
   const float b3 = k.b3[0];
   float acc_s = 0.f, acc_q = 0.f;
   const int groups = (k.npix + ppw - 1) / ppw;
-  constexpr int GU = 4;     // pixel groups in flight per warp (memory-level parallelism: one group is only 32 x 2 16-byte loads)
+  constexpr int GU = VPL == 4 ? 1 : VPL == 2 ? 2 : 4;     // pixel groups in flight per warp (8 x 2 16-byte loads per lane)
+  constexpr int NV = VPL ? VPL : 1;
   for (int g0 = (blockIdx.x * 8 + warp) * GU; g0 < groups; g0 += gridDim.x * 8 * GU) {
     float dot[GU];
     int pixs[GU];
+    const __nv_bfloat16 *pa[GU], *pb[GU];
+    uint4 ra[GU][NV], rb[GU][NV];
 #pragma unroll
     for (int u = 0; u < GU; ++u) {
       const int pix = (g0 + u) * ppw + sub;
       pixs[u] = pix;
-      dot[u] = 0.f;
-      if (g0 + u < groups && pix < k.npix) {
-        const uint32_t q = fast_div((uint32_t)pix, k.fd_w);
-        const int x = pix - (int)q * k.w;
-        const uint32_t n = fast_div(q, k.fd_h);
-        const int y = (int)q - (int)n * k.h;
-        for (int i = 0; i < vpl; ++i) {
-          const int c0 = (lv + i * lpp) * 8;
-          float a[8], b[8];
-          load8(vaddr(k.za, (int)n, y, x, c0), a);
-          load8(vaddr(k.zb, (int)n, y, x, c0), b);
+      const int pc = pix < k.npix ? pix : k.npix - 1;
+      const uint32_t q = fast_div((uint32_t)pc, k.fd_w);
+      const int x = pc - (int)q * k.w;
+      const uint32_t n = fast_div(q, k.fd_h);
+      const int y = (int)q - (int)n * k.h;
+      pa[u] = vaddr(k.za, (int)n, y, x, lv * 8);
+      pb[u] = vaddr(k.zb, (int)n, y, x, lv * 8);
+      if (VPL) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float c = fmaxf(fmaf(a[e], s_sa[c0 + e], s_ta[c0 + e]) + fmaf(b[e], s_sb[c0 + e], s_tb[c0 + e]), 0.f);
-            dot[u] = fmaf(c, s_w3[c0 + e], dot[u]);
-          }
+        for (int i = 0; i < NV; ++i) {
+          ra[u][i] = __ldg(reinterpret_cast<const uint4*>(pa[u] + i * lpp * 8));
+          rb[u][i] = __ldg(reinterpret_cast<const uint4*>(pb[u] + i * lpp * 8));
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < GU; ++u) {
+      float d = 0.f;
+      for (int i = 0; i < vpl; ++i) {
+        const int c0 = (lv + i * lpp) * 8;
+        uint4 va, vb;
+        if (VPL) { va = ra[u][VPL ? i : 0]; vb = rb[u][VPL ? i : 0]; }
+        else {
+          va = __ldg(reinterpret_cast<const uint4*>(pa[u] + i * lpp * 8));
+          vb = __ldg(reinterpret_cast<const uint4*>(pb[u] + i * lpp * 8));
+        }
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&va);
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+          const int c = c0 + 2 * e;
+          const float c_lo = fmaxf(fmaf(fa.x, s_sa[c], fmaf(fb.x, s_sb[c], s_t[c])), 0.f);
+          const float c_hi = fmaxf(fmaf(fa.y, s_sa[c + 1], fmaf(fb.y, s_sb[c + 1], s_t[c + 1])), 0.f);
+          d = fmaf(c_lo, s_w3[c], d);
+          d = fmaf(c_hi, s_w3[c + 1], d);
+        }
+      }
+      dot[u] = d;
+    }
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
       float dsum = dot[u];
       for (int off = lpp >> 1; off > 0; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
-      if (lv == 0 && g0 + u < groups && pixs[u] < k.npix) {
+      if (lv == 0 && pixs[u] < k.npix) {
         const float z = dsum + b3;
         k.z[pixs[u]] = z;
         acc_s += z; acc_q = fmaf(z, z, acc_q);
@@ -198,69 +224,74 @@ __device__ __forceinline__ Resampler gate_resample(const GateK& k, int n, int oy
 }
 
 // ------------------------------------------------------------------------------------------ forward / backward, high resolution
-// Block = 256 threads = one segment of GP pixels of one high-resolution row; r per pixel is computed once into shared memory,
-// then the (pixel, 8-channel vector) pairs are streamed.  BWD: dskip = dout * r and dr = sum_c dout * skip (per-pixel reduction).
-constexpr int kGateSeg = 256;
+// Block = 256 threads; one block iteration = a chunk of P consecutive high-resolution pixels in (n, y, x) order (P = 32 .. 1024, a
+// power of two picked by the host so that small maps still fill the SMs).  r and the pixel coordinates are computed once per pixel
+// into shared memory, then the chunk's (pixel, 8-channel vector) items are streamed, kGateU 16-byte loads in flight per thread and no
+// barrier until the chunk is done.  BWD: dskip = dout * r and dr = sum_c dout * skip (per-pixel reduction: warp shuffle, then shared).
+constexpr int kGateP = 1024;
 constexpr int kGateU = 4;      // (pixel, vector) items in flight per thread
 template <int MODE>   // 0 forward: out = skip * r;  1 backward: dr = sum_c dout * skip (+ dskip = dout * r when no second pass follows);
                       // 2 backward, second pass: dskip = dout * r + the stride-2 projection's input gradient at the even pixels
-__global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
+__global__ void __launch_bounds__(256) gate_out_kernel(const GateK k, int P, int vshift) {
   constexpr bool BWD = MODE == 1;
   pdl_prologue();
-  __shared__ float s_r[kGateSeg];
-  __shared__ float s_dr[kGateSeg];
+  __shared__ float s_r[kGateP];
+  __shared__ float s_dr[BWD ? kGateP : 1];
+  __shared__ uint32_t s_ny[kGateP];     // n << 16 | y
+  __shared__ uint16_t s_x[kGateP];
   __shared__ float s_wt[16];
   float sc, sh, mu, rs;
   bn3_coeffs(k, &sc, &sh, &mu, &rs);
   if (threadIdx.x < 16) s_wt[threadIdx.x] = k.wt[threadIdx.x * k.wt_stride];
   const float bt = k.bt[0];
   const int W2 = 2 * k.w, H2 = 2 * k.h;
-  const int segs_per_row = (W2 + kGateSeg - 1) / kGateSeg;
-  const int total_segs = k.skip.N * H2 * segs_per_row;
-  const int vpp = k.skip.C >> 3;
-  const int span = vpp < 32 ? vpp : 32;
+  const int total = k.skip.N * H2 * W2;
+  const int vmask = (1 << vshift) - 1;
+  const int span = vmask < 31 ? vmask + 1 : 32;
   if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0 && k.training) {
     const float var = fmaxf(k.sums3[1] * k.inv_count - mu * mu, 0.f);
     const float uv = (k.bessel && k.count > 1.f) ? var * k.count / (k.count - 1.f) : var;
     k.mm3[0] = k.mm3[0] * k.momentum + mu * (1.f - k.momentum);
     k.mv3[0] = k.mv3[0] * k.momentum + uv * (1.f - k.momentum);
   }
-  for (int seg = blockIdx.x; seg < total_segs; seg += gridDim.x) {
-    const uint32_t rowi = (uint32_t)seg / (uint32_t)segs_per_row;
-    const int x0 = (seg - (int)rowi * segs_per_row) * kGateSeg;
-    const uint32_t n = fast_div(rowi, k.fd_h2);
-    const int oy = (int)rowi - (int)n * H2;
-    const int npx = W2 - x0 < kGateSeg ? W2 - x0 : kGateSeg;
+  for (int p0 = blockIdx.x * P; p0 < total; p0 += gridDim.x * P) {
+    const int npx = total - p0 < P ? total - p0 : P;
     __syncthreads();
-    if ((int)threadIdx.x < npx) {
-      const int ox = x0 + (int)threadIdx.x;
-      s_r[threadIdx.x] = gate_resample<MODE != 0>(k, (int)n, oy, ox, sc, sh, s_wt, bt).r;      // backward: m from the map the forward left
-      if (BWD) s_dr[threadIdx.x] = 0.f;
+    for (int j = threadIdx.x; j < npx; j += 256) {
+      const uint32_t rowi = fast_div((uint32_t)(p0 + j), k.fd_w2);
+      const int ox = p0 + j - (int)rowi * W2;
+      const uint32_t n = fast_div(rowi, k.fd_h2);
+      const int oy = (int)rowi - (int)n * H2;
+      s_ny[j] = (n << 16) | (uint32_t)oy;
+      s_x[j] = (uint16_t)ox;
+      s_r[j] = gate_resample<MODE != 0>(k, (int)n, oy, ox, sc, sh, s_wt, bt).r;      // backward: m from the map the forward left
+      if (BWD) s_dr[j] = 0.f;
       else if (MODE == 0 && !(oy & 1) && !(ox & 1)) k.m[((int)n * k.h + (oy >> 1)) * k.w + (ox >> 1)] = gate_m<false>(k, (int)n, oy >> 1, ox >> 1, sc, sh);
     }
     __syncthreads();
-    const int work = npx * vpp;
+    const int work = npx << vshift;
     // (uniform trip count: the warp shuffles below need every lane, also in the ragged last round)
     for (int i0 = 0; i0 < work; i0 += 256 * kGateU) {
       uint4 sv[kGateU], dv4[kGateU];
-      int pp[kGateU], vv[kGateU];
+      int pp[kGateU], cc[kGateU];
       bool live[kGateU];
 #pragma unroll
       for (int u = 0; u < kGateU; ++u) {
         const int i = i0 + u * 256 + (int)threadIdx.x;
         live[u] = i < work;
-        pp[u] = live[u] ? i / vpp : 0;
-        vv[u] = live[u] ? i - pp[u] * vpp : 0;
+        pp[u] = live[u] ? i >> vshift : 0;
+        cc[u] = live[u] ? (i & vmask) * 8 : 0;
         sv[u] = make_uint4(0u, 0u, 0u, 0u);
         dv4[u] = sv[u];
         if (live[u]) {
+          const uint32_t ny = s_ny[pp[u]];
+          const int n = (int)(ny >> 16), oy = (int)(ny & 0xffffu), ox = (int)s_x[pp[u]];
           if (MODE == 2) {       // sv = the projection's input gradient (low resolution) at even pixels, else 0; dv4 = dout
-            const int ox = x0 + pp[u];
-            if (!(oy & 1) && !(ox & 1)) sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.da_low, (int)n, oy >> 1, ox >> 1, vv[u] * 8)));
-            dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, (int)n, oy, ox, vv[u] * 8)));
+            if (!(oy & 1) && !(ox & 1)) sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.da_low, n, oy >> 1, ox >> 1, cc[u])));
+            dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, n, oy, ox, cc[u])));
           } else {
-            sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.skip, (int)n, oy, x0 + pp[u], vv[u] * 8)));
-            if (BWD) dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, (int)n, oy, x0 + pp[u], vv[u] * 8)));
+            sv[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.skip, n, oy, ox, cc[u])));
+            if (BWD) dv4[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.dout, n, oy, ox, cc[u])));
           }
         }
       }
@@ -272,10 +303,12 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(hs[e]); s[2 * e] = t.x; s[2 * e + 1] = t.y; }
         const float r = s_r[pp[u]];
+        const uint32_t ny = s_ny[pp[u]];
+        const int n = (int)(ny >> 16), oy = (int)(ny & 0xffffu), ox = (int)s_x[pp[u]];
         if (MODE == 0) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = s[e] * r;
-          if (live[u]) store8(vaddr(k.out, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
+          if (live[u]) store8(vaddr(k.out, n, oy, ox, cc[u]), o);
         } else if (MODE == 2) {
           float d[8];
           const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&dv4[u]);
@@ -283,7 +316,7 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
           for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(hd[e]); d[2 * e] = t.x; d[2 * e + 1] = t.y; }
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = fmaf(d[e], r, s[e]);
-          if (live[u]) store8(vaddr(k.dskip, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
+          if (live[u]) store8(vaddr(k.dskip, n, oy, ox, cc[u]), o);
         } else {
           float d[8];
           const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&dv4[u]);
@@ -292,8 +325,8 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
           float part = 0.f;
 #pragma unroll
           for (int e = 0; e < 8; ++e) { o[e] = d[e] * r; part = fmaf(d[e], s[e], part); }
-          if (live[u] && k.dskip.ptr) store8(vaddr(k.dskip, (int)n, oy, x0 + pp[u], vv[u] * 8), o);
-          // lanes holding the same pixel are adjacent (vpp is a power of two): reduce within the warp first
+          if (live[u] && k.dskip.ptr) store8(vaddr(k.dskip, n, oy, ox, cc[u]), o);
+          // lanes holding the same pixel are adjacent (the vectors per pixel are a power of two): reduce within the warp first
           for (int off = span >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
           if (live[u] && (threadIdx.x & (span - 1)) == 0) atomicAdd(&s_dr[pp[u]], part);
         }
@@ -301,7 +334,7 @@ __global__ void __launch_bounds__(256) gate_out_kernel(const GateK k) {
     }
     if (BWD) {
       __syncthreads();
-      if ((int)threadIdx.x < npx) k.dr[((size_t)n * H2 + oy) * W2 + x0 + threadIdx.x] = s_dr[threadIdx.x];
+      for (int j = threadIdx.x; j < npx; j += 256) k.dr[p0 + j] = s_dr[j];     // dr is dense in (n, y, x) order
     }
   }
 }
@@ -375,7 +408,10 @@ __global__ void __launch_bounds__(256) gate_low_bwd_kernel(const GateK k) {
 
 // ------------------------------------------------------------------------------------------ backward, projections
 // Thread = one 8-channel vector (tcv) of a strided set of pixels (trow); blockIdx.x = vector group, blockIdx.y strides the pixels.
-// PASS 0: per-channel sums {g, g zhat_a, g zhat_b, dz3 c}; PASS 1: dza, dzb.
+// PASS 0: per-channel sums {g, g zhat_a, g zhat_b, dz3 c}; PASS 1: dza, dzb.   With c = a sa + b sb + t and g = [c > 0] dz3 w3:
+//   PASS 0 accumulates sum g, sum g a, sum g b, sum dz3 relu(c) (constants sa, sb, t, w3 only) and turns the raw products into
+//          sum g zhat = rstd (sum g x - mean sum g) once per block, before the atomics;
+//   PASS 1 dza = sa (g - mean(g) - zhat_a mean(g zhat_a)) = [c > 0] dz3 (sa w3) - A0 - A1 a with per-channel A0, A1 (same for b).
 template <int PASS>
 __global__ void __launch_bounds__(256, 2) gate_mid_bwd_kernel(const GateK k, int cvb) {
   pdl_prologue();
@@ -385,82 +421,85 @@ __global__ void __launch_bounds__(256, 2) gate_mid_bwd_kernel(const GateK k, int
   float sc3, sh3, mu3, rs3;
   bn3_coeffs(k, &sc3, &sh3, &mu3, &rs3);
   const float mg = k.bsums3[0] * k.inv_count, mgz = k.bsums3[1] * k.inv_count;     // mean g3, mean g3 zhat3
-  float sa[8], ta[8], sb[8], tb[8], w3[8], ma[8], ra[8], mb[8], rb[8], cg[8], cga[8], cgb[8];
+  float sa[8], sb[8], tt[8], w3[8];                    // PASS 1: w3 is not kept, saw = sa w3 and sbw = sb w3 are
+  float saw[PASS ? 8 : 1], sbw[PASS ? 8 : 1], A0[PASS ? 8 : 1], A1[PASS ? 8 : 1], B0[PASS ? 8 : 1], B1[PASS ? 8 : 1];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = c0 + e;
-    sa[e] = k.vec_a[c]; ta[e] = k.vec_a[C + c]; ma[e] = k.vec_a[2 * C + c]; ra[e] = k.vec_a[3 * C + c];
-    sb[e] = k.vec_b[c]; tb[e] = k.vec_b[C + c]; mb[e] = k.vec_b[2 * C + c]; rb[e] = k.vec_b[3 * C + c];
+    sa[e] = k.vec_a[c]; sb[e] = k.vec_b[c]; tt[e] = k.vec_a[C + c] + k.vec_b[C + c];
     w3[e] = k.w3[c];
     if (PASS == 1) {
-      cg[e] = k.bsums_ab[c] * k.inv_count; cga[e] = k.bsums_ab[C + c] * k.inv_count; cgb[e] = k.bsums_ab[2 * C + c] * k.inv_count;
+      const float ma = k.vec_a[2 * C + c], ra = k.vec_a[3 * C + c], mb = k.vec_b[2 * C + c], rb = k.vec_b[3 * C + c];
+      const float cg = k.bsums_ab[c] * k.inv_count, cga = k.bsums_ab[C + c] * k.inv_count, cgb = k.bsums_ab[2 * C + c] * k.inv_count;
+      saw[e] = sa[e] * w3[e]; sbw[e] = sb[e] * w3[e];
+      A1[e] = sa[e] * ra * cga; A0[e] = sa[e] * cg - A1[e] * ma;
+      B1[e] = sb[e] * rb * cgb; B0[e] = sb[e] * cg - B1[e] * mb;
     }
   }
-  float acc[4][8];
+  float acc[PASS ? 1 : 4][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < (PASS ? 1 : 4); ++a)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
   float acc_db3 = 0.f;
-  constexpr int PU = 2;      // pixels in flight per thread (two blocks per SM: 128 registers)
+  constexpr int PU = PASS ? 2 : 4;      // pixels in flight per thread (two blocks per SM: 128 registers)
   const int pstride = gridDim.y * rows;
   for (int pix0 = blockIdx.y * rows + trow; pix0 < k.npix; pix0 += pstride * PU) {
     uint4 rawa[PU], rawb[PU];
     float dz3s[PU];
-    int ns[PU], ys[PU], xs[PU];
+    const __nv_bfloat16 *oa[PU], *ob[PU];
 #pragma unroll
     for (int u = 0; u < PU; ++u) {
       const int pix = pix0 + u * pstride;
       const int pc = pix < k.npix ? pix : k.npix - 1;
       const uint32_t q = fast_div((uint32_t)pc, k.fd_w);
-      xs[u] = pc - (int)q * k.w;
+      const int x = pc - (int)q * k.w;
       const uint32_t n = fast_div(q, k.fd_h);
-      ys[u] = (int)q - (int)n * k.h;
-      ns[u] = (int)n;
+      const int y = (int)q - (int)n * k.h;
       const float zh3 = (k.z[pc] - mu3) * rs3;
       dz3s[u] = pix < k.npix ? sc3 * (k.g3[pc] - mg - zh3 * mgz) : 0.f;
-      rawa[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.za, ns[u], ys[u], xs[u], c0)));
-      rawb[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.zb, ns[u], ys[u], xs[u], c0)));
+      rawa[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.za, (int)n, y, x, c0)));
+      rawb[u] = __ldg(reinterpret_cast<const uint4*>(vaddr(k.zb, (int)n, y, x, c0)));
+      if (PASS == 1) { oa[u] = vaddr(k.dza, (int)n, y, x, c0); ob[u] = vaddr(k.dzb, (int)n, y, x, c0); }
     }
 #pragma unroll
     for (int u = 0; u < PU; ++u) {
-    const int pix = pix0 + u * pstride;
-    if (pix >= k.npix) break;
-    const int n = ns[u], y = ys[u], x = xs[u];
-    const float dz3 = dz3s[u];
-    float a[8], b[8];
-    {
-      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&rawa[u]);
-      const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rawb[u]);
+      const int pix = pix0 + u * pstride;
+      if (pix >= k.npix) break;
+      const float dz3 = dz3s[u];
+      float a[8], b[8];
+      {
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&rawa[u]);
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rawb[u]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 ta = __bfloat1622float2(ha[e]), tb = __bfloat1622float2(hb[e]);
-        a[2 * e] = ta.x; a[2 * e + 1] = ta.y; b[2 * e] = tb.x; b[2 * e + 1] = tb.y;
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+          a[2 * e] = fa.x; a[2 * e + 1] = fa.y; b[2 * e] = fb.x; b[2 * e + 1] = fb.y;
+        }
       }
-    }
-    if (PASS == 0) {
-      if (blockIdx.x == 0 && tcv == 0 && k.db3) acc_db3 += dz3;
+      if (PASS == 0) {
+        if (blockIdx.x == 0 && tcv == 0 && k.db3) acc_db3 += dz3;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float c = fmaf(a[e], sa[e], ta[e]) + fmaf(b[e], sb[e], tb[e]);
-        const float g = c > 0.f ? dz3 * w3[e] : 0.f;
-        acc[0][e] += g;
-        acc[1][e] = fmaf(g, (a[e] - ma[e]) * ra[e], acc[1][e]);
-        acc[2][e] = fmaf(g, (b[e] - mb[e]) * rb[e], acc[2][e]);
-        acc[3][e] = fmaf(dz3, fmaxf(c, 0.f), acc[3][e]);
-      }
-    } else {
-      float da[8], db[8];
+        for (int e = 0; e < 8; ++e) {
+          const float c = fmaf(a[e], sa[e], fmaf(b[e], sb[e], tt[e]));
+          const float g = c > 0.f ? dz3 * w3[e] : 0.f;
+          acc[0][e] += g;
+          acc[1][e] = fmaf(g, a[e], acc[1][e]);
+          acc[2][e] = fmaf(g, b[e], acc[2][e]);
+          acc[3][e] = fmaf(dz3, fmaxf(c, 0.f), acc[3][e]);
+        }
+      } else {
+        float da[8], db[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float c = fmaf(a[e], sa[e], ta[e]) + fmaf(b[e], sb[e], tb[e]);
-        const float g = c > 0.f ? dz3 * w3[e] : 0.f;
-        da[e] = sa[e] * (g - cg[e] - (a[e] - ma[e]) * ra[e] * cga[e]);
-        db[e] = sb[e] * (g - cg[e] - (b[e] - mb[e]) * rb[e] * cgb[e]);
+        for (int e = 0; e < 8; ++e) {
+          const float c = fmaf(a[e], sa[e], fmaf(b[e], sb[e], tt[e]));
+          const float G = c > 0.f ? dz3 : 0.f;
+          da[e] = fmaf(G, saw[e], -fmaf(A1[e], a[e], A0[e]));
+          db[e] = fmaf(G, sbw[e], -fmaf(B1[e], b[e], B0[e]));
+        }
+        store8(oa[u], da);
+        store8(ob[u], db);
       }
-      store8(vaddr(k.dza, (int)n, y, x, c0), da);
-      store8(vaddr(k.dzb, (int)n, y, x, c0), db);
-    }
     }
   }
   if (PASS == 0) {
@@ -475,10 +514,15 @@ __global__ void __launch_bounds__(256, 2) gate_mid_bwd_kernel(const GateK k, int
     // thread t < cvb * 32 sums slot (t % 32) of vector (t / 32) over the rows
     for (int t = threadIdx.x; t < cvb * 32; t += 256) {
       const int v = t >> 5, slot = t & 31;
-      float s = 0.f;
-      for (int r = 0; r < rows; ++r) s += red[(r * cvb + v) * 33 + slot];
-      const int c = (blockIdx.x * cvb + v) * 8 + (slot & 7);
       const int which = slot >> 3;
+      float s = 0.f, sg = 0.f;
+      for (int r = 0; r < rows; ++r) {
+        s += red[(r * cvb + v) * 33 + slot];
+        if (which == 1 || which == 2) sg += red[(r * cvb + v) * 33 + (slot & 7)];     // sum g of the same channel
+      }
+      const int c = (blockIdx.x * cvb + v) * 8 + (slot & 7);
+      if (which == 1) s = k.vec_a[3 * C + c] * (s - k.vec_a[2 * C + c] * sg);         // sum g zhat_a = rstd_a (sum g a - mean_a sum g)
+      if (which == 2) s = k.vec_b[3 * C + c] * (s - k.vec_b[2 * C + c] * sg);
       if (which < 3) atomicAdd(k.bsums_ab + which * C + c, s);
       else atomicAdd(k.dw3 + c, s);
     }
@@ -511,7 +555,7 @@ static int fill_gate(const b2seg_gate_desc* d, GateK* k, bool bwd) {
     set_error("gate: skip (%d,%d,%d,%d) must be (N, 2h, 2w, 8 * 2^k) for projections (%d,%d,%d)", d->skip.N, d->skip.H, d->skip.W, d->skip.C, za.N, za.H, za.W);
     return -1;
   }
-  if ((long long)za.N * za.H * za.W * 4 >= (1ll << 31)) { set_error("gate: map too large"); return -1; }
+  if ((long long)za.N * za.H * za.W * 4 >= (1ll << 31) || za.N >= 65536 || 2 * za.H >= 65536 || 2 * za.W >= 65536) { set_error("gate: map too large"); return -1; }
   if (!d->w3 || !d->b3 || !d->z || !d->m || !d->wt || !d->bt || !d->gamma3 || !d->beta3 || !d->mm3 || !d->mv3 || !d->vec_a || !d->vec_b) { set_error("gate: null parameter"); return -1; }
   if (d->training && (!d->sums_a || !d->sums_b || !d->sums3)) { set_error("gate: training needs the statistics accumulators"); return -1; }
   k->za = dv(d->za); k->zb = dv(d->zb); k->skip = dv(d->skip); k->out = dv(d->out);
@@ -543,26 +587,33 @@ struct GateLaunch : PreparedOp {
   int mode = 0;
   int launch(cudaStream_t s) override {
     const int sms = num_sms();
-    const int W2 = 2 * k.w, H2 = 2 * k.h;
-    const int segs = k.skip.N * H2 * ((W2 + kGateSeg - 1) / kGateSeg);
-    const int grid_out = segs < sms * 8 ? segs : sms * 8;
+    const int total = k.skip.N * 4 * k.h * k.w;
+    int P = kGateP;                                   // pixels per block iteration: smaller when the map would not fill the SMs
+    while (P > 32 && total / P < sms * 4) P >>= 1;
+    const int chunks = (total + P - 1) / P;
+    const int grid_out = chunks < sms * 8 ? chunks : sms * 8;
+    int vshift = 0;
+    while ((8 << vshift) < k.skip.C) ++vshift;
     const int vpp = k.C / 8;
     if (!bwd) {
       const int lpp = vpp < 32 ? vpp : 32, ppw = 32 / lpp;
       const int groups = (k.npix + ppw - 1) / ppw;
-      int grid = (groups + 31) / 32;      // 8 warps x 4 groups per block iteration
+      const int gu = vpp / lpp == 4 ? 1 : vpp / lpp == 2 ? 2 : 4;      // = GU of the kernel
+      int grid = (groups + 8 * gu - 1) / (8 * gu);      // 8 warps x GU groups per block iteration
       if (grid < 1) grid = 1;
       if (grid > sms * 4) grid = sms * 4;
-      const int smem = 5 * k.C * 4;
-      if (smem > 48 * 1024) B2_CUDA_OK(cudaFuncSetAttribute(gate_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      B2_CUDA_OK(launch_k(gate_mid_fwd_kernel, dim3(grid), dim3(256), smem, s, k));
-      B2_CUDA_OK(launch_k(gate_out_kernel<0>, dim3(grid_out), dim3(256), 0, s, k));
+      const int smem = 4 * k.C * 4;
+      const int vpl = vpp / lpp;
+      auto fwd = vpl == 1 ? gate_mid_fwd_kernel<1> : vpl == 2 ? gate_mid_fwd_kernel<2> : vpl == 4 ? gate_mid_fwd_kernel<4> : gate_mid_fwd_kernel<0>;
+      if (smem > 48 * 1024) B2_CUDA_OK(cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      B2_CUDA_OK(launch_k(fwd, dim3(grid), dim3(256), smem, s, k));
+      B2_CUDA_OK(launch_k(gate_out_kernel<0>, dim3(grid_out), dim3(256), 0, s, k, P, vshift));
     } else if (mode == 2) {
-      B2_CUDA_OK(launch_k(gate_out_kernel<2>, dim3(grid_out), dim3(256), 0, s, k));
+      B2_CUDA_OK(launch_k(gate_out_kernel<2>, dim3(grid_out), dim3(256), 0, s, k, P, vshift));
     } else {
       B2_CUDA_OK(cudaMemsetAsync(k.bsums3, 0, 8, s));
       B2_CUDA_OK(cudaMemsetAsync(k.bsums_ab, 0, (size_t)3 * k.C * 4, s));
-      B2_CUDA_OK(launch_k(gate_out_kernel<1>, dim3(grid_out), dim3(256), 0, s, k));
+      B2_CUDA_OK(launch_k(gate_out_kernel<1>, dim3(grid_out), dim3(256), 0, s, k, P, vshift));
       int grid_low = (k.npix + 255) / 256;
       if (grid_low > sms * 4) grid_low = sms * 4;
       B2_CUDA_OK(launch_k(gate_low_bwd_kernel, dim3(grid_low), dim3(256), 0, s, k));

@@ -142,10 +142,18 @@ struct BnActFastLaunch : PreparedOp {
 // ResPath glue in one pass (2DCNN/models/unet_variants.py:96-99, 108-112).  `add` fuses Add([shortcut, BatchNormalization(concat)]) +
 // Activation('relu') into the BatchNorm apply; the sums are the batch statistics of the BatchNormalization that follows, so that
 // layer needs no statistics pass of its own.  The sums are taken over the bf16 values that are stored (what its apply will read).
+// The sums are reproducible: the blocks add their partial sums into DOUBLE accumulators (red.add.f64: the order of the adds moves the
+// total by 2^-53 at most), the last block to arrive (ticket counter) rounds the totals to fp32 once, adds them into the caller's
+// accumulators and clears the scratch for the next launch.  (fp32 red.add from every block made a 48-BatchNorm MultiRes net at
+// random init differ by 0.6 % in its output and 10-35 % in its first layers' gradients from one run to the next:
+// profiles/r2_diag_multires_run_to_run.txt; with this scheme the forward pass of two runs is bit-identical.)
 struct BnAct2F {
   FV x, add, out0, out1;
   const float* scale; const float* shift;
   float* stats;
+  double* scratch;         // [2][scr_pitch] double accumulators (owned by the launch object), zero between launches
+  unsigned* tickets;       // [gridDim.x], zero between launches
+  int scr_pitch;
   int stats_pitch;
   int n_out;
   int C, W, rows;
@@ -216,8 +224,27 @@ __global__ void __launch_bounds__(256, 3) bn_act2_fast_kernel(const BnAct2F k) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) { ts[e] += o[e]; tq[e] += o[8 + e]; }
       }
+      double* acc = k.scratch + v * 8;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { atomicAdd(k.stats + v * 8 + e, ts[e]); atomicAdd(k.stats + k.stats_pitch + v * 8 + e, tq[e]); }
+      for (int e = 0; e < 8; ++e) { atomicAdd(acc + e, (double)ts[e]); atomicAdd(acc + k.scr_pitch + e, (double)tq[e]); }
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(k.tickets + blockIdx.x, 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int nch = k.cvb * 8;      // channels of this column of blocks
+      for (int i = threadIdx.x; i < 2 * nch; i += 256) {
+        const int which = i >= nch, c = blockIdx.x * nch + (which ? i - nch : i);
+        if (c >= k.C) continue;
+        double* col = k.scratch + (size_t)which * k.scr_pitch + c;
+        const double total = __ldcg(col);
+        __stcg(col, 0.0);
+        atomicAdd(k.stats + which * k.stats_pitch + c, (float)total);
+      }
+      if (threadIdx.x == 0) k.tickets[blockIdx.x] = 0u;
     }
   }
 }
@@ -226,6 +253,8 @@ struct BnAct2Launch : PreparedOp {
   int act;
   bool add, stats;
   dim3 grid;
+  void* d_scratch = nullptr;
+  ~BnAct2Launch() override { if (d_scratch) cudaFree(d_scratch); }
   template <int ACT>
   void go(cudaStream_t s) {
     const int smem = stats ? 256 * 16 * 4 : 0;
@@ -283,6 +312,15 @@ PreparedOp* prepare_bn_act_fast(const b2seg_bn_act_desc* d) {
     if (L2->stats) {   // one resident wave: the kernel ends with 16 * cvb atomics per block
       const unsigned wave = (unsigned)std::max(1, num_sms() * 3 / (int)L2->grid.x);
       if (L2->grid.y > wave) L2->grid.y = wave;
+      k2.scr_pitch = (int)L2->grid.x * k2.cvb * 8;
+      const size_t scr = (size_t)2 * k2.scr_pitch * sizeof(double), tick = (size_t)L2->grid.x * sizeof(unsigned);
+      if (cudaMalloc(&L2->d_scratch, scr + tick) != cudaSuccess || cudaMemset(L2->d_scratch, 0, scr + tick) != cudaSuccess) {
+        set_error("bn_act: cannot allocate %zu bytes of statistics scratch", scr + tick);
+        delete L2;
+        return nullptr;      // (the caller falls back to the generic kernel, which refuses out_stats: the plan fails loudly)
+      }
+      k2.scratch = reinterpret_cast<double*>(L2->d_scratch);
+      k2.tickets = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(L2->d_scratch) + scr);
     }
     return L2;
   }
