@@ -739,7 +739,7 @@ PreparedOp* prepare_bn_bwd(const b2seg_bn_bwd_desc* d) {
 
 // ------------------------------------------------------------------------------------------ Adam (Keras-2 rule)
 struct AdamK { float* w; const float* g; float* m; float* v; __nv_bfloat16* wb; long long n; float alpha, b1, b2, eps, gs; };
-__global__ void adam_kernel(AdamK k) {
+__global__ void __launch_bounds__(128, 12) adam_kernel(AdamK k) {   // 128 threads x 40 registers: two blocks fit into the register file a persistent convolution CTA (576 x 96) leaves free, so a bucket's Adam runs UNDER the tensor-core kernels of backward
   pdl_prologue();
   const long long n4 = k.n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -774,10 +774,10 @@ struct AdamLaunch : PreparedOp {
     const double t = (double)d.step;
     k.alpha = (float)((double)d.lr * sqrt(1.0 - pow((double)d.beta2, t)) / (1.0 - pow((double)d.beta1, t)));
     k.b1 = d.beta1; k.b2 = d.beta2; k.eps = d.eps; k.gs = d.grad_scale;
-    int grid = grid_for(d.n / 4, 256);
-    const int cap = num_sms() * 16;
+    int grid = grid_for(d.n / 4, 128);
+    const int cap = num_sms() * 24;
     if (grid > cap) grid = cap;
-    launch_k(adam_kernel, dim3(grid), dim3(256), 0, s, k);
+    launch_k(adam_kernel, dim3(grid), dim3(128), 0, s, k);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
   }

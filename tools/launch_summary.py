@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of
-`bench.py`: cut out ONE training step (first kernel of the forward = cast_input_kernel ... adam_kernel), print per-kernel
+`bench.py`: cut out ONE training step (first input kernel of a forward pass ... the kernel before the next forward pass), print per-kernel
 time share and DRAM traffic, and write
   <out>.step.csv   the launches of that step (id, kernel, ns, dram read, dram write)
   <out>.json       per-family totals; bench.py reads "conv" -> roofline.traffic (DRAM bytes per conv launch)
@@ -28,14 +28,17 @@ def main():
         e[rec["Metric Name"]] = float(rec["Metric Value"].replace(",", ""))
     seq = list(launches.values())
     starts = [i for i, e in enumerate(seq) if e["kernel"].startswith(("cast_input_kernel", "im2col_input_kernel"))]
+    # a step runs from the first input kernel of a forward pass to the kernel before the next forward pass's (Adam runs in buckets on
+    # a side stream beside backward, so "the first adam_kernel" is no longer the end of a step); input kernels that follow each
+    # other directly (im2col view + plain cast of the same batch) open the same step
+    heads = [s for j, s in enumerate(starts) if j == 0 or s != starts[j - 1] + 1]
     step = None
-    for s in starts:
-        ends = [i for i in range(s, len(seq)) if seq[i]["kernel"].startswith("adam_kernel")]
-        if ends:
-            step = seq[s:ends[0] + 1]
-            break
-    if step is None:
-        raise SystemExit("no complete step (cast_input_kernel ... adam_kernel) in the capture")
+    if len(heads) >= 3:
+        step = seq[heads[1]:heads[2]]            # the second step of the capture (the first one also pays one-time work)
+    elif len(heads) == 2:
+        step = seq[heads[0]:heads[1]]
+    if step is None or not any(e["kernel"].startswith("adam_kernel") for e in step):
+        raise SystemExit("no complete step (input kernel ... next input kernel, with an adam_kernel inside) in the capture")
     with open(out + ".step.csv", "w") as f:
         w = csv.writer(f)
         w.writerow(["i", "kernel", "grid", "gpu__time_duration.sum [ns]", "dram__bytes_read.sum", "dram__bytes_write.sum"])
