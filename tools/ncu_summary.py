@@ -28,8 +28,11 @@ def main():
             rec = dict(zip(hdr, r))
             print(f"== {path}: {rec.get('Kernel Name', '?')[:90]}")
             for w in WANT:
-                if w in rec and rec[w] != "":
-                    print(f"  {w:<85}{rec[w]:>16} {units[hdr.index(w)]}")
+                # (some metrics carry a section prefix in the raw page, e.g. "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime...")
+                for col in hdr:
+                    if (col == w or col.endswith("." + w)) and rec.get(col, "") != "":
+                        print(f"  {w:<85}{rec[col]:>16} {units[hdr.index(col)]}")
+                        break
 
 
 if __name__ == "__main__":
