@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, PH * PW * U > 4 ? 2 : 4) bn_act_fast_kern
             mx[e] = q == 0 ? f[e] : fmaxf(mx[e], f[e]);
           }
           const uint4 o = pack8(f);
-          st16(k.out0, o0row + (q / PW) * k.out0.sh + (wo * PW + q % PW) * k.out0.sw, o);
+          if (k.n_out > 0) st16(k.out0, o0row + (q / PW) * k.out0.sh + (wo * PW + q % PW) * k.out0.sw, o);      // (0: a stand-alone MaxPooling, only the pooled tensor is written)
           if (k.n_out > 1) st16(k.out1, o1row + (q / PW) * k.out1.sh + (wo * PW + q % PW) * k.out1.sw, o);
         }
         if (WIN > 1 && k.has_pool) st16(k.pooled, prow + wo * k.pooled.sw, pack8(mx));
@@ -289,8 +289,9 @@ static void row_grid(int C, int rows, int Wo, int* cvb, int* rp, dim3* grid) {
 
 PreparedOp* prepare_bn_act_fast(const b2seg_bn_act_desc* d) {
   static const bool disabled = getenv("B2SEG_NO_FAST_STREAM") != nullptr;
-  if (disabled || d->c_valid != 0 || d->x.C % 8 || d->n_out < 1 || d->n_out > 2) return nullptr;
+  if (disabled || d->c_valid != 0 || d->x.C % 8 || d->n_out < 0 || d->n_out > 2) return nullptr;
   const int ph = d->pool_h > 1 ? d->pool_h : 1, pw = d->pool_w > 1 ? d->pool_w : 1;
+  if (d->n_out == 0 && (ph * pw == 1 || d->add.ptr || d->out_stats)) return nullptr;      // no un-pooled output: only as a stand-alone pooling
   if (d->add.ptr || d->out_stats) {
     // fused add / output statistics (MultiResBlock, ResPath): un-pooled, ReLU / LeakyReLU / none, views addressable by (row, w)
     if (ph * pw > 1 || (d->act != B2SEG_ACT_NONE && d->act != B2SEG_ACT_RELU && d->act != B2SEG_ACT_LEAKY)) return nullptr;
@@ -330,7 +331,9 @@ PreparedOp* prepare_bn_act_fast(const b2seg_bn_act_desc* d) {
   auto* L = new BnActFastLaunch();
   BnActF& k = L->k;
   memset(&k, 0, sizeof(k));
-  bool ok = fv_make(d->x, &k.x) && fv_make(d->out[0], &k.out0);
+  bool ok = fv_make(d->x, &k.x);
+  k.out0 = k.x;
+  if (ok && d->n_out > 0) ok = fv_make(d->out[0], &k.out0);
   k.out1 = k.out0;
   if (ok && d->n_out > 1) ok = fv_make(d->out[1], &k.out1);
   k.pooled = k.out0;
