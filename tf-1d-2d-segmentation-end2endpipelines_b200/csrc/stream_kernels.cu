@@ -775,7 +775,10 @@ struct AdamLaunch : PreparedOp {
     k.alpha = (float)((double)d.lr * sqrt(1.0 - pow((double)d.beta2, t)) / (1.0 - pow((double)d.beta1, t)));
     k.b1 = d.beta1; k.b2 = d.beta2; k.eps = d.eps; k.gs = d.grad_scale;
     int grid = grid_for(d.n / 4, 128);
-    const int cap = num_sms() * 24;
+    // blocks per SM: 12 fill an idle SM; beside a persistent convolution CTA only two fit, and more than that make the convolution
+    // kernel that is launched next wait for Adam blocks to retire (B2SEG_ADAM_BLOCKS_PER_SM, A/B knob)
+    static const int bps = getenv("B2SEG_ADAM_BLOCKS_PER_SM") ? atoi(getenv("B2SEG_ADAM_BLOCKS_PER_SM")) : 24;
+    const int cap = num_sms() * (bps > 0 ? bps : 24);
     if (grid > cap) grid = cap;
     launch_k(adam_kernel, dim3(grid), dim3(128), 0, s, k);
     B2_CUDA_OK(cudaGetLastError());
